@@ -1,0 +1,531 @@
+"""oracle/api.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-ends for the two CPU checkers:
+
+* ``PortOracle``  -- oracle/libdjb_oracle.so, the C restatement (oracle/djb_oracle*.c).
+* ``RefOracle``   -- oracle/_ref/libdjbref.so (+ libleanref*.so), the UNMODIFIED reference compiled
+  in place from /root/reference by oracle/Makefile.  Exists only where it was built.
+
+Both expose the same numpy-level methods so a parity test can be written once and pointed at
+either.  Only tests/, bench.py's cpu_baseline / --impl reference legs and
+__graft_entry__.smoke() may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF_ROOT = Path(os.environ.get("DJB_REFERENCE_ROOT", "/root/reference"))
+
+NDF_BECKMANN, NDF_GGX = 0, 1
+F_IDEAL, F_SCHLICK, F_UNPOLARIZED, F_SGD, F_SPLINE = 0, 1, 2, 3, 4
+MERL_CELLS = 90 * 90 * 180
+
+c_f32p = C.c_void_p
+i64 = C.c_int64
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def build_port(quiet=True):
+    subprocess.run(["make", "-C", str(HERE), "port"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def build_ref(quiet=True):
+    """Compile the reference in place; only possible where /root/reference exists."""
+    if not (REF_ROOT / "dj_brdf.h").exists():
+        return False
+    subprocess.run(["make", "-C", str(HERE), "ref", f"REF={REF_ROOT}"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.DEVNULL if quiet else None)
+    return True
+
+
+def port_available():
+    return (HERE / "libdjb_oracle.so").exists()
+
+
+def ref_available():
+    return (HERE / "_ref" / "libdjbref.so").exists()
+
+
+class Fresnel:
+    """kind + data, mirrors djb::fresnel::{ideal,schlick,unpolarized,sgd,spline}."""
+
+    def __init__(self, kind=F_IDEAL, data=()):
+        self.kind = kind
+        self.data = _f32(np.asarray(data, dtype=np.float32).reshape(-1))
+
+    @staticmethod
+    def ideal():
+        return Fresnel(F_IDEAL)
+
+    @staticmethod
+    def schlick(f0):
+        return Fresnel(F_SCHLICK, f0)
+
+    @staticmethod
+    def unpolarized(ior):
+        return Fresnel(F_UNPOLARIZED, ior)
+
+    @staticmethod
+    def spline(points):
+        return Fresnel(F_SPLINE, points)
+
+
+class _OrcFresnel(C.Structure):
+    _fields_ = [("kind", C.c_int), ("v", C.c_float * 6), ("pts", C.c_void_p), ("npts", C.c_int)]
+
+
+class _OrcSource(C.Structure):
+    _fields_ = [("kind", C.c_int), ("ndf", C.c_int), ("F", _OrcFresnel), ("shadow", C.c_int),
+                ("P", C.c_float * 12), ("table", C.c_void_p)]
+
+
+class Source:
+    """Fit input: an analytic microfacet BRDF, a MERL table (3*1458000 float64) or a raw UTIA table."""
+
+    def __init__(self, kind, ndf=NDF_GGX, fresnel=None, shadow=True, params=None, table=None):
+        self.kind, self.ndf, self.fresnel, self.shadow = kind, ndf, fresnel or Fresnel.ideal(), shadow
+        self.params, self.table = params, table
+
+    @staticmethod
+    def microfacet(ndf, fresnel=None, shadow=True):
+        return Source("microfacet", ndf=ndf, fresnel=fresnel, shadow=shadow)
+
+    @staticmethod
+    def merl(table):
+        return Source("merl", table=np.ascontiguousarray(table, dtype=np.float64).reshape(-1))
+
+    @staticmethod
+    def utia(raw_table):
+        return Source("utia", table=np.ascontiguousarray(raw_table, dtype=np.float64).reshape(-1))
+
+
+def write_merl_file(path, table):
+    t = np.ascontiguousarray(table, dtype=np.float64).reshape(-1)
+    assert t.size == 3 * MERL_CELLS
+    with open(path, "wb") as f:
+        f.write(np.array([90, 90, 180], dtype=np.int32).tobytes())
+        f.write(t.tobytes())
+
+
+# --------------------------------------------------------------------------------------------------
+class PortOracle:
+    name = "port"
+
+    def __init__(self):
+        if not port_available():
+            build_port()
+        self.lib = C.CDLL(str(HERE / "libdjb_oracle.so"))
+
+    # -- helpers
+    def _fres(self, fr):
+        fr = fr or Fresnel.ideal()
+        s = _OrcFresnel()
+        s.kind = fr.kind
+        if fr.kind == F_SPLINE:
+            s.pts = fr.data.ctypes.data
+            s.npts = fr.data.size // 3
+        else:
+            for k in range(min(6, fr.data.size)):
+                s.v[k] = fr.data[k]
+        return s
+
+    def params_elliptic(self, a1, a2, phi_a=0.0):
+        out = np.zeros(12, np.float32)
+        self.lib.orc_params_elliptic(C.c_float(a1), C.c_float(a2), C.c_float(phi_a), c_f32p(out.ctypes.data))
+        return out
+
+    def params_pdfparams(self, ax, ay, rho=0.0, tx=0.0, ty=0.0):
+        out = np.zeros(12, np.float32)
+        self.lib.orc_params_pdfparams(C.c_float(ax), C.c_float(ay), C.c_float(rho), C.c_float(tx),
+                                      C.c_float(ty), c_f32p(out.ctypes.data))
+        return out
+
+    def _mf(self, fn, ndf, fresnel, shadow, params, a, b, outs, nthreads):
+        a, b = _f32(a), _f32(b)
+        n = b.shape[0]
+        fs = self._fres(fresnel)
+        p = None if params is None else _f32(params)
+        getattr(self.lib, fn)(C.c_int(ndf), C.byref(fs), C.c_int(int(shadow)), c_f32p(_ptr(p)),
+                              c_f32p(a.ctypes.data), c_f32p(b.ctypes.data), i64(n),
+                              *[c_f32p(o.ctypes.data) for o in outs], C.c_int(nthreads))
+
+    def eval(self, ndf, params, wi, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty((len(wo), 3), np.float32)
+        self._mf("orc_microfacet_eval", ndf, fresnel, shadow, params, wi, wo, [out], nthreads)
+        return out
+
+    def evalp(self, ndf, params, wi, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty((len(wo), 3), np.float32)
+        self._mf("orc_microfacet_evalp", ndf, fresnel, shadow, params, wi, wo, [out], nthreads)
+        return out
+
+    def pdf(self, ndf, params, wi, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty(len(wo), np.float32)
+        self._mf("orc_microfacet_pdf", ndf, fresnel, shadow, params, wi, wo, [out], nthreads)
+        return out
+
+    def sample(self, ndf, params, u, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty((len(wo), 3), np.float32)
+        self._mf("orc_microfacet_sample", ndf, fresnel, shadow, params, u, wo, [out], nthreads)
+        return out
+
+    def evalp_is(self, ndf, params, u, wo, fresnel=None, shadow=True, nthreads=1):
+        w = np.empty((len(wo), 3), np.float32)
+        i = np.empty((len(wo), 3), np.float32)
+        pdf = np.empty(len(wo), np.float32)
+        self._mf("orc_microfacet_evalp_is", ndf, fresnel, shadow, params, u, wo, [w, i, pdf], nthreads)
+        return w, i, pdf
+
+    def io_to_hd(self, wi, wo):
+        wi, wo = _f32(wi), _f32(wo)
+        h, d = np.empty_like(wi), np.empty_like(wi)
+        self.lib.orc_io_to_hd(c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data), i64(len(wi)),
+                              c_f32p(h.ctypes.data), c_f32p(d.ctypes.data))
+        return h, d
+
+    def hd_to_io(self, h, d):
+        h, d = _f32(h), _f32(d)
+        wi, wo = np.empty_like(h), np.empty_like(h)
+        self.lib.orc_hd_to_io(c_f32p(h.ctypes.data), c_f32p(d.ctypes.data), i64(len(h)),
+                              c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data))
+        return wi, wo
+
+    def merl_index(self, wi, wo, nthreads=1):
+        wi, wo = _f32(wi), _f32(wo)
+        idx = np.empty(len(wi), np.int32)
+        self.lib.orc_merl_index(c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data), i64(len(wi)),
+                                C.c_void_p(idx.ctypes.data), C.c_int(nthreads))
+        return idx
+
+    def merl_eval(self, table, wi, wo, nthreads=1):
+        table = np.ascontiguousarray(table, dtype=np.float64).reshape(-1)
+        assert table.size == 3 * MERL_CELLS
+        wi, wo = _f32(wi), _f32(wo)
+        out = np.empty((len(wi), 3), np.float32)
+        self.lib.orc_merl_eval(C.c_void_p(table.ctypes.data), c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data),
+                               i64(len(wi)), c_f32p(out.ctypes.data), C.c_int(nthreads))
+        return out
+
+    def utia_eval(self, raw_table, wi, wo, nthreads=1):
+        t = np.array(raw_table, dtype=np.float64).reshape(-1)
+        self.lib.orc_utia_normalize(C.c_void_p(t.ctypes.data))
+        wi, wo = _f32(wi), _f32(wo)
+        out = np.empty((len(wi), 3), np.float32)
+        self.lib.orc_utia_eval(C.c_void_p(t.ctypes.data), c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data),
+                               i64(len(wi)), c_f32p(out.ctypes.data), C.c_int(nthreads))
+        return out
+
+    def lrep_to_params(self, E5):
+        E5 = _f32(E5).reshape(-1, 5)
+        out = np.empty((len(E5), 12), np.float32)
+        self.lib.orc_lrep_to_params(c_f32p(E5.ctypes.data), i64(len(E5)), c_f32p(out.ctypes.data))
+        return out
+
+    def params_to_lrep(self, params):
+        params = _f32(params).reshape(-1, 12)
+        out = np.empty((len(params), 5), np.float32)
+        self.lib.orc_params_to_lrep(c_f32p(params.ctypes.data), i64(len(params)), c_f32p(out.ctypes.data))
+        return out
+
+    def nmap2leanmap(self, nmap_planar, base_roughness=1e-5, bias=0.0):
+        nmap = np.ascontiguousarray(nmap_planar, dtype=np.uint8)
+        _, h, w = nmap.shape
+        l1 = np.empty((4, h, w), np.float32)
+        l2 = np.empty((4, h, w), np.float32)
+        self.lib.orc_nmap2leanmap(C.c_void_p(nmap.ctypes.data), C.c_int(w), C.c_int(h),
+                                  C.c_float(base_roughness), C.c_float(bias),
+                                  c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data))
+        return l1, l2
+
+    # -- fits
+    def _source(self, src):
+        s = _OrcSource()
+        keep = []
+        if src.kind == "microfacet":
+            s.kind, s.ndf, s.shadow = 0, src.ndf, int(src.shadow)
+            s.F = self._fres(src.fresnel)
+            keep.append(src.fresnel)
+            p = self.params_elliptic(1.0, 1.0, 0.0) if src.params is None else _f32(src.params)
+            for k in range(12):
+                s.P[k] = p[k]
+        elif src.kind == "merl":
+            s.kind, s.table = 1, src.table.ctypes.data
+        elif src.kind == "utia":
+            t = np.array(src.table, dtype=np.float64)
+            self.lib.orc_utia_normalize(C.c_void_p(t.ctypes.data))
+            keep.append(t)
+            s.kind, s.table = 2, t.ctypes.data
+        else:
+            raise ValueError(src.kind)
+        return s, keep
+
+    def fit_tabular(self, src, res=90, shadow=True, iterations=4):
+        s, keep = self._source(src)
+        p22, sigma, cdf, qf = (np.zeros(res, np.float32) for _ in range(4))
+        fres = np.zeros((res, 3), np.float32)
+        alpha = np.zeros(2, np.float32)
+        self.lib.orc_fit_tabular(C.byref(s), C.c_int(res), C.c_int(int(shadow)), C.c_int(iterations),
+                                 *[c_f32p(a.ctypes.data) for a in (p22, sigma, cdf, qf, fres, alpha)])
+        return dict(p22=p22, sigma=sigma, cdf=cdf, qf=qf, fresnel=fres, alpha=alpha)
+
+    def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=8):
+        s, keep = self._source(src)
+        n = elev_res * azim_res
+        p22, sigma = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        fres = np.zeros((elev_res, 3), np.float32)
+        b5, g5 = np.zeros(5, np.float32), np.zeros(5, np.float32)
+        self.lib.orc_fit_tabular_anisotropic(C.byref(s), C.c_int(elev_res), C.c_int(azim_res),
+                                             C.c_int(int(shadow)), C.c_int(iterations),
+                                             *[c_f32p(a.ctypes.data) for a in (p22, sigma, fres, b5, g5)],
+                                             C.c_int(nthreads))
+        return dict(p22=p22, sigma=sigma, fresnel=fres, beckmann=b5, ggx=g5)
+
+
+# --------------------------------------------------------------------------------------------------
+class RefOracle:
+    """The unmodified reference, through oracle/ref_harness.cpp."""
+    name = "reference"
+
+    def __init__(self):
+        if not ref_available():
+            raise RuntimeError("oracle/_ref/libdjbref.so not built (needs /root/reference; run `make -C oracle ref`)")
+        L = self.lib = C.CDLL(str(HERE / "_ref" / "libdjbref.so"))
+        for fn in ("ref_microfacet_create", "ref_merl_open", "ref_utia_open", "ref_sgd_create",
+                   "ref_abc_create", "ref_tabular_create", "ref_tabular_anisotropic_create"):
+            getattr(L, fn).restype = C.c_void_p
+        self._lean = {}
+        self._tmp = tempfile.TemporaryDirectory(prefix="djbref_")
+        self._handles = []
+        assert L.ref_sizeof_params() == 48
+
+    def _lean_lib(self, biased):
+        name = "libleanref_biased.so" if biased else "libleanref.so"
+        if name not in self._lean:
+            self._lean[name] = C.CDLL(str(HERE / "_ref" / name))
+        return self._lean[name]
+
+    def params_elliptic(self, a1, a2, phi_a=0.0):
+        out = np.zeros(12, np.float32)
+        self.lib.ref_params_elliptic(C.c_float(a1), C.c_float(a2), C.c_float(phi_a), c_f32p(out.ctypes.data))
+        return out
+
+    def params_pdfparams(self, ax, ay, rho=0.0, tx=0.0, ty=0.0):
+        out = np.zeros(12, np.float32)
+        self.lib.ref_params_pdfparams(C.c_float(ax), C.c_float(ay), C.c_float(rho), C.c_float(tx),
+                                      C.c_float(ty), c_f32p(out.ctypes.data))
+        return out
+
+    def microfacet(self, ndf, fresnel=None, shadow=True):
+        fr = fresnel or Fresnel.ideal()
+        h = self.lib.ref_microfacet_create(C.c_int(ndf), C.c_int(fr.kind), c_f32p(_ptr(fr.data) if fr.data.size else None),
+                                           C.c_int(fr.data.size), C.c_int(int(shadow)))
+        assert h
+        return C.c_void_p(h)
+
+    def destroy(self, h):
+        self.lib.ref_brdf_destroy(h)
+
+    def _q(self, fn, h, params, a, b, outs, nthreads):
+        a, b = _f32(a), _f32(b)
+        p = None if params is None else _f32(params)
+        getattr(self.lib, fn)(h, c_f32p(_ptr(p)), c_f32p(a.ctypes.data), c_f32p(b.ctypes.data), i64(len(b)),
+                              *[c_f32p(o.ctypes.data) for o in outs], C.c_int(nthreads))
+
+    # generic-handle queries
+    def brdf_eval(self, h, params, wi, wo, nthreads=1):
+        out = np.empty((len(wo), 3), np.float32)
+        self._q("ref_brdf_eval", h, params, wi, wo, [out], nthreads)
+        return out
+
+    def _with_mf(self, ndf, fresnel, shadow, fn):
+        h = self.microfacet(ndf, fresnel, shadow)
+        try:
+            return fn(h)
+        finally:
+            self.destroy(h)
+
+    def eval(self, ndf, params, wi, wo, fresnel=None, shadow=True, nthreads=1):
+        return self._with_mf(ndf, fresnel, shadow, lambda h: self.brdf_eval(h, params, wi, wo, nthreads))
+
+    def evalp(self, ndf, params, wi, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty((len(wo), 3), np.float32)
+        self._with_mf(ndf, fresnel, shadow, lambda h: self._q("ref_brdf_evalp", h, params, wi, wo, [out], nthreads))
+        return out
+
+    def pdf(self, ndf, params, wi, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty(len(wo), np.float32)
+        self._with_mf(ndf, fresnel, shadow, lambda h: self._q("ref_brdf_pdf", h, params, wi, wo, [out], nthreads))
+        return out
+
+    def sample(self, ndf, params, u, wo, fresnel=None, shadow=True, nthreads=1):
+        out = np.empty((len(wo), 3), np.float32)
+        self._with_mf(ndf, fresnel, shadow, lambda h: self._q("ref_brdf_sample", h, params, u, wo, [out], nthreads))
+        return out
+
+    def evalp_is(self, ndf, params, u, wo, fresnel=None, shadow=True, nthreads=1):
+        w = np.empty((len(wo), 3), np.float32)
+        i = np.empty((len(wo), 3), np.float32)
+        pdf = np.empty(len(wo), np.float32)
+        self._with_mf(ndf, fresnel, shadow,
+                      lambda h: self._q("ref_brdf_evalp_is", h, params, u, wo, [w, i, pdf], nthreads))
+        return w, i, pdf
+
+    def io_to_hd(self, wi, wo):
+        wi, wo = _f32(wi), _f32(wo)
+        h, d = np.empty_like(wi), np.empty_like(wi)
+        self.lib.ref_io_to_hd(c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data), i64(len(wi)),
+                              c_f32p(h.ctypes.data), c_f32p(d.ctypes.data))
+        return h, d
+
+    def hd_to_io(self, h, d):
+        h, d = _f32(h), _f32(d)
+        wi, wo = np.empty_like(h), np.empty_like(h)
+        self.lib.ref_hd_to_io(c_f32p(h.ctypes.data), c_f32p(d.ctypes.data), i64(len(h)),
+                              c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data))
+        return wi, wo
+
+    def merl_index(self, wi, wo, nthreads=1):
+        wi, wo = _f32(wi), _f32(wo)
+        idx = np.empty(len(wi), np.int32)
+        self.lib.ref_merl_index(c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data), i64(len(wi)),
+                                C.c_void_p(idx.ctypes.data), C.c_int(nthreads))
+        return idx
+
+    def merl_open(self, path):
+        h = self.lib.ref_merl_open(str(path).encode())
+        assert h, path
+        return C.c_void_p(h)
+
+    def merl_from_table(self, table):
+        path = os.path.join(self._tmp.name, f"merl_{len(os.listdir(self._tmp.name))}.binary")
+        write_merl_file(path, table)
+        h = self.merl_open(path)
+        os.unlink(path)  # the reference copied the whole file into memory (dj_brdf.h:979-980)
+        return h
+
+    def utia_from_table(self, raw_table):
+        path = os.path.join(self._tmp.name, f"utia_{len(os.listdir(self._tmp.name))}.bin")
+        np.ascontiguousarray(raw_table, dtype=np.float64).tofile(path)
+        h = self.lib.ref_utia_open(path.encode())
+        assert h
+        os.unlink(path)
+        return C.c_void_p(h)
+
+    def merl_eval(self, table, wi, wo, nthreads=1):
+        h = self.merl_from_table(table)
+        try:
+            return self.brdf_eval(h, None, wi, wo, nthreads)
+        finally:
+            self.destroy(h)
+
+    def utia_eval(self, raw_table, wi, wo, nthreads=1):
+        h = self.utia_from_table(raw_table)
+        try:
+            return self.brdf_eval(h, None, wi, wo, nthreads)
+        finally:
+            self.destroy(h)
+
+    def lrep_to_params(self, E5):
+        E5 = _f32(E5).reshape(-1, 5)
+        out = np.empty((len(E5), 12), np.float32)
+        self.lib.ref_lrep_to_params(c_f32p(E5.ctypes.data), i64(len(E5)), c_f32p(out.ctypes.data))
+        return out
+
+    def params_to_lrep(self, params):
+        params = _f32(params).reshape(-1, 12)
+        out = np.empty((len(params), 5), np.float32)
+        self.lib.ref_params_to_lrep(c_f32p(params.ctypes.data), i64(len(params)), c_f32p(out.ctypes.data))
+        return out
+
+    def nmap2leanmap(self, nmap_planar, base_roughness=1e-5, bias=0.0, run_check=False):
+        assert bias in (0.0, 25.0)
+        L = self._lean_lib(bias != 0.0)
+        nmap = np.ascontiguousarray(nmap_planar, dtype=np.uint8)
+        _, h, w = nmap.shape
+        l1 = np.empty((4, h, w), np.float32)
+        l2 = np.empty((4, h, w), np.float32)
+        L.ref_nmap2leanmap(C.c_void_p(nmap.ctypes.data), C.c_int(w), C.c_int(h), C.c_float(base_roughness),
+                           c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data), C.c_int(int(run_check)))
+        return l1, l2
+
+    # -- fits
+    def _source_handle(self, src):
+        if src.kind == "microfacet":
+            return self.microfacet(src.ndf, src.fresnel, src.shadow)
+        if src.kind == "merl":
+            return self.merl_from_table(src.table)
+        if src.kind == "utia":
+            return self.utia_from_table(src.table)
+        raise ValueError(src.kind)
+
+    def fit_tabular(self, src, res=90, shadow=True, iterations=4):
+        assert iterations == 4, "the reference hard-codes 4 power iterations (dj_brdf.h:2518)"
+        h = self._source_handle(src)
+        t = C.c_void_p(self.lib.ref_tabular_create(h, C.c_int(res), C.c_int(int(shadow))))
+        p22, sigma, cdf, qf = (np.zeros(res, np.float32) for _ in range(4))
+        fres = np.zeros((res, 3), np.float32)
+        alpha = np.zeros(2, np.float32)
+        n = self.lib.ref_tabular_get(t, *[c_f32p(a.ctypes.data) for a in (p22, sigma, cdf, qf, fres, alpha)])
+        assert n == res, n
+        self.destroy(t)
+        self.destroy(h)
+        return dict(p22=p22, sigma=sigma, cdf=cdf, qf=qf, fresnel=fres, alpha=alpha)
+
+    def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=1):
+        assert iterations == 4
+        h = self._source_handle(src)
+        t = C.c_void_p(self.lib.ref_tabular_anisotropic_create(h, C.c_int(elev_res), C.c_int(azim_res),
+                                                               C.c_int(int(shadow))))
+        n = elev_res * azim_res
+        p22, sigma = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        fres = np.zeros((elev_res, 3), np.float32)
+        b5, g5 = np.zeros(5, np.float32), np.zeros(5, np.float32)
+        got = self.lib.ref_tabular_anisotropic_get(t, *[c_f32p(a.ctypes.data) for a in (p22, sigma, fres, b5, g5)])
+        assert got == n, got
+        self.destroy(t)
+        self.destroy(h)
+        return dict(p22=p22, sigma=sigma, fresnel=fres, beckmann=b5, ggx=g5)
+
+
+# --------------------------------------------------------------------------------------------------
+# Seeded synthetic inputs -- generated on the host with numpy so that the
+# checker and the CUDA path see bit-identical floats.
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def uniforms(n, stream, seed=0x9E3779B97F4A7C15):
+    """n float32 uniforms in [0,1) from a counter-based splitmix64 stream."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64) * np.uint64(8) + np.uint64(stream)
+        bits = _splitmix64(idx ^ np.uint64(seed))
+    return ((bits >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / (1 << 24))).astype(np.float32)
+
+
+def directions(n, stream, zmin=0.001):
+    """Upper-hemisphere unit vectors: z = 1 - (1-zmin) u1, phi = 2 pi u2 (float32 AoS [n,3])."""
+    u1 = uniforms(n, stream).astype(np.float64)
+    u2 = uniforms(n, stream + 1).astype(np.float64)
+    z = 1.0 - (1.0 - zmin) * u1
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    phi = 2.0 * np.pi * u2
+    return np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1).astype(np.float32)

@@ -1,0 +1,112 @@
+/* oracle/djb_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C11) of the reference's numeric hot paths, written from the
+ * behaviour of /root/reference/dj_brdf.h and utils/nmap2leanmap*.cpp.  Every function cites
+ * the reference lines it restates.  All float/double rounding points of the *pinned* reference
+ * build (SURVEY.md section 0 finding 2 and appendix A) are made explicit with casts:
+ * inside `namespace djb` the unqualified libm calls bind to the C double functions, double
+ * literals promote their sub-expression to double, and nothing is contracted into FMAs.
+ *
+ * Pinning: tests/test_oracle_vs_reference.py checks this port bit-for-bit against
+ * oracle/_ref/libdjbref.so (the unmodified reference compiled in place) whenever that library is
+ * present, and against the committed vectors in tests/golden/ (generated from the reference by
+ * tests/golden/make_golden.py) everywhere else.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (dj_brdf_b200/, include/) never does.
+ */
+#ifndef DJB_ORACLE_H
+#define DJB_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* layout-identical to djb::microfacet::params (dj_brdf.h:238-242), 48 bytes */
+typedef struct orc_params {
+	float n[3];          /* mean normal */
+	float a1, a2, phi_a; /* ellipse */
+	float ax, ay;        /* scales */
+	float rho, srho;     /* correlation, sqrt(1 - rho^2) */
+	float tx, ty;        /* location */
+} orc_params;
+
+enum { ORC_NDF_BECKMANN = 0, ORC_NDF_GGX = 1 };
+enum { ORC_F_IDEAL = 0, ORC_F_SCHLICK = 1, ORC_F_UNPOLARIZED = 2, ORC_F_SGD = 3, ORC_F_SPLINE = 4 };
+
+typedef struct orc_fresnel {
+	int kind;
+	float v[6];       /* schlick: f0[3]; unpolarized: ior[3]; sgd: f0[3], f1[3] */
+	const float *pts; /* spline: npts * 3 floats */
+	int npts;
+} orc_fresnel;
+
+/* params factories (dj_brdf.h:1355-1474) */
+void orc_params_elliptic(float a1, float a2, float phi_a, orc_params *out);
+void orc_params_pdfparams(float ax, float ay, float rho, float tx, float ty, orc_params *out);
+
+/* microfacet batch queries (dj_brdf.h:1529-1765); params==NULL => params::standard() */
+void orc_microfacet_eval(int ndf, const orc_fresnel *F, int shadow, const orc_params *P,
+                         const float *wi, const float *wo, int64_t n, float *out3, int nthreads);
+void orc_microfacet_evalp(int ndf, const orc_fresnel *F, int shadow, const orc_params *P,
+                          const float *wi, const float *wo, int64_t n, float *out3, int nthreads);
+void orc_microfacet_pdf(int ndf, const orc_fresnel *F, int shadow, const orc_params *P,
+                        const float *wi, const float *wo, int64_t n, float *out1, int nthreads);
+void orc_microfacet_sample(int ndf, const orc_fresnel *F, int shadow, const orc_params *P,
+                           const float *u2, const float *wo, int64_t n, float *out3, int nthreads);
+void orc_microfacet_evalp_is(int ndf, const orc_fresnel *F, int shadow, const orc_params *P,
+                             const float *u2, const float *wo, int64_t n,
+                             float *out_w3, float *out_i3, float *out_pdf, int nthreads);
+
+/* Rusinkiewicz transforms (dj_brdf.h:771-793) */
+void orc_io_to_hd(const float *wi, const float *wo, int64_t n, float *h3, float *d3);
+void orc_hd_to_io(const float *h3, const float *d3, int64_t n, float *wi, float *wo);
+
+/* MERL (dj_brdf.h:906-1024): table = 3 planes of 90*90*180 doubles as in the .binary file */
+void orc_merl_index(const float *wi, const float *wo, int64_t n, int32_t *idx, int nthreads);
+void orc_merl_eval(const double *table, const float *wi, const float *wo, int64_t n, float *out3,
+                   int nthreads);
+
+/* UTIA (dj_brdf.h:1039-1177): table = 3*6*48*6*48 doubles already normalised by orc_utia_normalize */
+void orc_utia_normalize(double *table);
+void orc_utia_eval(const double *table, const float *wi, const float *wo, int64_t n, float *out3,
+                   int nthreads);
+
+/* LEAN (dj_brdf.h:1965-1990; utils/nmap2leanmap.cpp:18-54; nmap2leanmap_biased.cpp:23-63) */
+void orc_lrep_to_params(const float *E5, int64_t n, orc_params *out);
+void orc_params_to_lrep(const orc_params *p, int64_t n, float *E5);
+void orc_nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float base_roughness, float bias,
+                      float *lean1_planar_rgba, float *lean2_planar_rgba);
+
+/* ---- fits: djb_oracle_fit.c ------------------------------------------------------------- */
+/* generic BRDF handle used as the fit input */
+enum { ORC_SRC_MICROFACET = 0, ORC_SRC_MERL = 1, ORC_SRC_UTIA = 2 };
+typedef struct orc_source {
+	int kind;
+	/* microfacet */
+	int ndf;
+	orc_fresnel F;
+	int shadow;
+	orc_params P; /* user_param is NULL in the reference's fit calls => P must be standard() */
+	/* merl / utia */
+	const double *table;
+} orc_source;
+void orc_source_eval(const orc_source *src, const float *wi, const float *wo, float *out3);
+
+/* isotropic fit: tabular::tabular + fit_*_parameters (dj_brdf.h:2215-2236, 3133-3184).
+ * iterations = 4 reproduces the reference (dj_brdf.h:2518).
+ * outputs: p22[res], sigma[res], cdf[res], qf[res], fresnel[3*res], alpha[2] = beckmann, ggx */
+void orc_fit_tabular(const orc_source *src, int res, int shadow, int iterations,
+                     float *p22, float *sigma, float *cdf, float *qf, float *fresnel3, float *alpha2);
+
+/* anisotropic fit: tabular_anisotropic (dj_brdf.h:2238-2273, 3186-3307), eval tables only.
+ * outputs: p22[er*ar], sigma[er*ar], fresnel[3*er], beckmann5/ggx5 = ax, ay, rho, tx, ty */
+void orc_fit_tabular_anisotropic(const orc_source *src, int elev_res, int azim_res, int shadow,
+                                 int iterations, float *p22, float *sigma, float *fresnel3,
+                                 float *beckmann5, float *ggx5, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
