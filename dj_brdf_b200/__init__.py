@@ -1,0 +1,15 @@
+"""dj_brdf_b200 -- B200-native (sm_100a) microfacet BRDF evaluation and fitting engine.
+
+Drop-in for the numeric hot paths of jdupuy/dj_brdf: batched GGX/Beckmann eval / pdf / sample /
+evalp_is, MERL and UTIA table lookups, the power-iteration fits, and normal-map -> LEAN-map
+conversion.  The product is ``libdjb200.so`` (hand-written CUDA behind the C-ABI declared in
+``include/djb200.h``); this package is the Python host mirror of the reference's ``djb::`` interface.
+There is no CPU fallback.
+"""
+from .capi import DjbError, device_count, kernel_launch_count, load  # noqa: F401
+from .brdf import (beckmann, brdf, fresnel, ggx, leanmap_to_params, merl, microfacet, nmap2leanmap,  # noqa: F401
+                   params, tabular, tabular_anisotropic, utia)
+
+__all__ = ["DjbError", "device_count", "kernel_launch_count", "load", "beckmann", "brdf", "fresnel", "ggx",
+           "leanmap_to_params", "merl", "microfacet", "nmap2leanmap", "params", "tabular", "tabular_anisotropic",
+           "utia"]

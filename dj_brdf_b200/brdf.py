@@ -1,0 +1,518 @@
+"""Host-side mirror of the reference's ``djb::`` interface for the accelerated paths, on top of the
+C-ABI (``libdjb200.so``).  Same names, argument order and error behaviour as dj_brdf.h, but every
+query is batched: ``i``/``o`` are ``[n, 3]`` float32 arrays (numpy = host memory, torch CUDA tensor
+= device memory, results come back in the same space).
+
+    ggx = djb.ggx(djb.fresnel.schlick([1.0, 0.8, 0.6]))
+    fr  = ggx.eval(i, o, djb.params.elliptic(0.1, 0.4, 0.7))         # dj_brdf.h:1551
+    fr16 = ggx.eval(i, o, [p0, ..., p15])                             # 16 materials x n pairs
+
+Direction convention as in the reference (dj_brdf.h:23-26): i -> light, o -> viewer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import Buf, DjbError, check
+
+
+# --------------------------------------------------------------------------------------------------
+class fresnel:
+    """djb::fresnel::* (dj_brdf.h:149-207)."""
+
+    class impl:
+        kind = capi.FRESNEL_IDEAL
+
+        def __init__(self, data=(), points=None):
+            self._v = np.zeros(6, np.float32)
+            d = np.asarray(data, np.float32).reshape(-1)
+            self._v[:d.size] = d
+            self._points = None if points is None else np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+
+        def _c(self):
+            f = capi.Fresnel()
+            f.kind = self.kind
+            for k in range(6):
+                f.v[k] = float(self._v[k])
+            if self._points is not None:
+                f.points = self._points.ctypes.data
+                f.n_points = len(self._points)
+            return f
+
+        def copy(self):
+            c = type(self).__new__(type(self))
+            c._v = self._v.copy()
+            c._points = None if self._points is None else self._points.copy()
+            return c
+
+    class ideal(impl):
+        kind = capi.FRESNEL_IDEAL
+
+        def __init__(self):
+            super().__init__()
+
+    class schlick(impl):
+        kind = capi.FRESNEL_SCHLICK
+
+        def __init__(self, f0):
+            super().__init__(np.broadcast_to(np.asarray(f0, np.float32), (3,)))
+
+    class unpolarized(impl):
+        kind = capi.FRESNEL_UNPOLARIZED
+
+        def __init__(self, ior):
+            super().__init__(np.broadcast_to(np.asarray(ior, np.float32), (3,)))
+
+    class sgd(impl):
+        kind = capi.FRESNEL_SGD
+
+        def __init__(self, f0, f1):
+            super().__init__(np.concatenate([np.asarray(f0, np.float32), np.asarray(f1, np.float32)]))
+
+    class spline(impl):
+        kind = capi.FRESNEL_SPLINE
+
+        def __init__(self, points):
+            super().__init__((), points)
+
+        def get_points(self):
+            return self._points
+
+    @staticmethod
+    def ior_to_f0(ior):  # dj_brdf.h:1255-1262
+        ior = np.asarray(ior, np.float32)
+        tmp = ((ior.astype(np.float64) - 1.0) / (ior.astype(np.float64) + 1.0)).astype(np.float32)
+        return tmp * tmp
+
+
+# --------------------------------------------------------------------------------------------------
+class params:
+    """djb::microfacet::params (dj_brdf.h:213-243): a 48-byte block, here a float32[12] ndarray with
+    fields n[3], a1, a2, phi_a, ax, ay, rho, sqrt(1-rho^2), tx_n, ty_n."""
+
+    @staticmethod
+    def _make(fn, *args):
+        out = np.zeros(12, np.float32)
+        check(getattr(capi.load(), fn)(*[C.c_float(a) for a in args], C.c_void_p(out.ctypes.data)))
+        return out
+
+    @staticmethod
+    def standard():
+        return params._make("djb200_params_standard")
+
+    @staticmethod
+    def isotropic(a):
+        return params._make("djb200_params_isotropic", a)
+
+    @staticmethod
+    def elliptic(a1, a2, phi_a=0.0):
+        return params._make("djb200_params_elliptic", a1, a2, phi_a)
+
+    @staticmethod
+    def pdfparams(ax, ay, rho=0.0, tx_n=0.0, ty_n=0.0):
+        return params._make("djb200_params_pdfparams", ax, ay, rho, tx_n, ty_n)
+
+    @staticmethod
+    def get_ellipse(p):
+        return float(p[3]), float(p[4]), float(p[5])
+
+    @staticmethod
+    def get_pdfparams(p):
+        return float(p[6]), float(p[7]), float(p[8]), float(p[10]), float(p[11])
+
+
+def _n_pairs(x, width):
+    n = Buf(x, np.float32).n
+    if n % width:
+        raise ValueError(f"array size {n} is not a multiple of {width}")
+    return n // width
+
+
+# --------------------------------------------------------------------------------------------------
+class brdf:
+    """djb::brdf (dj_brdf.h:74-109), batched."""
+
+    def eval(self, i, o, user_param=None):
+        raise NotImplementedError
+
+    def evalp(self, i, o, user_param=None):
+        # brdf::evalp: eval * cos(theta_i), dj_brdf.h:803-806
+        fr = self.eval(i, o, user_param)
+        iz = i[:, 2:3] if not capi._is_torch(i) else i[:, 2:3]
+        return fr * iz
+
+    @staticmethod
+    def io_to_hd(i, o):
+        bi, bo = Buf(i, np.float32), Buf(o, np.float32)
+        mem = capi.same_space(bi, bo)
+        n = bi.n // 3
+        h = capi.empty_like_space(bi.keep, (n, 3), np.float32)
+        d = capi.empty_like_space(bi.keep, (n, 3), np.float32)
+        bh, bd = Buf(h, np.float32, True), Buf(d, np.float32, True)
+        check(capi.load().djb200_io_to_hd(bi.ptr, bo.ptr, C.c_int64(n), bh.ptr, bd.ptr, mem,
+                                          capi.current_stream_ptr(mem)))
+        return h, d
+
+    @staticmethod
+    def hd_to_io(h, d):
+        bh, bd = Buf(h, np.float32), Buf(d, np.float32)
+        mem = capi.same_space(bh, bd)
+        n = bh.n // 3
+        i = capi.empty_like_space(bh.keep, (n, 3), np.float32)
+        o = capi.empty_like_space(bh.keep, (n, 3), np.float32)
+        bi, bo = Buf(i, np.float32, True), Buf(o, np.float32, True)
+        check(capi.load().djb200_hd_to_io(bh.ptr, bd.ptr, C.c_int64(n), bi.ptr, bo.ptr, mem,
+                                          capi.current_stream_ptr(mem)))
+        return i, o
+
+
+class microfacet(brdf):
+    """djb::microfacet (dj_brdf.h:210-298) restricted to the radial families the kernels implement."""
+    _ndf = None
+
+    def __init__(self, fresnel_impl=None, shadow=True):
+        self.m_fresnel = (fresnel_impl or fresnel.ideal()).copy()  # deep copy, dj_brdf.h:1514
+        self.m_shadow = bool(shadow)
+
+    # mutators / accessors, dj_brdf.h:278-282
+    def set_shadow(self, shadow):
+        self.m_shadow = bool(shadow)
+
+    def set_fresnel(self, f):
+        self.m_fresnel = f.copy()
+
+    def get_shadow(self):
+        return self.m_shadow
+
+    def get_fresnel(self):
+        return self.m_fresnel
+
+    def supports_smith_vndf_sampling(self):
+        return True
+
+    def _desc(self):
+        m = capi.Microfacet()
+        m.ndf = self._ndf
+        m.shadow = int(self.m_shadow)
+        m.fresnel = self.m_fresnel._c()
+        return m
+
+    def _params(self, user_param, n, mem):
+        """-> (pointer, n_params, layout, keepalive, broadcast_count or None)"""
+        if user_param is None:
+            return None, 0, capi.PARAMS_BROADCAST, None, None
+        if capi._is_torch(user_param):  # per-pair params living on the device
+            b = Buf(user_param, np.float32)
+            if b.n != 12 * n:
+                raise ValueError("device params must be [n, 12] (PER_PAIR layout)")
+            return b.ptr, n, capi.PARAMS_PER_PAIR, b, None
+        p = np.ascontiguousarray(user_param, np.float32)
+        if p.ndim == 1:
+            p = p.reshape(1, 12)
+            return C.c_void_p(p.ctypes.data), 1, capi.PARAMS_BROADCAST, p, None
+        return C.c_void_p(p.ctypes.data), len(p), capi.PARAMS_BROADCAST, p, len(p)
+
+    def _query(self, fn, a, b, a_width, out_widths, user_param, per_pair=False):
+        ba, bb = Buf(a, np.float32), Buf(b, np.float32)
+        mem = capi.same_space(ba, bb)
+        n = bb.n // 3
+        if ba.n != n * a_width:
+            raise ValueError("input arrays disagree on the number of pairs")
+        if per_pair and user_param is not None and not capi._is_torch(user_param):
+            p = np.ascontiguousarray(user_param, np.float32).reshape(-1, 12)
+            if len(p) != n:
+                raise ValueError("per_pair params must be [n, 12]")
+            if mem != capi.MEM_HOST:
+                raise ValueError("host per-pair params need host direction arrays")
+            pptr, npar, layout, keep, M = C.c_void_p(p.ctypes.data), n, capi.PARAMS_PER_PAIR, p, None
+        else:
+            pptr, npar, layout, keep, M = self._params(user_param, n, mem)
+        outs = []
+        for w in out_widths:
+            shape = ((n, w) if w > 1 else (n,)) if M is None else ((M, n, w) if w > 1 else (M, n))
+            outs.append(capi.empty_like_space(bb.keep, shape, np.float32))
+        bouts = [Buf(x, np.float32, True) for x in outs]
+        desc = self._desc()
+        check(getattr(capi.load(), fn)(C.byref(desc), pptr, C.c_int64(npar), C.c_int(layout), ba.ptr, bb.ptr,
+                                       C.c_int64(n), *[x.ptr for x in bouts], C.c_int(mem),
+                                       capi.current_stream_ptr(mem)))
+        return outs
+
+    # BRDF interface (dj_brdf.h:247-256).  user_param: None (standard), one params block, a list /
+    # [M,12] array of blocks (every pair under every block -> leading dim M), or with
+    # per_pair=True an [n,12] array (pair k under block k).
+    def eval(self, i, o, user_param=None, per_pair=False):
+        return self._query("djb200_microfacet_eval", i, o, 3, [3], user_param, per_pair)[0]
+
+    def evalp(self, i, o, user_param=None, per_pair=False):
+        return self._query("djb200_microfacet_evalp", i, o, 3, [3], user_param, per_pair)[0]
+
+    def pdf(self, i, o, user_param=None, per_pair=False):
+        return self._query("djb200_microfacet_pdf", i, o, 3, [1], user_param, per_pair)[0]
+
+    def sample(self, u, o, user_param=None, per_pair=False):
+        """u: [n, 2] uniforms (u1, u2) -- microfacet::sample(u1, u2, o, user_param)."""
+        return self._query("djb200_microfacet_sample", u, o, 2, [3], user_param, per_pair)[0]
+
+    def evalp_is(self, u, o, user_param=None, per_pair=False):
+        """-> (weight rgb, i, pdf) -- microfacet::evalp_is(u1, u2, o, &i, &pdf, user_param)."""
+        return tuple(self._query("djb200_microfacet_evalp_is", u, o, 2, [3, 3, 1], user_param, per_pair))
+
+
+class ggx(microfacet):
+    _ndf = capi.NDF_GGX
+
+
+class beckmann(microfacet):
+    _ndf = capi.NDF_BECKMANN
+
+    # LEAN algebra (dj_brdf.h:355-356)
+    @staticmethod
+    def lrep_to_params(E):
+        b = Buf(E, np.float32)
+        n = b.n // 5
+        out = capi.empty_like_space(b.keep, (n, 12), np.float32)
+        bo = Buf(out, np.float32, True)
+        check(capi.load().djb200_lrep_to_params(b.ptr, C.c_int64(n), bo.ptr, b.mem, capi.current_stream_ptr(b.mem)))
+        return out
+
+    @staticmethod
+    def params_to_lrep(p):
+        b = Buf(p, np.float32)
+        n = b.n // 12
+        out = capi.empty_like_space(b.keep, (n, 5), np.float32)
+        bo = Buf(out, np.float32, True)
+        check(capi.load().djb200_params_to_lrep(b.ptr, C.c_int64(n), bo.ptr, b.mem, capi.current_stream_ptr(b.mem)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+class _table_brdf(brdf):
+    _destroy = None
+    _eval = None
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                getattr(capi.load(), self._destroy)(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def eval(self, i, o, user_param=None):
+        bi, bo = Buf(i, np.float32), Buf(o, np.float32)
+        mem = capi.same_space(bi, bo)
+        n = bi.n // 3
+        out = capi.empty_like_space(bi.keep, (n, 3), np.float32)
+        bout = Buf(out, np.float32, True)
+        check(getattr(capi.load(), self._eval)(self._h, bi.ptr, bo.ptr, C.c_int64(n), bout.ptr, C.c_int(mem),
+                                               capi.current_stream_ptr(mem)))
+        return out
+
+
+class merl(_table_brdf):
+    """djb::merl (dj_brdf.h:126-133): from a .binary file name or a [3*1458000] float64 sample array."""
+    _destroy, _eval = "djb200_merl_destroy", "djb200_merl_eval"
+
+    def __init__(self, filename_or_samples):
+        super().__init__()
+        if isinstance(filename_or_samples, (str, bytes)) or hasattr(filename_or_samples, "__fspath__"):
+            check(capi.load().djb200_merl_load(str(filename_or_samples).encode(), C.byref(self._h)))
+        else:
+            s = np.ascontiguousarray(filename_or_samples, np.float64).reshape(-1)
+            if s.size != 3 * 90 * 90 * 180:
+                raise DjbError(1, "MERL sample array must hold 3*90*90*180 doubles")
+            check(capi.load().djb200_merl_create(C.c_void_p(s.ctypes.data), C.byref(self._h)))
+
+    @staticmethod
+    def index(i, o):
+        """The cell index merl::eval computes (dj_brdf.h:997-1002)."""
+        bi, bo = Buf(i, np.float32), Buf(o, np.float32)
+        mem = capi.same_space(bi, bo)
+        n = bi.n // 3
+        out = capi.empty_like_space(bi.keep, (n,), np.int32)
+        bout = Buf(out, np.int32, True)
+        check(capi.load().djb200_merl_index(bi.ptr, bo.ptr, C.c_int64(n), bout.ptr, C.c_int(mem),
+                                            capi.current_stream_ptr(mem)))
+        return out
+
+
+class utia(_table_brdf):
+    """djb::utia (dj_brdf.h:136-146): from a .bin file name or the raw [3*6*48*6*48] float64 samples."""
+    _destroy, _eval = "djb200_utia_destroy", "djb200_utia_eval"
+
+    def __init__(self, filename_or_samples):
+        super().__init__()
+        if isinstance(filename_or_samples, (str, bytes)) or hasattr(filename_or_samples, "__fspath__"):
+            check(capi.load().djb200_utia_load(str(filename_or_samples).encode(), C.byref(self._h)))
+        else:
+            s = np.ascontiguousarray(filename_or_samples, np.float64).reshape(-1)
+            if s.size != 3 * 6 * 48 * 6 * 48:
+                raise DjbError(1, "UTIA sample array must hold 3*6*48*6*48 doubles")
+            check(capi.load().djb200_utia_create(C.c_void_p(s.ctypes.data), C.byref(self._h)))
+
+
+# --------------------------------------------------------------------------------------------------
+def nmap2leanmap(nmap, base_roughness=1e-5, bias=0.0):
+    """utils/nmap2leanmap.cpp:18-54 (bias=0) / nmap2leanmap_biased.cpp:23-63 (bias=25).
+    nmap: planar uint8 [3, h, w] -> (leanmap_1, leanmap_2), planar float32 [4, h, w]."""
+    b = Buf(nmap, np.uint8)
+    shape = tuple(b.keep.shape)
+    if len(shape) != 3 or shape[0] != 3:
+        raise ValueError("nmap must be planar [3, h, w]")
+    _, h, w = shape
+    l1 = capi.empty_like_space(b.keep, (4, h, w), np.float32)
+    l2 = capi.empty_like_space(b.keep, (4, h, w), np.float32)
+    b1, b2 = Buf(l1, np.float32, True), Buf(l2, np.float32, True)
+    check(capi.load().djb200_nmap_to_leanmap(b.ptr, C.c_int32(w), C.c_int32(h), C.c_float(base_roughness),
+                                             C.c_float(bias), b1.ptr, b2.ptr, C.c_int(b.mem),
+                                             capi.current_stream_ptr(b.mem)))
+    return l1, l2
+
+
+def leanmap_to_params(leanmap_1, leanmap_2, bias=0.0):
+    """check_lean_maps (utils/nmap2leanmap.cpp:57-76) as a producer: per-texel lrep_to_params -> [h*w, 12]."""
+    b1, b2 = Buf(leanmap_1, np.float32), Buf(leanmap_2, np.float32)
+    mem = capi.same_space(b1, b2)
+    _, h, w = tuple(b1.keep.shape)
+    out = capi.empty_like_space(b1.keep, (h * w, 12), np.float32)
+    bo = Buf(out, np.float32, True)
+    check(capi.load().djb200_leanmap_to_params(b1.ptr, b2.ptr, C.c_int32(w), C.c_int32(h), C.c_float(bias), bo.ptr,
+                                               C.c_int(mem), capi.current_stream_ptr(mem)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+def _source_struct(src):
+    s = capi.Source()
+    if isinstance(src, merl):
+        s.kind, s.merl = capi.SOURCE_MERL, src._h
+    elif isinstance(src, utia):
+        s.kind, s.utia = capi.SOURCE_UTIA, src._h
+    elif isinstance(src, microfacet):
+        s.kind, s.microfacet = capi.SOURCE_MICROFACET, src._desc()
+    else:
+        raise DjbError(6, f"cannot fit from a {type(src).__name__}")
+    return s
+
+
+class tabular:
+    """djb::tabular (dj_brdf.h:394-425): the isotropic power-iteration fit of any source BRDF.
+
+    ``tabular(brdf, res, shadow)`` fits one material; ``tabular.fit_batch(brdfs, ...)`` fits many in
+    one device pass.  ``iterations`` is 4 in the reference (dj_brdf.h:2518)."""
+
+    def __init__(self, source, resolution, shadow=True, iterations=4, _result=None):
+        r = _result or tabular._run([source], resolution, shadow, iterations)[0]
+        self.__dict__.update(r)
+        self.m_shadow = bool(shadow)
+
+    @staticmethod
+    def _run(sources, res, shadow, iterations):
+        if res <= 2:
+            raise DjbError(1, "Invalid Resolution")  # DJB_ASSERT, dj_brdf.h:2218
+        n = len(sources)
+        srcs = (capi.Source * n)(*[_source_struct(s) for s in sources])
+        fits = (capi.TabularFit * n)()
+        arrays = []
+        for k in range(n):
+            a = dict(m_p22=np.zeros(res, np.float32), m_sigma=np.zeros(res, np.float32),
+                     m_cdf=np.zeros(res, np.float32), m_qf=np.zeros(res, np.float32),
+                     m_fresnel_points=np.zeros((res, 3), np.float32),
+                     residuals=np.zeros(max(1, iterations), np.float32))
+            arrays.append(a)
+            f = fits[k]
+            f.res = res
+            f.p22, f.sigma, f.cdf, f.qf = (a[x].ctypes.data for x in ("m_p22", "m_sigma", "m_cdf", "m_qf"))
+            f.fresnel = a["m_fresnel_points"].ctypes.data
+            f.residuals = a["residuals"].ctypes.data
+        check(capi.load().djb200_fit_tabular(srcs, C.c_int32(n), C.c_int32(res), C.c_int32(int(shadow)),
+                                             C.c_int32(iterations), fits, None))
+        for k in range(n):
+            arrays[k]["alpha_beckmann"] = float(fits[k].alpha_beckmann)
+            arrays[k]["alpha_ggx"] = float(fits[k].alpha_ggx)
+        return arrays
+
+    @staticmethod
+    def fit_batch(sources, resolution=90, shadow=True, iterations=4):
+        return [tabular(None, resolution, shadow, iterations, _result=r)
+                for r in tabular._run(list(sources), resolution, shadow, iterations)]
+
+    # accessors, dj_brdf.h:404-407
+    def get_p22v(self):
+        return self.m_p22
+
+    def get_sigmav(self):
+        return self.m_sigma
+
+    def get_cdfv(self):
+        return self.m_cdf
+
+    def get_qfv(self):
+        return self.m_qf
+
+    def get_fresnel(self):
+        return fresnel.spline(self.m_fresnel_points)
+
+    # dj_brdf.h:402-403
+    @staticmethod
+    def fit_beckmann_parameters(tab):
+        return params.isotropic(tab.alpha_beckmann)
+
+    @staticmethod
+    def fit_ggx_parameters(tab):
+        return params.isotropic(tab.alpha_ggx)
+
+
+class tabular_anisotropic:
+    """djb::tabular_anisotropic (dj_brdf.h:428-478), eval tables + parameter fits."""
+
+    def __init__(self, source, elevation_res, azimuthal_res, shadow=True, iterations=4, _result=None):
+        r = _result or tabular_anisotropic._run([source], elevation_res, azimuthal_res, shadow, iterations)[0]
+        self.__dict__.update(r)
+        self.m_elevation_res, self.m_azimuthal_res = elevation_res, azimuthal_res
+
+    @staticmethod
+    def _run(sources, er, ar, shadow, iterations):
+        if er <= 1 or ar <= 1:
+            raise DjbError(1, "Invalid Resolution")  # dj_brdf.h:2244
+        n = len(sources)
+        srcs = (capi.Source * n)(*[_source_struct(s) for s in sources])
+        fits = (capi.TabularAnisotropicFit * n)()
+        arrays = []
+        for k in range(n):
+            a = dict(m_p22=np.zeros(er * ar, np.float32), m_sigma=np.zeros(er * ar, np.float32),
+                     m_fresnel_points=np.zeros((er, 3), np.float32),
+                     residuals=np.zeros(max(1, iterations), np.float32))
+            arrays.append(a)
+            f = fits[k]
+            f.elev_res, f.azim_res = er, ar
+            f.p22, f.sigma = a["m_p22"].ctypes.data, a["m_sigma"].ctypes.data
+            f.fresnel = a["m_fresnel_points"].ctypes.data
+            f.residuals = a["residuals"].ctypes.data
+        check(capi.load().djb200_fit_tabular_anisotropic(srcs, C.c_int32(n), C.c_int32(er), C.c_int32(ar),
+                                                         C.c_int32(int(shadow)), C.c_int32(iterations), fits, None))
+        for k in range(n):
+            arrays[k]["beckmann"] = np.array(list(fits[k].beckmann), np.float32)
+            arrays[k]["ggx"] = np.array(list(fits[k].ggx), np.float32)
+        return arrays
+
+    def get_p22v(self):
+        return self.m_p22, self.m_elevation_res, self.m_azimuthal_res
+
+    def get_sigmav(self):
+        return self.m_sigma, self.m_elevation_res, self.m_azimuthal_res
+
+    @staticmethod
+    def fit_beckmann_parameters(tab):
+        return params.pdfparams(*[float(x) for x in tab.beckmann])
+
+    @staticmethod
+    def fit_ggx_parameters(tab):
+        return params.pdfparams(*[float(x) for x in tab.ggx])

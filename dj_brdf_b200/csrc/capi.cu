@@ -1,0 +1,680 @@
+// capi.cu -- the C-ABI of libdjb200.so (include/djb200.h): argument checking, error reporting,
+// host-side params factories, device-resident table handles and the host<->device staging
+// pipeline.  All numerics live in the kernel translation units; there is no CPU implementation
+// of any bulk path in this library.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "djb_internal.h"
+
+namespace djb200 {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+static thread_local std::string t_error;
+
+static djb200_status fail(djb200_status s, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	t_error = buf;
+	return s;
+}
+
+static djb200_status cuda_fail(cudaError_t e, const char *what)
+{
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+		return fail(DJB200_ERR_NO_DEVICE, "%s: no CUDA device (%s); libdjb200 has no CPU fallback", what,
+		            cudaGetErrorString(e));
+	if (e == cudaErrorMemoryAllocation) return fail(DJB200_ERR_OUT_OF_MEMORY, "%s: %s", what, cudaGetErrorString(e));
+	return fail(DJB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(call)                                                  \
+	do {                                                          \
+		cudaError_t e__ = (call);                                 \
+		if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+	} while (0)
+
+int sm_count()
+{
+	static thread_local int cached_dev = -1, cached = 0;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+	if (dev != cached_dev) {
+		cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+		cached_dev = dev;
+	}
+	return cached > 0 ? cached : 148;
+}
+
+static djb200_status require_device()
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+	if (n <= 0) return fail(DJB200_ERR_NO_DEVICE, "no CUDA device; libdjb200 has no CPU fallback");
+	return DJB200_OK;
+}
+
+// ---- host-side params factories (dj_brdf.h:1355-1474), same rounding points as the reference ----
+static inline float inv_sqrt_h(float x) { return (float)(1.0 / std::sqrt((double)x)); }
+
+static void set_location_h(djb200_params *p, float tx, float ty)
+{
+	p->tx_n = tx;
+	p->ty_n = ty;
+	float x = -tx, y = -ty, z = 1.0f;
+	float k = inv_sqrt_h((x * x + y * y) + z * z);
+	p->n[0] = k * x;
+	p->n[1] = k * y;
+	p->n[2] = k * z;
+}
+
+static void elliptic_h(float a1, float a2, float phi, djb200_params *p)
+{
+	float c = (float)std::cos((double)phi), s = (float)std::sin((double)phi);
+	float c2 = (float)(2.0 * (double)c * (double)c - 1.0);
+	float q1 = a1 * a1, q2 = a2 * a2, t1 = q1 + q2, t2 = q1 - q2;
+	p->a1 = a1;
+	p->a2 = a2;
+	p->phi_a = phi;
+	p->ax = (float)std::sqrt(0.5 * (double)(t1 + t2 * c2));
+	p->ay = (float)std::sqrt(0.5 * (double)(t1 - t2 * c2));
+	p->rho = (q2 - q1) * c * s / (p->ax * p->ay);
+	p->sqrt_one_minus_rho2 = (float)std::sqrt(1.0 - (double)(p->rho * p->rho));
+	set_location_h(p, 0.0f, 0.0f);
+}
+
+static void pdfparams_h(float ax, float ay, float rho, float tx, float ty, djb200_params *p)
+{
+	p->ax = ax;
+	p->ay = ay;
+	p->rho = rho;
+	p->sqrt_one_minus_rho2 = (float)std::sqrt(1.0 - (double)(rho * rho));
+	float qx = ax * ax, qy = ay * ay;
+	float cov = (float)((double)(rho * ax * ay) * 2.0);
+	float t1 = qx + qy, t2 = qx - qy;
+	float t3 = (float)std::sqrt((double)(t2 * t2 + cov * cov));
+	p->a1 = (float)std::sqrt(0.5 * (double)(t1 + t3));
+	p->a2 = (float)std::sqrt(0.5 * (double)(t1 - t3));
+	p->phi_a = (cov != 0.0f) ? (float)std::atan((double)((qx - qy - t3) / cov)) : 0.0f;
+	set_location_h(p, tx, ty);
+}
+
+// ---- staging pipeline for DJB200_MEM_HOST -------------------------------------------------------
+struct BulkIn { const void *host; size_t item; };                 // one item per pair
+struct BulkOut { void *host; size_t item; };                      // one item per (material, pair)
+
+// body(dev_in[], dev_out[], chunk_n, stream): enqueue the kernels for one chunk; outputs use
+// out_stride = chunk_n.  reps = number of material blocks each output holds per pair.
+template <class Body>
+static djb200_status host_pipeline(int64_t n, const std::vector<BulkIn> &ins, const std::vector<BulkOut> &outs,
+                                   int64_t reps, Body body)
+{
+	if (n <= 0) return DJB200_OK;
+	size_t per_pair = 0;
+	for (auto &i : ins) per_pair += i.item;
+	for (auto &o : outs) per_pair += o.item * (size_t)reps;
+	const size_t budget = (size_t)256 << 20; // device bytes per pipeline slot
+	int64_t chunk = (int64_t)(budget / (per_pair ? per_pair : 1));
+	chunk = chunk < 4096 ? 4096 : chunk;
+	chunk &= ~(int64_t)3;
+	if (chunk > n) chunk = n;
+	const int SLOTS = (n > chunk) ? 3 : 1;
+
+	struct Slot {
+		cudaStream_t st = nullptr;
+		std::vector<void *> din, dout;
+	} slot[3];
+	djb200_status rc = DJB200_OK;
+	auto cleanup = [&]() {
+		for (int s = 0; s < SLOTS; ++s) {
+			if (slot[s].st) cudaStreamSynchronize(slot[s].st);
+			for (void *p : slot[s].din) cudaFree(p);
+			for (void *p : slot[s].dout) cudaFree(p);
+			if (slot[s].st) cudaStreamDestroy(slot[s].st);
+		}
+	};
+#define PCU(call)                                                                   \
+	do {                                                                            \
+		cudaError_t e__ = (call);                                                   \
+		if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call); cleanup(); return rc; } \
+	} while (0)
+
+	for (int s = 0; s < SLOTS; ++s) {
+		PCU(cudaStreamCreateWithFlags(&slot[s].st, cudaStreamNonBlocking));
+		for (auto &i : ins) {
+			void *p = nullptr;
+			PCU(cudaMalloc(&p, i.item * (size_t)chunk));
+			slot[s].din.push_back(p);
+		}
+		for (auto &o : outs) {
+			void *p = nullptr;
+			PCU(cudaMalloc(&p, o.item * (size_t)chunk * (size_t)reps));
+			slot[s].dout.push_back(p);
+		}
+	}
+	int c = 0;
+	for (int64_t off = 0; off < n; off += chunk, ++c) {
+		Slot &S = slot[c % SLOTS];
+		int64_t cn = n - off < chunk ? n - off : chunk;
+		for (size_t k = 0; k < ins.size(); ++k)
+			PCU(cudaMemcpyAsync(S.din[k], (const char *)ins[k].host + (size_t)off * ins[k].item, ins[k].item * (size_t)cn,
+			                    cudaMemcpyHostToDevice, S.st));
+		cudaError_t e = body(S.din, S.dout, cn, S.st);
+		if (e != cudaSuccess) { rc = cuda_fail(e, "kernel launch"); cleanup(); return rc; }
+		for (size_t k = 0; k < outs.size(); ++k)
+			for (int64_t m = 0; m < reps; ++m)
+				PCU(cudaMemcpyAsync((char *)outs[k].host + ((size_t)m * (size_t)n + (size_t)off) * outs[k].item,
+				                    (const char *)S.dout[k] + (size_t)m * (size_t)cn * outs[k].item,
+				                    outs[k].item * (size_t)cn, cudaMemcpyDeviceToHost, S.st));
+	}
+	for (int s = 0; s < SLOTS; ++s) PCU(cudaStreamSynchronize(slot[s].st));
+#undef PCU
+	cleanup();
+	return rc;
+}
+
+// small host descriptor -> device scratch (stream ordered)
+static cudaError_t upload_small(const void *host, size_t bytes, void **dev, cudaStream_t st)
+{
+	cudaError_t e = cudaMallocAsync(dev, bytes, st);
+	if (e != cudaSuccess) return e;
+	return cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, st);
+}
+
+static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const djb200_params *params,
+                                     int64_t n_params, int layout, const float *a, const float *b, int64_t n,
+                                     float *out0, float *out1, float *out2, int mem, void *stream)
+{
+	if (!mf) return fail(DJB200_ERR_INVALID_ARGUMENT, "microfacet descriptor is NULL");
+	if (mf->ndf != DJB200_NDF_BECKMANN && mf->ndf != DJB200_NDF_GGX)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown ndf %d", mf->ndf);
+	if (mf->fresnel.kind < 0 || mf->fresnel.kind > DJB200_FRESNEL_SPLINE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown fresnel kind %d", mf->fresnel.kind);
+	if (mf->fresnel.kind == DJB200_FRESNEL_SPLINE && (!mf->fresnel.points || mf->fresnel.n_points < 1))
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "spline fresnel needs points");
+	if (n < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative pair count");
+	if (layout != DJB200_PARAMS_BROADCAST && layout != DJB200_PARAMS_PER_PAIR)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown params layout %d", layout);
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	// NULL params => params::standard(), like the reference's NULL user_param (dj_brdf.h:1532-1534)
+	djb200_params standard;
+	if (!params) {
+		elliptic_h(1.0f, 1.0f, 0.0f, &standard);
+		params = &standard;
+		n_params = 1;
+		layout = DJB200_PARAMS_BROADCAST;
+	}
+	if (layout == DJB200_PARAMS_BROADCAST && n_params < 1)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one params block");
+	if (layout == DJB200_PARAMS_PER_PAIR && n_params != n)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "PER_PAIR layout needs n_params == n");
+	if (n == 0) return DJB200_OK;
+	if (!a || !b) return fail(DJB200_ERR_INVALID_ARGUMENT, "direction arrays are NULL");
+	if (op != OP_EVALP_IS && !out0) return fail(DJB200_ERR_INVALID_ARGUMENT, "output array is NULL");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+
+	const bool uses_u = (op == OP_SAMPLE || op == OP_EVALP_IS);
+	const size_t a_item = uses_u ? 8 : 12;
+	const size_t out0_item = (op == OP_PDF) ? 4 : 12;
+
+	MfLaunch L;
+	memset(&L, 0, sizeof L);
+	L.op = op;
+	L.ndf = mf->ndf;
+	L.shadow = mf->shadow;
+	L.fresnel_kind = mf->fresnel.kind;
+	memcpy(L.fv, mf->fresnel.v, sizeof L.fv);
+	L.layout = layout;
+	L.n_params = n_params;
+
+	if (mem == DJB200_MEM_DEVICE) {
+		cudaStream_t st = (cudaStream_t)stream;
+		void *d_params = nullptr, *d_spline = nullptr;
+		if (layout == DJB200_PARAMS_BROADCAST) {
+			CU(upload_small(params, sizeof(djb200_params) * (size_t)n_params, &d_params, st));
+			L.params = d_params;
+		} else {
+			L.params = params; // bulk device array
+		}
+		if (L.fresnel_kind == DJB200_FRESNEL_SPLINE) {
+			CU(upload_small(mf->fresnel.points, sizeof(float) * 3 * (size_t)mf->fresnel.n_points, &d_spline, st));
+			L.spline_pts = (const float *)d_spline;
+			L.spline_n = mf->fresnel.n_points;
+		}
+		L.a = a; L.b = b; L.n = n; L.out_stride = n;
+		L.out0 = out0; L.out1 = out1; L.out2 = out2;
+		cudaError_t e = launch_microfacet(L, st);
+		if (d_params) cudaFreeAsync(d_params, st);
+		if (d_spline) cudaFreeAsync(d_spline, st);
+		if (e != cudaSuccess) return cuda_fail(e, "microfacet kernel launch");
+		return DJB200_OK;
+	}
+
+	// host memory: stage through the device in chunks
+	void *d_params = nullptr, *d_spline = nullptr;
+	if (layout == DJB200_PARAMS_BROADCAST) {
+		CU(cudaMalloc(&d_params, sizeof(djb200_params) * (size_t)n_params));
+		CU(cudaMemcpy(d_params, params, sizeof(djb200_params) * (size_t)n_params, cudaMemcpyHostToDevice));
+	}
+	if (L.fresnel_kind == DJB200_FRESNEL_SPLINE) {
+		CU(cudaMalloc(&d_spline, sizeof(float) * 3 * (size_t)mf->fresnel.n_points));
+		CU(cudaMemcpy(d_spline, mf->fresnel.points, sizeof(float) * 3 * (size_t)mf->fresnel.n_points,
+		              cudaMemcpyHostToDevice));
+		L.spline_pts = (const float *)d_spline;
+		L.spline_n = mf->fresnel.n_points;
+	}
+	std::vector<BulkIn> ins = {{a, a_item}, {b, 12}};
+	if (layout == DJB200_PARAMS_PER_PAIR) ins.push_back({params, sizeof(djb200_params)});
+	std::vector<BulkOut> outs;
+	int slot0 = -1, slot1 = -1, slot2 = -1;
+	if (out0) { slot0 = (int)outs.size(); outs.push_back({out0, out0_item}); }
+	if (out1) { slot1 = (int)outs.size(); outs.push_back({out1, 12}); }
+	if (out2) { slot2 = (int)outs.size(); outs.push_back({out2, 4}); }
+	const int64_t reps = (layout == DJB200_PARAMS_BROADCAST) ? n_params : 1;
+	djb200_status rc = host_pipeline(n, ins, outs, reps,
+		[&](const std::vector<void *> &din, const std::vector<void *> &dout, int64_t cn, cudaStream_t st) {
+			MfLaunch C = L;
+			C.a = (const float *)din[0];
+			C.b = (const float *)din[1];
+			C.params = (layout == DJB200_PARAMS_PER_PAIR) ? din[2] : d_params;
+			C.n_params = (layout == DJB200_PARAMS_PER_PAIR) ? cn : n_params;
+			C.n = cn;
+			C.out_stride = cn;
+			C.out0 = slot0 >= 0 ? (float *)dout[slot0] : nullptr;
+			C.out1 = slot1 >= 0 ? (float *)dout[slot1] : nullptr;
+			C.out2 = slot2 >= 0 ? (float *)dout[slot2] : nullptr;
+			return launch_microfacet(C, st);
+		});
+	if (d_params) cudaFree(d_params);
+	if (d_spline) cudaFree(d_spline);
+	return rc;
+}
+
+// generic "n items in, n items out" call used by the table / frame / LEAN entry points
+template <class Body>
+static djb200_status map_call(int64_t n, const std::vector<BulkIn> &ins, const std::vector<BulkOut> &outs, int mem,
+                              void *stream, Body body)
+{
+	if (n < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative element count");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	if (n == 0) return DJB200_OK;
+	for (auto &i : ins) if (!i.host) return fail(DJB200_ERR_INVALID_ARGUMENT, "input array is NULL");
+	for (auto &o : outs) if (!o.host) return fail(DJB200_ERR_INVALID_ARGUMENT, "output array is NULL");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	if (mem == DJB200_MEM_DEVICE) {
+		std::vector<void *> din, dout;
+		for (auto &i : ins) din.push_back(const_cast<void *>(i.host));
+		for (auto &o : outs) dout.push_back(o.host);
+		cudaError_t e = body(din, dout, n, (cudaStream_t)stream);
+		if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+		return DJB200_OK;
+	}
+	return host_pipeline(n, ins, outs, 1, body);
+}
+
+} // namespace djb200
+
+using namespace djb200;
+
+// ====================================================================================================
+extern "C" {
+
+struct djb200_merl {
+	float4 *cells;
+	int device;
+};
+
+struct djb200_utia {
+	float *table;
+	int device;
+};
+
+const char *djb200_last_error(void) { return t_error.c_str(); }
+const char *djb200_version(void) { return "djb200 0.1 (sm_100a)"; }
+
+djb200_status djb200_device_count(int *count)
+{
+	if (!count) return fail(DJB200_ERR_INVALID_ARGUMENT, "count is NULL");
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		*count = 0;
+		return cuda_fail(e, "cudaGetDeviceCount");
+	}
+	*count = n;
+	return DJB200_OK;
+}
+
+djb200_status djb200_set_device(int device)
+{
+	CU(cudaSetDevice(device));
+	return DJB200_OK;
+}
+
+uint64_t djb200_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+djb200_status djb200_params_standard(djb200_params *out) { return djb200_params_elliptic(1.0f, 1.0f, 0.0f, out); }
+djb200_status djb200_params_isotropic(float a, djb200_params *out) { return djb200_params_elliptic(a, a, 0.0f, out); }
+
+djb200_status djb200_params_elliptic(float a1, float a2, float phi_a, djb200_params *out)
+{
+	if (!out) return fail(DJB200_ERR_INVALID_ARGUMENT, "out is NULL");
+	// DJB_ASSERT(a1 > 0.0 && a2 > 0.0 && "Invalid ellipse radii"), dj_brdf.h:1453
+	if (!(a1 > 0.0f && a2 > 0.0f)) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid ellipse radii");
+	elliptic_h(a1, a2, phi_a, out);
+	return DJB200_OK;
+}
+
+djb200_status djb200_params_pdfparams(float ax, float ay, float rho, float tx_n, float ty_n, djb200_params *out)
+{
+	if (!out) return fail(DJB200_ERR_INVALID_ARGUMENT, "out is NULL");
+	// dj_brdf.h:1466-1467
+	if (!(ax > 0.0f && ay > 0.0f)) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid scale parameters");
+	if (!(std::fabs((double)rho) < 1.0)) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid correlation parameter");
+	pdfparams_h(ax, ay, rho, tx_n, ty_n, out);
+	return DJB200_OK;
+}
+
+djb200_status djb200_microfacet_eval(const djb200_microfacet *mf, const djb200_params *params, int64_t n_params,
+                                     int params_layout, const float *wi, const float *wo, int64_t n,
+                                     float *out_rgb, int mem, void *stream)
+{
+	return microfacet_call(OP_EVAL, mf, params, n_params, params_layout, wi, wo, n, out_rgb, nullptr, nullptr, mem, stream);
+}
+
+djb200_status djb200_microfacet_evalp(const djb200_microfacet *mf, const djb200_params *params, int64_t n_params,
+                                      int params_layout, const float *wi, const float *wo, int64_t n,
+                                      float *out_rgb, int mem, void *stream)
+{
+	return microfacet_call(OP_EVALP, mf, params, n_params, params_layout, wi, wo, n, out_rgb, nullptr, nullptr, mem, stream);
+}
+
+djb200_status djb200_microfacet_pdf(const djb200_microfacet *mf, const djb200_params *params, int64_t n_params,
+                                    int params_layout, const float *wi, const float *wo, int64_t n, float *out_pdf,
+                                    int mem, void *stream)
+{
+	return microfacet_call(OP_PDF, mf, params, n_params, params_layout, wi, wo, n, out_pdf, nullptr, nullptr, mem, stream);
+}
+
+djb200_status djb200_microfacet_sample(const djb200_microfacet *mf, const djb200_params *params, int64_t n_params,
+                                       int params_layout, const float *u, const float *wo, int64_t n, float *out_wi,
+                                       int mem, void *stream)
+{
+	return microfacet_call(OP_SAMPLE, mf, params, n_params, params_layout, u, wo, n, out_wi, nullptr, nullptr, mem, stream);
+}
+
+djb200_status djb200_microfacet_evalp_is(const djb200_microfacet *mf, const djb200_params *params, int64_t n_params,
+                                         int params_layout, const float *u, const float *wo, int64_t n,
+                                         float *out_weight_rgb, float *out_wi, float *out_pdf, int mem, void *stream)
+{
+	if (!out_weight_rgb && !out_wi && !out_pdf) return fail(DJB200_ERR_INVALID_ARGUMENT, "all outputs are NULL");
+	return microfacet_call(OP_EVALP_IS, mf, params, n_params, params_layout, u, wo, n, out_weight_rgb, out_wi, out_pdf,
+	                       mem, stream);
+}
+
+djb200_status djb200_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d, int mem, void *stream)
+{
+	return map_call(n, {{wi, 12}, {wo, 12}}, {{h, 12}, {d, 12}}, mem, stream,
+		[](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_io_to_hd((const float *)i[0], (const float *)i[1], cn, (float *)o[0], (float *)o[1], st);
+		});
+}
+
+djb200_status djb200_hd_to_io(const float *h, const float *d, int64_t n, float *wi, float *wo, int mem, void *stream)
+{
+	return map_call(n, {{h, 12}, {d, 12}}, {{wi, 12}, {wo, 12}}, mem, stream,
+		[](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_hd_to_io((const float *)i[0], (const float *)i[1], cn, (float *)o[0], (float *)o[1], st);
+		});
+}
+
+// ---- MERL ------------------------------------------------------------------------------------------
+static const int64_t MERL_N = 90 * 90 * 180;
+
+djb200_status djb200_merl_create(const double *samples, djb200_merl **out)
+{
+	if (!samples || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	double *tmp = nullptr;
+	float4 *cells = nullptr;
+	CU(cudaMalloc(&tmp, sizeof(double) * 3 * MERL_N));
+	cudaError_t e = cudaMalloc(&cells, sizeof(float4) * MERL_N);
+	if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "cudaMalloc(merl cells)"); }
+	e = cudaMemcpy(tmp, samples, sizeof(double) * 3 * MERL_N, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = launch_merl_convert(tmp, cells, 0);
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
+	cudaFree(tmp);
+	if (e != cudaSuccess) { cudaFree(cells); return cuda_fail(e, "merl upload"); }
+	djb200_merl *m = new djb200_merl;
+	m->cells = cells;
+	cudaGetDevice(&m->device);
+	*out = m;
+	return DJB200_OK;
+}
+
+djb200_status djb200_merl_load(const char *filename, djb200_merl **out)
+{
+	if (!filename || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	FILE *f = fopen(filename, "rb");
+	if (!f) return fail(DJB200_ERR_IO, "djb_error: Failed to open %s", filename); // dj_brdf.h:970
+	int32_t dims[3];
+	if (fread(dims, 4, 3, f) != 3) { fclose(f); return fail(DJB200_ERR_IO, "djb_error: Failed to read MERL header"); }
+	int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+	if (n <= 0) { fclose(f); return fail(DJB200_ERR_IO, "djb_error: Failed to read MERL header"); } // :976
+	if (n != MERL_N) { fclose(f); return fail(DJB200_ERR_UNSUPPORTED, "MERL header (%d,%d,%d) is not 90x90x180", dims[0], dims[1], dims[2]); }
+	std::vector<double> buf((size_t)3 * n);
+	size_t got = fread(buf.data(), sizeof(double), buf.size(), f);
+	fclose(f);
+	if (got != buf.size()) return fail(DJB200_ERR_IO, "djb_error: Reading %s failed", filename); // :982
+	return djb200_merl_create(buf.data(), out);
+}
+
+djb200_status djb200_merl_destroy(djb200_merl *m)
+{
+	if (!m) return DJB200_OK;
+	cudaFree(m->cells);
+	delete m;
+	return DJB200_OK;
+}
+
+djb200_status djb200_merl_eval(const djb200_merl *m, const float *wi, const float *wo, int64_t n, float *out_rgb,
+                               int mem, void *stream)
+{
+	if (!m) return fail(DJB200_ERR_INVALID_ARGUMENT, "merl handle is NULL");
+	const float4 *cells = m->cells;
+	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_rgb, 12}}, mem, stream,
+		[cells](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_merl_eval(cells, (const float *)i[0], (const float *)i[1], cn, (float *)o[0], st);
+		});
+}
+
+djb200_status djb200_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out_index, int mem, void *stream)
+{
+	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_index, 4}}, mem, stream,
+		[](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_merl_index((const float *)i[0], (const float *)i[1], cn, (int32_t *)o[0], st);
+		});
+}
+
+// ---- UTIA ------------------------------------------------------------------------------------------
+static const int64_t UTIA_N = 3 * 6 * 48 * 6 * 48;
+
+djb200_status djb200_utia_create(const double *raw_samples, djb200_utia **out)
+{
+	if (!raw_samples || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	double *tmp = nullptr;
+	float *table = nullptr;
+	CU(cudaMalloc(&tmp, sizeof(double) * UTIA_N));
+	cudaError_t e = cudaMalloc(&table, sizeof(float) * UTIA_N);
+	if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "cudaMalloc(utia table)"); }
+	e = cudaMemcpy(tmp, raw_samples, sizeof(double) * UTIA_N, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = launch_utia_convert(tmp, table, 0);
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
+	cudaFree(tmp);
+	if (e != cudaSuccess) { cudaFree(table); return cuda_fail(e, "utia upload"); }
+	djb200_utia *u = new djb200_utia;
+	u->table = table;
+	cudaGetDevice(&u->device);
+	*out = u;
+	return DJB200_OK;
+}
+
+djb200_status djb200_utia_load(const char *filename, djb200_utia **out)
+{
+	if (!filename || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	FILE *f = fopen(filename, "rb");
+	if (!f) return fail(DJB200_ERR_IO, "djb_error: Failed to open %s", filename); // dj_brdf.h:1044
+	std::vector<double> buf((size_t)UTIA_N);
+	size_t got = fread(buf.data(), sizeof(double), buf.size(), f);
+	fclose(f);
+	if (got != buf.size()) return fail(DJB200_ERR_IO, "djb_error: Reading %s failed", filename); // :1058
+	return djb200_utia_create(buf.data(), out);
+}
+
+djb200_status djb200_utia_destroy(djb200_utia *u)
+{
+	if (!u) return DJB200_OK;
+	cudaFree(u->table);
+	delete u;
+	return DJB200_OK;
+}
+
+djb200_status djb200_utia_eval(const djb200_utia *u, const float *wi, const float *wo, int64_t n, float *out_rgb,
+                               int mem, void *stream)
+{
+	if (!u) return fail(DJB200_ERR_INVALID_ARGUMENT, "utia handle is NULL");
+	const float *table = u->table;
+	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_rgb, 12}}, mem, stream,
+		[table](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_utia_eval(table, (const float *)i[0], (const float *)i[1], cn, (float *)o[0], st);
+		});
+}
+
+// ---- LEAN ------------------------------------------------------------------------------------------
+djb200_status djb200_nmap_to_leanmap(const uint8_t *nmap, int32_t w, int32_t h, float base_roughness, float bias,
+                                     float *lean1, float *lean2, int mem, void *stream)
+{
+	if (w < 0 || h < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative image size");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	int64_t npix = (int64_t)w * h;
+	if (npix == 0) return DJB200_OK;
+	if (!nmap || !lean1 || !lean2) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL image pointer");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	if (mem == DJB200_MEM_DEVICE) {
+		cudaError_t e = launch_nmap_to_leanmap(nmap, npix, base_roughness, bias, lean1, lean2, (cudaStream_t)stream);
+		if (e != cudaSuccess) return cuda_fail(e, "lean kernel launch");
+		return DJB200_OK;
+	}
+	// host images: planar data, so the whole image is staged in row bands that keep every plane
+	// contiguous on the device (band-local planar layout), then copied plane by plane
+	const int64_t band_rows_budget = ((int64_t)192 << 20) / ((int64_t)w * 35);
+	int64_t band = band_rows_budget < 1 ? 1 : band_rows_budget;
+	if (band > h) band = h;
+	const int SLOTS = band < h ? 2 : 1;
+	cudaStream_t st[2] = {nullptr, nullptr};
+	uint8_t *d_in[2] = {nullptr, nullptr};
+	float *d_o1[2] = {nullptr, nullptr}, *d_o2[2] = {nullptr, nullptr};
+	cudaError_t e = cudaSuccess;
+	for (int s = 0; s < SLOTS && e == cudaSuccess; ++s) {
+		e = cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaMalloc(&d_in[s], (size_t)band * w * 3);
+		if (e == cudaSuccess) e = cudaMalloc(&d_o1[s], (size_t)band * w * 16);
+		if (e == cudaSuccess) e = cudaMalloc(&d_o2[s], (size_t)band * w * 16);
+	}
+	int c = 0;
+	for (int64_t r0 = 0; r0 < h && e == cudaSuccess; r0 += band, ++c) {
+		int s = c % SLOTS;
+		int64_t rows = h - r0 < band ? h - r0 : band;
+		int64_t bp = rows * w; // band plane size
+		for (int ch = 0; ch < 3 && e == cudaSuccess; ++ch)
+			e = cudaMemcpyAsync(d_in[s] + ch * bp, nmap + ch * npix + r0 * w, (size_t)bp, cudaMemcpyHostToDevice, st[s]);
+		if (e == cudaSuccess) e = launch_nmap_to_leanmap(d_in[s], bp, base_roughness, bias, d_o1[s], d_o2[s], st[s]);
+		for (int ch = 0; ch < 4 && e == cudaSuccess; ++ch) {
+			e = cudaMemcpyAsync(lean1 + ch * npix + r0 * w, d_o1[s] + ch * bp, (size_t)bp * 4, cudaMemcpyDeviceToHost, st[s]);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(lean2 + ch * npix + r0 * w, d_o2[s] + ch * bp, (size_t)bp * 4, cudaMemcpyDeviceToHost, st[s]);
+		}
+	}
+	for (int s = 0; s < SLOTS; ++s) {
+		if (st[s]) {
+			cudaError_t e2 = cudaStreamSynchronize(st[s]);
+			if (e == cudaSuccess) e = e2;
+		}
+		cudaFree(d_in[s]);
+		cudaFree(d_o1[s]);
+		cudaFree(d_o2[s]);
+		if (st[s]) cudaStreamDestroy(st[s]);
+	}
+	if (e != cudaSuccess) return cuda_fail(e, "lean staging");
+	return DJB200_OK;
+}
+
+djb200_status djb200_lrep_to_params(const float *E, int64_t n, djb200_params *out, int mem, void *stream)
+{
+	return map_call(n, {{E, 20}}, {{out, 48}}, mem, stream,
+		[](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_lrep_to_params((const float *)i[0], cn, o[0], st);
+		});
+}
+
+djb200_status djb200_params_to_lrep(const djb200_params *params, int64_t n, float *E, int mem, void *stream)
+{
+	return map_call(n, {{params, 48}}, {{E, 20}}, mem, stream,
+		[](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_params_to_lrep(i[0], cn, (float *)o[0], st);
+		});
+}
+
+djb200_status djb200_leanmap_to_params(const float *lean1, const float *lean2, int32_t w, int32_t h, float bias,
+                                       djb200_params *out, int mem, void *stream)
+{
+	if (w < 0 || h < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative image size");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	int64_t npix = (int64_t)w * h;
+	if (npix == 0) return DJB200_OK;
+	if (!lean1 || !lean2 || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL pointer");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	if (mem == DJB200_MEM_DEVICE) {
+		cudaError_t e = launch_leanmap_to_params(lean1, lean2, npix, bias, out, (cudaStream_t)stream);
+		if (e != cudaSuccess) return cuda_fail(e, "leanmap_to_params launch");
+		return DJB200_OK;
+	}
+	// host: whole maps staged at once (5 used planes of 4 B + 48 B out per texel)
+	float *d1 = nullptr, *d2 = nullptr;
+	void *dp = nullptr;
+	cudaError_t e = cudaMalloc(&d1, (size_t)npix * 16);
+	if (e == cudaSuccess) e = cudaMalloc(&d2, (size_t)npix * 16);
+	if (e == cudaSuccess) e = cudaMalloc(&dp, (size_t)npix * 48);
+	if (e == cudaSuccess) e = cudaMemcpy(d1, lean1, (size_t)npix * 16, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(d2, lean2, (size_t)npix * 16, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = launch_leanmap_to_params(d1, d2, npix, bias, dp, 0);
+	if (e == cudaSuccess) e = cudaMemcpy(out, dp, (size_t)npix * 48, cudaMemcpyDeviceToHost);
+	cudaFree(d1);
+	cudaFree(d2);
+	cudaFree(dp);
+	if (e != cudaSuccess) return cuda_fail(e, "leanmap_to_params staging");
+	return DJB200_OK;
+}
+
+} // extern "C"

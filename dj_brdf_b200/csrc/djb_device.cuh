@@ -1,0 +1,551 @@
+// djb_device.cuh -- device-side numerics of the microfacet / MERL / LEAN paths (sm_100a).
+//
+// Parity contract (DESIGN.md "Numerics"): results must match the reference header compiled as a
+// pinned scalar CPU program (float_t = float, unqualified libm calls bind to the C double
+// functions, no FMA contraction).  So every function below keeps the reference's rounding points:
+// float storage, double sub-expressions exactly where the reference has a double literal, M_PI or
+// a libm call, IEEE division and square root.  This translation unit MUST be compiled with
+// -fmad=false (the build enforces it) and without -use_fast_math; CUDA's double sqrt and
+// division are IEEE-correct, double exp/acos/atan2/sin/cos are within 1-2 ulp of glibc's, which
+// survives the rounding back to float except for ~1e-8 of inputs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace djb200 {
+
+#define DJB_DEV __device__ __forceinline__
+#define DJB_PI 3.14159265358979323846
+
+struct V3 { float x, y, z; };
+
+// device copy of djb200_params / djb::microfacet::params (dj_brdf.h:238-242)
+struct Params {
+	float nx, ny, nz;
+	float a1, a2, phi_a;
+	float ax, ay;
+	float rho, srho;
+	float tx, ty;
+};
+static_assert(sizeof(Params) == 48, "params block must stay 48 bytes");
+
+enum { NDF_BECKMANN = 0, NDF_GGX = 1 };
+enum { FK_IDEAL = 0, FK_SCHLICK = 1, FK_UNPOLARIZED = 2, FK_SGD = 3, FK_SPLINE = 4 };
+
+struct FresnelDev {
+	float v[6];
+	const float *pts; // device (or shared) pointer to n*3 floats
+	int npts;
+};
+
+// ---- vec3 algebra, dj_brdf.h:597-637 ---------------------------------------------------------
+DJB_DEV V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+DJB_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+DJB_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+DJB_DEV V3 scale(float k, V3 a) { return mk(k * a.x, k * a.y, k * a.z); }
+DJB_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+DJB_DEV V3 cross(V3 a, V3 b)
+{
+	return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// (1.0 / b) rounded to float: the scalar of `vec3 / float_t` (:601)
+DJB_DEV float rcp_via_double(float b) { return (float)(1.0 / (double)b); }
+// inversesqrt(): 1.0 / sqrt(x) in double, rounded once to float (:612-616)
+DJB_DEV float inv_sqrt(float x) { return (float)(1.0 / sqrt((double)x)); }
+DJB_DEV V3 normalize(V3 v) { return scale(inv_sqrt(dot(v, v)), v); }
+// djb::min/max/sat templates (:574-576), including their NaN pass-through
+DJB_DEV float fmin_ref(float a, float b) { return a < b ? a : b; }
+DJB_DEV float fmax_ref(float a, float b) { return a > b ? a : b; }
+DJB_DEV float sat_ref(float x) { return fmin_ref(1.0f, fmax_ref(0.0f, x)); }
+
+// vec3(theta, phi), :589-595
+DJB_DEV V3 spherical(float theta, float phi)
+{
+	double st, ct, sp, cp;
+	sincos((double)theta, &st, &ct);
+	sincos((double)phi, &sp, &cp);
+	float s = (float)st;
+	return mk((float)((double)s * cp), (float)((double)s * sp), (float)ct);
+}
+
+// xyz_to_theta_phi, :650-661
+DJB_DEV void to_theta_phi(V3 p, float &theta, float &phi)
+{
+	double z = (double)p.z;
+	if (z > 0.99999) {
+		theta = 0.0f;
+		phi = 0.0f;
+	} else if (z < -0.99999) {
+		theta = (float)DJB_PI;
+		phi = 0.0f;
+	} else {
+		theta = (float)acos(z);
+		phi = (float)atan2((double)p.y, (double)p.x);
+	}
+}
+
+// ---- special functions ------------------------------------------------------------------------
+// djb::erf (A&S 7.1.26, :667-688).  `e` must be exp((double)(-x*x)), shared with the caller.
+DJB_DEV float erf_as(float x, double e)
+{
+	const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f;
+	const float a4 = -1.453152027f, a5 = 1.061405429f, p = 0.3275911f;
+	float sgn = (x < 0.0f) ? -1.0f : 1.0f;
+	x = fabsf(x);
+	float t = (float)(1.0 / (1.0 + (double)(p * x)));
+	float poly = ((((a5 * t + a4) * t) + a3) * t + a2) * t + a1;
+	float y = (float)(1.0 - (double)(poly * t) * e);
+	return sgn * y;
+}
+DJB_DEV float erf_as(float x) { return erf_as(x, exp((double)(-x * x))); }
+
+// single-precision libm calls of the reference (logf/expf/powf, :695, 1917, 1935): glibc returns
+// the correctly rounded float in all but a ~1e-3 fraction of cases, so they are mirrored by
+// evaluating in double and rounding once.
+DJB_DEV float logf_cr(float x) { return (float)log((double)x); }
+DJB_DEV float expf_cr(float x) { return (float)exp((double)x); }
+DJB_DEV float powf_cr(float x, float y) { return (float)pow((double)x, (double)y); }
+
+// djb::erfinv (Giles), :691-721
+DJB_DEV float erfinv_giles(float u)
+{
+	float w = -logf_cr((1.0f - u) * (1.0f + u)), p;
+	if (w < 5.0f) {
+		w = w - 2.5f;
+		p = 2.81022636e-08f;
+		p = 3.43273939e-07f + p * w;
+		p = -3.5233877e-06f + p * w;
+		p = -4.39150654e-06f + p * w;
+		p = 0.00021858087f + p * w;
+		p = -0.00125372503f + p * w;
+		p = -0.00417768164f + p * w;
+		p = 0.246640727f + p * w;
+		p = 1.50140941f + p * w;
+	} else {
+		w = (float)(sqrt((double)w) - 3.0);
+		p = -0.000200214257f;
+		p = 0.000100950558f + p * w;
+		p = 0.00134934322f + p * w;
+		p = -0.00367342844f + p * w;
+		p = 0.00573950773f + p * w;
+		p = -0.0076224613f + p * w;
+		p = 0.00943887047f + p * w;
+		p = 1.00167406f + p * w;
+		p = 2.83297682f + p * w;
+	}
+	return p * u;
+}
+
+// ---- rotations and the half / difference frame, :754-793 -------------------------------------
+DJB_DEV V3 rotate_about(V3 x, V3 axis, float angle)
+{
+	double sd, cd;
+	sincos((double)angle, &sd, &cd);
+	float c = (float)cd, s = (float)sd;
+	V3 out = scale(c, x);
+	float t1 = dot(axis, x);
+	float t2 = (float)((double)t1 * (1.0 - (double)c));
+	out = out + scale(t2, axis);
+	out = out + scale(s, cross(axis, x));
+	return out;
+}
+
+DJB_DEV void io_to_hd(V3 i, V3 o, V3 &h, V3 &d, float &theta_h)
+{
+	float ph;
+	h = normalize(i + o);
+	to_theta_phi(h, theta_h, ph);
+	V3 tmp = rotate_about(i, mk(0.f, 0.f, 1.f), -ph);
+	d = normalize(rotate_about(tmp, mk(0.f, 1.f, 0.f), -theta_h));
+}
+
+DJB_DEV void hd_to_io(V3 h, V3 d, V3 &i, V3 &o)
+{
+	float th, ph;
+	to_theta_phi(h, th, ph);
+	V3 tmp = rotate_about(d, mk(0.f, 1.f, 0.f), th);
+	i = normalize(rotate_about(tmp, mk(0.f, 0.f, 1.f), ph));
+	float k = (float)(2.0 * (double)dot(i, h));
+	o = normalize(scale(k, h) - i);
+}
+
+// ---- Fresnel, :1292-1344 -----------------------------------------------------------------------
+DJB_DEV float unpolarized_channel(float c, float n)
+{
+	float g = (float)sqrt((double)(n * n + c * c) - 1.0);
+	float t1 = (float)((double)(c * (g + c)) - 1.0);
+	float t2 = (float)((double)(c * (g - c)) + 1.0);
+	float t3 = (t1 * t1) / (t2 * t2);
+	float t4 = ((g - c) * (g - c)) / ((g + c) * (g + c));
+	return (float)((0.5 * (double)t4) * (1.0 + (double)t3));
+}
+
+// spline::eval<vec3> with uwrap_edge, :1191-1218
+DJB_DEV V3 spline_rgb(const float *pts, int n, float u)
+{
+	float x = u * (float)n - u;
+	float ip = truncf(x); // modf(): integral part towards zero, fraction keeps the sign
+	float frac = x - ip;
+	int i1 = (int)ip, i2 = (int)ip + 1;
+	i1 = i1 >= n ? n - 1 : (i1 < 0 ? 0 : i1);
+	i2 = i2 >= n ? n - 1 : (i2 < 0 ? 0 : i2);
+	V3 p1 = mk(pts[3 * i1], pts[3 * i1 + 1], pts[3 * i1 + 2]);
+	V3 p2 = mk(pts[3 * i2], pts[3 * i2 + 1], pts[3 * i2 + 2]);
+	return p1 + scale(frac, p2 - p1);
+}
+
+// spline::eval<float_t> with uwrap_edge (tabulated p22 / sigma / cdf / qf), :1207-1218
+DJB_DEV float spline_f(const float *pts, int n, float u)
+{
+	float x = u * (float)n - u;
+	float ip = truncf(x);
+	float frac = x - ip;
+	int i1 = (int)ip, i2 = (int)ip + 1;
+	i1 = i1 >= n ? n - 1 : (i1 < 0 ? 0 : i1);
+	i2 = i2 >= n ? n - 1 : (i2 < 0 ? 0 : i2);
+	float p1 = pts[i1], p2 = pts[i2];
+	return p1 + frac * (p2 - p1);
+}
+
+template <int FK>
+DJB_DEV V3 fresnel_eval(const FresnelDev &f, float c)
+{
+	if (FK == FK_SCHLICK) {
+		float c1 = (float)(1.0 - (double)c), c2 = c1 * c1, c5 = c2 * c2 * c1;
+		return mk(f.v[0] + c5 * (1.0f - f.v[0]), f.v[1] + c5 * (1.0f - f.v[1]), f.v[2] + c5 * (1.0f - f.v[2]));
+	} else if (FK == FK_UNPOLARIZED) {
+		return mk(unpolarized_channel(c, f.v[0]), unpolarized_channel(c, f.v[1]), unpolarized_channel(c, f.v[2]));
+	} else if (FK == FK_SGD) {
+		float pw = (float)pow(1.0 - (double)c, 5.0);
+		return mk((f.v[0] - c * f.v[3]) + pw * (1.0f - f.v[0]), (f.v[1] - c * f.v[4]) + pw * (1.0f - f.v[1]),
+		          (f.v[2] - c * f.v[5]) + pw * (1.0f - f.v[2]));
+	} else if (FK == FK_SPLINE) {
+		float u = (float)(2.0 * acos((double)c) / DJB_PI);
+		return spline_rgb(f.pts, f.npts, u);
+	}
+	return mk(1.0f, 1.0f, 1.0f);
+}
+
+// ---- standard radial distributions ------------------------------------------------------------
+template <int NDF>
+DJB_DEV float p22_radial(float r2)
+{
+	if (NDF == NDF_GGX) { // :2056-2060
+		float t = (float)(1.0 + (double)r2);
+		return (float)(1.0 / (DJB_PI * (double)t * (double)t));
+	}
+	return (float)(exp((double)(-r2)) / DJB_PI); // :1866-1869
+}
+
+template <int NDF>
+DJB_DEV float sigma_std_radial(float c)
+{
+	if (NDF == NDF_GGX) return (float)((1.0 + (double)c) / 2.0); // :2062-2065
+	// beckmann, :1871-1879
+	if (c == 1.0f) return 1.0f;
+	float s = (float)sqrt(1.0 - (double)(c * c));
+	float nu = c / s;
+	double e = exp((double)(-nu * nu)); // also the exp() inside djb::erf: (-|nu|)*|nu| == (-nu)*nu
+	float tmp = (float)(e * (double)inv_sqrt((float)DJB_PI));
+	return (float)(((double)c * (1.0 + (double)erf_as(nu, e)) + (double)(s * tmp)) / 2.0);
+}
+
+// microfacet::sigma, :1619-1631 (only the z of the normalised warped direction is consumed)
+template <int NDF>
+DJB_DEV float mf_sigma(const Params &p, V3 k)
+{
+	float a = k.x * p.ax + k.y * p.ay * p.rho;
+	float b = k.y * p.ay * p.srho;
+	float c = k.z - k.x * p.tx - k.y * p.ty;
+	float nrm = (float)sqrt((double)(a * a + b * b + c * c));
+	float cz = rcp_via_double(nrm) * c;
+	return nrm * sigma_std_radial<NDF>(cz);
+}
+
+// :1633-1642
+template <int NDF>
+DJB_DEV float mf_g1(const Params &p, V3 k)
+{
+	float test = dot(k, mk(p.nx, p.ny, p.nz));
+	if (test > 0.0f) return k.z / mf_sigma<NDF>(p, k);
+	return 0.0f;
+}
+
+// :1644-1665
+template <int NDF>
+DJB_DEV float mf_gaf(const Params &p, bool shadow, V3 i, V3 o)
+{
+	float g1o = mf_g1<NDF>(p, o);
+	if (shadow) {
+		float g1i = mf_g1<NDF>(p, i);
+		float t = g1i * g1o;
+		if (t > 0.0f) return t / (g1i + g1o - t);
+		return 0.0f;
+	}
+	return g1o;
+}
+
+// :1574-1587
+template <int NDF>
+DJB_DEV float mf_p22(const Params &p, float x, float y)
+{
+	x -= p.tx;
+	y -= p.ty;
+	float nrm = p.ax * p.ay * p.srho;
+	float xs = x / p.ax;
+	float t1 = p.ax * y - p.rho * p.ay * x;
+	float ys = t1 / nrm; // tmp2 of the reference is the same product as nrm
+	return p22_radial<NDF>(xs * xs + ys * ys) / nrm;
+}
+
+// :1559-1570
+template <int NDF>
+DJB_DEV float mf_ndf(const Params &p, V3 h)
+{
+	if (h.z > 1e-4f) {
+		float c2 = h.z * h.z, c4 = c2 * c2;
+		float sx = -h.x / h.z, sy = -h.y / h.z;
+		return mf_p22<NDF>(p, sx, sy) / c4;
+	}
+	return 0.0f;
+}
+
+// :1602-1615
+template <int NDF>
+DJB_DEV float mf_vndf(const Params &p, V3 h, V3 k)
+{
+	float kh = dot(k, h);
+	if (kh > 0.0f) return kh * mf_ndf<NDF>(p, h) / mf_sigma<NDF>(p, k);
+	return 0.0f;
+}
+
+// microfacet::evalp, :1529-1547 -- h = normalize(i + o) is supplied by the caller because it does
+// not depend on the params block
+template <int NDF, int FK>
+DJB_DEV V3 mf_evalp(const Params &p, const FresnelDev &f, bool shadow, V3 i, V3 o, V3 h)
+{
+	float G = mf_gaf<NDF>(p, shadow, i, o);
+	if (G > 0.0f) {
+		float cd = sat_ref(dot(o, h));
+		V3 Fr = fresnel_eval<FK>(f, cd);
+		float Dn = mf_ndf<NDF>(p, h);
+		return scale((float)((double)(Dn * G) / (4.0 * (double)o.z)), Fr);
+	}
+	return mk(0.f, 0.f, 0.f);
+}
+
+// :1713-1730 (beckmann and ggx both take the Smith-VNDF branch)
+template <int NDF>
+DJB_DEV float mf_pdf(const Params &p, bool shadow, V3 i, V3 o, V3 h)
+{
+	float G = mf_gaf<NDF>(p, shadow, i, o);
+	if (G > 0.0f) return (float)((double)mf_vndf<NDF>(p, h, o) / (4.0 * (double)dot(i, h)));
+	return 0.0f;
+}
+
+// ---- visible-normal sampling -------------------------------------------------------------------
+// ggx::qf2_radial, :2089-2119
+DJB_DEV float ggx_qf2(float u, float ck, float sk)
+{
+	float st = (float)((double)u * (1.0 + (double)ck) - 1.0);
+	float ct = (float)sqrt(1.0 - (double)(st * st));
+	if ((double)ct > 0.707107) {
+		float tt = st / ct;
+		if ((double)sk < 0.707107) {
+			float tk = sk / ck;
+			return (float)((double)(-(tt + tk)) / (1.0 - (double)(tt * tk)));
+		} else {
+			float kk = ck / sk;
+			return (float)((1.0 + (double)(tt * kk)) / (double)(tt - kk));
+		}
+	} else {
+		float cot = ct / st;
+		if ((double)sk < 0.707107) {
+			float tk = sk / ck;
+			return (float)((1.0 + (double)(tk * cot)) / (double)(tk - cot));
+		} else {
+			float kk = ck / sk;
+			return (float)((double)(cot + kk) / (1.0 - (double)(cot * kk)));
+		}
+	}
+}
+
+// ggx::qf3_radial + qf3_rational_approx, :2121-2146
+DJB_DEV float ggx_qf3(float u, float qf2)
+{
+	float alpha = (float)sqrt(1.0 + (double)(qf2 * qf2));
+	float S;
+	if ((double)u < 0.5) {
+		u = (float)(2.0 * (0.5 - (double)u));
+		S = -1.0f;
+	} else {
+		u = (float)(2.0 * ((double)u - 0.5));
+		S = 1.0f;
+	}
+	double du = (double)u;
+	float pn = (float)(du * (du * (du * (-0.365728915865723) + 0.790235037209296) - 0.424965825137544)
+	                   + 0.000152998850436920);
+	float qn = (float)(du * (du * (du * (du * 0.169507819808272 - 0.397203533833404) - 0.232500544458471) + 1.0)
+	                   - 0.539825872510702);
+	return S * alpha * (pn / qn);
+}
+
+// beckmann::qf2_radial, :1897-1952
+DJB_DEV float beckmann_qf2(float u, float ck, float sk)
+{
+	const float sqrt_pi_inv = (float)(1.0 / sqrt(DJB_PI));
+	float cot = ck / sk, tan_k = sk / ck;
+	float a = -1.0f, c = erf_as(cot);
+	u = fmax_ref(u, 1e-6f);
+	float fit = 1.0f + ck * (-0.876f + ck * (0.4265f - 0.0594f * ck));
+	float b = c - (1.0f + c) * powf_cr(1.0f - u, fit);
+	float normalization =
+		(float)(1.0 / ((double)(1.0f + c) + (double)(sqrt_pi_inv * tan_k) * exp((double)(-cot * cot))));
+	int it = 0;
+	while (++it < 10) {
+		if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+		float ie = erfinv_giles(b);
+		float value = normalization * (1.0f + b + sqrt_pi_inv * tan_k * expf_cr(-ie * ie)) - u;
+		float derivative = normalization * (1.0f - ie * tan_k);
+		if (fabsf(value) < 1e-5f) break;
+		if (value > 0.0f) c = b; else a = b;
+		b -= value / derivative;
+	}
+	return erfinv_giles(fmax_ref(-0.9999f, b));
+}
+
+// radial::sample_vp22_std_smith, :1818-1846
+template <int NDF>
+DJB_DEV void sample_std_slopes(float u1, float u2, V3 k, float &xs, float &ys)
+{
+	float ck = k.z;
+	float sk = k.z < 1.0f ? (float)sqrt(1.0 - (double)(k.z * k.z)) : 0.0f;
+	float tx, ty;
+	if (NDF == NDF_GGX) {
+		tx = ggx_qf2(u1, ck, sk);
+		ty = ggx_qf3(u2, tx);
+	} else {
+		tx = beckmann_qf2(u1, ck, sk);
+		ty = erfinv_giles((float)(2.0 * (double)u2 - 1.0)); // qf3_radial -> qf1, :1891-1894
+	}
+	if (sk == 0.0f) {
+		xs = tx;
+		ys = ty;
+	} else {
+		float nrm = inv_sqrt(k.x * k.x + k.y * k.y);
+		float cp = k.x * nrm, sp = k.y * nrm;
+		xs = cp * tx - sp * ty;
+		ys = sp * tx + cp * ty;
+	}
+}
+
+// microfacet::sample, :1669-1709
+template <int NDF>
+DJB_DEV V3 mf_sample(const Params &p, float u1, float u2, V3 o)
+{
+	u1 = sat_ref(u1) * 0.99998f + 0.00001f;
+	u2 = sat_ref(u2) * 0.99998f + 0.00001f;
+	float a = o.x * p.ax + o.y * p.ay * p.rho;
+	float b = o.y * p.ay * p.srho;
+	float c = o.z - o.x * p.tx - o.y * p.ty;
+	V3 os = normalize(mk(a, b, c));
+	if (os.z > 0.0f) {
+		float txm, tym;
+		sample_std_slopes<NDF>(u1, u2, os, txm, tym);
+		float txh = p.ax * txm + p.tx;
+		float chol = p.rho * txm + p.srho * tym;
+		float tyh = p.ay * chol + p.ty;
+		V3 h = normalize(mk(-txh, -tyh, 1.0f));
+		float k = (float)(2.0 * (double)dot(o, h));
+		return scale(k, h) - o;
+	}
+	return mk(0.f, 0.f, 1.f);
+}
+
+// microfacet::evalp_is, :1734-1765
+template <int NDF, int FK>
+DJB_DEV V3 mf_evalp_is(const Params &p, const FresnelDev &f, bool shadow, float u1, float u2, V3 o,
+                       V3 &i_out, float &pdf_out)
+{
+	V3 i = mf_sample<NDF>(p, u1, u2, o);
+	V3 h = normalize(i + o);
+	float G = mf_gaf<NDF>(p, shadow, i, o);
+	pdf_out = 0.0f;
+	i_out = mk(0.f, 0.f, 0.f);
+	if (G > 0.0f) {
+		float cd = sat_ref(dot(o, h));
+		i_out = i;
+		V3 Fr = fresnel_eval<FK>(f, cd);
+		float g1 = mf_g1<NDF>(p, o);
+		pdf_out = (float)((double)mf_vndf<NDF>(p, h, o) / (4.0 * (double)cd));
+		return scale(G / g1, Fr);
+	}
+	return mk(0.f, 0.f, 0.f);
+}
+
+// ---- params construction on the device (E10 / L2), dj_brdf.h:1378-1393, 1437-1474 ---------------
+DJB_DEV void params_from_pdf(float ax, float ay, float rho, float tx, float ty, Params &p)
+{
+	p.ax = ax;
+	p.ay = ay;
+	p.rho = rho;
+	p.srho = (float)sqrt(1.0 - (double)(rho * rho));
+	float qx = ax * ax, qy = ay * ay;
+	float cov = (float)((double)(rho * ax * ay) * 2.0);
+	float t1 = qx + qy, t2 = qx - qy;
+	float t3 = (float)sqrt((double)(t2 * t2 + cov * cov));
+	p.a1 = (float)sqrt(0.5 * (double)(t1 + t3));
+	p.a2 = (float)sqrt(0.5 * (double)(t1 - t3));
+	p.phi_a = (cov != 0.0f) ? (float)atan((double)((qx - qy - t3) / cov)) : 0.0f;
+	p.tx = tx;
+	p.ty = ty;
+	V3 n = normalize(mk(-tx, -ty, 1.0f));
+	p.nx = n.x;
+	p.ny = n.y;
+	p.nz = n.z;
+}
+
+// beckmann::lrep_to_params, :1976-1990
+DJB_DEV void lrep_to_params(float E1, float E2, float E3, float E4, float E5, Params &p)
+{
+	float t1 = fmax_ref(0.0f, E3 - E1 * E1);
+	float t2 = fmax_ref(0.0f, E4 - E2 * E2);
+	double sx = sqrt(2.0 * (double)t1), sy = sqrt(2.0 * (double)t2);
+	float ax = (float)(1e-5 > sx ? 1e-5 : sx);
+	float ay = (float)(1e-5 > sy ? 1e-5 : sy);
+	float rho = 2.0f * (E5 - E1 * E2) / (ax * ay);
+	rho = fmin_ref(0.99f, fmax_ref(-0.99f, rho));
+	params_from_pdf(ax, ay, rho, E1, E2, p);
+}
+
+// ---- MERL index arithmetic, :906-957 (IEEE double mul/div/sqrt + truncation: bit exact) ---------
+DJB_DEV int merl_theta_half_index(float th)
+{
+	if (th <= 0.0f) return 0;
+	float deg = (float)(((double)th / (DJB_PI / 2.0)) * 90.0);
+	float t = deg * 90.0f;
+	t = (float)sqrt((double)t);
+	int r = (int)t;
+	return r < 0 ? 0 : (r >= 90 ? 89 : r);
+}
+DJB_DEV int merl_theta_diff_index(float td)
+{
+	int t = (int)((double)td / (DJB_PI * 0.5) * 90.0);
+	return t < 0 ? 0 : (t < 89 ? t : 89);
+}
+DJB_DEV int merl_phi_diff_index(float pd)
+{
+	if (pd < 0.0f) pd = (float)((double)pd + DJB_PI);
+	int t = (int)((double)pd / DJB_PI * 360.0 / 2.0);
+	return t < 0 ? 0 : (t < 179 ? t : 179);
+}
+DJB_DEV int merl_cell(V3 i, V3 o)
+{
+	V3 h, d;
+	float th, td, pd;
+	io_to_hd(i, o, h, d, th); // merl::eval recomputes theta_h from h: same value
+	to_theta_phi(d, td, pd);
+	return merl_phi_diff_index(pd) + merl_theta_diff_index(td) * 180 + merl_theta_half_index(th) * 16200;
+}
+
+} // namespace djb200

@@ -1,0 +1,50 @@
+// djb_internal.h -- declarations shared by the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/djb200.h"
+
+namespace djb200 {
+
+enum MfOp { OP_EVAL = 0, OP_EVALP = 1, OP_PDF = 2, OP_SAMPLE = 3, OP_EVALP_IS = 4 };
+
+// One launch of a microfacet query over device-resident arrays.
+struct MfLaunch {
+	int op, ndf, shadow, fresnel_kind;
+	float fv[6];
+	const float *spline_pts; // device
+	int spline_n;
+	const void *params;      // device, djb200_params blocks
+	int64_t n_params;
+	int layout;              // djb200_params_layout
+	const float *a;          // wi (eval/evalp/pdf) or u (sample/evalp_is)
+	const float *b;          // wo
+	int64_t n;               // pairs in this launch
+	int64_t out_stride;      // elements between consecutive params blocks in the outputs (BROADCAST)
+	float *out0, *out1, *out2;
+};
+
+extern std::atomic<uint64_t> g_kernel_launches;
+int sm_count();
+
+cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st);
+
+// tables / frames / LEAN (kernels_tables.cu)
+cudaError_t launch_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d, cudaStream_t st);
+cudaError_t launch_hd_to_io(const float *h, const float *d, int64_t n, float *wi, float *wo, cudaStream_t st);
+cudaError_t launch_merl_convert(const double *samples_dev, float4 *cells_dev, cudaStream_t st);
+cudaError_t launch_merl_eval(const float4 *cells, const float *wi, const float *wo, int64_t n, float *out,
+                             cudaStream_t st);
+cudaError_t launch_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out, cudaStream_t st);
+cudaError_t launch_utia_convert(const double *raw_dev, float *table_dev, cudaStream_t st);
+cudaError_t launch_utia_eval(const float *table, const float *wi, const float *wo, int64_t n, float *out,
+                             cudaStream_t st);
+cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base_roughness, float bias,
+                                   float *lean1, float *lean2, cudaStream_t st);
+cudaError_t launch_lrep_to_params(const float *E, int64_t n, void *out_params, cudaStream_t st);
+cudaError_t launch_params_to_lrep(const void *params, int64_t n, float *E, cudaStream_t st);
+cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int64_t npix, float bias,
+                                     void *out_params, cudaStream_t st);
+
+} // namespace djb200

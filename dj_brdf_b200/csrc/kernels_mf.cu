@@ -1,0 +1,253 @@
+// kernels_mf.cu -- batched microfacet eval / evalp / pdf / sample / evalp_is (SURVEY.md rows E1-E10,
+// P1, S1-S5).  One thread owns one (wi, wo) pair and walks the params blocks staged in shared
+// memory, so a pair is read from HBM once however many materials it is evaluated under; the
+// half vector and the two double reciprocals that do not depend on the material are hoisted.
+//
+// HBM traffic per (pair, material): (24 + 12 M) / M bytes for eval -- 13.5 B at M = 16.
+// The kernel is bound by FP64 issue, not by HBM (DESIGN.md "Rooflines"): matching the reference to
+// the bit needs IEEE double sqrt/div/exp at its rounding points.
+#include "djb_device.cuh"
+#include "djb_internal.h"
+
+namespace djb200 {
+
+constexpr int MF_THREADS = 256;
+constexpr int MF_MAX_SMEM_PARAMS = 256; // 12 KB of shared memory
+constexpr int MF_MAX_SMEM_SPLINE = 256; // points, 3 KB
+
+struct MfKernelArgs {
+	int shadow, fresnel_kind;
+	FresnelDev fr;
+	const Params *params;
+	int n_params;
+	const float *a, *b;
+	long long n, out_stride;
+	float *out0, *out1, *out2;
+};
+
+DJB_DEV V3 fresnel_rt(int kind, const FresnelDev &f, float c)
+{
+	switch (kind) {
+	case FK_SCHLICK: return fresnel_eval<FK_SCHLICK>(f, c);
+	case FK_UNPOLARIZED: return fresnel_eval<FK_UNPOLARIZED>(f, c);
+	case FK_SGD: return fresnel_eval<FK_SGD>(f, c);
+	case FK_SPLINE: return fresnel_eval<FK_SPLINE>(f, c);
+	default: return mk(1.f, 1.f, 1.f);
+	}
+}
+
+// evalp with a run-time Fresnel kind (uniform across the grid, so the switch never diverges)
+template <int NDF>
+DJB_DEV V3 evalp_rt(const Params &p, int fk, const FresnelDev &f, bool shadow, V3 i, V3 o, V3 h)
+{
+	float G = mf_gaf<NDF>(p, shadow, i, o);
+	if (G > 0.0f) {
+		float cd = sat_ref(dot(o, h));
+		V3 Fr = fresnel_rt(fk, f, cd);
+		float Dn = mf_ndf<NDF>(p, h);
+		return scale((float)((double)(Dn * G) / (4.0 * (double)o.z)), Fr);
+	}
+	return mk(0.f, 0.f, 0.f);
+}
+
+template <int NDF>
+DJB_DEV V3 evalp_is_rt(const Params &p, int fk, const FresnelDev &f, bool shadow, float u1, float u2, V3 o,
+                       V3 &i_out, float &pdf_out)
+{
+	V3 i = mf_sample<NDF>(p, u1, u2, o);
+	V3 h = normalize(i + o);
+	float G = mf_gaf<NDF>(p, shadow, i, o);
+	pdf_out = 0.0f;
+	i_out = mk(0.f, 0.f, 0.f);
+	if (G > 0.0f) {
+		float cd = sat_ref(dot(o, h));
+		i_out = i;
+		V3 Fr = fresnel_rt(fk, f, cd);
+		float g1 = mf_g1<NDF>(p, o);
+		pdf_out = (float)((double)mf_vndf<NDF>(p, h, o) / (4.0 * (double)cd));
+		return scale(G / g1, Fr);
+	}
+	return mk(0.f, 0.f, 0.f);
+}
+
+DJB_DEV void st3(float *p, long long k, V3 v)
+{
+	p[3 * k] = v.x;
+	p[3 * k + 1] = v.y;
+	p[3 * k + 2] = v.z;
+}
+
+// one (pair, params) query; `h` and `inv_iz` are material independent and precomputed by the caller
+template <int NDF, int OP>
+DJB_DEV void mf_query(const MfKernelArgs &A, const FresnelDev &fr, const Params &p, long long slot, V3 va, V3 o,
+                      V3 h, float inv_iz)
+{
+	const bool shadow = A.shadow != 0;
+	if (OP == OP_EVAL) {
+		V3 e = evalp_rt<NDF>(p, A.fresnel_kind, fr, shadow, va, o, h);
+		st3(A.out0, slot, scale(inv_iz, e)); // evalp / i.z, dj_brdf.h:1554
+	} else if (OP == OP_EVALP) {
+		st3(A.out0, slot, evalp_rt<NDF>(p, A.fresnel_kind, fr, shadow, va, o, h));
+	} else if (OP == OP_PDF) {
+		A.out0[slot] = mf_pdf<NDF>(p, shadow, va, o, h);
+	} else if (OP == OP_SAMPLE) {
+		st3(A.out0, slot, mf_sample<NDF>(p, va.x, va.y, o));
+	} else {
+		V3 iv;
+		float pdf;
+		V3 w = evalp_is_rt<NDF>(p, A.fresnel_kind, fr, shadow, va.x, va.y, o, iv, pdf);
+		if (A.out0) st3(A.out0, slot, w);
+		if (A.out1) st3(A.out1, slot, iv);
+		if (A.out2) A.out2[slot] = pdf;
+	}
+}
+
+template <int NDF, int OP>
+DJB_DEV void load_pair(const MfKernelArgs &A, long long k, V3 &va, V3 &o, V3 &h, float &inv_iz)
+{
+	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
+	if (uses_u) {
+		float2 u = reinterpret_cast<const float2 *>(A.a)[k];
+		va = mk(u.x, u.y, 0.f);
+	} else {
+		va = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
+	}
+	o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
+	h = mk(0.f, 0.f, 0.f);
+	inv_iz = 0.f;
+	if (!uses_u) {
+		h = normalize(va + o);
+		if (OP == OP_EVAL) inv_iz = rcp_via_double(va.z);
+	}
+}
+
+// BROADCAST layout: every pair under every params block; output (m, k) at m * out_stride + k.
+template <int NDF, int OP>
+__global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A)
+{
+	__shared__ Params s_params[MF_MAX_SMEM_PARAMS];
+	__shared__ float s_spline[3 * MF_MAX_SMEM_SPLINE];
+
+	// stage the per-material parameters (48 B each) and the Fresnel spline once per CTA
+	{
+		const float *src = reinterpret_cast<const float *>(A.params);
+		float *dst = reinterpret_cast<float *>(s_params);
+		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
+	}
+	FresnelDev fr = A.fr;
+	if (A.fresnel_kind == FK_SPLINE && fr.npts <= MF_MAX_SMEM_SPLINE) {
+		for (int t = threadIdx.x; t < fr.npts * 3; t += blockDim.x) s_spline[t] = A.fr.pts[t];
+		fr.pts = s_spline;
+	}
+	__syncthreads();
+
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		V3 va, o, h;
+		float inv_iz;
+		load_pair<NDF, OP>(A, k, va, o, h, inv_iz);
+		for (int m = 0; m < A.n_params; ++m)
+			mf_query<NDF, OP>(A, fr, s_params[m], (long long)m * A.out_stride + k, va, o, h, inv_iz);
+	}
+}
+
+// PER_PAIR layout: pair k under params block k (roughness from textures at every shading point).
+template <int NDF, int OP>
+__global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
+{
+	__shared__ float s_spline[3 * MF_MAX_SMEM_SPLINE];
+	FresnelDev fr = A.fr;
+	if (A.fresnel_kind == FK_SPLINE && fr.npts <= MF_MAX_SMEM_SPLINE) {
+		for (int t = threadIdx.x; t < fr.npts * 3; t += blockDim.x) s_spline[t] = A.fr.pts[t];
+		fr.pts = s_spline;
+		__syncthreads();
+	}
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		V3 va, o, h;
+		float inv_iz;
+		load_pair<NDF, OP>(A, k, va, o, h, inv_iz);
+		const float4 *pp = reinterpret_cast<const float4 *>(A.params + k); // 48 B blocks: 16-B aligned
+		float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
+		Params p;
+		p.nx = q0.x; p.ny = q0.y; p.nz = q0.z; p.a1 = q0.w;
+		p.a2 = q1.x; p.phi_a = q1.y; p.ax = q1.z; p.ay = q1.w;
+		p.rho = q2.x; p.srho = q2.y; p.tx = q2.z; p.ty = q2.w;
+		mf_query<NDF, OP>(A, fr, p, k, va, o, h, inv_iz);
+	}
+}
+
+template <int NDF, int OP>
+static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
+{
+	MfKernelArgs A;
+	A.shadow = L.shadow;
+	A.fresnel_kind = L.fresnel_kind;
+	for (int k = 0; k < 6; ++k) A.fr.v[k] = L.fv[k];
+	A.fr.pts = L.spline_pts;
+	A.fr.npts = L.spline_n;
+	A.a = L.a;
+	A.b = L.b;
+	A.n = L.n;
+	A.out_stride = L.out_stride;
+	if (L.n <= 0) return cudaSuccess;
+
+	// persistent grid-stride launch: a whole number of waves (SM count x resident CTAs per SM)
+	long long want = (L.n + MF_THREADS - 1) / MF_THREADS;
+	static int resident_bc = 0, resident_pp = 0;
+	if (!resident_bc) {
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_bc, mf_broadcast_kernel<NDF, OP>, MF_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_pp, mf_perpair_kernel<NDF, OP>, MF_THREADS, 0);
+		if (resident_bc < 1) resident_bc = 1;
+		if (resident_pp < 1) resident_pp = 1;
+	}
+	long long cap = (long long)sm_count() * (L.layout == DJB200_PARAMS_PER_PAIR ? resident_pp : resident_bc);
+	int grid = (int)(want < cap ? want : cap);
+
+	if (L.layout == DJB200_PARAMS_PER_PAIR) {
+		A.params = reinterpret_cast<const Params *>(L.params);
+		A.n_params = 1;
+		A.out0 = L.out0; A.out1 = L.out1; A.out2 = L.out2;
+		mf_perpair_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+		return cudaGetLastError();
+	}
+	// BROADCAST: at most MF_MAX_SMEM_PARAMS blocks per launch
+	const int per = (OP == OP_PDF) ? 1 : 3;
+	for (int64_t m0 = 0; m0 < L.n_params; m0 += MF_MAX_SMEM_PARAMS) {
+		int64_t mc = L.n_params - m0 < MF_MAX_SMEM_PARAMS ? L.n_params - m0 : MF_MAX_SMEM_PARAMS;
+		A.params = reinterpret_cast<const Params *>(L.params) + m0;
+		A.n_params = (int)mc;
+		int64_t off = m0 * L.out_stride;
+		A.out0 = L.out0 ? L.out0 + off * per : nullptr;
+		A.out1 = L.out1 ? L.out1 + off * 3 : nullptr;
+		A.out2 = L.out2 ? L.out2 + off : nullptr;
+		mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return e;
+	}
+	return cudaSuccess;
+}
+
+template <int NDF>
+static cudaError_t launch_N(const MfLaunch &L, cudaStream_t st)
+{
+	switch (L.op) {
+	case OP_EVAL: return launch_T<NDF, OP_EVAL>(L, st);
+	case OP_EVALP: return launch_T<NDF, OP_EVALP>(L, st);
+	case OP_PDF: return launch_T<NDF, OP_PDF>(L, st);
+	case OP_SAMPLE: return launch_T<NDF, OP_SAMPLE>(L, st);
+	case OP_EVALP_IS: return launch_T<NDF, OP_EVALP_IS>(L, st);
+	}
+	return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st)
+{
+	if (L.ndf == NDF_GGX) return launch_N<NDF_GGX>(L, st);
+	if (L.ndf == NDF_BECKMANN) return launch_N<NDF_BECKMANN>(L, st);
+	return cudaErrorInvalidValue;
+}
+
+} // namespace djb200

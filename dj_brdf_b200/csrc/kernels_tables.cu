@@ -1,0 +1,381 @@
+// kernels_tables.cu -- MERL / UTIA table lookups, the Rusinkiewicz frame, and the LEAN-map
+// streaming kernels.
+//
+// MERL device layout: one float4 (r, g, b, 0) per cell, already multiplied by the channel scales.
+// The reference computes float(double_sample * SCALE) at every lookup (dj_brdf.h:1012-1014), which
+// is a pure function of the cell, so doing it once at upload time is bit-identical and turns the
+// three 8-byte gathers from three planes 11.7 MB apart into one 16-byte gather.  The 23.3 MB table
+// stays resident in the 126 MB L2; HBM traffic per lookup is the 24 B of directions + 12 B result.
+#include "djb_device.cuh"
+#include "djb_internal.h"
+
+namespace djb200 {
+
+constexpr int TB = 256;
+constexpr int MERL_CELLS = 90 * 90 * 180;
+
+static inline int grid_for(int64_t n, int per_thread = 1)
+{
+	int64_t want = (n + (int64_t)TB * per_thread - 1) / ((int64_t)TB * per_thread);
+	int64_t cap = (int64_t)sm_count() * 8;
+	return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+DJB_DEV V3 ld3(const float *p, long long k) { return mk(p[3 * k], p[3 * k + 1], p[3 * k + 2]); }
+DJB_DEV void st3t(float *p, long long k, V3 v)
+{
+	p[3 * k] = v.x;
+	p[3 * k + 1] = v.y;
+	p[3 * k + 2] = v.z;
+}
+
+// ---- Rusinkiewicz frame ------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB) io_to_hd_kernel(const float *wi, const float *wo, long long n, float *h, float *d)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		V3 hv, dv;
+		float th;
+		io_to_hd(ld3(wi, k), ld3(wo, k), hv, dv, th);
+		st3t(h, k, hv);
+		st3t(d, k, dv);
+	}
+}
+
+__global__ void __launch_bounds__(TB) hd_to_io_kernel(const float *h, const float *d, long long n, float *wi, float *wo)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		V3 iv, ov;
+		hd_to_io(ld3(h, k), ld3(d, k), iv, ov);
+		st3t(wi, k, iv);
+		st3t(wo, k, ov);
+	}
+}
+
+cudaError_t launch_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	io_to_hd_kernel<<<grid_for(n), TB, 0, st>>>(wi, wo, n, h, d);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_hd_to_io(const float *h, const float *d, int64_t n, float *wi, float *wo, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	hd_to_io_kernel<<<grid_for(n), TB, 0, st>>>(h, d, n, wi, wo);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+// ---- MERL ---------------------------------------------------------------------------------------
+// file planes (R, G, B doubles) -> scaled float4 cells; MERL_*_SCALE, dj_brdf.h:897-899
+__global__ void __launch_bounds__(TB) merl_convert_kernel(const double *samples, float4 *cells)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= MERL_CELLS) return;
+	float r = (float)(samples[c] * (1.00 / 1500.0));
+	float g = (float)(samples[c + MERL_CELLS] * (1.15 / 1500.0));
+	float b = (float)(samples[c + 2 * MERL_CELLS] * (1.66 / 1500.0));
+	cells[c] = make_float4(r, g, b, 0.f);
+}
+
+__global__ void __launch_bounds__(TB) merl_eval_kernel(const float4 *__restrict__ cells, const float *__restrict__ wi,
+                                                       const float *__restrict__ wo, long long n, float *__restrict__ out)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		int c = merl_cell(ld3(wi, k), ld3(wo, k));
+		float4 v = __ldg(cells + c);
+		// "below horizon" cells hold negative samples: the whole texel becomes 0 (dj_brdf.h:1016-1021)
+		if (v.x < 0.0f || v.y < 0.0f || v.z < 0.0f) v = make_float4(0.f, 0.f, 0.f, 0.f);
+		st3t(out, k, mk(v.x, v.y, v.z));
+	}
+}
+
+__global__ void __launch_bounds__(TB) merl_index_kernel(const float *__restrict__ wi, const float *__restrict__ wo,
+                                                        long long n, int32_t *__restrict__ out)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+		out[k] = merl_cell(ld3(wi, k), ld3(wo, k));
+}
+
+cudaError_t launch_merl_convert(const double *samples_dev, float4 *cells_dev, cudaStream_t st)
+{
+	merl_convert_kernel<<<(MERL_CELLS + TB - 1) / TB, TB, 0, st>>>(samples_dev, cells_dev);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_merl_eval(const float4 *cells, const float *wi, const float *wo, int64_t n, float *out,
+                             cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	merl_eval_kernel<<<grid_for(n), TB, 0, st>>>(cells, wi, wo, n, out);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	merl_index_kernel<<<grid_for(n), TB, 0, st>>>(wi, wo, n, out);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+// ---- UTIA, dj_brdf.h:1039-1177 ---------------------------------------------------------------------
+constexpr int UT_NTI = 6, UT_NPI = 48, UT_NTV = 6, UT_NPV = 48;
+constexpr int UT_CELLS = 3 * UT_NTI * UT_NPI * UT_NTV * UT_NPV;
+
+// utia::normalize (clamp at 0, scale by the float constant 1/140 in double) followed by the
+// (float_t) cast utia::eval applies to every fetched sample (:1144, 1162-1177)
+__global__ void __launch_bounds__(TB) utia_convert_kernel(const double *raw, float *table)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= UT_CELLS) return;
+	double v = raw[c];
+	v = 0.0 > v ? 0.0 : v;
+	const float k = 1.f / 140.f;
+	table[c] = (float)(v * (double)k);
+}
+
+DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
+{
+	const float r2d = (float)(180.0 / DJB_PI);
+	float ti = (float)((double)r2d * acos((double)i.z)), to = (float)((double)r2d * acos((double)o.z));
+	float pi = (float)((double)r2d * atan2((double)i.y, (double)i.x));
+	float po = (float)((double)r2d * atan2((double)o.y, (double)o.x));
+	if (ti >= 90.0f || to >= 90.0f) return mk(0.f, 0.f, 0.f);
+	while (pi < 0.0f) pi = (float)((double)pi + 360.0);
+	while (po < 0.0f) po = (float)((double)po + 360.0);
+	while (pi >= 360.0f) pi = (float)((double)pi - 360.0);
+	while (po >= 360.0f) po = (float)((double)po - 360.0);
+	int iti[2], itv[2], ipi[2], ipv[2];
+	iti[0] = (int)floor((double)ti / 15.0); iti[1] = iti[0] + 1;
+	if (iti[0] > UT_NTI - 2) { iti[0] = UT_NTI - 2; iti[1] = UT_NTI - 1; }
+	itv[0] = (int)floor((double)to / 15.0); itv[1] = itv[0] + 1;
+	if (itv[0] > UT_NTV - 2) { itv[0] = UT_NTV - 2; itv[1] = UT_NTV - 1; }
+	ipi[0] = (int)floor((double)pi / 7.5); ipi[1] = ipi[0] + 1;
+	ipv[0] = (int)floor((double)po / 7.5); ipv[1] = ipv[0] + 1;
+	float sum, wti[2], wtv[2], wpi[2], wpv[2];
+	wti[1] = ti - (float)(15.0 * iti[0]); wti[0] = (float)(15.0 * iti[1]) - ti;
+	sum = wti[0] + wti[1]; wti[0] /= sum; wti[1] /= sum;
+	wtv[1] = to - (float)(15.0 * itv[0]); wtv[0] = (float)(15.0 * itv[1]) - to;
+	sum = wtv[0] + wtv[1]; wtv[0] /= sum; wtv[1] /= sum;
+	wpi[1] = pi - (float)(7.5 * ipi[0]); wpi[0] = (float)(7.5 * ipi[1]) - pi;
+	sum = wpi[0] + wpi[1]; wpi[0] /= sum; wpi[1] /= sum;
+	wpv[1] = po - (float)(7.5 * ipv[0]); wpv[0] = (float)(7.5 * ipv[1]) - po;
+	sum = wpv[0] + wpv[1]; wpv[0] /= sum; wpv[1] /= sum;
+	if (ipi[1] == UT_NPI) ipi[1] = 0;
+	if (ipv[1] == UT_NPV) ipv[1] = 0;
+	const int nc = UT_NPV * UT_NTV, nr = UT_NPI * UT_NTI;
+	float rgb[3];
+#pragma unroll
+	for (int isp = 0; isp < 3; ++isp) {
+		float acc = 0.0f;
+#pragma unroll
+		for (int a = 0; a < 2; ++a)
+#pragma unroll
+		for (int b = 0; b < 2; ++b)
+#pragma unroll
+		for (int c = 0; c < 2; ++c)
+#pragma unroll
+		for (int d = 0; d < 2; ++d) {
+			float w = wti[a] * wtv[b] * wpi[c] * wpv[d];
+			int idx = isp * nr * nc + nc * (UT_NPI * iti[a] + ipi[c]) + UT_NPV * itv[b] + ipv[d];
+			acc += w * __ldg(tab + idx);
+		}
+		if ((double)acc > 0.0375)
+			acc = (float)pow((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f);
+		else
+			acc /= 12.92f;
+		rgb[isp] = acc * 100.0f;
+	}
+	return mk(fmax_ref(0.0f, rgb[0]), fmax_ref(0.0f, rgb[1]), fmax_ref(0.0f, rgb[2]));
+}
+
+__global__ void __launch_bounds__(TB) utia_eval_kernel(const float *__restrict__ tab, const float *__restrict__ wi,
+                                                       const float *__restrict__ wo, long long n, float *__restrict__ out)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+		st3t(out, k, utia_eval1(tab, ld3(wi, k), ld3(wo, k)));
+}
+
+cudaError_t launch_utia_convert(const double *raw_dev, float *table_dev, cudaStream_t st)
+{
+	utia_convert_kernel<<<(UT_CELLS + TB - 1) / TB, TB, 0, st>>>(raw_dev, table_dev);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_utia_eval(const float *table, const float *wi, const float *wo, int64_t n, float *out,
+                             cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	utia_eval_kernel<<<grid_for(n), TB, 0, st>>>(table, wi, wo, n, out);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+// ---- LEAN maps -------------------------------------------------------------------------------------
+// nmap2leanmap (utils/nmap2leanmap.cpp:18-54, _biased.cpp:23-63): pure float, no libm.  Planar
+// uint8 in, two planar RGBA float images out: 3 B read + 32 B written per texel, nothing reused,
+// so the kernel is a pure HBM stream.  Each thread converts 4 consecutive texels: one 32-bit load
+// per input plane and one 128-bit store per output plane.
+DJB_DEV void lean_texel(float r, float g, float b, float half_br2, float bias, float &e1, float &e2, float &e3,
+                        float &e4, float &e5)
+{
+	float t1 = (r / 255.f) * 2.0f - 1.0f;
+	float t2 = (g / 255.f) * 2.0f - 1.0f;
+	float t3 = b / 255.f;
+	float sx = -t1 / t3, sy = -t2 / t3;
+	e1 = bias != 0.0f ? sx + bias : sx;
+	e2 = bias != 0.0f ? sy + bias : sy;
+	e3 = sx * sx + half_br2;
+	e4 = sy * sy + half_br2;
+	e5 = bias != 0.0f ? sx * sy + bias * bias : sx * sy;
+}
+
+__global__ void __launch_bounds__(TB) lean_kernel_vec4(const uchar4 *__restrict__ pr, const uchar4 *__restrict__ pg,
+                                                       const uchar4 *__restrict__ pb, long long nquads, long long plane,
+                                                       float base_roughness, float bias, float *__restrict__ l1,
+                                                       float *__restrict__ l2)
+{
+	const float half_br2 = 0.5f * base_roughness * base_roughness;
+	const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+		uchar4 r = __ldcs(pr + q), g = __ldcs(pg + q), b = __ldcs(pb + q);
+		float4 E1, E2, E3, E4, E5;
+		lean_texel(r.x, g.x, b.x, half_br2, bias, E1.x, E2.x, E3.x, E4.x, E5.x);
+		lean_texel(r.y, g.y, b.y, half_br2, bias, E1.y, E2.y, E3.y, E4.y, E5.y);
+		lean_texel(r.z, g.z, b.z, half_br2, bias, E1.z, E2.z, E3.z, E4.z, E5.z);
+		lean_texel(r.w, g.w, b.w, half_br2, bias, E1.w, E2.w, E3.w, E4.w, E5.w);
+		float4 *o1 = reinterpret_cast<float4 *>(l1) + q;
+		float4 *o2 = reinterpret_cast<float4 *>(l2) + q;
+		const long long pq = plane / 4;
+		__stcs(o1, E1);
+		__stcs(o1 + pq, E2);
+		__stcs(o1 + 2 * pq, ones);
+		__stcs(o1 + 3 * pq, ones);
+		__stcs(o2, E3);
+		__stcs(o2 + pq, E4);
+		__stcs(o2 + 2 * pq, E5);
+		__stcs(o2 + 3 * pq, ones);
+	}
+}
+
+// scalar variant for planes whose size is not a multiple of 4 texels (alignment of planes 1..3)
+__global__ void __launch_bounds__(TB) lean_kernel_scalar(const uint8_t *__restrict__ nmap, long long plane,
+                                                         float base_roughness, float bias, float *__restrict__ l1,
+                                                         float *__restrict__ l2)
+{
+	const float half_br2 = 0.5f * base_roughness * base_roughness;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < plane; px += stride) {
+		float e1, e2, e3, e4, e5;
+		lean_texel(nmap[px], nmap[plane + px], nmap[2 * plane + px], half_br2, bias, e1, e2, e3, e4, e5);
+		l1[px] = e1; l1[plane + px] = e2; l1[2 * plane + px] = 1.f; l1[3 * plane + px] = 1.f;
+		l2[px] = e3; l2[plane + px] = e4; l2[2 * plane + px] = e5; l2[3 * plane + px] = 1.f;
+	}
+}
+
+cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base_roughness, float bias,
+                                   float *lean1, float *lean2, cudaStream_t st)
+{
+	if (npix <= 0) return cudaSuccess;
+	bool aligned = (npix % 4 == 0) && ((uintptr_t)nmap % 4 == 0) && ((uintptr_t)lean1 % 16 == 0) &&
+	               ((uintptr_t)lean2 % 16 == 0);
+	if (aligned) {
+		const uchar4 *p = reinterpret_cast<const uchar4 *>(nmap);
+		int64_t nq = npix / 4;
+		lean_kernel_vec4<<<grid_for(nq), TB, 0, st>>>(p, p + nq, p + 2 * nq, nq, npix, base_roughness, bias, lean1, lean2);
+	} else {
+		lean_kernel_scalar<<<grid_for(npix), TB, 0, st>>>(nmap, npix, base_roughness, bias, lean1, lean2);
+	}
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+// ---- LEAN algebra per texel --------------------------------------------------------------------------
+DJB_DEV void store_params(void *out, long long k, const Params &p)
+{
+	float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<Params *>(out) + k);
+	o[0] = make_float4(p.nx, p.ny, p.nz, p.a1);
+	o[1] = make_float4(p.a2, p.phi_a, p.ax, p.ay);
+	o[2] = make_float4(p.rho, p.srho, p.tx, p.ty);
+}
+
+__global__ void __launch_bounds__(TB) lrep_to_params_kernel(const float *__restrict__ E, long long n, void *out)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		Params p;
+		lrep_to_params(E[5 * k], E[5 * k + 1], E[5 * k + 2], E[5 * k + 3], E[5 * k + 4], p);
+		store_params(out, k, p);
+	}
+}
+
+// beckmann::params_to_lrep, dj_brdf.h:1965-1974
+__global__ void __launch_bounds__(TB) params_to_lrep_kernel(const Params *__restrict__ P, long long n, float *__restrict__ E)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		Params p = P[k];
+		E[5 * k] = p.tx;
+		E[5 * k + 1] = p.ty;
+		E[5 * k + 2] = 0.5f * p.ax * p.ax + p.tx * p.tx;
+		E[5 * k + 3] = 0.5f * p.ay * p.ay + p.ty * p.ty;
+		E[5 * k + 4] = 0.5f * p.rho * p.ax * p.ay + p.tx * p.ty;
+	}
+}
+
+// check_lean_maps (utils/nmap2leanmap.cpp:57-76) as a producer of per-texel params; with a bias the
+// plugin removes it first (mitsuba/dj_beckmannconductor.cpp:295-314)
+__global__ void __launch_bounds__(TB) leanmap_to_params_kernel(const float *__restrict__ l1, const float *__restrict__ l2,
+                                                               long long plane, float bias, void *out)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < plane; px += stride) {
+		float e1 = l1[px], e2 = l1[plane + px], e3 = l2[px], e4 = l2[plane + px], e5 = l2[2 * plane + px];
+		if (bias != 0.0f) {
+			e1 -= bias;
+			e2 -= bias;
+			e5 -= bias * bias;
+		}
+		Params p;
+		lrep_to_params(e1, e2, e3, e4, e5, p);
+		store_params(out, px, p);
+	}
+}
+
+cudaError_t launch_lrep_to_params(const float *E, int64_t n, void *out_params, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	lrep_to_params_kernel<<<grid_for(n), TB, 0, st>>>(E, n, out_params);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_params_to_lrep(const void *params, int64_t n, float *E, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	params_to_lrep_kernel<<<grid_for(n), TB, 0, st>>>(reinterpret_cast<const Params *>(params), n, E);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int64_t npix, float bias,
+                                     void *out_params, cudaStream_t st)
+{
+	if (npix <= 0) return cudaSuccess;
+	leanmap_to_params_kernel<<<grid_for(npix), TB, 0, st>>>(lean1, lean2, npix, bias, out_params);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+} // namespace djb200

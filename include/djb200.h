@@ -1,0 +1,241 @@
+/* djb200.h -- C-ABI of the B200-native BRDF engine (libdjb200.so).
+ *
+ * This is the drop-in boundary for the hot paths of jdupuy/dj_brdf: every entry point replaces
+ * one call a host program makes into the reference's single header `dj_brdf.h` (cited per
+ * function as dj_brdf.h:LINE) or into utils/nmap2leanmap*.cpp.  Plain C, plain pointers and
+ * sizes, no C++ or torch types.  The C++ facade in include/djb200_facade.hpp re-creates the
+ * reference's `djb::` class surface on top of these functions; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - Every function returns a djb200_status; djb200_last_error() gives a thread-local message.
+ *     Nothing throws across this boundary (the reference throws djb::exc, dj_brdf.h:54-59).
+ *   - Direction arrays are packed float[3] (x,y,z), `n` of them; i = towards the light,
+ *     o = towards the viewer (dj_brdf.h:23-26).
+ *   - `mem` says where the *bulk* arrays (directions, uniforms, images, outputs) live:
+ *     DJB200_MEM_HOST   -- host pointers; the library stages them through the GPU in chunks
+ *                          (pinned host memory is copied asynchronously without staging),
+ *     DJB200_MEM_DEVICE -- device pointers on the current CUDA device; the call only enqueues
+ *                          work on `stream` (a cudaStream_t, NULL = default stream).
+ *     Small descriptors (djb200_params blocks, Fresnel data) are always host pointers.
+ *   - The library works on the calling thread's current CUDA device.  All entry points are
+ *     re-entrant; concurrent calls may share handles (handles are immutable after creation).
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with
+ *     DJB200_ERR_NO_DEVICE.
+ */
+#ifndef DJB200_H
+#define DJB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DJB200_API
+#else
+#define DJB200_API __attribute__((visibility("default")))
+#endif
+
+typedef enum djb200_status {
+	DJB200_OK = 0,
+	DJB200_ERR_INVALID_ARGUMENT = 1,
+	DJB200_ERR_NO_DEVICE = 2,
+	DJB200_ERR_CUDA = 3,
+	DJB200_ERR_OUT_OF_MEMORY = 4,
+	DJB200_ERR_IO = 5,
+	DJB200_ERR_UNSUPPORTED = 6
+} djb200_status;
+
+typedef enum djb200_mem { DJB200_MEM_HOST = 0, DJB200_MEM_DEVICE = 1 } djb200_mem;
+
+/* NDF families: djb::beckmann (dj_brdf.h:327-371), djb::ggx (dj_brdf.h:374-391) */
+typedef enum djb200_ndf { DJB200_NDF_BECKMANN = 0, DJB200_NDF_GGX = 1 } djb200_ndf;
+
+/* djb::fresnel::{ideal,schlick,unpolarized,sgd,spline} (dj_brdf.h:149-207, 1292-1344) */
+typedef enum djb200_fresnel_kind {
+	DJB200_FRESNEL_IDEAL = 0,
+	DJB200_FRESNEL_SCHLICK = 1,     /* v[0..2] = f0 */
+	DJB200_FRESNEL_UNPOLARIZED = 2, /* v[0..2] = ior */
+	DJB200_FRESNEL_SGD = 3,         /* v[0..2] = f0, v[3..5] = f1 */
+	DJB200_FRESNEL_SPLINE = 4       /* points: n_points x rgb, uniform in theta_d (dj_brdf.h:1338-1344) */
+} djb200_fresnel_kind;
+
+typedef struct djb200_fresnel {
+	int32_t kind;
+	float v[6];
+	const float *points; /* host pointer, n_points * 3 floats (SPLINE only) */
+	int32_t n_points;
+} djb200_fresnel;
+
+/* Layout-identical to djb::microfacet::params (dj_brdf.h:238-242; 12 floats, 48 bytes), so a
+ * reference `const void *user_param` can be passed through unchanged. */
+typedef struct djb200_params {
+	float n[3];                      /* mean normal */
+	float a1, a2, phi_a;             /* ellipse radii and orientation */
+	float ax, ay;                    /* slope-space scales */
+	float rho, sqrt_one_minus_rho2;  /* slope correlation */
+	float tx_n, ty_n;                /* slope-space location */
+} djb200_params;
+
+/* How `params` pairs up with the direction arrays:
+ *   BROADCAST: n_params blocks, every pair is evaluated under every block; output element
+ *              (m, k) is stored at index m * n + k  (material-major, each material contiguous),
+ *   PER_PAIR:  n_params == n, pair k uses block k (what a renderer does when roughness comes
+ *              from textures, mitsuba/dj_brdf.cpp:353-357); params is then a bulk array (`mem`). */
+typedef enum djb200_params_layout { DJB200_PARAMS_BROADCAST = 0, DJB200_PARAMS_PER_PAIR = 1 } djb200_params_layout;
+
+/* djb::microfacet construction state: family, Fresnel term, shadowing flag (dj_brdf.h:285-297) */
+typedef struct djb200_microfacet {
+	int32_t ndf;    /* djb200_ndf */
+	int32_t shadow; /* m_shadow, dj_brdf.h:297 */
+	djb200_fresnel fresnel;
+} djb200_microfacet;
+
+/* ---- library / device ------------------------------------------------------------------ */
+DJB200_API const char *djb200_last_error(void);
+DJB200_API const char *djb200_version(void);
+DJB200_API djb200_status djb200_device_count(int *count);
+DJB200_API djb200_status djb200_set_device(int device);
+/* counts kernels launched by this library in the calling process (for bench.py `gpu_launches`) */
+DJB200_API uint64_t djb200_kernel_launch_count(void);
+
+/* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
+DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */
+DJB200_API djb200_status djb200_params_isotropic(float a, djb200_params *out);                 /* :1417 */
+DJB200_API djb200_status djb200_params_elliptic(float a1, float a2, float phi_a, djb200_params *out); /* :1422 */
+DJB200_API djb200_status djb200_params_pdfparams(float ax, float ay, float rho, float tx_n, float ty_n,
+                                                 djb200_params *out);                          /* :1428 */
+
+/* ---- batched microfacet queries ---------------------------------------------------------- */
+/* f_r: microfacet::eval, dj_brdf.h:1551-1555.  out_rgb: n_out x 3 floats. */
+DJB200_API djb200_status djb200_microfacet_eval(const djb200_microfacet *mf, const djb200_params *params,
+                                                int64_t n_params, int params_layout, const float *wi,
+                                                const float *wo, int64_t n, float *out_rgb, int mem,
+                                                void *stream);
+/* f_r cos: microfacet::evalp, dj_brdf.h:1529-1547 */
+DJB200_API djb200_status djb200_microfacet_evalp(const djb200_microfacet *mf, const djb200_params *params,
+                                                 int64_t n_params, int params_layout, const float *wi,
+                                                 const float *wo, int64_t n, float *out_rgb, int mem,
+                                                 void *stream);
+/* microfacet::pdf, dj_brdf.h:1713-1730.  out_pdf: n_out floats. */
+DJB200_API djb200_status djb200_microfacet_pdf(const djb200_microfacet *mf, const djb200_params *params,
+                                               int64_t n_params, int params_layout, const float *wi,
+                                               const float *wo, int64_t n, float *out_pdf, int mem,
+                                               void *stream);
+/* microfacet::sample, dj_brdf.h:1669-1709.  u: n x 2 uniforms; out_wi: n_out x 3. */
+DJB200_API djb200_status djb200_microfacet_sample(const djb200_microfacet *mf, const djb200_params *params,
+                                                  int64_t n_params, int params_layout, const float *u,
+                                                  const float *wo, int64_t n, float *out_wi, int mem,
+                                                  void *stream);
+/* microfacet::evalp_is, dj_brdf.h:1734-1765.  Any of the three outputs may be NULL.
+ * out_wi is written as (0,0,0) where the reference leaves *i untouched (G <= 0). */
+DJB200_API djb200_status djb200_microfacet_evalp_is(const djb200_microfacet *mf, const djb200_params *params,
+                                                    int64_t n_params, int params_layout, const float *u,
+                                                    const float *wo, int64_t n, float *out_weight_rgb,
+                                                    float *out_wi, float *out_pdf, int mem, void *stream);
+
+/* ---- Rusinkiewicz frame (brdf::io_to_hd / hd_to_io, dj_brdf.h:771-793) ------------------ */
+DJB200_API djb200_status djb200_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d,
+                                         int mem, void *stream);
+DJB200_API djb200_status djb200_hd_to_io(const float *h, const float *d, int64_t n, float *wi, float *wo,
+                                         int mem, void *stream);
+
+/* ---- MERL (djb::merl, dj_brdf.h:126-133, 893-1024) -------------------------------------- */
+typedef struct djb200_merl djb200_merl; /* device-resident table, immutable */
+/* samples: 3 planes (R, G, B) of 90*90*180 doubles exactly as in a MERL .binary file (host pointer) */
+DJB200_API djb200_status djb200_merl_create(const double *samples, djb200_merl **out);
+/* merl::merl(const char*), dj_brdf.h:963-983 */
+DJB200_API djb200_status djb200_merl_load(const char *filename, djb200_merl **out);
+DJB200_API djb200_status djb200_merl_destroy(djb200_merl *m);
+/* merl::eval, dj_brdf.h:987-1024 */
+DJB200_API djb200_status djb200_merl_eval(const djb200_merl *m, const float *wi, const float *wo, int64_t n,
+                                          float *out_rgb, int mem, void *stream);
+/* the cell index merl::eval forms at dj_brdf.h:997-1002 (phi_d + 180 theta_d + 16200 theta_h) */
+DJB200_API djb200_status djb200_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out_index,
+                                           int mem, void *stream);
+
+/* ---- UTIA (djb::utia, dj_brdf.h:136-146, 1029-1177) ------------------------------------- */
+typedef struct djb200_utia djb200_utia;
+/* raw_samples: 3*6*48*6*48 doubles as stored in a UTIA .bin file, before utia::normalize() */
+DJB200_API djb200_status djb200_utia_create(const double *raw_samples, djb200_utia **out);
+DJB200_API djb200_status djb200_utia_load(const char *filename, djb200_utia **out);
+DJB200_API djb200_status djb200_utia_destroy(djb200_utia *u);
+DJB200_API djb200_status djb200_utia_eval(const djb200_utia *u, const float *wi, const float *wo, int64_t n,
+                                          float *out_rgb, int mem, void *stream);
+
+/* ---- LEAN / LEADR ------------------------------------------------------------------------ */
+/* nmap2leanmap, utils/nmap2leanmap.cpp:18-54 (bias = 0) and nmap2leanmap_biased.cpp:23-63
+ * (bias = 25).  nmap: planar uint8 [3][h][w]; lean1/lean2: planar float [4][h][w] (CImg layout). */
+DJB200_API djb200_status djb200_nmap_to_leanmap(const uint8_t *nmap, int32_t w, int32_t h, float base_roughness,
+                                                float bias, float *lean1, float *lean2, int mem, void *stream);
+/* beckmann::lrep_to_params, dj_brdf.h:1976-1990.  E: n x 5 moments (E1..E5). */
+DJB200_API djb200_status djb200_lrep_to_params(const float *E, int64_t n, djb200_params *out, int mem,
+                                               void *stream);
+/* beckmann::params_to_lrep, dj_brdf.h:1965-1974 */
+DJB200_API djb200_status djb200_params_to_lrep(const djb200_params *params, int64_t n, float *E, int mem,
+                                               void *stream);
+/* check_lean_maps, utils/nmap2leanmap.cpp:57-76: per-texel lrep_to_params over the two planar maps
+ * (bias is subtracted from E1, E2 and bias^2 from E5 first, mitsuba/dj_beckmannconductor.cpp:295-314) */
+DJB200_API djb200_status djb200_leanmap_to_params(const float *lean1, const float *lean2, int32_t w, int32_t h,
+                                                  float bias, djb200_params *out, int mem, void *stream);
+
+/* ---- fits ("power iterations") ----------------------------------------------------------- */
+/* What a fit reads from its source BRDF: a MERL/UTIA table on the device, or an analytic
+ * microfacet BRDF.  (The reference takes any `const brdf&`, dj_brdf.h:401, 441.) */
+typedef enum djb200_source_kind {
+	DJB200_SOURCE_MERL = 0,
+	DJB200_SOURCE_UTIA = 1,
+	DJB200_SOURCE_MICROFACET = 2
+} djb200_source_kind;
+
+typedef struct djb200_source {
+	int32_t kind;
+	const djb200_merl *merl;
+	const djb200_utia *utia;
+	djb200_microfacet microfacet; /* evaluated with params::standard(), as the reference's NULL user_param */
+} djb200_source;
+
+/* Result of djb::tabular::tabular + fit_*_parameters for one material (dj_brdf.h:2215-2236,
+ * 3133-3184).  All arrays have `res` entries (fresnel: res x rgb). */
+typedef struct djb200_tabular_fit {
+	int32_t res;
+	float *p22;     /* get_p22v()   */
+	float *sigma;   /* get_sigmav() */
+	float *cdf;     /* get_cdfv()   */
+	float *qf;      /* get_qfv()    */
+	float *fresnel; /* get_fresnel() spline points */
+	float alpha_beckmann, alpha_ggx;
+	float *residuals; /* optional, `iterations` floats: ||v_k/|v_k| - v_{k-1}/|v_{k-1}|||_2 (diagnostic,
+	                     not in the reference, never fed back) */
+} djb200_tabular_fit;
+
+/* Batched isotropic fit: n_sources materials, host result structs with host arrays.
+ * iterations = 4 reproduces the reference (km.eigenvector(4), dj_brdf.h:2518). */
+DJB200_API djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources, int32_t res,
+                                            int32_t shadow, int32_t iterations, djb200_tabular_fit *results,
+                                            void *stream);
+
+/* Result of djb::tabular_anisotropic (eval tables) + fit_*_parameters (dj_brdf.h:2238-2273,
+ * 3186-3307): p22/sigma are elev_res x azim_res, fresnel elev_res x rgb,
+ * beckmann/ggx = (ax, ay, rho, tx_n, ty_n). */
+typedef struct djb200_tabular_anisotropic_fit {
+	int32_t elev_res, azim_res;
+	float *p22;
+	float *sigma;
+	float *fresnel;
+	float beckmann[5];
+	float ggx[5];
+	float *residuals;
+} djb200_tabular_anisotropic_fit;
+
+DJB200_API djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sources, int32_t n_sources,
+                                                        int32_t elev_res, int32_t azim_res, int32_t shadow,
+                                                        int32_t iterations,
+                                                        djb200_tabular_anisotropic_fit *results, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DJB200_H */

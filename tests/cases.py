@@ -1,0 +1,110 @@
+"""Shared definitions of the parity cases (inputs are regenerated from seeds, never stored)."""
+import numpy as np
+
+from oracle import api
+
+N_SMALL = 4096  # golden fixtures
+N_PARITY = 200_000  # GPU-vs-oracle parity sweeps (the oracle finishes each in well under a second)
+
+
+def pairs(n, stream=0):
+    wi = api.directions(n, stream)
+    wo = api.directions(n, stream + 2)
+    u = np.stack([api.uniforms(n, stream + 4), api.uniforms(n, stream + 5)], axis=1)
+    return wi, wo, u
+
+
+def edge_pairs():
+    """Hand-picked edge inputs the reference treats specially (SURVEY.md section 7 'edge cases')."""
+    v = []
+    z = np.float32
+    def d(x, y, zz):
+        a = np.array([x, y, zz], np.float64)
+        return (a / np.linalg.norm(a)).astype(np.float32)
+    v.append((d(0, 0, 1), d(0, 0, 1)))                   # normal incidence, h = z (pole guard)
+    v.append((d(1e-4, 0, 1), d(-1e-4, 0, 1)))            # h within the 0.99999 pole guard
+    v.append((d(1, 0, 1e-3), d(1, 0, 1e-3)))             # grazing retro-reflection
+    v.append((d(1, 0, 1e-3), d(-1, 0, 1e-3)))            # grazing forward: h ~ z
+    v.append((d(0.3, 0.4, -0.2), d(0.1, 0.2, 0.9)))      # i below the horizon (-> G1 gate)
+    v.append((d(0.3, 0.4, 0.5), d(0.1, 0.2, -0.9)))      # o below the horizon
+    v.append((d(0.6, 0, 0.8), d(-0.6, 0, 0.8)))          # mirror pair in the xz plane
+    v.append((d(0, 0.6, 0.8), d(0, -0.6, 0.8)))          # mirror pair in the yz plane
+    v.append((np.array([0.6, 0.0, 0.8], z), np.array([0.0, 0.0, 1.0], z)))
+    v.append((np.array([0.0, 1.0, 0.0], z), np.array([0.0, 0.0, 1.0], z)))  # i.z == 0 -> inf/NaN path
+    v.append((d(-0.5, -0.5, 0.7), d(-0.5, -0.5, 0.7)))
+    v.append((d(1, 1, 1e-6), d(0, 0, 1)))
+    wi = np.stack([a for a, _ in v]).astype(np.float32)
+    wo = np.stack([b for _, b in v]).astype(np.float32)
+    u = np.array([[0, 0], [1, 1], [0.5, 0.5], [1e-7, 0.999999], [0.25, 0.75], [0.3, 0.7], [0.9, 0.1],
+                  [0.5, 0.0], [0.0, 0.5], [1.0, 0.5], [0.123, 0.456], [0.999, 0.001]], np.float32)
+    return wi, wo, u
+
+
+def param_sets(o):
+    """Named params blocks built with oracle `o` (RefOracle or PortOracle)."""
+    return {
+        "iso0.1": o.params_elliptic(0.1, 0.1, 0.0),
+        "iso0.5": o.params_elliptic(0.5, 0.5, 0.0),
+        "aniso": o.params_elliptic(0.1, 0.4, 0.7),
+        "aniso2": o.params_elliptic(0.6, 0.05, 2.5),
+        "offcentre": o.params_pdfparams(0.3, 0.2, 0.4, 0.1, -0.2),
+        "standard": o.params_elliptic(1.0, 1.0, 0.0),
+    }
+
+
+def c2_materials(o, m=16, seed=1):
+    """config 2 of BASELINE.json: 16 anisotropic materials, alpha log-uniform [0.02, 0.8], phi_a in [0, pi)."""
+    rng = np.random.default_rng(seed)
+    a1 = np.exp(rng.uniform(np.log(0.02), np.log(0.8), m)).astype(np.float32)
+    a2 = np.exp(rng.uniform(np.log(0.02), np.log(0.8), m)).astype(np.float32)
+    ph = rng.uniform(0, np.pi, m).astype(np.float32)
+    return np.stack([o.params_elliptic(float(a), float(b), float(c)) for a, b, c in zip(a1, a2, ph)])
+
+
+def fresnels():
+    return {
+        "ideal": api.Fresnel.ideal(),
+        "schlick": api.Fresnel.schlick([0.9, 0.5, 0.2]),
+        "unpolarized": api.Fresnel.unpolarized([1.5, 1.8, 2.4]),
+        "spline": api.Fresnel.spline(np.linspace(0.2, 1.0, 30, dtype=np.float32).reshape(10, 3)),
+    }
+
+
+def synthetic_merl_table(alpha=0.15, seed=7, kind="ggx"):
+    """config 3: analytic microfacet lobe + diffuse sampled at MERL cell centres, stored unscaled (divided
+    by the MERL channel scales); below-horizon cells are -1 (exercises dj_brdf.h:1016-1021)."""
+    th = ((np.arange(90) + 0.5) / 90.0) ** 2 * (np.pi / 2)
+    td = (np.arange(90) + 0.5) / 90.0 * (np.pi / 2)
+    pd = (np.arange(180) + 0.5) / 180.0 * np.pi
+    TH, TD, PD = np.meshgrid(th, td, pd, indexing="ij")
+    # half / diff -> i, o (h in the xz-plane at elevation TH; d rotated by TH about y)
+    dx, dy, dz = np.sin(TD) * np.cos(PD), np.sin(TD) * np.sin(PD), np.cos(TD)
+    ix = dx * np.cos(TH) + dz * np.sin(TH)
+    iz = -dx * np.sin(TH) + dz * np.cos(TH)
+    hx, hz = np.sin(TH), np.cos(TH)
+    dot = ix * hx + iz * hz
+    ox, oz = 2 * dot * hx - ix, 2 * dot * hz - iz
+    below = (iz <= 0) | (oz <= 0)
+    t2 = np.tan(TH) ** 2
+    if kind == "ggx":
+        D = alpha ** 2 / (np.pi * np.cos(TH) ** 4 * (alpha ** 2 + t2) ** 2)
+    else:
+        D = np.exp(-t2 / alpha ** 2) / (np.pi * alpha ** 2 * np.cos(TH) ** 4)
+    F = 0.04 + 0.96 * (1 - np.clip(dot, 0, 1)) ** 5
+    spec = D * F / np.maximum(4 * np.abs(iz * oz), 1e-3)
+    rgb = []
+    scales = (1.00 / 1500.0, 1.15 / 1500.0, 1.66 / 1500.0)
+    for c, tint in enumerate((0.8, 0.6, 0.4)):
+        v = (tint * spec + 0.1 * (c + 1) / np.pi) / scales[c]
+        v = v.astype(np.float32).astype(np.float64)  # exactly representable in fp32
+        v[below] = -1.0
+        rgb.append(v.reshape(-1))
+    return np.concatenate(rgb)
+
+
+def synthetic_nmap(h, w, seed=12345):
+    rng = np.random.default_rng(seed)
+    r = rng.integers(64, 192, (h, w), dtype=np.uint8)
+    g = rng.integers(64, 192, (h, w), dtype=np.uint8)
+    b = rng.integers(128, 256, (h, w), dtype=np.uint8)
+    return np.stack([r, g, b])

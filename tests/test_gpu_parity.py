@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C-ABI, via the Python host mirror) against the CPU oracle
+on the same seeded inputs.  Bars (BASELINE.json north_star): eval / pdf within 1e-5 relative with
+identical zero / NaN pattern; MERL indices, LEAN maps and lrep params bit exact."""
+import numpy as np
+import pytest
+
+from oracle import api
+from tests import cases
+from tests.conftest import bits_equal, rel_err
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: eval/pdf <= 1e-5 relative FP32
+
+
+def mk_fresnel(djb, f):
+    k = f.kind
+    if k == api.F_IDEAL:
+        return djb.fresnel.ideal()
+    if k == api.F_SCHLICK:
+        return djb.fresnel.schlick(f.data[:3])
+    if k == api.F_UNPOLARIZED:
+        return djb.fresnel.unpolarized(f.data[:3])
+    if k == api.F_SPLINE:
+        return djb.fresnel.spline(f.data.reshape(-1, 3))
+    raise ValueError(k)
+
+
+def mk_brdf(djb, ndf, f, shadow=True):
+    cls = djb.ggx if ndf == api.NDF_GGX else djb.beckmann
+    return cls(mk_fresnel(djb, f), shadow)
+
+
+def check_close(got, want, what, tol=REL_TOL, min_bit_rate=0.0):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    e = rel_err(got, want)
+    same = bits_equal(got, want)
+    # identical zero pattern
+    assert np.array_equal(got == 0, want == 0), f"{what}: zero pattern differs"
+    worst = float(e.max()) if e.size else 0.0
+    assert worst <= tol, f"{what}: max rel err {worst:.3e} > {tol} (bit-identical {same.mean():.6f})"
+    assert same.mean() >= min_bit_rate, f"{what}: bit-identical rate {same.mean():.6f} < {min_bit_rate}"
+    return same.mean(), worst
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("pname", ["iso0.1", "iso0.5", "aniso", "aniso2", "offcentre", "standard"])
+def test_eval_pdf_parity(djb, port, ndf, pname):
+    wi, wo, _ = cases.pairs(cases.N_PARITY)
+    P = cases.param_sets(port)[pname]
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    check_close(b.eval(wi, wo, P), port.eval(ndf, P, wi, wo), f"eval {pname}", min_bit_rate=0.9999)
+    check_close(b.evalp(wi, wo, P), port.evalp(ndf, P, wi, wo), f"evalp {pname}", min_bit_rate=0.9999)
+    check_close(b.pdf(wi, wo, P), port.pdf(ndf, P, wi, wo), f"pdf {pname}", min_bit_rate=0.9999)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("fname", ["schlick", "unpolarized", "spline"])
+@pytest.mark.parametrize("shadow", [True, False])
+def test_eval_fresnel_and_shadow(djb, port, ndf, fname, shadow):
+    wi, wo, _ = cases.pairs(50_000, stream=16)
+    f = cases.fresnels()[fname]
+    P = cases.param_sets(port)["aniso"]
+    b = mk_brdf(djb, ndf, f, shadow)
+    check_close(b.eval(wi, wo, P), port.eval(ndf, P, wi, wo, f, shadow), f"eval {fname} shadow={shadow}",
+                min_bit_rate=0.9999)
+    check_close(b.pdf(wi, wo, P), port.pdf(ndf, P, wi, wo, f, shadow), f"pdf {fname} shadow={shadow}",
+                min_bit_rate=0.9999)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_null_params_is_standard(djb, port, ndf):
+    wi, wo, _ = cases.pairs(10_000, stream=32)
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    check_close(b.eval(wi, wo, None), port.eval(ndf, None, wi, wo), "eval NULL params")
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_edge_inputs(djb, port, ndf):
+    wi, wo, u = cases.edge_pairs()
+    b = mk_brdf(djb, ndf, api.Fresnel.schlick([0.9, 0.5, 0.2]))
+    f = api.Fresnel.schlick([0.9, 0.5, 0.2])
+    for pname, P in cases.param_sets(port).items():
+        got, want = b.eval(wi, wo, P), port.eval(ndf, P, wi, wo, f)
+        assert bits_equal(got, want).all(), (pname, got, want)
+        assert bits_equal(b.pdf(wi, wo, P), port.pdf(ndf, P, wi, wo, f)).all(), pname
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_broadcast_16_materials(djb, port, ndf):
+    """config 2 layout: every pair under each of 16 anisotropic materials, material-major output."""
+    wi, wo, u = cases.pairs(20_000, stream=48)
+    mats = cases.c2_materials(port)
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    got = b.eval(wi, wo, mats)
+    assert got.shape == (16, len(wi), 3)
+    gotp = b.pdf(wi, wo, mats)
+    gots = b.sample(u, wo, mats)
+    for m in range(16):
+        check_close(got[m], port.eval(ndf, mats[m], wi, wo), f"eval material {m}")
+        check_close(gotp[m], port.pdf(ndf, mats[m], wi, wo), f"pdf material {m}")
+        same = bits_equal(gots[m], port.sample(ndf, mats[m], u, wo))
+        assert same.mean() > (0.999 if ndf == api.NDF_GGX else 0.98), (m, same.mean())
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_per_pair_params(djb, port, ndf):
+    n = 4096
+    wi, wo, _ = cases.pairs(n, stream=64)
+    rng = np.random.default_rng(3)
+    blocks = np.stack([port.params_elliptic(float(a), float(b), float(c)) for a, b, c in
+                       zip(rng.uniform(0.05, 0.8, n), rng.uniform(0.05, 0.8, n), rng.uniform(0, 3.1, n))])
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    got = b.eval(wi, wo, blocks, per_pair=True)
+    want = np.stack([port.eval(ndf, blocks[k], wi[k:k + 1], wo[k:k + 1])[0] for k in range(n)])
+    check_close(got, want, "per-pair eval")
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("pname", ["iso0.1", "aniso", "offcentre"])
+def test_sample_parity(djb, port, ndf, pname):
+    """sample is not under the 1e-5 bar: the mirrored-rounding bit-match rate is
+    reported and bounded, and the mismatching tail must stay small in angle."""
+    _, wo, u = cases.pairs(cases.N_PARITY, stream=80)
+    P = cases.param_sets(port)[pname]
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    got, want = b.sample(u, wo, P), port.sample(ndf, P, u, wo)
+    same = bits_equal(got, want).all(axis=1)
+    # GGX has no single-precision libm call: it must match to the bit almost everywhere.
+    # Beckmann goes through logf/expf/powf, which glibc and the device round differently in ~1e-3 cases.
+    assert same.mean() >= (0.99999 if ndf == api.NDF_GGX else 0.97), same.mean()
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64)).max(axis=1)
+    assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, 0.999)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_evalp_is_parity(djb, port, ndf):
+    _, wo, u = cases.pairs(50_000, stream=96)
+    P = cases.param_sets(port)["aniso"]
+    f = api.Fresnel.schlick([0.9, 0.5, 0.2])
+    b = mk_brdf(djb, ndf, f)
+    gw, gi, gp = b.evalp_is(u, wo, P)
+    ww, wi_, wp = port.evalp_is(ndf, P, u, wo, f)
+    ok = bits_equal(gi, wi_).all(axis=1)
+    assert ok.mean() >= (0.9999 if ndf == api.NDF_GGX else 0.97)
+    # where the sampled direction agrees to the bit, weight and pdf must meet the eval/pdf bar
+    check_close(gw[ok], ww[ok], "evalp_is weight")
+    check_close(gp[ok], wp[ok], "evalp_is pdf")
+
+
+def test_sample_pdf_consistency(djb):
+    """Size-independent property: E[1/pdf] over sampled directions == measure of the sampled domain;
+    cheaper equivalent used here: weights F*G/G1 are in [0, 1] and pdf > 0 wherever the weight is > 0."""
+    import torch
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(0)
+    u = torch.rand(n, 2, device="cuda", generator=g)
+    z = 1 - 0.95 * torch.rand(n, device="cuda", generator=g)
+    ph = 6.2831853 * torch.rand(n, device="cuda", generator=g)
+    r = torch.sqrt(1 - z * z)
+    wo = torch.stack([r * torch.cos(ph), r * torch.sin(ph), z], 1).contiguous()
+    for cls in (djb.ggx, djb.beckmann):
+        w, i, pdf = cls().evalp_is(u, wo, djb.params.elliptic(0.2, 0.5, 0.3))
+        w, pdf = w.cpu().numpy(), pdf.cpu().numpy()
+        assert np.isfinite(w).all() and (w >= 0).all() and (w <= 1.0 + 1e-5).all()
+        assert (pdf[w[:, 0] > 0] > 0).all()
+
+
+def test_device_and_host_paths_agree(djb, port):
+    import torch
+    wi, wo, u = cases.pairs(100_000, stream=112)
+    mats = cases.c2_materials(port)[:3]
+    b = djb.beckmann()
+    host = b.eval(wi, wo, mats)
+    dev = b.eval(torch.from_numpy(wi).cuda(), torch.from_numpy(wo).cuda(), mats).cpu().numpy()
+    assert bits_equal(host, dev).all()
+
+
+def test_io_hd_roundtrip_and_parity(djb, port):
+    wi, wo, _ = cases.pairs(100_000, stream=128)
+    h, d = djb.brdf.io_to_hd(wi, wo)
+    hr, dr = port.io_to_hd(wi, wo)
+    assert bits_equal(h, hr).mean() > 0.99999 and bits_equal(d, dr).mean() > 0.9999
+    i2, o2 = djb.brdf.hd_to_io(hr, dr)
+    ir, or_ = port.hd_to_io(hr, dr)
+    assert bits_equal(i2, ir).mean() > 0.9999 and bits_equal(o2, or_).mean() > 0.9999
+    assert np.abs(i2 - wi).max() < 1e-5
+
+
+def test_merl_index_bit_exact(djb, port):
+    n = 2_000_000
+    wi, wo, _ = cases.pairs(n, stream=144)
+    got = djb.merl.index(wi, wo)
+    want = port.merl_index(wi, wo, nthreads=8)
+    mism = int((got != want).sum())
+    # north_star: bit exact index arithmetic.  The only tolerated source of difference is a device
+    # double acos/atan2 that rounds to another float than glibc's (expected ~0 in 2e6).
+    assert mism <= 2, f"{mism} MERL index mismatches in {n}"
+
+
+def test_merl_eval(djb, port):
+    table = cases.synthetic_merl_table()
+    m = djb.merl(table)
+    wi, wo, _ = cases.pairs(500_000, stream=160)
+    got = m.eval(wi, wo)
+    want = port.merl_eval(table, wi, wo, nthreads=8)
+    idx_ok = djb.merl.index(wi, wo) == port.merl_index(wi, wo, nthreads=8)
+    assert bits_equal(got[idx_ok], want[idx_ok]).all()
+    assert idx_ok.mean() > 0.999999
+    assert (want == 0).all(axis=1).any(), "the synthetic table must exercise the below-horizon branch"
+    ewi, ewo, _ = cases.edge_pairs()
+    assert bits_equal(m.eval(ewi, ewo), port.merl_eval(table, ewi, ewo)).all()
+
+
+def test_merl_random_table_bit_exact(djb, port):
+    rng = np.random.default_rng(0)
+    table = rng.uniform(-0.05, 3.0, 3 * api.MERL_CELLS)  # full double mantissas: exercises the scaling
+    m = djb.merl(table)
+    wi, wo, _ = cases.pairs(100_000, stream=176)
+    got, want = m.eval(wi, wo), port.merl_eval(table, wi, wo, nthreads=8)
+    assert bits_equal(got, want).mean() > 0.99999
+
+
+def test_utia_eval(djb, port):
+    rng = np.random.default_rng(1)
+    raw = rng.uniform(-0.5, 60.0, 3 * 6 * 48 * 6 * 48)
+    t = djb.utia(raw)
+    wi, wo, _ = cases.pairs(100_000, stream=192)
+    got, want = t.eval(wi, wo), port.utia_eval(raw, wi, wo, nthreads=8)
+    check_close(got, want, "utia eval", tol=1e-5, min_bit_rate=0.999)
+
+
+@pytest.mark.parametrize("bias", [0.0, 25.0])
+@pytest.mark.parametrize("shape", [(64, 48), (33, 17), (512, 1024)])
+def test_lean_maps_bit_exact(djb, port, bias, shape):
+    nm = cases.synthetic_nmap(*shape)
+    g1, g2 = djb.nmap2leanmap(nm, 1e-5, bias)
+    w1, w2 = port.nmap2leanmap(nm, 1e-5, bias)
+    assert bits_equal(g1, w1).all() and bits_equal(g2, w2).all()
+
+
+def test_lean_device_path_and_params(djb, port):
+    import torch
+    nm = cases.synthetic_nmap(256, 256)
+    g1, g2 = djb.nmap2leanmap(torch.from_numpy(nm).cuda(), 0.05, 0.0)
+    w1, w2 = port.nmap2leanmap(nm, 0.05, 0.0)
+    assert bits_equal(g1.cpu().numpy(), w1).all() and bits_equal(g2.cpu().numpy(), w2).all()
+    P = djb.leanmap_to_params(w1, w2, 0.0)
+    E = np.stack([w1[0].ravel(), w1[1].ravel(), w2[0].ravel(), w2[1].ravel(), w2[2].ravel()], 1)
+    assert bits_equal(P, port.lrep_to_params(E)).all()
+    assert bits_equal(djb.beckmann.lrep_to_params(E), port.lrep_to_params(E)).all()
+    assert bits_equal(djb.beckmann.params_to_lrep(P), port.params_to_lrep(P)).all()
+
+
+def test_empty_and_ragged(djb):
+    z = np.zeros((0, 3), np.float32)
+    assert djb.ggx().eval(z, z, djb.params.isotropic(0.1)).shape == (0, 3)
+    assert djb.merl.index(z, z).shape == (0,)
+    for n in (1, 2, 3, 5, 31, 33, 257):
+        wi, wo, u = cases.pairs(n, stream=208)
+        assert djb.ggx().eval(wi, wo, djb.params.isotropic(0.3)).shape == (n, 3)
+        assert djb.beckmann().sample(u, wo, djb.params.isotropic(0.3)).shape == (n, 3)
