@@ -237,8 +237,65 @@ ORC_API void orc_params_pdfparams(float ax, float ay, float rho, float tx, float
 
 /* ---------------------------------------------------------------------------------------------
  * standard (radial) distributions */
+/* spline::eval<float_t> with uwrap_edge, :1191-1218 */
+float orc__spline_eval_f(const float *pts, int n, float u)
+{
+	double ip;
+	float frac = F(modf(D(u * (float)n - u), &ip));
+	int i1 = (int)ip, i2 = (int)ip + 1;
+	if (i1 >= n) i1 = n - 1; else if (i1 < 0) i1 = 0;
+	if (i2 >= n) i2 = n - 1; else if (i2 < 0) i2 = 0;
+	float p1 = pts[i1], p2 = pts[i2];
+	return p1 + frac * (p2 - p1);
+}
+
+/* djb::tabular as a third radial family (ndf == ORC_NDF_TABULAR): the tables of the fit that is
+ * being built on this thread (djb_oracle_fit.c), :2151-2163 */
+#define ORC_NDF_TABULAR 2
+#define ORC_NDF_TABULAR_ANISO 3
+static __thread const float *t_tab_p22, *t_tab_sigma;
+static __thread int t_tab_np22, t_tab_nsigma; /* isotropic: table lengths; anisotropic: w (elevation), h (azimuth) */
+void orc__set_tabular(const float *p22, int np22, const float *sigma, int nsigma)
+{
+	t_tab_p22 = p22; t_tab_np22 = np22; t_tab_sigma = sigma; t_tab_nsigma = nsigma;
+}
+
+/* spline::eval2d<float_t>(uwrap_edge, u1, uwrap_repeat, u2), :1220-1247 */
+float orc__spline_eval2d_f(const float *pts, int w, int h, float u1, float u2)
+{
+	double ip1, ip2;
+	float frac1 = F(modf(D(u1 * (float)w - u1), &ip1));
+	int i1 = (int)ip1, i2 = (int)ip1 + 1;
+	if (i1 >= w) i1 = w - 1; else if (i1 < 0) i1 = 0;
+	if (i2 >= w) i2 = w - 1; else if (i2 < 0) i2 = 0;
+	float frac2 = F(modf(D(u2 * (float)h - u2), &ip2));
+	int j1 = (int)ip2, j2 = (int)ip2 + 1;
+	while (j1 >= h) j1 -= h;
+	while (j1 < 0) j1 += h;
+	while (j2 >= h) j2 -= h;
+	while (j2 < 0) j2 += h;
+	float p1 = pts[i1 + w * j1], p2 = pts[i2 + w * j1], p3 = pts[i1 + w * j2], p4 = pts[i2 + w * j2];
+	float t1 = p1 + frac1 * (p2 - p1);
+	float t2 = p3 + frac1 * (p4 - p3);
+	return t1 + frac2 * (t2 - t1);
+}
+
+/* tabular_anisotropic::p22_std_theta_phi, :2185-2197 */
+float orc__aniso_p22_theta_phi(float theta, float phi)
+{
+	if (D(phi) < 0.0) phi = F(D(phi) + 2.0 * ORC_PI);
+	float u1 = F(D(theta) * 2.0 / ORC_PI);
+	float u2 = F(D(phi) * 0.5 / ORC_PI);
+	return orc__spline_eval2d_f(t_tab_p22, t_tab_np22, t_tab_nsigma, u1, u2);
+}
+
 static float p22_radial(int ndf, float r2)
 {
+	if (ndf == ORC_NDF_TABULAR) { /* tabular::p22_radial, :2151-2156 */
+		float r = F(sqrt(D(r2)));
+		float u = F(sqrt(2.0 * atan(D(r)) / D(F(ORC_PI))));
+		return orc__spline_eval_f(t_tab_p22, t_tab_np22, u);
+	}
 	if (ndf == ORC_NDF_GGX) { /* :2056-2060 */
 		float t = F(1.0 + D(r2));
 		return F(1.0 / (ORC_PI * D(t) * D(t)));
@@ -248,6 +305,10 @@ static float p22_radial(int ndf, float r2)
 
 static float sigma_std_radial(int ndf, float c)
 {
+	if (ndf == ORC_NDF_TABULAR) { /* tabular::sigma_std_radial, :2158-2162 */
+		float u = F(2.0 * acos(D(c)) / D(F(ORC_PI)));
+		return orc__spline_eval_f(t_tab_sigma, t_tab_nsigma, u);
+	}
 	if (ndf == ORC_NDF_GGX) return F((1.0 + D(c)) / 2.0); /* :2062-2065 */
 	/* beckmann, :1871-1879 */
 	if (D(c) == 1.0) return 1.0f;
@@ -255,6 +316,31 @@ static float sigma_std_radial(int ndf, float c)
 	float nu = c / s;
 	float tmp = F(exp(D(-nu * nu)) * D(inv_sqrt(F(ORC_PI))));
 	return F((D(c) * (1.0 + D(as_erf(nu))) + D(s * tmp)) / 2.0);
+}
+
+/* the two virtuals of djb::microfacet: radial::p22_std / sigma_std (:1796-1804) forward to the
+ * radial functions; tabular_anisotropic has its own (:2178-2183, 2199-2211) */
+static float p22_std(int ndf, float x, float y)
+{
+	if (ndf == ORC_NDF_TABULAR_ANISO) {
+		float theta = F(atan(sqrt(D(x * x + y * y))));
+		float phi = F(atan2(D(-y), D(-x)));
+		return orc__aniso_p22_theta_phi(theta, phi);
+	}
+	return p22_radial(ndf, x * x + y * y);
+}
+
+static float sigma_std(int ndf, v3 k)
+{
+	if (ndf == ORC_NDF_TABULAR_ANISO) {
+		float theta = F(acos(D(k.z)));
+		float phi = F(atan2(D(k.y), D(k.x)));
+		if (D(phi) < 0.0) phi = F(D(phi) + 2.0 * ORC_PI);
+		float u1 = F(D(theta) * 2.0 / ORC_PI);
+		float u2 = F(D(phi) * 0.5 / ORC_PI);
+		return orc__spline_eval2d_f(t_tab_sigma, t_tab_np22, t_tab_nsigma, u1, u2);
+	}
+	return sigma_std_radial(ndf, k.z);
 }
 
 /* microfacet::sigma, :1619-1631 */
@@ -265,7 +351,7 @@ static float mf_sigma(int ndf, const orc_params *p, v3 k)
 	float c = k.z - k.x * p->tx - k.y * p->ty;
 	float nrm = F(sqrt(D(a * a + b * b + c * c)));
 	v3 ks = v3_div(v3_make(a, b, c), nrm);
-	return nrm * sigma_std_radial(ndf, ks.z);
+	return nrm * sigma_std(ndf, ks);
 }
 
 /* :1633-1642 */
@@ -299,7 +385,7 @@ static float mf_p22(int ndf, const orc_params *p, float x, float y)
 	float t1 = p->ax * y - p->rho * p->ay * x;
 	float t2 = p->ax * p->ay * p->srho;
 	float ys = t1 / t2;
-	return p22_radial(ndf, xs * xs + ys * ys) / nrm;
+	return p22_std(ndf, xs, ys) / nrm;
 }
 
 /* :1559-1570 */
@@ -797,3 +883,7 @@ ORC_API void orc_nmap2leanmap(const uint8_t *nmap, int w, int h, float base_roug
 		l2[3 * plane + px] = 1.f;
 	}
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * the power-iteration fits share this file's static helpers */
+#include "djb_oracle_fit.c"

@@ -1,4 +1,6 @@
 """Shared definitions of the parity cases (inputs are regenerated from seeds, never stored)."""
+import hashlib
+
 import numpy as np
 
 from oracle import api
@@ -108,3 +110,32 @@ def synthetic_nmap(h, w, seed=12345):
     g = rng.integers(64, 192, (h, w), dtype=np.uint8)
     b = rng.integers(128, 256, (h, w), dtype=np.uint8)
     return np.stack([r, g, b])
+
+
+# ---- tables made only of platform-independent arithmetic (PCG64 doubles, + - * /), for the golden files ----
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def random_merl_table(seed):
+    return np.random.default_rng(seed).uniform(-0.05, 3.0, 3 * api.MERL_CELLS)
+
+
+def random_utia_table(seed):
+    return np.random.default_rng(seed).uniform(-0.5, 60.0, 3 * 6 * 48 * 6 * 48)
+
+
+def smooth_merl_table(seed):
+    """A fit-able table made only of exactly reproducible arithmetic: a radially decreasing lobe in the
+    theta_h index plus a diffuse floor, jittered by PCG64 (no libm calls)."""
+    rng = np.random.default_rng(seed)
+    width = float(rng.integers(4, 40))
+    k = np.arange(90, dtype=np.float64)
+    lobe = 1.0 / (1.0 + (k / width) ** 2) ** 2            # over theta_h index
+    td = 1.0 + (np.arange(90, dtype=np.float64) / 89.0) ** 4  # mild growth towards grazing theta_d
+    base = lobe[:, None, None] * td[None, :, None] * np.ones((1, 1, 180))
+    planes = []
+    for c, tint in enumerate((900.0, 700.0, 500.0)):
+        jitter = 1.0 + 0.01 * rng.random(base.shape)
+        planes.append((tint * base * jitter + 30.0 * (c + 1)).reshape(-1))
+    return np.concatenate(planes)
