@@ -17,7 +17,7 @@ std::atomic<uint64_t> g_kernel_launches{0};
 
 static thread_local std::string t_error;
 
-static djb200_status fail(djb200_status s, const char *fmt, ...)
+djb200_status fail(djb200_status s, const char *fmt, ...)
 {
 	char buf[512];
 	va_list ap;
@@ -28,7 +28,7 @@ static djb200_status fail(djb200_status s, const char *fmt, ...)
 	return s;
 }
 
-static djb200_status cuda_fail(cudaError_t e, const char *what)
+djb200_status cuda_fail(cudaError_t e, const char *what)
 {
 	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
 		return fail(DJB200_ERR_NO_DEVICE, "%s: no CUDA device (%s); libdjb200 has no CPU fallback", what,
@@ -55,7 +55,7 @@ int sm_count()
 	return cached > 0 ? cached : 148;
 }
 
-static djb200_status require_device()
+djb200_status require_device()
 {
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
@@ -332,16 +332,6 @@ using namespace djb200;
 
 // ====================================================================================================
 extern "C" {
-
-struct djb200_merl {
-	float4 *cells;
-	int device;
-};
-
-struct djb200_utia {
-	float *table;
-	int device;
-};
 
 const char *djb200_last_error(void) { return t_error.c_str(); }
 const char *djb200_version(void) { return "djb200 0.1 (sm_100a)"; }

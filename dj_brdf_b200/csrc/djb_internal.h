@@ -5,7 +5,22 @@
 #include <atomic>
 #include "../../include/djb200.h"
 
+// opaque handles of include/djb200.h: device-resident, immutable after creation
+struct djb200_merl {
+	float4 *cells; // one (r, g, b, 0) per cell, already multiplied by the MERL channel scales
+	int device;
+};
+struct djb200_utia {
+	float *table; // utia::normalize()d samples cast to float
+	int device;
+};
+
 namespace djb200 {
+
+// error plumbing of the C-ABI layer (capi.cu)
+djb200_status fail(djb200_status s, const char *fmt, ...);
+djb200_status cuda_fail(cudaError_t e, const char *what);
+djb200_status require_device();
 
 enum MfOp { OP_EVAL = 0, OP_EVALP = 1, OP_PDF = 2, OP_SAMPLE = 3, OP_EVALP_IS = 4 };
 
@@ -46,5 +61,12 @@ cudaError_t launch_lrep_to_params(const float *E, int64_t n, void *out_params, c
 cudaError_t launch_params_to_lrep(const void *params, int64_t n, float *E, cudaStream_t st);
 cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int64_t npix, float bias,
                                      void *out_params, cudaStream_t st);
+
+// fits (kernels_fit.cu)
+struct FitSourceDev;
+size_t fit_tabular_smem_bytes(int res);
+cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
+                               double *K_ws, float *grid_ws, float *p22, float *sigma, float *cdf, float *qf,
+                               float *fresnel, float *alpha, float *residuals, cudaStream_t st);
 
 } // namespace djb200

@@ -25,17 +25,6 @@ struct MfKernelArgs {
 	float *out0, *out1, *out2;
 };
 
-DJB_DEV V3 fresnel_rt(int kind, const FresnelDev &f, float c)
-{
-	switch (kind) {
-	case FK_SCHLICK: return fresnel_eval<FK_SCHLICK>(f, c);
-	case FK_UNPOLARIZED: return fresnel_eval<FK_UNPOLARIZED>(f, c);
-	case FK_SGD: return fresnel_eval<FK_SGD>(f, c);
-	case FK_SPLINE: return fresnel_eval<FK_SPLINE>(f, c);
-	default: return mk(1.f, 1.f, 1.f);
-	}
-}
-
 // evalp with a run-time Fresnel kind (uniform across the grid, so the switch never diverges)
 template <int NDF>
 DJB_DEV V3 evalp_rt(const Params &p, int fk, const FresnelDev &f, bool shadow, V3 i, V3 o, V3 h)

@@ -127,9 +127,6 @@ cudaError_t launch_merl_index(const float *wi, const float *wo, int64_t n, int32
 }
 
 // ---- UTIA, dj_brdf.h:1039-1177 ---------------------------------------------------------------------
-constexpr int UT_NTI = 6, UT_NPI = 48, UT_NTV = 6, UT_NPV = 48;
-constexpr int UT_CELLS = 3 * UT_NTI * UT_NPI * UT_NTV * UT_NPV;
-
 // utia::normalize (clamp at 0, scale by the float constant 1/140 in double) followed by the
 // (float_t) cast utia::eval applies to every fetched sample (:1144, 1162-1177)
 __global__ void __launch_bounds__(TB) utia_convert_kernel(const double *raw, float *table)
@@ -140,61 +137,6 @@ __global__ void __launch_bounds__(TB) utia_convert_kernel(const double *raw, flo
 	v = 0.0 > v ? 0.0 : v;
 	const float k = 1.f / 140.f;
 	table[c] = (float)(v * (double)k);
-}
-
-DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
-{
-	const float r2d = (float)(180.0 / DJB_PI);
-	float ti = (float)((double)r2d * acos((double)i.z)), to = (float)((double)r2d * acos((double)o.z));
-	float pi = (float)((double)r2d * atan2((double)i.y, (double)i.x));
-	float po = (float)((double)r2d * atan2((double)o.y, (double)o.x));
-	if (ti >= 90.0f || to >= 90.0f) return mk(0.f, 0.f, 0.f);
-	while (pi < 0.0f) pi = (float)((double)pi + 360.0);
-	while (po < 0.0f) po = (float)((double)po + 360.0);
-	while (pi >= 360.0f) pi = (float)((double)pi - 360.0);
-	while (po >= 360.0f) po = (float)((double)po - 360.0);
-	int iti[2], itv[2], ipi[2], ipv[2];
-	iti[0] = (int)floor((double)ti / 15.0); iti[1] = iti[0] + 1;
-	if (iti[0] > UT_NTI - 2) { iti[0] = UT_NTI - 2; iti[1] = UT_NTI - 1; }
-	itv[0] = (int)floor((double)to / 15.0); itv[1] = itv[0] + 1;
-	if (itv[0] > UT_NTV - 2) { itv[0] = UT_NTV - 2; itv[1] = UT_NTV - 1; }
-	ipi[0] = (int)floor((double)pi / 7.5); ipi[1] = ipi[0] + 1;
-	ipv[0] = (int)floor((double)po / 7.5); ipv[1] = ipv[0] + 1;
-	float sum, wti[2], wtv[2], wpi[2], wpv[2];
-	wti[1] = ti - (float)(15.0 * iti[0]); wti[0] = (float)(15.0 * iti[1]) - ti;
-	sum = wti[0] + wti[1]; wti[0] /= sum; wti[1] /= sum;
-	wtv[1] = to - (float)(15.0 * itv[0]); wtv[0] = (float)(15.0 * itv[1]) - to;
-	sum = wtv[0] + wtv[1]; wtv[0] /= sum; wtv[1] /= sum;
-	wpi[1] = pi - (float)(7.5 * ipi[0]); wpi[0] = (float)(7.5 * ipi[1]) - pi;
-	sum = wpi[0] + wpi[1]; wpi[0] /= sum; wpi[1] /= sum;
-	wpv[1] = po - (float)(7.5 * ipv[0]); wpv[0] = (float)(7.5 * ipv[1]) - po;
-	sum = wpv[0] + wpv[1]; wpv[0] /= sum; wpv[1] /= sum;
-	if (ipi[1] == UT_NPI) ipi[1] = 0;
-	if (ipv[1] == UT_NPV) ipv[1] = 0;
-	const int nc = UT_NPV * UT_NTV, nr = UT_NPI * UT_NTI;
-	float rgb[3];
-#pragma unroll
-	for (int isp = 0; isp < 3; ++isp) {
-		float acc = 0.0f;
-#pragma unroll
-		for (int a = 0; a < 2; ++a)
-#pragma unroll
-		for (int b = 0; b < 2; ++b)
-#pragma unroll
-		for (int c = 0; c < 2; ++c)
-#pragma unroll
-		for (int d = 0; d < 2; ++d) {
-			float w = wti[a] * wtv[b] * wpi[c] * wpv[d];
-			int idx = isp * nr * nc + nc * (UT_NPI * iti[a] + ipi[c]) + UT_NPV * itv[b] + ipv[d];
-			acc += w * __ldg(tab + idx);
-		}
-		if ((double)acc > 0.0375)
-			acc = (float)pow((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f);
-		else
-			acc /= 12.92f;
-		rgb[isp] = acc * 100.0f;
-	}
-	return mk(fmax_ref(0.0f, rgb[0]), fmax_ref(0.0f, rgb[1]), fmax_ref(0.0f, rgb[2]));
 }
 
 __global__ void __launch_bounds__(TB) utia_eval_kernel(const float *__restrict__ tab, const float *__restrict__ wi,
