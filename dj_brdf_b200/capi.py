@@ -36,6 +36,8 @@ EXPORTED_SYMBOLS = [
     "djb200_utia_create", "djb200_utia_load", "djb200_utia_destroy", "djb200_utia_eval",
     "djb200_nmap_to_leanmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
     "djb200_fit_tabular", "djb200_fit_tabular_anisotropic",
+    "djb200_aniso_fit_create", "djb200_aniso_fit_destroy", "djb200_aniso_fit_size", "djb200_aniso_fit_matvec",
+    "djb200_aniso_fit_set_iterate", "djb200_aniso_fit_sigma", "djb200_aniso_fit_finish", "djb200_aniso_fit_download",
 ]
 
 
@@ -84,6 +86,7 @@ def load():
     lib.djb200_last_error.restype = C.c_char_p
     lib.djb200_version.restype = C.c_char_p
     lib.djb200_kernel_launch_count.restype = C.c_uint64
+    lib.djb200_aniso_fit_size.restype = C.c_int64
     _lib = lib
     return lib
 

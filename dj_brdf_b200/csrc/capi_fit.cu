@@ -141,10 +141,164 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 	return DJB200_OK;
 }
 
-djb200_status djb200_fit_tabular_anisotropic(const djb200_source *, int32_t, int32_t, int32_t, int32_t, int32_t,
-                                             djb200_tabular_anisotropic_fit *, void *)
+// ---- anisotropic fit ---------------------------------------------------------------------------------
+struct djb200_aniso_fit {
+	int er, ar, shadow, n, device;
+	FitSourceDev src;
+	DevBuf spline, rowpre, colpre, ones, p22, sigma, fresnel, terms, scale, pre_f, pre_d, params;
+};
+
+#define ACU(call)                                                \
+	do {                                                         \
+		cudaError_t e__ = (call);                                \
+		if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
+	} while (0)
+
+djb200_status djb200_aniso_fit_create(const djb200_source *source, int32_t elev_res, int32_t azim_res, int32_t shadow,
+                                      void *stream, djb200_aniso_fit **out)
 {
-	return fail(DJB200_ERR_UNSUPPORTED, "anisotropic fit: not built yet");
+	if (!source || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (elev_res <= 1 || azim_res <= 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid Resolution"); // dj_brdf.h:2244
+	if ((int64_t)(elev_res - 1) * azim_res > (1 << 24)) return fail(DJB200_ERR_UNSUPPORTED, "resolution too large");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	std::vector<FitSourceDev> src;
+	std::vector<DevBuf> splines;
+	rs = build_sources(source, 1, src, splines);
+	if (rs != DJB200_OK) return rs;
+	djb200_aniso_fit *f = new djb200_aniso_fit;
+	f->er = elev_res; f->ar = azim_res; f->shadow = shadow; f->n = (elev_res - 1) * azim_res;
+	cudaGetDevice(&f->device);
+	f->src = src[0];
+	f->spline.p = splines[0].p; splines[0].p = nullptr; // the handle keeps the spline points alive
+	const size_t n = (size_t)f->n, tab = (size_t)elev_res * azim_res;
+	cudaError_t e = f->rowpre.alloc(sizeof(float4) * n);
+	if (e == cudaSuccess) e = f->colpre.alloc(sizeof(float4) * n);
+	if (e == cudaSuccess) e = f->ones.alloc(sizeof(double) * n);
+	if (e == cudaSuccess) e = f->p22.alloc(sizeof(float) * tab);
+	if (e == cudaSuccess) e = f->sigma.alloc(sizeof(float) * tab);
+	if (e == cudaSuccess) e = f->fresnel.alloc(sizeof(float) * 3 * elev_res);
+	if (e == cudaSuccess) e = f->terms.alloc(sizeof(float) * 7 * 512 * 128);
+	if (e == cudaSuccess) e = f->scale.alloc(sizeof(float) * 4);
+	if (e == cudaSuccess) e = f->pre_f.alloc(sizeof(float) * aniso_sigma_pre_floats(azim_res));
+	if (e == cudaSuccess) e = f->pre_d.alloc(sizeof(double) * aniso_sigma_pre_doubles(azim_res));
+	if (e == cudaSuccess) e = f->params.alloc(sizeof(float) * 10);
+	if (e == cudaSuccess)
+		e = aniso_launch_pre(f->src, elev_res, azim_res, f->rowpre.as<float4>(), f->colpre.as<float4>(), f->ones.as<double>(),
+		                     (cudaStream_t)stream);
+	if (e != cudaSuccess) { delete f; return cuda_fail(e, "aniso fit setup"); }
+	*out = f;
+	return DJB200_OK;
+}
+
+djb200_status djb200_aniso_fit_destroy(djb200_aniso_fit *f)
+{
+	delete f;
+	return DJB200_OK;
+}
+
+int64_t djb200_aniso_fit_size(const djb200_aniso_fit *f) { return f ? f->n : 0; }
+
+djb200_status djb200_aniso_fit_matvec(djb200_aniso_fit *f, const double *v_in, double *v_out, int64_t row0, int64_t row1,
+                                      void *stream)
+{
+	if (!f || !v_out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (row0 < 0 || row1 > f->n || row0 > row1) return fail(DJB200_ERR_INVALID_ARGUMENT, "row range [%lld, %lld) outside [0, %d)", (long long)row0, (long long)row1, f->n);
+	ACU(aniso_launch_matvec(f->er, f->ar, f->rowpre.as<float4>(), f->colpre.as<float4>(), v_in ? v_in : f->ones.as<double>(),
+	                        v_out, (int)row0, (int)row1, (cudaStream_t)stream));
+	return DJB200_OK;
+}
+
+djb200_status djb200_aniso_fit_set_iterate(djb200_aniso_fit *f, const double *v, void *stream)
+{
+	if (!f || !v) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	ACU(aniso_launch_p22(f->er, f->ar, v, f->p22.as<float>(), f->terms.as<float>(), f->scale.as<float>(), (cudaStream_t)stream));
+	return DJB200_OK;
+}
+
+djb200_status djb200_aniso_fit_sigma(djb200_aniso_fit *f, float *sigma_rows, int64_t row0, int64_t row1, void *stream)
+{
+	if (!f || !sigma_rows) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (row0 < 0 || row1 > f->n || row0 > row1) return fail(DJB200_ERR_INVALID_ARGUMENT, "row range outside [0, %d)", f->n);
+	ACU(aniso_launch_sigma(f->er, f->ar, f->p22.as<float>(), f->pre_f.as<float>(), f->pre_d.as<double>(), sigma_rows, (int)row0,
+	                       (int)row1, (cudaStream_t)stream));
+	return DJB200_OK;
+}
+
+djb200_status djb200_aniso_fit_finish(djb200_aniso_fit *f, const float *sigma_rows, void *stream)
+{
+	if (!f || !sigma_rows) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	ACU(aniso_launch_finish(f->src, f->er, f->ar, f->shadow, f->p22.as<float>(), sigma_rows, f->sigma.as<float>(),
+	                        f->fresnel.as<float>(), f->terms.as<float>(), f->params.as<float>(), f->params.as<float>() + 5,
+	                        (cudaStream_t)stream));
+	return DJB200_OK;
+}
+
+djb200_status djb200_aniso_fit_download(djb200_aniso_fit *f, djb200_tabular_anisotropic_fit *r, void *stream)
+{
+	if (!f || !r) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (r->elev_res != f->er || r->azim_res != f->ar) return fail(DJB200_ERR_INVALID_ARGUMENT, "result resolution mismatch");
+	if (!r->p22 || !r->sigma || !r->fresnel) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL output array");
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t tab = (size_t)f->er * f->ar;
+	float params[10];
+	ACU(cudaMemcpyAsync(r->p22, f->p22.p, sizeof(float) * tab, cudaMemcpyDeviceToHost, st));
+	ACU(cudaMemcpyAsync(r->sigma, f->sigma.p, sizeof(float) * tab, cudaMemcpyDeviceToHost, st));
+	ACU(cudaMemcpyAsync(r->fresnel, f->fresnel.p, sizeof(float) * 3 * f->er, cudaMemcpyDeviceToHost, st));
+	ACU(cudaMemcpyAsync(params, f->params.p, sizeof params, cudaMemcpyDeviceToHost, st));
+	ACU(cudaStreamSynchronize(st));
+	memcpy(r->beckmann, params, sizeof(float) * 5);
+	memcpy(r->ggx, params + 5, sizeof(float) * 5);
+	return DJB200_OK;
+}
+
+// the whole fit on one GPU: the stages above over the full row range, materials one after the other (each
+// stage is a grid-wide launch, so one material already fills the device)
+djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sources, int32_t n_sources, int32_t elev_res,
+                                             int32_t azim_res, int32_t shadow, int32_t iterations,
+                                             djb200_tabular_anisotropic_fit *results, void *stream)
+{
+	if (n_sources < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative source count");
+	if (elev_res <= 1 || azim_res <= 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid Resolution");
+	if (iterations < 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one power iteration");
+	if (n_sources == 0) return DJB200_OK;
+	if (!sources || !results) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	cudaStream_t st = (cudaStream_t)stream;
+	for (int32_t k = 0; k < n_sources; ++k) {
+		djb200_aniso_fit *f = nullptr;
+		djb200_status rs = djb200_aniso_fit_create(sources + k, elev_res, azim_res, shadow, stream, &f);
+		if (rs != DJB200_OK) return rs;
+		const int64_t n = f->n;
+		DevBuf va, vb, srows, resid;
+		cudaError_t e = va.alloc(sizeof(double) * n);
+		if (e == cudaSuccess) e = vb.alloc(sizeof(double) * n);
+		if (e == cudaSuccess) e = srows.alloc(sizeof(float) * n);
+		if (e == cudaSuccess) e = resid.alloc(sizeof(float) * iterations);
+		if (e != cudaSuccess) { delete f; return cuda_fail(e, "aniso fit workspace"); }
+		const double *vin = nullptr;
+		double *bufs[2] = {va.as<double>(), vb.as<double>()};
+		for (int it = 0; it < iterations && rs == DJB200_OK; ++it) {
+			double *vout = bufs[it & 1];
+			rs = djb200_aniso_fit_matvec(f, vin, vout, 0, n, stream);
+			if (rs == DJB200_OK && results[k].residuals) {
+				e = aniso_launch_residual((int)n, vin ? vin : f->ones.as<double>(), vout, resid.as<float>() + it, st);
+				if (e != cudaSuccess) rs = cuda_fail(e, "residual kernel");
+			}
+			vin = vout;
+		}
+		if (rs == DJB200_OK) rs = djb200_aniso_fit_set_iterate(f, vin, stream);
+		if (rs == DJB200_OK) rs = djb200_aniso_fit_sigma(f, srows.as<float>(), 0, n, stream);
+		if (rs == DJB200_OK) rs = djb200_aniso_fit_finish(f, srows.as<float>(), stream);
+		if (rs == DJB200_OK) rs = djb200_aniso_fit_download(f, results + k, stream);
+		if (rs == DJB200_OK && results[k].residuals) {
+			e = cudaMemcpy(results[k].residuals, resid.p, sizeof(float) * iterations, cudaMemcpyDeviceToHost);
+			if (e != cudaSuccess) rs = cuda_fail(e, "residual download");
+		}
+		cudaStreamSynchronize(st);
+		delete f;
+		if (rs != DJB200_OK) return rs;
+	}
+	return DJB200_OK;
 }
 
 } // extern "C"

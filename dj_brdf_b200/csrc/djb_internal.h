@@ -69,4 +69,19 @@ cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials,
                                double *K_ws, float *grid_ws, float *p22, float *sigma, float *cdf, float *qf,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st);
 
+// anisotropic fit stages; [row0, row1) = this GPU's shard of the n = (er - 1) * ar rows
+cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *rowpre, float4 *colpre, double *v_ones,
+                             cudaStream_t st);
+cudaError_t aniso_launch_matvec(int er, int ar, const float4 *rowpre, const float4 *colpre, const double *v_in,
+                                double *v_out, int row0, int row1, cudaStream_t st);
+cudaError_t aniso_launch_residual(int n, const double *v0, const double *v1, float *out, cudaStream_t st);
+cudaError_t aniso_launch_p22(int er, int ar, const double *v, float *p22, float *terms, float *scale_tmp, cudaStream_t st);
+size_t aniso_sigma_pre_floats(int ar);
+size_t aniso_sigma_pre_doubles(int ar);
+cudaError_t aniso_launch_sigma(int er, int ar, const float *p22, float *pre_f, double *pre_d, float *sigma_rows, int row0,
+                               int row1, cudaStream_t st);
+cudaError_t aniso_launch_finish(const FitSourceDev &src, int er, int ar, int shadow, const float *p22,
+                                const float *sigma_rows, float *sigma, float *fresnel, float *terms, float *beckmann5,
+                                float *ggx5, cudaStream_t st);
+
 } // namespace djb200

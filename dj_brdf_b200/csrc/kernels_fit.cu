@@ -300,3 +300,363 @@ cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials,
 size_t fit_tabular_smem_bytes(int res) { return iso_smem_bytes(res); }
 
 } // namespace djb200
+
+// =====================================================================================================
+// Anisotropic fit, djb::tabular_anisotropic (dj_brdf.h:2238-2273).  n = w * h unknowns (w = elevation_res - 1,
+// h = azimuthal_res).  The reference materialises the n x n kernel matrix in fp64 (513 MB at 90 x 90) and
+// multiplies by it four times; an entry is a product of a row factor and a "ReLU-dot" of a row vector with a
+// column vector (dj_brdf.h:2548-2564), so the matvec below recomputes entries on the fly -- same float
+// roundings, same summation order, no 513 MB of HBM traffic per iteration.
+namespace djb200 {
+
+struct AnisoGeom {
+	int er, ar, w, h, n; // elevation_res, azimuthal_res, w = er - 1, h = ar, n = w * h
+};
+
+// row factors {zo, xo, yo, kji_tmp1} and column factors {tan_theta, slope1, slope2, cos_theta^2}: both live on
+// the same (theta_i1, phi_i2) grid, dj_brdf.h:2536-2561
+__global__ void __launch_bounds__(FIT_THREADS) aniso_pre_kernel(FitSourceDev src, AnisoGeom g, float4 *rowpre, float4 *colpre)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= g.n) return;
+	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+	const float dtheta = (float)(sqrt_half_pi / (double)(float)g.w);
+	const float dphi = (float)(2.0 * DJB_PI / (double)(float)g.h);
+	int i2 = r / g.w, i1 = r - i2 * g.w;
+	float t1 = (float)i1 / (float)g.w, t2 = (float)i2 / (float)g.h;
+	float theta = (float)((double)t1 * 0.5 * DJB_PI), phi = (float)((double)t2 * 2.0 * DJB_PI);
+	double st, ct, sp, cp;
+	sincos((double)theta, &st, &ct);
+	sincos((double)phi, &sp, &cp);
+	float sin_theta = (float)st, zo = (float)ct;
+	float xo = (float)((double)sin_theta * cp), yo = (float)((double)sin_theta * sp);
+	V3 dir = spherical(theta, phi);
+	float fr_i = intensity(source_eval(src, dir, dir));
+	float kji1 = (float)((double)(dtheta * dphi) * (4.0 * (double)fr_i * pow((double)zo, 5.0)));
+	rowpre[r] = make_float4(zo, xo, yo, kji1);
+	float cos_theta = zo, tan_theta = (float)tan((double)theta);
+	float s1 = (float)((double)(-tan_theta) * cp), s2 = (float)((double)(-tan_theta) * sp);
+	colpre[r] = make_float4(tan_theta, s1, s2, cos_theta * cos_theta);
+}
+
+// out[r] = sum_k K(r, k) v[k] for r in [row0, row1), k ascending (matrix::transform, dj_brdf.h:2456-2465)
+__global__ void __launch_bounds__(64) aniso_matvec_kernel(AnisoGeom g, const float4 *__restrict__ rowpre,
+                                                          const float4 *__restrict__ colpre, const double *__restrict__ v,
+                                                          double *__restrict__ out, int row0, int row1)
+{
+	int r = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= row1) return;
+	const float4 rp = rowpre[r];
+	double acc = 0.0;
+#pragma unroll 4
+	for (int k = 0; k < g.n; ++k) {
+		const float4 c = __ldg(colpre + k);
+		float m_dot_o = rp.x - rp.y * c.y - rp.z * c.z;
+		float kji2 = c.x * fmax_ref(0.0f, m_dot_o) / c.w;
+		acc += (double)(rp.w * kji2) * __ldg(v + k);
+	}
+	out[r] = acc;
+}
+
+__global__ void fill_ones_kernel(double *v, int n)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) v[k] = 1.0;
+}
+
+// diagnostic: || v1/|v1| - v0/|v0| ||_2 (not in the reference; order of this reduction is irrelevant)
+__global__ void __launch_bounds__(FIT_THREADS) aniso_residual_kernel(const double *v0, const double *v1, int n, float *out)
+{
+	__shared__ double red[3][FIT_THREADS];
+	double a = 0, b = 0, c = 0;
+	for (int k = threadIdx.x; k < n; k += blockDim.x) { a += v0[k] * v0[k]; b += v1[k] * v1[k]; c += v0[k] * v1[k]; }
+	red[0][threadIdx.x] = a; red[1][threadIdx.x] = b; red[2][threadIdx.x] = c;
+	__syncthreads();
+	for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+		if (threadIdx.x < s)
+			for (int q = 0; q < 3; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { // |a/|a| - b/|b||^2 = 2 - 2 a.b / (|a||b|)
+		double d = 2.0 - 2.0 * red[2][0] / (sqrt(red[0][0]) * sqrt(red[1][0]));
+		*out = (float)sqrt(d > 0.0 ? d : 0.0);
+	}
+}
+
+// m_p22 from the iterate, with the zero column at theta = pi/2 (dj_brdf.h:2570-2578)
+__global__ void aniso_p22_kernel(AnisoGeom g, const double *v, float *p22)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= g.er * g.ar) return;
+	int j = e / g.er, i = e - j * g.er;
+	p22[e] = i < g.w ? (float)v[j * g.w + i] : 0.0f;
+}
+
+constexpr int AN_NTHETA = 128, AN_NPHI = 256;   // normalize_p22, dj_brdf.h:2308-2309
+constexpr int AP_NTHETA = 128, AP_NPHI = 512;   // fit_*_parameters, dj_brdf.h:3189-3190
+constexpr int AS_NTHETA = 45, AS_NPHI = 90;     // compute_sigma, dj_brdf.h:2390-2391
+
+// the 256 x 128 terms of normalize_p22 (dj_brdf.h:2314-2327), phi-major like the reference's loops
+__global__ void aniso_norm_terms_kernel(AnisoGeom g, const float *p22, float *terms)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= AN_NPHI * AN_NTHETA) return;
+	int j = e / AN_NTHETA, i = e - j * AN_NTHETA;
+	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+	TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar;
+	float u = (float)j / (float)AN_NPHI;
+	float phi = (float)((double)u * 2.0 * DJB_PI);
+	float ui = (float)i / (float)AN_NTHETA;
+	float theta = (float)((double)ui * sqrt_half_pi);
+	float theta_sqr = theta * theta;
+	float c = (float)cos((double)theta_sqr);
+	float pdf = t.p22_theta_phi(theta_sqr, phi);
+	float weight = (float)(((double)theta * tan((double)theta_sqr)) / (double)(c * c));
+	terms[e] = weight * pdf;
+}
+
+// one thread adds the terms in the reference's order and derives the normalisation constant
+__global__ void aniso_norm_sum_kernel(const float *terms, float *scale_out)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+	float k = 0.0f;
+	for (int e = 0; e < AN_NPHI * AN_NTHETA; ++e) k += terms[e];
+	float dtheta = (float)(sqrt(0.5 * DJB_PI) / (double)(float)AN_NTHETA);
+	float dphi = (float)(2.0 * DJB_PI / (double)(float)AN_NPHI);
+	(void)sqrt_half_pi;
+	k = (float)((double)k * (2.0 * (double)dtheta * (double)dphi));
+	*scale_out = (float)(1.0 / (double)k);
+}
+
+__global__ void aniso_scale_kernel(float *p22, int n, const float *scale)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < n) p22[e] *= *scale;
+}
+
+// compute_sigma tables that do not depend on the view direction (dj_brdf.h:2397-2421):
+//   nd[j2 * 45 + j1] = ndf(vec3(theta_sqr, phi)),  cth[j1] = cos(theta_sqr) (double), sth[j1], th[j1],
+//   cdp[i2 * 90 + j2] = cos(phi_j2 - phi_k(i2)) (double, the difference formed in float)
+__global__ void aniso_sigma_pre_kernel(AnisoGeom g, const float *p22, float *nd, double *cth, float *sth, float *th, double *cdp)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+	if (e < AS_NPHI * AS_NTHETA) {
+		int j2 = e / AS_NTHETA, j1 = e - j2 * AS_NTHETA;
+		TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar;
+		float phi = (float)((double)((float)j2 / (float)AS_NPHI) * 2.0 * DJB_PI);
+		float theta = (float)((double)((float)j1 / (float)AS_NTHETA) * sqrt_half_pi);
+		nd[e] = tab_ndf(t, standard_params(), spherical(theta * theta, phi));
+	}
+	if (e < AS_NTHETA) {
+		float theta = (float)((double)((float)e / (float)AS_NTHETA) * sqrt_half_pi);
+		float theta_sqr = theta * theta;
+		cth[e] = cos((double)theta_sqr);
+		sth[e] = (float)sin((double)theta_sqr);
+		th[e] = theta;
+	}
+	if (e < g.h * AS_NPHI) {
+		int i2 = e / AS_NPHI, j2 = e - i2 * AS_NPHI;
+		float phi_k = (float)((double)((float)i2 / (float)g.h) * 2.0 * DJB_PI);
+		float phi = (float)((double)((float)j2 / (float)AS_NPHI) * 2.0 * DJB_PI);
+		cdp[e] = cos((double)(phi - phi_k));
+	}
+}
+
+// sigma_rows[r] for r = i2 * w + i1 in [row0, row1): the 90 x 45 quadrature in the reference's order
+__global__ void __launch_bounds__(64) aniso_sigma_kernel(AnisoGeom g, const float *__restrict__ nd, const double *__restrict__ cth,
+                                                         const float *__restrict__ sth, const float *__restrict__ th,
+                                                         const double *__restrict__ cdp, float *__restrict__ sigma_rows,
+                                                         int row0, int row1)
+{
+	__shared__ double s_cth[AS_NTHETA];
+	__shared__ float s_sth[AS_NTHETA], s_w[AS_NTHETA];
+	for (int k = threadIdx.x; k < AS_NTHETA; k += blockDim.x) {
+		s_cth[k] = cth[k];
+		s_sth[k] = sth[k];
+		s_w[k] = th[k] * sth[k]; // weight = theta * sin_theta
+	}
+	__syncthreads();
+	int r = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= row1) return;
+	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+	const float dtheta = (float)(sqrt_half_pi / (double)(float)AS_NTHETA);
+	const float dphi = (float)(2.0 * DJB_PI / (double)(float)AS_NPHI);
+	int i2 = r / g.w, i1 = r - i2 * g.w;
+	float theta_k = (float)((double)((float)i1 / (float)g.w) * 0.5 * DJB_PI);
+	float cos_theta_k = (float)cos((double)theta_k);
+	const double sin_k = sin((double)theta_k), cos_k = (double)cos_theta_k;
+	float nint = 0.0f;
+	for (int j2 = 0; j2 < AS_NPHI; ++j2) {
+		const double cd = __ldg(cdp + i2 * AS_NPHI + j2);
+		const float *ndrow = nd + j2 * AS_NTHETA;
+#pragma unroll 5
+		for (int j1 = 0; j1 < AS_NTHETA; ++j1) {
+			float m_dot_k = (float)(sin_k * (double)s_sth[j1] * cd + cos_k * s_cth[j1]);
+			float masking = fmax_ref(0.0f, m_dot_k) * __ldg(ndrow + j1);
+			nint += s_w[j1] * masking;
+		}
+	}
+	nint = (float)((double)nint * (2.0 * (double)dtheta * (double)dphi));
+	sigma_rows[r] = fmax_ref(cos_theta_k, nint);
+}
+
+// sigma table (er x ar, with the duplicated last elevation, dj_brdf.h:2426) from the per-row values
+__global__ void aniso_sigma_table_kernel(AnisoGeom g, const float *sigma_rows, float *sigma)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= g.er * g.ar) return;
+	int j = e / g.er, i = e - j * g.er;
+	sigma[e] = sigma_rows[j * g.w + (i < g.w ? i : g.w - 1)];
+}
+
+// compute_fresnel, dj_brdf.h:2643-2701
+__global__ void __launch_bounds__(FIT_THREADS) aniso_fresnel_kernel(FitSourceDev src, AnisoGeom g, int shadow, const float *p22,
+                                                                    const float *sigma, float *fresnel)
+{
+	TabAniso t; t.p22 = p22; t.sigma = sigma; t.w = g.er; t.h = g.ar;
+	const int cnt = g.er - 1;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+		V3 f = fresnel_bin(t, src, shadow != 0, i, cnt);
+		fresnel[3 * i] = f.x; fresnel[3 * i + 1] = f.y; fresnel[3 * i + 2] = f.z;
+		if (i == cnt - 1) { fresnel[3 * cnt] = f.x; fresnel[3 * cnt + 1] = f.y; fresnel[3 * cnt + 2] = f.z; }
+	}
+}
+
+// the 512 x 128 terms of fit_beckmann_parameters / fit_ggx_parameters (dj_brdf.h:3196-3226, 3260-3286):
+// seven distinct sequences -- tmp2*e1, tmp2*e2 (shared), tmp2*e3, tmp2*e4, tmp2*e5 (beckmann), tmp2*|e1|, tmp2*|e2| (ggx)
+__global__ void aniso_param_terms_kernel(AnisoGeom g, const float *p22, float *terms)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const int N = AP_NPHI * AP_NTHETA;
+	if (e >= N) return;
+	int j = e / AP_NTHETA, i = e - j * AP_NTHETA;
+	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+	TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar;
+	float phi = (float)((double)((float)j / (float)AP_NPHI) * 2.0 * DJB_PI);
+	float cos_phi = (float)cos((double)phi), sin_phi = (float)sin((double)phi);
+	float cos_phi_sqr = cos_phi * cos_phi, sin_phi_sqr = sin_phi * sin_phi;
+	float theta = (float)((double)((float)i / (float)AP_NTHETA) * sqrt_half_pi);
+	float theta_sqr = theta * theta;
+	float pv = t.p22_theta_phi(theta_sqr, phi);
+	float tan_theta = (float)tan((double)theta_sqr), cos_theta = (float)cos((double)theta_sqr);
+	float tan_theta_sqr = tan_theta * tan_theta, cos_theta_sqr = cos_theta * cos_theta;
+	float tmp2 = theta * pv * tan_theta / cos_theta_sqr;
+	float e1 = -tan_theta * cos_phi, e2 = -tan_theta * sin_phi;
+	float e3 = tan_theta_sqr * cos_phi_sqr, e4 = tan_theta_sqr * sin_phi_sqr;
+	float e5 = tan_theta_sqr * cos_phi * sin_phi;
+	terms[0 * N + e] = tmp2 * e1;
+	terms[1 * N + e] = tmp2 * e2;
+	terms[2 * N + e] = tmp2 * e3;
+	terms[3 * N + e] = tmp2 * e4;
+	terms[4 * N + e] = tmp2 * e5;
+	terms[5 * N + e] = tmp2 * fabsf(e1);
+	terms[6 * N + e] = tmp2 * fabsf(e2);
+}
+
+// seven lanes add their sequence in order; lane 0 then forms both parameter sets
+__global__ void aniso_param_sums_kernel(const float *terms, float *beckmann5, float *ggx5)
+{
+	__shared__ float s[7];
+	const int N = AP_NPHI * AP_NTHETA;
+	if (threadIdx.x < 7) {
+		const float *p = terms + (size_t)threadIdx.x * N;
+		float acc = 0.0f;
+		for (int e = 0; e < N; ++e) acc += p[e];
+		const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
+		float dtheta = (float)(sqrt_half_pi / (double)(float)AP_NTHETA);
+		float dphi = (float)(2.0 * DJB_PI / (double)(float)AP_NPHI);
+		s[threadIdx.x] = (float)((double)acc * (2.0 * (double)dtheta * (double)dphi));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		float mux = s[0], muy = s[1];
+		float ax = (float)sqrt((double)(2.0f * (s[2] - mux * mux)));
+		float ay = (float)sqrt((double)(2.0f * (s[3] - muy * muy)));
+		float rho = (float)(2.0 * (double)(s[4] - mux * muy) / (double)(ax * ay));
+		beckmann5[0] = ax; beckmann5[1] = ay; beckmann5[2] = rho; beckmann5[3] = mux; beckmann5[4] = muy;
+		float gx = (float)sqrt((double)(s[5] * s[5] - mux * mux));
+		float gy = (float)sqrt((double)(s[6] * s[6] - muy * muy));
+		ggx5[0] = gx; ggx5[1] = gy; ggx5[2] = 0.0f; ggx5[3] = mux; ggx5[4] = muy;
+	}
+}
+
+// ---- host-side launchers (one material; [row0, row1) is this GPU's shard of the rows) ---------------------
+static inline void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
+
+cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *rowpre, float4 *colpre, double *v_ones, cudaStream_t st)
+{
+	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
+	aniso_pre_kernel<<<blocks_for(g.n, FIT_THREADS), FIT_THREADS, 0, st>>>(src, g, rowpre, colpre);
+	count_launch();
+	if (v_ones) {
+		fill_ones_kernel<<<blocks_for(g.n, 256), 256, 0, st>>>(v_ones, g.n);
+		count_launch();
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t aniso_launch_matvec(int er, int ar, const float4 *rowpre, const float4 *colpre, const double *v_in, double *v_out,
+                                int row0, int row1, cudaStream_t st)
+{
+	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
+	if (row1 <= row0) return cudaSuccess;
+	aniso_matvec_kernel<<<blocks_for(row1 - row0, 64), 64, 0, st>>>(g, rowpre, colpre, v_in, v_out, row0, row1);
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t aniso_launch_residual(int n, const double *v0, const double *v1, float *out, cudaStream_t st)
+{
+	aniso_residual_kernel<<<1, FIT_THREADS, 0, st>>>(v0, v1, n, out);
+	count_launch();
+	return cudaGetLastError();
+}
+
+// p22 table from the iterate + normalize_p22; `terms` holds >= 7 * 512 * 128 floats, scale_tmp 1 float
+cudaError_t aniso_launch_p22(int er, int ar, const double *v, float *p22, float *terms, float *scale_tmp, cudaStream_t st)
+{
+	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
+	aniso_p22_kernel<<<blocks_for(er * ar, 256), 256, 0, st>>>(g, v, p22);
+	aniso_norm_terms_kernel<<<blocks_for(AN_NPHI * AN_NTHETA, 256), 256, 0, st>>>(g, p22, terms);
+	aniso_norm_sum_kernel<<<1, 32, 0, st>>>(terms, scale_tmp);
+	aniso_scale_kernel<<<blocks_for(er * ar, 256), 256, 0, st>>>(p22, er * ar, scale_tmp);
+	for (int k = 0; k < 4; ++k) count_launch();
+	return cudaGetLastError();
+}
+
+size_t aniso_sigma_pre_floats(int ar) { return (size_t)AS_NPHI * AS_NTHETA + 2 * AS_NTHETA; }
+size_t aniso_sigma_pre_doubles(int ar) { return (size_t)AS_NTHETA + (size_t)ar * AS_NPHI; }
+
+cudaError_t aniso_launch_sigma(int er, int ar, const float *p22, float *pre_f, double *pre_d, float *sigma_rows, int row0,
+                               int row1, cudaStream_t st)
+{
+	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
+	float *nd = pre_f, *sth = nd + AS_NPHI * AS_NTHETA, *th = sth + AS_NTHETA;
+	double *cth = pre_d, *cdp = cth + AS_NTHETA;
+	int pre_n = AS_NPHI * AS_NTHETA;
+	if (g.h * AS_NPHI > pre_n) pre_n = g.h * AS_NPHI;
+	aniso_sigma_pre_kernel<<<blocks_for(pre_n, 256), 256, 0, st>>>(g, p22, nd, cth, sth, th, cdp);
+	count_launch();
+	if (row1 > row0) {
+		aniso_sigma_kernel<<<blocks_for(row1 - row0, 64), 64, 0, st>>>(g, nd, cth, sth, th, cdp, sigma_rows, row0, row1);
+		count_launch();
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t aniso_launch_finish(const FitSourceDev &src, int er, int ar, int shadow, const float *p22, const float *sigma_rows,
+                                float *sigma, float *fresnel, float *terms, float *beckmann5, float *ggx5, cudaStream_t st)
+{
+	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
+	aniso_sigma_table_kernel<<<blocks_for(er * ar, 256), 256, 0, st>>>(g, sigma_rows, sigma);
+	aniso_fresnel_kernel<<<blocks_for(er - 1, 32), 32, 0, st>>>(src, g, shadow, p22, sigma, fresnel);
+	aniso_param_terms_kernel<<<blocks_for(AP_NPHI * AP_NTHETA, 256), 256, 0, st>>>(g, p22, terms);
+	aniso_param_sums_kernel<<<1, 32, 0, st>>>(terms, beckmann5, ggx5);
+	for (int k = 0; k < 4; ++k) count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace djb200

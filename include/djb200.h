@@ -235,6 +235,33 @@ DJB200_API djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sou
                                                         int32_t iterations,
                                                         djb200_tabular_anisotropic_fit *results, void *stream);
 
+/* ---- anisotropic fit, stage by stage ------------------------------------------------------- *
+ * The same fit as djb200_fit_tabular_anisotropic(), split at the two places where a fit whose
+ * n = (elev_res - 1) * azim_res matrix rows are sharded over several GPUs has to exchange data: the
+ * iterate after every power iteration (matrix::transform, dj_brdf.h:2456-2465) and the projected-area
+ * values (compute_sigma, dj_brdf.h:2388-2432).  Each rank owns the rows [row0, row1); the host layer
+ * all-gathers `v_out` / `sigma_rows` between calls (NCCL through torch.distributed in
+ * dj_brdf_b200/fit_sharded.py).  All pointers below are DEVICE pointers. */
+typedef struct djb200_aniso_fit djb200_aniso_fit;
+DJB200_API djb200_status djb200_aniso_fit_create(const djb200_source *source, int32_t elev_res, int32_t azim_res,
+                                                 int32_t shadow, void *stream, djb200_aniso_fit **out);
+DJB200_API djb200_status djb200_aniso_fit_destroy(djb200_aniso_fit *f);
+/* number of unknowns n (length of the iterate) */
+DJB200_API int64_t djb200_aniso_fit_size(const djb200_aniso_fit *f);
+/* v_out[row0:row1] = (K v_in)[row0:row1]; v_in = NULL means the all-ones start vector (dj_brdf.h:2473-2474) */
+DJB200_API djb200_status djb200_aniso_fit_matvec(djb200_aniso_fit *f, const double *v_in, double *v_out, int64_t row0,
+                                                 int64_t row1, void *stream);
+/* slope pdf table from the final iterate + normalize_p22 (dj_brdf.h:2570-2578, 2306-2338) */
+DJB200_API djb200_status djb200_aniso_fit_set_iterate(djb200_aniso_fit *f, const double *v, void *stream);
+/* sigma_rows[row0:row1]: projected area for view direction r = i2 * (elev_res - 1) + i1 */
+DJB200_API djb200_status djb200_aniso_fit_sigma(djb200_aniso_fit *f, float *sigma_rows, int64_t row0, int64_t row1,
+                                                void *stream);
+/* sigma table, Fresnel table and the Beckmann / GGX parameter fits from the complete sigma_rows[n] */
+DJB200_API djb200_status djb200_aniso_fit_finish(djb200_aniso_fit *f, const float *sigma_rows, void *stream);
+/* copies the tables to host arrays of `result` (residuals are not touched) */
+DJB200_API djb200_status djb200_aniso_fit_download(djb200_aniso_fit *f, djb200_tabular_anisotropic_fit *result,
+                                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

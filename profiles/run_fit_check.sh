@@ -4,13 +4,12 @@ python - <<'PY'
 import time, numpy as np, torch
 import dj_brdf_b200 as djb
 from tests import cases
-tabs=[cases.smooth_merl_table(100+s) for s in range(8)]
-src=[djb.merl(t) for t in tabs]
-srcs=[src[k%8] for k in range(128)]
-for it in (4,50):
-    djb.tabular.fit_batch(srcs[:4],90,True,it)
+ut=cases.random_utia_table(12)
+src=djb.utia(ut)
+djb.tabular_anisotropic(src,20,20)
+for it in (4,):
     torch.cuda.synchronize(); t=time.perf_counter()
-    r=djb.tabular.fit_batch(srcs,90,True,it)
+    r=djb.tabular_anisotropic(src,90,90,True,it)
     torch.cuda.synchronize(); dt=time.perf_counter()-t
-    print(f"iters={it}: 128 fits in {dt*1e3:.2f} ms -> {128/dt:.0f} fits/s; alpha_ggx[0]={r[0].alpha_ggx}")
+    print(f"aniso 90x90 iters={it}: {dt*1e3:.1f} ms; beckmann={r.beckmann} ggx={r.ggx} resid={r.residuals}")
 PY
