@@ -1,0 +1,676 @@
+// djb200_facade.hpp -- C++ host side of the B200 BRDF engine: the reference's `djb::` class surface
+// (jdupuy/dj_brdf, dj_brdf.h:62-535) re-created on top of the C-ABI in djb200.h.
+//
+// A host program written against dj_brdf.h keeps its source: same class names, constructors, virtual
+// signatures, `microfacet::params` factories, fit constructors / accessors and LEAN `lrep` algebra.
+// What changes is where the numbers are computed: every query goes through libdjb200.so to the GPU.
+//   * scalar calls (`eval(i, o, &params)`) are batches of one -- correct, but one kernel launch each;
+//   * the added `*_batch` members are the intended path: arrays of directions in, arrays out, optionally
+//     already in device memory (`djb::device` tag) and under M parameter blocks at once.
+// There is no CPU implementation behind this header: if libdjb200.so or the GPU is missing, calls throw
+// djb::exc (the reference's own exception type, dj_brdf.h:54-59).
+//
+// Header-only; C++11; link with -ldjb200.
+#ifndef DJB200_FACADE_HPP
+#define DJB200_FACADE_HPP
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "djb200.h"
+
+#ifndef DJB_ASSERT
+#include <cassert>
+#define DJB_ASSERT(x) assert(x)
+#endif
+
+namespace djb {
+
+typedef float float_t; // DJB_USE_DOUBLE_PRECISION is not supported: the kernels mirror the float build
+
+// dj_brdf.h:54-59
+class exc : public std::exception {
+	std::string m_str;
+public:
+	exc(const char *fmt, ...)
+	{
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof buf, fmt, ap);
+		va_end(ap);
+		m_str = buf;
+	}
+	virtual ~exc() throw() {}
+	const char *what() const throw() { return m_str.c_str(); }
+};
+
+namespace detail {
+inline void check(djb200_status s)
+{
+	if (s != DJB200_OK) throw exc("djb_error: %s", djb200_last_error());
+}
+} // namespace detail
+
+enum memory_space { host = DJB200_MEM_HOST, device = DJB200_MEM_DEVICE };
+
+// dj_brdf.h:62-71.  Packed 12 bytes: an array of vec3 is the float[3] layout the C-ABI takes.
+struct vec3 {
+	static vec3 from_raw(const double *v) { return vec3((float_t)v[0], (float_t)v[1], (float_t)v[2]); }
+	static vec3 from_raw(const float *v) { return vec3(v[0], v[1], v[2]); }
+	static const float_t *to_raw(const vec3 &v) { return &v.x; }
+	explicit vec3(float_t s = 0) : x(s), y(s), z(s) {}
+	vec3(float_t x, float_t y, float_t z) : x(x), y(y), z(z) {}
+	explicit vec3(float_t theta, float_t phi)
+	{
+		float_t s = (float_t)std::sin((double)theta);
+		x = (float_t)((double)s * std::cos((double)phi));
+		y = (float_t)((double)s * std::sin((double)phi));
+		z = (float_t)std::cos((double)theta);
+	}
+	float_t intensity() const { return (float_t)0.2126 * x + (float_t)0.7152 * y + (float_t)0.0722 * z; }
+	float_t x, y, z;
+};
+static_assert(sizeof(vec3) == 12, "vec3 must stay packed");
+inline vec3 operator+(const vec3 &a, const vec3 &b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline vec3 operator-(const vec3 &a, const vec3 &b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline vec3 operator*(const vec3 &a, const vec3 &b) { return vec3(a.x * b.x, a.y * b.y, a.z * b.z); }
+inline vec3 operator*(float_t a, const vec3 &b) { return vec3(a * b.x, a * b.y, a * b.z); }
+inline vec3 operator*(const vec3 &a, float_t b) { return b * a; }
+inline vec3 operator/(const vec3 &a, float_t b) { return (float_t)(1.0 / (double)b) * a; }
+inline vec3 operator-(const vec3 &a) { return vec3(-a.x, -a.y, -a.z); }
+inline vec3 &operator+=(vec3 &a, const vec3 &b) { a = a + b; return a; }
+inline vec3 &operator-=(vec3 &a, const vec3 &b) { a = a - b; return a; }
+inline vec3 &operator*=(vec3 &a, const vec3 &b) { a = a * b; return a; }
+inline vec3 &operator*=(vec3 &a, float_t b) { a = a * b; return a; }
+inline vec3 &operator/=(vec3 &a, float_t b) { a = a / b; return a; }
+inline float_t dot(const vec3 &a, const vec3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline vec3 normalize(const vec3 &v) { return (float_t)(1.0 / std::sqrt((double)dot(v, v))) * v; }
+
+// ---------------------------------------------------------------------------------------------------
+// dj_brdf.h:74-109
+class brdf {
+public:
+	virtual vec3 eval(const vec3 &i, const vec3 &o, const void *user_param = NULL) const = 0;
+	virtual vec3 eval_hd(const vec3 &h, const vec3 &d, const void *user_param = NULL) const
+	{
+		vec3 i, o;
+		hd_to_io(h, d, &i, &o);
+		return eval(i, o, user_param);
+	}
+	virtual vec3 evalp(const vec3 &i, const vec3 &o, const void *user_param = NULL) const
+	{
+		return eval(i, o, user_param) * i.z;
+	}
+	virtual vec3 evalp_hd(const vec3 &h, const vec3 &d, const void *user_param = NULL) const
+	{
+		vec3 i, o;
+		hd_to_io(h, d, &i, &o);
+		return eval(i, o, user_param) * i.z;
+	}
+	// default importance sampling: cosine-weighted hemisphere (dj_brdf.h:819-845)
+	virtual vec3 evalp_is(float_t u1, float_t u2, const vec3 &o, vec3 *i, float_t *pdf, const void *user_param = NULL) const
+	{
+		const vec3 i_ = sample(u1, u2, o, user_param);
+		float_t pdf_ = this->pdf(i_, o);
+		if (i) (*i) = i_;
+		if (pdf) (*pdf) = pdf_;
+		return evalp(i_, o, user_param) / pdf_;
+	}
+	virtual vec3 sample(float_t u1, float_t u2, const vec3 &, const void * = NULL) const
+	{
+		float_t x, y;
+		concentric(u1, u2, &x, &y);
+		return vec3(x, y, (float_t)std::sqrt(1.0 - (double)(x * x) - (double)(y * y)));
+	}
+	virtual float_t pdf(const vec3 &i, const vec3 &, const void * = NULL) const { return (float_t)((double)i.z / M_PI); }
+
+	// batched queries (added): n pairs, results in `out`; `where` says if the arrays are host or device memory
+	virtual void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void *user_param = NULL,
+	                        memory_space where = host, void *stream = NULL) const = 0;
+
+	// Rusinkiewicz frame, dj_brdf.h:771-793
+	static void io_to_hd(const vec3 &i, const vec3 &o, vec3 *h, vec3 *d)
+	{
+		detail::check(djb200_io_to_hd(&i.x, &o.x, 1, &h->x, &d->x, DJB200_MEM_HOST, NULL));
+	}
+	static void hd_to_io(const vec3 &h, const vec3 &d, vec3 *i, vec3 *o)
+	{
+		detail::check(djb200_hd_to_io(&h.x, &d.x, 1, &i->x, &o->x, DJB200_MEM_HOST, NULL));
+	}
+	static void io_to_hd_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *h, vec3 *d, memory_space where = host,
+	                           void *stream = NULL)
+	{
+		detail::check(djb200_io_to_hd(&i->x, &o->x, (int64_t)n, &h->x, &d->x, where, stream));
+	}
+
+	brdf() {}
+	virtual ~brdf() {}
+#if 1 // non-copyable, dj_brdf.h:104-108
+private:
+	brdf(const brdf &);
+	brdf &operator=(const brdf &);
+#endif
+protected:
+	static void concentric(float_t u1, float_t u2, float_t *x, float_t *y) // Shirley-Chiu, dj_brdf.h:726-752
+	{
+		float_t a = 2 * u1 - 1, b = 2 * u2 - 1, r, phi;
+		if (a == 0 && b == 0) { *x = *y = 0; return; }
+		if (a * a > b * b) { r = a; phi = (float_t)(M_PI / 4.0) * (b / a); }
+		else { r = b; phi = (float_t)(M_PI / 2.0) - (float_t)(M_PI / 4.0) * (a / b); }
+		*x = r * (float_t)std::cos((double)phi);
+		*y = r * (float_t)std::sin((double)phi);
+	}
+};
+
+// ---------------------------------------------------------------------------------------------------
+// dj_brdf.h:149-207: Fresnel terms.  Here they are descriptors handed to the kernels.
+namespace fresnel {
+inline vec3 ior_to_f0(const vec3 &ior)
+{
+	vec3 t((float_t)(((double)ior.x - 1.0) / ((double)ior.x + 1.0)), (float_t)(((double)ior.y - 1.0) / ((double)ior.y + 1.0)),
+	       (float_t)(((double)ior.z - 1.0) / ((double)ior.z + 1.0)));
+	return t * t;
+}
+class impl {
+public:
+	virtual ~impl() {}
+	virtual impl *copy() const = 0;
+	virtual void describe(djb200_fresnel *f) const = 0;
+};
+class ideal : public impl {
+public:
+	impl *copy() const { return new ideal(); }
+	void describe(djb200_fresnel *f) const { memset(f, 0, sizeof *f); f->kind = DJB200_FRESNEL_IDEAL; }
+};
+class schlick : public impl {
+	vec3 f0;
+public:
+	explicit schlick(const vec3 &f0) : f0(f0) {}
+	impl *copy() const { return new schlick(f0); }
+	void describe(djb200_fresnel *f) const
+	{
+		memset(f, 0, sizeof *f);
+		f->kind = DJB200_FRESNEL_SCHLICK;
+		f->v[0] = f0.x; f->v[1] = f0.y; f->v[2] = f0.z;
+	}
+};
+class unpolarized : public impl {
+	vec3 ior;
+public:
+	explicit unpolarized(const vec3 &ior) : ior(ior) {}
+	impl *copy() const { return new unpolarized(ior); }
+	void describe(djb200_fresnel *f) const
+	{
+		memset(f, 0, sizeof *f);
+		f->kind = DJB200_FRESNEL_UNPOLARIZED;
+		f->v[0] = ior.x; f->v[1] = ior.y; f->v[2] = ior.z;
+	}
+};
+class sgd : public impl {
+	vec3 f0, f1;
+public:
+	sgd(const vec3 &f0, const vec3 &f1) : f0(f0), f1(f1) {}
+	impl *copy() const { return new sgd(f0, f1); }
+	void describe(djb200_fresnel *f) const
+	{
+		memset(f, 0, sizeof *f);
+		f->kind = DJB200_FRESNEL_SGD;
+		f->v[0] = f0.x; f->v[1] = f0.y; f->v[2] = f0.z; f->v[3] = f1.x; f->v[4] = f1.y; f->v[5] = f1.z;
+	}
+};
+class spline : public impl {
+	std::vector<vec3> m_points;
+public:
+	explicit spline(const std::vector<vec3> &points) : m_points(points) {}
+	impl *copy() const { return new spline(m_points); }
+	const std::vector<vec3> &get_points() const { return m_points; }
+	void describe(djb200_fresnel *f) const
+	{
+		memset(f, 0, sizeof *f);
+		f->kind = DJB200_FRESNEL_SPLINE;
+		f->points = m_points.empty() ? NULL : &m_points[0].x;
+		f->n_points = (int32_t)m_points.size();
+	}
+};
+} // namespace fresnel
+
+// ---------------------------------------------------------------------------------------------------
+// dj_brdf.h:210-298
+class microfacet : public brdf {
+public:
+	class params { // 48 bytes, same layout as the reference (dj_brdf.h:238-242) and as djb200_params
+		friend class microfacet;
+		djb200_params m;
+	public:
+		static params standard() { return params(); }
+		static params isotropic(float_t a) { return params(a, a, 0); }
+		static params elliptic(float_t a1, float_t a2, float_t phi_a = 0.0) { return params(a1, a2, phi_a); }
+		static params pdfparams(float_t ax, float_t ay, float_t rho = 0.0, float_t tx_n = 0.0, float_t ty_n = 0.0)
+		{
+			return params(ax, ay, rho, tx_n, ty_n);
+		}
+		void set_ellipse(float_t a1, float_t a2, float_t phi_a = 0.0)
+		{
+			djb200_params t;
+			detail::check(djb200_params_elliptic(a1, a2, phi_a, &t));
+			t.tx_n = m.tx_n; t.ty_n = m.ty_n; // location is kept (dj_brdf.h:1451-1459)
+			memcpy(t.n, m.n, sizeof t.n);
+			m = t;
+		}
+		void set_pdfparams(float_t ax, float_t ay, float_t rho = 0.0, float_t tx_n = 0.0, float_t ty_n = 0.0)
+		{
+			detail::check(djb200_params_pdfparams(ax, ay, rho, tx_n, ty_n, &m));
+		}
+		void get_ellipse(float_t *a1, float_t *a2, float_t *phi_a = NULL) const
+		{
+			if (a1) *a1 = m.a1;
+			if (a2) *a2 = m.a2;
+			if (phi_a) *phi_a = m.phi_a;
+		}
+		void get_pdfparams(float_t *ax, float_t *ay, float_t *rho = NULL, float_t *tx_n = NULL, float_t *ty_n = NULL) const
+		{
+			if (ax) *ax = m.ax;
+			if (ay) *ay = m.ay;
+			if (rho) *rho = m.rho;
+			if (tx_n) *tx_n = m.tx_n;
+			if (ty_n) *ty_n = m.ty_n;
+		}
+		void get_location(float_t *tx_n, float_t *ty_n) const { *tx_n = m.tx_n; *ty_n = m.ty_n; }
+		void get_location(vec3 *n) const { *n = vec3(m.n[0], m.n[1], m.n[2]); }
+		params(float_t a1 = 1.0, float_t a2 = 1.0, float_t phi_a = 0.0)
+		{
+			DJB_ASSERT(a1 > 0.0 && a2 > 0.0 && "Invalid ellipse radii");
+			detail::check(djb200_params_elliptic(a1, a2, phi_a, &m));
+		}
+		params(float_t ax, float_t ay, float_t rho, float_t tx_n, float_t ty_n)
+		{
+			detail::check(djb200_params_pdfparams(ax, ay, rho, tx_n, ty_n, &m));
+		}
+		const djb200_params *raw() const { return &m; }
+	};
+	static_assert(sizeof(params) == 48, "params must stay layout-compatible with the reference");
+
+	virtual ~microfacet() { delete m_fresnel; }
+	// BRDF interface (dj_brdf.h:247-256): batches of one
+	vec3 eval(const vec3 &i, const vec3 &o, const void *user_param = NULL) const
+	{
+		vec3 r;
+		eval_batch(&i, &o, 1, &r, user_param);
+		return r;
+	}
+	vec3 evalp(const vec3 &i, const vec3 &o, const void *user_param = NULL) const
+	{
+		vec3 r;
+		evalp_batch(&i, &o, 1, &r, user_param);
+		return r;
+	}
+	vec3 sample(float_t u1, float_t u2, const vec3 &o, const void *user_param = NULL) const
+	{
+		float_t u[2] = {u1, u2};
+		vec3 r;
+		sample_batch(u, &o, 1, &r, user_param);
+		return r;
+	}
+	float_t pdf(const vec3 &i, const vec3 &o, const void *user_param = NULL) const
+	{
+		float_t r;
+		pdf_batch(&i, &o, 1, &r, user_param);
+		return r;
+	}
+	vec3 evalp_is(float_t u1, float_t u2, const vec3 &o, vec3 *i, float_t *pdf, const void *user_param = NULL) const
+	{
+		float_t u[2] = {u1, u2}, p = 0;
+		vec3 w, iv;
+		evalp_is_batch(u, &o, 1, &w, &iv, &p, user_param);
+		// the reference leaves *i untouched when the sample carries no energy (dj_brdf.h:1749-1764)
+		if (i && (p > 0 || w.x > 0 || w.y > 0 || w.z > 0)) *i = iv;
+		if (pdf) *pdf = p;
+		return w;
+	}
+
+	// batched interface: `user_param` is NULL (standard), or points at `n_params` blocks.  With BROADCAST every
+	// pair is evaluated under every block (out: [n_params][n]); with PER_PAIR block k belongs to pair k.
+	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void *user_param = NULL,
+	                memory_space where = host, void *stream = NULL) const
+	{
+		eval_batch(i, o, n, out, reinterpret_cast<const params *>(user_param), user_param ? 1 : 0, DJB200_PARAMS_BROADCAST, where,
+		           stream);
+	}
+	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const params *p, size_t n_params,
+	                djb200_params_layout layout, memory_space where = host, void *stream = NULL) const
+	{
+		djb200_microfacet d = describe();
+		detail::check(djb200_microfacet_eval(&d, raw(p), (int64_t)n_params, layout, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+	}
+	void evalp_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void *user_param = NULL, size_t n_params = 1,
+	                 djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host, void *stream = NULL) const
+	{
+		djb200_microfacet d = describe();
+		detail::check(djb200_microfacet_evalp(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, &i->x, &o->x,
+		                                      (int64_t)n, &out->x, where, stream));
+	}
+	void pdf_batch(const vec3 *i, const vec3 *o, size_t n, float_t *out, const void *user_param = NULL, size_t n_params = 1,
+	               djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host, void *stream = NULL) const
+	{
+		djb200_microfacet d = describe();
+		detail::check(djb200_microfacet_pdf(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, &i->x, &o->x,
+		                                    (int64_t)n, out, where, stream));
+	}
+	void sample_batch(const float_t *u12, const vec3 *o, size_t n, vec3 *out_i, const void *user_param = NULL,
+	                  size_t n_params = 1, djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host,
+	                  void *stream = NULL) const
+	{
+		djb200_microfacet d = describe();
+		detail::check(djb200_microfacet_sample(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, u12, &o->x,
+		                                       (int64_t)n, &out_i->x, where, stream));
+	}
+	void evalp_is_batch(const float_t *u12, const vec3 *o, size_t n, vec3 *out_weight, vec3 *out_i, float_t *out_pdf,
+	                    const void *user_param = NULL, size_t n_params = 1,
+	                    djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host,
+	                    void *stream = NULL) const
+	{
+		djb200_microfacet d = describe();
+		detail::check(djb200_microfacet_evalp_is(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, u12, &o->x,
+		                                         (int64_t)n, out_weight ? &out_weight->x : NULL, out_i ? &out_i->x : NULL, out_pdf,
+		                                         where, stream));
+	}
+
+	virtual bool supports_smith_vndf_sampling() const = 0;
+	void set_shadow(bool shadow) { m_shadow = shadow; }
+	void set_fresnel(const fresnel::impl &f)
+	{
+		delete m_fresnel;
+		m_fresnel = f.copy();
+	}
+	int get_shadow() const { return m_shadow; }
+	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
+	// construction state as the C-ABI sees it
+	djb200_microfacet describe() const
+	{
+		djb200_microfacet d;
+		d.ndf = ndf_id();
+		d.shadow = m_shadow ? 1 : 0;
+		m_fresnel->describe(&d.fresnel);
+		return d;
+	}
+
+protected:
+	microfacet(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : m_fresnel(f.copy()), m_shadow(shadow) {}
+	virtual int ndf_id() const = 0;
+	static const djb200_params *raw(const void *p) { return reinterpret_cast<const djb200_params *>(p); }
+	const fresnel::impl *m_fresnel;
+	bool m_shadow;
+};
+
+class radial : public microfacet {
+protected:
+	radial(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : microfacet(f, shadow) {}
+};
+
+// dj_brdf.h:374-391
+class ggx : public radial {
+public:
+	ggx(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : radial(f, shadow) {}
+	bool supports_smith_vndf_sampling() const { return true; }
+protected:
+	int ndf_id() const { return DJB200_NDF_GGX; }
+};
+
+// dj_brdf.h:327-371
+class beckmann : public radial {
+public:
+	// LEAN / LEADR linear representation: five slope moments (dj_brdf.h:330-356, 1959-2051)
+	class lrep {
+		friend class beckmann;
+		float_t m_E1, m_E2, m_E3, m_E4, m_E5;
+	public:
+		lrep(float_t E1 = 0, float_t E2 = 0, float_t E3 = 0, float_t E4 = 0, float_t E5 = 0)
+		    : m_E1(E1), m_E2(E2), m_E3(E3), m_E4(E4), m_E5(E5) {}
+		lrep operator+(const lrep &r) const
+		{
+			return lrep(m_E1 + r.m_E1, m_E2 + r.m_E2, m_E3 + r.m_E3 + (float_t)2.0 * m_E1 * r.m_E1,
+			            m_E4 + r.m_E4 + (float_t)2.0 * m_E2 * r.m_E2, m_E5 + r.m_E5 + m_E1 * r.m_E2 + m_E2 * r.m_E1);
+		}
+		lrep operator*(float_t sc) const
+		{
+			DJB_ASSERT(sc >= (float_t)0.0 && "Invalid scale");
+			float_t s2 = sc * sc;
+			return lrep(m_E1 * sc, m_E2 * sc, m_E3 * s2, m_E4 * s2, m_E5 * s2);
+		}
+		lrep &operator+=(const lrep &r)
+		{ // in-place update order of the reference: E1/E2 are advanced first (dj_brdf.h:2011-2020)
+			m_E1 += r.m_E1;
+			m_E2 += r.m_E2;
+			m_E3 += r.m_E3 + (float_t)2.0 * m_E1 * r.m_E1;
+			m_E4 += r.m_E4 + (float_t)2.0 * m_E2 * r.m_E2;
+			m_E5 += r.m_E5 + m_E1 * r.m_E2 + m_E2 * r.m_E1;
+			return *this;
+		}
+		lrep &operator*=(float_t sc) { return *this = *this * sc; }
+		void shear(float_t tx, float_t ty)
+		{
+			m_E1 += tx; m_E2 += ty; m_E3 += tx * tx; m_E4 += ty * ty; m_E5 += tx * ty;
+		}
+		void scale(float_t x, float_t y)
+		{
+			m_E1 *= x; m_E2 *= y; m_E3 *= x * x; m_E4 *= y * y; m_E5 *= x * y;
+		}
+		const float_t *raw() const { return &m_E1; }
+	};
+	beckmann(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : radial(f, shadow) {}
+	bool supports_smith_vndf_sampling() const { return true; }
+	static void params_to_lrep(const microfacet::params &p, lrep *l)
+	{
+		DJB_ASSERT(l && "Null output ptr");
+		detail::check(djb200_params_to_lrep(p.raw(), 1, &l->m_E1, DJB200_MEM_HOST, NULL));
+	}
+	static void lrep_to_params(const lrep &l, microfacet::params *p)
+	{
+		DJB_ASSERT(p && "Null output ptr");
+		detail::check(djb200_lrep_to_params(l.raw(), 1, const_cast<djb200_params *>(p->raw()), DJB200_MEM_HOST, NULL));
+	}
+	// per-texel batch (mitsuba/dj_beckmannconductor.cpp:295-314): n x 5 moments -> n params blocks
+	static void lrep_to_params_batch(const float_t *E, size_t n, microfacet::params *out, memory_space where = host,
+	                                 void *stream = NULL)
+	{
+		detail::check(djb200_lrep_to_params(E, (int64_t)n, const_cast<djb200_params *>(out->raw()), where, stream));
+	}
+protected:
+	int ndf_id() const { return DJB200_NDF_BECKMANN; }
+};
+static_assert(sizeof(beckmann::lrep) == 20, "lrep is five packed floats");
+
+// ---------------------------------------------------------------------------------------------------
+// dj_brdf.h:126-133
+class merl : public brdf {
+	djb200_merl *m_h;
+public:
+	explicit merl(const char *path_to_merl_binary) : m_h(NULL) { detail::check(djb200_merl_load(path_to_merl_binary, &m_h)); }
+	// samples: the three planes of doubles of a .binary file already in memory
+	explicit merl(const std::vector<double> &samples) : m_h(NULL)
+	{
+		if (samples.size() != (size_t)3 * 90 * 90 * 180) throw exc("djb_error: MERL sample array must hold 3*90*90*180 doubles");
+		detail::check(djb200_merl_create(&samples[0], &m_h));
+	}
+	~merl() { djb200_merl_destroy(m_h); }
+	vec3 eval(const vec3 &i, const vec3 &o, const void * = NULL) const
+	{
+		vec3 r;
+		eval_batch(&i, &o, 1, &r);
+		return r;
+	}
+	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void * = NULL, memory_space where = host,
+	                void *stream = NULL) const
+	{
+		detail::check(djb200_merl_eval(m_h, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+	}
+	const djb200_merl *handle() const { return m_h; }
+};
+
+// dj_brdf.h:136-146
+class utia : public brdf {
+	djb200_utia *m_h;
+public:
+	explicit utia(const char *filename) : m_h(NULL) { detail::check(djb200_utia_load(filename, &m_h)); }
+	~utia() { djb200_utia_destroy(m_h); }
+	vec3 eval(const vec3 &i, const vec3 &o, const void * = NULL) const
+	{
+		vec3 r;
+		eval_batch(&i, &o, 1, &r);
+		return r;
+	}
+	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void * = NULL, memory_space where = host,
+	                void *stream = NULL) const
+	{
+		detail::check(djb200_utia_eval(m_h, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+	}
+	const djb200_utia *handle() const { return m_h; }
+};
+
+namespace detail {
+inline djb200_source describe_source(const brdf &b)
+{
+	djb200_source s;
+	memset(&s, 0, sizeof s);
+	if (const merl *m = dynamic_cast<const merl *>(&b)) { s.kind = DJB200_SOURCE_MERL; s.merl = m->handle(); }
+	else if (const utia *u = dynamic_cast<const utia *>(&b)) { s.kind = DJB200_SOURCE_UTIA; s.utia = u->handle(); }
+	else if (const microfacet *f = dynamic_cast<const microfacet *>(&b)) { s.kind = DJB200_SOURCE_MICROFACET; s.microfacet = f->describe(); }
+	else throw exc("djb_error: this BRDF type cannot be fitted on the device (merl, utia, ggx, beckmann can)");
+	return s;
+}
+} // namespace detail
+
+// ---------------------------------------------------------------------------------------------------
+// dj_brdf.h:394-425: the isotropic "power iteration" fit.  The tables are built on the GPU; the object exposes the
+// reference's accessors.  (Evaluating / sampling the tabulated BRDF itself is SURVEY section 8f row N2: not yet.)
+class tabular {
+	std::vector<float_t> m_p22, m_sigma, m_cdf, m_qf, m_residuals;
+	std::vector<vec3> m_fresnel_pts;
+	fresnel::spline *m_fresnel;
+	float_t m_alpha_beckmann, m_alpha_ggx;
+	bool m_shadow;
+	tabular() : m_fresnel(NULL) {}
+public:
+	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4) : m_fresnel(NULL)
+	{
+		const brdf *src = &source;
+		std::vector<tabular *> self(1, this);
+		run(&src, 1, resolution, shadow, iterations, self);
+	}
+	~tabular() { delete m_fresnel; }
+	// many materials in one device pass (one CTA per material)
+	static std::vector<tabular *> fit_batch(const std::vector<const brdf *> &sources, int resolution, bool shadow = true,
+	                                        int iterations = 4)
+	{
+		std::vector<tabular *> out;
+		for (size_t k = 0; k < sources.size(); ++k) out.push_back(new tabular());
+		if (!sources.empty()) run(&sources[0], sources.size(), resolution, shadow, iterations, out);
+		return out;
+	}
+	static microfacet::params fit_beckmann_parameters(const tabular &tab) { return microfacet::params::isotropic(tab.m_alpha_beckmann); }
+	static microfacet::params fit_ggx_parameters(const tabular &tab) { return microfacet::params::isotropic(tab.m_alpha_ggx); }
+	const std::vector<float_t> &get_p22v() const { return m_p22; }
+	const std::vector<float_t> &get_sigmav() const { return m_sigma; }
+	const std::vector<float_t> &get_cdfv() const { return m_cdf; }
+	const std::vector<float_t> &get_qfv() const { return m_qf; }
+	const std::vector<float_t> &get_residuals() const { return m_residuals; }
+	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
+	int get_shadow() const { return m_shadow; }
+
+private:
+	tabular(const tabular &);
+	tabular &operator=(const tabular &);
+	static void run(const brdf *const *sources, size_t n, int res, bool shadow, int iterations, std::vector<tabular *> &out)
+	{
+		DJB_ASSERT(res > 2 && "Invalid Resolution");
+		std::vector<djb200_source> src(n);
+		std::vector<djb200_tabular_fit> fit(n);
+		for (size_t k = 0; k < n; ++k) {
+			tabular &t = *out[k];
+			src[k] = detail::describe_source(*sources[k]);
+			t.m_p22.assign(res, 0); t.m_sigma.assign(res, 0); t.m_cdf.assign(res, 0); t.m_qf.assign(res, 0);
+			t.m_residuals.assign(iterations > 0 ? iterations : 1, 0);
+			t.m_fresnel_pts.assign(res, vec3(0));
+			t.m_shadow = shadow;
+			fit[k].res = res;
+			fit[k].p22 = &t.m_p22[0]; fit[k].sigma = &t.m_sigma[0]; fit[k].cdf = &t.m_cdf[0]; fit[k].qf = &t.m_qf[0];
+			fit[k].fresnel = &t.m_fresnel_pts[0].x;
+			fit[k].residuals = &t.m_residuals[0];
+		}
+		detail::check(djb200_fit_tabular(&src[0], (int32_t)n, res, shadow ? 1 : 0, iterations, &fit[0], NULL));
+		for (size_t k = 0; k < n; ++k) {
+			out[k]->m_alpha_beckmann = fit[k].alpha_beckmann;
+			out[k]->m_alpha_ggx = fit[k].alpha_ggx;
+			out[k]->m_fresnel = new fresnel::spline(out[k]->m_fresnel_pts);
+		}
+	}
+};
+
+// dj_brdf.h:428-478 (eval tables + parameter fits)
+class tabular_anisotropic {
+	std::vector<float_t> m_p22, m_sigma, m_residuals;
+	std::vector<vec3> m_fresnel_pts;
+	fresnel::spline *m_fresnel;
+	float_t m_beckmann[5], m_ggx[5];
+	int m_elevation_res, m_azimuthal_res;
+public:
+	tabular_anisotropic(const brdf &source, int elevation_res, int azimuthal_res, bool shadow = true, int iterations = 4)
+	    : m_fresnel(NULL), m_elevation_res(elevation_res), m_azimuthal_res(azimuthal_res)
+	{
+		DJB_ASSERT(elevation_res > 1 && azimuthal_res > 1 && "Invalid Resolution");
+		djb200_source src = detail::describe_source(source);
+		size_t tab = (size_t)elevation_res * azimuthal_res;
+		m_p22.assign(tab, 0); m_sigma.assign(tab, 0);
+		m_residuals.assign(iterations > 0 ? iterations : 1, 0);
+		m_fresnel_pts.assign(elevation_res, vec3(0));
+		djb200_tabular_anisotropic_fit fit;
+		memset(&fit, 0, sizeof fit);
+		fit.elev_res = elevation_res; fit.azim_res = azimuthal_res;
+		fit.p22 = &m_p22[0]; fit.sigma = &m_sigma[0]; fit.fresnel = &m_fresnel_pts[0].x; fit.residuals = &m_residuals[0];
+		detail::check(djb200_fit_tabular_anisotropic(&src, 1, elevation_res, azimuthal_res, shadow ? 1 : 0, iterations, &fit, NULL));
+		memcpy(m_beckmann, fit.beckmann, sizeof m_beckmann);
+		memcpy(m_ggx, fit.ggx, sizeof m_ggx);
+		m_fresnel = new fresnel::spline(m_fresnel_pts);
+	}
+	~tabular_anisotropic() { delete m_fresnel; }
+	static microfacet::params fit_beckmann_parameters(const tabular_anisotropic &t)
+	{
+		return microfacet::params::pdfparams(t.m_beckmann[0], t.m_beckmann[1], t.m_beckmann[2], t.m_beckmann[3], t.m_beckmann[4]);
+	}
+	static microfacet::params fit_ggx_parameters(const tabular_anisotropic &t)
+	{
+		return microfacet::params::pdfparams(t.m_ggx[0], t.m_ggx[1], t.m_ggx[2], t.m_ggx[3], t.m_ggx[4]);
+	}
+	const std::vector<float_t> &get_p22v(int *w = NULL, int *h = NULL) const
+	{
+		if (w) *w = m_elevation_res;
+		if (h) *h = m_azimuthal_res;
+		return m_p22;
+	}
+	const std::vector<float_t> &get_sigmav(int *w = NULL, int *h = NULL) const
+	{
+		if (w) *w = m_elevation_res;
+		if (h) *h = m_azimuthal_res;
+		return m_sigma;
+	}
+	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
+private:
+	tabular_anisotropic(const tabular_anisotropic &);
+	tabular_anisotropic &operator=(const tabular_anisotropic &);
+};
+
+// utils/nmap2leanmap.cpp:18-54 (bias = 0) and nmap2leanmap_biased.cpp:23-63 (bias = 25) on raw planar buffers
+inline void nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float_t base_roughness, float_t bias,
+                         float_t *leanmap_1, float_t *leanmap_2, memory_space where = host, void *stream = NULL)
+{
+	detail::check(djb200_nmap_to_leanmap(nmap_planar_rgb, w, h, base_roughness, bias, leanmap_1, leanmap_2, where, stream));
+}
+
+} // namespace djb
+#endif // DJB200_FACADE_HPP

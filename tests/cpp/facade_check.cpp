@@ -1,0 +1,65 @@
+// tests/cpp/facade_check.cpp -- drives the C++ facade (include/djb200_facade.hpp) the way a host program written
+// against dj_brdf.h would, on inputs the Python test wrote, and dumps the results for comparison with the oracle.
+//   facade_check <in.bin> <out.bin>
+// in.bin : int32 n, then wi[n][3], wo[n][3], u[n][2] (float32)
+// out.bin: for ndf in (ggx, beckmann): eval[n][3] (batch), pdf[n] (batch), sample[n][3] (batch), eval_scalar[16][3],
+//          eval16[2][n][3] (two params blocks, BROADCAST); then lrep round trip [5]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "dj_brdf.h" // include/compat: the reference's header name
+
+static void put(FILE *f, const void *p, size_t bytes) { if (fwrite(p, 1, bytes, f) != bytes) abort(); }
+
+int main(int argc, char **argv)
+{
+	if (argc != 3) return 2;
+	FILE *fi = fopen(argv[1], "rb");
+	if (!fi) return 3;
+	int n = 0;
+	if (fread(&n, 4, 1, fi) != 1) return 4;
+	std::vector<djb::vec3> wi(n), wo(n), out(n);
+	std::vector<float> u(2 * n), pdf(n);
+	if (fread(&wi[0], 12, n, fi) != (size_t)n || fread(&wo[0], 12, n, fi) != (size_t)n || fread(&u[0], 8, n, fi) != (size_t)n) return 5;
+	fclose(fi);
+	FILE *fo = fopen(argv[2], "wb");
+	try {
+		djb::microfacet::params P = djb::microfacet::params::elliptic(0.1f, 0.4f, 0.7f);
+		djb::microfacet::params two[2] = {djb::microfacet::params::isotropic(0.3f),
+		                                  djb::microfacet::params::pdfparams(0.3f, 0.2f, 0.4f, 0.1f, -0.2f)};
+		djb::ggx ggx(djb::fresnel::schlick(djb::vec3(0.9f, 0.5f, 0.2f)));
+		djb::beckmann beckmann(djb::fresnel::schlick(djb::vec3(0.9f, 0.5f, 0.2f)));
+		const djb::microfacet *brdfs[2] = {&ggx, &beckmann};
+		for (int b = 0; b < 2; ++b) {
+			const djb::microfacet &m = *brdfs[b];
+			m.eval_batch(&wi[0], &wo[0], n, &out[0], &P);
+			put(fo, &out[0], 12 * (size_t)n);
+			m.pdf_batch(&wi[0], &wo[0], n, &pdf[0], &P);
+			put(fo, &pdf[0], 4 * (size_t)n);
+			m.sample_batch(&u[0], &wo[0], n, &out[0], &P);
+			put(fo, &out[0], 12 * (size_t)n);
+			const djb::brdf &as_base = m; // the reference's virtual interface, one pair per call
+			for (int k = 0; k < 16; ++k) {
+				djb::vec3 e = as_base.eval(wi[k], wo[k], &P);
+				put(fo, &e, 12);
+			}
+			std::vector<djb::vec3> out2(2 * (size_t)n);
+			m.eval_batch(&wi[0], &wo[0], n, &out2[0], two, 2, DJB200_PARAMS_BROADCAST);
+			put(fo, &out2[0], 24 * (size_t)n);
+		}
+		djb::beckmann::lrep l;
+		djb::beckmann::params_to_lrep(two[1], &l);
+		l += djb::beckmann::lrep(0.01f, 0.02f, 0.03f, 0.04f, 0.001f);
+		djb::microfacet::params back;
+		djb::beckmann::lrep_to_params(l, &back);
+		float q[5];
+		back.get_pdfparams(&q[0], &q[1], &q[2], &q[3], &q[4]);
+		put(fo, q, sizeof q);
+	} catch (const std::exception &e) {
+		fprintf(stderr, "%s\n", e.what());
+		return 1;
+	}
+	fclose(fo);
+	return 0;
+}

@@ -1,0 +1,118 @@
+"""The C++ host side (include/djb200_facade.hpp, include/compat/dj_brdf.h): programs written against the reference's
+`djb::` interface build against the facade and -- on the GPU box -- produce the oracle's numbers through the C-ABI."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import api
+from tests import cases
+from tests.conftest import bits_equal, rel_err
+
+ROOT = Path(__file__).resolve().parents[1]
+LIBDIR = ROOT / "dj_brdf_b200"
+
+
+def compile_cpp(src, out, incs, std="-std=c++11"):
+    cmd = ["g++", "-O2", std, *[f"-I{i}" for i in incs], str(src), f"-L{LIBDIR}", "-ldjb200",
+           f"-Wl,-rpath,{LIBDIR}", "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+@pytest.fixture(scope="module")
+def bins(djb, tmp_path_factory):
+    d = tmp_path_factory.mktemp("cpp")
+    return dict(
+        check=compile_cpp(ROOT / "tests/cpp/facade_check.cpp", d / "facade_check", [ROOT / "include/compat"]),
+        example=compile_cpp(ROOT / "examples/merl_params_batch.cpp", d / "merl_params_batch", [ROOT / "include"]),
+        dir=d)
+
+
+def test_facade_programs_compile(bins):
+    assert bins["check"].exists() and bins["example"].exists()
+
+
+def test_reference_example_compiles_unchanged(djb, tmp_path):
+    """examples/merl_params.cpp of the reference, byte for byte, against include/compat/dj_brdf.h."""
+    src = api.REF_ROOT / "examples" / "merl_params.cpp"
+    if not src.exists():
+        pytest.skip("/root/reference not present")
+    compile_cpp(src, tmp_path / "ref_merl_params", [ROOT / "include/compat"], std="-std=gnu++11")
+
+
+def test_facade_fails_loudly_without_gpu(djb, bins):
+    if djb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    wi, wo, u = cases.pairs(32)
+    inp = bins["dir"] / "in.bin"
+    with open(inp, "wb") as f:
+        f.write(np.int32(32).tobytes() + wi.tobytes() + wo.tobytes() + u.tobytes())
+    r = subprocess.run([str(bins["check"]), str(inp), str(bins["dir"] / "out.bin")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_facade_matches_oracle(bins, port):
+    n = 20_000
+    wi, wo, u = cases.pairs(n, stream=300)
+    inp, outp = bins["dir"] / "in.bin", bins["dir"] / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.int32(n).tobytes() + wi.tobytes() + wo.tobytes() + u.tobytes())
+    r = subprocess.run([str(bins["check"]), str(inp), str(outp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(outp, dtype=np.float32)
+    pos = 0
+
+    def take(*shape):
+        nonlocal pos
+        k = int(np.prod(shape))
+        a = raw[pos:pos + k].reshape(shape)
+        pos += k
+        return a
+
+    fr = api.Fresnel.schlick([0.9, 0.5, 0.2])
+    P = port.params_elliptic(0.1, 0.4, 0.7)
+    two = [port.params_elliptic(0.3, 0.3, 0.0), port.params_pdfparams(0.3, 0.2, 0.4, 0.1, -0.2)]
+    for ndf in (api.NDF_GGX, api.NDF_BECKMANN):
+        ev, pdf, smp, sc, ev2 = take(n, 3), take(n), take(n, 3), take(16, 3), take(2, n, 3)
+        want = port.eval(ndf, P, wi, wo, fr)
+        assert rel_err(ev, want).max() <= 1e-5 and np.array_equal(ev == 0, want == 0)
+        assert rel_err(pdf, port.pdf(ndf, P, wi, wo, fr)).max() <= 1e-5
+        same = bits_equal(smp, port.sample(ndf, P, u, wo)).all(axis=1).mean()
+        assert same >= (0.9999 if ndf == api.NDF_GGX else 0.97)
+        assert bits_equal(sc, ev[:16]).all(), "scalar virtual calls must equal the batch"
+        for m in range(2):
+            assert rel_err(ev2[m], port.eval(ndf, two[m], wi, wo, fr)).max() <= 1e-5
+    back = take(5)
+    E = port.params_to_lrep(two[1])[0]
+    d = np.array([0.01, 0.02, 0.03, 0.04, 0.001], np.float32)
+    e1, e2 = np.float32(E[0] + d[0]), np.float32(E[1] + d[1])  # operator+= advances E1, E2 first (dj_brdf.h:2011-2020)
+    E2 = np.array([e1, e2, E[2] + (d[2] + np.float32(2.0) * e1 * d[0]), E[3] + (d[3] + np.float32(2.0) * e2 * d[1]),
+                   E[4] + ((d[4] + e1 * d[1]) + e2 * d[0])], np.float32)
+    wantp = port.lrep_to_params(E2[None])[0]
+    assert np.allclose(back, [wantp[6], wantp[7], wantp[8], wantp[10], wantp[11]], rtol=1e-5, atol=1e-7)
+    assert pos == raw.size
+
+
+@pytest.mark.gpu
+def test_merl_params_example(bins, port):
+    d = bins["dir"]
+    tabs = {f"mat{s}": cases.smooth_merl_table(s) for s in (41, 42, 43)}
+    files = []
+    for name, t in tabs.items():
+        p = d / f"{name}.binary"
+        api.write_merl_file(p, t)
+        files.append(str(p))
+    out = d / "params.txt"
+    r = subprocess.run([str(bins["example"]), "-o", str(out), *files], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = out.read_text().strip().splitlines()
+    assert lines[0] == "# MERL Beckmann GGX" and len(lines) == 4
+    for line, (name, t) in zip(lines[1:], tabs.items()):
+        want = port.fit_tabular(api.Source.merl(t), 90)["alpha"]
+        nm, b, g = line.split()
+        assert nm == name and b == f"{want[0]:.3f}" and g == f"{want[1]:.3f}", (line, want)
