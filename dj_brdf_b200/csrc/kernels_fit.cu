@@ -7,7 +7,7 @@
 // workspace).  A batch of materials fills the GPU: 128 materials = 128 CTAs on 148 SMs.
 //
 // Parity: every sum keeps the reference's order (a float sum is not associative), so the tables are
-// bit-comparable with the CPU oracle.  Work that does not depend on the summation index is hoisted
+// bit-comparable with the reference.  Work that does not depend on the summation index is hoisted
 // (the 361 cos(phi) of the kernel-matrix integral, the 180 x 90 NDF grid of the sigma integral) and the
 // independent terms of each quadrature are computed in parallel before one thread adds them in order.
 //
