@@ -343,6 +343,20 @@ class merl(_table_brdf):
         return out
 
 
+def merl_filter_stats(i, o):
+    """Property check of the filtered MERL lookup on device arrays (djb200_debug_merl_filter_stats):
+    -> dict(rejected, certified_wrong, max_d_error, h_mismatch)."""
+    bi, bo = Buf(i, np.float32), Buf(o, np.float32)
+    if capi.same_space(bi, bo) != capi.MEM_DEVICE:
+        raise ValueError("merl_filter_stats needs device arrays")
+    st = (C.c_uint64 * 5)()
+    check(capi.load().djb200_debug_merl_filter_stats(bi.ptr, bo.ptr, C.c_int64(bi.n // 3), st,
+                                                     capi.current_stream_ptr(capi.MEM_DEVICE)))
+    return dict(rejected=int(st[0]), certified_wrong=int(st[1]),
+                max_d_error=float(np.array([st[2] & 0xFFFFFFFF], np.uint32).view(np.float32)[0]), h_mismatch=int(st[3]),
+                max_acos_error=float(np.array([st[4] & 0xFFFFFFFF], np.uint32).view(np.float32)[0]))
+
+
 class utia(_table_brdf):
     """djb::utia (dj_brdf.h:136-146): from a .bin file name or the raw [3*6*48*6*48] float64 samples."""
     _destroy, _eval = "djb200_utia_destroy", "djb200_utia_eval"

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "djb200_microfacet_evalp_is",
     "djb200_io_to_hd", "djb200_hd_to_io",
     "djb200_merl_create", "djb200_merl_load", "djb200_merl_destroy", "djb200_merl_eval", "djb200_merl_index",
+    "djb200_debug_merl_filter_stats",
     "djb200_utia_create", "djb200_utia_load", "djb200_utia_destroy", "djb200_utia_eval",
     "djb200_nmap_to_leanmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
     "djb200_fit_tabular", "djb200_fit_tabular_anisotropic",

@@ -501,6 +501,23 @@ djb200_status djb200_merl_index(const float *wi, const float *wo, int64_t n, int
 		});
 }
 
+djb200_status djb200_debug_merl_filter_stats(const float *wi_dev, const float *wo_dev, int64_t n, uint64_t out_stats[5],
+                                             void *stream)
+{
+	if (!wi_dev || !wo_dev || !out_stats || n < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "bad argument");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	unsigned long long *d = nullptr;
+	CU(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
+	cudaError_t e = cudaMemsetAsync(d, 0, 5 * sizeof(unsigned long long), (cudaStream_t)stream);
+	if (e == cudaSuccess) e = launch_merl_filter_stats(wi_dev, wo_dev, n, d, (cudaStream_t)stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out_stats, d, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return cuda_fail(e, "merl filter stats");
+	return DJB200_OK;
+}
+
 // ---- UTIA ------------------------------------------------------------------------------------------
 static const int64_t UTIA_N = 3 * 6 * 48 * 6 * 48;
 

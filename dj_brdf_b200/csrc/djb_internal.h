@@ -52,6 +52,8 @@ cudaError_t launch_merl_convert(const double *samples_dev, float4 *cells_dev, cu
 cudaError_t launch_merl_eval(const float4 *cells, const float *wi, const float *wo, int64_t n, float *out,
                              cudaStream_t st);
 cudaError_t launch_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out, cudaStream_t st);
+cudaError_t launch_merl_filter_stats(const float *wi, const float *wo, int64_t n, unsigned long long *stats_dev,
+                                     cudaStream_t st);
 cudaError_t launch_utia_convert(const double *raw_dev, float *table_dev, cudaStream_t st);
 cudaError_t launch_utia_eval(const float *table, const float *wi, const float *wo, int64_t n, float *out,
                              cudaStream_t st);

@@ -12,7 +12,6 @@
 namespace djb200 {
 
 constexpr int TB = 256;
-constexpr int MERL_CELLS = 90 * 90 * 180;
 
 static inline int grid_for(int64_t n, int per_thread = 1)
 {
@@ -65,63 +64,6 @@ cudaError_t launch_hd_to_io(const float *h, const float *d, int64_t n, float *wi
 {
 	if (n <= 0) return cudaSuccess;
 	hd_to_io_kernel<<<grid_for(n), TB, 0, st>>>(h, d, n, wi, wo);
-	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-	return cudaGetLastError();
-}
-
-// ---- MERL ---------------------------------------------------------------------------------------
-// file planes (R, G, B doubles) -> scaled float4 cells; MERL_*_SCALE, dj_brdf.h:897-899
-__global__ void __launch_bounds__(TB) merl_convert_kernel(const double *samples, float4 *cells)
-{
-	int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= MERL_CELLS) return;
-	float r = (float)(samples[c] * (1.00 / 1500.0));
-	float g = (float)(samples[c + MERL_CELLS] * (1.15 / 1500.0));
-	float b = (float)(samples[c + 2 * MERL_CELLS] * (1.66 / 1500.0));
-	cells[c] = make_float4(r, g, b, 0.f);
-}
-
-__global__ void __launch_bounds__(TB) merl_eval_kernel(const float4 *__restrict__ cells, const float *__restrict__ wi,
-                                                       const float *__restrict__ wo, long long n, float *__restrict__ out)
-{
-	const long long stride = (long long)gridDim.x * blockDim.x;
-	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-		int c = merl_cell(ld3(wi, k), ld3(wo, k));
-		float4 v = __ldg(cells + c);
-		// "below horizon" cells hold negative samples: the whole texel becomes 0 (dj_brdf.h:1016-1021)
-		if (v.x < 0.0f || v.y < 0.0f || v.z < 0.0f) v = make_float4(0.f, 0.f, 0.f, 0.f);
-		st3t(out, k, mk(v.x, v.y, v.z));
-	}
-}
-
-__global__ void __launch_bounds__(TB) merl_index_kernel(const float *__restrict__ wi, const float *__restrict__ wo,
-                                                        long long n, int32_t *__restrict__ out)
-{
-	const long long stride = (long long)gridDim.x * blockDim.x;
-	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
-		out[k] = merl_cell(ld3(wi, k), ld3(wo, k));
-}
-
-cudaError_t launch_merl_convert(const double *samples_dev, float4 *cells_dev, cudaStream_t st)
-{
-	merl_convert_kernel<<<(MERL_CELLS + TB - 1) / TB, TB, 0, st>>>(samples_dev, cells_dev);
-	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_merl_eval(const float4 *cells, const float *wi, const float *wo, int64_t n, float *out,
-                             cudaStream_t st)
-{
-	if (n <= 0) return cudaSuccess;
-	merl_eval_kernel<<<grid_for(n), TB, 0, st>>>(cells, wi, wo, n, out);
-	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out, cudaStream_t st)
-{
-	if (n <= 0) return cudaSuccess;
-	merl_index_kernel<<<grid_for(n), TB, 0, st>>>(wi, wo, n, out);
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	return cudaGetLastError();
 }

@@ -156,6 +156,13 @@ DJB200_API djb200_status djb200_merl_eval(const djb200_merl *m, const float *wi,
 DJB200_API djb200_status djb200_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out_index,
                                            int mem, void *stream);
 
+/* Property check of the filtered lookup (csrc/kernels_merl.cu) on DEVICE arrays: out_stats[0] = lookups the FP32
+ * filter handed to the exact double path, [1] = lookups it certified with a cell different from the exact one
+ * (must be 0), [2] = float bits of max |d_fast - d_exact|, [3] = half vectors not bit-identical to the reference's,
+ * [4] = float bits of max |acos_poly - acos| over the sampled arguments. */
+DJB200_API djb200_status djb200_debug_merl_filter_stats(const float *wi_dev, const float *wo_dev, int64_t n,
+                                                        uint64_t out_stats[5], void *stream);
+
 /* ---- UTIA (djb::utia, dj_brdf.h:136-146, 1029-1177) ------------------------------------- */
 typedef struct djb200_utia djb200_utia;
 /* raw_samples: 3*6*48*6*48 doubles as stored in a UTIA .bin file, before utia::normalize() */

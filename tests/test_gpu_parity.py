@@ -261,3 +261,44 @@ def test_empty_and_ragged(djb):
         wi, wo, u = cases.pairs(n, stream=208)
         assert djb.ggx().eval(wi, wo, djb.params.isotropic(0.3)).shape == (n, 3)
         assert djb.beckmann().sample(u, wo, djb.params.isotropic(0.3)).shape == (n, 3)
+
+
+def test_merl_filter_certifies_only_exact_cells_at_full_size(djb):
+    """BASELINE config 3 size (1e8 lookups): the FP32 filter of the MERL lookup may only certify a cell that equals
+    the exact (double-arithmetic) one; everything else must be handed to the exact path.  Also on the two input
+    families where the filter is weakest (half vector / difference vector near their poles)."""
+    import torch
+    n = 100_000_000
+    g = torch.Generator(device="cuda").manual_seed(11)
+
+    def dirs(k):
+        z = 1.0 - 0.999 * torch.rand(k, device="cuda", generator=g)
+        ph = 6.283185307179586 * torch.rand(k, device="cuda", generator=g)
+        r = torch.sqrt(torch.clamp(1 - z * z, min=0))
+        return torch.stack([r * torch.cos(ph), r * torch.sin(ph), z], 1).contiguous()
+
+    wi, wo = dirs(n), dirs(n)
+    s = djb.merl_filter_stats(wi, wo)
+    assert s["certified_wrong"] == 0 and s["h_mismatch"] == 0, s
+    assert s["rejected"] < 0.01 * n, s
+    assert s["max_d_error"] < 1e-6 and s["max_acos_error"] < 1e-6, s  # budgets in kernels_merl.cu are 2e-6 each
+    m = 20_000_000
+    wo2 = dirs(m)
+    spec = wo2.clone()
+    spec[:, :2] *= -1
+    for base, sg in ((spec, 1e-2), (wo2, 1e-2), (spec, 5e-2), (wo2, 5e-2)):
+        w = base + sg * torch.randn(m, 3, device="cuda", generator=g)
+        w = (w / w.norm(dim=1, keepdim=True)).contiguous()
+        s = djb.merl_filter_stats(w, wo2)
+        assert s["certified_wrong"] == 0 and s["h_mismatch"] == 0, s
+    # and the product path itself: eval == table[index] for every lookup (index kernel and eval kernel agree)
+    rng = np.random.default_rng(0)
+    tab = rng.uniform(-0.05, 3.0, 3 * 90 * 90 * 180)
+    mm = djb.merl(tab)
+    out = mm.eval(wi[:m], wo[:m])
+    idx = djb.merl.index(wi[:m], wo[:m]).long()
+    cells = np.stack([(tab[:1458000] * (1.00 / 1500.0)).astype(np.float32),
+                      (tab[1458000:2916000] * (1.15 / 1500.0)).astype(np.float32),
+                      (tab[2916000:] * (1.66 / 1500.0)).astype(np.float32)], 1)
+    cells[(cells < 0).any(axis=1)] = 0
+    assert torch.equal(torch.from_numpy(cells).cuda()[idx], out)
