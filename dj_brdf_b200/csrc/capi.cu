@@ -2,9 +2,11 @@
 // host-side params factories, device-resident table handles and the host<->device staging
 // pipeline.  All numerics live in the kernel translation units; there is no CPU implementation
 // of any bulk path in this library.
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -113,6 +115,78 @@ static void pdfparams_h(float ax, float ay, float rho, float tx, float ty, djb20
 struct BulkIn { const void *host; size_t item; };                 // one item per pair
 struct BulkOut { void *host; size_t item; };                      // one item per (material, pair)
 
+// Per host thread: three device staging slots + streams, kept between calls (a renderer calls the C-ABI in a
+// loop; cudaMalloc / cudaFree per call would serialise the device).  Grow-only; djb200_release_cache() or thread
+// exit frees it.
+struct StagingArena {
+	int device = -1;
+	size_t slot_bytes = 0, aux_bytes = 0;
+	void *buf[3] = {nullptr, nullptr, nullptr};
+	void *aux = nullptr; // small per-call descriptors (params blocks, Fresnel spline points)
+	cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t aux_ready = nullptr;
+	// upload `bytes` of descriptors to aux + offset; every slot stream waits for it
+	cudaError_t upload_aux(const void *host, size_t offset, size_t bytes)
+	{
+		cudaError_t e = cudaMemcpyAsync((char *)aux + offset, host, bytes, cudaMemcpyHostToDevice, st[0]);
+		if (e == cudaSuccess) e = cudaEventRecord(aux_ready, st[0]);
+		for (int s = 1; s < 3 && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(st[s], aux_ready, 0);
+		return e;
+	}
+	cudaError_t reserve_aux(size_t bytes)
+	{
+		if (bytes <= aux_bytes) return cudaSuccess;
+		if (aux) cudaFree(aux);
+		aux = nullptr;
+		aux_bytes = 0;
+		size_t want = bytes < 65536 ? 65536 : bytes;
+		cudaError_t e = cudaMalloc(&aux, want);
+		if (e == cudaSuccess) aux_bytes = want;
+		return e;
+	}
+	void release()
+	{
+		if (aux) cudaFree(aux);
+		aux = nullptr;
+		aux_bytes = 0;
+		if (aux_ready) cudaEventDestroy(aux_ready);
+		aux_ready = nullptr;
+		for (int s = 0; s < 3; ++s) {
+			if (buf[s]) cudaFree(buf[s]);
+			if (st[s]) cudaStreamDestroy(st[s]);
+			buf[s] = nullptr;
+			st[s] = nullptr;
+		}
+		slot_bytes = 0;
+		device = -1;
+	}
+	cudaError_t reserve(size_t bytes)
+	{
+		int dev = 0;
+		cudaError_t e = cudaGetDevice(&dev);
+		if (e != cudaSuccess) return e;
+		if (dev != device) release();
+		device = dev;
+		for (int s = 0; s < 3; ++s)
+			if (!st[s] && (e = cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking)) != cudaSuccess) return e;
+		if (!aux_ready && (e = cudaEventCreateWithFlags(&aux_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+		if (bytes <= slot_bytes) return cudaSuccess;
+		for (int s = 0; s < 3; ++s) {
+			if (buf[s]) cudaFree(buf[s]);
+			buf[s] = nullptr;
+		}
+		slot_bytes = 0;
+		for (int s = 0; s < 3; ++s)
+			if ((e = cudaMalloc(&buf[s], bytes)) != cudaSuccess) return e;
+		slot_bytes = bytes;
+		return cudaSuccess;
+	}
+	~StagingArena() { release(); }
+};
+static thread_local StagingArena t_arena;
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
 // body(dev_in[], dev_out[], chunk_n, stream): enqueue the kernels for one chunk; outputs use
 // out_stride = chunk_n.  reps = number of material blocks each output holds per pair.
 template <class Body>
@@ -123,63 +197,77 @@ static djb200_status host_pipeline(int64_t n, const std::vector<BulkIn> &ins, co
 	size_t per_pair = 0;
 	for (auto &i : ins) per_pair += i.item;
 	for (auto &o : outs) per_pair += o.item * (size_t)reps;
-	const size_t budget = (size_t)256 << 20; // device bytes per pipeline slot
+	static const char *env_mb = getenv("DJB200_CHUNK_MB");
+	static const bool trace = getenv("DJB200_TRACE") != nullptr;
+	const size_t budget = (size_t)(env_mb ? atoi(env_mb) : 256) << 20; // device bytes per pipeline slot
+	auto t_begin = std::chrono::steady_clock::now();
 	int64_t chunk = (int64_t)(budget / (per_pair ? per_pair : 1));
 	chunk = chunk < 4096 ? 4096 : chunk;
 	chunk &= ~(int64_t)3;
 	if (chunk > n) chunk = n;
-	const int SLOTS = (n > chunk) ? 3 : 1;
-
-	struct Slot {
-		cudaStream_t st = nullptr;
-		std::vector<void *> din, dout;
-	} slot[3];
+	const int SLOTS = 3;
+	size_t slot_bytes = 0;
+	for (auto &i : ins) slot_bytes += align_up(i.item * (size_t)chunk);
+	for (auto &o : outs) slot_bytes += align_up(o.item * (size_t)chunk * (size_t)reps);
+	StagingArena &A = t_arena;
+	cudaError_t e0 = A.reserve(slot_bytes);
+	if (e0 != cudaSuccess) {
+		A.release();
+		return cuda_fail(e0, "staging buffers");
+	}
 	djb200_status rc = DJB200_OK;
-	auto cleanup = [&]() {
-		for (int s = 0; s < SLOTS; ++s) {
-			if (slot[s].st) cudaStreamSynchronize(slot[s].st);
-			for (void *p : slot[s].din) cudaFree(p);
-			for (void *p : slot[s].dout) cudaFree(p);
-			if (slot[s].st) cudaStreamDestroy(slot[s].st);
-		}
-	};
-#define PCU(call)                                                                   \
-	do {                                                                            \
-		cudaError_t e__ = (call);                                                   \
-		if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call); cleanup(); return rc; } \
+#define PCU(call)                                                                                          \
+	do {                                                                                                   \
+		cudaError_t e__ = (call);                                                                          \
+		if (e__ != cudaSuccess) {                                                                          \
+			rc = cuda_fail(e__, #call);                                                                    \
+			for (int s__ = 0; s__ < SLOTS; ++s__) cudaStreamSynchronize(A.st[s__]);                        \
+			return rc;                                                                                     \
+		}                                                                                                  \
 	} while (0)
 
-	for (int s = 0; s < SLOTS; ++s) {
-		PCU(cudaStreamCreateWithFlags(&slot[s].st, cudaStreamNonBlocking));
-		for (auto &i : ins) {
-			void *p = nullptr;
-			PCU(cudaMalloc(&p, i.item * (size_t)chunk));
-			slot[s].din.push_back(p);
-		}
-		for (auto &o : outs) {
-			void *p = nullptr;
-			PCU(cudaMalloc(&p, o.item * (size_t)chunk * (size_t)reps));
-			slot[s].dout.push_back(p);
-		}
-	}
+	auto t_alloc = std::chrono::steady_clock::now();
+	std::vector<void *> din(ins.size()), dout(outs.size());
 	int c = 0;
 	for (int64_t off = 0; off < n; off += chunk, ++c) {
-		Slot &S = slot[c % SLOTS];
+		const int si = c % SLOTS;
+		cudaStream_t st = A.st[si];
+		char *base = (char *)A.buf[si];
+		size_t pos = 0;
+		for (size_t k = 0; k < ins.size(); ++k) { din[k] = base + pos; pos += align_up(ins[k].item * (size_t)chunk); }
+		for (size_t k = 0; k < outs.size(); ++k) { dout[k] = base + pos; pos += align_up(outs[k].item * (size_t)chunk * (size_t)reps); }
 		int64_t cn = n - off < chunk ? n - off : chunk;
 		for (size_t k = 0; k < ins.size(); ++k)
-			PCU(cudaMemcpyAsync(S.din[k], (const char *)ins[k].host + (size_t)off * ins[k].item, ins[k].item * (size_t)cn,
-			                    cudaMemcpyHostToDevice, S.st));
-		cudaError_t e = body(S.din, S.dout, cn, S.st);
-		if (e != cudaSuccess) { rc = cuda_fail(e, "kernel launch"); cleanup(); return rc; }
-		for (size_t k = 0; k < outs.size(); ++k)
-			for (int64_t m = 0; m < reps; ++m)
-				PCU(cudaMemcpyAsync((char *)outs[k].host + ((size_t)m * (size_t)n + (size_t)off) * outs[k].item,
-				                    (const char *)S.dout[k] + (size_t)m * (size_t)cn * outs[k].item,
-				                    outs[k].item * (size_t)cn, cudaMemcpyDeviceToHost, S.st));
+			PCU(cudaMemcpyAsync(din[k], (const char *)ins[k].host + (size_t)off * ins[k].item, ins[k].item * (size_t)cn,
+			                    cudaMemcpyHostToDevice, st));
+		cudaError_t e = body(din, dout, cn, st);
+		if (e != cudaSuccess) {
+			rc = cuda_fail(e, "kernel launch");
+			for (int s = 0; s < SLOTS; ++s) cudaStreamSynchronize(A.st[s]);
+			return rc;
+		}
+		for (size_t k = 0; k < outs.size(); ++k) {
+			// `reps` rows of cn items: device rows are cn items apart, host rows n items apart (material-major output)
+			if (reps == 1)
+				PCU(cudaMemcpyAsync((char *)outs[k].host + (size_t)off * outs[k].item, dout[k], outs[k].item * (size_t)cn,
+				                    cudaMemcpyDeviceToHost, st));
+			else
+				PCU(cudaMemcpy2DAsync((char *)outs[k].host + (size_t)off * outs[k].item, (size_t)n * outs[k].item, dout[k],
+				                      (size_t)cn * outs[k].item, (size_t)cn * outs[k].item, (size_t)reps,
+				                      cudaMemcpyDeviceToHost, st));
+		}
 	}
-	for (int s = 0; s < SLOTS; ++s) PCU(cudaStreamSynchronize(slot[s].st));
+	auto t_enq = std::chrono::steady_clock::now();
+	for (int s = 0; s < SLOTS; ++s) PCU(cudaStreamSynchronize(A.st[s]));
 #undef PCU
-	cleanup();
+	if (trace) {
+		auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+			return std::chrono::duration<double, std::milli>(b - a).count();
+		};
+		fprintf(stderr, "[djb200] host_pipeline n=%lld chunk=%lld: reserve %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
+		        (long long)n, (long long)chunk, ms(t_begin, t_alloc), ms(t_alloc, t_enq),
+		        ms(t_enq, std::chrono::steady_clock::now()));
+	}
 	return rc;
 }
 
@@ -262,18 +350,27 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 		return DJB200_OK;
 	}
 
-	// host memory: stage through the device in chunks
-	void *d_params = nullptr, *d_spline = nullptr;
-	if (layout == DJB200_PARAMS_BROADCAST) {
-		CU(cudaMalloc(&d_params, sizeof(djb200_params) * (size_t)n_params));
-		CU(cudaMemcpy(d_params, params, sizeof(djb200_params) * (size_t)n_params, cudaMemcpyHostToDevice));
-	}
-	if (L.fresnel_kind == DJB200_FRESNEL_SPLINE) {
-		CU(cudaMalloc(&d_spline, sizeof(float) * 3 * (size_t)mf->fresnel.n_points));
-		CU(cudaMemcpy(d_spline, mf->fresnel.points, sizeof(float) * 3 * (size_t)mf->fresnel.n_points,
-		              cudaMemcpyHostToDevice));
-		L.spline_pts = (const float *)d_spline;
-		L.spline_n = mf->fresnel.n_points;
+	// host memory: stage through the device in chunks; descriptors go to the arena's aux area (no per-call malloc)
+	void *d_params = nullptr;
+	{
+		StagingArena &A = t_arena;
+		const size_t pbytes = layout == DJB200_PARAMS_BROADCAST ? sizeof(djb200_params) * (size_t)n_params : 0;
+		const size_t poff = (pbytes + 255) & ~(size_t)255;
+		const size_t sbytes = L.fresnel_kind == DJB200_FRESNEL_SPLINE ? sizeof(float) * 3 * (size_t)mf->fresnel.n_points : 0;
+		CU(A.reserve(0));
+		CU(cudaStreamSynchronize(A.st[0])); // aux may still be read by the previous call's last chunks
+		CU(cudaStreamSynchronize(A.st[1]));
+		CU(cudaStreamSynchronize(A.st[2]));
+		CU(A.reserve_aux(poff + sbytes + 256));
+		if (pbytes) {
+			CU(A.upload_aux(params, 0, pbytes));
+			d_params = A.aux;
+		}
+		if (sbytes) {
+			CU(A.upload_aux(mf->fresnel.points, poff, sbytes));
+			L.spline_pts = (const float *)((char *)A.aux + poff);
+			L.spline_n = mf->fresnel.n_points;
+		}
 	}
 	std::vector<BulkIn> ins = {{a, a_item}, {b, 12}};
 	if (layout == DJB200_PARAMS_PER_PAIR) ins.push_back({params, sizeof(djb200_params)});
@@ -297,8 +394,6 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 			C.out2 = slot2 >= 0 ? (float *)dout[slot2] : nullptr;
 			return launch_microfacet(C, st);
 		});
-	if (d_params) cudaFree(d_params);
-	if (d_spline) cudaFree(d_spline);
 	return rc;
 }
 
@@ -356,6 +451,12 @@ djb200_status djb200_set_device(int device)
 }
 
 uint64_t djb200_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+djb200_status djb200_release_cache(void)
+{
+	t_arena.release();
+	return DJB200_OK;
+}
 
 djb200_status djb200_params_standard(djb200_params *out) { return djb200_params_elliptic(1.0f, 1.0f, 0.0f, out); }
 djb200_status djb200_params_isotropic(float a, djb200_params *out) { return djb200_params_elliptic(a, a, 0.0f, out); }

@@ -100,6 +100,9 @@ DJB200_API djb200_status djb200_device_count(int *count);
 DJB200_API djb200_status djb200_set_device(int device);
 /* counts kernels launched by this library in the calling process (for bench.py `gpu_launches`) */
 DJB200_API uint64_t djb200_kernel_launch_count(void);
+/* DJB200_MEM_HOST calls stage through per-thread device buffers that are kept between calls; this frees the
+ * calling thread's buffers (they are also freed when the thread exits) */
+DJB200_API djb200_status djb200_release_cache(void);
 
 /* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
 DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */
