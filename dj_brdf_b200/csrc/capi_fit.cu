@@ -17,6 +17,30 @@ struct DevBuf { // RAII for cudaMalloc
 	template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// grow-only device scratch kept per host thread between fit calls (cudaMalloc / cudaFree per call cost more than
+// the fit kernel itself); freed at thread exit
+struct Scratch {
+	void *p = nullptr;
+	size_t bytes = 0;
+	int device = -1;
+	~Scratch() { if (p) cudaFree(p); }
+	cudaError_t reserve(size_t want)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev == device && want <= bytes) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		bytes = 0;
+		device = dev;
+		cudaError_t e = cudaMalloc(&p, want ? want : 1);
+		if (e == cudaSuccess) bytes = want;
+		return e;
+	}
+	template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+thread_local Scratch t_fit_src, t_fit_K, t_fit_ws, t_fit_out, t_fit_resid;
+
 // host source descriptors -> device array (spline Fresnel points are uploaded into `spline_store`)
 djb200_status build_sources(const djb200_source *sources, int32_t n, std::vector<FitSourceDev> &out,
                             std::vector<DevBuf> &spline_store)
@@ -82,7 +106,8 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 {
 	if (n_sources < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative source count");
 	if (res <= 2) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid Resolution"); // DJB_ASSERT, dj_brdf.h:2218
-	if (res > 1024) return fail(DJB200_ERR_UNSUPPORTED, "resolution %d > 1024 does not fit one CTA's shared memory", res);
+	if (fit_tabular_smem_bytes(res) > 227 * 1024)
+		return fail(DJB200_ERR_UNSUPPORTED, "resolution %d does not fit one CTA's shared memory (max ~1500)", res);
 	if (iterations < 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one power iteration");
 	if (n_sources == 0) return DJB200_OK;
 	if (!sources || !results) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -102,7 +127,7 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 
 	cudaStream_t st = (cudaStream_t)stream;
 	const size_t n = (size_t)n_sources, cnt = (size_t)res - 1;
-	DevBuf d_src, d_K, d_grid, d_out, d_resid;
+	Scratch &d_src = t_fit_src, &d_K = t_fit_K, &d_grid = t_fit_ws, &d_out = t_fit_out, &d_resid = t_fit_resid;
 	// outputs packed per kind: p22 | sigma | cdf | qf (n x res each) | fresnel (n x res x 3) | alpha (n x 2)
 	const size_t per_kind = n * (size_t)res;
 	const size_t out_floats = 4 * per_kind + 3 * per_kind + 2 * n;
@@ -111,17 +136,17 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 		cudaError_t e__ = (call);                                \
 		if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
 	} while (0)
-	FCU(d_src.alloc(sizeof(FitSourceDev) * n));
-	FCU(d_K.alloc(sizeof(double) * n * cnt * cnt));
-	FCU(d_grid.alloc(sizeof(float) * n * 180 * 90));
-	FCU(d_out.alloc(sizeof(float) * out_floats));
-	FCU(d_resid.alloc(sizeof(float) * n * (size_t)iterations));
+	FCU(d_src.reserve(sizeof(FitSourceDev) * n));
+	FCU(d_K.reserve(sizeof(double) * n * cnt * cnt));
+	FCU(d_grid.reserve(sizeof(float4) * n * cnt * (cnt + 2))); // Fresnel ratio workspace
+	FCU(d_out.reserve(sizeof(float) * out_floats));
+	FCU(d_resid.reserve(sizeof(float) * n * (size_t)iterations));
 	FCU(cudaMemcpyAsync(d_src.p, src.data(), sizeof(FitSourceDev) * n, cudaMemcpyHostToDevice, st));
 	float *o = d_out.as<float>();
 	float *o_p22 = o, *o_sigma = o + per_kind, *o_cdf = o + 2 * per_kind, *o_qf = o + 3 * per_kind;
 	float *o_fres = o + 4 * per_kind, *o_alpha = o_fres + 3 * per_kind;
 	FCU(launch_fit_tabular(d_src.as<FitSourceDev>(), n_sources, res, shadow, iterations, d_K.as<double>(),
-	                       d_grid.as<float>(), o_p22, o_sigma, o_cdf, o_qf, o_fres, o_alpha, d_resid.as<float>(), st));
+	                       d_grid.as<float4>(), o_p22, o_sigma, o_cdf, o_qf, o_fres, o_alpha, d_resid.as<float>(), st));
 	std::vector<float> h(out_floats), hres(n * (size_t)iterations);
 	FCU(cudaMemcpyAsync(h.data(), o, sizeof(float) * out_floats, cudaMemcpyDeviceToHost, st));
 	FCU(cudaMemcpyAsync(hres.data(), d_resid.p, sizeof(float) * hres.size(), cudaMemcpyDeviceToHost, st));

@@ -68,7 +68,7 @@ cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int
 struct FitSourceDev;
 size_t fit_tabular_smem_bytes(int res);
 cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
-                               double *K_ws, float *grid_ws, float *p22, float *sigma, float *cdf, float *qf,
+                               double *K_ws, float4 *fres_ws, float *p22, float *sigma, float *cdf, float *qf,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st);
 
 // anisotropic fit stages; [row0, row1) = this GPU's shard of the n = (er - 1) * ar rows

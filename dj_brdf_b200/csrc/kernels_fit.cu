@@ -29,7 +29,7 @@ struct IsoFitArgs {
 	const FitSourceDev *sources; // [n_materials]
 	int res, shadow, iterations;
 	double *K;        // workspace: n_materials x cnt x cnt, K[b * cnt + a] = km(b, a)   (column of row a contiguous in a)
-	float *ndf_grid;  // workspace: n_materials x SIG_NPHI x SIG_NTHETA
+	float4 *fres_ws;  // workspace: n_materials x cnt x (cnt + 2) Fresnel ratios (rx, ry, rz, valid)
 	// outputs, n_materials x ...
 	float *p22, *sigma, *cdf, *qf, *fresnel, *alpha, *residuals;
 };
@@ -41,11 +41,15 @@ struct IsoFitArgs {
 //   float row_theta[cnt], row_tan[cnt], row_cos[cnt], row_kji[cnt]
 //   float cosphi[MAX_PHI_STEPS], terms[2 * NORM_NTHETA], sth[SIG_NTHETA], ui[SIG_NTHETA]
 //   float scan[8 * cnt]
+//   float grid[SIG_NPHI * SIG_NTHETA]      the NDF over the sigma quadrature nodes
+//   int   fr_count[cnt], fr_offset[cnt + 1]  trip counts of the Fresnel loops
 static size_t iso_smem_bytes(int res)
 {
 	size_t cnt = res - 1;
 	return sizeof(double) * (2 * cnt + SIG_NPHI + SIG_NTHETA) +
-	       sizeof(float) * (3 * (size_t)res + 4 * cnt + MAX_PHI_STEPS + 2 * NORM_NTHETA + 2 * SIG_NTHETA + 8 * cnt + 8);
+	       sizeof(float) * (3 * (size_t)res + 4 * cnt + MAX_PHI_STEPS + 2 * NORM_NTHETA + 2 * SIG_NTHETA + 8 * cnt + 8 +
+	                        SIG_NPHI * SIG_NTHETA) +
+	       sizeof(int) * (2 * cnt + 2);
 }
 
 __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
@@ -58,13 +62,16 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	float *row_theta = s_cdf + res, *row_tan = row_theta + cnt, *row_cos = row_tan + cnt, *row_kji = row_cos + cnt;
 	float *cosphi = row_kji + cnt, *terms = cosphi + MAX_PHI_STEPS, *sth = terms + 2 * NORM_NTHETA, *ui = sth + SIG_NTHETA;
 	float *scan = ui + SIG_NTHETA;
+	float *grid = scan + 8 * cnt;
+	int *fr_count = reinterpret_cast<int *>(grid + SIG_NPHI * SIG_NTHETA), *fr_offset = fr_count + cnt;
 	__shared__ int s_nphi;
+	__shared__ double s_red[3][FIT_THREADS / 32];
 	__shared__ float s_scale;
 
 	const FitSourceDev src = A.sources[mat];
 	const bool shadow = A.shadow != 0;
 	double *K = A.K + (size_t)mat * cnt * cnt;
-	float *grid = A.ndf_grid + (size_t)mat * SIG_NPHI * SIG_NTHETA;
+	float4 *fres_ws = A.fres_ws + (size_t)mat * cnt * (cnt + 2);
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
 	const Params sp = standard_params();
 
@@ -119,12 +126,22 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 			vout[a] = acc;
 		}
 		__syncthreads();
-		if (A.residuals && tid == 0) { // diagnostic only (not in the reference, never fed back)
-			double n0 = 0.0, n1 = 0.0, d = 0.0;
-			for (int a = 0; a < cnt; ++a) { n0 += vin[a] * vin[a]; n1 += vout[a] * vout[a]; }
-			n0 = sqrt(n0); n1 = sqrt(n1);
-			for (int a = 0; a < cnt; ++a) { double x = vout[a] / n1 - vin[a] / n0; d += x * x; }
-			A.residuals[(size_t)mat * A.iterations + it] = (float)sqrt(d);
+		if (A.residuals) { // diagnostic only (not in the reference, never fed back): ||v1/|v1| - v0/|v0||| = sqrt(2 - 2 cos)
+			double n0 = 0.0, n1 = 0.0, d01 = 0.0;
+			for (int a = tid; a < cnt; a += nt) { n0 += vin[a] * vin[a]; n1 += vout[a] * vout[a]; d01 += vin[a] * vout[a]; }
+			for (int o = 16; o > 0; o >>= 1) {
+				n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+				n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+				d01 += __shfl_xor_sync(0xffffffffu, d01, o);
+			}
+			if ((tid & 31) == 0) { s_red[0][tid >> 5] = n0; s_red[1][tid >> 5] = n1; s_red[2][tid >> 5] = d01; }
+			__syncthreads();
+			if (tid == 0) {
+				n0 = n1 = d01 = 0.0;
+				for (int w = 0; w < nt / 32; ++w) { n0 += s_red[0][w]; n1 += s_red[1][w]; d01 += s_red[2][w]; }
+				double d = 2.0 - 2.0 * d01 / (sqrt(n0) * sqrt(n1));
+				A.residuals[(size_t)mat * A.iterations + it] = (float)sqrt(d > 0.0 ? d : 0.0);
+			}
 		}
 		double *tmp = vin; vin = vout; vout = tmp;
 		__syncthreads();
@@ -175,6 +192,8 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	}
 	__syncthreads();
 	{
+		// 89 ordered sums of 16 200 terms each, one thread per view angle; every operand of the inner loop is in
+		// shared memory and is the same address for all lanes (broadcast)
 		const float dtheta = (float)(DJB_PI / (double)(float)SIG_NTHETA);
 		const float dphi = (float)(2.0 * DJB_PI / (double)(float)SIG_NPHI);
 		for (int i = tid; i < cnt; i += nt) {
@@ -186,7 +205,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 			for (int j2 = 0; j2 < SIG_NPHI; ++j2) {
 				const double cp = cphi_d[j2];
 				const float *g = grid + j2 * SIG_NTHETA;
-#pragma unroll 6
+#pragma unroll 10
 				for (int j1 = 0; j1 < SIG_NTHETA; ++j1) {
 					float s_h = sth[j1];
 					float kh = (float)((double)(sk * s_h) * cp + ckd * cth_d[j1]);
@@ -202,11 +221,70 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	__syncthreads();
 
 	// ---- compute_fresnel, dj_brdf.h:2583-2641 -------------------------------------------------------
+	// The reference walks theta_h for every theta_d bin i; the (i, j) evaluations are independent, only the running
+	// sums are ordered.  So: trip counts per bin, all ratios in parallel over the flattened (i, j) list, ordered sums.
+	for (int i = tid; i < cnt; i += nt) {
+		float tt = (float)i / (float)cnt;
+		float theta_d = (float)((double)tt * DJB_PI * 0.5);
+		const double bound = DJB_PI * 0.5 - (double)theta_d;
+		float theta_h = 0.0f;
+		int J = 0;
+		for (int j = 0; (double)theta_h < bound && j < cnt + 2; ++j) { // theta_h(cnt + 1) > pi/2 >= bound: at most cnt + 2 trips
+			float t1 = (float)j / (float)cnt;
+			theta_h = (float)((double)(t1 * t1) * DJB_PI * 0.5);
+			++J;
+		}
+		fr_count[i] = J;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		int acc = 0;
+		for (int i = 0; i < cnt; ++i) { fr_offset[i] = acc; acc += fr_count[i]; }
+		fr_offset[cnt] = acc;
+	}
+	__syncthreads();
+	{
+		const int total = fr_offset[cnt];
+		const float phi_d = (float)(DJB_PI * 0.5), phi_h = 0.0f;
+		for (int e = tid; e < total; e += nt) {
+			int lo = 0, hi = cnt - 1; // bin i with fr_offset[i] <= e < fr_offset[i + 1]
+			while (lo < hi) {
+				int mid = (lo + hi + 1) >> 1;
+				if (fr_offset[mid] <= e) lo = mid; else hi = mid - 1;
+			}
+			const int i = lo, j = e - fr_offset[lo];
+			float tt = (float)i / (float)cnt;
+			float theta_d = (float)((double)tt * DJB_PI * 0.5);
+			float t1 = (float)j / (float)cnt;
+			float theta_h = (float)((double)(t1 * t1) * DJB_PI * 0.5);
+			float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (!((double)theta_h > DJB_PI * 0.5)) {
+				V3 dir_i, dir_o;
+				hd_to_io(spherical(theta_h, phi_h), spherical(theta_d, phi_d), dir_i, dir_o);
+				dir_i = mk(0.f, 0.f, 1.f); // "hack to reproduce my EGSR fits", dj_brdf.h:2609
+				V3 fr1 = source_eval(src, dir_i, dir_o);
+				float fr2 = tab_eval_ideal(tab, sp, shadow, dir_i, dir_o); // ideal Fresnel: r == g == b
+				if ((double)fr2 > 1e-4) r = make_float4(fr1.x / fr2, fr1.y / fr2, fr1.z / fr2, 1.0f);
+			}
+			fres_ws[e] = r;
+		}
+	}
+	__syncthreads();
 	float *o_fres = A.fresnel + (size_t)mat * res * 3;
 	for (int i = tid; i < cnt; i += nt) {
-		V3 f = fresnel_bin(tab, src, shadow, i, cnt);
-		o_fres[3 * i] = f.x; o_fres[3 * i + 1] = f.y; o_fres[3 * i + 2] = f.z;
-		if (i == cnt - 1) { o_fres[3 * cnt] = f.x; o_fres[3 * cnt + 1] = f.y; o_fres[3 * cnt + 2] = f.z; }
+		V3 f = mk(0.f, 0.f, 0.f);
+		int c = 0;
+		const float4 *w = fres_ws + fr_offset[i];
+		for (int j = 0; j < fr_count[i]; ++j) {
+			float4 r = w[j];
+			if (r.w != 0.0f) { f.x += r.x; f.y += r.y; f.z += r.z; ++c; }
+		}
+		V3 o;
+		o.x = c == 0 ? 1.0f : fmin_ref(1.0f, f.x / (float)c);
+		o.y = c == 0 ? 1.0f : fmin_ref(1.0f, f.y / (float)c);
+		o.z = c == 0 ? 1.0f : fmin_ref(1.0f, f.z / (float)c);
+		o_fres[3 * i] = o.x; o_fres[3 * i + 1] = o.y; o_fres[3 * i + 2] = o.z;
+		if (i == cnt - 1) { o_fres[3 * cnt] = o.x; o_fres[3 * cnt + 1] = o.y; o_fres[3 * cnt + 2] = o.z; }
 	}
 
 	// ---- compute_cdf, dj_brdf.h:2705-2727 ------------------------------------------------------------
@@ -280,14 +358,14 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 }
 
 cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
-                               double *K_ws, float *grid_ws, float *p22, float *sigma, float *cdf, float *qf,
+                               double *K_ws, float4 *fres_ws, float *p22, float *sigma, float *cdf, float *qf,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st)
 {
 	if (n_materials <= 0) return cudaSuccess;
 	IsoFitArgs A;
 	A.sources = sources_dev;
 	A.res = res; A.shadow = shadow; A.iterations = iterations;
-	A.K = K_ws; A.ndf_grid = grid_ws;
+	A.K = K_ws; A.fres_ws = fres_ws;
 	A.p22 = p22; A.sigma = sigma; A.cdf = cdf; A.qf = qf; A.fresnel = fresnel; A.alpha = alpha; A.residuals = residuals;
 	size_t smem = iso_smem_bytes(res);
 	cudaError_t e = cudaFuncSetAttribute(fit_tabular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
