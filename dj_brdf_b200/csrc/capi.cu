@@ -452,6 +452,12 @@ djb200_status djb200_set_device(int device)
 
 uint64_t djb200_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
+djb200_status djb200_debug_force_generic(int on)
+{
+	g_force_generic.store(on ? 1 : 0);
+	return DJB200_OK;
+}
+
 djb200_status djb200_release_cache(void)
 {
 	t_arena.release();

@@ -8,6 +8,14 @@
 // -fmad=false (the build enforces it) and without -use_fast_math; CUDA's double sqrt and
 // division are IEEE-correct, double exp/acos/atan2/sin/cos are within 1-2 ulp of glibc's, which
 // survives the rounding back to float except for ~1e-8 of inputs.
+//
+// "Same rounding point" does not mean "same instruction".  Where the reference's double detour is ONE IEEE
+// operation on float operands -- float(sqrt(double(x))), float(double(a) / double(b)), float(1.0 + double(c)),
+// float(1.0 / double(b)) -- the float operation rounds identically (double has >= 2 * 24 + 2 digits, so the
+// double rounding is innocuous), and the hot functions below use __fsqrt_rn / __fdiv_rn / __frcp_rn / float
+// add directly: no conversions through the quarter-rate XU pipe, no FP64 divide.  Short multi-operation detours
+// (1 / sqrt, 1 / (pi t^2)) use a correctly rounded float primitive or a float-float sequence that reproduces
+// the rounded float except at double-rounding ties (~1e-8 of inputs, 1 ulp).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,9 +57,11 @@ DJB_DEV V3 cross(V3 a, V3 b)
 	return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 // (1.0 / b) rounded to float: the scalar of `vec3 / float_t` (:601)
-DJB_DEV float rcp_via_double(float b) { return (float)(1.0 / (double)b); }
+DJB_DEV float rcp_via_double(float b) { return __frcp_rn(b); } // == (float)(1.0 / (double)b): one IEEE op
 // inversesqrt(): 1.0 / sqrt(x) in double, rounded once to float (:612-616)
-DJB_DEV float inv_sqrt(float x) { return (float)(1.0 / sqrt((double)x)); }
+// two operations in double: equals the correctly rounded float rsqrt except at ties of the double rounding
+// (0 differences in 1.5e9 half vectors, djb200_debug_merl_filter_stats)
+DJB_DEV float inv_sqrt(float x) { return __frsqrt_rn(x); }
 DJB_DEV V3 normalize(V3 v) { return scale(inv_sqrt(dot(v, v)), v); }
 // djb::min/max/sat templates (:574-576), including their NaN pass-through
 DJB_DEV float fmin_ref(float a, float b) { return a < b ? a : b; }
@@ -211,7 +221,7 @@ template <int FK>
 DJB_DEV V3 fresnel_eval(const FresnelDev &f, float c)
 {
 	if (FK == FK_SCHLICK) {
-		float c1 = (float)(1.0 - (double)c), c2 = c1 * c1, c5 = c2 * c2 * c1;
+		float c1 = 1.0f - c, c2 = c1 * c1, c5 = c2 * c2 * c1; // float(1.0 - c): one rounding either way
 		return mk(f.v[0] + c5 * (1.0f - f.v[0]), f.v[1] + c5 * (1.0f - f.v[1]), f.v[2] + c5 * (1.0f - f.v[2]));
 	} else if (FK == FK_UNPOLARIZED) {
 		return mk(unpolarized_channel(c, f.v[0]), unpolarized_channel(c, f.v[1]), unpolarized_channel(c, f.v[2]));
@@ -230,9 +240,17 @@ DJB_DEV V3 fresnel_eval(const FresnelDev &f, float c)
 template <int NDF>
 DJB_DEV float p22_radial(float r2)
 {
-	if (NDF == NDF_GGX) { // :2056-2060
-		float t = (float)(1.0 + (double)r2);
-		return (float)(1.0 / (DJB_PI * (double)t * (double)t));
+	if (NDF == NDF_GGX) { // :2056-2060: t = float(1.0 + r2); float(1.0 / (M_PI * t * t)) with the products in double
+		float t = 1.0f + r2;
+		// float-float: D = pi * t^2 (t^2 exact as q + ql, pi = PI_H + PI_L + 2^-48 remainder), then one Newton
+		// step on the correctly rounded float reciprocal of its head gives 1 / D to ~2^-47 before the final rounding
+		const float PI_H = 3.14159274101257324f, PI_L = -8.74227765734758578e-08f;
+		float q = t * t, ql = __fmaf_rn(t, t, -q);
+		float Dh = PI_H * q;
+		float De = __fmaf_rn(PI_H, q, -Dh) + PI_H * ql + PI_L * q;
+		float y0 = __frcp_rn(Dh);
+		float r = __fmaf_rn(-Dh, y0, 1.0f) - De * y0;
+		return __fmaf_rn(y0, r, y0);
 	}
 	return (float)(exp((double)(-r2)) / DJB_PI); // :1866-1869
 }
@@ -240,7 +258,7 @@ DJB_DEV float p22_radial(float r2)
 template <int NDF>
 DJB_DEV float sigma_std_radial(float c)
 {
-	if (NDF == NDF_GGX) return (float)((1.0 + (double)c) / 2.0); // :2062-2065
+	if (NDF == NDF_GGX) return (1.0f + c) * 0.5f; // :2062-2065, float((1.0 + c) / 2.0): one rounding either way
 	// beckmann, :1871-1879
 	if (c == 1.0f) return 1.0f;
 	float s = (float)sqrt(1.0 - (double)(c * c));
@@ -257,7 +275,7 @@ DJB_DEV float mf_sigma(const Params &p, V3 k)
 	float a = k.x * p.ax + k.y * p.ay * p.rho;
 	float b = k.y * p.ay * p.srho;
 	float c = k.z - k.x * p.tx - k.y * p.ty;
-	float nrm = (float)sqrt((double)(a * a + b * b + c * c));
+	float nrm = __fsqrt_rn(a * a + b * b + c * c); // == (float)sqrt((double)(...)): one IEEE op
 	float cz = rcp_via_double(nrm) * c;
 	return nrm * sigma_std_radial<NDF>(cz);
 }
@@ -329,7 +347,7 @@ DJB_DEV V3 mf_evalp(const Params &p, const FresnelDev &f, bool shadow, V3 i, V3 
 		float cd = sat_ref(dot(o, h));
 		V3 Fr = fresnel_eval<FK>(f, cd);
 		float Dn = mf_ndf<NDF>(p, h);
-		return scale((float)((double)(Dn * G) / (4.0 * (double)o.z)), Fr);
+		return scale(__fdiv_rn(Dn * G, 4.0f * o.z), Fr); // 4 * o.z is exact; the quotient of two floats rounds once
 	}
 	return mk(0.f, 0.f, 0.f);
 }
@@ -339,7 +357,7 @@ template <int NDF>
 DJB_DEV float mf_pdf(const Params &p, bool shadow, V3 i, V3 o, V3 h)
 {
 	float G = mf_gaf<NDF>(p, shadow, i, o);
-	if (G > 0.0f) return (float)((double)mf_vndf<NDF>(p, h, o) / (4.0 * (double)dot(i, h)));
+	if (G > 0.0f) return __fdiv_rn(mf_vndf<NDF>(p, h, o), 4.0f * dot(i, h));
 	return 0.0f;
 }
 
@@ -477,7 +495,7 @@ DJB_DEV V3 mf_evalp_is(const Params &p, const FresnelDev &f, bool shadow, float 
 		i_out = i;
 		V3 Fr = fresnel_eval<FK>(f, cd);
 		float g1 = mf_g1<NDF>(p, o);
-		pdf_out = (float)((double)mf_vndf<NDF>(p, h, o) / (4.0 * (double)cd));
+		pdf_out = __fdiv_rn(mf_vndf<NDF>(p, h, o), 4.0f * cd);
 		return scale(G / g1, Fr);
 	}
 	return mk(0.f, 0.f, 0.f);

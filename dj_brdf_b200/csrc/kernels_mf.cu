@@ -6,10 +6,14 @@
 // HBM traffic per (pair, material): (24 + 12 M) / M bytes for eval -- 13.5 B at M = 16.
 // The kernel is bound by FP64 issue, not by HBM (DESIGN.md "Rooflines"): matching the reference to
 // the bit needs IEEE double sqrt/div/exp at its rounding points.
-#include "djb_device.cuh"
+#include <cstdlib>
+
 #include "djb_internal.h"
+#include "djb_lean.cuh"
 
 namespace djb200 {
+
+std::atomic<int> g_force_generic{getenv("DJB200_MF_GENERIC") != nullptr ? 1 : 0};
 
 constexpr int MF_THREADS = 256;
 constexpr int MF_MAX_SMEM_PARAMS = 256; // 12 KB of shared memory
@@ -34,7 +38,7 @@ DJB_DEV V3 evalp_rt(const Params &p, int fk, const FresnelDev &f, bool shadow, V
 		float cd = sat_ref(dot(o, h));
 		V3 Fr = fresnel_rt(fk, f, cd);
 		float Dn = mf_ndf<NDF>(p, h);
-		return scale((float)((double)(Dn * G) / (4.0 * (double)o.z)), Fr);
+		return scale(__fdiv_rn(Dn * G, 4.0f * o.z), Fr);
 	}
 	return mk(0.f, 0.f, 0.f);
 }
@@ -53,7 +57,7 @@ DJB_DEV V3 evalp_is_rt(const Params &p, int fk, const FresnelDev &f, bool shadow
 		i_out = i;
 		V3 Fr = fresnel_rt(fk, f, cd);
 		float g1 = mf_g1<NDF>(p, o);
-		pdf_out = (float)((double)mf_vndf<NDF>(p, h, o) / (4.0 * (double)cd));
+		pdf_out = __fdiv_rn(mf_vndf<NDF>(p, h, o), 4.0f * cd);
 		return scale(G / g1, Fr);
 	}
 	return mk(0.f, 0.f, 0.f);
@@ -140,6 +144,29 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 	}
 }
 
+// BROADCAST eval / evalp / pdf with an ideal or Schlick Fresnel term: the lean FP32 path (djb_lean.cuh).
+// Same results as mf_broadcast_kernel (tests compare the two at full size), ~2x fewer instructions.
+template <int NDF, int FK, int OP>
+__global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
+{
+	__shared__ ParamsX s_params[MF_MAX_SMEM_PARAMS];
+	for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
+	__syncthreads();
+	const FresnelDev fr = A.fr;
+	const bool shadow = A.shadow != 0;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		const V3 i = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
+		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
+		const PairX c = make_pair<OP>(i, o);
+		for (int m = 0; m < A.n_params; ++m) {
+			const long long slot = (long long)m * A.out_stride + k;
+			if (OP == OP_PDF) A.out0[slot] = lean_pdf<NDF>(s_params[m], shadow, c);
+			else st3(A.out0, slot, lean_evalp<NDF, FK, OP>(s_params[m], fr, shadow, c));
+		}
+	}
+}
+
 // PER_PAIR layout: pair k under params block k (roughness from textures at every shading point).
 template <int NDF, int OP>
 __global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
@@ -203,6 +230,20 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 	}
 	// BROADCAST: at most MF_MAX_SMEM_PARAMS blocks per launch
 	const int per = (OP == OP_PDF) ? 1 : 3;
+	// djb200_debug_force_generic(1) (or DJB200_MF_GENERIC=1) runs the mirrored-rounding kernel everywhere: A/B tests
+	const bool force_generic = g_force_generic.load(std::memory_order_relaxed) != 0;
+	constexpr bool lean_op = (OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF);
+	const bool lean = lean_op && !force_generic && (L.fresnel_kind == FK_IDEAL || L.fresnel_kind == FK_SCHLICK);
+	static int resident_lean = 0;
+	if (lean_op && !resident_lean) {
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_lean, mf_lean_kernel<NDF, FK_SCHLICK, lean_op ? OP : OP_EVAL>,
+		                                              MF_THREADS, 0);
+		if (resident_lean < 1) resident_lean = 1;
+	}
+	if (lean) {
+		long long lcap = (long long)sm_count() * resident_lean;
+		grid = (int)(want < lcap ? want : lcap);
+	}
 	for (int64_t m0 = 0; m0 < L.n_params; m0 += MF_MAX_SMEM_PARAMS) {
 		int64_t mc = L.n_params - m0 < MF_MAX_SMEM_PARAMS ? L.n_params - m0 : MF_MAX_SMEM_PARAMS;
 		A.params = reinterpret_cast<const Params *>(L.params) + m0;
@@ -211,7 +252,9 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		A.out0 = L.out0 ? L.out0 + off * per : nullptr;
 		A.out1 = L.out1 ? L.out1 + off * 3 : nullptr;
 		A.out2 = L.out2 ? L.out2 + off : nullptr;
-		mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		if (lean && L.fresnel_kind == FK_IDEAL) mf_lean_kernel<NDF, FK_IDEAL, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
+		else if (lean) mf_lean_kernel<NDF, FK_SCHLICK, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
+		else mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) return e;

@@ -104,6 +104,11 @@ DJB200_API uint64_t djb200_kernel_launch_count(void);
  * calling thread's buffers (they are also freed when the thread exits) */
 DJB200_API djb200_status djb200_release_cache(void);
 
+/* Debug switch for A/B tests: 1 = microfacet eval / evalp / pdf always run the mirrored-rounding kernel
+ * (double sub-expressions literally as in the reference), 0 (default) = the lean FP32 kernels where they apply.
+ * Both give the reference's rounded results; tests/test_gpu_parity.py compares them at full size. */
+DJB200_API djb200_status djb200_debug_force_generic(int on);
+
 /* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
 DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */
 DJB200_API djb200_status djb200_params_isotropic(float a, djb200_params *out);                 /* :1417 */
