@@ -150,7 +150,9 @@ template <int NDF, int FK, int OP>
 __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 {
 	__shared__ ParamsX s_params[MF_MAX_SMEM_PARAMS];
+	__shared__ float2 s_exp2[64]; // 2^(j/64) as float-float, for the Beckmann exponentials
 	for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
+	if (NDF == NDF_BECKMANN && threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
 	__syncthreads();
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 		const PairX c = make_pair<OP>(i, o);
 		for (int m = 0; m < A.n_params; ++m) {
 			const long long slot = (long long)m * A.out_stride + k;
-			if (OP == OP_PDF) A.out0[slot] = lean_pdf<NDF>(s_params[m], shadow, c);
-			else st3(A.out0, slot, lean_evalp<NDF, FK, OP>(s_params[m], fr, shadow, c));
+			if (OP == OP_PDF) A.out0[slot] = lean_pdf<NDF>(s_exp2, s_params[m], shadow, c);
+			else st3(A.out0, slot, lean_evalp<NDF, FK, OP>(s_exp2, s_params[m], fr, shadow, c));
 		}
 	}
 }
