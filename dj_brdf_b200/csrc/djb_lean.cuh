@@ -44,6 +44,15 @@ DJB_DEV float div_by(float a, float b, float y)
 	return __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
 }
 DJB_DEV float div_lean(float a, float b) { return div_by(a, b, rcp_lean(b)); }
+// a / b for a >= 0 that may be tiny (Beckmann tails): the FMA residual of div_by must not underflow, so small
+// numerators are lifted by 2^64 (exact), divided, and lowered again (exact unless the quotient is subnormal,
+// in which case the guarded IEEE division does the single rounding)
+DJB_DEV float div_by_small(float a, float b, float y)
+{
+	if (a > 1e-18f) return div_by(a, b, y);
+	float q = div_by(a * 0x1p64f, b, y) * 0x1p-64f;
+	return fabsf(q) > 0x1p-120f ? q : __fdiv_rn(a, b);
+}
 // correctly rounded sqrt(x) for normal x > 0
 DJB_DEV float sqrt_lean(float x)
 {
@@ -341,8 +350,10 @@ DJB_DEV float lean_ndf(const float2 *T, const ParamsX &m, const PairX &c)
 	float ys = div_by(t1, m.nrm, m.rcp_nrm);
 	float r2 = xs * xs + ys * ys;
 	float pv = NDF == NDF_BECKMANN ? beck_p22_lean(T, r2) : p22_radial<NDF_GGX>(r2);
-	// Beckmann's exp underflows gradually: below the normal range the FMA quotients would round twice
-	if (NDF == NDF_BECKMANN && !(pv > 1e-28f)) return __fdiv_rn(__fdiv_rn(pv, m.nrm), c.c4);
+	if (NDF == NDF_BECKMANN) { // the exponential underflows gradually: small numerators take the lifted division
+		if (pv == 0.0f) return 0.0f;
+		return div_by_small(div_by_small(pv, m.nrm, m.rcp_nrm), c.c4, c.rcp_c4);
+	}
 	return div_by(div_by(pv, m.nrm, m.rcp_nrm), c.c4, c.rcp_c4);
 }
 
@@ -350,31 +361,50 @@ DJB_DEV float lean_ndf(const float2 *T, const ParamsX &m, const PairX &c)
 template <int NDF, int FK, int OP>
 DJB_DEV V3 lean_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)
 {
-	float G = lean_gaf<NDF>(T, m.p, shadow, c.i, c.o);
+	const V3 z = mk(0.f, 0.f, 0.f);
+	const V3 zero = OP == OP_EVAL ? scale(c.inv_iz, z) : z; // 0 * (1 / i.z): keeps the reference's -0 / NaN for i.z <= 0
+	const float Dn = lean_ndf<NDF>(T, m, c);
+	// D == 0 (h below the 1e-4 gate, or Beckmann's exponential underflowed): F D G / (4 o.z) is +0 for o.z > 0
+	// whatever G is, so the two projected-area evaluations are skipped
+	if (Dn == 0.0f && c.den > 0.0f) return zero;
+	const float G = lean_gaf<NDF>(T, m.p, shadow, c.i, c.o);
 	if (G > 0.0f) {
-		float Dn = lean_ndf<NDF>(T, m, c);
-		float num = Dn * G;
-		float k = (c.den_ok && (NDF == NDF_GGX || num > 1e-28f)) ? div_by(num, c.den, c.rcp_den) : __fdiv_rn(num, c.den);
+		const float num = Dn * G;
+		float k;
+		if (!c.den_ok) k = __fdiv_rn(num, c.den);
+		else k = NDF == NDF_GGX ? div_by(num, c.den, c.rcp_den) : div_by_small(num, c.den, c.rcp_den);
 		V3 e = scale(k, fresnel_eval<FK>(f, c.cd));
 		return OP == OP_EVAL ? scale(c.inv_iz, e) : e;
 	}
-	V3 z = mk(0.f, 0.f, 0.f);
-	return OP == OP_EVAL ? scale(c.inv_iz, z) : z; // 0 * (1 / i.z): keeps the reference's -0 / NaN for i.z <= 0
+	return zero;
 }
 
-// microfacet::pdf, dj_brdf.h:1713-1730 with vndf, dj_brdf.h:1602-1615
+// microfacet::pdf, dj_brdf.h:1713-1730 with vndf, dj_brdf.h:1602-1615.  sigma(o) appears in G1(o) and in the
+// visible-normal density: evaluated once.
 template <int NDF>
 DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c)
 {
-	float G = lean_gaf<NDF>(T, m.p, shadow, c.i, c.o);
+	const float Dn = lean_ndf<NDF>(T, m, c);
+	if (Dn == 0.0f && c.den > 0.0f) return 0.0f; // vndf == 0: the pdf is +0 whatever G is
+	const Params &p = m.p;
+	const float sg_o = lean_sigma<NDF>(T, p, c.o);
+	const float rsg_o = rcp_lean(sg_o);
+	const float g1o = dot(c.o, mk(p.nx, p.ny, p.nz)) > 0.0f ? div_by(c.o.z, sg_o, rsg_o) : 0.0f;
+	float G = g1o;
+	if (shadow) { // gaf, dj_brdf.h:1644-1665
+		const float g1i = lean_g1<NDF>(T, p, c.i);
+		const float t = g1i * g1o;
+		G = t > 0.0f ? div_lean(t, g1i + g1o - t) : 0.0f;
+	}
 	if (G > 0.0f) {
-		float kh = dot(c.o, c.h);
+		const float kh = dot(c.o, c.h);
 		float v = 0.0f;
 		if (kh > 0.0f) {
-			float num = kh * lean_ndf<NDF>(T, m, c), sg = lean_sigma<NDF>(T, m.p, c.o);
-			v = (NDF == NDF_GGX || num > 1e-28f) ? div_lean(num, sg) : __fdiv_rn(num, sg);
+			const float num = kh * Dn;
+			v = NDF == NDF_GGX ? div_by(num, sg_o, rsg_o) : div_by_small(num, sg_o, rsg_o);
 		}
-		return (c.den_ok && (NDF == NDF_GGX || v > 1e-28f)) ? div_by(v, c.den, c.rcp_den) : __fdiv_rn(v, c.den);
+		if (!c.den_ok) return __fdiv_rn(v, c.den);
+		return NDF == NDF_GGX ? div_by(v, c.den, c.rcp_den) : div_by_small(v, c.den, c.rcp_den);
 	}
 	return 0.0f;
 }

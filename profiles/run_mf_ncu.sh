@@ -1,2 +1,2 @@
-ncu --set full --clock-control none --import-source on -k regex:mf_broadcast -s 6 -c 6 -f -o gpurun_out/prof_mf_b python bench.py --steps 1 --warmup 1 --pairs 20000000 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:mf_lean_kernel -s 4 -c 4 -f -o gpurun_out/prof_mf_lean python bench.py --steps 1 --warmup 1 --pairs 20000000 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
