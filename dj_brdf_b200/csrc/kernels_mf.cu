@@ -169,6 +169,30 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 	}
 }
 
+// BROADCAST sample: the lean path of djb_lean.cuh
+template <int NDF>
+__global__ void __launch_bounds__(MF_THREADS) mf_lean_sample_kernel(MfKernelArgs A)
+{
+	__shared__ Params s_params[MF_MAX_SMEM_PARAMS];
+	__shared__ float2 s_exp2[64];
+	__shared__ float4 s_log[128];
+	if (NDF == NDF_BECKMANN && threadIdx.x < 128) s_log[threadIdx.x] = g_log_128[threadIdx.x];
+	{
+		const float *src = reinterpret_cast<const float *>(A.params);
+		float *dst = reinterpret_cast<float *>(s_params);
+		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
+	}
+	if (threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
+	__syncthreads();
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		const float2 u = reinterpret_cast<const float2 *>(A.a)[k];
+		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
+		for (int m = 0; m < A.n_params; ++m)
+			st3(A.out0, (long long)m * A.out_stride + k, lean_sample<NDF>(s_exp2, s_log, s_params[m], u.x, u.y, o));
+	}
+}
+
 // PER_PAIR layout: pair k under params block k (roughness from textures at every shading point).
 template <int NDF, int OP>
 __global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
@@ -254,7 +278,8 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		A.out0 = L.out0 ? L.out0 + off * per : nullptr;
 		A.out1 = L.out1 ? L.out1 + off * 3 : nullptr;
 		A.out2 = L.out2 ? L.out2 + off : nullptr;
-		if (lean && L.fresnel_kind == FK_IDEAL) mf_lean_kernel<NDF, FK_IDEAL, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
+		if (OP == OP_SAMPLE && !force_generic) mf_lean_sample_kernel<NDF><<<grid, MF_THREADS, 0, st>>>(A);
+		else if (lean && L.fresnel_kind == FK_IDEAL) mf_lean_kernel<NDF, FK_IDEAL, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
 		else if (lean) mf_lean_kernel<NDF, FK_SCHLICK, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
 		else mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);

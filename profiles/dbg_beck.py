@@ -22,3 +22,17 @@ for pname, P in cases.param_sets(port).items():
             k = np.argmax(rel)
             print("   worst:", wi[k], wo[k], "lean", lean[k], "oracle", want[k], "generic", gen[k])
 lib.djb200_debug_force_generic(C.c_int(0))
+
+wi, wo, u = cases.pairs(200000, stream=80)
+for ndfname, ndf, cls in (("ggx", api.NDF_GGX, djb.ggx), ("beckmann", api.NDF_BECKMANN, djb.beckmann)):
+    for pname in ("iso0.1", "aniso", "offcentre"):
+        P = cases.param_sets(port)[pname]
+        b = cls()
+        lib.djb200_debug_force_generic(C.c_int(0)); lean = b.sample(u, wo, P)
+        lib.djb200_debug_force_generic(C.c_int(1)); gen = b.sample(u, wo, P)
+        want = port.sample(ndf, P, u, wo)
+        sl = (lean.view(np.uint32) == want.view(np.uint32)).all(axis=1).mean()
+        sg = (gen.view(np.uint32) == want.view(np.uint32)).all(axis=1).mean()
+        slg = (gen.view(np.uint32) == lean.view(np.uint32)).all(axis=1).mean()
+        print(f"sample {ndfname:8s} {pname:10s} lean==oracle {sl:.6f} generic==oracle {sg:.6f} lean==generic {slg:.6f}")
+lib.djb200_debug_force_generic(C.c_int(0))

@@ -338,5 +338,13 @@ def test_lean_kernels_match_mirrored_kernels_at_scale(djb, ndf):
             rel = ((lean[bad] - ref[bad]).abs() / ref[bad].abs().clamp_min(1e-30)).max().item() if bad.any() else 0.0
             assert rate >= 0.99999 and rel <= 1e-5, f"{ndf} {q}: bit-identical {rate:.7f}, worst rel {rel:.2e}"
             del lean, ref, same, bad
+        u = torch.rand(n, 2, device="cuda", generator=g)
+        lib.djb200_debug_force_generic(C.c_int(0))
+        lean = b.sample(u, wo, mats)
+        lib.djb200_debug_force_generic(C.c_int(1))
+        ref = b.sample(u, wo, mats)
+        same = ((lean.view(torch.int32) == ref.view(torch.int32)) | (torch.isnan(lean) & torch.isnan(ref))).all(dim=-1)
+        rate = same.float().mean().item()
+        assert rate >= 0.9999, f"{ndf} sample: lean vs mirrored bit-identical {rate:.6f}"
     finally:
         lib.djb200_debug_force_generic(C.c_int(0))
