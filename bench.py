@@ -249,6 +249,10 @@ def run_ours(args, rank, local_rank, world):
     kern_ms = {f"{n}_{o}": float(np.mean([ev[s][k][0].elapsed_time(ev[s][k][1]) for s in range(args.steps)]))
                for k, (n, o) in enumerate(kernels)}
 
+    if os.environ.get("DJB200_BENCH_TRACE"):
+        for s in range(args.steps):
+            print(f"[bench] rank {rank} step {s}: " + " ".join(f"{n}_{o}={ev[s][k][0].elapsed_time(ev[s][k][1]):.1f}ms"
+                                                                 for k, (n, o) in enumerate(kernels)), file=sys.stderr)
     # max over ranks
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
