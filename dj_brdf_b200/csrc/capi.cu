@@ -197,9 +197,9 @@ static djb200_status host_pipeline(int64_t n, const std::vector<BulkIn> &ins, co
 	size_t per_pair = 0;
 	for (auto &i : ins) per_pair += i.item;
 	for (auto &o : outs) per_pair += o.item * (size_t)reps;
-	static const char *env_mb = getenv("DJB200_CHUNK_MB");
+	const char *env_mb = getenv("DJB200_CHUNK_MB"); // device megabytes per staging slot (default 256); read per call so tests can shrink it
 	static const bool trace = getenv("DJB200_TRACE") != nullptr;
-	const size_t budget = (size_t)(env_mb ? atoi(env_mb) : 256) << 20; // device bytes per pipeline slot
+	const size_t budget = (size_t)(env_mb && atoi(env_mb) > 0 ? atoi(env_mb) : 256) << 20; // device bytes per pipeline slot
 	auto t_begin = std::chrono::steady_clock::now();
 	int64_t chunk = (int64_t)(budget / (per_pair ? per_pair : 1));
 	chunk = chunk < 4096 ? 4096 : chunk;

@@ -850,4 +850,49 @@ DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const Pai
 	return 0.0f;
 }
 
+// microfacet::evalp_is, dj_brdf.h:1734-1765: sample, weight F G / G1(o), pdf = vndf / (4 cos theta_d)
+template <int NDF, int FK>
+DJB_DEV V3 lean_evalp_is(const float2 *T, const float4 *LT, const ParamsX &m, const FresnelDev &f, bool shadow, float u1,
+                         float u2, V3 o, V3 &i_out, float &pdf_out)
+{
+	const Params &p = m.p;
+	const V3 i = lean_sample<NDF>(T, LT, p, u1, u2, o);
+	pdf_out = 0.0f;
+	i_out = mk(0.f, 0.f, 0.f);
+	// G1(o) and sigma(o) are shared by the shadowing term, the weight and the visible-normal density
+	const float sg_o = lean_sigma<NDF>(T, p, o);
+	const float rsg_o = rcp_lean(sg_o);
+	const float g1o = dot(o, mk(p.nx, p.ny, p.nz)) > 0.0f ? div_by(o.z, sg_o, rsg_o) : 0.0f;
+	float G = g1o;
+	if (shadow) {
+		const float g1i = lean_g1<NDF>(T, p, i);
+		const float t = g1i * g1o;
+		G = t > 0.0f ? div_lean(t, g1i + g1o - t) : 0.0f;
+	}
+	if (G > 0.0f) {
+		PairX c; // only the half-vector fields are used by lean_ndf
+		c.h = normalize(i + o);
+		c.facing = c.h.z > 1e-4f;
+		const float rz = rcp_lean(c.h.z);
+		c.sx = div_by(-c.h.x, c.h.z, rz);
+		c.sy = div_by(-c.h.y, c.h.z, rz);
+		const float c2 = c.h.z * c.h.z;
+		c.c4 = c2 * c2;
+		c.rcp_c4 = rcp_lean(c.c4);
+		const float kh = dot(o, c.h);
+		const float cd = sat_ref(kh);
+		i_out = i;
+		float v = 0.0f;
+		if (kh > 0.0f) {
+			const float num = kh * lean_ndf<NDF>(T, m, c);
+			v = NDF == NDF_GGX ? div_by(num, sg_o, rsg_o) : div_by_small(num, sg_o, rsg_o);
+		}
+		const float den = 4.0f * cd;
+		if (!(den > 1e-28f)) pdf_out = __fdiv_rn(v, den);
+		else pdf_out = NDF == NDF_GGX ? div_lean(v, den) : div_by_small(v, den, rcp_lean(den));
+		return scale(div_by(G, g1o, rcp_lean(g1o)), fresnel_eval<FK>(f, cd));
+	}
+	return mk(0.f, 0.f, 0.f);
+}
+
 } // namespace djb200

@@ -144,52 +144,61 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 	}
 }
 
-// BROADCAST eval / evalp / pdf with an ideal or Schlick Fresnel term: the lean FP32 path (djb_lean.cuh).
-// Same results as mf_broadcast_kernel (tests compare the two at full size), ~2x fewer instructions.
-template <int NDF, int FK, int OP>
+// The lean FP32 path (djb_lean.cuh) for an ideal or Schlick Fresnel term, every query, both params layouts.
+// Same results as the mirrored kernels below (tests compare the two at full size), about half the instructions.
+template <int NDF, int FK, int OP, bool PERPAIR>
 __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 {
-	__shared__ ParamsX s_params[MF_MAX_SMEM_PARAMS];
+	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
+	__shared__ ParamsX s_params[PERPAIR ? 1 : MF_MAX_SMEM_PARAMS];
 	__shared__ float2 s_exp2[64]; // 2^(j/64) as float-float, for the Beckmann exponentials
-	for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
+	__shared__ float4 s_log[128]; // logarithm table of the Beckmann sampling path
+	if (!PERPAIR)
+		for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
 	if (NDF == NDF_BECKMANN && threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
+	if (NDF == NDF_BECKMANN && uses_u && threadIdx.x < 128) s_log[threadIdx.x] = g_log_128[threadIdx.x];
 	__syncthreads();
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
-		const V3 i = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
-		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
-		const PairX c = make_pair<OP>(i, o);
-		for (int m = 0; m < A.n_params; ++m) {
-			const long long slot = (long long)m * A.out_stride + k;
-			if (OP == OP_PDF) A.out0[slot] = lean_pdf<NDF>(s_exp2, s_params[m], shadow, c);
-			else st3(A.out0, slot, lean_evalp<NDF, FK, OP>(s_exp2, s_params[m], fr, shadow, c));
+		V3 va;
+		if (uses_u) {
+			const float2 u = reinterpret_cast<const float2 *>(A.a)[k];
+			va = mk(u.x, u.y, 0.f);
+		} else {
+			va = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
 		}
-	}
-}
-
-// BROADCAST sample: the lean path of djb_lean.cuh
-template <int NDF>
-__global__ void __launch_bounds__(MF_THREADS) mf_lean_sample_kernel(MfKernelArgs A)
-{
-	__shared__ Params s_params[MF_MAX_SMEM_PARAMS];
-	__shared__ float2 s_exp2[64];
-	__shared__ float4 s_log[128];
-	if (NDF == NDF_BECKMANN && threadIdx.x < 128) s_log[threadIdx.x] = g_log_128[threadIdx.x];
-	{
-		const float *src = reinterpret_cast<const float *>(A.params);
-		float *dst = reinterpret_cast<float *>(s_params);
-		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
-	}
-	if (threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
-	__syncthreads();
-	const long long stride = (long long)gridDim.x * blockDim.x;
-	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
-		const float2 u = reinterpret_cast<const float2 *>(A.a)[k];
 		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
-		for (int m = 0; m < A.n_params; ++m)
-			st3(A.out0, (long long)m * A.out_stride + k, lean_sample<NDF>(s_exp2, s_log, s_params[m], u.x, u.y, o));
+		PairX c;
+		if (!uses_u) c = make_pair<uses_u ? OP_EVAL : OP>(va, o);
+		auto one = [&](const ParamsX &mx, long long slot) {
+			if (OP == OP_PDF) {
+				A.out0[slot] = lean_pdf<NDF>(s_exp2, mx, shadow, c);
+			} else if (OP == OP_SAMPLE) {
+				st3(A.out0, slot, lean_sample<NDF>(s_exp2, s_log, mx.p, va.x, va.y, o));
+			} else if (OP == OP_EVALP_IS) {
+				V3 iv;
+				float pdf;
+				const V3 w = lean_evalp_is<NDF, FK>(s_exp2, s_log, mx, fr, shadow, va.x, va.y, o, iv, pdf);
+				if (A.out0) st3(A.out0, slot, w);
+				if (A.out1) st3(A.out1, slot, iv);
+				if (A.out2) A.out2[slot] = pdf;
+			} else {
+				st3(A.out0, slot, lean_evalp<NDF, FK, (OP == OP_EVALP ? OP_EVALP : OP_EVAL)>(s_exp2, mx, fr, shadow, c));
+			}
+		};
+		if (PERPAIR) {
+			const float4 *pp = reinterpret_cast<const float4 *>(A.params + k); // 48 B blocks: 16-B aligned
+			const float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
+			Params p;
+			p.nx = q0.x; p.ny = q0.y; p.nz = q0.z; p.a1 = q0.w;
+			p.a2 = q1.x; p.phi_a = q1.y; p.ax = q1.z; p.ay = q1.w;
+			p.rho = q2.x; p.srho = q2.y; p.tx = q2.z; p.ty = q2.w;
+			one(extend_params(p), k);
+		} else {
+			for (int m = 0; m < A.n_params; ++m) one(s_params[m], (long long)m * A.out_stride + k);
+		}
 	}
 }
 
@@ -219,6 +228,24 @@ __global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
 	}
 }
 
+template <int NDF, int FK, int OP, bool PERPAIR>
+static int lean_grid_cap()
+{
+	static int resident = 0;
+	if (!resident) {
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_lean_kernel<NDF, FK, OP, PERPAIR>, MF_THREADS, 0);
+		if (resident < 1) resident = 1;
+	}
+	return sm_count() * resident;
+}
+
+template <int NDF, int FK, int OP, bool PERPAIR>
+static void launch_lean(const MfKernelArgs &A, long long want, cudaStream_t st)
+{
+	const long long cap = lean_grid_cap<NDF, FK, OP, PERPAIR>();
+	mf_lean_kernel<NDF, FK, OP, PERPAIR><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
+}
+
 template <int NDF, int OP>
 static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 {
@@ -235,7 +262,7 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 	if (L.n <= 0) return cudaSuccess;
 
 	// persistent grid-stride launch: a whole number of waves (SM count x resident CTAs per SM)
-	long long want = (L.n + MF_THREADS - 1) / MF_THREADS;
+	const long long want = (L.n + MF_THREADS - 1) / MF_THREADS;
 	static int resident_bc = 0, resident_pp = 0;
 	if (!resident_bc) {
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_bc, mf_broadcast_kernel<NDF, OP>, MF_THREADS, 0);
@@ -243,33 +270,26 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		if (resident_bc < 1) resident_bc = 1;
 		if (resident_pp < 1) resident_pp = 1;
 	}
-	long long cap = (long long)sm_count() * (L.layout == DJB200_PARAMS_PER_PAIR ? resident_pp : resident_bc);
-	int grid = (int)(want < cap ? want : cap);
+	const long long cap = (long long)sm_count() * (L.layout == DJB200_PARAMS_PER_PAIR ? resident_pp : resident_bc);
+	const int grid = (int)(want < cap ? want : cap);
+	// djb200_debug_force_generic(1) (or DJB200_MF_GENERIC=1) runs the mirrored-rounding kernels everywhere: A/B tests
+	const bool force_generic = g_force_generic.load(std::memory_order_relaxed) != 0;
+	// the lean kernels cover the ideal and Schlick Fresnel terms (sampling does not evaluate the Fresnel term at all)
+	const bool lean = !force_generic && (OP == OP_SAMPLE || L.fresnel_kind == FK_IDEAL || L.fresnel_kind == FK_SCHLICK);
+	const bool schlick = L.fresnel_kind == FK_SCHLICK && OP != OP_SAMPLE && OP != OP_PDF;
 
 	if (L.layout == DJB200_PARAMS_PER_PAIR) {
 		A.params = reinterpret_cast<const Params *>(L.params);
 		A.n_params = 1;
 		A.out0 = L.out0; A.out1 = L.out1; A.out2 = L.out2;
-		mf_perpair_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, true>(A, want, st);
+		else if (lean) launch_lean<NDF, FK_IDEAL, OP, true>(A, want, st);
+		else mf_perpair_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 		return cudaGetLastError();
 	}
 	// BROADCAST: at most MF_MAX_SMEM_PARAMS blocks per launch
 	const int per = (OP == OP_PDF) ? 1 : 3;
-	// djb200_debug_force_generic(1) (or DJB200_MF_GENERIC=1) runs the mirrored-rounding kernel everywhere: A/B tests
-	const bool force_generic = g_force_generic.load(std::memory_order_relaxed) != 0;
-	constexpr bool lean_op = (OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF);
-	const bool lean = lean_op && !force_generic && (L.fresnel_kind == FK_IDEAL || L.fresnel_kind == FK_SCHLICK);
-	static int resident_lean = 0;
-	if (lean_op && !resident_lean) {
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_lean, mf_lean_kernel<NDF, FK_SCHLICK, lean_op ? OP : OP_EVAL>,
-		                                              MF_THREADS, 0);
-		if (resident_lean < 1) resident_lean = 1;
-	}
-	if (lean) {
-		long long lcap = (long long)sm_count() * resident_lean;
-		grid = (int)(want < lcap ? want : lcap);
-	}
 	for (int64_t m0 = 0; m0 < L.n_params; m0 += MF_MAX_SMEM_PARAMS) {
 		int64_t mc = L.n_params - m0 < MF_MAX_SMEM_PARAMS ? L.n_params - m0 : MF_MAX_SMEM_PARAMS;
 		A.params = reinterpret_cast<const Params *>(L.params) + m0;
@@ -278,9 +298,8 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		A.out0 = L.out0 ? L.out0 + off * per : nullptr;
 		A.out1 = L.out1 ? L.out1 + off * 3 : nullptr;
 		A.out2 = L.out2 ? L.out2 + off : nullptr;
-		if (OP == OP_SAMPLE && !force_generic) mf_lean_sample_kernel<NDF><<<grid, MF_THREADS, 0, st>>>(A);
-		else if (lean && L.fresnel_kind == FK_IDEAL) mf_lean_kernel<NDF, FK_IDEAL, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
-		else if (lean) mf_lean_kernel<NDF, FK_SCHLICK, lean_op ? OP : OP_EVAL><<<grid, MF_THREADS, 0, st>>>(A);
+		if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, false>(A, want, st);
+		else if (lean) launch_lean<NDF, FK_IDEAL, OP, false>(A, want, st);
 		else mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 		cudaError_t e = cudaGetLastError();

@@ -346,5 +346,47 @@ def test_lean_kernels_match_mirrored_kernels_at_scale(djb, ndf):
         same = ((lean.view(torch.int32) == ref.view(torch.int32)) | (torch.isnan(lean) & torch.isnan(ref))).all(dim=-1)
         rate = same.float().mean().item()
         assert rate >= 0.9999, f"{ndf} sample: lean vs mirrored bit-identical {rate:.6f}"
+        # evalp_is and the PER_PAIR layout (roughness from textures) on a smaller set
+        k = 2_000_000
+        pp = torch.from_numpy(np.ascontiguousarray(mats[np.arange(k) % 16])).cuda()
+        outs = {}
+        for mode in (0, 1):
+            lib.djb200_debug_force_generic(C.c_int(mode))
+            w, iv, pd = b.evalp_is(u[:k], wo[:k], mats[3])
+            outs[mode] = (w, iv, pd, b.eval(wi[:k], wo[:k], pp), b.pdf(wi[:k], wo[:k], pp), b.sample(u[:k], wo[:k], pp))
+        names = ("evalp_is weight", "evalp_is i", "evalp_is pdf", "per-pair eval", "per-pair pdf", "per-pair sample")
+        for name, x, y in zip(names, outs[0], outs[1]):
+            same = (x.view(torch.int32) == y.view(torch.int32)) | (torch.isnan(x) & torch.isnan(y))
+            assert same.float().mean().item() >= 0.9999, f"{ndf} {name}: lean vs mirrored bit-identical {same.float().mean().item():.6f}"
     finally:
         lib.djb200_debug_force_generic(C.c_int(0))
+
+
+def test_host_pipeline_many_chunks(djb, port, monkeypatch):
+    """DJB200_MEM_HOST arrays are staged through the device in chunks (3-slot copy / compute pipeline, one pitched
+    D2H copy per chunk and output).  With a 1 MB slot the 100k-pair calls below take ~20 chunks each: results must be
+    the same as with device-resident arrays, for every output shape (rgb, scalar, three outputs, PER_PAIR params)."""
+    import torch
+    monkeypatch.setenv("DJB200_CHUNK_MB", "1")
+    n = 100_003  # not a multiple of the chunk size
+    wi, wo, u = cases.pairs(n, stream=320)
+    mats = cases.c2_materials(port)[:5]
+    dwi, dwo, du = (torch.from_numpy(x).cuda() for x in (wi, wo, u))
+    for cls in (djb.ggx, djb.beckmann):
+        b = cls(djb.fresnel.schlick([0.9, 0.5, 0.2]))
+        assert bits_equal(b.eval(wi, wo, mats), b.eval(dwi, dwo, mats).cpu().numpy()).all()
+        assert bits_equal(b.pdf(wi, wo, mats), b.pdf(dwi, dwo, mats).cpu().numpy()).all()
+        assert bits_equal(b.sample(u, wo, mats), b.sample(du, dwo, mats).cpu().numpy()).all()
+        hw, hi, hp = b.evalp_is(u, wo, mats[0])
+        gw, gi, gp = b.evalp_is(du, dwo, mats[0])
+        assert bits_equal(hw, gw.cpu().numpy()).all() and bits_equal(hi, gi.cpu().numpy()).all() and bits_equal(hp, gp.cpu().numpy()).all()
+    rng = np.random.default_rng(4)
+    blocks = np.stack([port.params_elliptic(float(a), float(c), float(d)) for a, c, d in
+                       zip(rng.uniform(0.05, 0.8, n), rng.uniform(0.05, 0.8, n), rng.uniform(0, 3.1, n))])
+    host = djb.ggx().eval(wi, wo, blocks, per_pair=True)
+    dev = djb.ggx().eval(dwi, dwo, torch.from_numpy(blocks).cuda()).cpu().numpy()
+    assert bits_equal(host, dev).all()
+    table = cases.random_merl_table(3)
+    m = djb.merl(table)
+    assert bits_equal(m.eval(wi, wo), m.eval(dwi, dwo).cpu().numpy()).all()
+    assert (djb.merl.index(wi, wo) == djb.merl.index(dwi, dwo).cpu().numpy()).all()
