@@ -171,6 +171,26 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads (and hence its pinned host buffers, first-touched below) to the CPUs NVML reports as
+    local to GPU `index`: with one process per GPU the host<->device copies of the e2e leg then stay on the GPU's
+    own socket instead of crossing the inter-socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -183,6 +203,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device -- dj_brdf_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = capi.load()
@@ -344,7 +365,8 @@ def run_ours(args, rank, local_rank, world):
             "kernels": per_kernel,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps, "slab_pairs": slab,
-                    "note": "pinned host buffers through the C-ABI (DJB200_MEM_HOST), wall clock max over ranks"},
+                    "note": "pinned host buffers through the C-ABI (DJB200_MEM_HOST), wall clock max over ranks",
+                    "cpus_bound_to_gpu_numa_node": numa},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "cpu_baseline": cpu,
