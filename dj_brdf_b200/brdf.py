@@ -200,6 +200,13 @@ class microfacet(brdf):
         m.fresnel = self.m_fresnel._c()
         return m
 
+    _prefix = "djb200_microfacet_"
+
+    def _first_arg(self):
+        """First argument of the C-ABI query: the construction-state descriptor (-> pointer, keepalive)."""
+        d = self._desc()
+        return C.byref(d), d
+
     def _params(self, user_param, n, mem):
         """-> (pointer, n_params, layout, keepalive, broadcast_count or None)"""
         if user_param is None:
@@ -235,8 +242,8 @@ class microfacet(brdf):
             shape = ((n, w) if w > 1 else (n,)) if M is None else ((M, n, w) if w > 1 else (M, n))
             outs.append(capi.empty_like_space(bb.keep, shape, np.float32))
         bouts = [Buf(x, np.float32, True) for x in outs]
-        desc = self._desc()
-        check(getattr(capi.load(), fn)(C.byref(desc), pptr, C.c_int64(npar), C.c_int(layout), ba.ptr, bb.ptr,
+        first, keep_first = self._first_arg()
+        check(getattr(capi.load(), fn)(first, pptr, C.c_int64(npar), C.c_int(layout), ba.ptr, bb.ptr,
                                        C.c_int64(n), *[x.ptr for x in bouts], C.c_int(mem),
                                        capi.current_stream_ptr(mem)))
         return outs
@@ -245,21 +252,21 @@ class microfacet(brdf):
     # [M,12] array of blocks (every pair under every block -> leading dim M), or with
     # per_pair=True an [n,12] array (pair k under block k).
     def eval(self, i, o, user_param=None, per_pair=False):
-        return self._query("djb200_microfacet_eval", i, o, 3, [3], user_param, per_pair)[0]
+        return self._query(self._prefix + "eval", i, o, 3, [3], user_param, per_pair)[0]
 
     def evalp(self, i, o, user_param=None, per_pair=False):
-        return self._query("djb200_microfacet_evalp", i, o, 3, [3], user_param, per_pair)[0]
+        return self._query(self._prefix + "evalp", i, o, 3, [3], user_param, per_pair)[0]
 
     def pdf(self, i, o, user_param=None, per_pair=False):
-        return self._query("djb200_microfacet_pdf", i, o, 3, [1], user_param, per_pair)[0]
+        return self._query(self._prefix + "pdf", i, o, 3, [1], user_param, per_pair)[0]
 
     def sample(self, u, o, user_param=None, per_pair=False):
         """u: [n, 2] uniforms (u1, u2) -- microfacet::sample(u1, u2, o, user_param)."""
-        return self._query("djb200_microfacet_sample", u, o, 2, [3], user_param, per_pair)[0]
+        return self._query(self._prefix + "sample", u, o, 2, [3], user_param, per_pair)[0]
 
     def evalp_is(self, u, o, user_param=None, per_pair=False):
         """-> (weight rgb, i, pdf) -- microfacet::evalp_is(u1, u2, o, &i, &pdf, user_param)."""
-        return tuple(self._query("djb200_microfacet_evalp_is", u, o, 2, [3, 3, 1], user_param, per_pair))
+        return tuple(self._query(self._prefix + "evalp_is", u, o, 2, [3, 3, 1], user_param, per_pair))
 
 
 class ggx(microfacet):
@@ -416,16 +423,43 @@ def _source_struct(src):
     return s
 
 
-class tabular:
-    """djb::tabular (dj_brdf.h:394-425): the isotropic power-iteration fit of any source BRDF.
+class tabular(microfacet):
+    """djb::tabular (dj_brdf.h:394-425): the isotropic power-iteration fit of any source BRDF -- and, like in the
+    reference, itself a microfacet BRDF: ``eval / evalp / pdf / sample / evalp_is`` run on the fitted tables
+    (normal-map sampling, since tabular does not support Smith VNDF sampling, dj_brdf.h:413).
 
     ``tabular(brdf, res, shadow)`` fits one material; ``tabular.fit_batch(brdfs, ...)`` fits many in
     one device pass.  ``iterations`` is 4 in the reference (dj_brdf.h:2518)."""
+    _prefix = "djb200_tabular_"
 
     def __init__(self, source, resolution, shadow=True, iterations=4, _result=None):
         r = _result or tabular._run([source], resolution, shadow, iterations)[0]
         self.__dict__.update(r)
         self.m_shadow = bool(shadow)
+        self.m_fresnel = fresnel.spline(self.m_fresnel_points)
+        self._h = None
+
+    def supports_smith_vndf_sampling(self):
+        return False
+
+    def _first_arg(self):
+        if self._h is None:  # upload the tables once
+            f = capi.TabularFit()
+            f.res = len(self.m_p22)
+            f.p22, f.sigma, f.cdf, f.qf = (self.__dict__[x].ctypes.data for x in ("m_p22", "m_sigma", "m_cdf", "m_qf"))
+            f.fresnel = self.m_fresnel_points.ctypes.data
+            h = C.c_void_p()
+            check(capi.load().djb200_tabular_create(C.byref(f), C.c_int32(int(self.m_shadow)), C.byref(h)))
+            self._h = h
+        return self._h, self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                capi.load().djb200_tabular_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     @staticmethod
     def _run(sources, res, shadow, iterations):

@@ -279,10 +279,25 @@ static cudaError_t upload_small(const void *host, size_t bytes, void **dev, cuda
 	return cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, st);
 }
 
+// `tab` != NULL: the queries run on a tabulated BRDF (kernels_tabular.cu) and `mf` is ignored
 static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const djb200_params *params,
                                      int64_t n_params, int layout, const float *a, const float *b, int64_t n,
-                                     float *out0, float *out1, float *out2, int mem, void *stream)
+                                     float *out0, float *out1, float *out2, int mem, void *stream,
+                                     const djb200_tabular *tab = nullptr)
 {
+	djb200_microfacet tab_desc;
+	if (tab) { // only the shadowing flag of the descriptor is used on this path
+		memset(&tab_desc, 0, sizeof tab_desc);
+		tab_desc.ndf = DJB200_NDF_GGX;
+		tab_desc.shadow = tab->shadow;
+		mf = &tab_desc;
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev != tab->device) return fail(DJB200_ERR_INVALID_ARGUMENT, "tabular handle lives on device %d, current device is %d", tab->device, dev);
+	}
+	auto launch = [tab](const MfLaunch &X, cudaStream_t s) {
+		return tab ? launch_tabular_query(tab->tables, tab->res, X, s) : launch_microfacet(X, s);
+	};
 	if (!mf) return fail(DJB200_ERR_INVALID_ARGUMENT, "microfacet descriptor is NULL");
 	if (mf->ndf != DJB200_NDF_BECKMANN && mf->ndf != DJB200_NDF_GGX)
 		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown ndf %d", mf->ndf);
@@ -343,7 +358,7 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 		}
 		L.a = a; L.b = b; L.n = n; L.out_stride = n;
 		L.out0 = out0; L.out1 = out1; L.out2 = out2;
-		cudaError_t e = launch_microfacet(L, st);
+		cudaError_t e = launch(L, st);
 		if (d_params) cudaFreeAsync(d_params, st);
 		if (d_spline) cudaFreeAsync(d_spline, st);
 		if (e != cudaSuccess) return cuda_fail(e, "microfacet kernel launch");
@@ -392,7 +407,7 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 			C.out0 = slot0 >= 0 ? (float *)dout[slot0] : nullptr;
 			C.out1 = slot1 >= 0 ? (float *)dout[slot1] : nullptr;
 			C.out2 = slot2 >= 0 ? (float *)dout[slot2] : nullptr;
-			return launch_microfacet(C, st);
+			return launch(C, st);
 		});
 	return rc;
 }
@@ -538,6 +553,76 @@ djb200_status djb200_hd_to_io(const float *h, const float *d, int64_t n, float *
 			return launch_hd_to_io((const float *)i[0], (const float *)i[1], cn, (float *)o[0], (float *)o[1], st);
 		});
 }
+
+// ---- djb::tabular as a BRDF ----------------------------------------------------------------------------
+djb200_status djb200_tabular_create(const djb200_tabular_fit *fit, int32_t shadow, djb200_tabular **out)
+{
+	if (!fit || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (fit->res <= 2 || !fit->p22 || !fit->sigma || !fit->qf || !fit->fresnel)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "incomplete fit (needs res > 2, p22, sigma, qf, fresnel)");
+	if (fit->res > 8192) return fail(DJB200_ERR_UNSUPPORTED, "resolution %d too large", fit->res);
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	const size_t res = (size_t)fit->res;
+	std::vector<float> h(6 * res);
+	memcpy(h.data(), fit->p22, 4 * res);
+	memcpy(h.data() + res, fit->sigma, 4 * res);
+	memcpy(h.data() + 2 * res, fit->qf, 4 * res);
+	memcpy(h.data() + 3 * res, fit->fresnel, 12 * res);
+	float *d = nullptr;
+	CU(cudaMalloc(&d, 4 * h.size()));
+	cudaError_t e = cudaMemcpy(d, h.data(), 4 * h.size(), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "tabular upload"); }
+	djb200_tabular *t = new djb200_tabular;
+	t->tables = d; t->res = fit->res; t->shadow = shadow ? 1 : 0;
+	cudaGetDevice(&t->device);
+	*out = t;
+	return DJB200_OK;
+}
+
+djb200_status djb200_tabular_destroy(djb200_tabular *t)
+{
+	if (!t) return DJB200_OK;
+	cudaFree(t->tables);
+	delete t;
+	return DJB200_OK;
+}
+
+#define DJB200_TAB_NULLCHECK if (!t) return fail(DJB200_ERR_INVALID_ARGUMENT, "tabular handle is NULL")
+djb200_status djb200_tabular_eval(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
+                                  const float *wi, const float *wo, int64_t n, float *out_rgb, int mem, void *stream)
+{
+	DJB200_TAB_NULLCHECK;
+	return microfacet_call(OP_EVAL, nullptr, params, n_params, params_layout, wi, wo, n, out_rgb, nullptr, nullptr, mem, stream, t);
+}
+djb200_status djb200_tabular_evalp(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
+                                   const float *wi, const float *wo, int64_t n, float *out_rgb, int mem, void *stream)
+{
+	DJB200_TAB_NULLCHECK;
+	return microfacet_call(OP_EVALP, nullptr, params, n_params, params_layout, wi, wo, n, out_rgb, nullptr, nullptr, mem, stream, t);
+}
+djb200_status djb200_tabular_pdf(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
+                                 const float *wi, const float *wo, int64_t n, float *out_pdf, int mem, void *stream)
+{
+	DJB200_TAB_NULLCHECK;
+	return microfacet_call(OP_PDF, nullptr, params, n_params, params_layout, wi, wo, n, out_pdf, nullptr, nullptr, mem, stream, t);
+}
+djb200_status djb200_tabular_sample(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
+                                    const float *u, const float *wo, int64_t n, float *out_wi, int mem, void *stream)
+{
+	DJB200_TAB_NULLCHECK;
+	return microfacet_call(OP_SAMPLE, nullptr, params, n_params, params_layout, u, wo, n, out_wi, nullptr, nullptr, mem, stream, t);
+}
+djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
+                                      const float *u, const float *wo, int64_t n, float *out_weight_rgb, float *out_wi,
+                                      float *out_pdf, int mem, void *stream)
+{
+	DJB200_TAB_NULLCHECK;
+	if (!out_weight_rgb && !out_wi && !out_pdf) return fail(DJB200_ERR_INVALID_ARGUMENT, "all outputs are NULL");
+	return microfacet_call(OP_EVALP_IS, nullptr, params, n_params, params_layout, u, wo, n, out_weight_rgb, out_wi, out_pdf, mem,
+	                       stream, t);
+}
+#undef DJB200_TAB_NULLCHECK
 
 // ---- MERL ------------------------------------------------------------------------------------------
 static const int64_t MERL_N = 90 * 90 * 180;

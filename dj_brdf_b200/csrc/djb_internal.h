@@ -10,6 +10,10 @@ struct djb200_merl {
 	float4 *cells; // one (r, g, b, 0) per cell, already multiplied by the MERL channel scales
 	int device;
 };
+struct djb200_tabular {
+	float *tables; // p22[res] | sigma[res] | qf[res] | fresnel[res][3]
+	int res, shadow, device;
+};
 struct djb200_utia {
 	float *table; // utia::normalize()d samples cast to float
 	int device;
@@ -45,6 +49,8 @@ extern std::atomic<int> g_force_generic; // kernels_mf.cu: 1 = never take the le
 int sm_count();
 
 cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st);
+// djb::tabular as a BRDF (kernels_tabular.cu); tables: device, p22[res] | sigma[res] | qf[res] | fresnel[res][3]
+cudaError_t launch_tabular_query(const float *tables, int res, const MfLaunch &L, cudaStream_t st);
 
 // tables / frames / LEAN (kernels_tables.cu)
 cudaError_t launch_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d, cudaStream_t st);

@@ -232,6 +232,32 @@ DJB200_API djb200_status djb200_fit_tabular(const djb200_source *sources, int32_
                                             int32_t shadow, int32_t iterations, djb200_tabular_fit *results,
                                             void *stream);
 
+/* ---- djb::tabular as a BRDF (dj_brdf.h:394-425) ---------------------------------------------- *
+ * The fitted tables evaluated / sampled like any other microfacet BRDF: the queries of dj_brdf.h:1529-1765 with
+ * tabular::p22_radial / sigma_std_radial / qf_radial (:2151-2176), the fitted Fresnel spline, and -- because
+ * tabular::supports_smith_vndf_sampling() is false (:413) -- normal-map sampling (:1806-1816) with its pdf
+ * D cos(theta_h) / (4 i.h).  `params` as in the microfacet queries (the tabulated distribution is the
+ * standard-space one; params stretch / shear / offset it). */
+typedef struct djb200_tabular djb200_tabular;
+DJB200_API djb200_status djb200_tabular_create(const djb200_tabular_fit *fit, int32_t shadow, djb200_tabular **out);
+DJB200_API djb200_status djb200_tabular_destroy(djb200_tabular *t);
+DJB200_API djb200_status djb200_tabular_eval(const djb200_tabular *t, const djb200_params *params, int64_t n_params,
+                                             int params_layout, const float *wi, const float *wo, int64_t n,
+                                             float *out_rgb, int mem, void *stream);
+DJB200_API djb200_status djb200_tabular_evalp(const djb200_tabular *t, const djb200_params *params, int64_t n_params,
+                                              int params_layout, const float *wi, const float *wo, int64_t n,
+                                              float *out_rgb, int mem, void *stream);
+DJB200_API djb200_status djb200_tabular_pdf(const djb200_tabular *t, const djb200_params *params, int64_t n_params,
+                                            int params_layout, const float *wi, const float *wo, int64_t n,
+                                            float *out_pdf, int mem, void *stream);
+DJB200_API djb200_status djb200_tabular_sample(const djb200_tabular *t, const djb200_params *params, int64_t n_params,
+                                               int params_layout, const float *u, const float *wo, int64_t n,
+                                               float *out_wi, int mem, void *stream);
+DJB200_API djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const djb200_params *params, int64_t n_params,
+                                                 int params_layout, const float *u, const float *wo, int64_t n,
+                                                 float *out_weight_rgb, float *out_wi, float *out_pdf, int mem,
+                                                 void *stream);
+
 /* Result of djb::tabular_anisotropic (eval tables) + fit_*_parameters (dj_brdf.h:2238-2273,
  * 3186-3307): p22/sigma are elev_res x azim_res, fresnel elev_res x rgb,
  * beckmann/ggx = (ax, ay, rho, tx_n, ty_n). */

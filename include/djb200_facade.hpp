@@ -345,40 +345,31 @@ public:
 	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const params *p, size_t n_params,
 	                djb200_params_layout layout, memory_space where = host, void *stream = NULL) const
 	{
-		djb200_microfacet d = describe();
-		detail::check(djb200_microfacet_eval(&d, raw(p), (int64_t)n_params, layout, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+		dispatch(0, raw(p), p ? (int64_t)n_params : 0, layout, &i->x, &o->x, n, &out->x, NULL, NULL, where, stream);
 	}
 	void evalp_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void *user_param = NULL, size_t n_params = 1,
 	                 djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host, void *stream = NULL) const
 	{
-		djb200_microfacet d = describe();
-		detail::check(djb200_microfacet_evalp(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, &i->x, &o->x,
-		                                      (int64_t)n, &out->x, where, stream));
+		dispatch(1, raw(user_param), user_param ? (int64_t)n_params : 0, layout, &i->x, &o->x, n, &out->x, NULL, NULL, where, stream);
 	}
 	void pdf_batch(const vec3 *i, const vec3 *o, size_t n, float_t *out, const void *user_param = NULL, size_t n_params = 1,
 	               djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host, void *stream = NULL) const
 	{
-		djb200_microfacet d = describe();
-		detail::check(djb200_microfacet_pdf(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, &i->x, &o->x,
-		                                    (int64_t)n, out, where, stream));
+		dispatch(2, raw(user_param), user_param ? (int64_t)n_params : 0, layout, &i->x, &o->x, n, out, NULL, NULL, where, stream);
 	}
 	void sample_batch(const float_t *u12, const vec3 *o, size_t n, vec3 *out_i, const void *user_param = NULL,
 	                  size_t n_params = 1, djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host,
 	                  void *stream = NULL) const
 	{
-		djb200_microfacet d = describe();
-		detail::check(djb200_microfacet_sample(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, u12, &o->x,
-		                                       (int64_t)n, &out_i->x, where, stream));
+		dispatch(3, raw(user_param), user_param ? (int64_t)n_params : 0, layout, u12, &o->x, n, &out_i->x, NULL, NULL, where, stream);
 	}
 	void evalp_is_batch(const float_t *u12, const vec3 *o, size_t n, vec3 *out_weight, vec3 *out_i, float_t *out_pdf,
 	                    const void *user_param = NULL, size_t n_params = 1,
 	                    djb200_params_layout layout = DJB200_PARAMS_BROADCAST, memory_space where = host,
 	                    void *stream = NULL) const
 	{
-		djb200_microfacet d = describe();
-		detail::check(djb200_microfacet_evalp_is(&d, raw(user_param), user_param ? (int64_t)n_params : 0, layout, u12, &o->x,
-		                                         (int64_t)n, out_weight ? &out_weight->x : NULL, out_i ? &out_i->x : NULL, out_pdf,
-		                                         where, stream));
+		dispatch(4, raw(user_param), user_param ? (int64_t)n_params : 0, layout, u12, &o->x, n, out_weight ? &out_weight->x : NULL,
+		         out_i ? &out_i->x : NULL, out_pdf, where, stream);
 	}
 
 	virtual bool supports_smith_vndf_sampling() const = 0;
@@ -403,6 +394,21 @@ public:
 protected:
 	microfacet(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : m_fresnel(f.copy()), m_shadow(shadow) {}
 	virtual int ndf_id() const = 0;
+	// one C-ABI call; op: 0 eval, 1 evalp, 2 pdf, 3 sample, 4 evalp_is.  tabular overrides this with its own entry points.
+	virtual void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a,
+	                      const float *b, size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
+	{
+		djb200_microfacet d = describe();
+		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
+		switch (op) {
+		case 0: st = djb200_microfacet_eval(&d, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 1: st = djb200_microfacet_evalp(&d, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 2: st = djb200_microfacet_pdf(&d, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 3: st = djb200_microfacet_sample(&d, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 4: st = djb200_microfacet_evalp_is(&d, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
+		}
+		detail::check(st);
+	}
 	static const djb200_params *raw(const void *p) { return reinterpret_cast<const djb200_params *>(p); }
 	const fresnel::impl *m_fresnel;
 	bool m_shadow;
@@ -540,30 +546,33 @@ inline djb200_source describe_source(const brdf &b)
 	memset(&s, 0, sizeof s);
 	if (const merl *m = dynamic_cast<const merl *>(&b)) { s.kind = DJB200_SOURCE_MERL; s.merl = m->handle(); }
 	else if (const utia *u = dynamic_cast<const utia *>(&b)) { s.kind = DJB200_SOURCE_UTIA; s.utia = u->handle(); }
-	else if (const microfacet *f = dynamic_cast<const microfacet *>(&b)) { s.kind = DJB200_SOURCE_MICROFACET; s.microfacet = f->describe(); }
+	else if (dynamic_cast<const ggx *>(&b) || dynamic_cast<const beckmann *>(&b)) {
+		s.kind = DJB200_SOURCE_MICROFACET;
+		s.microfacet = static_cast<const microfacet &>(b).describe();
+	}
 	else throw exc("djb_error: this BRDF type cannot be fitted on the device (merl, utia, ggx, beckmann can)");
 	return s;
 }
 } // namespace detail
 
 // ---------------------------------------------------------------------------------------------------
-// dj_brdf.h:394-425: the isotropic "power iteration" fit.  The tables are built on the GPU; the object exposes the
-// reference's accessors.  (Evaluating / sampling the tabulated BRDF itself is SURVEY section 8f row N2: not yet.)
-class tabular {
+// dj_brdf.h:394-425: the isotropic "power iteration" fit, and -- as in the reference -- a microfacet BRDF of its own: the
+// tables are built on the GPU, uploaded once as a device-resident handle, and eval / evalp / pdf / sample / evalp_is run on
+// them (normal-map sampling: tabular does not support Smith VNDF sampling, dj_brdf.h:413).
+class tabular : public radial {
 	std::vector<float_t> m_p22, m_sigma, m_cdf, m_qf, m_residuals;
 	std::vector<vec3> m_fresnel_pts;
-	fresnel::spline *m_fresnel;
 	float_t m_alpha_beckmann, m_alpha_ggx;
-	bool m_shadow;
-	tabular() : m_fresnel(NULL) {}
+	mutable djb200_tabular *m_handle;
+	tabular() : radial(), m_handle(NULL) {}
 public:
-	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4) : m_fresnel(NULL)
+	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4) : radial(fresnel::ideal(), shadow), m_handle(NULL)
 	{
 		const brdf *src = &source;
 		std::vector<tabular *> self(1, this);
 		run(&src, 1, resolution, shadow, iterations, self);
 	}
-	~tabular() { delete m_fresnel; }
+	~tabular() { djb200_tabular_destroy(m_handle); }
 	// many materials in one device pass (one CTA per material)
 	static std::vector<tabular *> fit_batch(const std::vector<const brdf *> &sources, int resolution, bool shadow = true,
 	                                        int iterations = 4)
@@ -580,12 +589,34 @@ public:
 	const std::vector<float_t> &get_cdfv() const { return m_cdf; }
 	const std::vector<float_t> &get_qfv() const { return m_qf; }
 	const std::vector<float_t> &get_residuals() const { return m_residuals; }
-	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
-	int get_shadow() const { return m_shadow; }
+	bool supports_smith_vndf_sampling() const { return false; }
+
+protected:
+	int ndf_id() const { return -1; }
+	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
+	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
+	{
+		if (!m_handle) { // upload the tables once
+			djb200_tabular_fit f;
+			memset(&f, 0, sizeof f);
+			f.res = (int32_t)m_p22.size();
+			f.p22 = const_cast<float *>(&m_p22[0]); f.sigma = const_cast<float *>(&m_sigma[0]);
+			f.cdf = const_cast<float *>(&m_cdf[0]); f.qf = const_cast<float *>(&m_qf[0]);
+			f.fresnel = const_cast<float *>(&m_fresnel_pts[0].x);
+			detail::check(djb200_tabular_create(&f, m_shadow ? 1 : 0, &m_handle));
+		}
+		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
+		switch (op) {
+		case 0: st = djb200_tabular_eval(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 1: st = djb200_tabular_evalp(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 2: st = djb200_tabular_pdf(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 3: st = djb200_tabular_sample(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 4: st = djb200_tabular_evalp_is(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
+		}
+		detail::check(st);
+	}
 
 private:
-	tabular(const tabular &);
-	tabular &operator=(const tabular &);
 	static void run(const brdf *const *sources, size_t n, int res, bool shadow, int iterations, std::vector<tabular *> &out)
 	{
 		DJB_ASSERT(res > 2 && "Invalid Resolution");
@@ -607,7 +638,7 @@ private:
 		for (size_t k = 0; k < n; ++k) {
 			out[k]->m_alpha_beckmann = fit[k].alpha_beckmann;
 			out[k]->m_alpha_ggx = fit[k].alpha_ggx;
-			out[k]->m_fresnel = new fresnel::spline(out[k]->m_fresnel_pts);
+			out[k]->set_fresnel(fresnel::spline(out[k]->m_fresnel_pts)); // get_fresnel() returns the fitted spline
 		}
 	}
 };

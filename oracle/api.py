@@ -283,6 +283,24 @@ class PortOracle:
                                  *[c_f32p(a.ctypes.data) for a in (p22, sigma, cdf, qf, fres, alpha)])
         return dict(p22=p22, sigma=sigma, cdf=cdf, qf=qf, fresnel=fres, alpha=alpha)
 
+    def tabular_query(self, op, fit, u_or_wi, wo, params=None, shadow=True, fresnel=None, nthreads=1):
+        """djb::tabular as a BRDF on the tables of `fit` (a fit_tabular() result): op in eval/evalp/pdf/sample/evalp_is."""
+        code = {"eval": 0, "evalp": 1, "pdf": 2, "sample": 3, "evalp_is": 4}[op]
+        a, b = _f32(u_or_wi), _f32(wo)
+        n = len(b)
+        fr = fresnel or Fresnel.spline(fit["fresnel"])
+        fs = self._fres(fr)
+        p = None if params is None else _f32(params)
+        o0 = np.zeros(n if code == 2 else (n, 3), np.float32)
+        o1 = np.zeros((n, 3), np.float32)
+        o2 = np.zeros(n, np.float32)
+        res = len(fit["p22"])
+        self.lib.orc_tabular_query(C.c_int(code), c_f32p(_f32(fit["p22"]).ctypes.data), c_f32p(_f32(fit["sigma"]).ctypes.data),
+                                   c_f32p(_f32(fit["qf"]).ctypes.data), C.c_int(res), C.byref(fs), C.c_int(int(shadow)),
+                                   c_f32p(_ptr(p)), c_f32p(a.ctypes.data), c_f32p(b.ctypes.data), i64(n),
+                                   c_f32p(o0.ctypes.data), c_f32p(o1.ctypes.data), c_f32p(o2.ctypes.data), C.c_int(nthreads))
+        return (o0, o1, o2) if code == 4 else o0
+
     def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=8):
         s, keep = self._source(src)
         n = elev_res * azim_res
@@ -485,6 +503,26 @@ class RefOracle:
         self.destroy(t)
         self.destroy(h)
         return dict(p22=p22, sigma=sigma, cdf=cdf, qf=qf, fresnel=fres, alpha=alpha)
+
+    def tabular_query(self, op, src, res, u_or_wi, wo, params=None, shadow=True, nthreads=1):
+        """The reference's djb::tabular object built from `src`, queried through the virtual brdf interface."""
+        h = self._source_handle(src)
+        t = C.c_void_p(self.lib.ref_tabular_create(h, C.c_int(res), C.c_int(int(shadow))))
+        n = len(wo)
+        try:
+            if op == "eval":
+                return self.brdf_eval(t, params, u_or_wi, wo, nthreads)
+            if op == "evalp_is":
+                w, i, pdf = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.float32)
+                self._q("ref_brdf_evalp_is", t, params, u_or_wi, wo, [w, i, pdf], nthreads)
+                return w, i, pdf
+            out = np.empty(n if op == "pdf" else (n, 3), np.float32)
+            self._q({"evalp": "ref_brdf_evalp", "pdf": "ref_brdf_pdf", "sample": "ref_brdf_sample"}[op], t, params, u_or_wi,
+                    wo, [out], nthreads)
+            return out
+        finally:
+            self.destroy(t)
+            self.destroy(h)
 
     def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=1):
         assert iterations == 4

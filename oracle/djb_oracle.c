@@ -253,12 +253,13 @@ float orc__spline_eval_f(const float *pts, int n, float u)
  * being built on this thread (djb_oracle_fit.c), :2151-2163 */
 #define ORC_NDF_TABULAR 2
 #define ORC_NDF_TABULAR_ANISO 3
-static __thread const float *t_tab_p22, *t_tab_sigma;
+static __thread const float *t_tab_p22, *t_tab_sigma, *t_tab_qf;
 static __thread int t_tab_np22, t_tab_nsigma; /* isotropic: table lengths; anisotropic: w (elevation), h (azimuth) */
 void orc__set_tabular(const float *p22, int np22, const float *sigma, int nsigma)
 {
 	t_tab_p22 = p22; t_tab_np22 = np22; t_tab_sigma = sigma; t_tab_nsigma = nsigma;
 }
+void orc__set_tabular_qf(const float *qf) { t_tab_qf = qf; }
 
 /* spline::eval2d<float_t>(uwrap_edge, u1, uwrap_repeat, u2), :1220-1247 */
 float orc__spline_eval2d_f(const float *pts, int w, int h, float u1, float u2)
@@ -432,7 +433,11 @@ static float mf_pdf(int ndf, int shadow, const orc_params *p, v3 i, v3 o)
 {
 	v3 h = v3_normalize(v3_add(i, o));
 	float G = mf_gaf(ndf, shadow, p, i, o);
-	if (D(G) > 0.0) return F(D(mf_vndf(ndf, p, h, o)) / (4.0 * D(v3_dot(i, h))));
+	if (D(G) > 0.0) {
+		/* tabular::supports_smith_vndf_sampling() is false (:413): the pdf of normal-map sampling, :1724-1725 */
+		if (ndf == ORC_NDF_TABULAR) return F(D(h.z * mf_ndf(ndf, p, h)) / (4.0 * D(v3_dot(i, h))));
+		return F(D(mf_vndf(ndf, p, h, o)) / (4.0 * D(v3_dot(i, h))));
+	}
 	return 0.0f;
 }
 
@@ -510,6 +515,14 @@ static float beckmann_qf2(float u, float ck, float sk)
 /* radial::sample_vp22_std_smith, :1818-1846 */
 static void sample_std_slopes(int ndf, float u1, float u2, v3 k, float *xs, float *ys)
 {
+	if (ndf == ORC_NDF_TABULAR) { /* radial::sample_vp22_std_nmap, :1806-1816, with tabular::qf_radial, :2172-2176 */
+		float phi_h = F(D(u1) * ORC_PI * 2.0);
+		float qf = orc__spline_eval_f(t_tab_qf, t_tab_np22, u2);
+		float r_h = F(tan(D(qf * F(ORC_PI) / 2.0f)));
+		*xs = F(D(r_h) * cos(D(phi_h)));
+		*ys = F(D(r_h) * sin(D(phi_h)));
+		return;
+	}
 	float ck = k.z;
 	float sk = D(k.z) < 1.0 ? F(sqrt(1.0 - D(k.z * k.z))) : 0.0f;
 	float tx, ty;
@@ -564,6 +577,11 @@ static v3 mf_evalp_is(int ndf, const orc_fresnel *fr, int shadow, const orc_para
 	if (D(G) > 0.0) {
 		float cd = f_sat(v3_dot(o, h));
 		*i_out = i;
+		if (ndf == ORC_NDF_TABULAR) { /* :1753-1756 */
+			float pdf_ = F(D(h.z * mf_ndf(ndf, p, h)) / (4.0 * D(cd)));
+			*pdf_out = pdf_;
+			return v3_div(mf_evalp(ndf, fr, shadow, p, i, o), pdf_);
+		}
 		v3 Fr = fresnel_eval(fr, cd);
 		float g1 = mf_g1(ndf, p, o);
 		*pdf_out = F(D(mf_vndf(ndf, p, h, o)) / (4.0 * D(cd)));
@@ -606,11 +624,17 @@ typedef struct {
 	orc_params P;
 	const float *a, *b;
 	float *o0, *o1, *o2;
+	const float *tab_p22, *tab_sigma, *tab_qf; /* ORC_NDF_TABULAR only */
+	int tab_res;
 } mf_ctx;
 
 static void mf_range(void *vctx, int64_t s, int64_t e)
 {
 	mf_ctx *c = (mf_ctx *)vctx;
+	if (c->ndf == ORC_NDF_TABULAR) { /* the tables are thread-local state */
+		orc__set_tabular(c->tab_p22, c->tab_res, c->tab_sigma, c->tab_res);
+		orc__set_tabular_qf(c->tab_qf);
+	}
 	for (int64_t k = s; k < e; ++k) {
 		switch (c->op) {
 		case 0: v3_st(c->o0, k, mf_eval(c->ndf, c->F, c->shadow, &c->P, v3_ld(c->a, k), v3_ld(c->b, k))); break;
@@ -633,6 +657,7 @@ static void mf_run(int op, int ndf, const orc_fresnel *F, int shadow, const orc_
                    const float *a, const float *b, int64_t n, float *o0, float *o1, float *o2, int nthreads)
 {
 	mf_ctx c;
+	memset(&c, 0, sizeof c);
 	c.op = op; c.ndf = ndf; c.shadow = shadow; c.F = F;
 	if (P) c.P = *P; else orc_params_elliptic(1.0f, 1.0f, 0.0f, &c.P); /* params::standard(), :1412-1415 */
 	c.a = a; c.b = b; c.o0 = o0; c.o1 = o1; c.o2 = o2;
@@ -655,6 +680,23 @@ ORC_API void orc_microfacet_evalp_is(int ndf, const orc_fresnel *F, int shadow, 
                                      const float *u2, const float *wo, int64_t n,
                                      float *out_w3, float *out_i3, float *out_pdf, int nthreads)
 { mf_run(4, ndf, F, shadow, P, u2, wo, n, out_w3, out_i3, out_pdf, nthreads); }
+
+/* djb::tabular as an evaluable / samplable BRDF (the tables come from orc_fit_tabular): the microfacet queries of
+ * dj_brdf.h:1529-1765 on the tabulated radial distribution.  op: 0 eval, 1 evalp, 2 pdf, 3 sample, 4 evalp_is */
+ORC_API void orc_tabular_query(int op, const float *p22, const float *sigma, const float *qf, int res,
+                               const orc_fresnel *F, int shadow, const orc_params *P, const float *a, const float *b,
+                               int64_t n, float *o0, float *o1, float *o2, int nthreads)
+{
+	mf_ctx c;
+	memset(&c, 0, sizeof c);
+	c.op = op; c.ndf = ORC_NDF_TABULAR; c.shadow = shadow; c.F = F;
+	if (P) c.P = *P; else orc_params_elliptic(1.0f, 1.0f, 0.0f, &c.P);
+	c.a = a; c.b = b; c.o0 = o0; c.o1 = o1; c.o2 = o2;
+	c.tab_p22 = p22; c.tab_sigma = sigma; c.tab_qf = qf; c.tab_res = res;
+	orc_parallel_ranges(n, nthreads, mf_range, &c);
+	orc__set_tabular(NULL, 0, NULL, 0);
+	orc__set_tabular_qf(NULL);
+}
 
 /* used by djb_oracle_fit.c */
 void orc__mf_eval1(int ndf, const orc_fresnel *F, int shadow, const orc_params *P,

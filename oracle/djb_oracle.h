@@ -100,6 +100,13 @@ void orc_source_eval(const orc_source *src, const float *wi, const float *wo, fl
 void orc_fit_tabular(const orc_source *src, int res, int shadow, int iterations,
                      float *p22, float *sigma, float *cdf, float *qf, float *fresnel3, float *alpha2);
 
+/* djb::tabular as a BRDF: eval (op 0), evalp (1), pdf (2), sample (3), evalp_is (4) on fitted tables
+ * (dj_brdf.h:1529-1765 with tabular::p22_radial / sigma_std_radial / qf_radial :2151-2176 and normal-map sampling
+ * :1806-1816); F = the fitted Fresnel spline (or any other term), P = NULL for params::standard() */
+void orc_tabular_query(int op, const float *p22, const float *sigma, const float *qf, int res,
+                       const orc_fresnel *F, int shadow, const orc_params *P, const float *a, const float *b,
+                       int64_t n, float *o0, float *o1, float *o2, int nthreads);
+
 /* anisotropic fit: tabular_anisotropic (dj_brdf.h:2238-2273, 3186-3307), eval tables only.
  * outputs: p22[er*ar], sigma[er*ar], fresnel[3*er], beckmann5/ggx5 = ax, ay, rho, tx, ty */
 void orc_fit_tabular_anisotropic(const orc_source *src, int elev_res, int azim_res, int shadow,

@@ -3,7 +3,8 @@
 //   facade_check <in.bin> <out.bin>
 // in.bin : int32 n, then wi[n][3], wo[n][3], u[n][2] (float32)
 // out.bin: for ndf in (ggx, beckmann): eval[n][3] (batch), pdf[n] (batch), sample[n][3] (batch), eval_scalar[16][3],
-//          eval16[2][n][3] (two params blocks, BROADCAST); then lrep round trip [5]
+//          eval16[2][n][3] (two params blocks, BROADCAST); then lrep round trip [5]; then djb::tabular(ggx, 90) as a BRDF:
+//          eval[n][3], sample[n][3], eval_scalar[3], alpha (beckmann, ggx)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -56,6 +57,20 @@ int main(int argc, char **argv)
 		float q[5];
 		back.get_pdfparams(&q[0], &q[1], &q[2], &q[3], &q[4]);
 		put(fo, q, sizeof q);
+		// djb::tabular: fitted on the GPU from an analytic GGX, then used as a BRDF through the base-class interface
+		djb::ggx plain;
+		djb::tabular tab(plain, 90);
+		const djb::brdf &tb = tab;
+		tb.eval_batch(&wi[0], &wo[0], n, &out[0]);
+		put(fo, &out[0], 12 * (size_t)n);
+		tab.sample_batch(&u[0], &wo[0], n, &out[0]);
+		put(fo, &out[0], 12 * (size_t)n);
+		djb::vec3 e0 = tb.eval(wi[0], wo[0]);
+		put(fo, &e0, 12);
+		float ab[2], dummy;
+		djb::tabular::fit_beckmann_parameters(tab).get_ellipse(&ab[0], &dummy, NULL);
+		djb::tabular::fit_ggx_parameters(tab).get_ellipse(&ab[1], &dummy, NULL);
+		put(fo, ab, sizeof ab);
 	} catch (const std::exception &e) {
 		fprintf(stderr, "%s\n", e.what());
 		return 1;

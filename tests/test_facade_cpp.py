@@ -95,6 +95,14 @@ def test_facade_matches_oracle(bins, port):
                    E[4] + ((d[4] + e1 * d[1]) + e2 * d[0])], np.float32)
     wantp = port.lrep_to_params(E2[None])[0]
     assert np.allclose(back, [wantp[6], wantp[7], wantp[8], wantp[10], wantp[11]], rtol=1e-5, atol=1e-7)
+    # djb::tabular fitted from an analytic GGX and evaluated / sampled through the brdf base class
+    tev, tsm, te0, tal = take(n, 3), take(n, 3), take(3), take(2)
+    fit = port.fit_tabular(api.Source.microfacet(api.NDF_GGX), 90)
+    want = port.tabular_query("eval", fit, wi, wo, None, nthreads=8)
+    assert rel_err(tev, want).max() <= 1e-5 and np.array_equal(tev == 0, want == 0)
+    assert bits_equal(tsm, port.tabular_query("sample", fit, u, wo, None, nthreads=8)).all(axis=1).mean() >= 0.9995
+    assert bits_equal(te0, tev[0]).all()
+    assert np.allclose(tal, fit["alpha"], rtol=1e-6)
     assert pos == raw.size
 
 

@@ -154,3 +154,42 @@ def test_aniso_row_sharding_is_bit_identical(djb):
     t1 = fs.tabular_anisotropic_sharded(src, er, ar, True, iters)
     assert bits_equal(t1.m_p22, whole.m_p22).all() and bits_equal(t1.ggx, whole.ggx).all()
     assert np.allclose(t1.residuals, whole.residuals, atol=1e-5)
+
+
+# ---- djb::tabular as a BRDF -----------------------------------------------------------
+@pytest.mark.parametrize("srcname", ["ggx", "merl"])
+def test_tabular_brdf_queries(djb, port, srcname):
+    """eval / evalp / pdf / sample / evalp_is of the fitted tabular BRDF against the oracle port (which is bit-identical
+    to the reference's own djb::tabular object, tests/test_oracle_vs_reference.py)."""
+    from tests.conftest import rel_err
+    if srcname == "ggx":
+        src, osrc = djb.ggx(), api.Source.microfacet(api.NDF_GGX)
+    else:
+        tab = cases.smooth_merl_table(21)
+        src, osrc = djb.merl(tab), api.Source.merl(tab)
+    fit = djb.tabular(src, 90)
+    ofit = port.fit_tabular(osrc, 90)
+    ofit = {k: np.asarray(v) for k, v in dict(p22=fit.m_p22, sigma=fit.m_sigma, qf=fit.m_qf, fresnel=fit.m_fresnel_points).items()}
+    wi, wo, u = cases.pairs(100_000, stream=500)
+    ewi, ewo, eu = cases.edge_pairs()
+    wi, wo, u = np.concatenate([wi, ewi]), np.concatenate([wo, ewo]), np.concatenate([u, eu])
+    for P, Pg in ((None, None), (port.params_elliptic(0.6, 0.3, 0.5),) * 2, (port.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1),) * 2):
+        for op in ("eval", "evalp", "pdf", "sample"):
+            a = u if op == "sample" else wi
+            got = getattr(fit, op)(a, wo, Pg)
+            want = port.tabular_query(op, ofit, a, wo, P, nthreads=8)
+            rate = bits_equal(got, want).mean()
+            assert rate >= 0.9995, f"{srcname} {op}: bit-identical {rate:.6f}"
+            if op != "sample":
+                assert np.array_equal(got == 0, want == 0) and rel_err(got, want).max() <= 1e-5, (srcname, op)
+        gw, gi, gp = fit.evalp_is(u, wo, Pg)
+        ww, wi_, wp = port.tabular_query("evalp_is", ofit, u, wo, P, nthreads=8)
+        ok = bits_equal(gi, wi_).all(axis=1)
+        assert ok.mean() >= 0.9995
+        assert rel_err(gw[ok], ww[ok]).max() <= 1e-5 and rel_err(gp[ok], wp[ok]).max() <= 1e-5
+    # PER_PAIR params on the device + sample / pdf consistency: weights are finite and non-negative
+    import torch
+    blocks = np.stack([port.params_elliptic(0.3 + 0.001 * (k % 400), 0.5, 0.1) for k in range(len(wo))])
+    dev = fit.eval(torch.from_numpy(wi).cuda(), torch.from_numpy(wo).cuda(), torch.from_numpy(blocks).cuda()).cpu().numpy()
+    want = np.stack([port.tabular_query("eval", ofit, wi[k:k + 1], wo[k:k + 1], blocks[k])[0] for k in range(0, 2000)])
+    assert rel_err(dev[:2000], want).max() <= 1e-5

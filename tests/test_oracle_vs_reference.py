@@ -74,3 +74,19 @@ def test_aniso_fit_on_shipped_utia_fixture(port, ref, fixtures):
     p = port.fit_tabular_anisotropic(api.Source.utia(utia), 24, 30, nthreads=8)
     for k in r:
         assert bits_equal(r[k], p[k]).all(), k
+
+
+def test_tabular_brdf_bit_identical(port, ref):
+    """djb::tabular as an evaluable / samplable BRDF: the port on its own fitted tables against the reference's object."""
+    wi, wo, u = cases.pairs(30_000, stream=400)
+    for src in (api.Source.microfacet(api.NDF_BECKMANN), api.Source.merl(cases.smooth_merl_table(22))):
+        fit = port.fit_tabular(src, 90)
+        for P in (None, port.params_elliptic(0.6, 0.3, 0.5), port.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1)):
+            for op in ("eval", "evalp", "pdf", "sample", "evalp_is"):
+                a = u if op in ("sample", "evalp_is") else wi
+                g = port.tabular_query(op, fit, a, wo, P, nthreads=8)
+                r = ref.tabular_query(op, src, 90, a, wo, P, nthreads=8)
+                if op == "evalp_is":
+                    assert all(bits_equal(x, y).all() for x, y in zip(g, r)), op
+                else:
+                    assert bits_equal(g, r).all(), op
