@@ -518,13 +518,40 @@ class tabular(microfacet):
         return params.isotropic(tab.alpha_ggx)
 
 
-class tabular_anisotropic:
-    """djb::tabular_anisotropic (dj_brdf.h:428-478), eval tables + parameter fits."""
+class tabular_anisotropic(microfacet):
+    """djb::tabular_anisotropic (dj_brdf.h:428-478): eval tables + parameter fits, and an evaluable BRDF
+    (``eval / evalp / pdf`` on the elevation x azimuth tables; its sampling tables are not built, so ``sample`` /
+    ``evalp_is`` raise DjbError UNSUPPORTED)."""
+    _prefix = "djb200_tabular_"
 
     def __init__(self, source, elevation_res, azimuthal_res, shadow=True, iterations=4, _result=None):
         r = _result or tabular_anisotropic._run([source], elevation_res, azimuthal_res, shadow, iterations)[0]
         self.__dict__.update(r)
         self.m_elevation_res, self.m_azimuthal_res = elevation_res, azimuthal_res
+        self.m_shadow = bool(shadow)
+        self.m_fresnel = fresnel.spline(self.m_fresnel_points)
+        self._h = None
+
+    def supports_smith_vndf_sampling(self):
+        return False
+
+    def _first_arg(self):
+        if self._h is None:
+            f = capi.TabularAnisotropicFit()
+            f.elev_res, f.azim_res = self.m_elevation_res, self.m_azimuthal_res
+            f.p22, f.sigma, f.fresnel = self.m_p22.ctypes.data, self.m_sigma.ctypes.data, self.m_fresnel_points.ctypes.data
+            h = C.c_void_p()
+            check(capi.load().djb200_tabular_anisotropic_create(C.byref(f), C.c_int32(int(self.m_shadow)), C.byref(h)))
+            self._h = h
+        return self._h, self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                capi.load().djb200_tabular_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     @staticmethod
     def _run(sources, er, ar, shadow, iterations):

@@ -296,7 +296,9 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 		if (dev != tab->device) return fail(DJB200_ERR_INVALID_ARGUMENT, "tabular handle lives on device %d, current device is %d", tab->device, dev);
 	}
 	auto launch = [tab](const MfLaunch &X, cudaStream_t s) {
-		return tab ? launch_tabular_query(tab->tables, tab->res, X, s) : launch_microfacet(X, s);
+		if (!tab) return launch_microfacet(X, s);
+		if (tab->azim_res > 0) return launch_tabular_aniso_query(tab->tables, tab->res, tab->azim_res, X, s);
+		return launch_tabular_query(tab->tables, tab->res, X, s);
 	};
 	if (!mf) return fail(DJB200_ERR_INVALID_ARGUMENT, "microfacet descriptor is NULL");
 	if (mf->ndf != DJB200_NDF_BECKMANN && mf->ndf != DJB200_NDF_GGX)
@@ -574,7 +576,30 @@ djb200_status djb200_tabular_create(const djb200_tabular_fit *fit, int32_t shado
 	cudaError_t e = cudaMemcpy(d, h.data(), 4 * h.size(), cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "tabular upload"); }
 	djb200_tabular *t = new djb200_tabular;
-	t->tables = d; t->res = fit->res; t->shadow = shadow ? 1 : 0;
+	t->tables = d; t->res = fit->res; t->shadow = shadow ? 1 : 0; t->azim_res = 0;
+	cudaGetDevice(&t->device);
+	*out = t;
+	return DJB200_OK;
+}
+
+djb200_status djb200_tabular_anisotropic_create(const djb200_tabular_anisotropic_fit *fit, int32_t shadow, djb200_tabular **out)
+{
+	if (!fit || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (fit->elev_res <= 1 || fit->azim_res <= 1 || !fit->p22 || !fit->sigma || !fit->fresnel)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "incomplete fit (needs resolutions > 1, p22, sigma, fresnel)");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	const size_t tab = (size_t)fit->elev_res * fit->azim_res, er = (size_t)fit->elev_res;
+	std::vector<float> h(2 * tab + 3 * er);
+	memcpy(h.data(), fit->p22, 4 * tab);
+	memcpy(h.data() + tab, fit->sigma, 4 * tab);
+	memcpy(h.data() + 2 * tab, fit->fresnel, 12 * er);
+	float *d = nullptr;
+	CU(cudaMalloc(&d, 4 * h.size()));
+	cudaError_t e = cudaMemcpy(d, h.data(), 4 * h.size(), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "tabular upload"); }
+	djb200_tabular *t = new djb200_tabular;
+	t->tables = d; t->res = fit->elev_res; t->azim_res = fit->azim_res; t->shadow = shadow ? 1 : 0;
 	cudaGetDevice(&t->device);
 	*out = t;
 	return DJB200_OK;
@@ -611,6 +636,7 @@ djb200_status djb200_tabular_sample(const djb200_tabular *t, const djb200_params
                                     const float *u, const float *wo, int64_t n, float *out_wi, int mem, void *stream)
 {
 	DJB200_TAB_NULLCHECK;
+	if (t->azim_res > 0) return fail(DJB200_ERR_UNSUPPORTED, "sampling tables of tabular_anisotropic are not built (SURVEY 8f N2)");
 	return microfacet_call(OP_SAMPLE, nullptr, params, n_params, params_layout, u, wo, n, out_wi, nullptr, nullptr, mem, stream, t);
 }
 djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
@@ -618,6 +644,7 @@ djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const djb200_para
                                       float *out_pdf, int mem, void *stream)
 {
 	DJB200_TAB_NULLCHECK;
+	if (t->azim_res > 0) return fail(DJB200_ERR_UNSUPPORTED, "sampling tables of tabular_anisotropic are not built (SURVEY 8f N2)");
 	if (!out_weight_rgb && !out_wi && !out_pdf) return fail(DJB200_ERR_INVALID_ARGUMENT, "all outputs are NULL");
 	return microfacet_call(OP_EVALP_IS, nullptr, params, n_params, params_layout, u, wo, n, out_weight_rgb, out_wi, out_pdf, mem,
 	                       stream, t);

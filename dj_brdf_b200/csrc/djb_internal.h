@@ -11,8 +11,9 @@ struct djb200_merl {
 	int device;
 };
 struct djb200_tabular {
-	float *tables; // p22[res] | sigma[res] | qf[res] | fresnel[res][3]
+	float *tables; // radial: p22[res] | sigma[res] | qf[res] | fresnel[res][3]; anisotropic: p22[er * ar] | sigma[er * ar] | fresnel[er][3]
 	int res, shadow, device;
+	int azim_res; // 0: radial tables (djb::tabular); > 0: djb::tabular_anisotropic with res = elevation resolution
 };
 struct djb200_utia {
 	float *table; // utia::normalize()d samples cast to float
@@ -51,6 +52,8 @@ int sm_count();
 cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st);
 // djb::tabular as a BRDF (kernels_tabular.cu); tables: device, p22[res] | sigma[res] | qf[res] | fresnel[res][3]
 cudaError_t launch_tabular_query(const float *tables, int res, const MfLaunch &L, cudaStream_t st);
+// djb::tabular_anisotropic as a BRDF (eval / evalp / pdf); tables: device, p22[er * ar] | sigma[er * ar] | fresnel[er][3]
+cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, const MfLaunch &L, cudaStream_t st);
 
 // tables / frames / LEAN (kernels_tables.cu)
 cudaError_t launch_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d, cudaStream_t st);

@@ -23,14 +23,17 @@ struct TabQueryArgs {
 	float *out0, *out1, *out2;
 };
 
-struct TabBrdf {
-	TabIso t;
-	const float *qf;
+template <class TAB>
+struct TabBrdfT {
+	TAB t;
+	const float *qf; // radial quantile table (isotropic only)
 	FresnelDev fr;
 	bool shadow;
 };
+typedef TabBrdfT<TabIso> TabBrdf;
 
-DJB_DEV float tabq_gaf(const TabBrdf &B, const Params &p, V3 i, V3 o)
+template <class TB>
+DJB_DEV float tabq_gaf(const TB &B, const Params &p, V3 i, V3 o)
 {
 	float g1o = tab_g1(B.t, p, o);
 	if (B.shadow) {
@@ -42,7 +45,8 @@ DJB_DEV float tabq_gaf(const TabBrdf &B, const Params &p, V3 i, V3 o)
 }
 
 // microfacet::evalp, dj_brdf.h:1529-1547
-DJB_DEV V3 tabq_evalp(const TabBrdf &B, const Params &p, V3 i, V3 o)
+template <class TB>
+DJB_DEV V3 tabq_evalp(const TB &B, const Params &p, V3 i, V3 o)
 {
 	V3 h = normalize(i + o);
 	float G = tabq_gaf(B, p, i, o);
@@ -56,7 +60,8 @@ DJB_DEV V3 tabq_evalp(const TabBrdf &B, const Params &p, V3 i, V3 o)
 }
 
 // microfacet::pdf without Smith VNDF sampling, dj_brdf.h:1724-1725
-DJB_DEV float tabq_pdf(const TabBrdf &B, const Params &p, V3 i, V3 o)
+template <class TB>
+DJB_DEV float tabq_pdf(const TB &B, const Params &p, V3 i, V3 o)
 {
 	V3 h = normalize(i + o);
 	float G = tabq_gaf(B, p, i, o);
@@ -185,6 +190,86 @@ static cudaError_t launch_tq(const TabQueryArgs &A, cudaStream_t st)
 	tabular_query_kernel<OP, PERPAIR><<<(int)(want < cap ? want : cap), TQ_THREADS, smem, st>>>(A);
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	return cudaGetLastError();
+}
+
+// djb::tabular_anisotropic (dj_brdf.h:428-478) as an evaluable BRDF: eval / evalp / pdf on the elevation x azimuth
+// tables (2 x 32 KB at 90 x 90: read through the read-only cache, not staged)
+template <int OP, bool PERPAIR>
+__global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQueryArgs A, int azim_res)
+{
+	__shared__ Params s_params[PERPAIR ? 1 : TQ_MAX_SMEM_PARAMS];
+	if (!PERPAIR) {
+		const float *src = reinterpret_cast<const float *>(A.params);
+		float *dst = reinterpret_cast<float *>(s_params);
+		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
+		__syncthreads();
+	}
+	TabBrdfT<TabAniso> B;
+	const int tab = A.res * azim_res;
+	B.t.p22 = A.tables; B.t.sigma = A.tables + tab; B.t.w = A.res; B.t.h = azim_res;
+	B.qf = nullptr;
+	B.fr.pts = A.tables + 2 * tab; B.fr.npts = A.res;
+	B.shadow = A.shadow != 0;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		const V3 i = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
+		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
+		auto one = [&](const Params &p, long long slot) {
+			if (OP == OP_EVAL) tq_st3(A.out0, slot, scale(rcp_via_double(i.z), tabq_evalp(B, p, i, o)));
+			else if (OP == OP_EVALP) tq_st3(A.out0, slot, tabq_evalp(B, p, i, o));
+			else A.out0[slot] = tabq_pdf(B, p, i, o);
+		};
+		if (PERPAIR) {
+			const float4 *pp = reinterpret_cast<const float4 *>(A.params + k);
+			const float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
+			Params p;
+			p.nx = q0.x; p.ny = q0.y; p.nz = q0.z; p.a1 = q0.w;
+			p.a2 = q1.x; p.phi_a = q1.y; p.ax = q1.z; p.ay = q1.w;
+			p.rho = q2.x; p.srho = q2.y; p.tx = q2.z; p.ty = q2.w;
+			one(p, k);
+		} else {
+			for (int m = 0; m < A.n_params; ++m) one(s_params[m], (long long)m * A.out_stride + k);
+		}
+	}
+}
+
+// tables: device, p22[er * ar] | sigma[er * ar] | fresnel[er][3]
+cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, const MfLaunch &L, cudaStream_t st)
+{
+	if (L.n <= 0) return cudaSuccess;
+	if (L.op != OP_EVAL && L.op != OP_EVALP && L.op != OP_PDF) return cudaErrorNotSupported;
+	TabQueryArgs A;
+	A.tables = tables; A.res = elev_res; A.shadow = L.shadow;
+	A.a = L.a; A.b = L.b; A.n = L.n; A.out_stride = L.out_stride;
+	A.out1 = A.out2 = nullptr;
+	const int per = (L.op == OP_PDF) ? 1 : 3;
+	long long want = (L.n + TQ_THREADS - 1) / TQ_THREADS, cap = (long long)sm_count() * 4;
+	const int grid = (int)(want < cap ? want : cap);
+#define TA_DISPATCH(PP)                                                                                             \
+	switch (L.op) {                                                                                                 \
+	case OP_EVAL: tabular_aniso_query_kernel<OP_EVAL, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res); break;          \
+	case OP_EVALP: tabular_aniso_query_kernel<OP_EVALP, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res); break;        \
+	default: tabular_aniso_query_kernel<OP_PDF, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res);                       \
+	}                                                                                                               \
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	if (L.layout == DJB200_PARAMS_PER_PAIR) {
+		A.params = reinterpret_cast<const Params *>(L.params);
+		A.n_params = 1;
+		A.out0 = L.out0;
+		TA_DISPATCH(true)
+		return cudaGetLastError();
+	}
+	for (int64_t m0 = 0; m0 < L.n_params; m0 += TQ_MAX_SMEM_PARAMS) {
+		int64_t mc = L.n_params - m0 < TQ_MAX_SMEM_PARAMS ? L.n_params - m0 : TQ_MAX_SMEM_PARAMS;
+		A.params = reinterpret_cast<const Params *>(L.params) + m0;
+		A.n_params = (int)mc;
+		A.out0 = L.out0 + m0 * L.out_stride * per;
+		TA_DISPATCH(false)
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return e;
+	}
+#undef TA_DISPATCH
+	return cudaSuccess;
 }
 
 // L: same launch description as the microfacet queries; tables: device, p22 | sigma | qf | fresnel

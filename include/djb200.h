@@ -275,6 +275,12 @@ DJB200_API djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sou
                                                         int32_t elev_res, int32_t azim_res, int32_t shadow,
                                                         int32_t iterations,
                                                         djb200_tabular_anisotropic_fit *results, void *stream);
+/* djb::tabular_anisotropic as an evaluable BRDF: a djb200_tabular handle on the elevation x azimuth tables.
+ * djb200_tabular_eval / _evalp / _pdf work on it (p22_std / sigma_std of dj_brdf.h:2178-2211, pdf = D cos / (4 i.h));
+ * _sample / _evalp_is return DJB200_ERR_UNSUPPORTED (its marginal / conditional sampling tables, dj_brdf.h:2766-3122,
+ * are not built). */
+DJB200_API djb200_status djb200_tabular_anisotropic_create(const djb200_tabular_anisotropic_fit *fit, int32_t shadow,
+                                                           djb200_tabular **out);
 
 /* ---- anisotropic fit, stage by stage ------------------------------------------------------- *
  * The same fit as djb200_fit_tabular_anisotropic(), split at the two places where a fit whose

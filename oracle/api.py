@@ -301,6 +301,19 @@ class PortOracle:
                                    c_f32p(o0.ctypes.data), c_f32p(o1.ctypes.data), c_f32p(o2.ctypes.data), C.c_int(nthreads))
         return (o0, o1, o2) if code == 4 else o0
 
+    def tabular_aniso_query(self, op, fit, er, ar, wi, wo, params=None, shadow=True, nthreads=1):
+        """djb::tabular_anisotropic as a BRDF on the tables of a fit_tabular_anisotropic() result: eval / evalp / pdf."""
+        code = {"eval": 0, "evalp": 1, "pdf": 2}[op]
+        a, b = _f32(wi), _f32(wo)
+        n = len(b)
+        fs = self._fres(Fresnel.spline(fit["fresnel"]))
+        p = None if params is None else _f32(params)
+        o0 = np.zeros(n if code == 2 else (n, 3), np.float32)
+        self.lib.orc_tabular_aniso_query(C.c_int(code), c_f32p(_f32(fit["p22"]).ctypes.data), c_f32p(_f32(fit["sigma"]).ctypes.data),
+                                         C.c_int(er), C.c_int(ar), C.byref(fs), C.c_int(int(shadow)), c_f32p(_ptr(p)),
+                                         c_f32p(a.ctypes.data), c_f32p(b.ctypes.data), i64(n), c_f32p(o0.ctypes.data), C.c_int(nthreads))
+        return o0
+
     def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=8):
         s, keep = self._source(src)
         n = elev_res * azim_res
@@ -519,6 +532,20 @@ class RefOracle:
             out = np.empty(n if op == "pdf" else (n, 3), np.float32)
             self._q({"evalp": "ref_brdf_evalp", "pdf": "ref_brdf_pdf", "sample": "ref_brdf_sample"}[op], t, params, u_or_wi,
                     wo, [out], nthreads)
+            return out
+        finally:
+            self.destroy(t)
+            self.destroy(h)
+
+    def tabular_aniso_query(self, op, src, er, ar, wi, wo, params=None, shadow=True, nthreads=1):
+        h = self._source_handle(src)
+        t = C.c_void_p(self.lib.ref_tabular_anisotropic_create(h, C.c_int(er), C.c_int(ar), C.c_int(int(shadow))))
+        n = len(wo)
+        try:
+            if op == "eval":
+                return self.brdf_eval(t, params, wi, wo, nthreads)
+            out = np.empty(n if op == "pdf" else (n, 3), np.float32)
+            self._q({"evalp": "ref_brdf_evalp", "pdf": "ref_brdf_pdf"}[op], t, params, wi, wo, [out], nthreads)
             return out
         finally:
             self.destroy(t)

@@ -435,7 +435,8 @@ static float mf_pdf(int ndf, int shadow, const orc_params *p, v3 i, v3 o)
 	float G = mf_gaf(ndf, shadow, p, i, o);
 	if (D(G) > 0.0) {
 		/* tabular::supports_smith_vndf_sampling() is false (:413): the pdf of normal-map sampling, :1724-1725 */
-		if (ndf == ORC_NDF_TABULAR) return F(D(h.z * mf_ndf(ndf, p, h)) / (4.0 * D(v3_dot(i, h))));
+		if (ndf == ORC_NDF_TABULAR || ndf == ORC_NDF_TABULAR_ANISO)
+			return F(D(h.z * mf_ndf(ndf, p, h)) / (4.0 * D(v3_dot(i, h))));
 		return F(D(mf_vndf(ndf, p, h, o)) / (4.0 * D(v3_dot(i, h))));
 	}
 	return 0.0f;
@@ -624,8 +625,8 @@ typedef struct {
 	orc_params P;
 	const float *a, *b;
 	float *o0, *o1, *o2;
-	const float *tab_p22, *tab_sigma, *tab_qf; /* ORC_NDF_TABULAR only */
-	int tab_res;
+	const float *tab_p22, *tab_sigma, *tab_qf; /* ORC_NDF_TABULAR / ORC_NDF_TABULAR_ANISO only */
+	int tab_res, tab_ar;                       /* radial: table length; anisotropic: elevation x azimuth resolution */
 } mf_ctx;
 
 static void mf_range(void *vctx, int64_t s, int64_t e)
@@ -634,6 +635,8 @@ static void mf_range(void *vctx, int64_t s, int64_t e)
 	if (c->ndf == ORC_NDF_TABULAR) { /* the tables are thread-local state */
 		orc__set_tabular(c->tab_p22, c->tab_res, c->tab_sigma, c->tab_res);
 		orc__set_tabular_qf(c->tab_qf);
+	} else if (c->ndf == ORC_NDF_TABULAR_ANISO) {
+		orc__set_tabular(c->tab_p22, c->tab_res, c->tab_sigma, c->tab_ar);
 	}
 	for (int64_t k = s; k < e; ++k) {
 		switch (c->op) {
@@ -696,6 +699,23 @@ ORC_API void orc_tabular_query(int op, const float *p22, const float *sigma, con
 	orc_parallel_ranges(n, nthreads, mf_range, &c);
 	orc__set_tabular(NULL, 0, NULL, 0);
 	orc__set_tabular_qf(NULL);
+}
+
+/* djb::tabular_anisotropic as an evaluable BRDF (eval, evalp, pdf; its sampling tables are not restated):
+ * op 0 eval, 1 evalp, 2 pdf on the elev_res x azim_res tables of orc_fit_tabular_anisotropic */
+ORC_API void orc_tabular_aniso_query(int op, const float *p22, const float *sigma, int elev_res, int azim_res,
+                                     const orc_fresnel *F, int shadow, const orc_params *P, const float *wi,
+                                     const float *wo, int64_t n, float *o0, int nthreads)
+{
+	mf_ctx c;
+	memset(&c, 0, sizeof c);
+	if (op < 0 || op > 2) return;
+	c.op = op; c.ndf = ORC_NDF_TABULAR_ANISO; c.shadow = shadow; c.F = F;
+	if (P) c.P = *P; else orc_params_elliptic(1.0f, 1.0f, 0.0f, &c.P);
+	c.a = wi; c.b = wo; c.o0 = o0;
+	c.tab_p22 = p22; c.tab_sigma = sigma; c.tab_res = elev_res; c.tab_ar = azim_res;
+	orc_parallel_ranges(n, nthreads, mf_range, &c);
+	orc__set_tabular(NULL, 0, NULL, 0);
 }
 
 /* used by djb_oracle_fit.c */

@@ -113,6 +113,12 @@ void orc_fit_tabular_anisotropic(const orc_source *src, int elev_res, int azim_r
                                  int iterations, float *p22, float *sigma, float *fresnel3,
                                  float *beckmann5, float *ggx5, int nthreads);
 
+/* djb::tabular_anisotropic as an evaluable BRDF: op 0 eval, 1 evalp, 2 pdf (dj_brdf.h:1529-1555, 1724-1725 with
+ * tabular_anisotropic::p22_std / sigma_std :2178-2211) */
+void orc_tabular_aniso_query(int op, const float *p22, const float *sigma, int elev_res, int azim_res,
+                             const orc_fresnel *F, int shadow, const orc_params *P, const float *wi,
+                             const float *wo, int64_t n, float *o0, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

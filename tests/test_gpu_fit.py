@@ -193,3 +193,22 @@ def test_tabular_brdf_queries(djb, port, srcname):
     dev = fit.eval(torch.from_numpy(wi).cuda(), torch.from_numpy(wo).cuda(), torch.from_numpy(blocks).cuda()).cpu().numpy()
     want = np.stack([port.tabular_query("eval", ofit, wi[k:k + 1], wo[k:k + 1], blocks[k])[0] for k in range(0, 2000)])
     assert rel_err(dev[:2000], want).max() <= 1e-5
+
+
+def test_tabular_anisotropic_brdf_queries(djb, port):
+    """djb::tabular_anisotropic as an evaluable BRDF: eval / evalp / pdf on the 2-D tables against the oracle port (bit-identical
+    to the reference's object, tests/test_oracle_vs_reference.py); sampling is reported as unsupported, not faked."""
+    from tests.conftest import rel_err
+    ut = cases.random_utia_table(12)
+    er, ar = 16, 20
+    fit = djb.tabular_anisotropic(djb.utia(ut), er, ar)
+    ofit = dict(p22=fit.m_p22, sigma=fit.m_sigma, fresnel=fit.m_fresnel_points)
+    wi, wo, u = cases.pairs(100_000, stream=600)
+    for P in (None, port.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1)):
+        for op in ("eval", "evalp", "pdf"):
+            got = getattr(fit, op)(wi, wo, P)
+            want = port.tabular_aniso_query(op, ofit, er, ar, wi, wo, P, nthreads=8)
+            assert bits_equal(got, want).mean() >= 0.9995, op
+            assert np.array_equal(got == 0, want == 0) and rel_err(got, want).max() <= 1e-5, op
+    with pytest.raises(djb.DjbError):
+        fit.sample(u, wo)

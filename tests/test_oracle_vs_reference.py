@@ -90,3 +90,14 @@ def test_tabular_brdf_bit_identical(port, ref):
                     assert all(bits_equal(x, y).all() for x, y in zip(g, r)), op
                 else:
                     assert bits_equal(g, r).all(), op
+
+
+def test_tabular_anisotropic_brdf_bit_identical(port, ref):
+    wi, wo, _ = cases.pairs(20_000, stream=400)
+    src = api.Source.utia(cases.random_utia_table(12))
+    fit = port.fit_tabular_anisotropic(src, 16, 20, nthreads=8)
+    for P in (None, port.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1)):
+        for op in ("eval", "evalp", "pdf"):
+            g = port.tabular_aniso_query(op, fit, 16, 20, wi, wo, P, nthreads=8)
+            r = ref.tabular_aniso_query(op, src, 16, 20, wi, wo, P, nthreads=8)
+            assert bits_equal(g, r).all(), op
