@@ -379,6 +379,58 @@ class utia(_table_brdf):
             check(capi.load().djb200_utia_create(C.c_void_p(s.ctypes.data), C.byref(self._h)))
 
 
+class _analytic_brdf(brdf):
+    """Shared by djb::sgd and djb::abc: coefficients looked up by MERL material name, eval through the C-ABI."""
+    _preset = _eval = _names = None
+    _data_type = None
+
+    def __init__(self, name):
+        self._data = self._data_type()
+        self.name = name
+        check(getattr(capi.load(), self._preset)(str(name).encode(), C.byref(self._data)))
+
+    @classmethod
+    def names(cls):
+        lib = capi.load()
+        return [getattr(lib, cls._names)(C.c_int32(k)).decode() for k in range(lib.djb200_preset_count())]
+
+    def eval(self, i, o, user_param=None):
+        bi, bo = Buf(i, np.float32), Buf(o, np.float32)
+        mem = capi.same_space(bi, bo)
+        n = bi.n // 3
+        out = capi.empty_like_space(bi.keep, (n, 3), np.float32)
+        bout = Buf(out, np.float32, True)
+        check(getattr(capi.load(), self._eval)(C.byref(self._data), bi.ptr, bo.ptr, C.c_int64(n), bout.ptr, C.c_int(mem),
+                                               capi.current_stream_ptr(mem)))
+        return out
+
+
+class sgd(_analytic_brdf):
+    """djb::sgd (dj_brdf.h:481-511): shifted-gamma-distribution BRDF of a MERL material, by name."""
+    _preset, _eval, _names, _data_type = "djb200_sgd_preset", "djb200_sgd_eval", "djb200_sgd_preset_name", capi.SgdData
+
+    def coefficients(self):
+        """[3, 11] float64: rhoD rhoS alpha p f0 f1 kap lambda c k theta0 per colour channel."""
+        return np.array([[self._data.ch[c][f] for f in range(11)] for c in range(3)], np.float64)
+
+    def get_fresnel(self):
+        c = self.coefficients()
+        return fresnel.sgd(c[:, 4].astype(np.float32), c[:, 5].astype(np.float32))
+
+
+class abc(_analytic_brdf):
+    """djb::abc (dj_brdf.h:514-535): ABC-distribution BRDF of a MERL material, by name."""
+    _preset, _eval, _names, _data_type = "djb200_abc_preset", "djb200_abc_eval", "djb200_abc_preset_name", capi.AbcData
+
+    def coefficients(self):
+        """[9] float64: kD[3], A[3], B, C, ior."""
+        d = self._data
+        return np.array([*d.kD, *d.A, d.B, d.C, d.ior], np.float64)
+
+    def get_fresnel(self):
+        return fresnel.unpolarized([np.float32(self._data.ior)] * 3)
+
+
 # --------------------------------------------------------------------------------------------------
 def nmap2leanmap(nmap, base_roughness=1e-5, bias=0.0):
     """utils/nmap2leanmap.cpp:18-54 (bias=0) / nmap2leanmap_biased.cpp:23-63 (bias=25).
@@ -418,6 +470,10 @@ def _source_struct(src):
         s.kind, s.utia = capi.SOURCE_UTIA, src._h
     elif isinstance(src, microfacet):
         s.kind, s.microfacet = capi.SOURCE_MICROFACET, src._desc()
+    elif isinstance(src, sgd):
+        s.kind, s.sgd = capi.SOURCE_SGD, C.pointer(src._data)
+    elif isinstance(src, abc):
+        s.kind, s.abc = capi.SOURCE_ABC, C.pointer(src._data)
     else:
         raise DjbError(6, f"cannot fit from a {type(src).__name__}")
     return s

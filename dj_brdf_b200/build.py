@@ -19,8 +19,9 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 BUILD = PKG / "build"
 LIB = PKG / "libdjb200.so"
-SOURCES = ["capi.cu", "capi_fit.cu", "kernels_mf.cu", "kernels_tables.cu", "kernels_merl.cu", "kernels_fit.cu", "kernels_tabular.cu"]
-HEADERS = ["djb_device.cuh", "djb_lean.cuh", "djb_fit.cuh", "djb_internal.h", "../../include/djb200.h"]
+SOURCES = ["capi.cu", "capi_fit.cu", "kernels_mf.cu", "kernels_tables.cu", "kernels_merl.cu", "kernels_fit.cu", "kernels_tabular.cu",
+           "kernels_analytic.cu", "presets.cu"]
+HEADERS = ["djb_presets.inc", "djb_device.cuh", "djb_lean.cuh", "djb_fit.cuh", "djb_internal.h", "../../include/djb200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

@@ -19,7 +19,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 NDF_BECKMANN, NDF_GGX = 0, 1
 FRESNEL_IDEAL, FRESNEL_SCHLICK, FRESNEL_UNPOLARIZED, FRESNEL_SGD, FRESNEL_SPLINE = range(5)
 PARAMS_BROADCAST, PARAMS_PER_PAIR = 0, 1
-SOURCE_MERL, SOURCE_UTIA, SOURCE_MICROFACET = 0, 1, 2
+SOURCE_MERL, SOURCE_UTIA, SOURCE_MICROFACET, SOURCE_SGD, SOURCE_ABC = 0, 1, 2, 3, 4
 
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "NO_DEVICE", 3: "CUDA", 4: "OUT_OF_MEMORY", 5: "IO",
                 6: "UNSUPPORTED"}
@@ -35,6 +35,8 @@ EXPORTED_SYMBOLS = [
     "djb200_merl_create", "djb200_merl_load", "djb200_merl_destroy", "djb200_merl_eval", "djb200_merl_index",
     "djb200_debug_merl_filter_stats",
     "djb200_utia_create", "djb200_utia_load", "djb200_utia_destroy", "djb200_utia_eval",
+    "djb200_sgd_preset", "djb200_abc_preset", "djb200_preset_count", "djb200_sgd_preset_name", "djb200_abc_preset_name",
+    "djb200_sgd_eval", "djb200_abc_eval",
     "djb200_nmap_to_leanmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
     "djb200_fit_tabular", "djb200_fit_tabular_anisotropic",
     "djb200_tabular_create", "djb200_tabular_anisotropic_create", "djb200_tabular_destroy", "djb200_tabular_eval", "djb200_tabular_evalp", "djb200_tabular_pdf",
@@ -58,8 +60,18 @@ class Microfacet(C.Structure):
     _fields_ = [("ndf", C.c_int32), ("shadow", C.c_int32), ("fresnel", Fresnel)]
 
 
+class SgdData(C.Structure):
+    _fields_ = [("ch", (C.c_double * 11) * 3)]
+
+
+class AbcData(C.Structure):
+    _fields_ = [("kD", C.c_double * 3), ("A", C.c_double * 3), ("B", C.c_double), ("C", C.c_double),
+                ("ior", C.c_double)]
+
+
 class Source(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("merl", C.c_void_p), ("utia", C.c_void_p), ("microfacet", Microfacet)]
+    _fields_ = [("kind", C.c_int32), ("merl", C.c_void_p), ("utia", C.c_void_p), ("microfacet", Microfacet),
+                ("sgd", C.POINTER(SgdData)), ("abc", C.POINTER(AbcData))]
 
 
 class TabularFit(C.Structure):
@@ -90,6 +102,8 @@ def load():
     lib.djb200_version.restype = C.c_char_p
     lib.djb200_kernel_launch_count.restype = C.c_uint64
     lib.djb200_aniso_fit_size.restype = C.c_int64
+    lib.djb200_sgd_preset_name.restype = C.c_char_p
+    lib.djb200_abc_preset_name.restype = C.c_char_p
     _lib = lib
     return lib
 

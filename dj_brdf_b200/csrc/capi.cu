@@ -854,6 +854,31 @@ djb200_status djb200_nmap_to_leanmap(const uint8_t *nmap, int32_t w, int32_t h, 
 	return DJB200_OK;
 }
 
+djb200_status djb200_sgd_eval(const djb200_sgd_data *material, const float *wi, const float *wo, int64_t n,
+                              float *out_rgb, int mem, void *stream)
+{
+	if (!material) return fail(DJB200_ERR_INVALID_ARGUMENT, "material is NULL");
+	const djb200_sgd_data m = *material;
+	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_rgb, 12}}, mem, stream,
+		[&m](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_analytic_eval(DJB200_SOURCE_SGD, &m.ch[0][0], 33, (const float *)i[0], (const float *)i[1], cn,
+			                            (float *)o[0], st);
+		});
+}
+
+djb200_status djb200_abc_eval(const djb200_abc_data *material, const float *wi, const float *wo, int64_t n,
+                              float *out_rgb, int mem, void *stream)
+{
+	if (!material) return fail(DJB200_ERR_INVALID_ARGUMENT, "material is NULL");
+	const double m[9] = {material->kD[0], material->kD[1], material->kD[2], material->A[0], material->A[1],
+	                     material->A[2], material->B, material->C, material->ior};
+	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_rgb, 12}}, mem, stream,
+		[&m](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_analytic_eval(DJB200_SOURCE_ABC, m, 9, (const float *)i[0], (const float *)i[1], cn,
+			                            (float *)o[0], st);
+		});
+}
+
 djb200_status djb200_lrep_to_params(const float *E, int64_t n, djb200_params *out, int mem, void *stream)
 {
 	return map_call(n, {{E, 20}}, {{out, 48}}, mem, stream,

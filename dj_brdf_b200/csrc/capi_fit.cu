@@ -90,6 +90,20 @@ djb200_status build_sources(const djb200_source *sources, int32_t n, std::vector
 				d.fr.npts = m.fresnel.n_points;
 			}
 		} break;
+		case DJB200_SOURCE_SGD:
+			if (!s.sgd) return fail(DJB200_ERR_INVALID_ARGUMENT, "source %d: sgd coefficients are NULL", k);
+			memcpy(d.coef, s.sgd->ch, sizeof(double) * 33);
+			break;
+		case DJB200_SOURCE_ABC:
+			if (!s.abc) return fail(DJB200_ERR_INVALID_ARGUMENT, "source %d: abc coefficients are NULL", k);
+			for (int c = 0; c < 3; ++c) {
+				d.coef[c] = s.abc->kD[c];
+				d.coef[3 + c] = s.abc->A[c];
+			}
+			d.coef[6] = s.abc->B;
+			d.coef[7] = s.abc->C;
+			d.coef[8] = s.abc->ior;
+			break;
 		default: return fail(DJB200_ERR_INVALID_ARGUMENT, "source %d: unknown kind %d", k, s.kind);
 		}
 		out[k] = d;

@@ -626,6 +626,69 @@ DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
 }
 
 
+// ---- SGD / ABC analytic BRDFs, dj_brdf.h:3416-3499, 3608-3668 -----------------------------------------
+// Coefficients stay doubles (they are doubles in the reference's tables); the per-channel helpers run in double and
+// their results are narrowed where the reference's vec3::from_raw narrows them.
+// m: djb200_sgd_data.ch, i.e. [3][11] = rhoD rhoS alpha p f0 f1 kap lambda c k theta0 per channel
+DJB_DEV double sgd_g1_ch(double acos_kz, const double *m) // sgd__g1, :3415-3422
+{
+	double t1 = acos_kz - m[10];
+	t1 = 0.0 > t1 ? 0.0 : t1;
+	double t3 = 1.0 + m[7] * (1.0 - exp(m[8] * pow(t1, m[9])));
+	t3 = 0.0 > t3 ? 0.0 : t3;
+	return 1.0 < t3 ? 1.0 : t3;
+}
+DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o) // sgd::eval, :3454-3469
+{
+	if (!(i.z > 0.0f && o.z > 0.0f)) return mk(0.f, 0.f, 0.f);
+	const V3 h = normalize(i + o);
+	FresnelDev fr;
+	fr.pts = nullptr;
+	fr.npts = 0;
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		fr.v[c] = (float)m[11 * c + 4];
+		fr.v[3 + c] = (float)m[11 * c + 5];
+	}
+	const V3 Fr = fresnel_eval<FK_SGD>(fr, sat_ref(dot(i, h)));
+	const double ai = acos((double)i.z), ao = acos((double)o.z);
+	const double ch = (double)h.z, c2 = ch * ch, t2 = (1.0 - c2) / c2;
+	const double inv_pi = 1.0 / DJB_PI;
+	float fdg[3], ks[3], kd[3];
+	const float f3[3] = {Fr.x, Fr.y, Fr.z};
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		const double *mc = m + 11 * c;
+		const float g1i = (float)sgd_g1_ch(ai, mc), g1o = (float)sgd_g1_ch(ao, mc);
+		const double ax = mc[2] + t2 / mc[2];
+		const float nd = (float)((mc[6] * exp(-ax) * inv_pi) / (pow(ax, mc[3]) * c2 * c2)); // sgd__ndf, :3424-3432
+		fdg[c] = (f3[c] * nd) * (g1i * g1o);
+		kd[c] = (float)mc[0];
+		ks[c] = (float)mc[1];
+	}
+	const float r1 = rcp_via_double(i.z * o.z), r2 = rcp_via_double((float)DJB_PI);
+	return mk(r2 * (kd[0] + r1 * (ks[0] * fdg[0])), r2 * (kd[1] + r1 * (ks[1] * fdg[1])), r2 * (kd[2] + r1 * (ks[2] * fdg[2])));
+}
+// m: kD[3] A[3] B C ior (djb200_abc_data)
+DJB_DEV V3 abc_eval1(const double *__restrict__ m, V3 i, V3 o) // abc::eval, :3633-3647
+{
+	if (!(i.z > 0.0f && o.z > 0.0f)) return mk(0.f, 0.f, 0.f);
+	const V3 h = normalize(i + o);
+	const float Fc = unpolarized_channel(sat_ref(dot(i, h)), (float)m[8]);
+	const float g1_i = fmin_ref(1.0f, 2.0f * (h.z * i.z / dot(h, i))); // abc::gaf, :3649-3655
+	const float g1_o = fmin_ref(1.0f, 2.0f * (h.z * o.z / dot(h, o)));
+	const float G = fmin_ref(g1_i, g1_o);
+	const double den = pow(1.0 + m[6] * (1.0 - (double)h.z), m[7]); // abc__ndf, :3608-3613
+	const float r1 = rcp_via_double((float)DJB_PI), r2 = rcp_via_double((float)(DJB_PI * (double)i.z * (double)o.z));
+	float out[3];
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		const float nd = (float)(m[3 + c] / den);
+		out[c] = r1 * (float)m[c] + r2 * ((Fc * nd) * G);
+	}
+	return mk(out[0], out[1], out[2]);
+}
+
 // merl::eval on the uploaded cells (scaled float4 per cell), dj_brdf.h:987-1024
 DJB_DEV V3 merl_eval1(const float4 *__restrict__ cells, V3 i, V3 o)
 {

@@ -14,6 +14,7 @@ struct FitSourceDev {
 	const float *utia;    // normalised float table
 	int ndf, shadow, fresnel_kind;
 	FresnelDev fr;        // fr.pts: device pointer
+	double coef[33];      // SGD: djb200_sgd_data.ch flattened; ABC: djb200_abc_data (9 values)
 };
 
 DJB_DEV Params standard_params()
@@ -46,6 +47,8 @@ DJB_DEV V3 source_eval(const FitSourceDev &s, V3 i, V3 o)
 {
 	if (s.kind == DJB200_SOURCE_MERL) return merl_eval1(s.merl, i, o);
 	if (s.kind == DJB200_SOURCE_UTIA) return utia_eval1(s.utia, i, o);
+	if (s.kind == DJB200_SOURCE_SGD) return sgd_eval1(s.coef, i, o);
+	if (s.kind == DJB200_SOURCE_ABC) return abc_eval1(s.coef, i, o);
 	const Params p = standard_params();
 	if (s.ndf == NDF_GGX) return mf_eval_rt<NDF_GGX>(p, s.fresnel_kind, s.fr, s.shadow != 0, i, o);
 	return mf_eval_rt<NDF_BECKMANN>(p, s.fresnel_kind, s.fr, s.shadow != 0, i, o);

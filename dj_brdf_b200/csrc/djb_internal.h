@@ -74,6 +74,10 @@ cudaError_t launch_params_to_lrep(const void *params, int64_t n, float *E, cudaS
 cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int64_t npix, float bias,
                                      void *out_params, cudaStream_t st);
 
+// djb::sgd / djb::abc (kernels_analytic.cu); kind = DJB200_SOURCE_SGD / _ABC, coef = host pointer to the material's doubles
+cudaError_t launch_analytic_eval(int kind, const double *coef, int n_coef, const float *wi, const float *wo, int64_t n,
+                                 float *out, cudaStream_t st);
+
 // fits (kernels_fit.cu)
 struct FitSourceDev;
 size_t fit_tabular_smem_bytes(int res);

@@ -180,6 +180,28 @@ DJB200_API djb200_status djb200_utia_destroy(djb200_utia *u);
 DJB200_API djb200_status djb200_utia_eval(const djb200_utia *u, const float *wi, const float *wo, int64_t n,
                                           float *out_rgb, int mem, void *stream);
 
+/* ---- SGD and ABC analytic BRDFs (djb::sgd, djb::abc; dj_brdf.h:481-535, 3416-3499, 3608-3668) ------ *
+ * One material = a block of double coefficients (the reference keeps them in static tables of 100 MERL fits each,
+ * dj_brdf.h:3312-3413, 3505-3606, and looks them up by name in the constructor, :3436-3451, :3617-3631). */
+enum { /* columns of djb200_sgd_data.ch[c]: the fields of sgd::data (dj_brdf.h:482-497) for colour channel c */
+	DJB200_SGD_RHO_D = 0, DJB200_SGD_RHO_S, DJB200_SGD_ALPHA, DJB200_SGD_P, DJB200_SGD_F0, DJB200_SGD_F1,
+	DJB200_SGD_KAP, DJB200_SGD_LAMBDA, DJB200_SGD_C, DJB200_SGD_K, DJB200_SGD_THETA0, DJB200_SGD_NCOEF
+};
+typedef struct djb200_sgd_data { double ch[3][DJB200_SGD_NCOEF]; } djb200_sgd_data;
+typedef struct djb200_abc_data { double kD[3], A[3], B, C, ior; } djb200_abc_data; /* abc::data, dj_brdf.h:515-522 */
+/* name lookup of the constructors; an unknown name fails with DJB200_ERR_INVALID_ARGUMENT and the reference's message
+ * ("djb_error: No SGD parameters for ...", dj_brdf.h:3449).  SGD materials answer to two names (name, otherName). */
+DJB200_API djb200_status djb200_sgd_preset(const char *name, djb200_sgd_data *out);
+DJB200_API djb200_status djb200_abc_preset(const char *name, djb200_abc_data *out);
+DJB200_API int32_t djb200_preset_count(void);                    /* 100 */
+DJB200_API const char *djb200_sgd_preset_name(int32_t index);    /* NULL when out of range */
+DJB200_API const char *djb200_abc_preset_name(int32_t index);
+/* sgd::eval, dj_brdf.h:3454-3469; abc::eval, dj_brdf.h:3633-3647 (f_r; f_r cos is the base class's eval * i.z, :803) */
+DJB200_API djb200_status djb200_sgd_eval(const djb200_sgd_data *material, const float *wi, const float *wo, int64_t n,
+                                         float *out_rgb, int mem, void *stream);
+DJB200_API djb200_status djb200_abc_eval(const djb200_abc_data *material, const float *wi, const float *wo, int64_t n,
+                                         float *out_rgb, int mem, void *stream);
+
 /* ---- LEAN / LEADR ------------------------------------------------------------------------ */
 /* nmap2leanmap, utils/nmap2leanmap.cpp:18-54 (bias = 0) and nmap2leanmap_biased.cpp:23-63
  * (bias = 25).  nmap: planar uint8 [3][h][w]; lean1/lean2: planar float [4][h][w] (CImg layout). */
@@ -202,7 +224,9 @@ DJB200_API djb200_status djb200_leanmap_to_params(const float *lean1, const floa
 typedef enum djb200_source_kind {
 	DJB200_SOURCE_MERL = 0,
 	DJB200_SOURCE_UTIA = 1,
-	DJB200_SOURCE_MICROFACET = 2
+	DJB200_SOURCE_MICROFACET = 2,
+	DJB200_SOURCE_SGD = 3, /* what mitsuba/dj_sgd.cpp:29-30 fits */
+	DJB200_SOURCE_ABC = 4  /* mitsuba/dj_abc.cpp:30-32 */
 } djb200_source_kind;
 
 typedef struct djb200_source {
@@ -210,6 +234,8 @@ typedef struct djb200_source {
 	const djb200_merl *merl;
 	const djb200_utia *utia;
 	djb200_microfacet microfacet; /* evaluated with params::standard(), as the reference's NULL user_param */
+	const djb200_sgd_data *sgd;   /* host pointers, copied by the call */
+	const djb200_abc_data *abc;
 } djb200_source;
 
 /* Result of djb::tabular::tabular + fit_*_parameters for one material (dj_brdf.h:2215-2236,

@@ -539,6 +539,60 @@ public:
 	const djb200_utia *handle() const { return m_h; }
 };
 
+// dj_brdf.h:481-511: shifted gamma distribution BRDF of a MERL material (coefficients looked up by name)
+class sgd : public brdf {
+	djb200_sgd_data m_data;
+	fresnel::impl *m_fresnel;
+public:
+	explicit sgd(const char *name) : m_fresnel(NULL)
+	{
+		detail::check(djb200_sgd_preset(name, &m_data)); // throws "djb_error: No SGD parameters for <name>" like :3449
+		m_fresnel = new fresnel::sgd(
+			vec3((float_t)m_data.ch[0][DJB200_SGD_F0], (float_t)m_data.ch[1][DJB200_SGD_F0], (float_t)m_data.ch[2][DJB200_SGD_F0]),
+			vec3((float_t)m_data.ch[0][DJB200_SGD_F1], (float_t)m_data.ch[1][DJB200_SGD_F1], (float_t)m_data.ch[2][DJB200_SGD_F1]));
+	}
+	~sgd() { delete m_fresnel; }
+	vec3 eval(const vec3 &i, const vec3 &o, const void * = NULL) const
+	{
+		vec3 r;
+		eval_batch(&i, &o, 1, &r);
+		return r;
+	}
+	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void * = NULL, memory_space where = host,
+	                void *stream = NULL) const
+	{
+		detail::check(djb200_sgd_eval(&m_data, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+	}
+	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
+	const djb200_sgd_data *data() const { return &m_data; }
+};
+
+// dj_brdf.h:514-535: ABC distribution BRDF of a MERL material
+class abc : public brdf {
+	djb200_abc_data m_data;
+	fresnel::impl *m_fresnel;
+public:
+	explicit abc(const char *name) : m_fresnel(NULL)
+	{
+		detail::check(djb200_abc_preset(name, &m_data));
+		m_fresnel = new fresnel::unpolarized(vec3((float_t)m_data.ior));
+	}
+	~abc() { delete m_fresnel; }
+	vec3 eval(const vec3 &i, const vec3 &o, const void * = NULL) const
+	{
+		vec3 r;
+		eval_batch(&i, &o, 1, &r);
+		return r;
+	}
+	void eval_batch(const vec3 *i, const vec3 *o, size_t n, vec3 *out, const void * = NULL, memory_space where = host,
+	                void *stream = NULL) const
+	{
+		detail::check(djb200_abc_eval(&m_data, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+	}
+	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
+	const djb200_abc_data *data() const { return &m_data; }
+};
+
 namespace detail {
 inline djb200_source describe_source(const brdf &b)
 {
@@ -550,7 +604,9 @@ inline djb200_source describe_source(const brdf &b)
 		s.kind = DJB200_SOURCE_MICROFACET;
 		s.microfacet = static_cast<const microfacet &>(b).describe();
 	}
-	else throw exc("djb_error: this BRDF type cannot be fitted on the device (merl, utia, ggx, beckmann can)");
+	else if (const sgd *g = dynamic_cast<const sgd *>(&b)) { s.kind = DJB200_SOURCE_SGD; s.sgd = g->data(); }
+	else if (const abc *a = dynamic_cast<const abc *>(&b)) { s.kind = DJB200_SOURCE_ABC; s.abc = a->data(); }
+	else throw exc("djb_error: this BRDF type cannot be fitted on the device (merl, utia, sgd, abc, ggx, beckmann can)");
 	return s;
 }
 } // namespace detail

@@ -91,7 +91,13 @@ class _OrcFresnel(C.Structure):
 
 class _OrcSource(C.Structure):
     _fields_ = [("kind", C.c_int), ("ndf", C.c_int), ("F", _OrcFresnel), ("shadow", C.c_int),
-                ("P", C.c_float * 12), ("table", C.c_void_p)]
+                ("P", C.c_float * 12), ("table", C.c_void_p), ("sgd", C.c_void_p), ("abc", C.c_void_p)]
+
+
+def sgd_field_major(coef_channel_major):
+    """[3, 11] channel-major coefficients (the product's djb200_sgd_data) -> the 33 doubles of orc_sgd (field-major,
+    the order of the reference's sgd::data, dj_brdf.h:482-497)."""
+    return np.ascontiguousarray(np.asarray(coef_channel_major, np.float64).reshape(3, 11).T).reshape(-1)
 
 
 class Source:
@@ -112,6 +118,19 @@ class Source:
     @staticmethod
     def utia(raw_table):
         return Source("utia", table=np.ascontiguousarray(raw_table, dtype=np.float64).reshape(-1))
+
+    @staticmethod
+    def sgd(name, coef_channel_major):
+        """djb::sgd(name): the reference looks the name up itself, the port gets the 33 coefficients."""
+        s = Source("sgd", table=sgd_field_major(coef_channel_major))
+        s.name = name
+        return s
+
+    @staticmethod
+    def abc(name, coef9):
+        s = Source("abc", table=np.ascontiguousarray(coef9, dtype=np.float64).reshape(9))
+        s.name = name
+        return s
 
 
 def write_merl_file(path, table):
@@ -270,9 +289,29 @@ class PortOracle:
             self.lib.orc_utia_normalize(C.c_void_p(t.ctypes.data))
             keep.append(t)
             s.kind, s.table = 2, t.ctypes.data
+        elif src.kind == "sgd":
+            s.kind, s.sgd = 3, src.table.ctypes.data
+        elif src.kind == "abc":
+            s.kind, s.abc = 4, src.table.ctypes.data
         else:
             raise ValueError(src.kind)
         return s, keep
+
+    def sgd_eval(self, coef_channel_major, wi, wo, nthreads=1):
+        m = sgd_field_major(coef_channel_major)
+        wi, wo = _f32(wi), _f32(wo)
+        out = np.zeros((len(wi), 3), np.float32)
+        self.lib.orc_sgd_eval(C.c_void_p(m.ctypes.data), c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data), i64(len(wi)),
+                              c_f32p(out.ctypes.data), C.c_int(nthreads))
+        return out
+
+    def abc_eval(self, coef9, wi, wo, nthreads=1):
+        m = np.ascontiguousarray(coef9, dtype=np.float64).reshape(9)
+        wi, wo = _f32(wi), _f32(wo)
+        out = np.zeros((len(wi), 3), np.float32)
+        self.lib.orc_abc_eval(C.c_void_p(m.ctypes.data), c_f32p(wi.ctypes.data), c_f32p(wo.ctypes.data), i64(len(wi)),
+                              c_f32p(out.ctypes.data), C.c_int(nthreads))
+        return out
 
     def fit_tabular(self, src, res=90, shadow=True, iterations=4):
         s, keep = self._source(src)
@@ -502,7 +541,28 @@ class RefOracle:
             return self.merl_from_table(src.table)
         if src.kind == "utia":
             return self.utia_from_table(src.table)
+        if src.kind in ("sgd", "abc"):
+            return self.analytic(src.kind, src.name)
         raise ValueError(src.kind)
+
+    def analytic(self, kind, name):
+        """djb::sgd(name) / djb::abc(name); None when the reference throws (unknown material)."""
+        h = (self.lib.ref_sgd_create if kind == "sgd" else self.lib.ref_abc_create)(str(name).encode())
+        return C.c_void_p(h) if h else None
+
+    def sgd_eval(self, name, wi, wo, nthreads=1):
+        h = self.analytic("sgd", name)
+        try:
+            return self.brdf_eval(h, None, wi, wo, nthreads)
+        finally:
+            self.destroy(h)
+
+    def abc_eval(self, name, wi, wo, nthreads=1):
+        h = self.analytic("abc", name)
+        try:
+            return self.brdf_eval(h, None, wi, wo, nthreads)
+        finally:
+            self.destroy(h)
 
     def fit_tabular(self, src, res=90, shadow=True, iterations=4):
         assert iterations == 4, "the reference hard-codes 4 power iterations (dj_brdf.h:2518)"

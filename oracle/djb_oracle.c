@@ -894,6 +894,82 @@ void orc__utia_eval1(const double *tab, const float *wi, const float *wo, float 
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * SGD and ABC analytic BRDFs, :3416-3499 and :3608-3668.  Coefficients are doubles (the reference's static tables);
+ * the per-channel helper functions run in double and their results are narrowed by vec3::from_raw. */
+static v3 sgd_eval1(const orc_sgd *m, v3 i, v3 o) /* :3454-3469 */
+{
+	if (!(D(i.z) > 0.0 && D(o.z) > 0.0)) return v3_make(0, 0, 0);
+	v3 h = v3_normalize(v3_add(i, o));
+	v3 Ks = v3_make(F(m->rhoS[0]), F(m->rhoS[1]), F(m->rhoS[2]));
+	v3 Kd = v3_make(F(m->rhoD[0]), F(m->rhoD[1]), F(m->rhoD[2]));
+	orc_fresnel fr;
+	fr.kind = ORC_F_SGD; /* fresnel::sgd(from_raw(f0), from_raw(f1)), :3443-3444 */
+	for (int c = 0; c < 3; ++c) { fr.v[c] = F(m->f0[c]); fr.v[3 + c] = F(m->f1[c]); }
+	fr.pts = NULL; fr.npts = 0;
+	v3 Fr = fresnel_eval(&fr, f_sat(v3_dot(i, h)));
+	float g1i[3], g1o[3], nd[3];
+	for (int c = 0; c < 3; ++c) {
+		/* sgd__g1, :3415-3422 */
+		double ti = acos(D(i.z)) - m->theta0[c], to = acos(D(o.z)) - m->theta0[c];
+		ti = 0.0 > ti ? 0.0 : ti;
+		to = 0.0 > to ? 0.0 : to;
+		double vi = 1.0 + m->lambda[c] * (1.0 - exp(m->c[c] * pow(ti, m->k[c])));
+		double vo = 1.0 + m->lambda[c] * (1.0 - exp(m->c[c] * pow(to, m->k[c])));
+		vi = 0.0 > vi ? 0.0 : vi; vi = 1.0 < vi ? 1.0 : vi;
+		vo = 0.0 > vo ? 0.0 : vo; vo = 1.0 < vo ? 1.0 : vo;
+		g1i[c] = F(vi);
+		g1o[c] = F(vo);
+		/* sgd__ndf, :3424-3432 */
+		const double inv_pi = 1.0 / ORC_PI;
+		double ch = D(h.z), c2 = ch * ch, t2 = (1.0 - c2) / c2, ax = m->alpha[c] + t2 / m->alpha[c];
+		nd[c] = F((m->kap[c] * exp(-ax) * inv_pi) / (pow(ax, m->p[c]) * c2 * c2));
+	}
+	v3 G = v3_make(g1i[0] * g1o[0], g1i[1] * g1o[1], g1i[2] * g1o[2]);
+	v3 Dn = v3_make(nd[0], nd[1], nd[2]);
+	v3 FDG = v3_make((Fr.x * Dn.x) * G.x, (Fr.y * Dn.y) * G.y, (Fr.z * Dn.z) * G.z);
+	v3 spec = v3_div(v3_make(Ks.x * FDG.x, Ks.y * FDG.y, Ks.z * FDG.z), i.z * o.z);
+	return v3_div(v3_add(Kd, spec), F(ORC_PI));
+}
+
+static v3 abc_eval1(const orc_abc *m, v3 i, v3 o) /* :3633-3647 */
+{
+	if (!(D(i.z) > 0.0 && D(o.z) > 0.0)) return v3_make(0, 0, 0);
+	v3 h = v3_normalize(v3_add(i, o));
+	v3 Kd = v3_make(F(m->kD[0]), F(m->kD[1]), F(m->kD[2]));
+	float ior = F(m->ior); /* fresnel::unpolarized(vec3(ior)), :3623 */
+	float Fc = unpolarized_channel(f_sat(v3_dot(i, h)), ior);
+	/* abc::gaf, :3649-3655 */
+	float g1_i = f_min(1.0f, 2.0f * (h.z * i.z / v3_dot(h, i)));
+	float g1_o = f_min(1.0f, 2.0f * (h.z * o.z / v3_dot(h, o)));
+	float G = f_min(g1_i, g1_o);
+	float nd[3];
+	for (int c = 0; c < 3; ++c) /* abc__ndf, :3608-3613 */
+		nd[c] = F(m->A[c] / pow(1.0 + m->B * (1.0 - D(h.z)), m->C));
+	v3 FDG = v3_make((Fc * nd[0]) * G, (Fc * nd[1]) * G, (Fc * nd[2]) * G);
+	float den = F(ORC_PI * D(i.z) * D(o.z));
+	return v3_add(v3_div(Kd, F(ORC_PI)), v3_div(FDG, den));
+}
+
+typedef struct { const orc_sgd *sgd; const orc_abc *abc; const float *wi, *wo; float *out; } analytic_ctx;
+static void analytic_range(void *vctx, int64_t s, int64_t e)
+{
+	analytic_ctx *c = (analytic_ctx *)vctx;
+	for (int64_t k = s; k < e; ++k)
+		v3_st(c->out, k, c->sgd ? sgd_eval1(c->sgd, v3_ld(c->wi, k), v3_ld(c->wo, k))
+		                        : abc_eval1(c->abc, v3_ld(c->wi, k), v3_ld(c->wo, k)));
+}
+ORC_API void orc_sgd_eval(const orc_sgd *m, const float *wi, const float *wo, int64_t n, float *out3, int nthreads)
+{
+	analytic_ctx c = {m, NULL, wi, wo, out3};
+	orc_parallel_ranges(n, nthreads, analytic_range, &c);
+}
+ORC_API void orc_abc_eval(const orc_abc *m, const float *wi, const float *wo, int64_t n, float *out3, int nthreads)
+{
+	analytic_ctx c = {NULL, m, wi, wo, out3};
+	orc_parallel_ranges(n, nthreads, analytic_range, &c);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * LEAN */
 ORC_API void orc_lrep_to_params(const float *E5, int64_t n, orc_params *out) /* :1976-1990 */
 {

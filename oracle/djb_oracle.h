@@ -73,6 +73,15 @@ void orc_utia_normalize(double *table);
 void orc_utia_eval(const double *table, const float *wi, const float *wo, int64_t n, float *out3,
                    int nthreads);
 
+/* djb::sgd / djb::abc (dj_brdf.h:481-535, 3416-3499, 3608-3668): one material's coefficients, field-major as in the
+ * reference's static tables */
+typedef struct orc_sgd {
+	double rhoD[3], rhoS[3], alpha[3], p[3], f0[3], f1[3], kap[3], lambda[3], c[3], k[3], theta0[3];
+} orc_sgd;
+typedef struct orc_abc { double kD[3], A[3], B, C, ior; } orc_abc;
+void orc_sgd_eval(const orc_sgd *m, const float *wi, const float *wo, int64_t n, float *out3, int nthreads);
+void orc_abc_eval(const orc_abc *m, const float *wi, const float *wo, int64_t n, float *out3, int nthreads);
+
 /* LEAN (dj_brdf.h:1965-1990; utils/nmap2leanmap.cpp:18-54; nmap2leanmap_biased.cpp:23-63) */
 void orc_lrep_to_params(const float *E5, int64_t n, orc_params *out);
 void orc_params_to_lrep(const orc_params *p, int64_t n, float *E5);
@@ -81,7 +90,7 @@ void orc_nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float base_r
 
 /* ---- fits: djb_oracle_fit.c ------------------------------------------------------------- */
 /* generic BRDF handle used as the fit input */
-enum { ORC_SRC_MICROFACET = 0, ORC_SRC_MERL = 1, ORC_SRC_UTIA = 2 };
+enum { ORC_SRC_MICROFACET = 0, ORC_SRC_MERL = 1, ORC_SRC_UTIA = 2, ORC_SRC_SGD = 3, ORC_SRC_ABC = 4 };
 typedef struct orc_source {
 	int kind;
 	/* microfacet */
@@ -91,6 +100,9 @@ typedef struct orc_source {
 	orc_params P; /* user_param is NULL in the reference's fit calls => P must be standard() */
 	/* merl / utia */
 	const double *table;
+	/* sgd / abc */
+	const orc_sgd *sgd;
+	const orc_abc *abc;
 } orc_source;
 void orc_source_eval(const orc_source *src, const float *wi, const float *wo, float *out3);
 

@@ -17,6 +17,8 @@ static v3 source_eval(const orc_source *s, v3 i, v3 o)
 	switch (s->kind) {
 	case ORC_SRC_MERL: return merl_eval1(s->table, i, o);
 	case ORC_SRC_UTIA: return utia_eval1(s->table, i, o);
+	case ORC_SRC_SGD: return sgd_eval1(s->sgd, i, o);
+	case ORC_SRC_ABC: return abc_eval1(s->abc, i, o);
 	default: return mf_eval(s->ndf, &s->F, s->shadow, &s->P, i, o);
 	}
 }

@@ -26,8 +26,33 @@ sha, random_merl_table, random_utia_table, smooth_merl_table = (cases.sha, cases
                                                                  cases.random_utia_table, cases.smooth_merl_table)
 
 
+def extra(ref):
+    """Golden vectors of the section-8f rows added after the first two files (kept in a file of their own so that
+    adding a row never rewrites the earlier vectors): djb::sgd / djb::abc."""
+    e = {}
+    wi, wo, _ = cases.pairs(96, stream=77)
+    wi[:4, 2] = [0.0, -0.1, 1.0, 1e-4]
+    e["analytic/wi"], e["analytic/wo"] = wi, wo
+    import dj_brdf_b200 as djb  # host-only calls: the preset names (the coefficient tables are what is being pinned)
+    e["sgd/names"] = np.array(djb.sgd.names())
+    e["abc/names"] = np.array(djb.abc.names())
+    e["sgd/eval"] = np.stack([ref.sgd_eval(n, wi, wo) for n in djb.sgd.names()])
+    e["abc/eval"] = np.stack([ref.abc_eval(n, wi, wo) for n in djb.abc.names()])
+    for kind, name in (("sgd", "gold-metallic-paint"), ("abc", "blue-metallic-paint")):
+        m = getattr(djb, kind)(name)
+        r = ref.fit_tabular(getattr(api.Source, kind)(name, m.coefficients()), 90)
+        for k, v in r.items():
+            e[f"fit/{kind}/{name}/{k}"] = v
+    np.savez_compressed(OUT / "extra_golden.npz", **e)
+    print("extra_golden.npz", (OUT / "extra_golden.npz").stat().st_size, "bytes")
+
+
 def main():
     ref = api.RefOracle()
+    if "--extra-only" in sys.argv:
+        extra(ref)
+        return
+    extra(ref)
     wi, wo, u = cases.pairs(N)
     ewi, ewo, eu = cases.edge_pairs()
     wi = np.concatenate([wi, ewi]); wo = np.concatenate([wo, ewo]); u = np.concatenate([u, eu])

@@ -129,3 +129,29 @@ def test_survey_spot_values(port):
     u = np.array([[0.3, 0.7]], np.float32)
     assert np.abs(port.sample(api.NDF_GGX, P, u, o)[0] - [0.282283455, -0.468485653, 0.837159991]).max() < 1e-6
     assert np.abs(port.sample(api.NDF_BECKMANN, P, u, o)[0] - [0.230195954, -0.343669266, 0.910440087]).max() < 1e-6
+
+
+@pytest.fixture(scope="module")
+def x():
+    return np.load(GOLD / "extra_golden.npz")
+
+
+def test_sgd_abc_presets(port, x):
+    """djb::sgd / djb::abc for all 100 materials: the product's coefficient tables (host-only preset lookup) through the
+    port's eval must reproduce the reference's output bit for bit."""
+    import dj_brdf_b200 as djb
+    wi, wo = x["analytic/wi"], x["analytic/wo"]
+    assert list(x["sgd/names"]) == djb.sgd.names() and list(x["abc/names"]) == djb.abc.names()
+    for k, name in enumerate(djb.sgd.names()):
+        assert bits_equal(port.sgd_eval(djb.sgd(name).coefficients(), wi, wo), x["sgd/eval"][k]).all(), name
+    for k, name in enumerate(djb.abc.names()):
+        assert bits_equal(port.abc_eval(djb.abc(name).coefficients(), wi, wo), x["abc/eval"][k]).all(), name
+
+
+@pytest.mark.parametrize("kind,name", [("sgd", "gold-metallic-paint"), ("abc", "blue-metallic-paint")])
+def test_fit_from_analytic_source(port, x, kind, name):
+    import dj_brdf_b200 as djb
+    m = getattr(djb, kind)(name)
+    p = port.fit_tabular(getattr(api.Source, kind)(name, m.coefficients()), 90)
+    for k, v in p.items():
+        assert bits_equal(v, x[f"fit/{kind}/{name}/{k}"]).all(), k

@@ -101,3 +101,34 @@ def test_tabular_anisotropic_brdf_bit_identical(port, ref):
             g = port.tabular_aniso_query(op, fit, 16, 20, wi, wo, P, nthreads=8)
             r = ref.tabular_aniso_query(op, src, 16, 20, wi, wo, P, nthreads=8)
             assert bits_equal(g, r).all(), op
+
+
+def test_sgd_abc_all_presets_bit_identical(port, ref):
+    """djb::sgd / djb::abc: every one of the 100 materials, the port fed with the product's coefficient tables
+    (djb200_sgd_preset / djb200_abc_preset, host-only calls) against the reference's own name lookup + eval.  Pins the
+    generated tables (dj_brdf_b200/csrc/djb_presets.inc) and the restatement at once."""
+    import dj_brdf_b200 as djb
+    wi, wo, _ = cases.pairs(2000, stream=77)
+    wi[:8, 2] = [0.0, -0.1, 1.0, 1e-4, 0.5, 0.5, 0.5, 0.5]  # horizon / below-horizon / normal incidence
+    for name in djb.sgd.names():
+        assert bits_equal(port.sgd_eval(djb.sgd(name).coefficients(), wi, wo), ref.sgd_eval(name, wi, wo)).all(), name
+    for name in djb.abc.names():
+        assert bits_equal(port.abc_eval(djb.abc(name).coefficients(), wi, wo), ref.abc_eval(name, wi, wo)).all(), name
+    # the second names of the SGD table resolve to the same rows (dj_brdf.h:3440-3441)
+    for other, first in (("fabric-beige", "beige-fabric"), ("paint-yellow", "yellow-paint")):
+        assert np.array_equal(djb.sgd(other).coefficients(), djb.sgd(first).coefficients())
+        assert bits_equal(ref.sgd_eval(other, wi, wo), ref.sgd_eval(first, wi, wo)).all()
+    assert ref.analytic("sgd", "no-such-material") is None and ref.analytic("abc", "no-such-material") is None
+    with pytest.raises(djb.DjbError):
+        djb.abc("no-such-material")
+
+
+@pytest.mark.parametrize("kind,name", [("sgd", "gold-metallic-paint"), ("abc", "blue-metallic-paint")])
+def test_fit_from_analytic_source(port, ref, kind, name):
+    """what mitsuba/dj_sgd.cpp:29-30 and dj_abc.cpp:30-32 do: tabular(sgd / abc, 90)"""
+    import dj_brdf_b200 as djb
+    m = getattr(djb, kind)(name)
+    src = getattr(api.Source, kind)(name, m.coefficients())
+    r, p = ref.fit_tabular(src, 90), port.fit_tabular(src, 90)
+    for k in r:
+        assert bits_equal(r[k], p[k]).all(), k
