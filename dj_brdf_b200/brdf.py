@@ -575,9 +575,9 @@ class tabular(microfacet):
 
 
 class tabular_anisotropic(microfacet):
-    """djb::tabular_anisotropic (dj_brdf.h:428-478): eval tables + parameter fits, and an evaluable BRDF
-    (``eval / evalp / pdf`` on the elevation x azimuth tables; its sampling tables are not built, so ``sample`` /
-    ``evalp_is`` raise DjbError UNSUPPORTED)."""
+    """djb::tabular_anisotropic (dj_brdf.h:428-478): eval tables + parameter fits, and an evaluable / samplable BRDF:
+    ``eval / evalp / pdf`` on the elevation x azimuth tables, ``sample / evalp_is`` by normal-map sampling through the
+    marginal / conditional quantile tables (built on the device when the handle is created, dj_brdf.h:2848-3103)."""
     _prefix = "djb200_tabular_"
 
     def __init__(self, source, elevation_res, azimuthal_res, shadow=True, iterations=4, _result=None):
@@ -639,6 +639,19 @@ class tabular_anisotropic(microfacet):
 
     def get_sigmav(self):
         return self.m_sigma, self.m_elevation_res, self.m_azimuthal_res
+
+    def sampling_tables(self):
+        """The tables behind pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 (dj_brdf.h:2766-2824) -> dict of float32 arrays
+        (+ n_qf1 / n_qf2: the entries the reference's inversion searches produce)."""
+        h, _ = self._first_arg()
+        er, ar = self.m_elevation_res, self.m_azimuthal_res
+        one = [np.zeros(ar, np.float32) for _ in range(3)]
+        two = [np.zeros(er * ar, np.float32) for _ in range(3)]
+        counts = (C.c_int32 * 2)()
+        check(capi.load().djb200_tabular_anisotropic_sampling_tables(
+            h, *[C.c_void_p(a.ctypes.data) for a in (one[0], one[1], one[2], two[0], two[1], two[2])], counts))
+        return dict(pdf1=one[0], cdf1=one[1], qf1=one[2], pdf2=two[0], cdf2=two[1], qf2=two[2], n_qf1=counts[0],
+                    n_qf2=counts[1])
 
     @staticmethod
     def fit_beckmann_parameters(tab):

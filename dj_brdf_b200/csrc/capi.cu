@@ -297,7 +297,7 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 	}
 	auto launch = [tab](const MfLaunch &X, cudaStream_t s) {
 		if (!tab) return launch_microfacet(X, s);
-		if (tab->azim_res > 0) return launch_tabular_aniso_query(tab->tables, tab->res, tab->azim_res, X, s);
+		if (tab->azim_res > 0) return launch_tabular_aniso_query(tab->tables, tab->res, tab->azim_res, tab->n_qf1, X, s);
 		return launch_tabular_query(tab->tables, tab->res, X, s);
 	};
 	if (!mf) return fail(DJB200_ERR_INVALID_ARGUMENT, "microfacet descriptor is NULL");
@@ -590,18 +590,39 @@ djb200_status djb200_tabular_anisotropic_create(const djb200_tabular_anisotropic
 	djb200_status rs = require_device();
 	if (rs != DJB200_OK) return rs;
 	const size_t tab = (size_t)fit->elev_res * fit->azim_res, er = (size_t)fit->elev_res;
+	if (fit->elev_res > 4096 || fit->azim_res > 4096) return fail(DJB200_ERR_UNSUPPORTED, "resolution too large");
 	std::vector<float> h(2 * tab + 3 * er);
 	memcpy(h.data(), fit->p22, 4 * tab);
 	memcpy(h.data() + tab, fit->sigma, 4 * tab);
 	memcpy(h.data() + 2 * tab, fit->fresnel, 12 * er);
 	float *d = nullptr;
-	CU(cudaMalloc(&d, 4 * h.size()));
+	CU(cudaMalloc(&d, 4 * aniso_table_floats(fit->elev_res, fit->azim_res)));
 	cudaError_t e = cudaMemcpy(d, h.data(), 4 * h.size(), cudaMemcpyHostToDevice);
-	if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "tabular upload"); }
+	// the marginal / conditional sampling tables are built on the device from the p22 block (dj_brdf.h:2266-2272)
+	int counts[2] = {0, 0};
+	if (e == cudaSuccess) e = build_aniso_sampling_tables(d, fit->elev_res, fit->azim_res, counts, 0);
+	if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "tabular_anisotropic upload / sampling tables"); }
 	djb200_tabular *t = new djb200_tabular;
 	t->tables = d; t->res = fit->elev_res; t->azim_res = fit->azim_res; t->shadow = shadow ? 1 : 0;
+	t->n_qf1 = counts[0]; t->n_qf2 = counts[1];
 	cudaGetDevice(&t->device);
 	*out = t;
+	return DJB200_OK;
+}
+
+djb200_status djb200_tabular_anisotropic_sampling_tables(const djb200_tabular *t, float *pdf1, float *cdf1, float *qf1,
+                                                         float *pdf2, float *cdf2, float *qf2, int32_t counts[2])
+{
+	if (!t) return fail(DJB200_ERR_INVALID_ARGUMENT, "tabular handle is NULL");
+	if (t->azim_res <= 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "not a tabular_anisotropic handle");
+	const int er = t->res, ar = t->azim_res;
+	const size_t T = (size_t)er * ar;
+	struct { float *dst; size_t off, n; } parts[6] = {
+		{pdf1, aniso_off_pdf1(er, ar), (size_t)ar}, {cdf1, aniso_off_cdf1(er, ar), (size_t)ar}, {qf1, aniso_off_qf1(er, ar), (size_t)ar},
+		{pdf2, aniso_off_pdf2(er, ar), T}, {cdf2, aniso_off_cdf2(er, ar), T}, {qf2, aniso_off_qf2(er, ar), T}};
+	for (auto &p : parts)
+		if (p.dst) CU(cudaMemcpy(p.dst, t->tables + p.off, 4 * p.n, cudaMemcpyDeviceToHost));
+	if (counts) { counts[0] = t->n_qf1; counts[1] = t->n_qf2; }
 	return DJB200_OK;
 }
 
@@ -636,7 +657,6 @@ djb200_status djb200_tabular_sample(const djb200_tabular *t, const djb200_params
                                     const float *u, const float *wo, int64_t n, float *out_wi, int mem, void *stream)
 {
 	DJB200_TAB_NULLCHECK;
-	if (t->azim_res > 0) return fail(DJB200_ERR_UNSUPPORTED, "sampling tables of tabular_anisotropic are not built (SURVEY 8f N2)");
 	return microfacet_call(OP_SAMPLE, nullptr, params, n_params, params_layout, u, wo, n, out_wi, nullptr, nullptr, mem, stream, t);
 }
 djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const djb200_params *params, int64_t n_params, int params_layout,
@@ -644,7 +664,6 @@ djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const djb200_para
                                       float *out_pdf, int mem, void *stream)
 {
 	DJB200_TAB_NULLCHECK;
-	if (t->azim_res > 0) return fail(DJB200_ERR_UNSUPPORTED, "sampling tables of tabular_anisotropic are not built (SURVEY 8f N2)");
 	if (!out_weight_rgb && !out_wi && !out_pdf) return fail(DJB200_ERR_INVALID_ARGUMENT, "all outputs are NULL");
 	return microfacet_call(OP_EVALP_IS, nullptr, params, n_params, params_layout, u, wo, n, out_weight_rgb, out_wi, out_pdf, mem,
 	                       stream, t);

@@ -11,9 +11,10 @@ struct djb200_merl {
 	int device;
 };
 struct djb200_tabular {
-	float *tables; // radial: p22[res] | sigma[res] | qf[res] | fresnel[res][3]; anisotropic: p22[er * ar] | sigma[er * ar] | fresnel[er][3]
+	float *tables; // radial: p22[res] | sigma[res] | qf[res] | fresnel[res][3]; anisotropic: see aniso_table_floats()
 	int res, shadow, device;
 	int azim_res; // 0: radial tables (djb::tabular); > 0: djb::tabular_anisotropic with res = elevation resolution
+	int n_qf1, n_qf2; // anisotropic: entries the quantile-table searches produced (dj_brdf.h:2904-2935, 3004-3037)
 };
 struct djb200_utia {
 	float *table; // utia::normalize()d samples cast to float
@@ -21,6 +22,16 @@ struct djb200_utia {
 };
 
 namespace djb200 {
+
+// device layout of a djb::tabular_anisotropic handle, T = er * ar floats per 2-D table:
+//   p22[T] | sigma[T] | fresnel[er][3] | qf1[ar] | qf2[T] | pdf1[ar] | cdf1[ar] | pdf2[T] | cdf2[T]
+__host__ __device__ inline size_t aniso_off_qf1(int er, int ar) { return 2 * (size_t)er * ar + 3 * (size_t)er; }
+__host__ __device__ inline size_t aniso_off_qf2(int er, int ar) { return aniso_off_qf1(er, ar) + ar; }
+__host__ __device__ inline size_t aniso_off_pdf1(int er, int ar) { return aniso_off_qf2(er, ar) + (size_t)er * ar; }
+__host__ __device__ inline size_t aniso_off_cdf1(int er, int ar) { return aniso_off_pdf1(er, ar) + ar; }
+__host__ __device__ inline size_t aniso_off_pdf2(int er, int ar) { return aniso_off_cdf1(er, ar) + ar; }
+__host__ __device__ inline size_t aniso_off_cdf2(int er, int ar) { return aniso_off_pdf2(er, ar) + (size_t)er * ar; }
+__host__ __device__ inline size_t aniso_table_floats(int er, int ar) { return aniso_off_cdf2(er, ar) + (size_t)er * ar; }
 
 // error plumbing of the C-ABI layer (capi.cu)
 djb200_status fail(djb200_status s, const char *fmt, ...);
@@ -53,7 +64,11 @@ cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st);
 // djb::tabular as a BRDF (kernels_tabular.cu); tables: device, p22[res] | sigma[res] | qf[res] | fresnel[res][3]
 cudaError_t launch_tabular_query(const float *tables, int res, const MfLaunch &L, cudaStream_t st);
 // djb::tabular_anisotropic as a BRDF (eval / evalp / pdf); tables: device, p22[er * ar] | sigma[er * ar] | fresnel[er][3]
-cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, const MfLaunch &L, cudaStream_t st);
+cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, int n_qf1, const MfLaunch &L,
+                                       cudaStream_t st);
+// builds qf1 | qf2 | pdf1 | cdf1 | pdf2 | cdf2 inside `tables` from its p22 block (dj_brdf.h:2848-3103); counts_host[2]
+// receives the fill counts of qf1 / qf2 (the call synchronises the stream)
+cudaError_t build_aniso_sampling_tables(float *tables, int elev_res, int azim_res, int counts_host[2], cudaStream_t st);
 
 // tables / frames / LEAN (kernels_tables.cu)
 cudaError_t launch_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d, cudaStream_t st);

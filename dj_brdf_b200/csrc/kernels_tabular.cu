@@ -27,6 +27,8 @@ template <class TAB>
 struct TabBrdfT {
 	TAB t;
 	const float *qf; // radial quantile table (isotropic only)
+	const float *qf1, *qf2; // azimuth / elevation quantile tables (anisotropic only)
+	int n_qf1;
 	FresnelDev fr;
 	bool shadow;
 };
@@ -69,8 +71,48 @@ DJB_DEV float tabq_pdf(const TB &B, const Params &p, V3 i, V3 o)
 	return 0.0f;
 }
 
-// microfacet::sample (dj_brdf.h:1669-1709) with radial::sample_vp22_std_nmap (:1806-1816)
-DJB_DEV V3 tabq_sample(const TabBrdf &B, const Params &p, float u1, float u2, V3 o)
+// spline::eval<float_t> with uwrap_repeat, dj_brdf.h:1183-1218
+DJB_DEV float spline_repeat_f(const float *pts, int n, float u)
+{
+	const float x = u * (float)n - u;
+	const float ip = truncf(x), frac = x - ip; // == (float)modf((double)x, &ip): exact in both precisions
+	int i1 = (int)ip, i2 = (int)ip + 1;
+	while (i1 >= n) i1 -= n;
+	while (i1 < 0) i1 += n;
+	while (i2 >= n) i2 -= n;
+	while (i2 < 0) i2 += n;
+	const float p1 = pts[i1], p2 = pts[i2];
+	return p1 + frac * (p2 - p1);
+}
+
+// standard slopes of a normal drawn from the tabulated distribution
+DJB_DEV void tabq_std_slopes(const TabBrdfT<TabIso> &B, float u1, float u2, float &txm, float &tym)
+{
+	// radial::sample_vp22_std_nmap, dj_brdf.h:1806-1816
+	float phi_h = (float)((double)u1 * DJB_PI * 2.0);
+	float q = spline_f(B.qf, B.t.n, u2);                        // tabular::qf_radial, :2172-2176
+	float r_h = (float)tan((double)(q * (float)DJB_PI / 2.0f));
+	double sp, cp;
+	sincos((double)phi_h, &sp, &cp);
+	txm = (float)((double)r_h * cp);
+	tym = (float)((double)r_h * sp);
+}
+DJB_DEV void tabq_std_slopes(const TabBrdfT<TabAniso> &B, float u1, float u2, float &txm, float &tym)
+{
+	// tabular_anisotropic::sample_vp22_std_nmap with qf1 / qf2, dj_brdf.h:2826-2837, 2780-2784, 2814-2824
+	const float phi = (float)((double)spline_f(B.qf1, B.n_qf1, u1) * 2.0 * DJB_PI);
+	const float uphi = (float)((double)phi / (2.0 * DJB_PI));
+	const float theta = (float)((double)spline2d_f(B.qf2, B.t.w, B.t.h, u2, uphi) * 0.5 * DJB_PI);
+	const float tan_theta = (float)tan((double)theta);
+	double sp, cp;
+	sincos((double)phi, &sp, &cp);
+	txm = (float)((double)(-tan_theta) * cp);
+	tym = (float)((double)(-tan_theta) * sp);
+}
+
+// microfacet::sample (dj_brdf.h:1669-1709) through sample_vp22_std_nmap
+template <class TB>
+DJB_DEV V3 tabq_sample(const TB &B, const Params &p, float u1, float u2, V3 o)
 {
 	u1 = sat_ref(u1) * 0.99998f + 0.00001f;
 	u2 = sat_ref(u2) * 0.99998f + 0.00001f;
@@ -79,12 +121,8 @@ DJB_DEV V3 tabq_sample(const TabBrdf &B, const Params &p, float u1, float u2, V3
 	float c = o.z - o.x * p.tx - o.y * p.ty;
 	V3 os = normalize(mk(a, b, c));
 	if (os.z > 0.0f) {
-		float phi_h = (float)((double)u1 * DJB_PI * 2.0);
-		float q = spline_f(B.qf, B.t.n, u2);                        // tabular::qf_radial, :2172-2176
-		float r_h = (float)tan((double)(q * (float)DJB_PI / 2.0f));
-		double sp, cp;
-		sincos((double)phi_h, &sp, &cp);
-		float txm = (float)((double)r_h * cp), tym = (float)((double)r_h * sp);
+		float txm, tym;
+		tabq_std_slopes(B, u1, u2, txm, tym);
 		float txh = p.ax * txm + p.tx;
 		float chol = p.rho * txm + p.srho * tym;
 		float tyh = p.ay * chol + p.ty;
@@ -96,7 +134,8 @@ DJB_DEV V3 tabq_sample(const TabBrdf &B, const Params &p, float u1, float u2, V3
 }
 
 // microfacet::evalp_is without Smith VNDF sampling, dj_brdf.h:1734-1765
-DJB_DEV V3 tabq_evalp_is(const TabBrdf &B, const Params &p, float u1, float u2, V3 o, V3 &i_out, float &pdf_out)
+template <class TB>
+DJB_DEV V3 tabq_evalp_is(const TB &B, const Params &p, float u1, float u2, V3 o, V3 &i_out, float &pdf_out)
 {
 	V3 i = tabq_sample(B, p, u1, u2, o);
 	V3 h = normalize(i + o);
@@ -195,7 +234,7 @@ static cudaError_t launch_tq(const TabQueryArgs &A, cudaStream_t st)
 // djb::tabular_anisotropic (dj_brdf.h:428-478) as an evaluable BRDF: eval / evalp / pdf on the elevation x azimuth
 // tables (2 x 32 KB at 90 x 90: read through the read-only cache, not staged)
 template <int OP, bool PERPAIR>
-__global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQueryArgs A, int azim_res)
+__global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQueryArgs A, int azim_res, int n_qf1)
 {
 	__shared__ Params s_params[PERPAIR ? 1 : TQ_MAX_SMEM_PARAMS];
 	if (!PERPAIR) {
@@ -209,15 +248,33 @@ __global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQuer
 	B.t.p22 = A.tables; B.t.sigma = A.tables + tab; B.t.w = A.res; B.t.h = azim_res;
 	B.qf = nullptr;
 	B.fr.pts = A.tables + 2 * tab; B.fr.npts = A.res;
+	B.qf1 = A.tables + aniso_off_qf1(A.res, azim_res); B.n_qf1 = n_qf1;
+	B.qf2 = A.tables + aniso_off_qf2(A.res, azim_res);
 	B.shadow = A.shadow != 0;
+	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
-		const V3 i = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
+		V3 i;
+		if (uses_u) {
+			const float2 u = reinterpret_cast<const float2 *>(A.a)[k];
+			i = mk(u.x, u.y, 0.f);
+		} else {
+			i = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]);
+		}
 		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
 		auto one = [&](const Params &p, long long slot) {
 			if (OP == OP_EVAL) tq_st3(A.out0, slot, scale(rcp_via_double(i.z), tabq_evalp(B, p, i, o)));
 			else if (OP == OP_EVALP) tq_st3(A.out0, slot, tabq_evalp(B, p, i, o));
-			else A.out0[slot] = tabq_pdf(B, p, i, o);
+			else if (OP == OP_PDF) A.out0[slot] = tabq_pdf(B, p, i, o);
+			else if (OP == OP_SAMPLE) tq_st3(A.out0, slot, tabq_sample(B, p, i.x, i.y, o));
+			else {
+				V3 iv;
+				float pdf;
+				V3 w = tabq_evalp_is(B, p, i.x, i.y, o, iv, pdf);
+				if (A.out0) tq_st3(A.out0, slot, w);
+				if (A.out1) tq_st3(A.out1, slot, iv);
+				if (A.out2) A.out2[slot] = pdf;
+			}
 		};
 		if (PERPAIR) {
 			const float4 *pp = reinterpret_cast<const float4 *>(A.params + k);
@@ -233,29 +290,242 @@ __global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQuer
 	}
 }
 
-// tables: device, p22[er * ar] | sigma[er * ar] | fresnel[er][3]
-cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, const MfLaunch &L, cudaStream_t st)
+// ---- tabular_anisotropic's sampling tables (dj_brdf.h:2848-3103) ----------------------------------------------------
+// A chain of eight small table passes, each depending on the previous one: marginal azimuth density (256-point elevation
+// quadrature per azimuth), its normalisation, running integral and inverse; conditional elevation density, its per-azimuth
+// normalisation, running integrals and inverses.  ~130 k table lookups in all: one CTA of 1024 threads walks the chain,
+// every phase computes its independent terms in parallel (global scratch) and then adds them in the reference's order --
+// float accumulation is not associative, so each ordered sum is done by a single thread (one per azimuth where the
+// sums are per azimuth).
+struct AnisoBuild {
+	float *tab;       // handle tables (layout: aniso_table_floats)
+	int er, ar;
+	double *terms;    // ar * 256
+	float *q;         // ar * 8 * (er - 1): running-integral lookups of the inversion searches (also 512 + 8 * ar for the 1-D passes)
+	float *rows;      // ar * er: unpacked qf2 rows
+	int *rowcnt;      // ar
+	int *counts;      // 2
+};
+
+DJB_DEV float ab_angle(int i, int n, double scale) { return (float)((double)((float)i / (float)n) * scale); }
+DJB_DEV float ab_lookup1(const float *t, int n, float phi) { return spline_repeat_f(t, n, (float)((double)phi * 0.5 / DJB_PI)); }
+DJB_DEV float ab_lookup2(const float *t, int w, int h, float theta, float phi, float beyond)
+{
+	if ((double)theta >= 0.5 * DJB_PI) return beyond;
+	return spline2d_f(t, w, h, (float)((double)theta * 2.0 / DJB_PI), (float)((double)phi * 0.5 / DJB_PI));
+}
+DJB_DEV double ab_term(float f, float theta) // (f * tan(theta)) / (cos_theta * cos_theta)
+{
+	const float c = (float)cos((double)theta);
+	return ((double)f * tan((double)theta)) / (double)(c * c);
+}
+
+__global__ void __launch_bounds__(1024) aniso_sampling_tables_kernel(AnisoBuild A)
+{
+	const int er = A.er, ar = A.ar, T = er * ar, tid = threadIdx.x, nt = blockDim.x;
+	const float *p22 = A.tab;
+	float *qf1 = A.tab + aniso_off_qf1(er, ar), *qf2 = A.tab + aniso_off_qf2(er, ar);
+	float *pdf1 = A.tab + aniso_off_pdf1(er, ar), *cdf1 = A.tab + aniso_off_cdf1(er, ar);
+	float *pdf2 = A.tab + aniso_off_pdf2(er, ar), *cdf2 = A.tab + aniso_off_cdf2(er, ar);
+	TabAniso tp; tp.p22 = p22; tp.sigma = nullptr; tp.w = er; tp.h = ar;
+	const double TWO_PI = 2.0 * DJB_PI, HALF_PI = 0.5 * DJB_PI;
+	__shared__ float s_k;
+	__shared__ int s_total;
+
+	for (int t = tid; t < ar; t += nt) { qf1[t] = 0.f; pdf1[t] = 0.f; cdf1[t] = 0.f; }
+	for (int t = tid; t < T; t += nt) { qf2[t] = 0.f; pdf2[t] = 0.f; cdf2[t] = 0.f; }
+	// compute_pdf1, :2848-2874
+	for (int t = tid; t < ar * 256; t += nt) {
+		const int i = t / 256, j = t % 256;
+		const float phi = ab_angle(i, ar, TWO_PI), theta = ab_angle(j, 256, HALF_PI);
+		A.terms[t] = ab_term(tp.p22_theta_phi(theta, phi), theta);
+	}
+	__syncthreads();
+	for (int i = tid; i < ar; i += nt) {
+		const float dtheta = (float)(HALF_PI / (double)256.0f);
+		float nint = 0.0f;
+		for (int j = 0; j < 256; ++j) nint = (float)((double)nint + A.terms[i * 256 + j]);
+		pdf1[i] = nint * dtheta;
+	}
+	__syncthreads();
+	// normalize_pdf1, :3029-3051
+	for (int t = tid; t < 512; t += nt) A.q[t] = ab_lookup1(pdf1, ar, ab_angle(t, 512, TWO_PI));
+	__syncthreads();
+	if (tid == 0) {
+		float nint = 0.0f;
+		for (int i = 0; i < 512; ++i) nint += A.q[i];
+		nint *= (float)(TWO_PI / (double)512.0f);
+		s_k = rcp_via_double(nint);
+	}
+	__syncthreads();
+	for (int t = tid; t < ar; t += nt) pdf1[t] *= s_k;
+	__syncthreads();
+	// compute_cdf1, :2878-2900
+	{
+		const int cnt = ar - 1;
+		for (int t = tid; t < cnt; t += nt) A.q[t] = ab_lookup1(pdf1, ar, ab_angle(t, cnt, TWO_PI));
+		__syncthreads();
+		if (tid == 0) {
+			const float dphi = (float)(TWO_PI / (double)(float)cnt);
+			float nint = 0.0f;
+			cdf1[0] = 0.0f;
+			for (int i = 1; i < cnt; ++i) {
+				nint += A.q[i];
+				cdf1[i] = nint * dphi;
+			}
+			cdf1[cnt] = 1.0f;
+		}
+		__syncthreads();
+		// compute_qf1, :2904-2935: first j (never moving backwards) whose running integral reaches i / cnt
+		const int res = cnt * 8;
+		for (int t = tid; t < res; t += nt) A.q[t] = ab_lookup1(cdf1, ar, ab_angle(t, res, TWO_PI));
+		__syncthreads();
+		if (tid == 0) {
+			int n1 = 0, j = 0;
+			qf1[n1++] = 0.0f;
+			for (int i = 1; i < cnt; ++i) {
+				const float cdf = (float)i / (float)cnt;
+				for (; j < res; ++j)
+					if (A.q[j] >= cdf) { qf1[n1++] = (float)j / (float)res; break; }
+			}
+			qf1[n1++] = 1.0f;
+			A.counts[0] = n1;
+		}
+		__syncthreads();
+	}
+	// compute_pdf2, :2944-2969
+	{
+		const int ntheta = er - 1;
+		for (int t = tid; t < T; t += nt) {
+			const int i = t / er, j = t % er;
+			const float phi = ab_angle(i, ar, TWO_PI);
+			pdf2[t] = j < ntheta ? tp.p22_theta_phi(ab_angle(j, ntheta, HALF_PI), phi) / ab_lookup1(pdf1, ar, phi) : 0.0f;
+		}
+		__syncthreads();
+		// normalize_pdf2, :3055-3088 (all constants on the unscaled table, then the rows are scaled)
+		for (int t = tid; t < ar * 256; t += nt) {
+			const int j = t / 256, i = t % 256;
+			const float phi = ab_angle(j, ar, TWO_PI), theta = ab_angle(i, 256, HALF_PI);
+			A.terms[t] = ab_term(ab_lookup2(pdf2, er, ar, theta, phi, 0.0f), theta);
+		}
+		__syncthreads();
+		for (int j = tid; j < ar; j += nt) {
+			float nint = 0.0f;
+			for (int i = 0; i < 256; ++i) nint = (float)((double)nint + A.terms[j * 256 + i]);
+			nint *= (float)(HALF_PI / (double)256.0f);
+			A.q[j] = rcp_via_double(nint);
+		}
+		__syncthreads();
+		for (int t = tid; t < T; t += nt) pdf2[t] *= A.q[t / er];
+		__syncthreads();
+		// compute_cdf2, :2973-3000
+		for (int t = tid; t < ar * ntheta; t += nt) {
+			const int i = t / ntheta, j = t % ntheta;
+			const float phi = ab_angle(i, ar, TWO_PI), theta = ab_angle(j, ntheta, HALF_PI);
+			A.terms[t] = ab_term(ab_lookup2(pdf2, er, ar, theta, phi, 0.0f), theta);
+		}
+		__syncthreads();
+		for (int i = tid; i < ar; i += nt) {
+			const float dtheta = (float)(HALF_PI / (double)(float)ntheta);
+			float nint = 0.0f;
+			for (int j = 0; j < ntheta; ++j) {
+				nint = (float)((double)nint + A.terms[i * ntheta + j]);
+				cdf2[i * er + j] = nint * dtheta;
+			}
+			cdf2[i * er + ntheta] = 1.0f;
+		}
+		__syncthreads();
+		// compute_qf2, :3004-3037
+		const int res = ntheta * 8;
+		for (int t = tid; t < ar * res; t += nt) {
+			const int k = t / res, j = t % res;
+			A.q[t] = ab_lookup2(cdf2, er, ar, ab_angle(j, res, HALF_PI), ab_angle(k, ar, TWO_PI), 1.0f);
+		}
+		__syncthreads();
+		for (int k = tid; k < ar; k += nt) {
+			float *row = A.rows + k * er;
+			int n = 0, j = 0;
+			row[n++] = 0.0f;
+			for (int i = 1; i < ntheta; ++i) {
+				const float cdf = (float)i / (float)ntheta;
+				for (; j < res; ++j)
+					if (A.q[k * res + j] >= cdf) { row[n++] = (float)j / (float)res; break; }
+			}
+			row[n++] = 1.0f;
+			A.rowcnt[k] = n;
+		}
+		__syncthreads();
+		// the reference appends the rows to one vector: pack them back to back
+		if (tid == 0) {
+			int off = 0;
+			for (int k = 0; k < ar; ++k) {
+				const int n = A.rowcnt[k];
+				A.rowcnt[k] = off;
+				off += n;
+			}
+			A.counts[1] = off;
+			s_total = off;
+		}
+		__syncthreads();
+		for (int t = tid; t < T; t += nt) {
+			const int k = t / er, e = t % er;
+			const int begin = A.rowcnt[k], end = k + 1 < ar ? A.rowcnt[k + 1] : s_total;
+			if (e < end - begin) qf2[begin + e] = A.rows[t];
+		}
+	}
+}
+
+cudaError_t build_aniso_sampling_tables(float *tables, int elev_res, int azim_res, int counts_host[2], cudaStream_t st)
+{
+	const size_t er = (size_t)elev_res, ar = (size_t)azim_res;
+	const size_t n_terms = ar * 256 > ar * er ? ar * 256 : ar * er;
+	size_t n_q = ar * 8 * (er - 1);
+	if (n_q < 512 + 8 * ar) n_q = 512 + 8 * ar;
+	const size_t bytes = 8 * n_terms + 4 * n_q + 4 * ar * er + 4 * ar + 8;
+	char *ws = nullptr;
+	cudaError_t e = cudaMalloc(&ws, bytes);
+	if (e != cudaSuccess) return e;
+	AnisoBuild A;
+	A.tab = tables; A.er = elev_res; A.ar = azim_res;
+	A.terms = reinterpret_cast<double *>(ws);
+	A.q = reinterpret_cast<float *>(ws + 8 * n_terms);
+	A.rows = A.q + n_q;
+	A.rowcnt = reinterpret_cast<int *>(A.rows + ar * er);
+	A.counts = A.rowcnt + ar;
+	aniso_sampling_tables_kernel<<<1, 1024, 0, st>>>(A);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(counts_host, A.counts, 8, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	cudaFree(ws);
+	return e;
+}
+
+// tables: device, laid out as aniso_table_floats() describes
+cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, int n_qf1, const MfLaunch &L,
+                                       cudaStream_t st)
 {
 	if (L.n <= 0) return cudaSuccess;
-	if (L.op != OP_EVAL && L.op != OP_EVALP && L.op != OP_PDF) return cudaErrorNotSupported;
 	TabQueryArgs A;
 	A.tables = tables; A.res = elev_res; A.shadow = L.shadow;
 	A.a = L.a; A.b = L.b; A.n = L.n; A.out_stride = L.out_stride;
-	A.out1 = A.out2 = nullptr;
+	A.out1 = L.out1; A.out2 = L.out2;
 	const int per = (L.op == OP_PDF) ? 1 : 3;
 	long long want = (L.n + TQ_THREADS - 1) / TQ_THREADS, cap = (long long)sm_count() * 4;
 	const int grid = (int)(want < cap ? want : cap);
 #define TA_DISPATCH(PP)                                                                                             \
 	switch (L.op) {                                                                                                 \
-	case OP_EVAL: tabular_aniso_query_kernel<OP_EVAL, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res); break;          \
-	case OP_EVALP: tabular_aniso_query_kernel<OP_EVALP, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res); break;        \
-	default: tabular_aniso_query_kernel<OP_PDF, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res);                       \
+	case OP_EVAL: tabular_aniso_query_kernel<OP_EVAL, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res, n_qf1); break;          \
+	case OP_EVALP: tabular_aniso_query_kernel<OP_EVALP, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res, n_qf1); break;        \
+	case OP_PDF: tabular_aniso_query_kernel<OP_PDF, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res, n_qf1); break;            \
+	case OP_SAMPLE: tabular_aniso_query_kernel<OP_SAMPLE, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res, n_qf1); break;      \
+	default: tabular_aniso_query_kernel<OP_EVALP_IS, PP><<<grid, TQ_THREADS, 0, st>>>(A, azim_res, n_qf1);                  \
 	}                                                                                                               \
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	if (L.layout == DJB200_PARAMS_PER_PAIR) {
 		A.params = reinterpret_cast<const Params *>(L.params);
 		A.n_params = 1;
-		A.out0 = L.out0;
+		A.out0 = L.out0; A.out1 = L.out1; A.out2 = L.out2;
 		TA_DISPATCH(true)
 		return cudaGetLastError();
 	}
@@ -263,7 +533,9 @@ cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int az
 		int64_t mc = L.n_params - m0 < TQ_MAX_SMEM_PARAMS ? L.n_params - m0 : TQ_MAX_SMEM_PARAMS;
 		A.params = reinterpret_cast<const Params *>(L.params) + m0;
 		A.n_params = (int)mc;
-		A.out0 = L.out0 + m0 * L.out_stride * per;
+		A.out0 = L.out0 ? L.out0 + m0 * L.out_stride * per : nullptr;
+		A.out1 = L.out1 ? L.out1 + m0 * L.out_stride * 3 : nullptr;
+		A.out2 = L.out2 ? L.out2 + m0 * L.out_stride : nullptr;
 		TA_DISPATCH(false)
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) return e;

@@ -301,12 +301,19 @@ DJB200_API djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sou
                                                         int32_t elev_res, int32_t azim_res, int32_t shadow,
                                                         int32_t iterations,
                                                         djb200_tabular_anisotropic_fit *results, void *stream);
-/* djb::tabular_anisotropic as an evaluable BRDF: a djb200_tabular handle on the elevation x azimuth tables.
- * djb200_tabular_eval / _evalp / _pdf work on it (p22_std / sigma_std of dj_brdf.h:2178-2211, pdf = D cos / (4 i.h));
- * _sample / _evalp_is return DJB200_ERR_UNSUPPORTED (its marginal / conditional sampling tables, dj_brdf.h:2766-3122,
- * are not built). */
+/* djb::tabular_anisotropic as an evaluable / samplable BRDF: a djb200_tabular handle on the elevation x azimuth tables.
+ * Every djb200_tabular_* query works on it: p22_std / sigma_std of dj_brdf.h:2178-2211, pdf = D cos / (4 i.h), and
+ * normal-map sampling through the azimuth-marginal / elevation-conditional quantile tables (dj_brdf.h:2766-2837), which
+ * this call builds on the device from the p22 table exactly as the constructor does (compute_pdf1 / cdf1 / qf1 / pdf2 /
+ * cdf2 / qf2, dj_brdf.h:2266-2272, 2848-3103). */
 DJB200_API djb200_status djb200_tabular_anisotropic_create(const djb200_tabular_anisotropic_fit *fit, int32_t shadow,
                                                            djb200_tabular **out);
+/* The sampling tables behind tabular_anisotropic::pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 (dj_brdf.h:2766-2824), copied to
+ * host arrays (any may be NULL): 1-D tables azim_res floats, 2-D tables elev_res * azim_res floats (azimuth-major rows of
+ * elev_res).  counts = entries the reference's push_back loops produce for qf1 / qf2 (normally the full sizes). */
+DJB200_API djb200_status djb200_tabular_anisotropic_sampling_tables(const djb200_tabular *t, float *pdf1, float *cdf1,
+                                                                    float *qf1, float *pdf2, float *cdf2, float *qf2,
+                                                                    int32_t counts[2]);
 
 /* ---- anisotropic fit, stage by stage ------------------------------------------------------- *
  * The same fit as djb200_fit_tabular_anisotropic(), split at the two places where a fit whose

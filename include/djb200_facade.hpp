@@ -373,11 +373,12 @@ public:
 	}
 
 	virtual bool supports_smith_vndf_sampling() const = 0;
-	void set_shadow(bool shadow) { m_shadow = shadow; }
+	void set_shadow(bool shadow) { m_shadow = shadow; ++m_fresnel_rev; }
 	void set_fresnel(const fresnel::impl &f)
 	{
 		delete m_fresnel;
 		m_fresnel = f.copy();
+		++m_fresnel_rev; // table-backed subclasses re-upload their device handle
 	}
 	int get_shadow() const { return m_shadow; }
 	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
@@ -392,8 +393,18 @@ public:
 	}
 
 protected:
-	microfacet(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : m_fresnel(f.copy()), m_shadow(shadow) {}
+	microfacet(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : m_fresnel(f.copy()), m_shadow(shadow), m_fresnel_rev(0) {}
 	virtual int ndf_id() const = 0;
+	// The Fresnel term of a table-backed BRDF travels as `n` spline points: the fitted spline as it is, fresnel::ideal as
+	// a table of ones (a lerp between ones is exactly 1); other terms cannot be tabulated without changing results.
+	void fresnel_points(size_t n, std::vector<float> *out) const
+	{
+		djb200_fresnel d;
+		m_fresnel->describe(&d);
+		if (d.kind == DJB200_FRESNEL_SPLINE && (size_t)d.n_points == n) out->assign(d.points, d.points + 3 * n);
+		else if (d.kind == DJB200_FRESNEL_IDEAL) out->assign(3 * n, 1.0f);
+		else throw exc("djb_error: a tabulated BRDF takes its fitted Fresnel spline or fresnel::ideal");
+	}
 	// one C-ABI call; op: 0 eval, 1 evalp, 2 pdf, 3 sample, 4 evalp_is.  tabular overrides this with its own entry points.
 	virtual void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a,
 	                      const float *b, size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
@@ -412,6 +423,7 @@ protected:
 	static const djb200_params *raw(const void *p) { return reinterpret_cast<const djb200_params *>(p); }
 	const fresnel::impl *m_fresnel;
 	bool m_shadow;
+	unsigned m_fresnel_rev;
 };
 
 class radial : public microfacet {
@@ -620,9 +632,11 @@ class tabular : public radial {
 	std::vector<vec3> m_fresnel_pts;
 	float_t m_alpha_beckmann, m_alpha_ggx;
 	mutable djb200_tabular *m_handle;
-	tabular() : radial(), m_handle(NULL) {}
+	mutable unsigned m_handle_rev;
+	tabular() : radial(), m_handle(NULL), m_handle_rev(0) {}
 public:
-	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4) : radial(fresnel::ideal(), shadow), m_handle(NULL)
+	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4)
+	    : radial(fresnel::ideal(), shadow), m_handle(NULL), m_handle_rev(0)
 	{
 		const brdf *src = &source;
 		std::vector<tabular *> self(1, this);
@@ -652,14 +666,19 @@ protected:
 	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
 	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
 	{
-		if (!m_handle) { // upload the tables once
+		if (!m_handle || m_handle_rev != m_fresnel_rev) { // upload the tables once (again after set_fresnel)
+			djb200_tabular_destroy(m_handle);
+			m_handle = NULL;
+			std::vector<float> fr;
+			fresnel_points(m_p22.size(), &fr);
 			djb200_tabular_fit f;
 			memset(&f, 0, sizeof f);
 			f.res = (int32_t)m_p22.size();
 			f.p22 = const_cast<float *>(&m_p22[0]); f.sigma = const_cast<float *>(&m_sigma[0]);
 			f.cdf = const_cast<float *>(&m_cdf[0]); f.qf = const_cast<float *>(&m_qf[0]);
-			f.fresnel = const_cast<float *>(&m_fresnel_pts[0].x);
+			f.fresnel = &fr[0];
 			detail::check(djb200_tabular_create(&f, m_shadow ? 1 : 0, &m_handle));
+			m_handle_rev = m_fresnel_rev;
 		}
 		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
 		switch (op) {
@@ -699,16 +718,20 @@ private:
 	}
 };
 
-// dj_brdf.h:428-478 (eval tables + parameter fits)
-class tabular_anisotropic {
+// dj_brdf.h:428-478: the anisotropic fit (elevation x azimuth tables + 5-parameter Beckmann / GGX fits) and, as in the
+// reference, a microfacet BRDF of its own: eval / evalp / pdf on the tables, sample / evalp_is by normal-map sampling through
+// the marginal / conditional quantile tables, which the device builds when the handle is created.
+class tabular_anisotropic : public microfacet {
 	std::vector<float_t> m_p22, m_sigma, m_residuals;
 	std::vector<vec3> m_fresnel_pts;
-	fresnel::spline *m_fresnel;
 	float_t m_beckmann[5], m_ggx[5];
 	int m_elevation_res, m_azimuthal_res;
+	mutable djb200_tabular *m_handle;
+	mutable unsigned m_handle_rev;
 public:
 	tabular_anisotropic(const brdf &source, int elevation_res, int azimuthal_res, bool shadow = true, int iterations = 4)
-	    : m_fresnel(NULL), m_elevation_res(elevation_res), m_azimuthal_res(azimuthal_res)
+	    : microfacet(fresnel::ideal(), shadow), m_elevation_res(elevation_res), m_azimuthal_res(azimuthal_res), m_handle(NULL),
+	      m_handle_rev(0)
 	{
 		DJB_ASSERT(elevation_res > 1 && azimuthal_res > 1 && "Invalid Resolution");
 		djb200_source src = detail::describe_source(source);
@@ -723,9 +746,9 @@ public:
 		detail::check(djb200_fit_tabular_anisotropic(&src, 1, elevation_res, azimuthal_res, shadow ? 1 : 0, iterations, &fit, NULL));
 		memcpy(m_beckmann, fit.beckmann, sizeof m_beckmann);
 		memcpy(m_ggx, fit.ggx, sizeof m_ggx);
-		m_fresnel = new fresnel::spline(m_fresnel_pts);
+		set_fresnel(fresnel::spline(m_fresnel_pts)); // get_fresnel() returns the fitted spline (dj_brdf.h:2700)
 	}
-	~tabular_anisotropic() { delete m_fresnel; }
+	~tabular_anisotropic() { djb200_tabular_destroy(m_handle); }
 	static microfacet::params fit_beckmann_parameters(const tabular_anisotropic &t)
 	{
 		return microfacet::params::pdfparams(t.m_beckmann[0], t.m_beckmann[1], t.m_beckmann[2], t.m_beckmann[3], t.m_beckmann[4]);
@@ -746,10 +769,56 @@ public:
 		if (h) *h = m_azimuthal_res;
 		return m_sigma;
 	}
-	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
-private:
-	tabular_anisotropic(const tabular_anisotropic &);
-	tabular_anisotropic &operator=(const tabular_anisotropic &);
+	const std::vector<float_t> &get_residuals() const { return m_residuals; }
+	bool supports_smith_vndf_sampling() const { return false; }
+	// the six sampling tables behind pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 (dj_brdf.h:2766-2824); any pointer may be NULL
+	void get_sampling_tables(std::vector<float_t> *pdf1, std::vector<float_t> *cdf1, std::vector<float_t> *qf1,
+	                         std::vector<float_t> *pdf2, std::vector<float_t> *cdf2, std::vector<float_t> *qf2) const
+	{
+		upload();
+		std::vector<float_t> *v[6] = {pdf1, cdf1, qf1, pdf2, cdf2, qf2};
+		float *p[6];
+		for (int k = 0; k < 6; ++k) {
+			if (v[k]) v[k]->assign(k < 3 ? (size_t)m_azimuthal_res : m_p22.size(), 0);
+			p[k] = v[k] ? &(*v[k])[0] : NULL;
+		}
+		int32_t counts[2];
+		detail::check(djb200_tabular_anisotropic_sampling_tables(m_handle, p[0], p[1], p[2], p[3], p[4], p[5], counts));
+		if (qf1) qf1->resize(counts[0]);
+		if (qf2) qf2->resize(counts[1]);
+	}
+
+protected:
+	int ndf_id() const { return -1; }
+	void upload() const
+	{
+		if (m_handle && m_handle_rev == m_fresnel_rev) return;
+		djb200_tabular_destroy(m_handle);
+		m_handle = NULL;
+		std::vector<float> fr;
+		fresnel_points((size_t)m_elevation_res, &fr);
+		djb200_tabular_anisotropic_fit f;
+		memset(&f, 0, sizeof f);
+		f.elev_res = m_elevation_res; f.azim_res = m_azimuthal_res;
+		f.p22 = const_cast<float *>(&m_p22[0]); f.sigma = const_cast<float *>(&m_sigma[0]);
+		f.fresnel = &fr[0];
+		detail::check(djb200_tabular_anisotropic_create(&f, m_shadow ? 1 : 0, &m_handle));
+		m_handle_rev = m_fresnel_rev;
+	}
+	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
+	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
+	{
+		upload();
+		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
+		switch (op) {
+		case 0: st = djb200_tabular_eval(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 1: st = djb200_tabular_evalp(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 2: st = djb200_tabular_pdf(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 3: st = djb200_tabular_sample(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 4: st = djb200_tabular_evalp_is(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
+		}
+		detail::check(st);
+	}
 };
 
 // utils/nmap2leanmap.cpp:18-54 (bias = 0) and nmap2leanmap_biased.cpp:23-63 (bias = 25) on raw planar buffers

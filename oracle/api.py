@@ -353,6 +353,33 @@ class PortOracle:
                                          c_f32p(a.ctypes.data), c_f32p(b.ctypes.data), i64(n), c_f32p(o0.ctypes.data), C.c_int(nthreads))
         return o0
 
+    def aniso_sampling_tables(self, p22, er, ar):
+        """tabular_anisotropic's sampling tables from its normalised p22 table (dj_brdf.h:2848-3103)."""
+        p22 = _f32(p22).reshape(-1)
+        one = [np.zeros(ar, np.float32) for _ in range(3)]
+        two = [np.zeros(er * ar, np.float32) for _ in range(3)]
+        counts = (C.c_int * 2)()
+        self.lib.orc_aniso_sampling_tables(c_f32p(p22.ctypes.data), C.c_int(er), C.c_int(ar),
+                                           *[c_f32p(a.ctypes.data) for a in (one[0], one[1], one[2], two[0], two[1], two[2])],
+                                           counts)
+        return dict(pdf1=one[0], cdf1=one[1], qf1=one[2], pdf2=two[0], cdf2=two[1], qf2=two[2],
+                    n_qf1=counts[0], n_qf2=counts[1])
+
+    def tabular_aniso_sample_query(self, op, fit, tabs, er, ar, u, wo, params=None, shadow=True, nthreads=1):
+        """sample / evalp_is of djb::tabular_anisotropic on a fit_tabular_anisotropic() result + aniso_sampling_tables()."""
+        code = {"sample": 3, "evalp_is": 4}[op]
+        a, b = _f32(u), _f32(wo)
+        n = len(b)
+        fs = self._fres(Fresnel.spline(fit["fresnel"]))
+        p = None if params is None else _f32(params)
+        o0, o1, o2 = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        self.lib.orc_tabular_aniso_sample_query(
+            C.c_int(code), c_f32p(_f32(fit["p22"]).ctypes.data), c_f32p(_f32(fit["sigma"]).ctypes.data),
+            c_f32p(tabs["qf1"].ctypes.data), C.c_int(tabs["n_qf1"]), c_f32p(tabs["qf2"].ctypes.data), C.c_int(er), C.c_int(ar),
+            C.byref(fs), C.c_int(int(shadow)), c_f32p(_ptr(p)), c_f32p(a.ctypes.data), c_f32p(b.ctypes.data), i64(n),
+            c_f32p(o0.ctypes.data), c_f32p(o1.ctypes.data), c_f32p(o2.ctypes.data), C.c_int(nthreads))
+        return (o0, o1, o2) if code == 4 else o0
+
     def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=8):
         s, keep = self._source(src)
         n = elev_res * azim_res
@@ -371,10 +398,13 @@ class RefOracle:
     """The unmodified reference, through oracle/ref_harness.cpp."""
     name = "reference"
 
-    def __init__(self):
+    def __init__(self, opened=False):
+        """opened=True loads libdjbref_open.so: the same harness + reference compiled with the access specifiers opened
+        (oracle/ref_open.cpp), which additionally exports the reference's private sampling tables."""
         if not ref_available():
             raise RuntimeError("oracle/_ref/libdjbref.so not built (needs /root/reference; run `make -C oracle ref`)")
-        L = self.lib = C.CDLL(str(HERE / "_ref" / "libdjbref.so"))
+        self.opened = opened
+        L = self.lib = C.CDLL(str(HERE / "_ref" / ("libdjbref_open.so" if opened else "libdjbref.so")))
         for fn in ("ref_microfacet_create", "ref_merl_open", "ref_utia_open", "ref_sgd_create",
                    "ref_abc_create", "ref_tabular_create", "ref_tabular_anisotropic_create"):
             getattr(L, fn).restype = C.c_void_p
@@ -604,9 +634,35 @@ class RefOracle:
         try:
             if op == "eval":
                 return self.brdf_eval(t, params, wi, wo, nthreads)
+            if op == "evalp_is":
+                w, i, pdf = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.float32)
+                self._q("ref_brdf_evalp_is", t, params, wi, wo, [w, i, pdf], nthreads)
+                return w, i, pdf
             out = np.empty(n if op == "pdf" else (n, 3), np.float32)
-            self._q({"evalp": "ref_brdf_evalp", "pdf": "ref_brdf_pdf"}[op], t, params, wi, wo, [out], nthreads)
+            self._q({"evalp": "ref_brdf_evalp", "pdf": "ref_brdf_pdf", "sample": "ref_brdf_sample"}[op], t, params, wi, wo,
+                    [out], nthreads)
             return out
+        finally:
+            self.destroy(t)
+            self.destroy(h)
+
+    def aniso_sampling_tables(self, src, er, ar, shadow=True):
+        """The reference's private m_pdf1 / m_cdf1 / m_qf1 / m_pdf2 / m_cdf2 / m_qf2 (needs RefOracle(opened=True))
+        plus its p22 table -> dict; `sizes` = the six vector sizes."""
+        assert self.opened, "private tables need RefOracle(opened=True)"
+        h = self._source_handle(src)
+        t = C.c_void_p(self.lib.ref_tabular_anisotropic_create(h, C.c_int(er), C.c_int(ar), C.c_int(int(shadow))))
+        try:
+            one = [np.zeros(ar, np.float32) for _ in range(3)]
+            two = [np.zeros(er * ar, np.float32) for _ in range(3)]
+            sizes = (C.c_int * 6)()
+            rc = self.lib.ref_tabular_anisotropic_sampling_tables(
+                t, *[c_f32p(a.ctypes.data) for a in (one[0], one[1], one[2], two[0], two[1], two[2])], sizes)
+            assert rc == 0, rc
+            p22, sigma = np.zeros(er * ar, np.float32), np.zeros(er * ar, np.float32)
+            self.lib.ref_tabular_anisotropic_get(t, c_f32p(p22.ctypes.data), c_f32p(sigma.ctypes.data), None, None, None)
+            return dict(pdf1=one[0], cdf1=one[1], qf1=one[2], pdf2=two[0], cdf2=two[1], qf2=two[2], p22=p22,
+                        sigma=sigma, sizes=list(sizes))
         finally:
             self.destroy(t)
             self.destroy(h)

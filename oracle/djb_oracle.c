@@ -260,6 +260,13 @@ void orc__set_tabular(const float *p22, int np22, const float *sigma, int nsigma
 	t_tab_p22 = p22; t_tab_np22 = np22; t_tab_sigma = sigma; t_tab_nsigma = nsigma;
 }
 void orc__set_tabular_qf(const float *qf) { t_tab_qf = qf; }
+/* tabular_anisotropic's quantile tables: qf1 has n_qf1 entries (normally azim_res), qf2 is elev_res x azim_res */
+static __thread const float *t_tab_qf1, *t_tab_qf2;
+static __thread int t_tab_nqf1;
+void orc__set_tabular_aniso_qf(const float *qf1, int n_qf1, const float *qf2)
+{
+	t_tab_qf1 = qf1; t_tab_nqf1 = n_qf1; t_tab_qf2 = qf2;
+}
 
 /* spline::eval2d<float_t>(uwrap_edge, u1, uwrap_repeat, u2), :1220-1247 */
 float orc__spline_eval2d_f(const float *pts, int w, int h, float u1, float u2)
@@ -516,6 +523,15 @@ static float beckmann_qf2(float u, float ck, float sk)
 /* radial::sample_vp22_std_smith, :1818-1846 */
 static void sample_std_slopes(int ndf, float u1, float u2, v3 k, float *xs, float *ys)
 {
+	if (ndf == ORC_NDF_TABULAR_ANISO) { /* tabular_anisotropic::sample_vp22_std_nmap, :2826-2837, with qf1 / qf2, :2780-2784, 2814-2824 */
+		float phi = F(D(orc__spline_eval_f(t_tab_qf1, t_tab_nqf1, u1)) * 2.0 * ORC_PI);
+		float uphi = F(D(phi) / (2.0 * ORC_PI));
+		float theta = F(D(orc__spline_eval2d_f(t_tab_qf2, t_tab_np22, t_tab_nsigma, u2, uphi)) * 0.5 * ORC_PI);
+		float tan_theta = F(tan(D(theta)));
+		*xs = F(D(-tan_theta) * cos(D(phi)));
+		*ys = F(D(-tan_theta) * sin(D(phi)));
+		return;
+	}
 	if (ndf == ORC_NDF_TABULAR) { /* radial::sample_vp22_std_nmap, :1806-1816, with tabular::qf_radial, :2172-2176 */
 		float phi_h = F(D(u1) * ORC_PI * 2.0);
 		float qf = orc__spline_eval_f(t_tab_qf, t_tab_np22, u2);
@@ -578,7 +594,7 @@ static v3 mf_evalp_is(int ndf, const orc_fresnel *fr, int shadow, const orc_para
 	if (D(G) > 0.0) {
 		float cd = f_sat(v3_dot(o, h));
 		*i_out = i;
-		if (ndf == ORC_NDF_TABULAR) { /* :1753-1756 */
+		if (ndf == ORC_NDF_TABULAR || ndf == ORC_NDF_TABULAR_ANISO) { /* :1753-1756 */
 			float pdf_ = F(D(h.z * mf_ndf(ndf, p, h)) / (4.0 * D(cd)));
 			*pdf_out = pdf_;
 			return v3_div(mf_evalp(ndf, fr, shadow, p, i, o), pdf_);
@@ -626,6 +642,8 @@ typedef struct {
 	const float *a, *b;
 	float *o0, *o1, *o2;
 	const float *tab_p22, *tab_sigma, *tab_qf; /* ORC_NDF_TABULAR / ORC_NDF_TABULAR_ANISO only */
+	const float *tab_qf1, *tab_qf2;            /* ORC_NDF_TABULAR_ANISO sampling */
+	int tab_nqf1;
 	int tab_res, tab_ar;                       /* radial: table length; anisotropic: elevation x azimuth resolution */
 } mf_ctx;
 
@@ -637,6 +655,7 @@ static void mf_range(void *vctx, int64_t s, int64_t e)
 		orc__set_tabular_qf(c->tab_qf);
 	} else if (c->ndf == ORC_NDF_TABULAR_ANISO) {
 		orc__set_tabular(c->tab_p22, c->tab_res, c->tab_sigma, c->tab_ar);
+		orc__set_tabular_aniso_qf(c->tab_qf1, c->tab_nqf1, c->tab_qf2);
 	}
 	for (int64_t k = s; k < e; ++k) {
 		switch (c->op) {
@@ -716,6 +735,25 @@ ORC_API void orc_tabular_aniso_query(int op, const float *p22, const float *sigm
 	c.tab_p22 = p22; c.tab_sigma = sigma; c.tab_res = elev_res; c.tab_ar = azim_res;
 	orc_parallel_ranges(n, nthreads, mf_range, &c);
 	orc__set_tabular(NULL, 0, NULL, 0);
+}
+
+/* sample (op 3) / evalp_is (op 4) of djb::tabular_anisotropic with the quantile tables of orc_aniso_sampling_tables */
+ORC_API void orc_tabular_aniso_sample_query(int op, const float *p22, const float *sigma, const float *qf1, int n_qf1,
+                                            const float *qf2, int elev_res, int azim_res, const orc_fresnel *F,
+                                            int shadow, const orc_params *P, const float *u, const float *wo,
+                                            int64_t n, float *o0, float *o1, float *o2, int nthreads)
+{
+	mf_ctx c;
+	memset(&c, 0, sizeof c);
+	if (op < 3 || op > 4) return;
+	c.op = op; c.ndf = ORC_NDF_TABULAR_ANISO; c.shadow = shadow; c.F = F;
+	if (P) c.P = *P; else orc_params_elliptic(1.0f, 1.0f, 0.0f, &c.P);
+	c.a = u; c.b = wo; c.o0 = o0; c.o1 = o1; c.o2 = o2;
+	c.tab_p22 = p22; c.tab_sigma = sigma; c.tab_res = elev_res; c.tab_ar = azim_res;
+	c.tab_qf1 = qf1; c.tab_nqf1 = n_qf1; c.tab_qf2 = qf2;
+	orc_parallel_ranges(n, nthreads, mf_range, &c);
+	orc__set_tabular(NULL, 0, NULL, 0);
+	orc__set_tabular_aniso_qf(NULL, 0, NULL);
 }
 
 /* used by djb_oracle_fit.c */

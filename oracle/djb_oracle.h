@@ -131,6 +131,17 @@ void orc_tabular_aniso_query(int op, const float *p22, const float *sigma, int e
                              const orc_fresnel *F, int shadow, const orc_params *P, const float *wi,
                              const float *wo, int64_t n, float *o0, int nthreads);
 
+/* tabular_anisotropic's sampling tables (dj_brdf.h:2848-3103) from its normalised p22 table; 1-D outputs hold azim_res
+ * floats, 2-D ones elev_res * azim_res; counts[0] / counts[1] = entries the reference's push_back loops produce for
+ * qf1 / qf2 (azim_res and elev_res * azim_res unless a search runs out) */
+void orc_aniso_sampling_tables(const float *p22, int elev_res, int azim_res, float *pdf1, float *cdf1, float *qf1,
+                               float *pdf2, float *cdf2, float *qf2, int *counts);
+/* djb::tabular_anisotropic sample (op 3) / evalp_is (op 4): normal-map sampling through qf1 / qf2 (:2826-2837) */
+void orc_tabular_aniso_sample_query(int op, const float *p22, const float *sigma, const float *qf1, int n_qf1,
+                                    const float *qf2, int elev_res, int azim_res, const orc_fresnel *F, int shadow,
+                                    const orc_params *P, const float *u, const float *wo, int64_t n, float *o0,
+                                    float *o1, float *o2, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

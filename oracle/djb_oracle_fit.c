@@ -498,3 +498,162 @@ ORC_API void orc_fit_tabular_anisotropic(const orc_source *src, int elev_res, in
 	}
 	orc__set_tabular(NULL, 0, NULL, 0);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * tabular_anisotropic's sampling tables: the marginal density of the azimuth, the conditional density of the elevation,
+ * their running integrals and the inverted tables (compute_pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 and the two
+ * normalisations, dj_brdf.h:2848-3103), from the final (normalised) p22 table.
+ * All six outputs have room for azim_res (1-D) or elev_res * azim_res (2-D) floats and are zero-filled first; the
+ * reference builds qf1 / qf2 with push_back inside a search loop that can run out without pushing, so their fill
+ * counts are returned in counts[0] (qf1) and counts[1] (qf2; rows are packed back to back exactly as push_back leaves
+ * them). */
+static float spline_eval_repeat_f(const float *pts, int n, float u) /* spline::eval with uwrap_repeat, :1183-1218 */
+{
+	double ip;
+	float frac = F(modf(D(u * (float)n - u), &ip));
+	int i1 = (int)ip, i2 = (int)ip + 1;
+	while (i1 >= n) i1 -= n;
+	while (i1 < 0) i1 += n;
+	while (i2 >= n) i2 -= n;
+	while (i2 < 0) i2 += n;
+	float p1 = pts[i1], p2 = pts[i2];
+	return p1 + frac * (p2 - p1);
+}
+static float aniso_lookup1(const float *tab, int n, float phi) /* pdf1 / cdf1, :2766-2778 */
+{
+	return spline_eval_repeat_f(tab, n, F(D(phi) * 0.5 / ORC_PI));
+}
+static float aniso_lookup2(const float *tab, int w, int h, float theta, float phi, float beyond) /* pdf2 / cdf2, :2786-2812 */
+{
+	if (D(theta) >= 0.5 * ORC_PI) return beyond;
+	float u1 = F(D(theta) * 2.0 / ORC_PI), u2 = F(D(phi) * 0.5 / ORC_PI);
+	return orc__spline_eval2d_f(tab, w, h, u1, u2);
+}
+/* one term of the three elevation quadratures: (f * tan(theta)) / (cos_theta * cos_theta), accumulated in float */
+static float quad_step(float nint, float f, float theta)
+{
+	float c = F(cos(D(theta)));
+	return F(D(nint) + (D(f) * tan(D(theta))) / D(c * c));
+}
+
+ORC_API void orc_aniso_sampling_tables(const float *p22, int elev_res, int azim_res, float *pdf1, float *cdf1,
+                                       float *qf1, float *pdf2, float *cdf2, float *qf2, int *counts)
+{
+	const int er = elev_res, ar = azim_res;
+	memset(pdf1, 0, sizeof(float) * ar); memset(cdf1, 0, sizeof(float) * ar); memset(qf1, 0, sizeof(float) * ar);
+	memset(pdf2, 0, sizeof(float) * er * ar); memset(cdf2, 0, sizeof(float) * er * ar);
+	memset(qf2, 0, sizeof(float) * er * ar);
+	orc__set_tabular(p22, er, NULL, ar);
+	/* compute_pdf1, :2848-2874 */
+	{
+		const int ntheta = 256;
+		float dtheta = F(0.5 * ORC_PI / D((float)ntheta));
+		for (int i = 0; i < ar; ++i) {
+			float phi = F(D((float)i / (float)ar) * 2.0 * ORC_PI), nint = 0.0f;
+			for (int j = 0; j < ntheta; ++j) {
+				float theta = F(D((float)j / (float)ntheta) * 0.5 * ORC_PI);
+				nint = quad_step(nint, orc__aniso_p22_theta_phi(theta, phi), theta);
+			}
+			pdf1[i] = nint * dtheta;
+		}
+	}
+	/* normalize_pdf1, :3029-3051 */
+	{
+		const int cnt = 512;
+		float dphi = F(2.0 * ORC_PI / D((float)cnt)), nint = 0.0f;
+		for (int i = 0; i < cnt; ++i) nint += aniso_lookup1(pdf1, ar, F(D((float)i / (float)cnt) * 2.0 * ORC_PI));
+		nint *= dphi;
+		float k = F(1.0 / D(nint));
+		for (int i = 0; i < ar; ++i) pdf1[i] *= k;
+	}
+	/* compute_cdf1, :2878-2900 */
+	{
+		int cnt = ar - 1;
+		float dphi = F(2.0 * ORC_PI / D((float)cnt)), nint = 0.0f;
+		cdf1[0] = 0.0f;
+		for (int i = 1; i < cnt; ++i) {
+			nint += aniso_lookup1(pdf1, ar, F(D((float)i / (float)cnt) * 2.0 * ORC_PI));
+			cdf1[i] = nint * dphi;
+		}
+		cdf1[cnt] = 1.0f;
+	}
+	/* compute_qf1, :2904-2935 */
+	int n1 = 0;
+	{
+		int cnt = ar - 1, res = cnt * 8, j = 0;
+		qf1[n1++] = 0.0f;
+		for (int i = 1; i < cnt; ++i) {
+			float cdf = (float)i / (float)cnt;
+			for (; j < res; ++j) {
+				float u = (float)j / (float)res;
+				if (aniso_lookup1(cdf1, ar, F(D(u) * 2.0 * ORC_PI)) >= cdf) { qf1[n1++] = u; break; }
+			}
+		}
+		qf1[n1++] = 1.0f;
+	}
+	/* compute_pdf2, :2944-2969 */
+	{
+		int ntheta = er - 1;
+		for (int i = 0; i < ar; ++i) {
+			float phi = F(D((float)i / (float)ar) * 2.0 * ORC_PI);
+			for (int j = 0; j < ntheta; ++j) {
+				float theta = F(D((float)j / (float)ntheta) * 0.5 * ORC_PI);
+				pdf2[i * er + j] = orc__aniso_p22_theta_phi(theta, phi) / aniso_lookup1(pdf1, ar, phi);
+			}
+			pdf2[i * er + ntheta] = 0.0f;
+		}
+	}
+	/* normalize_pdf2, :3055-3088: every constant is computed on the unscaled table, then the rows are scaled */
+	{
+		const int ntheta = 256;
+		float dtheta = F(0.5 * ORC_PI / D((float)ntheta));
+		float *k = (float *)malloc(sizeof(float) * ar);
+		for (int j = 0; j < ar; ++j) {
+			float phi = F(D((float)j / (float)ar) * 2.0 * ORC_PI), nint = 0.0f;
+			for (int i = 0; i < ntheta; ++i) {
+				float theta = F(D((float)i / (float)ntheta) * 0.5 * ORC_PI);
+				nint = quad_step(nint, aniso_lookup2(pdf2, er, ar, theta, phi, 0.0f), theta);
+			}
+			nint *= dtheta;
+			k[j] = F(1.0 / D(nint));
+		}
+		for (int j = 0; j < ar; ++j)
+			for (int i = 0; i < er; ++i) pdf2[i + er * j] *= k[j];
+		free(k);
+	}
+	/* compute_cdf2, :2973-3000 */
+	{
+		int ntheta = er - 1;
+		float dtheta = F(0.5 * ORC_PI / D((float)ntheta));
+		for (int i = 0; i < ar; ++i) {
+			float phi = F(D((float)i / (float)ar) * 2.0 * ORC_PI), nint = 0.0f;
+			for (int j = 0; j < ntheta; ++j) {
+				float theta = F(D((float)j / (float)ntheta) * 0.5 * ORC_PI);
+				nint = quad_step(nint, aniso_lookup2(pdf2, er, ar, theta, phi, 0.0f), theta);
+				cdf2[i * er + j] = nint * dtheta;
+			}
+			cdf2[i * er + ntheta] = 1.0f;
+		}
+	}
+	/* compute_qf2, :3004-3037 */
+	int n2 = 0;
+	{
+		int ntheta = er - 1, res = ntheta * 8;
+		for (int kk = 0; kk < ar; ++kk) {
+			float phi = F(D((float)kk / (float)ar) * 2.0 * ORC_PI);
+			int j = 0;
+			qf2[n2++] = 0.0f;
+			for (int i = 1; i < ntheta; ++i) {
+				float cdf = (float)i / (float)ntheta;
+				for (; j < res; ++j) {
+					float u = (float)j / (float)res;
+					float theta = F(D(u) * 0.5 * ORC_PI);
+					if (aniso_lookup2(cdf2, er, ar, theta, phi, 1.0f) >= cdf) { qf2[n2++] = u; break; }
+				}
+			}
+			qf2[n2++] = 1.0f;
+		}
+	}
+	if (counts) { counts[0] = n1; counts[1] = n2; }
+	orc__set_tabular(NULL, 0, NULL, 0);
+}

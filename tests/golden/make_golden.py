@@ -43,6 +43,22 @@ def extra(ref):
         r = ref.fit_tabular(getattr(api.Source, kind)(name, m.coefficients()), 90)
         for k, v in r.items():
             e[f"fit/{kind}/{name}/{k}"] = v
+    # tabular_anisotropic sampling: private tables (opened harness) + sample / evalp_is through the reference's object
+    ro = api.RefOracle(opened=True)
+    src, er, ar = api.Source.utia(cases.random_utia_table(12)), 14, 18
+    t = ro.aniso_sampling_tables(src, er, ar)
+    for k in ("pdf1", "cdf1", "qf1", "pdf2", "cdf2", "qf2", "p22", "sigma"):
+        e[f"aniso_sampling/utia12/14x18/{k}"] = t[k]
+    e["aniso_sampling/utia12/14x18/sizes"] = np.array(t["sizes"])
+    _, swo, su = cases.pairs(512, stream=400)
+    e["aniso_sampling/wo"], e["aniso_sampling/u"] = swo, su
+    P = ref.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1)
+    e["aniso_sampling/params"] = P
+    e["aniso_sampling/utia12/14x18/sample"] = ref.tabular_aniso_query("sample", src, er, ar, su, swo, P)
+    w, i, pdf = ref.tabular_aniso_query("evalp_is", src, er, ar, su, swo, P)
+    e["aniso_sampling/utia12/14x18/evalp_is_w"], e["aniso_sampling/utia12/14x18/evalp_is_i"] = w, i
+    e["aniso_sampling/utia12/14x18/evalp_is_pdf"] = pdf
+    e["aniso_sampling/utia12/14x18/fresnel"] = ref.fit_tabular_anisotropic(src, er, ar)["fresnel"]
     np.savez_compressed(OUT / "extra_golden.npz", **e)
     print("extra_golden.npz", (OUT / "extra_golden.npz").stat().st_size, "bytes")
 

@@ -196,8 +196,9 @@ def test_tabular_brdf_queries(djb, port, srcname):
 
 
 def test_tabular_anisotropic_brdf_queries(djb, port):
-    """djb::tabular_anisotropic as an evaluable BRDF: eval / evalp / pdf on the 2-D tables against the oracle port (bit-identical
-    to the reference's object, tests/test_oracle_vs_reference.py); sampling is reported as unsupported, not faked."""
+    """djb::tabular_anisotropic as an evaluable / samplable BRDF: eval / evalp / pdf on the 2-D tables, the device-built
+    marginal / conditional sampling tables, and sample / evalp_is through them, against the oracle port (bit-identical
+    to the reference's object and private tables, tests/test_oracle_vs_reference.py)."""
     from tests.conftest import rel_err
     ut = cases.random_utia_table(12)
     er, ar = 16, 20
@@ -210,5 +211,23 @@ def test_tabular_anisotropic_brdf_queries(djb, port):
             want = port.tabular_aniso_query(op, ofit, er, ar, wi, wo, P, nthreads=8)
             assert bits_equal(got, want).mean() >= 0.9995, op
             assert np.array_equal(got == 0, want == 0) and rel_err(got, want).max() <= 1e-5, op
-    with pytest.raises(djb.DjbError):
-        fit.sample(u, wo)
+    # sampling tables built on the device from the p22 table (dj_brdf.h:2848-3103)
+    got_t, want_t = fit.sampling_tables(), port.aniso_sampling_tables(fit.m_p22, er, ar)
+    assert got_t["n_qf1"] == want_t["n_qf1"] == ar and got_t["n_qf2"] == want_t["n_qf2"] == er * ar
+    for k in ("pdf1", "cdf1", "pdf2", "cdf2"):
+        assert rel_err(got_t[k], want_t[k]).max() <= 1e-5 and bits_equal(got_t[k], want_t[k]).mean() >= 0.99, k
+    for k in ("qf1", "qf2"):  # inverted tables: a search step is 1 / (8 cnt); at most a stray entry may land one step off
+        assert (got_t[k] != want_t[k]).sum() <= 1 and np.abs(got_t[k] - want_t[k]).max() <= 1.0 / (8 * (min(er, ar) - 1)) + 1e-7, k
+    # sample / evalp_is with the device's own tables on both sides (isolates the query kernels from the table build)
+    for P in (None, port.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1)):
+        got = fit.sample(u, wo, P)
+        want = port.tabular_aniso_sample_query("sample", ofit, got_t, er, ar, u, wo, P, nthreads=8)
+        assert bits_equal(got, want).mean() >= 0.9995, "sample"
+        gw, gi, gp = fit.evalp_is(u, wo, P)
+        ww, wi_, wp = port.tabular_aniso_sample_query("evalp_is", ofit, got_t, er, ar, u, wo, P, nthreads=8)
+        ok = bits_equal(gi, wi_).all(axis=1)
+        assert ok.mean() >= 0.9995
+        assert rel_err(gw[ok], ww[ok]).max() <= 1e-5 and rel_err(gp[ok], wp[ok]).max() <= 1e-5
+    # furnace-style sanity: sampled directions are unit vectors and the weights are finite
+    nrm = np.linalg.norm(fit.sample(u, wo), axis=1)
+    assert np.abs(nrm - 1.0).max() < 1e-4

@@ -155,3 +155,18 @@ def test_fit_from_analytic_source(port, x, kind, name):
     p = port.fit_tabular(getattr(api.Source, kind)(name, m.coefficients()), 90)
     for k, v in p.items():
         assert bits_equal(v, x[f"fit/{kind}/{name}/{k}"]).all(), k
+
+
+def test_tabular_anisotropic_sampling(port, x):
+    """the port's sampling tables and sample / evalp_is against the reference's (golden) ones"""
+    er, ar, tag = 14, 18, "aniso_sampling/utia12/14x18"
+    pt = port.aniso_sampling_tables(x[f"{tag}/p22"], er, ar)
+    for k in ("pdf1", "cdf1", "qf1", "pdf2", "cdf2", "qf2"):
+        assert bits_equal(pt[k], x[f"{tag}/{k}"]).all(), k
+    assert list(x[f"{tag}/sizes"]) == [ar, ar, pt["n_qf1"], er * ar, er * ar, pt["n_qf2"]]
+    fit = dict(p22=x[f"{tag}/p22"], sigma=x[f"{tag}/sigma"], fresnel=x[f"{tag}/fresnel"])
+    u, wo, P = x["aniso_sampling/u"], x["aniso_sampling/wo"], x["aniso_sampling/params"]
+    assert bits_equal(port.tabular_aniso_sample_query("sample", fit, pt, er, ar, u, wo, P), x[f"{tag}/sample"]).all()
+    w, i, pdf = port.tabular_aniso_sample_query("evalp_is", fit, pt, er, ar, u, wo, P)
+    assert bits_equal(w, x[f"{tag}/evalp_is_w"]).all() and bits_equal(i, x[f"{tag}/evalp_is_i"]).all()
+    assert bits_equal(pdf, x[f"{tag}/evalp_is_pdf"]).all()

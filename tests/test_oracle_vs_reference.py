@@ -103,6 +103,29 @@ def test_tabular_anisotropic_brdf_bit_identical(port, ref):
             assert bits_equal(g, r).all(), op
 
 
+def test_tabular_anisotropic_sampling_bit_identical(port, ref):
+    """tabular_anisotropic's marginal / conditional sampling tables (private in the reference: read through the harness
+    build with opened access specifiers, oracle/ref_open.cpp) and sample / evalp_is through them."""
+    ro = api.RefOracle(opened=True)
+    wi, wo, u = cases.pairs(20_000, stream=400)
+    for src, er, ar in ((api.Source.utia(cases.random_utia_table(12)), 16, 20),
+                        (api.Source.microfacet(api.NDF_GGX), 12, 10),
+                        (api.Source.merl(cases.smooth_merl_table(21)), 20, 24)):
+        rt = ro.aniso_sampling_tables(src, er, ar)
+        fit = port.fit_tabular_anisotropic(src, er, ar, nthreads=8)
+        assert bits_equal(fit["p22"], rt["p22"]).all()
+        pt = port.aniso_sampling_tables(fit["p22"], er, ar)
+        assert rt["sizes"] == [ar, ar, pt["n_qf1"], er * ar, er * ar, pt["n_qf2"]]
+        for k in ("pdf1", "cdf1", "qf1", "pdf2", "cdf2", "qf2"):
+            assert bits_equal(pt[k], rt[k]).all(), k
+        for P in (None, port.params_pdfparams(0.7, 0.5, 0.3, 0.1, -0.1)):
+            g = port.tabular_aniso_sample_query("sample", fit, pt, er, ar, u, wo, P, nthreads=8)
+            assert bits_equal(g, ref.tabular_aniso_query("sample", src, er, ar, u, wo, P, nthreads=8)).all()
+            g = port.tabular_aniso_sample_query("evalp_is", fit, pt, er, ar, u, wo, P, nthreads=8)
+            r = ref.tabular_aniso_query("evalp_is", src, er, ar, u, wo, P, nthreads=8)
+            assert all(bits_equal(x, y).all() for x, y in zip(g, r))
+
+
 def test_sgd_abc_all_presets_bit_identical(port, ref):
     """djb::sgd / djb::abc: every one of the 100 materials, the port fed with the product's coefficient tables
     (djb200_sgd_preset / djb200_abc_preset, host-only calls) against the reference's own name lookup + eval.  Pins the
