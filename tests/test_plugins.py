@@ -1,0 +1,141 @@
+"""the six Mitsuba plugin sources of the reference (mitsuba/dj_*.cpp), UNMODIFIED, compiled
+against a mock Mitsuba API (tests/cpp/mock_mitsuba) -- once with the reference's own dj_brdf.h, once with the facade over
+libdjb200.so (include/compat/dj_brdf.h) -- and driven with the same BSDFSamplingRecords (tests/cpp/plugin_driver.cpp).
+
+The binaries are built by `make -C oracle plugins` where /root/reference exists (oracle/_ref/ travels to the GPU box):
+plugin_<name>_ref is the CPU reference, plugin_<name>_b200 runs every djb:: call through the C-ABI on the GPU."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import api
+from tests import cases
+
+ROOT = Path(__file__).resolve().parents[1]
+BIN = ROOT / "oracle" / "_ref"
+PLUGINS = ["dj_merl", "dj_utia", "dj_sgd", "dj_abc", "dj_brdf", "dj_beckmannconductor"]
+
+
+@pytest.fixture(scope="module")
+def binaries(djb):
+    if not all((BIN / f"plugin_{p}_{s}").exists() for p in PLUGINS for s in ("ref", "b200")):
+        if not (api.REF_ROOT / "mitsuba" / "dj_merl.cpp").exists():
+            pytest.skip("plugin binaries not built and /root/reference is absent")
+        api.build_ref()
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "plugins", f"REF={api.REF_ROOT}"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return {p: (BIN / f"plugin_{p}_ref", BIN / f"plugin_{p}_b200") for p in PLUGINS}
+
+
+def records(n, seed, textured=False, lean=False):
+    """n x 16 floats: wi, wo, u, (alpha1, alpha2, alphaAngle), (E1..E5 as a biased LEAN texel); NaN = no texture value"""
+    wi, wo, u = cases.pairs(n, stream=seed)
+    rng = np.random.default_rng(seed)
+    r = np.full((n, 16), np.nan, np.float32)
+    r[:, 0:3], r[:, 3:6], r[:, 6:8] = wi, wo, u
+    if textured:
+        r[:, 8] = rng.uniform(0.05, 0.6, n)
+        r[:, 9] = rng.uniform(0.05, 0.6, n)
+        r[:, 10] = rng.uniform(0.0, 3.1, n)
+    if lean:
+        # texels of a biased LEAN map (utils/nmap2leanmap_biased.cpp): slopes + 25, second moments of the biased slopes
+        sx, sy = rng.normal(0, 0.2, n), rng.normal(0, 0.2, n)
+        vx, vy = rng.uniform(1e-4, 0.05, n), rng.uniform(1e-4, 0.05, n)
+        cxy = rng.uniform(-0.5, 0.5, n) * np.sqrt(vx * vy)
+        r[:, 11], r[:, 12] = sx + 25, sy + 25
+        r[:, 13], r[:, 14] = sx * sx + vx, sy * sy + vy
+        r[:, 15] = sx * sy + cxy + 625
+    return r
+
+
+def run(binary, config_lines, rec, tmp_path, tag):
+    cfg, rin, rout = tmp_path / f"{tag}.cfg", tmp_path / f"{tag}.in", tmp_path / f"{tag}.out"
+    cfg.write_text("\n".join(config_lines) + "\n")
+    with open(rin, "wb") as f:
+        f.write(np.int32(len(rec)).tobytes() + np.ascontiguousarray(rec, np.float32).tobytes())
+    r = subprocess.run([str(binary), str(cfg), str(rin), str(rout)], capture_output=True, text=True, timeout=900)
+    return r, (np.fromfile(rout, np.float32).reshape(-1, 11) if r.returncode == 0 else None)
+
+
+def configs(tmp_path):
+    merl = tmp_path / "synthetic.binary"
+    api.write_merl_file(merl, cases.smooth_merl_table(21))
+    utia = tmp_path / "synthetic.bin"
+    np.ascontiguousarray(cases.random_utia_table(12), np.float64).tofile(utia)
+    c = {
+        "dj_merl": [("merl", [f"string filename {merl}"], {})],
+        "dj_utia": [("utia", [f"string filename {utia}"], {})],
+        "dj_sgd": [("gold", ["string merlID gold-metallic-paint"], {})],
+        "dj_abc": [("blue", ["string merlID blue-metallic-paint"], {})],
+        "dj_brdf": [
+            ("ggx_const", ["string distribution ggx", "float alpha1 0.2", "float alpha2 0.45", "float alphaAngle 30"], {}),
+            ("beckmann_textured", ["string distribution beckmann", "driver textured 1"], dict(textured=True)),
+            ("merl_tabular", ["string distribution tabular", f"string merl {merl}", "float alpha 1.0"], {}),
+            ("merl_ggx_fit", ["string distribution ggx", f"string merl {merl}", "float alpha 1.0",
+                              "spectrum eta 0.2 0.9 1.1", "spectrum k 3.9 2.4 2.2"], {}),
+            ("utia_tabular", ["string distribution tabular", f"string utia {utia}"], {}),
+        ],
+        "dj_beckmannconductor": [
+            ("lean", ["float alpha 0.08", "driver textured 1", "float dmapscale 1.5"], dict(textured=True, lean=True)),
+            ("naive_mip", ["float alpha1 0.1", "float alpha2 0.3", "bool leanFiltering 0", "driver textured 1"],
+             dict(lean=True)),
+            ("merl_fresnel", [f"string merl {merl}", "float alpha 1.0"], {}),
+        ],
+    }
+    return c
+
+
+def test_plugin_sources_build_against_the_facade(binaries):
+    """all six plugin sources compiled unchanged against include/compat/dj_brdf.h and linked with libdjb200.so"""
+    for p, (ref_bin, b200_bin) in binaries.items():
+        assert ref_bin.exists() and b200_bin.exists(), p
+        needed = subprocess.run(["readelf", "-d", str(b200_bin)], capture_output=True, text=True).stdout
+        assert "libdjb200.so" in needed, p
+        assert "libdjb200.so" not in subprocess.run(["readelf", "-d", str(ref_bin)], capture_output=True, text=True).stdout
+
+
+def test_reference_side_runs_and_b200_side_needs_a_gpu(djb, binaries, tmp_path):
+    rec = records(64, 900)
+    for p in ("dj_sgd", "dj_brdf"):
+        tag, lines, kw = configs(tmp_path)[p][0]
+        r, out = run(binaries[p][0], lines, records(64, 900, **kw), tmp_path, f"{p}_ref")
+        assert r.returncode == 0, r.stderr
+        assert np.isfinite(out[:, :4]).all() and (out[:, :3] >= 0).all()
+    if djb.device_count() == 0:  # no CPU fallback behind the facade
+        tag, lines, kw = configs(tmp_path)["dj_brdf"][0]
+        r, _ = run(binaries["dj_brdf"][1], lines, rec, tmp_path, "nogpu")
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plugin", PLUGINS)
+def test_plugin_matches_reference(binaries, tmp_path, plugin):
+    """eval / pdf / sample of the plugin: GPU-backed build against the reference build, record by record.
+    Bars: eval, pdf <= 1e-5 relative (the north star's bar; tables that come out of a fit <= 1e-4, its fit bar);
+    sampled directions bit-identical for >= 99 % of the records, the rest within 1e-3."""
+    n = 1500
+    for tag, lines, kw in configs(tmp_path)[plugin]:
+        rec = records(n, 901, **kw)
+        r0, want = run(binaries[plugin][0], lines, rec, tmp_path, f"{tag}_ref")
+        r1, got = run(binaries[plugin][1], lines, rec, tmp_path, f"{tag}_b200")
+        assert r0.returncode == 0, r0.stderr
+        assert r1.returncode == 0, r1.stderr
+        fitted = any(k in " ".join(lines) for k in ("merl", "utia", "merlID")) and plugin not in ("dj_utia",)
+        tol = 1e-4 if fitted else 1e-5
+        for name, sl in (("eval", slice(0, 3)), ("pdf", slice(3, 4))):
+            g, w = got[:, sl].astype(np.float64), want[:, sl].astype(np.float64)
+            assert np.array_equal(np.isnan(g), np.isnan(w)), (plugin, tag, name)
+            ok = ~np.isnan(w)
+            scale = np.maximum(np.abs(w[ok]), 1e-3 * max(1e-30, np.abs(w[ok]).max()))
+            err = np.abs(g[ok] - w[ok]) / scale
+            assert err.max() <= tol, (plugin, tag, name, float(err.max()))
+        # sampled direction, weight, pdf
+        same = (got[:, 7:10].view(np.uint32) == want[:, 7:10].view(np.uint32)).all(axis=1)
+        close = np.abs(got[:, 7:10] - want[:, 7:10]).max(axis=1) <= 1e-3
+        assert same.mean() >= (0.95 if fitted else 0.99) and close.mean() >= 0.995, (plugin, tag, float(same.mean()), float(close.mean()))
+        g, w = got[same][:, [4, 5, 6, 10]].astype(np.float64), want[same][:, [4, 5, 6, 10]].astype(np.float64)
+        fin = np.isfinite(w) & np.isfinite(g)
+        scale = np.maximum(np.abs(w[fin]), 1e-3 * max(1e-30, np.abs(w[fin]).max()))
+        assert (np.abs(g[fin] - w[fin]) / scale).max() <= 10 * tol, (plugin, tag, "sample weight / pdf")
