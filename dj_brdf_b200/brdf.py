@@ -269,6 +269,61 @@ class microfacet(brdf):
         return tuple(self._query(self._prefix + "evalp_is", u, o, 2, [3, 3, 1], user_param, per_pair))
 
 
+    # ---- LEAN-filtered shading, fused (mitsuba/dj_beckmannconductor.cpp:283-319, 338-366, 379-410) ----------------
+    @staticmethod
+    def _lean_cfg(alpha, n, bias, dmap_scale, lean_filtering, like):
+        cfg = capi.LeanShading()
+        cfg.bias, cfg.dmap_scale, cfg.lean_filtering = bias, dmap_scale, int(bool(lean_filtering))
+        if capi._is_torch(alpha) or np.ndim(alpha) == 2:
+            ba = Buf(alpha, np.float32)
+            if ba.n != 3 * n:
+                raise ValueError("per-pair roughness must be [n, 3] (alpha1, alpha2, alphaAngle)")
+            cfg.alpha_per_pair = 1
+            return cfg, ba
+        a = np.asarray(alpha, np.float32).reshape(3)
+        cfg.alpha_per_pair = 0
+        cfg.alpha[0], cfg.alpha[1], cfg.alpha[2] = float(a[0]), float(a[1]), float(a[2])
+        return cfg, Buf(None, np.float32)
+
+    @staticmethod
+    def lean_shading_params(E, alpha, bias=25.0, dmap_scale=1.0, lean_filtering=True):
+        """The params block the plugin builds per shading point: E [n, 5] LEAN texels (E1..E5 as fetched, still biased),
+        alpha = (alpha1, alpha2, alphaAngle) for all pairs or [n, 3] -> [n, 12]."""
+        bE = Buf(E, np.float32)
+        n = bE.n // 5
+        cfg, ba = microfacet._lean_cfg(alpha, n, bias, dmap_scale, lean_filtering, bE.keep)
+        mem = capi.same_space(bE, ba)
+        out = capi.empty_like_space(bE.keep, (n, 12), np.float32)
+        bo = Buf(out, np.float32, True)
+        check(capi.load().djb200_lean_shading_params(C.byref(cfg), ba.ptr, bE.ptr, C.c_int64(n), bo.ptr, C.c_int(mem),
+                                                     capi.current_stream_ptr(mem)))
+        return out
+
+    def _lean_query(self, fn, a, b, a_width, out_widths, E, alpha, bias, dmap_scale, lean_filtering):
+        ba_, bb, bE = Buf(a, np.float32), Buf(b, np.float32), Buf(E, np.float32)
+        n = bb.n // 3
+        if ba_.n != n * a_width or bE.n != 5 * n:
+            raise ValueError("input arrays disagree on the number of pairs")
+        cfg, balpha = microfacet._lean_cfg(alpha, n, bias, dmap_scale, lean_filtering, bb.keep)
+        mem = capi.same_space(ba_, bb, bE, balpha)
+        outs = [capi.empty_like_space(bb.keep, (n, w) if w > 1 else (n,), np.float32) for w in out_widths]
+        bouts = [Buf(x, np.float32, True) for x in outs]
+        d = self._desc()
+        check(getattr(capi.load(), fn)(C.byref(d), C.byref(cfg), balpha.ptr, bE.ptr, ba_.ptr, bb.ptr, C.c_int64(n),
+                                       *[x.ptr for x in bouts], C.c_int(mem), capi.current_stream_ptr(mem)))
+        return outs
+
+    def evalp_lean(self, i, o, E, alpha, bias=25.0, dmap_scale=1.0, lean_filtering=True):
+        return self._lean_query("djb200_lean_shading_evalp", i, o, 3, [3], E, alpha, bias, dmap_scale, lean_filtering)[0]
+
+    def pdf_lean(self, i, o, E, alpha, bias=25.0, dmap_scale=1.0, lean_filtering=True):
+        return self._lean_query("djb200_lean_shading_pdf", i, o, 3, [1], E, alpha, bias, dmap_scale, lean_filtering)[0]
+
+    def evalp_is_lean(self, u, o, E, alpha, bias=25.0, dmap_scale=1.0, lean_filtering=True):
+        return tuple(self._lean_query("djb200_lean_shading_evalp_is", u, o, 2, [3, 3, 1], E, alpha, bias, dmap_scale,
+                                      lean_filtering))
+
+
 class ggx(microfacet):
     _ndf = capi.NDF_GGX
 

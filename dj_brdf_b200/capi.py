@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "djb200_sgd_preset", "djb200_abc_preset", "djb200_preset_count", "djb200_sgd_preset_name", "djb200_abc_preset_name",
     "djb200_sgd_eval", "djb200_abc_eval",
     "djb200_nmap_to_leanmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
+    "djb200_lean_shading_params", "djb200_lean_shading_evalp", "djb200_lean_shading_pdf", "djb200_lean_shading_evalp_is",
     "djb200_fit_tabular", "djb200_fit_tabular_anisotropic",
     "djb200_tabular_create", "djb200_tabular_anisotropic_create", "djb200_tabular_anisotropic_sampling_tables", "djb200_tabular_destroy", "djb200_tabular_eval", "djb200_tabular_evalp", "djb200_tabular_pdf",
     "djb200_tabular_sample", "djb200_tabular_evalp_is",
@@ -67,6 +68,11 @@ class SgdData(C.Structure):
 class AbcData(C.Structure):
     _fields_ = [("kD", C.c_double * 3), ("A", C.c_double * 3), ("B", C.c_double), ("C", C.c_double),
                 ("ior", C.c_double)]
+
+
+class LeanShading(C.Structure):
+    _fields_ = [("bias", C.c_float), ("dmap_scale", C.c_float), ("lean_filtering", C.c_int32),
+                ("alpha_per_pair", C.c_int32), ("alpha", C.c_float * 3)]
 
 
 class Source(C.Structure):

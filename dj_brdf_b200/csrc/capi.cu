@@ -414,6 +414,105 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 	return rc;
 }
 
+// LEAN-filtered shading: per-pair params from the renderer's texture fetches, fused in front of the query
+// (op < 0: only the params construction).  Bulk arrays: E (n x 5), alpha (n x 3, optional), a, b, outputs.
+static djb200_status lean_shading_call(int op, const djb200_microfacet *mf, const djb200_lean_shading *cfg,
+                                       const float *alpha, const float *E, const float *a, const float *b, int64_t n,
+                                       float *out0, float *out1, float *out2, int mem, void *stream)
+{
+	if (!cfg) return fail(DJB200_ERR_INVALID_ARGUMENT, "lean shading descriptor is NULL");
+	if (!(cfg->dmap_scale >= 0.0f)) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid scale"); // DJB_ASSERT, dj_brdf.h:2022
+	if (!cfg->alpha_per_pair && !(cfg->alpha[0] > 0.0f && cfg->alpha[1] > 0.0f))
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid ellipse radii"); // DJB_ASSERT, dj_brdf.h:1453
+	if (n < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative pair count");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	if (op >= 0) {
+		if (!mf) return fail(DJB200_ERR_INVALID_ARGUMENT, "microfacet descriptor is NULL");
+		if (mf->ndf != DJB200_NDF_BECKMANN && mf->ndf != DJB200_NDF_GGX)
+			return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown ndf %d", mf->ndf);
+		if (mf->fresnel.kind < 0 || mf->fresnel.kind > DJB200_FRESNEL_SPLINE)
+			return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown fresnel kind %d", mf->fresnel.kind);
+		if (mf->fresnel.kind == DJB200_FRESNEL_SPLINE && (!mf->fresnel.points || mf->fresnel.n_points < 1))
+			return fail(DJB200_ERR_INVALID_ARGUMENT, "spline fresnel needs points");
+	}
+	if (n == 0) return DJB200_OK;
+	if (!E || (cfg->alpha_per_pair && !alpha)) return fail(DJB200_ERR_INVALID_ARGUMENT, "LEAN moment / roughness arrays are NULL");
+	if (op >= 0 && (!a || !b)) return fail(DJB200_ERR_INVALID_ARGUMENT, "direction arrays are NULL");
+	if (op != OP_EVALP_IS && !out0) return fail(DJB200_ERR_INVALID_ARGUMENT, "output array is NULL");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+
+	MfLaunch L;
+	memset(&L, 0, sizeof L);
+	L.op = op;
+	L.layout = PARAMS_LEAN_SHADING;
+	L.lean_bias = cfg->bias;
+	L.lean_dmap_scale = cfg->dmap_scale;
+	L.lean_filtering = cfg->lean_filtering;
+	memcpy(L.lean_alpha0, cfg->alpha, sizeof L.lean_alpha0);
+	if (op >= 0) {
+		L.ndf = mf->ndf;
+		L.shadow = mf->shadow;
+		L.fresnel_kind = mf->fresnel.kind;
+		memcpy(L.fv, mf->fresnel.v, sizeof L.fv);
+	}
+	const bool uses_u = (op == OP_SAMPLE || op == OP_EVALP_IS);
+	const size_t out0_item = op < 0 ? 48 : (op == OP_PDF ? 4 : 12);
+
+	std::vector<BulkIn> ins = {{E, 20}};
+	int slot_alpha = -1, slot_a = -1, slot_b = -1;
+	if (cfg->alpha_per_pair) { slot_alpha = (int)ins.size(); ins.push_back({alpha, 12}); }
+	if (op >= 0) {
+		slot_a = (int)ins.size(); ins.push_back({a, uses_u ? (size_t)8 : (size_t)12});
+		slot_b = (int)ins.size(); ins.push_back({b, 12});
+	}
+	std::vector<BulkOut> outs;
+	int slot0 = -1, slot1 = -1, slot2 = -1;
+	if (out0) { slot0 = (int)outs.size(); outs.push_back({out0, out0_item}); }
+	if (out1) { slot1 = (int)outs.size(); outs.push_back({out1, 12}); }
+	if (out2) { slot2 = (int)outs.size(); outs.push_back({out2, 4}); }
+
+	void *d_spline = nullptr;
+	const bool spline = op >= 0 && L.fresnel_kind == DJB200_FRESNEL_SPLINE;
+	if (spline) { // small descriptor: a plain device allocation for the duration of the call
+		const size_t bytes = sizeof(float) * 3 * (size_t)mf->fresnel.n_points;
+		CU(cudaMalloc(&d_spline, bytes));
+		cudaError_t e = cudaMemcpy(d_spline, mf->fresnel.points, bytes, cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) { cudaFree(d_spline); return cuda_fail(e, "fresnel spline upload"); }
+		L.spline_pts = (const float *)d_spline;
+		L.spline_n = mf->fresnel.n_points;
+	}
+	auto body = [&](const std::vector<void *> &din, const std::vector<void *> &dout, int64_t cn, cudaStream_t st) {
+		MfLaunch C = L;
+		C.lean_E = (const float *)din[0];
+		C.lean_alpha = slot_alpha >= 0 ? (const float *)din[slot_alpha] : nullptr;
+		C.n = cn;
+		C.n_params = cn;
+		C.out_stride = cn;
+		if (op < 0) return launch_lean_shading_params(C, (float *)dout[slot0], st);
+		C.a = (const float *)din[slot_a];
+		C.b = (const float *)din[slot_b];
+		C.out0 = slot0 >= 0 ? (float *)dout[slot0] : nullptr;
+		C.out1 = slot1 >= 0 ? (float *)dout[slot1] : nullptr;
+		C.out2 = slot2 >= 0 ? (float *)dout[slot2] : nullptr;
+		return launch_microfacet(C, st);
+	};
+	djb200_status rc;
+	if (mem == DJB200_MEM_DEVICE) {
+		std::vector<void *> din, dout;
+		for (auto &i : ins) din.push_back(const_cast<void *>(i.host));
+		for (auto &o : outs) dout.push_back(o.host);
+		cudaError_t e = body(din, dout, n, (cudaStream_t)stream);
+		if (e == cudaSuccess && spline) e = cudaStreamSynchronize((cudaStream_t)stream); // the spline copy is freed below
+		rc = e == cudaSuccess ? DJB200_OK : cuda_fail(e, "lean shading launch");
+	} else {
+		rc = host_pipeline(n, ins, outs, 1, body);
+	}
+	if (d_spline) cudaFree(d_spline);
+	return rc;
+}
+
 // generic "n items in, n items out" call used by the table / frame / LEAN entry points
 template <class Body>
 static djb200_status map_call(int64_t n, const std::vector<BulkIn> &ins, const std::vector<BulkOut> &outs, int mem,
@@ -896,6 +995,30 @@ djb200_status djb200_abc_eval(const djb200_abc_data *material, const float *wi, 
 			return launch_analytic_eval(DJB200_SOURCE_ABC, m, 9, (const float *)i[0], (const float *)i[1], cn,
 			                            (float *)o[0], st);
 		});
+}
+
+djb200_status djb200_lean_shading_params(const djb200_lean_shading *cfg, const float *alpha, const float *E, int64_t n,
+                                         djb200_params *out, int mem, void *stream)
+{
+	return lean_shading_call(-1, nullptr, cfg, alpha, E, nullptr, nullptr, n, (float *)out, nullptr, nullptr, mem, stream);
+}
+djb200_status djb200_lean_shading_evalp(const djb200_microfacet *mf, const djb200_lean_shading *cfg, const float *alpha,
+                                        const float *E, const float *wi, const float *wo, int64_t n, float *out_rgb, int mem,
+                                        void *stream)
+{
+	return lean_shading_call(OP_EVALP, mf, cfg, alpha, E, wi, wo, n, out_rgb, nullptr, nullptr, mem, stream);
+}
+djb200_status djb200_lean_shading_pdf(const djb200_microfacet *mf, const djb200_lean_shading *cfg, const float *alpha,
+                                      const float *E, const float *wi, const float *wo, int64_t n, float *out_pdf, int mem,
+                                      void *stream)
+{
+	return lean_shading_call(OP_PDF, mf, cfg, alpha, E, wi, wo, n, out_pdf, nullptr, nullptr, mem, stream);
+}
+djb200_status djb200_lean_shading_evalp_is(const djb200_microfacet *mf, const djb200_lean_shading *cfg, const float *alpha,
+                                           const float *E, const float *u, const float *wo, int64_t n,
+                                           float *out_weight_rgb, float *out_wi, float *out_pdf, int mem, void *stream)
+{
+	return lean_shading_call(OP_EVALP_IS, mf, cfg, alpha, E, u, wo, n, out_weight_rgb, out_wi, out_pdf, mem, stream);
 }
 
 djb200_status djb200_lrep_to_params(const float *E, int64_t n, djb200_params *out, int mem, void *stream)

@@ -523,6 +523,29 @@ DJB_DEV void params_from_pdf(float ax, float ay, float rho, float tx, float ty, 
 	p.nz = n.z;
 }
 
+// params::elliptic on the device, dj_brdf.h:1355-1376, 1422-1426, 1451-1459 (same rounding points as capi.cu's elliptic_h)
+DJB_DEV void params_elliptic_dev(float a1, float a2, float phi, Params &p)
+{
+	double sd, cd;
+	sincos((double)phi, &sd, &cd);
+	const float c = (float)cd, s = (float)sd;
+	const float c2 = (float)(2.0 * (double)c * (double)c - 1.0);
+	const float q1 = a1 * a1, q2 = a2 * a2, t1 = q1 + q2, t2 = q1 - q2;
+	p.a1 = a1;
+	p.a2 = a2;
+	p.phi_a = phi;
+	p.ax = (float)sqrt(0.5 * (double)(t1 + t2 * c2));
+	p.ay = (float)sqrt(0.5 * (double)(t1 - t2 * c2));
+	p.rho = (q2 - q1) * c * s / (p.ax * p.ay);
+	p.srho = (float)sqrt(1.0 - (double)(p.rho * p.rho));
+	p.tx = 0.0f;
+	p.ty = 0.0f;
+	const V3 n = normalize(mk(-0.0f, -0.0f, 1.0f));
+	p.nx = n.x;
+	p.ny = n.y;
+	p.nz = n.z;
+}
+
 // beckmann::lrep_to_params, :1976-1990
 DJB_DEV void lrep_to_params(float E1, float E2, float E3, float E4, float E5, Params &p)
 {
@@ -534,6 +557,36 @@ DJB_DEV void lrep_to_params(float E1, float E2, float E3, float E4, float E5, Pa
 	float rho = 2.0f * (E5 - E1 * E2) / (ax * ay);
 	rho = fmin_ref(0.99f, fmax_ref(-0.99f, rho));
 	params_from_pdf(ax, ay, rho, E1, E2, p);
+}
+
+// The per-shading-point parameter construction of the LEAN-filtering plugin (mitsuba/dj_beckmannconductor.cpp:283-314):
+// base roughness ellipse -> params -> lrep; LEAN texel (E1..E5, biased) -> lrep, scaled by dmapscale; sum; -> params.
+struct LeanShadingCfg {
+	float bias, dmap_scale;
+	int lean_filtering;
+};
+DJB_DEV void lean_shading_params(const LeanShadingCfg &c, float a1, float a2, float phi, float E1, float E2, float E3, float E4,
+                                 float E5, Params &out)
+{
+	Params base;
+	params_elliptic_dev(a1, a2, phi, base);
+	E1 -= c.bias;
+	E2 -= c.bias;
+	E5 -= c.bias * c.bias;
+	if (!c.lean_filtering) { // naive MIP mapping: second moments rebuilt from the filtered means
+		E3 = E1 * E1;
+		E4 = E2 * E2;
+		E5 = E1 * E2;
+	}
+	const float sc = c.dmap_scale, sc2 = sc * sc; // lrep::operator*=, dj_brdf.h:2020-2031
+	E1 *= sc; E2 *= sc; E3 *= sc2; E4 *= sc2; E5 *= sc2;
+	// params_to_lrep(base), dj_brdf.h:1965-1974
+	const float r1 = base.tx, r2 = base.ty;
+	const float r3 = 0.5f * base.ax * base.ax + base.tx * base.tx;
+	const float r4 = 0.5f * base.ay * base.ay + base.ty * base.ty;
+	const float r5 = 0.5f * base.rho * base.ax * base.ay + base.tx * base.ty;
+	// lrep1 + lrep2, dj_brdf.h:1992-1999
+	lrep_to_params(E1 + r1, E2 + r2, E3 + r3 + 2.0f * E1 * r1, E4 + r4 + 2.0f * E2 * r2, E5 + r5 + E1 * r2 + E2 * r1, out);
 }
 
 // ---- MERL index arithmetic, :906-957 (IEEE double mul/div/sqrt + truncation: bit exact) ---------

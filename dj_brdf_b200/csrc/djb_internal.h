@@ -38,6 +38,7 @@ djb200_status fail(djb200_status s, const char *fmt, ...);
 djb200_status cuda_fail(cudaError_t e, const char *what);
 djb200_status require_device();
 
+constexpr int PARAMS_LEAN_SHADING = 2; // third params layout, only reachable through djb200_lean_shading_*
 enum MfOp { OP_EVAL = 0, OP_EVALP = 1, OP_PDF = 2, OP_SAMPLE = 3, OP_EVALP_IS = 4 };
 
 // One launch of a microfacet query over device-resident arrays.
@@ -48,7 +49,13 @@ struct MfLaunch {
 	int spline_n;
 	const void *params;      // device, djb200_params blocks
 	int64_t n_params;
-	int layout;              // djb200_params_layout
+	int layout;              // djb200_params_layout, or PARAMS_LEAN_SHADING (internal)
+	// PARAMS_LEAN_SHADING: params are built per pair from the renderer's texture fetches (kernels_mf.cu)
+	const float *lean_E;     // device, n x 5 LEAN moments
+	const float *lean_alpha; // device, n x 3 (alpha1, alpha2, alphaAngle), or NULL: lean_alpha0 for every pair
+	float lean_alpha0[3];
+	float lean_bias, lean_dmap_scale;
+	int lean_filtering;
 	const float *a;          // wi (eval/evalp/pdf) or u (sample/evalp_is)
 	const float *b;          // wo
 	int64_t n;               // pairs in this launch
@@ -61,6 +68,8 @@ extern std::atomic<int> g_force_generic; // kernels_mf.cu: 1 = never take the le
 int sm_count();
 
 cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st);
+// only the per-pair params construction of PARAMS_LEAN_SHADING; params_out: device, n x 12 floats
+cudaError_t launch_lean_shading_params(const MfLaunch &L, float *params_out, cudaStream_t st);
 // djb::tabular as a BRDF (kernels_tabular.cu); tables: device, p22[res] | sigma[res] | qf[res] | fresnel[res][3]
 cudaError_t launch_tabular_query(const float *tables, int res, const MfLaunch &L, cudaStream_t st);
 // djb::tabular_anisotropic as a BRDF (eval / evalp / pdf); tables: device, p22[er * ar] | sigma[er * ar] | fresnel[er][3]

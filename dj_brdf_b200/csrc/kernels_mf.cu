@@ -7,6 +7,7 @@
 // The kernel is bound by FP64 issue, not by HBM (DESIGN.md "Rooflines"): matching the reference to
 // the bit needs IEEE double sqrt/div/exp at its rounding points.
 #include <cstdlib>
+#include <cstring>
 
 #include "djb_internal.h"
 #include "djb_lean.cuh"
@@ -27,7 +28,38 @@ struct MfKernelArgs {
 	const float *a, *b;
 	long long n, out_stride;
 	float *out0, *out1, *out2;
+	// PSRC_LEAN: per-pair params from LEAN texels + base roughness (mitsuba/dj_beckmannconductor.cpp:283-314)
+	const float *lean_E, *lean_alpha;
+	float lean_alpha0[3];
+	LeanShadingCfg lean_cfg;
+	float *params_out; // optional: the constructed blocks (djb200_lean_shading_params)
 };
+
+// where a thread's params block comes from
+enum { PSRC_BROADCAST = 0, PSRC_PER_PAIR = 1, PSRC_LEAN = 2 };
+
+template <int PSRC>
+DJB_DEV Params pair_params(const MfKernelArgs &A, long long k)
+{
+	Params p;
+	if (PSRC == PSRC_PER_PAIR) {
+		const float4 *pp = reinterpret_cast<const float4 *>(A.params + k); // 48 B blocks: 16-B aligned
+		const float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
+		p.nx = q0.x; p.ny = q0.y; p.nz = q0.z; p.a1 = q0.w;
+		p.a2 = q1.x; p.phi_a = q1.y; p.ax = q1.z; p.ay = q1.w;
+		p.rho = q2.x; p.srho = q2.y; p.tx = q2.z; p.ty = q2.w;
+	} else {
+		float a1 = A.lean_alpha0[0], a2 = A.lean_alpha0[1], phi = A.lean_alpha0[2];
+		if (A.lean_alpha) {
+			a1 = A.lean_alpha[3 * k];
+			a2 = A.lean_alpha[3 * k + 1];
+			phi = A.lean_alpha[3 * k + 2];
+		}
+		const float *E = A.lean_E + 5 * k;
+		lean_shading_params(A.lean_cfg, a1, a2, phi, E[0], E[1], E[2], E[3], E[4], p);
+	}
+	return p;
+}
 
 // evalp with a run-time Fresnel kind (uniform across the grid, so the switch never diverges)
 template <int NDF>
@@ -146,10 +178,11 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 
 // The lean FP32 path (djb_lean.cuh) for an ideal or Schlick Fresnel term, every query, both params layouts.
 // Same results as the mirrored kernels below (tests compare the two at full size), about half the instructions.
-template <int NDF, int FK, int OP, bool PERPAIR>
+template <int NDF, int FK, int OP, int PSRC>
 __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 {
 	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
+	constexpr bool PERPAIR = PSRC != PSRC_BROADCAST;
 	__shared__ ParamsX s_params[PERPAIR ? 1 : MF_MAX_SMEM_PARAMS];
 	__shared__ float2 s_exp2[64]; // 2^(j/64) as float-float, for the Beckmann exponentials
 	__shared__ float4 s_log[128]; // logarithm table of the Beckmann sampling path
@@ -189,13 +222,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 			}
 		};
 		if (PERPAIR) {
-			const float4 *pp = reinterpret_cast<const float4 *>(A.params + k); // 48 B blocks: 16-B aligned
-			const float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
-			Params p;
-			p.nx = q0.x; p.ny = q0.y; p.nz = q0.z; p.a1 = q0.w;
-			p.a2 = q1.x; p.phi_a = q1.y; p.ax = q1.z; p.ay = q1.w;
-			p.rho = q2.x; p.srho = q2.y; p.tx = q2.z; p.ty = q2.w;
-			one(extend_params(p), k);
+			one(extend_params(pair_params<PERPAIR ? PSRC : PSRC_PER_PAIR>(A, k)), k);
 		} else {
 			for (int m = 0; m < A.n_params; ++m) one(s_params[m], (long long)m * A.out_stride + k);
 		}
@@ -203,7 +230,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 }
 
 // PER_PAIR layout: pair k under params block k (roughness from textures at every shading point).
-template <int NDF, int OP>
+template <int NDF, int OP, int PSRC>
 __global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
 {
 	__shared__ float s_spline[3 * MF_MAX_SMEM_SPLINE];
@@ -218,32 +245,39 @@ __global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
 		V3 va, o, h;
 		float inv_iz;
 		load_pair<NDF, OP>(A, k, va, o, h, inv_iz);
-		const float4 *pp = reinterpret_cast<const float4 *>(A.params + k); // 48 B blocks: 16-B aligned
-		float4 q0 = pp[0], q1 = pp[1], q2 = pp[2];
-		Params p;
-		p.nx = q0.x; p.ny = q0.y; p.nz = q0.z; p.a1 = q0.w;
-		p.a2 = q1.x; p.phi_a = q1.y; p.ax = q1.z; p.ay = q1.w;
-		p.rho = q2.x; p.srho = q2.y; p.tx = q2.z; p.ty = q2.w;
-		mf_query<NDF, OP>(A, fr, p, k, va, o, h, inv_iz);
+		mf_query<NDF, OP>(A, fr, pair_params<PSRC>(A, k), k, va, o, h, inv_iz);
 	}
 }
 
-template <int NDF, int FK, int OP, bool PERPAIR>
+// the per-pair construction alone (djb200_lean_shading_params): what the plugin computes before every query
+__global__ void __launch_bounds__(MF_THREADS) lean_shading_params_kernel(MfKernelArgs A)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		const Params p = pair_params<PSRC_LEAN>(A, k);
+		float4 *o = reinterpret_cast<float4 *>(A.params_out + 12 * k);
+		o[0] = make_float4(p.nx, p.ny, p.nz, p.a1);
+		o[1] = make_float4(p.a2, p.phi_a, p.ax, p.ay);
+		o[2] = make_float4(p.rho, p.srho, p.tx, p.ty);
+	}
+}
+
+template <int NDF, int FK, int OP, int PSRC>
 static int lean_grid_cap()
 {
 	static int resident = 0;
 	if (!resident) {
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_lean_kernel<NDF, FK, OP, PERPAIR>, MF_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_lean_kernel<NDF, FK, OP, PSRC>, MF_THREADS, 0);
 		if (resident < 1) resident = 1;
 	}
 	return sm_count() * resident;
 }
 
-template <int NDF, int FK, int OP, bool PERPAIR>
+template <int NDF, int FK, int OP, int PSRC>
 static void launch_lean(const MfKernelArgs &A, long long want, cudaStream_t st)
 {
-	const long long cap = lean_grid_cap<NDF, FK, OP, PERPAIR>();
-	mf_lean_kernel<NDF, FK, OP, PERPAIR><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
+	const long long cap = lean_grid_cap<NDF, FK, OP, PSRC>();
+	mf_lean_kernel<NDF, FK, OP, PSRC><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
 }
 
 template <int NDF, int OP>
@@ -259,6 +293,13 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 	A.b = L.b;
 	A.n = L.n;
 	A.out_stride = L.out_stride;
+	A.lean_E = L.lean_E;
+	A.lean_alpha = L.lean_alpha;
+	for (int k = 0; k < 3; ++k) A.lean_alpha0[k] = L.lean_alpha0[k];
+	A.lean_cfg.bias = L.lean_bias;
+	A.lean_cfg.dmap_scale = L.lean_dmap_scale;
+	A.lean_cfg.lean_filtering = L.lean_filtering;
+	A.params_out = nullptr;
 	if (L.n <= 0) return cudaSuccess;
 
 	// persistent grid-stride launch: a whole number of waves (SM count x resident CTAs per SM)
@@ -266,11 +307,11 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 	static int resident_bc = 0, resident_pp = 0;
 	if (!resident_bc) {
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_bc, mf_broadcast_kernel<NDF, OP>, MF_THREADS, 0);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_pp, mf_perpair_kernel<NDF, OP>, MF_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_pp, mf_perpair_kernel<NDF, OP, PSRC_LEAN>, MF_THREADS, 0);
 		if (resident_bc < 1) resident_bc = 1;
 		if (resident_pp < 1) resident_pp = 1;
 	}
-	const long long cap = (long long)sm_count() * (L.layout == DJB200_PARAMS_PER_PAIR ? resident_pp : resident_bc);
+	const long long cap = (long long)sm_count() * (L.layout != DJB200_PARAMS_BROADCAST ? resident_pp : resident_bc);
 	const int grid = (int)(want < cap ? want : cap);
 	// djb200_debug_force_generic(1) (or DJB200_MF_GENERIC=1) runs the mirrored-rounding kernels everywhere: A/B tests
 	const bool force_generic = g_force_generic.load(std::memory_order_relaxed) != 0;
@@ -282,9 +323,19 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		A.params = reinterpret_cast<const Params *>(L.params);
 		A.n_params = 1;
 		A.out0 = L.out0; A.out1 = L.out1; A.out2 = L.out2;
-		if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, true>(A, want, st);
-		else if (lean) launch_lean<NDF, FK_IDEAL, OP, true>(A, want, st);
-		else mf_perpair_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, PSRC_PER_PAIR>(A, want, st);
+		else if (lean) launch_lean<NDF, FK_IDEAL, OP, PSRC_PER_PAIR>(A, want, st);
+		else mf_perpair_kernel<NDF, OP, PSRC_PER_PAIR><<<grid, MF_THREADS, 0, st>>>(A);
+		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+		return cudaGetLastError();
+	}
+	if (L.layout == PARAMS_LEAN_SHADING) { // params built per pair from LEAN texels, fused in front of the query
+		A.params = nullptr;
+		A.n_params = 1;
+		A.out0 = L.out0; A.out1 = L.out1; A.out2 = L.out2;
+		if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, PSRC_LEAN>(A, want, st);
+		else if (lean) launch_lean<NDF, FK_IDEAL, OP, PSRC_LEAN>(A, want, st);
+		else mf_perpair_kernel<NDF, OP, PSRC_LEAN><<<grid, MF_THREADS, 0, st>>>(A);
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 		return cudaGetLastError();
 	}
@@ -319,6 +370,25 @@ static cudaError_t launch_N(const MfLaunch &L, cudaStream_t st)
 	case OP_EVALP_IS: return launch_T<NDF, OP_EVALP_IS>(L, st);
 	}
 	return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_lean_shading_params(const MfLaunch &L, float *params_out, cudaStream_t st)
+{
+	if (L.n <= 0) return cudaSuccess;
+	MfKernelArgs A;
+	memset(&A, 0, sizeof A);
+	A.n = L.n;
+	A.lean_E = L.lean_E;
+	A.lean_alpha = L.lean_alpha;
+	for (int k = 0; k < 3; ++k) A.lean_alpha0[k] = L.lean_alpha0[k];
+	A.lean_cfg.bias = L.lean_bias;
+	A.lean_cfg.dmap_scale = L.lean_dmap_scale;
+	A.lean_cfg.lean_filtering = L.lean_filtering;
+	A.params_out = params_out;
+	const long long want = (L.n + MF_THREADS - 1) / MF_THREADS, cap = (long long)sm_count() * 8;
+	lean_shading_params_kernel<<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st)

@@ -218,6 +218,36 @@ DJB200_API djb200_status djb200_params_to_lrep(const djb200_params *params, int6
 DJB200_API djb200_status djb200_leanmap_to_params(const float *lean1, const float *lean2, int32_t w, int32_t h,
                                                   float bias, djb200_params *out, int mem, void *stream);
 
+/* LEAN-filtered shading, fused: what mitsuba/dj_beckmannconductor.cpp does on the CPU before EVERY query (:283-314 in
+ * eval, :338-366 in pdf, :379-400 in sample) -- base roughness ellipse -> params -> lrep; LEAN texel (E1..E5 as fetched
+ * from leanmap1.rg / leanmap2.rgb, still biased) -> lrep, scaled by dmapscale; lrep sum -> params -- done per pair on the
+ * device in front of evalp / pdf / evalp_is, so that neither the 48-byte params blocks nor the intermediate lreps ever
+ * touch memory.  Per pair the kernel reads 20 B of moments (+ 12 B of roughness when it is textured) next to the
+ * directions. */
+typedef struct djb200_lean_shading {
+	float bias;             /* BIAS of utils/nmap2leanmap_biased.cpp:11 (25 in the plugin, :300): E1 -= b, E2 -= b, E5 -= b*b */
+	float dmap_scale;       /* lrep1 *= dmapscale (:312); >= 0 */
+	int32_t lean_filtering; /* 1: LEAN filtering (:307), 0: naive MIP mapping, second moments rebuilt from the means (:309) */
+	int32_t alpha_per_pair; /* 0: every pair uses alpha[3] below; 1: the `alpha` bulk array holds n x (alpha1, alpha2, alphaAngle) */
+	float alpha[3];         /* (alpha1, alpha2, alphaAngle in radians) of params::elliptic (:290-294) */
+} djb200_lean_shading;
+/* only the parameter construction: out = n params blocks (what the plugin hands to evalp as user_param) */
+DJB200_API djb200_status djb200_lean_shading_params(const djb200_lean_shading *cfg, const float *alpha, const float *E,
+                                                    int64_t n, djb200_params *out, int mem, void *stream);
+/* m_brdf->evalp(i, o, &params) of dj_beckmannconductor.cpp:316-319 with the construction fused in */
+DJB200_API djb200_status djb200_lean_shading_evalp(const djb200_microfacet *mf, const djb200_lean_shading *cfg,
+                                                   const float *alpha, const float *E, const float *wi, const float *wo,
+                                                   int64_t n, float *out_rgb, int mem, void *stream);
+/* m_brdf->pdf(i, o, &params), dj_beckmannconductor.cpp:362-364 */
+DJB200_API djb200_status djb200_lean_shading_pdf(const djb200_microfacet *mf, const djb200_lean_shading *cfg,
+                                                 const float *alpha, const float *E, const float *wi, const float *wo,
+                                                 int64_t n, float *out_pdf, int mem, void *stream);
+/* m_brdf->evalp_is(u1, u2, o, &i, &pdf, &params), dj_beckmannconductor.cpp:402-410; outputs as djb200_microfacet_evalp_is */
+DJB200_API djb200_status djb200_lean_shading_evalp_is(const djb200_microfacet *mf, const djb200_lean_shading *cfg,
+                                                      const float *alpha, const float *E, const float *u, const float *wo,
+                                                      int64_t n, float *out_weight_rgb, float *out_wi, float *out_pdf,
+                                                      int mem, void *stream);
+
 /* ---- fits ("power iterations") ----------------------------------------------------------- */
 /* What a fit reads from its source BRDF: a MERL/UTIA table on the device, or an analytic
  * microfacet BRDF.  (The reference takes any `const brdf&`, dj_brdf.h:401, 441.) */

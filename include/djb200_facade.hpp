@@ -372,6 +372,48 @@ public:
 		         out_i ? &out_i->x : NULL, out_pdf, where, stream);
 	}
 
+	// LEAN-filtered shading, wavefront style (added): what mitsuba/dj_beckmannconductor.cpp:283-319, 338-366, 379-410 do
+	// per shading point -- (alpha1, alpha2, alphaAngle) and the LEAN texel E1..E5 -> params -> query -- for n points in one
+	// fused device pass.  E5: n x 5 moments as fetched from the two LEAN maps (still biased); alpha3: n x 3 when the
+	// roughness is textured, else NULL and cfg.alpha applies to every point.
+	static djb200_lean_shading lean_config(float_t alpha1, float_t alpha2, float_t alpha_angle, float_t bias = 25,
+	                                       float_t dmap_scale = 1, bool lean_filtering = true)
+	{
+		djb200_lean_shading c;
+		c.bias = bias; c.dmap_scale = dmap_scale; c.lean_filtering = lean_filtering ? 1 : 0; c.alpha_per_pair = 0;
+		c.alpha[0] = alpha1; c.alpha[1] = alpha2; c.alpha[2] = alpha_angle;
+		return c;
+	}
+	static void lean_params_batch(djb200_lean_shading cfg, const float_t *alpha3, const float_t *E5, size_t n, params *out,
+	                              memory_space where = host, void *stream = NULL)
+	{
+		cfg.alpha_per_pair = alpha3 ? 1 : 0;
+		detail::check(djb200_lean_shading_params(&cfg, alpha3, E5, (int64_t)n, const_cast<djb200_params *>(out->raw()), where, stream));
+	}
+	void evalp_lean_batch(djb200_lean_shading cfg, const float_t *alpha3, const float_t *E5, const vec3 *i, const vec3 *o,
+	                      size_t n, vec3 *out, memory_space where = host, void *stream = NULL) const
+	{
+		cfg.alpha_per_pair = alpha3 ? 1 : 0;
+		djb200_microfacet d = describe();
+		detail::check(djb200_lean_shading_evalp(&d, &cfg, alpha3, E5, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
+	}
+	void pdf_lean_batch(djb200_lean_shading cfg, const float_t *alpha3, const float_t *E5, const vec3 *i, const vec3 *o,
+	                    size_t n, float_t *out, memory_space where = host, void *stream = NULL) const
+	{
+		cfg.alpha_per_pair = alpha3 ? 1 : 0;
+		djb200_microfacet d = describe();
+		detail::check(djb200_lean_shading_pdf(&d, &cfg, alpha3, E5, &i->x, &o->x, (int64_t)n, out, where, stream));
+	}
+	void evalp_is_lean_batch(djb200_lean_shading cfg, const float_t *alpha3, const float_t *E5, const float_t *u12,
+	                         const vec3 *o, size_t n, vec3 *out_weight, vec3 *out_i, float_t *out_pdf,
+	                         memory_space where = host, void *stream = NULL) const
+	{
+		cfg.alpha_per_pair = alpha3 ? 1 : 0;
+		djb200_microfacet d = describe();
+		detail::check(djb200_lean_shading_evalp_is(&d, &cfg, alpha3, E5, u12, &o->x, (int64_t)n, out_weight ? &out_weight->x : NULL,
+		                                           out_i ? &out_i->x : NULL, out_pdf, where, stream));
+	}
+
 	virtual bool supports_smith_vndf_sampling() const = 0;
 	void set_shadow(bool shadow) { m_shadow = shadow; ++m_fresnel_rev; }
 	void set_fresnel(const fresnel::impl &f)

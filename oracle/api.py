@@ -261,6 +261,15 @@ class PortOracle:
         self.lib.orc_params_to_lrep(c_f32p(params.ctypes.data), i64(len(params)), c_f32p(out.ctypes.data))
         return out
 
+    def lean_shading_params(self, E5, alpha, bias=25.0, dmap_scale=1.0, lean_filtering=True):
+        """mitsuba/dj_beckmannconductor.cpp:283-314 per pair; alpha: 3 floats or [n, 3]."""
+        E5, alpha = _f32(E5).reshape(-1, 5), _f32(alpha)
+        out = np.zeros((len(E5), 12), np.float32)
+        self.lib.orc_lean_shading_params(C.c_float(bias), C.c_float(dmap_scale), C.c_int(int(lean_filtering)),
+                                         C.c_int(int(alpha.ndim == 2)), c_f32p(alpha.ctypes.data), c_f32p(E5.ctypes.data),
+                                         i64(len(E5)), c_f32p(out.ctypes.data))
+        return out
+
     def nmap2leanmap(self, nmap_planar, base_roughness=1e-5, bias=0.0):
         nmap = np.ascontiguousarray(nmap_planar, dtype=np.uint8)
         _, h, w = nmap.shape
@@ -550,6 +559,14 @@ class RefOracle:
         params = _f32(params).reshape(-1, 12)
         out = np.empty((len(params), 5), np.float32)
         self.lib.ref_params_to_lrep(c_f32p(params.ctypes.data), i64(len(params)), c_f32p(out.ctypes.data))
+        return out
+
+    def lean_shading_params(self, E5, alpha, bias=25.0, dmap_scale=1.0, lean_filtering=True):
+        E5, alpha = _f32(E5).reshape(-1, 5), _f32(alpha)
+        out = np.zeros((len(E5), 12), np.float32)
+        self.lib.ref_lean_shading_params(C.c_float(bias), C.c_float(dmap_scale), C.c_int(int(lean_filtering)),
+                                         C.c_int(int(alpha.ndim == 2)), c_f32p(alpha.ctypes.data), c_f32p(E5.ctypes.data),
+                                         i64(len(E5)), c_f32p(out.ctypes.data))
         return out
 
     def nmap2leanmap(self, nmap_planar, base_roughness=1e-5, bias=0.0, run_check=False):

@@ -1037,6 +1037,37 @@ ORC_API void orc_params_to_lrep(const orc_params *p, int64_t n, float *E5) /* :1
 	}
 }
 
+/* The per-shading-point parameter construction of mitsuba/dj_beckmannconductor.cpp:283-314 (the same block is repeated
+ * in pdf, :338-361, and sample, :379-400): params::elliptic(alpha1, alpha2, alphaAngle); the LEAN texel (E1..E5) minus
+ * its bias, as a lrep (or, without LEAN filtering, the lrep rebuilt from the means); lrep1 *= dmapscale (:2020-2031);
+ * params_to_lrep(params) (:1965-1974); lrep1 + lrep2 (:1992-1999); lrep_to_params (:1976-1990).
+ * alpha: n x 3 when alpha_per_pair, else 3 floats. */
+ORC_API void orc_lean_shading_params(float bias, float dmap_scale, int lean_filtering, int alpha_per_pair,
+                                     const float *alpha, const float *E5, int64_t n, orc_params *out)
+{
+	for (int64_t k = 0; k < n; ++k) {
+		const float *a = alpha + (alpha_per_pair ? 3 * k : 0), *E = E5 + 5 * k;
+		orc_params base;
+		orc_params_elliptic(a[0], a[1], a[2], &base);
+		float E1 = E[0], E2 = E[1], E3 = E[2], E4 = E[3], E5v = E[4];
+		E1 -= bias;
+		E2 -= bias;
+		E5v -= bias * bias;
+		if (!lean_filtering) { E3 = E1 * E1; E4 = E2 * E2; E5v = E1 * E2; }
+		float sc2 = dmap_scale * dmap_scale;
+		E1 *= dmap_scale; E2 *= dmap_scale; E3 *= sc2; E4 *= sc2; E5v *= sc2;
+		float r[5], s[5];
+		orc_params_to_lrep(&base, 1, r);
+		s[0] = E1 + r[0];
+		s[1] = E2 + r[1];
+		s[2] = E3 + r[2] + 2.0f * E1 * r[0];
+		s[3] = E4 + r[3] + 2.0f * E2 * r[1];
+		s[4] = E5v + r[4] + E1 * r[1] + E2 * r[0];
+		orc_lrep_to_params(s, 1, out + k);
+	}
+}
+
+
 /* utils/nmap2leanmap.cpp:18-54 (bias == 0) and nmap2leanmap_biased.cpp:23-63 (bias == 25).
  * Planar layout c*W*H + y*W + x on both sides (CImg.h:10146-10149). */
 ORC_API void orc_nmap2leanmap(const uint8_t *nmap, int w, int h, float base_roughness, float bias,

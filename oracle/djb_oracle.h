@@ -85,6 +85,9 @@ void orc_abc_eval(const orc_abc *m, const float *wi, const float *wo, int64_t n,
 /* LEAN (dj_brdf.h:1965-1990; utils/nmap2leanmap.cpp:18-54; nmap2leanmap_biased.cpp:23-63) */
 void orc_lrep_to_params(const float *E5, int64_t n, orc_params *out);
 void orc_params_to_lrep(const orc_params *p, int64_t n, float *E5);
+/* per-shading-point params of the LEAN-filtering plugin (mitsuba/dj_beckmannconductor.cpp:283-314) */
+void orc_lean_shading_params(float bias, float dmap_scale, int lean_filtering, int alpha_per_pair, const float *alpha,
+                             const float *E5, int64_t n, orc_params *out);
 void orc_nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float base_roughness, float bias,
                       float *lean1_planar_rgba, float *lean2_planar_rgba);
 

@@ -261,6 +261,29 @@ REF_API void ref_params_to_lrep(const float *params12, int64_t n, float *E5)
 	}
 }
 
+// The statements of mitsuba/dj_beckmannconductor.cpp:283-314 on the reference's own classes (Float = float,
+// BIAS = 25 there; a parameter here so that unbiased maps can be checked too).
+REF_API void ref_lean_shading_params(float bias, float dmap_scale, int lean_filtering, int alpha_per_pair,
+                                     const float *alpha, const float *E5, int64_t n, float *out12)
+{
+	for (int64_t k = 0; k < n; ++k) {
+		const float *a = alpha + (alpha_per_pair ? 3 * k : 0), *E = E5 + 5 * k;
+		djb::microfacet::params params = djb::microfacet::params::elliptic(a[0], a[1], a[2]);
+		float E1 = E[0], E2 = E[1], E3 = E[2], E4 = E[3], E5v = E[4];
+		const float BIAS = bias;
+		E1 -= BIAS;
+		E2 -= BIAS;
+		E5v -= BIAS * BIAS;
+		djb::beckmann::lrep lrep1, lrep2;
+		if (lean_filtering) lrep1 = djb::beckmann::lrep(E1, E2, E3, E4, E5v);
+		else lrep1 = djb::beckmann::lrep(E1, E2, E1 * E1, E2 * E2, E1 * E2);
+		lrep1 *= dmap_scale;
+		djb::beckmann::params_to_lrep(params, &lrep2);
+		djb::beckmann::lrep_to_params(lrep1 + lrep2, &params);
+		memcpy(out12 + 12 * k, &params, sizeof(params));
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // isotropic fit (dj_brdf.h:2215-2236, 3133-3184).  Returns a djb::brdf* that is a djb::tabular.
 REF_API void *ref_tabular_create(void *src, int res, int shadow)

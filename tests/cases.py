@@ -139,3 +139,16 @@ def smooth_merl_table(seed):
         jitter = 1.0 + 0.01 * rng.random(base.shape)
         planes.append((tint * base * jitter + 30.0 * (c + 1)).reshape(-1))
     return np.concatenate(planes)
+
+
+def lean_texels(n, seed=7, bias=25.0):
+    """n texels of a (biased) LEAN map pair as a renderer would fetch them: E1..E5 = mean slopes + bias, second moments
+    of the unbiased slopes (E3, E4) and the biased cross moment (E5), utils/nmap2leanmap_biased.cpp:43-58 -- plus a
+    per-texel base roughness (alpha1, alpha2, alphaAngle)."""
+    rng = np.random.default_rng(seed)
+    sx, sy = rng.normal(0, 0.25, n), rng.normal(0, 0.25, n)
+    vx, vy = rng.uniform(1e-5, 0.08, n), rng.uniform(1e-5, 0.08, n)
+    cxy = rng.uniform(-0.7, 0.7, n) * np.sqrt(vx * vy)
+    E = np.stack([sx + bias, sy + bias, sx * sx + vx, sy * sy + vy, sx * sy + cxy + bias * bias], 1).astype(np.float32)
+    alpha = np.stack([rng.uniform(0.03, 0.5, n), rng.uniform(0.03, 0.5, n), rng.uniform(0, np.pi, n)], 1).astype(np.float32)
+    return E, alpha

@@ -59,6 +59,18 @@ def extra(ref):
     e["aniso_sampling/utia12/14x18/evalp_is_w"], e["aniso_sampling/utia12/14x18/evalp_is_i"] = w, i
     e["aniso_sampling/utia12/14x18/evalp_is_pdf"] = pdf
     e["aniso_sampling/utia12/14x18/fresnel"] = ref.fit_tabular_anisotropic(src, er, ar)["fresnel"]
+    # LEAN-filtered shading: per-shading-point params (mitsuba/dj_beckmannconductor.cpp:283-314) + the queries on them
+    E, alpha = cases.lean_texels(768, seed=9)
+    lwi, lwo, lu = cases.pairs(768, stream=700)
+    e["lean_shading/E"], e["lean_shading/alpha"] = E, alpha
+    e["lean_shading/wi"], e["lean_shading/wo"], e["lean_shading/u"] = lwi, lwo, lu
+    for tag, kw in (("lean", dict()), ("mip", dict(lean_filtering=False)), ("scaled", dict(dmap_scale=1.5))):
+        P = ref.lean_shading_params(E, alpha, **kw)
+        e[f"lean_shading/{tag}/params"] = P
+        e[f"lean_shading/{tag}/evalp"] = np.concatenate(
+            [ref.evalp(api.NDF_BECKMANN, P[k], lwi[k:k + 1], lwo[k:k + 1]) for k in range(len(P))])
+        e[f"lean_shading/{tag}/pdf"] = np.concatenate(
+            [ref.pdf(api.NDF_BECKMANN, P[k], lwi[k:k + 1], lwo[k:k + 1]) for k in range(len(P))])
     np.savez_compressed(OUT / "extra_golden.npz", **e)
     print("extra_golden.npz", (OUT / "extra_golden.npz").stat().st_size, "bytes")
 

@@ -58,3 +58,70 @@ def test_fit_from_analytic_source(djb, port, kind, name):
     want = port.fit_tabular(getattr(api.Source, kind)(name, m.coefficients()), 90)
     check_fit(t, want, f"{kind}/{name} vs port")
     check_fit(t, {k: x[f"fit/{kind}/{name}/{k}"] for k in want}, f"{kind}/{name} vs golden")
+
+
+# ---- LEAN-filtered shading, fused (N1: mitsuba/dj_beckmannconductor.cpp:283-319) ------------------------------------------
+def per_pair(fn, ndf, P, a, b, **kw):
+    return np.concatenate([fn(ndf, P[k], a[k:k + 1], b[k:k + 1], **kw) for k in range(len(P))])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(lean_filtering=False), dict(dmap_scale=1.5), dict(bias=0.0)],
+                         ids=["lean", "naive_mip", "dmapscale", "unbiased"])
+def test_lean_shading_params(djb, port, kw):
+    import torch
+    E, alpha = cases.lean_texels(100_000)
+    want = port.lean_shading_params(E, alpha, **kw)
+    got = djb.beckmann.lean_shading_params(E, alpha, **kw)
+    # device double sin / cos / sqrt / atan vs glibc: an ulp now and then in phi_a / ax; everything within 1e-6
+    assert bits_equal(got, want).all(axis=1).mean() >= 0.999
+    assert np.abs(got - want).max() <= 2e-6 * max(1.0, float(np.abs(want).max()))
+    dev = djb.beckmann.lean_shading_params(torch.from_numpy(E).cuda(), torch.from_numpy(alpha).cuda(), **kw).cpu().numpy()
+    assert bits_equal(dev, got).all()
+    a0 = np.array([0.1, 0.3, 0.4], np.float32)
+    got0, want0 = djb.beckmann.lean_shading_params(E, a0, **kw), port.lean_shading_params(E, a0, **kw)
+    assert bits_equal(got0, want0).all(axis=1).mean() >= 0.999
+
+
+@pytest.mark.parametrize("fname", ["ideal", "schlick", "unpolarized"])
+def test_lean_shading_queries_match_unfused_path(djb, port, fname):
+    """fused kernel == params construction + PER_PAIR query (bit for bit: same device code on both routes), and both
+    == the oracle on the golden records"""
+    import torch
+    from tests.test_gpu_parity import mk_fresnel
+    f = api.Fresnel.ideal() if fname == "ideal" else cases.fresnels()[fname]
+    b = djb.beckmann(mk_fresnel(djb, f))
+    n = 200_000
+    E, alpha = cases.lean_texels(n, seed=11)
+    wi, wo, u = cases.pairs(n, stream=710)
+    tE, ta, twi, two, tu = (torch.from_numpy(v).cuda() for v in (E, alpha, wi, wo, u))
+    P = djb.beckmann.lean_shading_params(tE, ta)
+    assert bits_equal(b.evalp_lean(twi, two, tE, ta).cpu().numpy(), b.evalp(twi, two, P).cpu().numpy()).all()
+    assert bits_equal(b.pdf_lean(twi, two, tE, ta).cpu().numpy(), b.pdf(twi, two, P).cpu().numpy()).all()
+    fw, fi, fp = b.evalp_is_lean(tu, two, tE, ta)
+    uw, ui, up = b.evalp_is(tu, two, P)
+    assert bits_equal(fw.cpu().numpy(), uw.cpu().numpy()).all() and bits_equal(fi.cpu().numpy(), ui.cpu().numpy()).all()
+    assert bits_equal(fp.cpu().numpy(), up.cpu().numpy()).all()
+    # host arrays through the staging pipeline give the same numbers
+    assert bits_equal(b.evalp_lean(wi, wo, E, alpha), b.evalp_lean(twi, two, tE, ta).cpu().numpy()).all()
+    # against the oracle on a subset (oracle params, so a params ulp does not blur the query comparison)
+    m = 3000
+    Po = port.lean_shading_params(E[:m], alpha[:m])
+    same = bits_equal(P.cpu().numpy()[:m], Po).all(axis=1)
+    got = b.evalp_lean(wi[:m], wo[:m], E[:m], alpha[:m])
+    want = per_pair(port.evalp, api.NDF_BECKMANN, Po, wi[:m], wo[:m], fresnel=f)
+    close(got[same], want[same], f"evalp_lean {fname}", 0.999)
+    gp = b.pdf_lean(wi[:m], wo[:m], E[:m], alpha[:m])
+    wp = per_pair(port.pdf, api.NDF_BECKMANN, Po, wi[:m], wo[:m])
+    close(gp[same], wp[same], "pdf_lean", 0.999)
+
+
+def test_lean_shading_vs_golden(djb):
+    x = np.load(GOLD / "extra_golden.npz")
+    E, alpha, wi, wo = (x[f"lean_shading/{k}"] for k in ("E", "alpha", "wi", "wo"))
+    b = djb.beckmann()
+    for tag, kw in (("lean", dict()), ("mip", dict(lean_filtering=False)), ("scaled", dict(dmap_scale=1.5))):
+        P = djb.beckmann.lean_shading_params(E, alpha, **kw)
+        same = bits_equal(P, x[f"lean_shading/{tag}/params"]).all(axis=1)
+        assert same.mean() >= 0.995, tag
+        close(b.evalp_lean(wi, wo, E, alpha, **kw)[same], x[f"lean_shading/{tag}/evalp"][same], f"{tag} evalp", 0.999)
+        close(b.pdf_lean(wi, wo, E, alpha, **kw)[same], x[f"lean_shading/{tag}/pdf"][same], f"{tag} pdf", 0.999)

@@ -170,3 +170,13 @@ def test_tabular_anisotropic_sampling(port, x):
     w, i, pdf = port.tabular_aniso_sample_query("evalp_is", fit, pt, er, ar, u, wo, P)
     assert bits_equal(w, x[f"{tag}/evalp_is_w"]).all() and bits_equal(i, x[f"{tag}/evalp_is_i"]).all()
     assert bits_equal(pdf, x[f"{tag}/evalp_is_pdf"]).all()
+
+
+def test_lean_shading_params(port, x):
+    E, alpha = x["lean_shading/E"], x["lean_shading/alpha"]
+    for tag, kw in (("lean", dict()), ("mip", dict(lean_filtering=False)), ("scaled", dict(dmap_scale=1.5))):
+        P = port.lean_shading_params(E, alpha, **kw)
+        assert bits_equal(P, x[f"lean_shading/{tag}/params"]).all(), tag
+        wi, wo = x["lean_shading/wi"], x["lean_shading/wo"]
+        got = np.concatenate([port.evalp(api.NDF_BECKMANN, P[k], wi[k:k + 1], wo[k:k + 1]) for k in range(len(P))])
+        assert bits_equal(got, x[f"lean_shading/{tag}/evalp"]).all(), tag

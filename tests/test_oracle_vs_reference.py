@@ -155,3 +155,16 @@ def test_fit_from_analytic_source(port, ref, kind, name):
     r, p = ref.fit_tabular(src, 90), port.fit_tabular(src, 90)
     for k in r:
         assert bits_equal(r[k], p[k]).all(), k
+
+
+def test_lean_shading_params_bit_identical(port, ref):
+    """the per-shading-point parameter construction of mitsuba/dj_beckmannconductor.cpp:283-314"""
+    E, alpha = cases.lean_texels(50_000)
+    for kw in (dict(), dict(lean_filtering=False), dict(dmap_scale=2.5), dict(bias=0.0)):
+        if kw.get("bias") == 0.0:
+            E2 = E.copy(); E2[:, 0] -= 25; E2[:, 1] -= 25; E2[:, 4] -= 625
+        else:
+            E2 = E
+        assert bits_equal(port.lean_shading_params(E2, alpha, **kw), ref.lean_shading_params(E2, alpha, **kw)).all(), kw
+        a0 = np.array([0.1, 0.3, 0.4], np.float32)
+        assert bits_equal(port.lean_shading_params(E2, a0, **kw), ref.lean_shading_params(E2, a0, **kw)).all(), kw
