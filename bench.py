@@ -416,6 +416,50 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
     res["lean"] = {"pixels_per_s": W * H / (ms * 1e-3), "ms": ms, "size": [W, H],
                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                 "traffic": None}}
+    # section 8f rows, measured the same way.  LEAN-filtered Beckmann shading (mitsuba/dj_beckmannconductor.cpp:283-319):
+    # fused params construction + evalp against the two-pass route (params blocks written to HBM, then a PER_PAIR query)
+    ns = min(n, 50_000_000)
+    g = torch.Generator(device=dev).manual_seed(5)
+    sl = torch.randn(ns, 2, device=dev, generator=g) * 0.25
+    var = torch.rand(ns, 3, device=dev, generator=g)
+    vx, vy = 1e-5 + 0.08 * var[:, 0], 1e-5 + 0.08 * var[:, 1]
+    E = torch.stack([sl[:, 0] + 25, sl[:, 1] + 25, sl[:, 0] ** 2 + vx, sl[:, 1] ** 2 + vy,
+                     sl[:, 0] * sl[:, 1] + (1.4 * var[:, 2] - 0.7) * torch.sqrt(vx * vy) + 625], 1).contiguous()
+    al = torch.rand(ns, 3, device=dev, generator=g)
+    al[:, :2] = 0.03 + 0.47 * al[:, :2]
+    al[:, 2] *= 3.14159
+    del sl, var, vx, vy
+    cfg = capi.LeanShading()
+    cfg.bias, cfg.dmap_scale, cfg.lean_filtering, cfg.alpha_per_pair = 25.0, 1.0, 1, 1
+    bk = djb.beckmann()
+    d = bk._desc()
+    P = out[: 12 * ns]
+    res_rgb = out[12 * ns: 15 * ns]
+    pv = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    ms_f = timed(lambda: capi.check(lib.djb200_lean_shading_evalp(C.byref(d), C.byref(cfg), pv(al), pv(E), pv(wi), pv(wo),
+                                                                  C.c_int64(ns), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
+
+    def two_pass():
+        capi.check(lib.djb200_lean_shading_params(C.byref(cfg), pv(al), pv(E), C.c_int64(ns), pv(P), C.c_int(capi.MEM_DEVICE), sptr))
+        capi.check(lib.djb200_microfacet_evalp(C.byref(d), pv(P), C.c_int64(ns), C.c_int(capi.PARAMS_PER_PAIR), pv(wi), pv(wo),
+                                               C.c_int64(ns), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr))
+    ms_2 = timed(two_pass)
+    gbs = 68.0 * ns / (ms_f * 1e-3) / 1e9  # 24 B directions + 20 B moments + 12 B roughness in, 12 B out
+    res["lean_shading"] = {"evals_per_s": ns / (ms_f * 1e-3), "ms": ms_f, "pairs": ns, "two_pass_ms": ms_2,
+                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                        "traffic": None}}
+    del E, al
+    # djb::sgd / djb::abc eval (36 B per pair; double exp / pow / acos per channel: issue bound)
+    na = min(n, 20_000_000)
+    for kind, name in (("sgd", "gold-metallic-paint"), ("abc", "blue-metallic-paint")):
+        mobj = getattr(djb, kind)(name)
+        fn = getattr(lib, f"djb200_{kind}_eval")
+        ms = timed(lambda: capi.check(fn(C.byref(mobj._data), pv(wi), pv(wo), C.c_int64(na), pv(res_rgb),
+                                         C.c_int(capi.MEM_DEVICE), sptr)))
+        gbs = 36.0 * na / (ms * 1e-3) / 1e9
+        res[kind] = {"evals_per_s": na / (ms * 1e-3), "ms": ms, "pairs": na,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                  "traffic": None}}
     return res
 
 

@@ -504,6 +504,24 @@ def nmap2leanmap(nmap, base_roughness=1e-5, bias=0.0):
     return l1, l2
 
 
+def dmap2nmap(dmap, scale=0.01):
+    """utils/dmap2nmap.cpp:13-44: uint8 displacement map [h, w] -> planar uint8 normal map [3, h, w]."""
+    b = Buf(dmap, np.uint8)
+    shape = tuple(b.keep.shape)
+    if len(shape) != 2:
+        raise ValueError("dmap must be [h, w]")
+    h, w = shape
+    if capi._is_torch(b.keep):
+        import torch
+        out = torch.empty((3, h, w), dtype=torch.uint8, device=b.keep.device)
+    else:
+        out = np.empty((3, h, w), np.uint8)
+    bo = Buf(out, np.uint8, True)
+    check(capi.load().djb200_dmap_to_nmap(b.ptr, C.c_int32(w), C.c_int32(h), C.c_float(scale), bo.ptr, C.c_int(b.mem),
+                                          capi.current_stream_ptr(b.mem)))
+    return out
+
+
 def leanmap_to_params(leanmap_1, leanmap_2, bias=0.0):
     """check_lean_maps (utils/nmap2leanmap.cpp:57-76) as a producer: per-texel lrep_to_params -> [h*w, 12]."""
     b1, b2 = Buf(leanmap_1, np.float32), Buf(leanmap_2, np.float32)

@@ -997,6 +997,32 @@ djb200_status djb200_abc_eval(const djb200_abc_data *material, const float *wi, 
 		});
 }
 
+djb200_status djb200_dmap_to_nmap(const uint8_t *dmap, int32_t w, int32_t h, float scale, uint8_t *nmap, int mem, void *stream)
+{
+	if (w < 0 || h < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative image size");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	const size_t npix = (size_t)w * h;
+	if (npix == 0) return DJB200_OK;
+	if (!dmap || !nmap) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL pointer");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	if (mem == DJB200_MEM_DEVICE) {
+		cudaError_t e = launch_dmap2nmap(dmap, w, h, scale, nmap, (cudaStream_t)stream);
+		return e == cudaSuccess ? DJB200_OK : cuda_fail(e, "dmap2nmap launch");
+	}
+	// host: the stencil needs whole rows and their neighbours; a map is 1 + 3 bytes per texel, staged in one piece
+	uint8_t *d_in = nullptr, *d_out = nullptr;
+	cudaError_t e = cudaMalloc(&d_in, npix);
+	if (e == cudaSuccess) e = cudaMalloc(&d_out, 3 * npix);
+	if (e == cudaSuccess) e = cudaMemcpy(d_in, dmap, npix, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = launch_dmap2nmap(d_in, w, h, scale, d_out, 0);
+	if (e == cudaSuccess) e = cudaMemcpy(nmap, d_out, 3 * npix, cudaMemcpyDeviceToHost);
+	cudaFree(d_in);
+	cudaFree(d_out);
+	return e == cudaSuccess ? DJB200_OK : cuda_fail(e, "dmap2nmap staging");
+}
+
 djb200_status djb200_lean_shading_params(const djb200_lean_shading *cfg, const float *alpha, const float *E, int64_t n,
                                          djb200_params *out, int mem, void *stream)
 {

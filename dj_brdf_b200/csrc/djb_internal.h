@@ -93,6 +93,7 @@ cudaError_t launch_utia_eval(const float *table, const float *wi, const float *w
                              cudaStream_t st);
 cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base_roughness, float bias,
                                    float *lean1, float *lean2, cudaStream_t st);
+cudaError_t launch_dmap2nmap(const uint8_t *dmap, int w, int h, float scale, uint8_t *nmap, cudaStream_t st);
 cudaError_t launch_lrep_to_params(const float *E, int64_t n, void *out_params, cudaStream_t st);
 cudaError_t launch_params_to_lrep(const void *params, int64_t n, float *E, cudaStream_t st);
 cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int64_t npix, float bias,

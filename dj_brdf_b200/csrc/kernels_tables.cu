@@ -185,6 +185,70 @@ cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base
 	return cudaGetLastError();
 }
 
+// ---- dmap2nmap, utils/dmap2nmap.cpp:13-44 --------------------------------------------------------------------------
+// Central differences of an 8-bit displacement map (CImg atXY(): clamped at the borders) -> unit normal packed as planar
+// 8-bit RGB.  1 B in (+ 4 neighbours, which the row / L2 locality makes free) and 3 B out per texel: HBM bound.
+// That utility is compiled with <math.h> in scope, so its sqrt(float) is sqrtf; 1.0 / x and 0.5 * n + 0.5 are double
+// expressions rounded once to float -- one IEEE reciprocal and one fused multiply-add give the same floats.
+DJB_DEV void dmap_texel(const uint8_t *__restrict__ d, int w, int h, int i, int j, float kx, float ky, uint8_t &r, uint8_t &g,
+                        uint8_t &b)
+{
+	const int il = i > 0 ? i - 1 : 0, ir = i + 1 < w ? i + 1 : w - 1;
+	const int jt = j > 0 ? j - 1 : 0, jb = j + 1 < h ? j + 1 : h - 1;
+	const size_t row = (size_t)j * w;
+	const float z_l = (float)d[il + row] / 255.f, z_r = (float)d[ir + row] / 255.f;
+	const float z_b = (float)d[i + (size_t)jb * w] / 255.f, z_t = (float)d[i + (size_t)jt * w] / 255.f;
+	const float sx = kx * (z_r - z_l), sy = ky * (z_t - z_b);
+	const float nrm_sqr = 1.f + sx * sx + sy * sy;
+	const float nrm_inv = __frcp_rn(__fsqrt_rn(nrm_sqr));
+	const float nx = -sx * nrm_inv, ny = -sy * nrm_inv;
+	r = (uint8_t)(__fmaf_rn(0.5f, nx, 0.5f) * 255.f);
+	g = (uint8_t)(__fmaf_rn(0.5f, ny, 0.5f) * 255.f);
+	b = (uint8_t)(nrm_inv * 255.f);
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(TB) dmap2nmap_kernel(const uint8_t *__restrict__ d, int w, int h, float scale,
+                                                       uint8_t *__restrict__ out)
+{
+	const float kx = (float)w * 0.5f * scale, ky = (float)h * 0.5f * scale;
+	const long long plane = (long long)w * h, stride = (long long)gridDim.x * blockDim.x;
+	if (VEC4) { // w % 4 == 0 and 4-byte aligned planes: four texels of one row per thread, 32-bit stores
+		const long long nq = plane / 4;
+		for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+			const long long px = 4 * q;
+			const int j = (int)(px / w), i0 = (int)(px % w);
+			uchar4 r, g, b;
+			dmap_texel(d, w, h, i0, j, kx, ky, r.x, g.x, b.x);
+			dmap_texel(d, w, h, i0 + 1, j, kx, ky, r.y, g.y, b.y);
+			dmap_texel(d, w, h, i0 + 2, j, kx, ky, r.z, g.z, b.z);
+			dmap_texel(d, w, h, i0 + 3, j, kx, ky, r.w, g.w, b.w);
+			reinterpret_cast<uchar4 *>(out)[q] = r;
+			reinterpret_cast<uchar4 *>(out + plane)[q] = g;
+			reinterpret_cast<uchar4 *>(out + 2 * plane)[q] = b;
+		}
+	} else {
+		for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < plane; px += stride) {
+			uint8_t r, g, b;
+			dmap_texel(d, w, h, (int)(px % w), (int)(px / w), kx, ky, r, g, b);
+			out[px] = r;
+			out[plane + px] = g;
+			out[2 * plane + px] = b;
+		}
+	}
+}
+
+cudaError_t launch_dmap2nmap(const uint8_t *dmap, int w, int h, float scale, uint8_t *nmap, cudaStream_t st)
+{
+	const int64_t plane = (int64_t)w * h;
+	if (plane <= 0) return cudaSuccess;
+	const bool vec = (w % 4 == 0) && ((uintptr_t)nmap % 4 == 0);
+	if (vec) dmap2nmap_kernel<true><<<grid_for(plane / 4), TB, 0, st>>>(dmap, w, h, scale, nmap);
+	else dmap2nmap_kernel<false><<<grid_for(plane), TB, 0, st>>>(dmap, w, h, scale, nmap);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
 // ---- LEAN algebra per texel --------------------------------------------------------------------------
 DJB_DEV void store_params(void *out, long long k, const Params &p)
 {

@@ -207,6 +207,10 @@ DJB200_API djb200_status djb200_abc_eval(const djb200_abc_data *material, const 
  * (bias = 25).  nmap: planar uint8 [3][h][w]; lean1/lean2: planar float [4][h][w] (CImg layout). */
 DJB200_API djb200_status djb200_nmap_to_leanmap(const uint8_t *nmap, int32_t w, int32_t h, float base_roughness,
                                                 float bias, float *lean1, float *lean2, int mem, void *stream);
+/* dmap2nmap, utils/dmap2nmap.cpp:13-44: 8-bit displacement map [h][w] -> planar 8-bit normal map [3][h][w] (central
+ * differences clamped at the borders, slopes scaled by (size / 2) * scale; the tool's default scale is 0.01, :69) */
+DJB200_API djb200_status djb200_dmap_to_nmap(const uint8_t *dmap, int32_t w, int32_t h, float scale, uint8_t *nmap,
+                                             int mem, void *stream);
 /* beckmann::lrep_to_params, dj_brdf.h:1976-1990.  E: n x 5 moments (E1..E5). */
 DJB200_API djb200_status djb200_lrep_to_params(const float *E, int64_t n, djb200_params *out, int mem,
                                                void *stream);

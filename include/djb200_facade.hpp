@@ -870,5 +870,12 @@ inline void nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float_t b
 	detail::check(djb200_nmap_to_leanmap(nmap_planar_rgb, w, h, base_roughness, bias, leanmap_1, leanmap_2, where, stream));
 }
 
+// utils/dmap2nmap.cpp:13-44 on raw buffers: 8-bit displacement map [h][w] -> planar 8-bit normal map [3][h][w]
+inline void dmap2nmap(const uint8_t *dmap, int w, int h, uint8_t *nmap_planar_rgb, float scale = 0.1f, memory_space where = host,
+                      void *stream = NULL)
+{
+	detail::check(djb200_dmap_to_nmap(dmap, w, h, scale, nmap_planar_rgb, where, stream));
+}
+
 } // namespace djb
 #endif // DJB200_FACADE_HPP

@@ -280,6 +280,13 @@ class PortOracle:
                                   c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data))
         return l1, l2
 
+    def dmap2nmap(self, dmap, scale=0.1):
+        d = np.ascontiguousarray(dmap, np.uint8)
+        h, w = d.shape
+        out = np.zeros((3, h, w), np.uint8)
+        self.lib.orc_dmap2nmap(C.c_void_p(d.ctypes.data), C.c_int(w), C.c_int(h), C.c_float(scale), C.c_void_p(out.ctypes.data))
+        return out
+
     # -- fits
     def _source(self, src):
         s = _OrcSource()
@@ -579,6 +586,14 @@ class RefOracle:
         L.ref_nmap2leanmap(C.c_void_p(nmap.ctypes.data), C.c_int(w), C.c_int(h), C.c_float(base_roughness),
                            c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data), C.c_int(int(run_check)))
         return l1, l2
+
+    def dmap2nmap(self, dmap, scale=0.1):
+        d = np.ascontiguousarray(dmap, np.uint8)
+        h, w = d.shape
+        out = np.zeros((3, h, w), np.uint8)
+        lib = C.CDLL(str(HERE / "_ref" / "libdmapref.so"))
+        lib.ref_dmap2nmap(C.c_void_p(d.ctypes.data), C.c_int(w), C.c_int(h), C.c_float(scale), C.c_void_p(out.ctypes.data))
+        return out
 
     # -- fits
     def _source_handle(self, src):

@@ -1094,3 +1094,29 @@ ORC_API void orc_nmap2leanmap(const uint8_t *nmap, int w, int h, float base_roug
 /* ---------------------------------------------------------------------------------------------
  * the power-iteration fits share this file's static helpers */
 #include "djb_oracle_fit.c"
+
+/* ---------------------------------------------------------------------------------------------
+ * dmap2nmap, utils/dmap2nmap.cpp:13-44: central differences of an 8-bit displacement map with CImg's atXY() clamping at
+ * the borders, slopes scaled by (size / 2) * scale, unit normal packed as 8-bit RGB (truncating casts).
+ * That file includes <math.h> through CImg.h, so its sqrt(float) is the float overload (unlike inside dj_brdf.h). */
+ORC_API void orc_dmap2nmap(const uint8_t *dmap, int w, int h, float scale, uint8_t *nmap)
+{
+	const size_t plane = (size_t)w * h;
+	for (int j = 0; j < h; ++j)
+		for (int i = 0; i < w; ++i) {
+			int il = i - 1 < 0 ? 0 : i - 1, ir = i + 1 >= w ? w - 1 : i + 1;
+			int jt = j - 1 < 0 ? 0 : j - 1, jb = j + 1 >= h ? h - 1 : j + 1;
+			float z_l = (float)dmap[il + (size_t)j * w] / 255.f, z_r = (float)dmap[ir + (size_t)j * w] / 255.f;
+			float z_b = (float)dmap[i + (size_t)jb * w] / 255.f, z_t = (float)dmap[i + (size_t)jt * w] / 255.f;
+			float slope_x = (float)w * 0.5f * scale * (z_r - z_l);
+			float slope_y = (float)h * 0.5f * scale * (z_t - z_b);
+			float nrm_sqr = 1.f + slope_x * slope_x + slope_y * slope_y;
+			float nrm_inv = F(1.0 / D(sqrtf(nrm_sqr)));
+			float nx = -slope_x * nrm_inv, ny = -slope_y * nrm_inv, nz = nrm_inv;
+			float tmp1 = F(0.5 * D(nx) + 0.5), tmp2 = F(0.5 * D(ny) + 0.5);
+			size_t px = i + (size_t)j * w;
+			nmap[px] = (uint8_t)(tmp1 * 255);
+			nmap[plane + px] = (uint8_t)(tmp2 * 255);
+			nmap[2 * plane + px] = (uint8_t)(nz * 255);
+		}
+}

@@ -91,6 +91,9 @@ void orc_lean_shading_params(float bias, float dmap_scale, int lean_filtering, i
 void orc_nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float base_roughness, float bias,
                       float *lean1_planar_rgba, float *lean2_planar_rgba);
 
+/* dmap2nmap (utils/dmap2nmap.cpp:13-44): uint8 [h][w] displacement map -> planar uint8 [3][h][w] normal map */
+void orc_dmap2nmap(const uint8_t *dmap, int w, int h, float scale, uint8_t *nmap_planar_rgb);
+
 /* ---- fits: djb_oracle_fit.c ------------------------------------------------------------- */
 /* generic BRDF handle used as the fit input */
 enum { ORC_SRC_MICROFACET = 0, ORC_SRC_MERL = 1, ORC_SRC_UTIA = 2, ORC_SRC_SGD = 3, ORC_SRC_ABC = 4 };

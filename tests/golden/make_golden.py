@@ -71,6 +71,11 @@ def extra(ref):
             [ref.evalp(api.NDF_BECKMANN, P[k], lwi[k:k + 1], lwo[k:k + 1]) for k in range(len(P))])
         e[f"lean_shading/{tag}/pdf"] = np.concatenate(
             [ref.pdf(api.NDF_BECKMANN, P[k], lwi[k:k + 1], lwo[k:k + 1]) for k in range(len(P))])
+    # dmap2nmap (utils/dmap2nmap.cpp compiled in place)
+    rng = np.random.default_rng(3)
+    for tag, (h, w, sc) in (("a", (37, 53, 0.1)), ("b", (64, 96, 0.01)), ("c", (3, 5, 1.0))):
+        d = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        e[f"dmap/{tag}/dmap"], e[f"dmap/{tag}/scale"], e[f"dmap/{tag}/nmap"] = d, np.float32(sc), ref.dmap2nmap(d, sc)
     np.savez_compressed(OUT / "extra_golden.npz", **e)
     print("extra_golden.npz", (OUT / "extra_golden.npz").stat().st_size, "bytes")
 

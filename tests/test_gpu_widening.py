@@ -125,3 +125,23 @@ def test_lean_shading_vs_golden(djb):
         assert same.mean() >= 0.995, tag
         close(b.evalp_lean(wi, wo, E, alpha, **kw)[same], x[f"lean_shading/{tag}/evalp"][same], f"{tag} evalp", 0.999)
         close(b.pdf_lean(wi, wo, E, alpha, **kw)[same], x[f"lean_shading/{tag}/pdf"][same], f"{tag} pdf", 0.999)
+
+
+# ---- dmap2nmap (N4: utils/dmap2nmap.cpp:13-44) ----------------------------------------------------------------------------
+def test_dmap2nmap_bit_exact(djb, port):
+    import torch
+    x = np.load(GOLD / "extra_golden.npz")
+    for tag in "abc":
+        assert np.array_equal(djb.dmap2nmap(x[f"dmap/{tag}/dmap"], float(x[f"dmap/{tag}/scale"])), x[f"dmap/{tag}/nmap"]), tag
+    rng = np.random.default_rng(8)
+    for h, w, sc in ((1, 1, 0.1), (2, 1, 0.3), (7, 1023, 0.5), (1024, 2048, 0.01), (513, 511, 0.1)):
+        d = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        want = port.dmap2nmap(d, sc)
+        assert np.array_equal(djb.dmap2nmap(d, sc), want), (h, w, "host")
+        assert np.array_equal(djb.dmap2nmap(torch.from_numpy(d).cuda(), sc).cpu().numpy(), want), (h, w, "device")
+    # the full chain of the reference's asset tools on the device: dmap -> nmap -> LEAN maps
+    d = rng.integers(96, 160, (256, 256), dtype=np.uint8)
+    nm = djb.dmap2nmap(torch.from_numpy(d).cuda(), 0.01)
+    l1, l2 = djb.nmap2leanmap(nm, 1e-5, 25.0)
+    w1, w2 = port.nmap2leanmap(port.dmap2nmap(d, 0.01), 1e-5, 25.0)
+    assert bits_equal(l1.cpu().numpy(), w1).all() and bits_equal(l2.cpu().numpy(), w2).all()

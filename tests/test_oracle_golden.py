@@ -180,3 +180,8 @@ def test_lean_shading_params(port, x):
         wi, wo = x["lean_shading/wi"], x["lean_shading/wo"]
         got = np.concatenate([port.evalp(api.NDF_BECKMANN, P[k], wi[k:k + 1], wo[k:k + 1]) for k in range(len(P))])
         assert bits_equal(got, x[f"lean_shading/{tag}/evalp"]).all(), tag
+
+
+def test_dmap2nmap(port, x):
+    for tag in "abc":
+        assert np.array_equal(port.dmap2nmap(x[f"dmap/{tag}/dmap"], float(x[f"dmap/{tag}/scale"])), x[f"dmap/{tag}/nmap"]), tag

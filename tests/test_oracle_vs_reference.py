@@ -168,3 +168,11 @@ def test_lean_shading_params_bit_identical(port, ref):
         assert bits_equal(port.lean_shading_params(E2, alpha, **kw), ref.lean_shading_params(E2, alpha, **kw)).all(), kw
         a0 = np.array([0.1, 0.3, 0.4], np.float32)
         assert bits_equal(port.lean_shading_params(E2, a0, **kw), ref.lean_shading_params(E2, a0, **kw)).all(), kw
+
+
+def test_dmap2nmap_bit_identical(port, ref):
+    """utils/dmap2nmap.cpp compiled in place against the port, incl. degenerate sizes (borders clamp)"""
+    rng = np.random.default_rng(3)
+    for h, w, sc in ((37, 53, 0.1), (64, 64, 0.01), (5, 300, 1.0), (1, 1, 0.1), (2, 1, 0.3), (128, 256, 0.05)):
+        d = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(port.dmap2nmap(d, sc), ref.dmap2nmap(d, sc)), (h, w, sc)
