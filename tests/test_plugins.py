@@ -139,3 +139,35 @@ def test_plugin_matches_reference(binaries, tmp_path, plugin):
         fin = np.isfinite(w) & np.isfinite(g)
         scale = np.maximum(np.abs(w[fin]), 1e-3 * max(1e-30, np.abs(w[fin]).max()))
         assert (np.abs(g[fin] - w[fin]) / scale).max() <= 10 * tol, (plugin, tag, "sample weight / pdf")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plugin,tag,mode", [("dj_beckmannconductor", "lean", "lean"),
+                                             ("dj_beckmannconductor", "naive_mip", "naive_mip"),
+                                             ("dj_brdf", "beckmann_textured", "beckmann_textured")])
+def test_wavefront_adapter_matches_scalar_plugin(djb, binaries, tmp_path, plugin, tag, mode):
+    """include/djb200_wavefront.hpp: the plugin's per-record work for a whole array of records in one fused device pass
+    (LEAN texel -> params -> query), against the UNMODIFIED scalar plugin built on the reference header."""
+    exe = tmp_path / "wavefront_check"
+    r = subprocess.run(["g++", "-O2", "-std=c++11", f"-I{ROOT / 'include'}", str(ROOT / "tests/cpp/wavefront_check.cpp"),
+                        f"-L{ROOT / 'dj_brdf_b200'}", "-ldjb200", f"-Wl,-rpath,{ROOT / 'dj_brdf_b200'}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n = 20_000
+    _, lines, kw = next(c for c in configs(tmp_path)[plugin] if c[0] == tag)
+    rec = records(n, 902, **kw)
+    r0, want = run(binaries[plugin][0], lines, rec, tmp_path, f"{tag}_ref")
+    assert r0.returncode == 0, r0.stderr
+    rin, rout = tmp_path / f"{tag}_ref.in", tmp_path / "wf.out"
+    r1 = subprocess.run([str(exe), mode, str(rin), str(rout)], capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stderr
+    got = np.fromfile(rout, np.float32).reshape(-1, 11)
+    for name, sl in (("eval", slice(0, 3)), ("pdf", slice(3, 4))):
+        g, w = got[:, sl].astype(np.float64), want[:, sl].astype(np.float64)
+        scale = np.maximum(np.abs(w), 1e-3 * max(1e-30, np.abs(w).max()))
+        assert (np.abs(g - w) / scale).max() <= 1e-5, (tag, name)
+    same = (got[:, 7:10].view(np.uint32) == want[:, 7:10].view(np.uint32)).all(axis=1)
+    assert same.mean() >= 0.99, (tag, float(same.mean()))
+    g, w = got[same][:, [4, 5, 6, 10]].astype(np.float64), want[same][:, [4, 5, 6, 10]].astype(np.float64)
+    scale = np.maximum(np.abs(w), 1e-3 * max(1e-30, np.abs(w).max()))
+    assert (np.abs(g - w) / scale).max() <= 1e-4, (tag, "sample weight / pdf")
