@@ -53,6 +53,16 @@ def build_ref(quiet=True):
     return True
 
 
+def build_plugins(quiet=True):
+    """The six Mitsuba plugin sources of the reference, compiled in place against the mock Mitsuba API, once per backend
+    (oracle/Makefile `plugins`); needs /root/reference and a built dj_brdf_b200/libdjb200.so."""
+    if not (REF_ROOT / "mitsuba" / "dj_merl.cpp").exists():
+        return False
+    subprocess.run(["make", "-C", str(HERE), "plugins", f"REF={REF_ROOT}"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.DEVNULL if quiet else None)
+    return True
+
+
 def port_available():
     return (HERE / "libdjb_oracle.so").exists()
 
