@@ -324,6 +324,35 @@ class microfacet(brdf):
                                       lean_filtering))
 
 
+    # ---- djb::radial's public scalar queries (dj_brdf.h:307-310), batched -----------------------------------------------
+    def _radial(self, what, x):
+        b = Buf(x, np.float32)
+        out = capi.empty_like_space(b.keep, (b.n,), np.float32)
+        bo = Buf(out, np.float32, True)
+        if self._ndf is None:  # tabular: the handle carries the tables
+            h, _keep = self._first_arg()
+            if getattr(self, "m_azimuthal_res", 0):
+                raise DjbError(1, "tabular_anisotropic is not a radial distribution")
+            check(capi.load().djb200_radial_query(C.c_int(what), C.c_int(0), h, b.ptr, C.c_int64(b.n), bo.ptr, C.c_int(b.mem),
+                                                  capi.current_stream_ptr(b.mem)))
+        else:
+            check(capi.load().djb200_radial_query(C.c_int(what), C.c_int(self._ndf), None, b.ptr, C.c_int64(b.n), bo.ptr,
+                                                  C.c_int(b.mem), capi.current_stream_ptr(b.mem)))
+        return out
+
+    def p22_radial(self, r_sqr):
+        return self._radial(0, r_sqr)
+
+    def sigma_std_radial(self, cos_theta_k):
+        return self._radial(1, cos_theta_k)
+
+    def cdf_radial(self, r):
+        return self._radial(2, r)
+
+    def qf_radial(self, u):
+        return self._radial(3, u)
+
+
 class ggx(microfacet):
     _ndf = capi.NDF_GGX
 

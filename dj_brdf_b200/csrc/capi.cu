@@ -665,11 +665,12 @@ djb200_status djb200_tabular_create(const djb200_tabular_fit *fit, int32_t shado
 	djb200_status rs = require_device();
 	if (rs != DJB200_OK) return rs;
 	const size_t res = (size_t)fit->res;
-	std::vector<float> h(6 * res);
+	std::vector<float> h(7 * res, 0.0f);
 	memcpy(h.data(), fit->p22, 4 * res);
 	memcpy(h.data() + res, fit->sigma, 4 * res);
 	memcpy(h.data() + 2 * res, fit->qf, 4 * res);
 	memcpy(h.data() + 3 * res, fit->fresnel, 12 * res);
+	if (fit->cdf) memcpy(h.data() + 6 * res, fit->cdf, 4 * res); // only radial_query(CDF_RADIAL) reads it
 	float *d = nullptr;
 	CU(cudaMalloc(&d, 4 * h.size()));
 	cudaError_t e = cudaMemcpy(d, h.data(), 4 * h.size(), cudaMemcpyHostToDevice);
@@ -707,6 +708,24 @@ djb200_status djb200_tabular_anisotropic_create(const djb200_tabular_anisotropic
 	cudaGetDevice(&t->device);
 	*out = t;
 	return DJB200_OK;
+}
+
+djb200_status djb200_radial_query(int what, int ndf, const djb200_tabular *t, const float *x, int64_t n, float *out, int mem,
+                                  void *stream)
+{
+	if (what < DJB200_RADIAL_P22 || what > DJB200_RADIAL_QF) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown radial query %d", what);
+	int family = ndf, res = 0;
+	const float *tables = nullptr;
+	if (t) {
+		if (t->azim_res > 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "tabular_anisotropic is not a radial distribution");
+		family = 2; res = t->res; tables = t->tables;
+	} else if (ndf != DJB200_NDF_BECKMANN && ndf != DJB200_NDF_GGX) {
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown ndf %d", ndf);
+	}
+	return map_call(n, {{x, 4}}, {{out, 4}}, mem, stream,
+		[=](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_radial_query(family, what, tables, res, (const float *)i[0], cn, (float *)o[0], st);
+		});
 }
 
 djb200_status djb200_tabular_anisotropic_sampling_tables(const djb200_tabular *t, float *pdf1, float *cdf1, float *qf1,

@@ -11,7 +11,7 @@ struct djb200_merl {
 	int device;
 };
 struct djb200_tabular {
-	float *tables; // radial: p22[res] | sigma[res] | qf[res] | fresnel[res][3]; anisotropic: see aniso_table_floats()
+	float *tables; // radial: p22[res] | sigma[res] | qf[res] | fresnel[res][3] | cdf[res]; anisotropic: see aniso_table_floats()
 	int res, shadow, device;
 	int azim_res; // 0: radial tables (djb::tabular); > 0: djb::tabular_anisotropic with res = elevation resolution
 	int n_qf1, n_qf2; // anisotropic: entries the quantile-table searches produced (dj_brdf.h:2904-2935, 3004-3037)
@@ -75,6 +75,9 @@ cudaError_t launch_tabular_query(const float *tables, int res, const MfLaunch &L
 // djb::tabular_anisotropic as a BRDF (eval / evalp / pdf); tables: device, p22[er * ar] | sigma[er * ar] | fresnel[er][3]
 cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int azim_res, int n_qf1, const MfLaunch &L,
                                        cudaStream_t st);
+// djb::radial's scalar queries; family: djb200_ndf or 2 = tabular (radial tables: p22 | sigma | qf | fresnel[3] | cdf)
+cudaError_t launch_radial_query(int family, int what, const float *tables, int res, const float *x, int64_t n, float *out,
+                                cudaStream_t st);
 // builds qf1 | qf2 | pdf1 | cdf1 | pdf2 | cdf2 inside `tables` from its p22 block (dj_brdf.h:2848-3103); counts_host[2]
 // receives the fill counts of qf1 / qf2 (the call synchronises the stream)
 cudaError_t build_aniso_sampling_tables(float *tables, int elev_res, int azim_res, int counts_host[2], cudaStream_t st);

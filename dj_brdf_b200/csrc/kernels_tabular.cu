@@ -290,6 +290,53 @@ __global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQuer
 	}
 }
 
+// ---- the public scalar queries of djb::radial (dj_brdf.h:307-310): p22_radial, sigma_std_radial, cdf_radial, qf_radial ---
+// what tests/plot_qf.cpp / plot_cdf.cpp of the reference call; one thread per argument.
+// family: NDF_BECKMANN, NDF_GGX, or 2 = tabular (tables: p22 | sigma | qf | fresnel[3] | cdf, `res` entries each)
+__global__ void __launch_bounds__(TQ_THREADS) radial_query_kernel(int family, int what, const float *__restrict__ tables, int res,
+                                                                  const float *__restrict__ x, long long n, float *__restrict__ out)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		const float v = x[k];
+		float r = 0.0f;
+		if (family == 2) {
+			TabIso t; t.p22 = tables; t.sigma = tables + res; t.n = res;
+			if (what == 0) r = t.p22_radial(v);
+			else if (what == 1) r = spline_f(t.sigma, res, (float)(2.0 * acos((double)v) / (double)(float)DJB_PI)); // :2158-2162
+			else if (what == 2) { // tabular::cdf_radial, :2164-2169
+				float u = (float)(atan((double)v) * (double)2.0f / (double)(float)DJB_PI);
+				if (u < 0.0f) u = 0.0f;
+				r = spline_f(tables + 6 * res, res, (float)sqrt((double)u));
+			} else { // tabular::qf_radial, :2171-2176
+				const float q = spline_f(tables + 2 * res, res, v);
+				r = (float)tan((double)(q * (float)DJB_PI / 2.0f));
+			}
+		} else if (family == NDF_GGX) {
+			if (what == 0) r = p22_radial<NDF_GGX>(v);
+			else if (what == 1) r = sigma_std_radial<NDF_GGX>(v);
+			else if (what == 2) { const float t = v * v; r = (float)((double)t / (1.0 + (double)t)); }     // :2067-2071
+			else r = (float)sqrt((double)v / (1.0 - (double)v));                                           // :2073-2076
+		} else {
+			if (what == 0) r = p22_radial<NDF_BECKMANN>(v);
+			else if (what == 1) r = sigma_std_radial<NDF_BECKMANN>(v);
+			else if (what == 2) r = (float)(1.0 - exp((double)(-v * v)));                                 // :1881-1884
+			else r = (float)sqrt(-log(1.0 - (double)v));                                                   // :1886-1889
+		}
+		out[k] = r;
+	}
+}
+
+cudaError_t launch_radial_query(int family, int what, const float *tables, int res, const float *x, int64_t n, float *out,
+                                cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	long long want = (n + TQ_THREADS - 1) / TQ_THREADS, cap = (long long)sm_count() * 8;
+	radial_query_kernel<<<(int)(want < cap ? want : cap), TQ_THREADS, 0, st>>>(family, what, tables, res, x, n, out);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
 // ---- tabular_anisotropic's sampling tables (dj_brdf.h:2848-3103) ----------------------------------------------------
 // A chain of eight small table passes, each depending on the previous one: marginal azimuth density (256-point elevation
 // quadrature per azimuth), its normalisation, running integral and inverse; conditional elevation density, its per-azimuth

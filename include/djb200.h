@@ -318,6 +318,16 @@ DJB200_API djb200_status djb200_tabular_evalp_is(const djb200_tabular *t, const 
                                                  float *out_weight_rgb, float *out_wi, float *out_pdf, int mem,
                                                  void *stream);
 
+/* The public scalar queries of djb::radial (dj_brdf.h:307-310) -- what tests/plot_qf.cpp and tests/plot_cdf.cpp of the
+ * reference tabulate: x[k] is r^2 (P22), cos(theta_k) (SIGMA_STD), r (CDF) or u (QF).  `t` = a radial djb200_tabular handle
+ * (then `ndf` is ignored; dj_brdf.h:2151-2176; CDF needs the fit's cdf table at djb200_tabular_create), or NULL for the
+ * analytic family `ndf` (dj_brdf.h:1866-1889, 2056-2076). */
+typedef enum djb200_radial_what {
+	DJB200_RADIAL_P22 = 0, DJB200_RADIAL_SIGMA_STD = 1, DJB200_RADIAL_CDF = 2, DJB200_RADIAL_QF = 3
+} djb200_radial_what;
+DJB200_API djb200_status djb200_radial_query(int what, int ndf, const djb200_tabular *t, const float *x, int64_t n, float *out,
+                                             int mem, void *stream);
+
 /* Result of djb::tabular_anisotropic (eval tables) + fit_*_parameters (dj_brdf.h:2238-2273,
  * 3186-3307): p22/sigma are elev_res x azim_res, fresnel elev_res x rgb,
  * beckmann/ggx = (ax, ay, rho, tx_n, ty_n). */

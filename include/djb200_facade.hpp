@@ -468,9 +468,29 @@ protected:
 	unsigned m_fresnel_rev;
 };
 
+// dj_brdf.h:300-324: the radial families and their public scalar queries (what tests/plot_qf.cpp / plot_cdf.cpp tabulate)
 class radial : public microfacet {
+public:
+	float_t p22_radial(float_t r_sqr) const { return radial_query(DJB200_RADIAL_P22, r_sqr); }
+	float_t sigma_std_radial(float_t cos_theta_k) const { return radial_query(DJB200_RADIAL_SIGMA_STD, cos_theta_k); }
+	float_t cdf_radial(float_t r) const { return radial_query(DJB200_RADIAL_CDF, r); }
+	float_t qf_radial(float_t u) const { return radial_query(DJB200_RADIAL_QF, u); }
+	// batched (added): n arguments per call
+	void radial_query_batch(djb200_radial_what what, const float_t *x, size_t n, float_t *out, memory_space where = host,
+	                        void *stream = NULL) const
+	{
+		detail::check(djb200_radial_query(what, ndf_id(), radial_handle(), x, (int64_t)n, out, where, stream));
+	}
 protected:
 	radial(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : microfacet(f, shadow) {}
+	virtual const djb200_tabular *radial_handle() const { return NULL; } // tabular: its device tables
+private:
+	float_t radial_query(djb200_radial_what what, float_t x) const
+	{
+		float_t r;
+		radial_query_batch(what, &x, 1, &r);
+		return r;
+	}
 };
 
 // dj_brdf.h:374-391
@@ -708,6 +728,24 @@ protected:
 	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
 	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
 	{
+		upload();
+		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
+		switch (op) {
+		case 0: st = djb200_tabular_eval(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 1: st = djb200_tabular_evalp(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 2: st = djb200_tabular_pdf(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 3: st = djb200_tabular_sample(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 4: st = djb200_tabular_evalp_is(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
+		}
+		detail::check(st);
+	}
+	const djb200_tabular *radial_handle() const
+	{
+		upload();
+		return m_handle;
+	}
+	void upload() const
+	{
 		if (!m_handle || m_handle_rev != m_fresnel_rev) { // upload the tables once (again after set_fresnel)
 			djb200_tabular_destroy(m_handle);
 			m_handle = NULL;
@@ -722,15 +760,6 @@ protected:
 			detail::check(djb200_tabular_create(&f, m_shadow ? 1 : 0, &m_handle));
 			m_handle_rev = m_fresnel_rev;
 		}
-		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
-		switch (op) {
-		case 0: st = djb200_tabular_eval(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 1: st = djb200_tabular_evalp(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 2: st = djb200_tabular_pdf(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 3: st = djb200_tabular_sample(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 4: st = djb200_tabular_evalp_is(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
-		}
-		detail::check(st);
 	}
 
 private:

@@ -290,6 +290,21 @@ class PortOracle:
                                   c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data))
         return l1, l2
 
+    def radial_query(self, what, x, ndf=None, fit=None):
+        """djb::radial's p22_radial / sigma_std_radial / cdf_radial / qf_radial for an analytic family (ndf) or a
+        fit_tabular() result (fit)."""
+        code = {"p22": 0, "sigma_std": 1, "cdf": 2, "qf": 3}[what]
+        x = _f32(x)
+        out = np.zeros(len(x), np.float32)
+        if fit is not None:
+            t = [_f32(fit[k]) for k in ("p22", "sigma", "qf", "cdf")]
+            self.lib.orc_radial_query(C.c_int(2), C.c_int(code), *[c_f32p(a.ctypes.data) for a in t], C.c_int(len(t[0])),
+                                      c_f32p(x.ctypes.data), i64(len(x)), c_f32p(out.ctypes.data))
+        else:
+            self.lib.orc_radial_query(C.c_int(ndf), C.c_int(code), None, None, None, None, C.c_int(0),
+                                      c_f32p(x.ctypes.data), i64(len(x)), c_f32p(out.ctypes.data))
+        return out
+
     def dmap2nmap(self, dmap, scale=0.1):
         d = np.ascontiguousarray(dmap, np.uint8)
         h, w = d.shape
@@ -596,6 +611,25 @@ class RefOracle:
         L.ref_nmap2leanmap(C.c_void_p(nmap.ctypes.data), C.c_int(w), C.c_int(h), C.c_float(base_roughness),
                            c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data), C.c_int(int(run_check)))
         return l1, l2
+
+    def radial_query(self, what, x, ndf=None, src=None, res=90):
+        """the same queries on the reference's objects: djb::ggx / djb::beckmann (ndf) or djb::tabular(src, res)"""
+        code = {"p22": 0, "sigma_std": 1, "cdf": 2, "qf": 3}[what]
+        x = _f32(x)
+        out = np.zeros(len(x), np.float32)
+        if src is not None:
+            hs = self._source_handle(src)
+            h = C.c_void_p(self.lib.ref_tabular_create(hs, C.c_int(res), C.c_int(1)))
+        else:
+            hs, h = None, self.microfacet(ndf)
+        try:
+            rc = self.lib.ref_radial_query(h, C.c_int(code), c_f32p(x.ctypes.data), C.c_int(len(x)), c_f32p(out.ctypes.data))
+            assert rc == 0, rc
+        finally:
+            self.destroy(h)
+            if hs is not None:
+                self.destroy(hs)
+        return out
 
     def dmap2nmap(self, dmap, scale=0.1):
         d = np.ascontiguousarray(dmap, np.uint8)

@@ -1096,6 +1096,38 @@ ORC_API void orc_nmap2leanmap(const uint8_t *nmap, int w, int h, float base_roug
 #include "djb_oracle_fit.c"
 
 /* ---------------------------------------------------------------------------------------------
+ * the public scalar queries of djb::radial (:307-310): what = 0 p22_radial(r^2), 1 sigma_std_radial(cos), 2 cdf_radial(r),
+ * 3 qf_radial(u); family = ORC_NDF_BECKMANN / ORC_NDF_GGX / 2 (tabular: the four fitted tables of length res) */
+ORC_API void orc_radial_query(int family, int what, const float *p22, const float *sigma, const float *qf, const float *cdf,
+                              int res, const float *x, int64_t n, float *out)
+{
+	if (family == ORC_NDF_TABULAR) orc__set_tabular(p22, res, sigma, res);
+	for (int64_t k = 0; k < n; ++k) {
+		float v = x[k], r;
+		if (what == 0) r = p22_radial(family, v);
+		else if (what == 1) r = sigma_std_radial(family, v);
+		else if (family == ORC_NDF_TABULAR) {
+			if (what == 2) { /* tabular::cdf_radial, :2164-2169 */
+				float u = F(atan(D(v)) * D(2.0f) / D(F(ORC_PI)));
+				if (u < 0.0f) u = 0.0f;
+				r = orc__spline_eval_f(cdf, res, F(sqrt(D(u))));
+			} else { /* tabular::qf_radial, :2171-2176 */
+				float q = orc__spline_eval_f(qf, res, v);
+				r = F(tan(D(q * F(ORC_PI) / 2.0f)));
+			}
+		} else if (family == ORC_NDF_GGX) {
+			if (what == 2) { float t = v * v; r = F(D(t) / (1.0 + D(t))); } /* :2067-2071 */
+			else r = F(sqrt(D(v) / (1.0 - D(v))));                          /* :2073-2076 */
+		} else {
+			if (what == 2) r = F(1.0 - exp(D(-v * v)));                     /* :1881-1884 */
+			else r = F(sqrt(-log(1.0 - D(v))));                             /* :1886-1889 */
+		}
+		out[k] = r;
+	}
+	if (family == ORC_NDF_TABULAR) orc__set_tabular(NULL, 0, NULL, 0);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * dmap2nmap, utils/dmap2nmap.cpp:13-44: central differences of an 8-bit displacement map with CImg's atXY() clamping at
  * the borders, slopes scaled by (size / 2) * scale, unit normal packed as 8-bit RGB (truncating casts).
  * That file includes <math.h> through CImg.h, so its sqrt(float) is the float overload (unlike inside dj_brdf.h). */

@@ -352,6 +352,24 @@ REF_API int ref_tabular_anisotropic_get(void *tabh, float *p22, float *sigma, fl
 	return (int)pv.size();
 }
 
+// the four public scalar queries of djb::radial (dj_brdf.h:307-310): what = 0 p22_radial, 1 sigma_std_radial, 2 cdf_radial,
+// 3 qf_radial
+REF_API int ref_radial_query(void *h, int what, const float *x, int n, float *out)
+{
+	const djb::radial *r = dynamic_cast<djb::radial *>(static_cast<djb::brdf *>(h));
+	if (!r) return -1;
+	for (int k = 0; k < n; ++k) {
+		switch (what) {
+		case 0: out[k] = r->p22_radial(x[k]); break;
+		case 1: out[k] = r->sigma_std_radial(x[k]); break;
+		case 2: out[k] = r->cdf_radial(x[k]); break;
+		case 3: out[k] = r->qf_radial(x[k]); break;
+		default: return -2;
+		}
+	}
+	return 0;
+}
+
 // radial queries used by tests/plot_qf.cpp and tests/plot_cdf.cpp of the reference
 REF_API int ref_radial_qf_cdf(void *h, const float *x, int n, float *qf_out, float *cdf_out)
 {

@@ -41,6 +41,6 @@ torch.cuda.synchronize()
 PY
 ncu --set full --clock-control none --import-source on \
     -k regex:'mf_lean_kernel|analytic_eval_kernel|dmap2nmap_kernel|aniso_sampling_tables_kernel' -c 12 -f \
-    -o gpurun_out/prof_r01_e_new python /tmp/new_kernels.py > gpurun_out/ncu_new_e.log 2>&1
+    -o gpurun_out/prof_r01_e_new env PYTHONPATH=$PWD python /tmp/new_kernels.py > gpurun_out/ncu_new_e.log 2>&1
 tail -2 gpurun_out/ncu_new_e.log
 tail -2 gpurun_out/bench_e.err

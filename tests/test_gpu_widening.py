@@ -145,3 +145,21 @@ def test_dmap2nmap_bit_exact(djb, port):
     l1, l2 = djb.nmap2leanmap(nm, 1e-5, 25.0)
     w1, w2 = port.nmap2leanmap(port.dmap2nmap(d, 0.01), 1e-5, 25.0)
     assert bits_equal(l1.cpu().numpy(), w1).all() and bits_equal(l2.cpu().numpy(), w2).all()
+
+
+# ---- djb::radial's public scalar queries (dj_brdf.h:307-310) --------------------------------------------------------------
+def test_radial_scalar_queries(djb, port):
+    rng = np.random.default_rng(4)
+    args = dict(p22=rng.uniform(0, 30, 50_000), sigma_std=rng.uniform(-1, 1, 50_000), cdf=rng.uniform(0, 20, 50_000),
+                qf=rng.uniform(1e-4, 1 - 1e-4, 50_000))
+    args["sigma_std"][:3] = [1.0, 0.0, -1.0]
+    args = {k: v.astype(np.float32) for k, v in args.items()}
+    for ndf, cls in ((api.NDF_GGX, djb.ggx), (api.NDF_BECKMANN, djb.beckmann)):
+        for what, x in args.items():
+            got, want = getattr(cls(), what + "_radial")(x), port.radial_query(what, x, ndf=ndf)
+            assert rel_err(got, want).max() <= REL_TOL and bits_equal(got, want).mean() >= 0.999, (ndf, what)
+    t = djb.tabular(djb.beckmann(), 90)
+    fit = dict(p22=t.m_p22, sigma=t.m_sigma, qf=t.m_qf, cdf=t.m_cdf)
+    for what, x in args.items():
+        got, want = getattr(t, what + "_radial")(x), port.radial_query(what, x, fit=fit)
+        assert rel_err(got, want).max() <= REL_TOL and bits_equal(got, want).mean() >= 0.999, ("tabular", what)

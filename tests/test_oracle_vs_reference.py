@@ -176,3 +176,18 @@ def test_dmap2nmap_bit_identical(port, ref):
     for h, w, sc in ((37, 53, 0.1), (64, 64, 0.01), (5, 300, 1.0), (1, 1, 0.1), (2, 1, 0.3), (128, 256, 0.05)):
         d = rng.integers(0, 256, (h, w), dtype=np.uint8)
         assert np.array_equal(port.dmap2nmap(d, sc), ref.dmap2nmap(d, sc)), (h, w, sc)
+
+
+def test_radial_scalar_queries_bit_identical(port, ref):
+    """p22_radial / sigma_std_radial / cdf_radial / qf_radial of djb::radial (what tests/plot_qf.cpp, plot_cdf.cpp tabulate)"""
+    rng = np.random.default_rng(4)
+    args = dict(p22=rng.uniform(0, 30, 4000), sigma_std=rng.uniform(-1, 1, 4000), cdf=rng.uniform(0, 20, 4000),
+                qf=rng.uniform(1e-4, 1 - 1e-4, 4000))
+    args["sigma_std"][:3] = [1.0, 0.0, -1.0]
+    for ndf in (api.NDF_GGX, api.NDF_BECKMANN):
+        for what, x in args.items():
+            assert bits_equal(port.radial_query(what, x, ndf=ndf), ref.radial_query(what, x, ndf=ndf)).all(), (ndf, what)
+    src = api.Source.microfacet(api.NDF_BECKMANN)
+    fit = port.fit_tabular(src, 90)
+    for what, x in args.items():
+        assert bits_equal(port.radial_query(what, x, fit=fit), ref.radial_query(what, x, src=src, res=90)).all(), what

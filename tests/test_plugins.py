@@ -171,3 +171,33 @@ def test_wavefront_adapter_matches_scalar_plugin(djb, binaries, tmp_path, plugin
     g, w = got[same][:, [4, 5, 6, 10]].astype(np.float64), want[same][:, [4, 5, 6, 10]].astype(np.float64)
     scale = np.maximum(np.abs(w), 1e-3 * max(1e-30, np.abs(w).max()))
     assert (np.abs(g - w) / scale).max() <= 1e-4, (tag, "sample weight / pdf")
+
+
+# ---- the reference's own test programs (tests/plot_qf.cpp, plot_cdf.cpp, nrm_utia.cpp), unmodified, on the facade ---------
+REFTESTS = ["plot_qf", "plot_cdf", "nrm_utia"]
+
+
+def test_reference_test_programs_build_against_the_facade(binaries):
+    for t in REFTESTS:
+        b = BIN / f"reftest_{t}_b200"
+        assert b.exists() and (BIN / f"reftest_{t}_ref").exists(), t
+        assert "libdjb200.so" in subprocess.run(["readelf", "-d", str(b)], capture_output=True, text=True).stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", ["plot_qf", "plot_cdf"])
+def test_reference_plot_programs_match(binaries, tmp_path, prog):
+    """plot_qf / plot_cdf write the radial quantile / distribution tables of beckmann, ggx and their tabulated fits (res
+    180) as text: the GPU-backed build must write the reference build's tables (%f text: 1e-6 absolute + 1e-5 relative)."""
+    outs = {}
+    for side in ("ref", "b200"):
+        d = tmp_path / side
+        d.mkdir()
+        r = subprocess.run([str(BIN / f"reftest_{prog}_{side}")], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs[side] = {p.name: np.loadtxt(p) for p in sorted(d.glob("*.txt"))}
+    assert outs["ref"].keys() == outs["b200"].keys() and len(outs["ref"]) == 4
+    for name, want in outs["ref"].items():
+        got = outs["b200"][name]
+        assert got.shape == want.shape == (89, 2), name
+        assert np.abs(got - want).max() <= 2e-6 + 1e-5 * np.abs(want).max(), (name, float(np.abs(got - want).max()))
