@@ -8,6 +8,10 @@
 
 #include "djb200_wavefront.hpp"
 
+// the plugins read their roughness textures through Spectrum::average() (mitsuba/dj_brdf.cpp:354-356): for a grey texel
+// v that is (v + v + v) * (1 / 3), which is not always v in float -- a renderer hands the adapters the same number
+static float spectrum_average(float v) { return (v + v + v) * (1.0f / 3.0f); }
+
 int main(int argc, char **argv)
 {
 	if (argc != 4) return 2;
@@ -25,7 +29,7 @@ int main(int argc, char **argv)
 			wi[k] = djb::vec3(r[0], r[1], r[2]);
 			wo[k] = djb::vec3(r[3], r[4], r[5]);
 			u[2 * k] = r[6]; u[2 * k + 1] = r[7];
-			memcpy(&a3[3 * k], r + 8, 12);
+			for (int c = 0; c < 3; ++c) a3[3 * k + c] = spectrum_average(r[8 + c]);
 			memcpy(&e5[5 * k], r + 11, 20);
 		}
 		djb::wavefront::records R;
@@ -35,7 +39,7 @@ int main(int argc, char **argv)
 			const bool lean = mode == "lean";
 			R.alpha3 = lean ? a3.data() : NULL; // the "naive_mip" config of the test keeps constant roughness
 			R.lean5 = e5.data();
-			djb::wavefront::beckmann_conductor b(0.1f, 0.1f, 0.0f, lean, lean ? 1.5f : 1.0f);
+			djb::wavefront::beckmann_conductor b(spectrum_average(0.1f), spectrum_average(0.1f), 0.0f, lean, lean ? 1.5f : 1.0f);
 			b.eval(R, ev.data());
 			b.pdf(R, pdf.data());
 			b.sample(R, w.data(), swo.data(), spdf.data());
