@@ -190,14 +190,9 @@ cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base
 // 8-bit RGB.  1 B in (+ 4 neighbours, which the row / L2 locality makes free) and 3 B out per texel: HBM bound.
 // That utility is compiled with <math.h> in scope, so its sqrt(float) is sqrtf; 1.0 / x and 0.5 * n + 0.5 are double
 // expressions rounded once to float -- one IEEE reciprocal and one fused multiply-add give the same floats.
-DJB_DEV void dmap_texel(const uint8_t *__restrict__ d, int w, int h, int i, int j, float kx, float ky, uint8_t &r, uint8_t &g,
-                        uint8_t &b)
+// one texel from its four neighbours' heights (already divided by 255)
+DJB_DEV void dmap_normal(float z_l, float z_r, float z_b, float z_t, float kx, float ky, uint8_t &r, uint8_t &g, uint8_t &b)
 {
-	const int il = i > 0 ? i - 1 : 0, ir = i + 1 < w ? i + 1 : w - 1;
-	const int jt = j > 0 ? j - 1 : 0, jb = j + 1 < h ? j + 1 : h - 1;
-	const size_t row = (size_t)j * w;
-	const float z_l = (float)d[il + row] / 255.f, z_r = (float)d[ir + row] / 255.f;
-	const float z_b = (float)d[i + (size_t)jb * w] / 255.f, z_t = (float)d[i + (size_t)jt * w] / 255.f;
 	const float sx = kx * (z_r - z_l), sy = ky * (z_t - z_b);
 	const float nrm_sqr = 1.f + sx * sx + sy * sy;
 	const float nrm_inv = __frcp_rn(__fsqrt_rn(nrm_sqr));
@@ -207,34 +202,56 @@ DJB_DEV void dmap_texel(const uint8_t *__restrict__ d, int w, int h, int i, int 
 	b = (uint8_t)(nrm_inv * 255.f);
 }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(TB) dmap2nmap_kernel(const uint8_t *__restrict__ d, int w, int h, float scale,
-                                                       uint8_t *__restrict__ out)
+// Row-walking variant for w % 4 == 0 and 4-byte aligned rows: a thread owns four consecutive texels of a column quad and
+// walks down the rows (no index divisions); three 32-bit loads + two bytes bring in all 14 neighbours, and the
+// reference's `(float)px / 255.f` -- 256 possible operands -- comes from a shared-memory table filled with that division.
+__global__ void __launch_bounds__(TB) dmap2nmap_rows_kernel(const uint8_t *__restrict__ d, int w, int h, float scale,
+                                                            uint8_t *__restrict__ out)
+{
+	__shared__ float s_z[256];
+	for (int t = threadIdx.x; t < 256; t += blockDim.x) s_z[t] = (float)t / 255.f;
+	__syncthreads();
+	const int iq = blockIdx.x * blockDim.x + threadIdx.x;
+	if (iq >= w / 4) return;
+	const int i0 = 4 * iq;
+	const float kx = (float)w * 0.5f * scale, ky = (float)h * 0.5f * scale;
+	const size_t plane = (size_t)w * h;
+	for (int j = blockIdx.y; j < h; j += gridDim.y) {
+		const uint8_t *row = d + (size_t)j * w;
+		const uchar4 c = *reinterpret_cast<const uchar4 *>(row + i0);
+		const uchar4 t = *reinterpret_cast<const uchar4 *>(d + (size_t)(j > 0 ? j - 1 : 0) * w + i0);
+		const uchar4 b = *reinterpret_cast<const uchar4 *>(d + (size_t)(j + 1 < h ? j + 1 : h - 1) * w + i0);
+		const float zl = s_z[row[i0 > 0 ? i0 - 1 : 0]], zr = s_z[row[i0 + 4 < w ? i0 + 4 : w - 1]];
+		const float z0 = s_z[c.x], z1 = s_z[c.y], z2 = s_z[c.z], z3 = s_z[c.w];
+		uchar4 R, G, B;
+		dmap_normal(zl, z1, s_z[b.x], s_z[t.x], kx, ky, R.x, G.x, B.x);
+		dmap_normal(z0, z2, s_z[b.y], s_z[t.y], kx, ky, R.y, G.y, B.y);
+		dmap_normal(z1, z3, s_z[b.z], s_z[t.z], kx, ky, R.z, G.z, B.z);
+		dmap_normal(z2, zr, s_z[b.w], s_z[t.w], kx, ky, R.w, G.w, B.w);
+		const size_t o = (size_t)j * w + i0;
+		__stcs(reinterpret_cast<uchar4 *>(out + o), R);
+		__stcs(reinterpret_cast<uchar4 *>(out + plane + o), G);
+		__stcs(reinterpret_cast<uchar4 *>(out + 2 * plane + o), B);
+	}
+}
+
+// any size / alignment: one texel per thread
+__global__ void __launch_bounds__(TB) dmap2nmap_scalar_kernel(const uint8_t *__restrict__ d, int w, int h, float scale,
+                                                              uint8_t *__restrict__ out)
 {
 	const float kx = (float)w * 0.5f * scale, ky = (float)h * 0.5f * scale;
 	const long long plane = (long long)w * h, stride = (long long)gridDim.x * blockDim.x;
-	if (VEC4) { // w % 4 == 0 and 4-byte aligned planes: four texels of one row per thread, 32-bit stores
-		const long long nq = plane / 4;
-		for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
-			const long long px = 4 * q;
-			const int j = (int)(px / w), i0 = (int)(px % w);
-			uchar4 r, g, b;
-			dmap_texel(d, w, h, i0, j, kx, ky, r.x, g.x, b.x);
-			dmap_texel(d, w, h, i0 + 1, j, kx, ky, r.y, g.y, b.y);
-			dmap_texel(d, w, h, i0 + 2, j, kx, ky, r.z, g.z, b.z);
-			dmap_texel(d, w, h, i0 + 3, j, kx, ky, r.w, g.w, b.w);
-			reinterpret_cast<uchar4 *>(out)[q] = r;
-			reinterpret_cast<uchar4 *>(out + plane)[q] = g;
-			reinterpret_cast<uchar4 *>(out + 2 * plane)[q] = b;
-		}
-	} else {
-		for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < plane; px += stride) {
-			uint8_t r, g, b;
-			dmap_texel(d, w, h, (int)(px % w), (int)(px / w), kx, ky, r, g, b);
-			out[px] = r;
-			out[plane + px] = g;
-			out[2 * plane + px] = b;
-		}
+	for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < plane; px += stride) {
+		const int i = (int)(px % w), j = (int)(px / w);
+		const int il = i > 0 ? i - 1 : 0, ir = i + 1 < w ? i + 1 : w - 1;
+		const int jt = j > 0 ? j - 1 : 0, jb = j + 1 < h ? j + 1 : h - 1;
+		const size_t row = (size_t)j * w;
+		uint8_t r, g, b;
+		dmap_normal((float)d[il + row] / 255.f, (float)d[ir + row] / 255.f, (float)d[i + (size_t)jb * w] / 255.f,
+		            (float)d[i + (size_t)jt * w] / 255.f, kx, ky, r, g, b);
+		out[px] = r;
+		out[plane + px] = g;
+		out[2 * plane + px] = b;
 	}
 }
 
@@ -242,9 +259,16 @@ cudaError_t launch_dmap2nmap(const uint8_t *dmap, int w, int h, float scale, uin
 {
 	const int64_t plane = (int64_t)w * h;
 	if (plane <= 0) return cudaSuccess;
-	const bool vec = (w % 4 == 0) && ((uintptr_t)nmap % 4 == 0);
-	if (vec) dmap2nmap_kernel<true><<<grid_for(plane / 4), TB, 0, st>>>(dmap, w, h, scale, nmap);
-	else dmap2nmap_kernel<false><<<grid_for(plane), TB, 0, st>>>(dmap, w, h, scale, nmap);
+	const bool vec = (w % 4 == 0) && ((uintptr_t)nmap % 4 == 0) && ((uintptr_t)dmap % 4 == 0);
+	if (vec) {
+		const int wq = w / 4, gx = (wq + TB - 1) / TB;
+		int gy = (sm_count() * 8 + gx - 1) / gx; // ~8 resident CTAs per SM in all
+		if (gy > h) gy = h;
+		if (gy > 65535) gy = 65535;
+		dmap2nmap_rows_kernel<<<dim3(gx, gy), TB, 0, st>>>(dmap, w, h, scale, nmap);
+	} else {
+		dmap2nmap_scalar_kernel<<<grid_for(plane), TB, 0, st>>>(dmap, w, h, scale, nmap);
+	}
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	return cudaGetLastError();
 }
