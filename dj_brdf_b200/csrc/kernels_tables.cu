@@ -190,6 +190,10 @@ cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base
 // 8-bit RGB.  1 B in (+ 4 neighbours, which the row / L2 locality makes free) and 3 B out per texel: HBM bound.
 // That utility is compiled with <math.h> in scope, so its sqrt(float) is sqrtf; 1.0 / x and 0.5 * n + 0.5 are double
 // expressions rounded once to float -- one IEEE reciprocal and one fused multiply-add give the same floats.
+// (uint8_t)v for 0 <= v < 2^23 without the quarter-rate F2I: adding 2^23 with round-toward-zero leaves floor(v) in the low
+// mantissa bits (the float grid at 2^23 is the integers)
+DJB_DEV uint8_t trunc_u8(float v) { return (uint8_t)(__float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu); }
+
 // one texel from its four neighbours' heights (already divided by 255)
 DJB_DEV void dmap_normal(float z_l, float z_r, float z_b, float z_t, float kx, float ky, uint8_t &r, uint8_t &g, uint8_t &b)
 {
@@ -197,9 +201,9 @@ DJB_DEV void dmap_normal(float z_l, float z_r, float z_b, float z_t, float kx, f
 	const float nrm_sqr = 1.f + sx * sx + sy * sy;
 	const float nrm_inv = __frcp_rn(__fsqrt_rn(nrm_sqr));
 	const float nx = -sx * nrm_inv, ny = -sy * nrm_inv;
-	r = (uint8_t)(__fmaf_rn(0.5f, nx, 0.5f) * 255.f);
-	g = (uint8_t)(__fmaf_rn(0.5f, ny, 0.5f) * 255.f);
-	b = (uint8_t)(nrm_inv * 255.f);
+	r = trunc_u8(__fmaf_rn(0.5f, nx, 0.5f) * 255.f);
+	g = trunc_u8(__fmaf_rn(0.5f, ny, 0.5f) * 255.f);
+	b = trunc_u8(nrm_inv * 255.f);
 }
 
 // Row-walking variant for w % 4 == 0 and 4-byte aligned rows: a thread owns four consecutive texels of a column quad and
