@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "NO_DEVICE", 3: "CUDA", 4: "O
 # every symbol include/djb200.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
     "djb200_last_error", "djb200_version", "djb200_device_count", "djb200_set_device",
-    "djb200_kernel_launch_count", "djb200_release_cache", "djb200_debug_force_generic",
+    "djb200_kernel_launch_count", "djb200_release_cache", "djb200_debug_force_generic", "djb200_debug_beckmann_compaction",
     "djb200_params_standard", "djb200_params_isotropic", "djb200_params_elliptic", "djb200_params_pdfparams",
     "djb200_microfacet_eval", "djb200_microfacet_evalp", "djb200_microfacet_pdf", "djb200_microfacet_sample",
     "djb200_microfacet_evalp_is",

@@ -574,6 +574,12 @@ djb200_status djb200_debug_force_generic(int on)
 	return DJB200_OK;
 }
 
+djb200_status djb200_debug_beckmann_compaction(int on)
+{
+	g_beck_compact.store(on ? 1 : 0);
+	return DJB200_OK;
+}
+
 djb200_status djb200_release_cache(void)
 {
 	t_arena.release();

@@ -65,6 +65,7 @@ struct MfLaunch {
 
 extern std::atomic<uint64_t> g_kernel_launches;
 extern std::atomic<int> g_force_generic; // kernels_mf.cu: 1 = never take the lean FP32 kernels
+extern std::atomic<int> g_beck_compact;  // kernels_mf.cu: 0 = Beckmann BROADCAST queries stay on the uncompacted lean kernel
 int sm_count();
 
 cudaError_t launch_microfacet(const MfLaunch &L, cudaStream_t st);

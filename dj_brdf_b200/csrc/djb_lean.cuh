@@ -798,17 +798,22 @@ DJB_DEV float lean_ndf(const float2 *T, const ParamsX &m, const PairX &c)
 	return div_by(div_by(pv, m.nrm, m.rcp_nrm), c.c4, c.rcp_c4);
 }
 
-// F D G / (4 o.z) (evalp, dj_brdf.h:1529-1547); `scale` = 1 / i.z for eval (dj_brdf.h:1551-1555), unused otherwise
-template <int NDF, int FK, int OP>
-DJB_DEV V3 lean_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)
+// F D G / (4 o.z) (evalp, dj_brdf.h:1529-1547); `scale` = 1 / i.z for eval (dj_brdf.h:1551-1555), unused otherwise.
+// Split in two so that the Beckmann kernel can compact the expensive second half across a warp (kernels_mf.cu):
+//   head: Dn = lean_ndf; if lean_skip(Dn, c) the result is lean_zero<OP>(c) -- D == 0 (h below the 1e-4 gate, or Beckmann's
+//         exponential underflowed) makes F D G / (4 o.z) +0 for o.z > 0 whatever G is, so both projected areas are skipped;
+//   tail: the shadowing term, the Fresnel term and the quotient, from Dn and the pair.
+DJB_DEV bool lean_skip(float Dn, const PairX &c) { return Dn == 0.0f && c.den > 0.0f; }
+template <int OP>
+DJB_DEV V3 lean_zero(const PairX &c)
 {
 	const V3 z = mk(0.f, 0.f, 0.f);
-	const V3 zero = OP == OP_EVAL ? scale(c.inv_iz, z) : z; // 0 * (1 / i.z): keeps the reference's -0 / NaN for i.z <= 0
-	const float Dn = lean_ndf<NDF>(T, m, c);
-	// D == 0 (h below the 1e-4 gate, or Beckmann's exponential underflowed): F D G / (4 o.z) is +0 for o.z > 0
-	// whatever G is, so the two projected-area evaluations are skipped
-	if (Dn == 0.0f && c.den > 0.0f) return zero;
-	const float G = lean_gaf<NDF>(T, m.p, shadow, c.i, c.o);
+	return OP == OP_EVAL ? scale(c.inv_iz, z) : z; // 0 * (1 / i.z): keeps the reference's -0 / NaN for i.z <= 0
+}
+template <int NDF, int FK, int OP>
+DJB_DEV V3 lean_evalp_tail(const float2 *T, const Params &p, const FresnelDev &f, bool shadow, const PairX &c, float Dn)
+{
+	const float G = lean_gaf<NDF>(T, p, shadow, c.i, c.o);
 	if (G > 0.0f) {
 		const float num = Dn * G;
 		float k;
@@ -817,17 +822,21 @@ DJB_DEV V3 lean_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bo
 		V3 e = scale(k, fresnel_eval<FK>(f, c.cd));
 		return OP == OP_EVAL ? scale(c.inv_iz, e) : e;
 	}
-	return zero;
+	return lean_zero<OP>(c);
+}
+template <int NDF, int FK, int OP>
+DJB_DEV V3 lean_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)
+{
+	const float Dn = lean_ndf<NDF>(T, m, c);
+	if (lean_skip(Dn, c)) return lean_zero<OP>(c);
+	return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, Dn);
 }
 
 // microfacet::pdf, dj_brdf.h:1713-1730 with vndf, dj_brdf.h:1602-1615.  sigma(o) appears in G1(o) and in the
-// visible-normal density: evaluated once.
+// visible-normal density: evaluated once.  Same head / tail split (vndf == 0: the pdf is +0 whatever G is).
 template <int NDF>
-DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c)
+DJB_DEV float lean_pdf_tail(const float2 *T, const Params &p, bool shadow, const PairX &c, float Dn)
 {
-	const float Dn = lean_ndf<NDF>(T, m, c);
-	if (Dn == 0.0f && c.den > 0.0f) return 0.0f; // vndf == 0: the pdf is +0 whatever G is
-	const Params &p = m.p;
 	const float sg_o = lean_sigma<NDF>(T, p, c.o);
 	const float rsg_o = rcp_lean(sg_o);
 	const float g1o = dot(c.o, mk(p.nx, p.ny, p.nz)) > 0.0f ? div_by(c.o.z, sg_o, rsg_o) : 0.0f;
@@ -848,6 +857,13 @@ DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const Pai
 		return NDF == NDF_GGX ? div_by(v, c.den, c.rcp_den) : div_by_small(v, c.den, c.rcp_den);
 	}
 	return 0.0f;
+}
+template <int NDF>
+DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c)
+{
+	const float Dn = lean_ndf<NDF>(T, m, c);
+	if (lean_skip(Dn, c)) return 0.0f;
+	return lean_pdf_tail<NDF>(T, m.p, shadow, c, Dn);
 }
 
 // microfacet::evalp_is, dj_brdf.h:1734-1765: sample, weight F G / G1(o), pdf = vndf / (4 cos theta_d)

@@ -108,6 +108,10 @@ DJB200_API djb200_status djb200_release_cache(void);
  * (double sub-expressions literally as in the reference), 0 (default) = the lean FP32 kernels where they apply.
  * Both give the reference's rounded results; tests/test_gpu_parity.py compares them at full size. */
 DJB200_API djb200_status djb200_debug_force_generic(int on);
+/* Debug switch for A/B tests: 0 = Beckmann eval / evalp / pdf over several materials (BROADCAST) run on the plain lean
+ * kernel instead of the warp-compacting one (csrc/kernels_mf.cu, mf_beck_compact_kernel); 1 (default) = compaction on.
+ * The two produce the same floats (same functions on the same operands, scheduled on other lanes). */
+DJB200_API djb200_status djb200_debug_beckmann_compaction(int on);
 
 /* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
 DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */

@@ -390,3 +390,41 @@ def test_host_pipeline_many_chunks(djb, port, monkeypatch):
     m = djb.merl(table)
     assert bits_equal(m.eval(wi, wo), m.eval(dwi, dwo).cpu().numpy()).all()
     assert (djb.merl.index(wi, wo) == djb.merl.index(dwi, dwo).cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("fname", ["ideal", "schlick"])
+def test_beckmann_compaction_is_bit_identical(djb, port, fname):
+    """mf_beck_compact_kernel (shadowing work compacted across the warp) against the plain lean kernel: the same functions
+    run on the same operands on other lanes, so every result must be the same float -- ragged sizes (tail warps, a single
+    pair), edge directions, 2 .. 40 materials, and against the oracle."""
+    import ctypes as C
+    import torch
+    from dj_brdf_b200 import capi
+    lib = capi.load()
+    f = api.Fresnel.ideal() if fname == "ideal" else cases.fresnels()["schlick"]
+    b = mk_brdf(djb, api.NDF_BECKMANN, f)
+    ewi, ewo, _ = cases.edge_pairs()
+    try:
+        for n, nm in ((1, 2), (31, 3), (33, 16), (1_000_003, 16), (200_000, 40)):
+            wi, wo, _ = cases.pairs(n, stream=900 + nm)
+            if n > 1000:
+                wi, wo = np.concatenate([wi, ewi]), np.concatenate([wo, ewo])
+            mats = cases.c2_materials(port, nm, seed=nm)
+            mats[-1] = port.params_pdfparams(0.3, 0.2, 0.4, 0.1, -0.2)
+            twi, two = torch.from_numpy(wi).cuda(), torch.from_numpy(wo).cuda()
+            for q in ("eval", "evalp", "pdf"):
+                lib.djb200_debug_beckmann_compaction(C.c_int(1))
+                on = getattr(b, q)(twi, two, mats).cpu().numpy()
+                lib.djb200_debug_beckmann_compaction(C.c_int(0))
+                off = getattr(b, q)(twi, two, mats).cpu().numpy()
+                assert bits_equal(on, off).all(), (n, nm, q)
+        # against the oracle with compaction on (default)
+        lib.djb200_debug_beckmann_compaction(C.c_int(1))
+        wi, wo, _ = cases.pairs(50_000, stream=77)
+        mats = cases.c2_materials(port, 16)
+        got_e, got_p = b.eval(wi, wo, mats), b.pdf(wi, wo, mats)
+        for m in range(16):
+            check_close(got_e[m], port.eval(api.NDF_BECKMANN, mats[m], wi, wo, f), f"compact eval m{m}", min_bit_rate=0.9999)
+            check_close(got_p[m], port.pdf(api.NDF_BECKMANN, mats[m], wi, wo, f), f"compact pdf m{m}", min_bit_rate=0.9999)
+    finally:
+        lib.djb200_debug_beckmann_compaction(C.c_int(1))
