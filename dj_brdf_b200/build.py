@@ -29,6 +29,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2",
     "-Xptxas", "-v",
+    *os.environ.get("DJB200_NVCC_EXTRA", "").split(),  # experiments only (e.g. -DDJB200_COMPACT_MINB=4)
 ]
 
 

@@ -780,22 +780,32 @@ DJB_DEV float lean_gaf(const float2 *T, const Params &p, bool shadow, V3 i, V3 o
 	return g1o;
 }
 
-// microfacet::ndf + p22, dj_brdf.h:1559-1587, with the per-pair and per-material reciprocals
-template <int NDF>
-DJB_DEV float lean_ndf(const float2 *T, const ParamsX &m, const PairX &c)
+// microfacet::ndf + p22, dj_brdf.h:1559-1587, with the per-pair and per-material reciprocals.  In two steps so that the
+// Beckmann kernel can test the cheap part (squared standard-space slope radius) on every lane and compact the rest:
+// r2 > 103.5 means exp(-r2) / pi rounds to zero, i.e. D == 0 exactly (beck_p22_lean's first test).
+DJB_DEV float lean_ndf_r2(const ParamsX &m, const PairX &c)
 {
-	if (!c.facing) return 0.0f;
 	float x = c.sx - m.p.tx, y = c.sy - m.p.ty;
 	float xs = div_by(x, m.p.ax, m.rcp_ax);
 	float t1 = m.p.ax * y - m.rho_ay * x;
 	float ys = div_by(t1, m.nrm, m.rcp_nrm);
-	float r2 = xs * xs + ys * ys;
+	return xs * xs + ys * ys;
+}
+template <int NDF>
+DJB_DEV float lean_ndf_from_r2(const float2 *T, const ParamsX &m, const PairX &c, float r2)
+{
 	float pv = NDF == NDF_BECKMANN ? beck_p22_lean(T, r2) : p22_radial<NDF_GGX>(r2);
 	if (NDF == NDF_BECKMANN) { // the exponential underflows gradually: small numerators take the lifted division
 		if (pv == 0.0f) return 0.0f;
 		return div_by_small(div_by_small(pv, m.nrm, m.rcp_nrm), c.c4, c.rcp_c4);
 	}
 	return div_by(div_by(pv, m.nrm, m.rcp_nrm), c.c4, c.rcp_c4);
+}
+template <int NDF>
+DJB_DEV float lean_ndf(const float2 *T, const ParamsX &m, const PairX &c)
+{
+	if (!c.facing) return 0.0f;
+	return lean_ndf_from_r2<NDF>(T, m, c, lean_ndf_r2(m, c));
 }
 
 // F D G / (4 o.z) (evalp, dj_brdf.h:1529-1547); `scale` = 1 / i.z for eval (dj_brdf.h:1551-1555), unused otherwise.

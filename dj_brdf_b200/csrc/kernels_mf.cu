@@ -231,49 +231,55 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 	}
 }
 
-// Beckmann eval / evalp / pdf, BROADCAST layout, with the shadowing work COMPACTED across the warp.
-// For a material whose lobe is narrow, D underflows to zero for most random pairs and the result is +0 without evaluating the
-// two projected areas (the expensive half: sqrt, reciprocal, exp and erf each).  In mf_lean_kernel the lanes that do need
-// them run with the others idle -- measured 18 of 32 lanes active per instruction on the benchmark's 16 materials.  Here
-// every lane evaluates D for its own pair under every material (full warp), lanes with D != 0 push a work item
-// (source lane, material, D) into a per-warp queue in shared memory, and whenever 32 items are waiting the whole warp
-// evaluates their second halves, one item per lane, reading the source lane's pair from shared memory.  Results are the
-// same floats: the same functions run on the same operands, only on another lane.
-struct PairS { float4 a, b, c, d; }; // i.xyz o.x | o.yz h.xy | h.z den rcp_den inv_iz | cd den_ok - -
+// Beckmann eval / evalp / pdf, BROADCAST layout, with the expensive work COMPACTED across the warp.
+// For a material whose lobe is narrow, D underflows to zero for most random pairs, and the result is then +0 without the
+// exponential and without the two projected areas (sqrt, reciprocal, exp and erf each).  In mf_lean_kernel the lanes that
+// do need them run with the others idle -- measured 18 of 32 lanes active per instruction on the benchmark's 16 materials.
+// Here every lane does only the cheap test for its own pair under every material (the squared standard-space slope radius
+// r2; r2 > 103.5 <=> D == 0), lanes that pass push a work item (source lane, material, r2) into a per-warp queue in shared
+// memory, and whenever 32 items are waiting the whole warp evaluates them, one item per lane, reading the source lane's
+// pair from shared memory.  Results are the same floats: the same functions run on the same operands, on another lane.
+struct PairS { float4 a, b, c, d; }; // i.xyz o.x | o.yz h.xy | h.z den rcp_den inv_iz | cd den_ok c4 rcp_c4
 
+#ifndef DJB200_COMPACT_MINB
+#define DJB200_COMPACT_MINB 1
+#endif
 template <int FK, int OP>
-__global__ void __launch_bounds__(MF_THREADS) mf_beck_compact_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compact_kernel(MfKernelArgs A)
 {
 	constexpr int NDF = NDF_BECKMANN;
 	constexpr int WARPS = MF_THREADS / 32;
 	__shared__ ParamsX s_params[MF_MAX_SMEM_PARAMS];
 	__shared__ float2 s_exp2[64];
 	__shared__ PairS s_pair[MF_THREADS];
-	__shared__ uint2 s_q[WARPS][64];
+	__shared__ uint2 s_q[WARPS][64], s_qs[WARPS][64];
 	for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
 	if (threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
+	for (int t = threadIdx.x; t < WARPS * 64; t += blockDim.x) (&s_q[0][0])[t] = (&s_qs[0][0])[t] = make_uint2(0u, 0u);
 	__syncthreads();
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
-	uint2 *q = s_q[warp];
+	uint2 *q = s_q[warp], *qs = s_qs[warp];
 	PairS *pairs = s_pair + warp * 32;
 
-	// second half of one queued item, run by whichever lane picked it up
+	// one queued item, run by whichever lane picked it up: D from r2, then (unless D == 0) shadowing, Fresnel, quotient
 	auto finish = [&](uint2 item, long long kb) {
 		const int src = item.x & 31, m = item.x >> 8;
-		const float Dn = __uint_as_float(item.y);
 		const PairS s = pairs[src];
 		PairX c;
 		c.i = mk(s.a.x, s.a.y, s.a.z);
 		c.o = mk(s.a.w, s.b.x, s.b.y);
 		c.h = mk(s.b.z, s.b.w, s.c.x);
 		c.den = s.c.y; c.rcp_den = s.c.z; c.inv_iz = s.c.w;
-		c.cd = s.d.x; c.den_ok = s.d.y != 0.0f;
+		c.cd = s.d.x; c.den_ok = s.d.y != 0.0f; c.c4 = s.d.z; c.rcp_c4 = s.d.w;
+		const ParamsX &mx = s_params[m];
+		// item.y: r2, or the NaN-free marker "not facing" (D == 0 with a non-positive denominator: the rare literal case)
+		const float Dn = (item.x & 0x80u) ? 0.0f : lean_ndf_from_r2<NDF>(s_exp2, mx, c, __uint_as_float(item.y));
 		const long long slot = (long long)m * A.out_stride + kb + src;
-		if (OP == OP_PDF) A.out0[slot] = lean_pdf_tail<NDF>(s_exp2, s_params[m].p, shadow, c, Dn);
-		else st3(A.out0, slot, lean_evalp_tail<NDF, FK, OP>(s_exp2, s_params[m].p, fr, shadow, c, Dn));
+		if (OP == OP_PDF) A.out0[slot] = lean_skip(Dn, c) ? 0.0f : lean_pdf_tail<NDF>(s_exp2, mx.p, shadow, c, Dn);
+		else st3(A.out0, slot, lean_skip(Dn, c) ? lean_zero<OP>(c) : lean_evalp_tail<NDF, FK, OP>(s_exp2, mx.p, fr, shadow, c, Dn));
 	};
 
 	const long long stride = (long long)gridDim.x * blockDim.x;
@@ -290,37 +296,54 @@ __global__ void __launch_bounds__(MF_THREADS) mf_beck_compact_kernel(MfKernelArg
 		s.a = make_float4(c.i.x, c.i.y, c.i.z, c.o.x);
 		s.b = make_float4(c.o.y, c.o.z, c.h.x, c.h.y);
 		s.c = make_float4(c.h.z, c.den, c.rcp_den, c.inv_iz);
-		s.d = make_float4(c.cd, c.den_ok ? 1.0f : 0.0f, 0.0f, 0.0f);
+		s.d = make_float4(c.cd, c.den_ok ? 1.0f : 0.0f, c.c4, c.rcp_c4);
 		__syncwarp(); // the previous round's items have all been finished: the pair slots may be overwritten
 		pairs[lane] = s;
 		__syncwarp();
-		int qn = 0; // items waiting, warp-uniform
-		for (int m = 0; m < A.n_params; ++m) {
-			const float Dn = lean_ndf<NDF>(s_exp2, s_params[m], c);
-			const bool skip = lean_skip(Dn, c);
-			if (valid && skip) {
-				const long long slot = (long long)m * A.out_stride + k;
-				if (OP == OP_PDF) A.out0[slot] = 0.0f;
-				else st3(A.out0, slot, lean_zero<OP>(c));
+		// D == 0 makes the result +0 when the denominator is positive (lean_skip); otherwise the item is queued.
+		// Two queues: items whose exponential lands in the gradual-underflow range (r2 > 78: quotients near or below 2^-120 take
+		// the guarded IEEE division and the hand-rounded subnormal path, ~10x the instructions) wait in their own queue,
+		// so that those long paths also run with many lanes instead of the one or two a mixed batch would have.
+		const bool zero_ok = c.den > 0.0f;
+		int qn = 0, qsn = 0; // items waiting (regular / slow), warp-uniform
+		for (int m = 0; m <= A.n_params; ++m) {
+			const bool last = m == A.n_params; // one extra trip that only drains the queues (single call site of `finish`)
+			if (!last) {
+				const float r2 = lean_ndf_r2(s_params[m], c);
+				const bool d_zero = !c.facing || r2 > 103.5f; // D == 0 exactly (lean_ndf / beck_p22_lean)
+				const bool skip = d_zero && zero_ok;
+				if (valid && skip) {
+					const long long slot = (long long)m * A.out_stride + k;
+					if (OP == OP_PDF) A.out0[slot] = 0.0f;
+					else st3(A.out0, slot, lean_zero<OP>(c));
+				}
+				const bool need = valid && !skip;
+				const bool slow = need && (d_zero || r2 > 78.0f);
+				const unsigned mask_f = __ballot_sync(FULL, need && !slow), mask_s = __ballot_sync(FULL, slow);
+				const uint2 item = make_uint2((unsigned)lane | (d_zero ? 0x80u : 0u) | ((unsigned)m << 8), __float_as_uint(r2));
+				if (slow) qs[qsn + __popc(mask_s & lt)] = item;
+				else if (need) q[qn + __popc(mask_f & lt)] = item;
+				qn += __popc(mask_f);
+				qsn += __popc(mask_s);
 			}
-			const bool need = valid && !skip;
-			const unsigned mask = __ballot_sync(FULL, need);
-			if (need) q[qn + __popc(mask & lt)] = make_uint2((unsigned)lane | ((unsigned)m << 8), __float_as_uint(Dn));
-			qn += __popc(mask);
-			if (qn >= 32) {
+			for (;;) { // full batches; on the last trip whatever is left (the pair slots are reused afterwards)
+				uint2 *Q;
+				int cnt;
+				const bool fast = qn >= 32 || (last && qn > 0);
+				if (fast) { Q = q; cnt = qn; }
+				else if (qsn >= 32 || (last && qsn > 0)) { Q = qs; cnt = qsn; }
+				else break;
 				__syncwarp();
-				const uint2 item = q[lane];
-				const uint2 rest = q[32 + lane]; // only the first qn - 32 are meaningful
-				finish(item, kb);
+				const int nb = cnt < 32 ? cnt : 32;
+				const uint2 item = Q[lane];
+				const uint2 rest = Q[32 + lane]; // only the first cnt - 32 are meaningful
+				if (lane < nb) finish(item, kb);
 				__syncwarp();
-				qn -= 32;
-				if (lane < qn) q[lane] = rest;
+				cnt -= nb;
+				if (lane < cnt) Q[lane] = rest;
+				if (fast) qn = cnt; else qsn = cnt;
 				__syncwarp();
 			}
-		}
-		if (qn > 0) { // flush before the pair slots are reused
-			__syncwarp();
-			if (lane < qn) finish(q[lane], kb);
 		}
 	}
 }
