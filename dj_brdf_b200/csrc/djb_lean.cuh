@@ -540,7 +540,10 @@ DJB_DEV float erf_lean(const float2 *__restrict__ T, float xin)
 {
 	const float x = fabsf(xin);
 	const float xx = -x * x;
-	if (!(xx > -100.0f)) return erf_as(xin); // saturated (or NaN): literal path
+	// |x| >= 10: (poly t) exp(-x^2) < e^-100 is far below half an ulp of 1.0 in double, so the reference's
+	// float(1.0 - ...) is exactly 1 (also for x = inf: t = 0, exp = 0).  Common: narrow lobes make cot(theta_k) large.
+	if (xx <= -100.0f) return xin < 0.0f ? -1.0f : 1.0f;
+	if (!(xx > -100.0f)) return erf_as(xin); // NaN: literal path
 	const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
 	const float px = 0.3275911f * x;
 	const float uh = 1.0f + px;
