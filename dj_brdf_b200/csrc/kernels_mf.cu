@@ -1,11 +1,15 @@
 // kernels_mf.cu -- batched microfacet eval / evalp / pdf / sample / evalp_is (SURVEY.md rows E1-E10,
 // P1, S1-S5).  One thread owns one (wi, wo) pair and walks the params blocks staged in shared
 // memory, so a pair is read from HBM once however many materials it is evaluated under; the
-// half vector and the two double reciprocals that do not depend on the material are hoisted.
+// half vector and the reciprocals that do not depend on the material are hoisted.
 //
 // HBM traffic per (pair, material): (24 + 12 M) / M bytes for eval -- 13.5 B at M = 16.
-// The kernel is bound by FP64 issue, not by HBM (DESIGN.md "Rooflines"): matching the reference to
-// the bit needs IEEE double sqrt/div/exp at its rounding points.
+// The kernels are bound by instruction issue, not by HBM: matching the reference to the bit
+// costs ~190 (GGX eval) to ~1650 (Beckmann sample) warp instructions per result.  Three kernel families:
+//   mf_lean_kernel          lean FP32 tier (djb_lean.cuh), every query, params BROADCAST / PER_PAIR / built per pair
+//                           from LEAN texels (PSRC_LEAN: mitsuba/dj_beckmannconductor.cpp:283-314 fused in front);
+//   mf_beck_compact_kernel  Beckmann eval / evalp / pdf over several materials with warp-level work compaction;
+//   mf_broadcast_kernel / mf_perpair_kernel   mirrored-rounding tier (djb_device.cuh): the other Fresnel terms, A/B tests.
 #include <cstdlib>
 #include <cstring>
 
