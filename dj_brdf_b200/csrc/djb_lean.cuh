@@ -486,26 +486,25 @@ DJB_DEV float ggx_qf2_lean(float u, float ck, float sk)
 	const FF d = two_sum(pr, -1.0f);
 	const float st = d.h + (d.l + pe);
 	const float ct = sqrt_1m_sq(st);
-	if (ct >= T45) { // (double)ct > 0.707107
-		const float tt = div_lean(st, ct);
-		if (sk < T45) {
-			const float tk = div_lean(sk, ck);
-			const FF den = two_sum(1.0f, -(tt * tk));
-			return div_ff(-(tt + tk), 0.0f, den.h, den.l);
-		}
-		const float kk = div_lean(ck, sk);
-		const FF num = two_sum(1.0f, tt * kk);
-		return div_ff(num.h, num.l, tt - kk, 0.0f);
-	}
-	const float cot = div_lean(ct, st);
-	if (sk < T45) {
-		const float tk = div_lean(sk, ck);
-		const FF num = two_sum(1.0f, tk * cot);
-		return div_ff(num.h, num.l, tk - cot, 0.0f);
-	}
-	const float kk = div_lean(ck, sk);
-	const FF den = two_sum(1.0f, -(cot * kk));
-	return div_ff(cot + kk, 0.0f, den.h, den.l);
+	// The reference branches four ways on (cos theta > 0.707107, sin theta_k < 0.707107) so that each tangent /
+	// cotangent is formed from the well-conditioned quotient (dj_brdf.h:2096-2118).  The four formulas are the same
+	// operations on selected operands -- two quotients, one product, one sum or difference, one 1 +- product, one final
+	// quotient -- so they are evaluated once, branch-free (random pairs put ~8 lanes of a warp in each branch):
+	//   A = ct >= T45: q1 = st / ct (tan theta)      else q1 = ct / st (cot theta)
+	//   B = sk <  T45: q2 = sk / ck (tan theta_k)    else q2 = ck / sk (cot theta_k)
+	//   A == B:  -+(q1 + q2) / (1 - q1 q2)   (minus when both are tangents)
+	//   A != B:  (1 + q1 q2) / (q1 - q2 when A, q2 - q1 otherwise)
+	const bool A = ct >= T45; // (double)ct > 0.707107
+	const bool B = sk < T45;
+	const float q1 = div_lean(A ? st : ct, A ? ct : st);
+	const float q2 = div_lean(B ? sk : ck, B ? ck : sk);
+	const float p = q1 * q2;
+	const bool same = A == B;
+	const FF t = two_sum(1.0f, same ? -p : p);
+	const float sum = q1 + q2;
+	const float nh = same ? (A ? -sum : sum) : t.h, nl = same ? 0.0f : t.l;
+	const float dh = same ? t.h : (A ? q1 - q2 : q2 - q1), dl = same ? t.l : 0.0f;
+	return div_ff(nh, nl, dh, dl);
 }
 
 // ggx::qf3_radial + qf3_rational_approx, dj_brdf.h:2121-2146 (the two double Horner forms stay in double)
