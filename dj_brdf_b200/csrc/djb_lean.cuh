@@ -609,14 +609,8 @@ DJB_DEV float erfinv_lean(const float4 *__restrict__ LT, float u)
 	return p * u;
 }
 
-// beckmann::qf2_radial, dj_brdf.h:1897-1952, in three pieces so that the Newton / bisection search can be scheduled
-// iteration by iteration (kernels_mf.cu, mf_beck_sample_pool_kernel): the state of one search, its set-up, one trip of
-// the reference's `while (++it < 10)` loop, and the conversion of the converged erf-domain value back to a slope.
-struct BeckQf2 {
-	float u, a, b, c, normalization, tan_k;
-	int it;
-};
-DJB_DEV BeckQf2 beckmann_qf2_init(const float2 *__restrict__ T, const float4 *__restrict__ LT, float u, float ck, float sk)
+// beckmann::qf2_radial, dj_brdf.h:1897-1952
+DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, const float4 *__restrict__ LT, float u, float ck, float sk)
 {
 	const float sqrt_pi_inv = (float)(1.0 / sqrt(DJB_PI));
 	const float cot = div_lean(ck, sk), tan_k = div_lean(sk, ck);
@@ -638,46 +632,33 @@ DJB_DEV BeckQf2 beckmann_qf2_init(const float2 *__restrict__ T, const float4 *__
 	} else {
 		normalization = (float)(1.0 / ((double)A + (double)B * exp((double)xx)));
 	}
-	BeckQf2 q;
-	q.u = u; q.a = a; q.b = b; q.c = c; q.normalization = normalization; q.tan_k = tan_k; q.it = 0;
-	return q;
-}
-// one trip of the loop; returns true when the search is over (converged, or the ninth trip has been made)
-DJB_DEV bool beckmann_qf2_step(const float2 *__restrict__ T, const float4 *__restrict__ LT, BeckQf2 &q)
-{
-	const float sqrt_pi_inv = (float)(1.0 / sqrt(DJB_PI));
-	if (!(++q.it < 10)) return true;
-	if (!(q.b >= q.a && q.b <= q.c)) q.b = 0.5f * (q.a + q.c);
-	const float ie = erfinv_lean(LT, q.b);
-	const float value = q.normalization * (1.0f + q.b + sqrt_pi_inv * q.tan_k * expf_lean(T, -ie * ie)) - q.u;
-	const float derivative = q.normalization * (1.0f - ie * q.tan_k);
-	if (fabsf(value) < 1e-5f) return true;
-	if (value > 0.0f) q.c = q.b; else q.a = q.b;
-	q.b -= __fdiv_rn(value, derivative);
-	return false;
-}
-DJB_DEV float beckmann_qf2_finish(const float4 *__restrict__ LT, float b) { return erfinv_lean(LT, fmax_ref(-0.9999f, b)); }
-DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, const float4 *__restrict__ LT, float u, float ck, float sk)
-{
-	BeckQf2 q = beckmann_qf2_init(T, LT, u, ck, sk);
-	while (!beckmann_qf2_step(T, LT, q)) {}
-	return beckmann_qf2_finish(LT, q.b);
+	int it = 0;
+	while (++it < 10) {
+		if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+		const float ie = erfinv_lean(LT, b);
+		const float value = normalization * (1.0f + b + sqrt_pi_inv * tan_k * expf_lean(T, -ie * ie)) - u;
+		const float derivative = normalization * (1.0f - ie * tan_k);
+		if (fabsf(value) < 1e-5f) break;
+		if (value > 0.0f) c = b; else a = b;
+		b -= __fdiv_rn(value, derivative);
+	}
+	return erfinv_lean(LT, fmax_ref(-0.9999f, b));
 }
 
-// pieces of microfacet::sample (dj_brdf.h:1669-1709) and radial::sample_vp22_std_smith (dj_brdf.h:1818-1846), shared by
-// lean_sample below and by the pooled Beckmann sampling kernel
-DJB_DEV float lean_clamp_u(float u) { return sat_ref(u) * 0.99998f + 0.00001f; }
-DJB_DEV V3 lean_warp_dir(const Params &p, V3 o) // the receiver direction in the standard configuration
+// radial::sample_vp22_std_smith, dj_brdf.h:1818-1846
+template <int NDF>
+DJB_DEV void lean_std_slopes(const float2 *T, const float4 *LT, float u1, float u2, V3 k, float &xs, float &ys)
 {
-	const float oyay = o.y * p.ay;
-	const float a = o.x * p.ax + oyay * p.rho;
-	const float b = oyay * p.srho;
-	const float c = o.z - o.x * p.tx - o.y * p.ty;
-	return normalize(mk(a, b, c));
-}
-DJB_DEV float lean_sin_k(float kz) { return kz < 1.0f ? sqrt_1m_sq(kz) : 0.0f; }
-DJB_DEV void lean_rotate_slopes(V3 k, float sk, float tx, float ty, float &xs, float &ys)
-{
+	const float ck = k.z;
+	const float sk = k.z < 1.0f ? sqrt_1m_sq(k.z) : 0.0f;
+	float tx, ty;
+	if (NDF == NDF_GGX) {
+		tx = ggx_qf2_lean(u1, ck, sk);
+		ty = ggx_qf3_lean(u2, tx);
+	} else {
+		tx = beckmann_qf2_lean(T, LT, u1, ck, sk);
+		ty = erfinv_lean(LT, 2.0f * u2 - 1.0f); // float(2.0 * u2 - 1): the product is exact, one rounding
+	}
 	if (sk == 0.0f) {
 		xs = tx;
 		ys = ty;
@@ -688,44 +669,27 @@ DJB_DEV void lean_rotate_slopes(V3 k, float sk, float tx, float ty, float &xs, f
 		ys = sp * tx + cp * ty;
 	}
 }
-DJB_DEV V3 lean_reflect(const Params &p, V3 o, float txm, float tym) // un-warp the slopes, reflect o about the normal
-{
-	const float txh = p.ax * txm + p.tx;
-	const float chol = p.rho * txm + p.srho * tym;
-	const float tyh = p.ay * chol + p.ty;
-	const V3 h = normalize(mk(-txh, -tyh, 1.0f));
-	const float k = 2.0f * dot(o, h); // float(2.0 * dot): exact
-	return scale(k, h) - o;
-}
-
-// radial::sample_vp22_std_smith, dj_brdf.h:1818-1846
-template <int NDF>
-DJB_DEV void lean_std_slopes(const float2 *T, const float4 *LT, float u1, float u2, V3 k, float &xs, float &ys)
-{
-	const float ck = k.z;
-	const float sk = lean_sin_k(k.z);
-	float tx, ty;
-	if (NDF == NDF_GGX) {
-		tx = ggx_qf2_lean(u1, ck, sk);
-		ty = ggx_qf3_lean(u2, tx);
-	} else {
-		tx = beckmann_qf2_lean(T, LT, u1, ck, sk);
-		ty = erfinv_lean(LT, 2.0f * u2 - 1.0f); // float(2.0 * u2 - 1): the product is exact, one rounding
-	}
-	lean_rotate_slopes(k, sk, tx, ty, xs, ys);
-}
 
 // microfacet::sample, dj_brdf.h:1669-1709
 template <int NDF>
 DJB_DEV V3 lean_sample(const float2 *T, const float4 *LT, const Params &p, float u1, float u2, V3 o)
 {
-	u1 = lean_clamp_u(u1);
-	u2 = lean_clamp_u(u2);
-	const V3 os = lean_warp_dir(p, o);
+	u1 = sat_ref(u1) * 0.99998f + 0.00001f;
+	u2 = sat_ref(u2) * 0.99998f + 0.00001f;
+	const float oyay = o.y * p.ay;
+	const float a = o.x * p.ax + oyay * p.rho;
+	const float b = oyay * p.srho;
+	const float c = o.z - o.x * p.tx - o.y * p.ty;
+	const V3 os = normalize(mk(a, b, c));
 	if (os.z > 0.0f) {
 		float txm, tym;
 		lean_std_slopes<NDF>(T, LT, u1, u2, os, txm, tym);
-		return lean_reflect(p, o, txm, tym);
+		const float txh = p.ax * txm + p.tx;
+		const float chol = p.rho * txm + p.srho * tym;
+		const float tyh = p.ay * chol + p.ty;
+		const V3 h = normalize(mk(-txh, -tyh, 1.0f));
+		const float k = 2.0f * dot(o, h); // float(2.0 * dot): exact
+		return scale(k, h) - o;
 	}
 	return mk(0.f, 0.f, 1.f);
 }

@@ -364,120 +364,6 @@ static void launch_beck_compact(const MfKernelArgs &A, long long want, cudaStrea
 	mf_beck_compact_kernel<FK, OP><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
 }
 
-// Beckmann sampling, BROADCAST layout, with the quantile searches POOLED across the warp.
-// beckmann::qf2_radial inverts the visible-slope CDF by a Newton / bisection search of 2 .. 9 trips (70 % of the searches
-// take 3, 24 % take 4), each trip an erfinv (log) and an exp: half of the kernel's instructions.  With one search per lane
-// a warp makes as many trips as its slowest lane -- measured 22 of 32 lanes active in that loop.  Here a warp works on
-// 32 pairs x POOL_G materials at a time in three phases: (1) every lane sets up the searches of its own pair and pushes
-// their states into a pool in shared memory; (2) the lanes run searches from the pool, one trip per loop iteration, and a
-// lane whose search ends writes the result back and takes the next one, so the loop stays dense until the pool runs dry;
-// (3) every lane finishes the samples of its own pair from the stored results.  The same functions on the same operands
-// (djb_lean.cuh: beckmann_qf2_init / _step / _finish): bit-identical to lean_sample by construction and by test.
-constexpr int POOL_THREADS = 128, POOL_G = 8, POOL_MAX_PARAMS = 64;
-
-__global__ void __launch_bounds__(POOL_THREADS) mf_beck_sample_pool_kernel(MfKernelArgs A)
-{
-	constexpr int WARPS = POOL_THREADS / 32, JOBS = 32 * POOL_G;
-	__shared__ Params s_params[POOL_MAX_PARAMS];
-	__shared__ float2 s_exp2[64];
-	__shared__ float4 s_log[128];
-	__shared__ float4 s_job[WARPS][JOBS];  // u, b, c, normalization
-	__shared__ float2 s_job2[WARPS][JOBS]; // tan_k, job id (material slot * 32 + source lane)
-	__shared__ float s_b[WARPS][JOBS];     // converged erf-domain value per job id
-	{
-		const float *src = reinterpret_cast<const float *>(A.params);
-		float *dst = reinterpret_cast<float *>(s_params);
-		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
-	}
-	if (threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
-	if (threadIdx.x < 128) s_log[threadIdx.x] = g_log_128[threadIdx.x];
-	__syncthreads();
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
-	float4 *job = s_job[warp];
-	float2 *job2 = s_job2[warp];
-	float *bfin = s_b[warp];
-
-	const long long stride = (long long)gridDim.x * blockDim.x;
-	for (long long kb = (long long)blockIdx.x * blockDim.x + warp * 32; kb < A.n; kb += stride) { // warp-uniform
-		const long long k = kb + lane;
-		const bool valid = k < A.n;
-		float u1 = 0.5f, u2 = 0.5f;
-		V3 o = mk(0.f, 0.f, 1.f);
-		if (valid) {
-			const float2 u = reinterpret_cast<const float2 *>(A.a)[k];
-			u1 = lean_clamp_u(u.x);
-			u2 = lean_clamp_u(u.y);
-			o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
-		}
-		for (int m0 = 0; m0 < A.n_params; m0 += POOL_G) {
-			const int mc = A.n_params - m0 < POOL_G ? A.n_params - m0 : POOL_G;
-			// phase 1: set up the searches of this lane's pair under materials m0 .. m0 + mc - 1
-			int njobs = 0; // warp-uniform
-			for (int g = 0; g < mc; ++g) {
-				const Params &p = s_params[m0 + g];
-				const V3 os = lean_warp_dir(p, o);
-				const bool need = valid && os.z > 0.0f;
-				const unsigned mask = __ballot_sync(FULL, need);
-				if (need) {
-					const BeckQf2 q = beckmann_qf2_init(s_exp2, s_log, u1, os.z, lean_sin_k(os.z));
-					const int slot = njobs + __popc(mask & lt);
-					job[slot] = make_float4(q.u, q.b, q.c, q.normalization);
-					job2[slot] = make_float2(q.tan_k, __int_as_float(g * 32 + lane));
-				}
-				njobs += __popc(mask);
-			}
-			__syncwarp();
-			// phase 2: run the pooled searches, one trip per iteration; a lane that finishes one takes the next
-			{
-				int head = 0; // next pool entry to hand out, warp-uniform
-				bool have = false;
-				BeckQf2 q;
-				int jid = 0;
-				for (;;) {
-					const unsigned idle = __ballot_sync(FULL, !have);
-					if (idle) {
-						if (!have) {
-							const int j = head + __popc(idle & lt);
-							if (j < njobs) {
-								const float4 s = job[j];
-								const float2 s2 = job2[j];
-								q.u = s.x; q.a = -1.0f; q.b = s.y; q.c = s.z; q.normalization = s.w; q.tan_k = s2.x; q.it = 0;
-								jid = __float_as_int(s2.y);
-								have = true;
-							}
-						}
-						head += __popc(idle);
-					}
-					if (!__any_sync(FULL, have)) break;
-					if (have && beckmann_qf2_step(s_exp2, s_log, q)) {
-						bfin[jid] = q.b;
-						have = false;
-					}
-				}
-			}
-			__syncwarp();
-			// phase 3: finish the samples of this lane's pair
-			if (valid) {
-				for (int g = 0; g < mc; ++g) {
-					const Params &p = s_params[m0 + g];
-					const V3 os = lean_warp_dir(p, o);
-					V3 r = mk(0.f, 0.f, 1.f);
-					if (os.z > 0.0f) {
-						const float tx = beckmann_qf2_finish(s_log, bfin[g * 32 + lane]);
-						const float ty = erfinv_lean(s_log, 2.0f * u2 - 1.0f);
-						float xs, ys;
-						lean_rotate_slopes(os, lean_sin_k(os.z), tx, ty, xs, ys);
-						r = lean_reflect(p, o, xs, ys);
-					}
-					st3(A.out0, (long long)(m0 + g) * A.out_stride + k, r);
-				}
-			}
-			__syncwarp(); // the pool is rewritten by the next round
-		}
-	}
-}
-
 // PER_PAIR layout: pair k under params block k (roughness from textures at every shading point).
 template <int NDF, int OP, int PSRC>
 __global__ void __launch_bounds__(MF_THREADS) mf_perpair_kernel(MfKernelArgs A)
@@ -588,32 +474,16 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 		return cudaGetLastError();
 	}
-	// BROADCAST: at most MF_MAX_SMEM_PARAMS blocks per launch (POOL_MAX_PARAMS for the pooled Beckmann sampling kernel)
+	// BROADCAST: at most MF_MAX_SMEM_PARAMS blocks per launch
 	const int per = (OP == OP_PDF) ? 1 : 3;
-	constexpr bool can_pool = NDF == NDF_BECKMANN && OP == OP_SAMPLE;
-	const bool pool = can_pool && !force_generic && L.n_params >= 2 && g_beck_compact.load(std::memory_order_relaxed) != 0;
-	const int64_t chunk = pool ? POOL_MAX_PARAMS : MF_MAX_SMEM_PARAMS;
-	for (int64_t m0 = 0; m0 < L.n_params; m0 += chunk) {
-		int64_t mc = L.n_params - m0 < chunk ? L.n_params - m0 : chunk;
+	for (int64_t m0 = 0; m0 < L.n_params; m0 += MF_MAX_SMEM_PARAMS) {
+		int64_t mc = L.n_params - m0 < MF_MAX_SMEM_PARAMS ? L.n_params - m0 : MF_MAX_SMEM_PARAMS;
 		A.params = reinterpret_cast<const Params *>(L.params) + m0;
 		A.n_params = (int)mc;
 		int64_t off = m0 * L.out_stride;
 		A.out0 = L.out0 ? L.out0 + off * per : nullptr;
 		A.out1 = L.out1 ? L.out1 + off * 3 : nullptr;
 		A.out2 = L.out2 ? L.out2 + off : nullptr;
-		if (pool) {
-			static int resident_pool = 0;
-			if (!resident_pool) {
-				cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_pool, mf_beck_sample_pool_kernel, POOL_THREADS, 0);
-				if (resident_pool < 1) resident_pool = 1;
-			}
-			const long long want_p = (L.n + POOL_THREADS - 1) / POOL_THREADS, cap_p = (long long)sm_count() * resident_pool;
-			mf_beck_sample_pool_kernel<<<(int)(want_p < cap_p ? want_p : cap_p), POOL_THREADS, 0, st>>>(A);
-			g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-			cudaError_t e = cudaGetLastError();
-			if (e != cudaSuccess) return e;
-			continue;
-		}
 		// Beckmann eval / evalp / pdf over several materials: the warp-compacting kernel
 		constexpr bool can_compact = NDF == NDF_BECKMANN && (OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF);
 		bool compacted = false;
