@@ -18,6 +18,6 @@ for _ in range(2):
     b.sample(u, wo, P)
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:mf_lean_kernel -s 1 -c 1 -f -o gpurun_out/prof_r01_e_bsample \
+ncu --set full --clock-control none --import-source on -k regex:"mf_beck_sample_pool|mf_lean_kernel" -s 1 -c 1 -f -o gpurun_out/prof_r01_e_bsample \
     python /tmp/bs.py > gpurun_out/ncu_bsample.log 2>&1
 tail -1 gpurun_out/ncu_bsample.log
