@@ -405,7 +405,7 @@ def test_beckmann_compaction_is_bit_identical(djb, port, fname):
     b = mk_brdf(djb, api.NDF_BECKMANN, f)
     ewi, ewo, _ = cases.edge_pairs()
     try:
-        for n, nm in ((1, 2), (31, 3), (33, 16), (1_000_003, 16), (200_000, 40)):
+        for n, nm in ((1, 2), (31, 3), (33, 16), (1_000_003, 16), (200_000, 40), (20_001, 300)):  # 300: two params chunks
             wi, wo, _ = cases.pairs(n, stream=900 + nm)
             if n > 1000:
                 wi, wo = np.concatenate([wi, ewi]), np.concatenate([wo, ewo])
