@@ -494,10 +494,11 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 				compacted = true;
 			}
 		}
-		if (compacted) {
-		} else if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, PSRC_BROADCAST>(A, want, st);
-		else if (lean) launch_lean<NDF, FK_IDEAL, OP, PSRC_BROADCAST>(A, want, st);
-		else mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		if (!compacted) {
+			if (lean && schlick) launch_lean<NDF, FK_SCHLICK, OP, PSRC_BROADCAST>(A, want, st);
+			else if (lean) launch_lean<NDF, FK_IDEAL, OP, PSRC_BROADCAST>(A, want, st);
+			else mf_broadcast_kernel<NDF, OP><<<grid, MF_THREADS, 0, st>>>(A);
+		}
 		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) return e;
