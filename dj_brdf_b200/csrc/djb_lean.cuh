@@ -539,9 +539,10 @@ DJB_DEV float erf_lean(const float2 *__restrict__ T, float xin)
 {
 	const float x = fabsf(xin);
 	const float xx = -x * x;
-	// |x| >= 10: (poly t) exp(-x^2) < e^-100 is far below half an ulp of 1.0 in double, so the reference's
-	// float(1.0 - ...) is exactly 1 (also for x = inf: t = 0, exp = 0).  Common: narrow lobes make cot(theta_k) large.
-	if (xx <= -100.0f) return xin < 0.0f ? -1.0f : 1.0f;
+	// |x| >= 4: (poly t) exp(-x^2) <= 0.137 e^-16 = 1.5e-8 is below half an ulp of 1.0f (2^-25 = 3.0e-8), so the
+	// reference's float(1.0 - ...) is exactly 1 (also for x = inf: t = 0, exp = 0).  Checked exhaustively on the CPU for
+	// every float in [3.9, 10]: the result is 1.0f from x = 3.9195216 on.  Common: narrow lobes make cot(theta_k) large.
+	if (xx <= -16.0f) return xin < 0.0f ? -1.0f : 1.0f;
 	if (!(xx > -100.0f)) return erf_as(xin); // NaN: literal path
 	const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
 	const float px = 0.3275911f * x;
