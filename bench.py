@@ -460,6 +460,28 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
         res[kind] = {"evals_per_s": na / (ms * 1e-3), "ms": ms, "pairs": na,
                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                   "traffic": None}}
+    # djb::tabular / djb::tabular_anisotropic as BRDFs (fitted tables of an analytic GGX), djb::utia eval
+    nt = min(n, 20_000_000)
+    u_t = torch.rand(nt, 2, device=dev, generator=g).contiguous()
+    tab = djb.tabular(djb.ggx(), 90)
+    th, _keep = tab._first_arg()
+    ms = timed(lambda: capi.check(lib.djb200_tabular_eval(th, None, C.c_int64(0), C.c_int(capi.PARAMS_BROADCAST), pv(wi), pv(wo),
+                                                          C.c_int64(nt), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
+    res["tabular_eval"] = {"evals_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt,
+                           "roofline": {"bound": "hbm", "achieved": 36.0 * nt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": 36.0 * nt / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+    ta = djb.tabular_anisotropic(djb.ggx(), 90, 90)
+    tah, _keep2 = ta._first_arg()
+    ms = timed(lambda: capi.check(lib.djb200_tabular_sample(tah, None, C.c_int64(0), C.c_int(capi.PARAMS_BROADCAST), pv(u_t), pv(wo),
+                                                            C.c_int64(nt), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
+    res["tabular_anisotropic_sample"] = {"samples_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt,
+                                         "roofline": {"bound": "hbm", "achieved": 32.0 * nt / (ms * 1e-3) / 1e9, "peak": peak,
+                                                      "unit": "GB/s", "frac": 32.0 * nt / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+    ut = djb.utia(np.random.default_rng(3).uniform(0.0, 40.0, 3 * 6 * 48 * 6 * 48))
+    ms = timed(lambda: capi.check(lib.djb200_utia_eval(ut._h, pv(wi), pv(wo), C.c_int64(nt), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
+    res["utia"] = {"evals_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt,
+                   "roofline": {"bound": "hbm", "achieved": 36.0 * nt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": 36.0 * nt / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
     return res
 
 
