@@ -271,9 +271,27 @@ static djb200_status host_pipeline(int64_t n, const std::vector<BulkIn> &ins, co
 	return rc;
 }
 
-// small host descriptor -> device scratch (stream ordered)
+// small host descriptor -> device scratch (stream ordered).  The device's default memory pool gives freed blocks back to
+// the OS at every synchronisation unless told otherwise, which turns the next cudaMallocAsync into a driver allocation
+// (0.5 - 3 ms measured per DEVICE-memory call after a sync: more than a 2e7-pair table-BRDF kernel).  A small release
+// threshold, set once per device, keeps the few hundred bytes of descriptors cached in the pool.
+static void keep_descriptor_pool_warm()
+{
+	static std::atomic<unsigned> done_mask{0};
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+	if (done_mask.load(std::memory_order_relaxed) & (1u << dev)) return;
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+		uint64_t cur = 0, want = 8ull << 20;
+		if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+	}
+	done_mask.fetch_or(1u << dev, std::memory_order_relaxed);
+}
 static cudaError_t upload_small(const void *host, size_t bytes, void **dev, cudaStream_t st)
 {
+	keep_descriptor_pool_warm();
 	cudaError_t e = cudaMallocAsync(dev, bytes, st);
 	if (e != cudaSuccess) return e;
 	return cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, st);
