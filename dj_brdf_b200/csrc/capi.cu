@@ -493,11 +493,15 @@ static djb200_status lean_shading_call(int op, const djb200_microfacet *mf, cons
 
 	void *d_spline = nullptr;
 	const bool spline = op >= 0 && L.fresnel_kind == DJB200_FRESNEL_SPLINE;
-	if (spline) { // small descriptor: a plain device allocation for the duration of the call
+	if (spline) { // small descriptor: stream-ordered scratch for device calls, a plain allocation for the staged host path
 		const size_t bytes = sizeof(float) * 3 * (size_t)mf->fresnel.n_points;
-		CU(cudaMalloc(&d_spline, bytes));
-		cudaError_t e = cudaMemcpy(d_spline, mf->fresnel.points, bytes, cudaMemcpyHostToDevice);
-		if (e != cudaSuccess) { cudaFree(d_spline); return cuda_fail(e, "fresnel spline upload"); }
+		if (mem == DJB200_MEM_DEVICE) {
+			CU(upload_small(mf->fresnel.points, bytes, &d_spline, (cudaStream_t)stream));
+		} else {
+			CU(cudaMalloc(&d_spline, bytes));
+			cudaError_t e = cudaMemcpy(d_spline, mf->fresnel.points, bytes, cudaMemcpyHostToDevice);
+			if (e != cudaSuccess) { cudaFree(d_spline); return cuda_fail(e, "fresnel spline upload"); }
+		}
 		L.spline_pts = (const float *)d_spline;
 		L.spline_n = mf->fresnel.n_points;
 	}
@@ -522,12 +526,12 @@ static djb200_status lean_shading_call(int op, const djb200_microfacet *mf, cons
 		for (auto &i : ins) din.push_back(const_cast<void *>(i.host));
 		for (auto &o : outs) dout.push_back(o.host);
 		cudaError_t e = body(din, dout, n, (cudaStream_t)stream);
-		if (e == cudaSuccess && spline) e = cudaStreamSynchronize((cudaStream_t)stream); // the spline copy is freed below
+		if (d_spline) cudaFreeAsync(d_spline, (cudaStream_t)stream);
 		rc = e == cudaSuccess ? DJB200_OK : cuda_fail(e, "lean shading launch");
 	} else {
 		rc = host_pipeline(n, ins, outs, 1, body);
+		if (d_spline) cudaFree(d_spline);
 	}
-	if (d_spline) cudaFree(d_spline);
 	return rc;
 }
 

@@ -82,7 +82,7 @@ def test_lean_shading_params(djb, port, kw):
     assert bits_equal(got0, want0).all(axis=1).mean() >= 0.999
 
 
-@pytest.mark.parametrize("fname", ["ideal", "schlick", "unpolarized"])
+@pytest.mark.parametrize("fname", ["ideal", "schlick", "unpolarized", "spline"])
 def test_lean_shading_queries_match_unfused_path(djb, port, fname):
     """fused kernel == params construction + PER_PAIR query (bit for bit: same device code on both routes), and both
     == the oracle on the golden records"""
