@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-1, session e, final: full GPU suite, smoke, both bench arms, launch list, ncu of the compacting kernel
+# round-1, session e (records r01_f and r01_g were taken with this script): full GPU suite, smoke, both bench arms, launch list, ncu of the compacting kernel
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader
 python -m pytest tests -m gpu -q 2>&1 | tail -4
