@@ -290,6 +290,12 @@ class PortOracle:
                                   c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data))
         return l1, l2
 
+    def erf(self, x):
+        x = _f32(x)
+        out = np.zeros(len(x), np.float32)
+        self.lib.orc_erf(c_f32p(x.ctypes.data), i64(len(x)), c_f32p(out.ctypes.data))
+        return out
+
     def radial_query(self, what, x, ndf=None, fit=None):
         """djb::radial's p22_radial / sigma_std_radial / cdf_radial / qf_radial for an analytic family (ndf) or a
         fit_tabular() result (fit)."""

@@ -1095,6 +1095,13 @@ ORC_API void orc_nmap2leanmap(const uint8_t *nmap, int w, int h, float base_roug
  * the power-iteration fits share this file's static helpers */
 #include "djb_oracle_fit.c"
 
+/* djb::erf (A&S 7.1.26, :667-688) on an array: lets tests check exhaustively the ranges where device code replaces it
+ * by its saturated value */
+ORC_API void orc_erf(const float *x, int64_t n, float *out)
+{
+	for (int64_t k = 0; k < n; ++k) out[k] = as_erf(x[k]);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * the public scalar queries of djb::radial (:307-310): what = 0 p22_radial(r^2), 1 sigma_std_radial(cos), 2 cdf_radial(r),
  * 3 qf_radial(u); family = ORC_NDF_BECKMANN / ORC_NDF_GGX / 2 (tabular: the four fitted tables of length res) */

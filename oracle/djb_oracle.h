@@ -91,6 +91,9 @@ void orc_lean_shading_params(float bias, float dmap_scale, int lean_filtering, i
 void orc_nmap2leanmap(const uint8_t *nmap_planar_rgb, int w, int h, float base_roughness, float bias,
                       float *lean1_planar_rgba, float *lean2_planar_rgba);
 
+/* djb::erf (dj_brdf.h:667-688) */
+void orc_erf(const float *x, int64_t n, float *out);
+
 /* djb::radial's public scalar queries (dj_brdf.h:307-310); family 0 beckmann, 1 ggx, 2 tabular (tables of length res) */
 void orc_radial_query(int family, int what, const float *p22, const float *sigma, const float *qf, const float *cdf, int res,
                       const float *x, int64_t n, float *out);

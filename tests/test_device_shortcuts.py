@@ -1,0 +1,66 @@
+"""CPU: the exactness claims behind shortcuts that only the device code takes (csrc/djb_lean.cuh), checked EXHAUSTIVELY over
+the float ranges they cover with the oracle port (which is bit-identical to the reference), plus the sync of the generated
+preset table with the reference header."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import api
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def floats_between(lo, hi):
+    a, b = np.array([lo, hi], np.float32).view(np.uint32)
+    return np.arange(a, b + 1, dtype=np.uint32).view(np.float32)
+
+
+def test_erf_saturates_exactly_from_4(port):
+    """erf_lean returns +-1 for x^2 >= 16 without evaluating the exponential: djb::erf must be exactly 1.0f there (and for
+    the first time at x = 3.9195216, so the threshold has margin)."""
+    x = floats_between(3.9, 10.5)
+    y = port.erf(x)
+    assert (y[x >= np.float32(4.0)] == np.float32(1.0)).all()
+    assert (port.erf(-x[x >= np.float32(4.0)]) == np.float32(-1.0)).all()
+    first = x[np.argmax(y == np.float32(1.0))]
+    assert abs(float(first) - 3.9195216) < 1e-6 and (y[x >= first] == np.float32(1.0)).all()
+    big = np.array([10.5, 50.0, 1e4, 1e19, 3e38, np.inf], np.float32)
+    assert (port.erf(big) == np.float32(1.0)).all()
+
+
+def test_beckmann_sigma_std_equals_cosine_past_the_shortcut(port):
+    """beck_sigma_std_lean returns c itself when -(c / s)^2 < -16.5 and c > 0 (cot > 4.06): every float c in that range must
+    give sigma_std_radial(c) == c in the reference's arithmetic."""
+    c = floats_between(0.96, 0.99999994)
+    s = np.sqrt(1.0 - c.astype(np.float64) ** 2)
+    nu = (c / s.astype(np.float32)).astype(np.float32)
+    sel = -(nu * nu) < np.float32(-16.5)
+    assert sel.sum() > 400_000
+    got = port.radial_query("sigma_std", c[sel], ndf=api.NDF_BECKMANN)
+    assert np.array_equal(got.view(np.uint32), c[sel].view(np.uint32))
+
+
+def test_beckmann_p22_is_zero_past_103_5(port):
+    """lean_ndf / the compacting kernel treat r^2 > 103.5 as D == 0: exp(-r^2) / pi must round to +0 there."""
+    r2 = np.concatenate([floats_between(103.5, 104.5)[1:], np.array([110, 200, 1e4, 3e38, np.inf], np.float32)])
+    got = port.radial_query("p22", r2, ndf=api.NDF_BECKMANN)
+    assert (got == 0).all() and not np.signbit(got).any()
+    # the threshold is conservative: the smallest subnormal results end near r^2 = 102.83
+    below = port.radial_query("p22", floats_between(102.0, 102.8), ndf=api.NDF_BECKMANN)
+    assert (below > 0).all()
+
+
+def test_generated_preset_table_is_in_sync_with_the_reference(tmp_path):
+    ref = api.REF_ROOT / "dj_brdf.h"
+    if not ref.exists():
+        pytest.skip("/root/reference not present")
+    committed = (ROOT / "dj_brdf_b200" / "csrc" / "djb_presets.inc").read_text()
+    script = (ROOT / "tools" / "extract_presets.py").read_text().replace(
+        'OUT = Path(__file__).resolve().parent.parent / "dj_brdf_b200" / "csrc" / "djb_presets.inc"',
+        f'OUT = Path(r"{tmp_path / "presets.inc"}")')
+    (tmp_path / "extract.py").write_text(script)
+    subprocess.run([sys.executable, str(tmp_path / "extract.py"), str(ref)], check=True, capture_output=True)
+    assert (tmp_path / "presets.inc").read_text() == committed
