@@ -57,6 +57,15 @@ DJB_DEV V3 source_eval(const FitSourceDev &s, V3 i, V3 o)
 // vec3::intensity, dj_brdf.h:69
 DJB_DEV float intensity(V3 v) { return (0.2126f * v.x + 0.7152f * v.y) + 0.0722f * v.z; }
 
+// spline::uwrap_repeat (dj_brdf.h:1183-1189) without its loops: the same residue for every int, a single compare in the
+// common case, and no multi-second spin when a degenerate (inf / NaN) table coordinate saturates the index
+DJB_DEV int wrap_repeat(int i, int n)
+{
+	if ((unsigned)i < (unsigned)n) return i;
+	i %= n;
+	return i < 0 ? i + n : i;
+}
+
 // spline::eval2d<float_t>(uwrap_edge, u1, uwrap_repeat, u2), dj_brdf.h:1220-1247
 DJB_DEV float spline2d_f(const float *pts, int w, int h, float u1, float u2)
 {
@@ -68,10 +77,8 @@ DJB_DEV float spline2d_f(const float *pts, int w, int h, float u1, float u2)
 	float x2 = u2 * (float)h - u2;
 	float ip2 = truncf(x2), frac2 = x2 - ip2;
 	int j1 = (int)ip2, j2 = (int)ip2 + 1;
-	while (j1 >= h) j1 -= h;
-	while (j1 < 0) j1 += h;
-	while (j2 >= h) j2 -= h;
-	while (j2 < 0) j2 += h;
+	j1 = wrap_repeat(j1, h);
+	j2 = wrap_repeat(j2, h);
 	float p1 = pts[i1 + w * j1], p2 = pts[i2 + w * j1], p3 = pts[i1 + w * j2], p4 = pts[i2 + w * j2];
 	float t1 = p1 + frac1 * (p2 - p1);
 	float t2 = p3 + frac1 * (p4 - p3);

@@ -77,10 +77,8 @@ DJB_DEV float spline_repeat_f(const float *pts, int n, float u)
 	const float x = u * (float)n - u;
 	const float ip = truncf(x), frac = x - ip; // == (float)modf((double)x, &ip): exact in both precisions
 	int i1 = (int)ip, i2 = (int)ip + 1;
-	while (i1 >= n) i1 -= n;
-	while (i1 < 0) i1 += n;
-	while (i2 >= n) i2 -= n;
-	while (i2 < 0) i2 += n;
+	i1 = wrap_repeat(i1, n);
+	i2 = wrap_repeat(i2, n);
 	const float p1 = pts[i1], p2 = pts[i2];
 	return p1 + frac * (p2 - p1);
 }
