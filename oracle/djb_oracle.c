@@ -268,6 +268,14 @@ void orc__set_tabular_aniso_qf(const float *qf1, int n_qf1, const float *qf2)
 	t_tab_qf1 = qf1; t_tab_nqf1 = n_qf1; t_tab_qf2 = qf2;
 }
 
+/* spline::uwrap_repeat, :1183-1189: the residue its two loops arrive at, computed directly (a degenerate coordinate casts to
+ * INT_MIN, and the loops then take seconds per call unless the compiler replaces them, as gcc -O3 does in the reference build) */
+static inline int wrap_repeat(int i, int n)
+{
+	i %= n;
+	return i < 0 ? i + n : i;
+}
+
 /* spline::eval2d<float_t>(uwrap_edge, u1, uwrap_repeat, u2), :1220-1247 */
 float orc__spline_eval2d_f(const float *pts, int w, int h, float u1, float u2)
 {
@@ -278,10 +286,8 @@ float orc__spline_eval2d_f(const float *pts, int w, int h, float u1, float u2)
 	if (i2 >= w) i2 = w - 1; else if (i2 < 0) i2 = 0;
 	float frac2 = F(modf(D(u2 * (float)h - u2), &ip2));
 	int j1 = (int)ip2, j2 = (int)ip2 + 1;
-	while (j1 >= h) j1 -= h;
-	while (j1 < 0) j1 += h;
-	while (j2 >= h) j2 -= h;
-	while (j2 < 0) j2 += h;
+	j1 = wrap_repeat(j1, h);
+	j2 = wrap_repeat(j2, h);
 	float p1 = pts[i1 + w * j1], p2 = pts[i2 + w * j1], p3 = pts[i1 + w * j2], p4 = pts[i2 + w * j2];
 	float t1 = p1 + frac1 * (p2 - p1);
 	float t2 = p3 + frac1 * (p4 - p3);

@@ -416,6 +416,8 @@ ORC_API void orc_fit_tabular_anisotropic(const orc_source *src, int elev_res, in
 		sc.dphi = F(2.0 * ORC_PI / D((float)90));
 		sc.P = &std_params; sc.p22 = p22; sc.sigma = sigma; sc.sigma_tab = sigma;
 		orc_parallel_ranges(n, nthreads, aniso_sigma_range, &sc);
+		/* a range that ran inline on this thread (nthreads <= 1, or few rows) cleared this thread's table pointers */
+		orc__set_tabular(p22, elev_res, sigma, azim_res);
 		for (int i2 = 0; i2 < h; ++i2) sigma[i2 * elev_res + w] = sigma[i2 * elev_res + w - 1];
 	}
 
@@ -512,10 +514,8 @@ static float spline_eval_repeat_f(const float *pts, int n, float u) /* spline::e
 	double ip;
 	float frac = F(modf(D(u * (float)n - u), &ip));
 	int i1 = (int)ip, i2 = (int)ip + 1;
-	while (i1 >= n) i1 -= n;
-	while (i1 < 0) i1 += n;
-	while (i2 >= n) i2 -= n;
-	while (i2 < 0) i2 += n;
+	i1 = wrap_repeat(i1, n);
+	i2 = wrap_repeat(i2, n);
 	float p1 = pts[i1], p2 = pts[i2];
 	return p1 + frac * (p2 - p1);
 }

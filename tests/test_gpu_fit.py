@@ -231,3 +231,22 @@ def test_tabular_anisotropic_brdf_queries(djb, port):
     # furnace-style sanity: sampled directions are unit vectors and the weights are finite
     nrm = np.linalg.norm(fit.sample(u, wo), axis=1)
     assert np.abs(nrm - 1.0).max() < 1e-4
+
+
+def test_tabular_anisotropic_tiny_resolutions_on_device(djb, port):
+    """degenerate table sizes on the device: NaN tables and inversion searches that run out (fewer quantile entries than
+    slots) must come out as in the reference's arithmetic, and the kernels must not spin on saturated spline indices"""
+    from tests.conftest import rel_err
+    for er, ar in ((2, 2), (3, 2), (2, 5), (3, 3), (5, 3)):
+        fit = djb.tabular_anisotropic(djb.beckmann(), er, ar)
+        want = port.fit_tabular_anisotropic(api.Source.microfacet(api.NDF_BECKMANN), er, ar, nthreads=1)
+        assert np.array_equal(np.isnan(fit.m_p22), np.isnan(want["p22"])), (er, ar)
+        ok = ~np.isnan(want["p22"])
+        assert rel_err(fit.m_p22[ok], want["p22"][ok]).max() <= TOL if ok.any() else True
+        got_t, want_t = fit.sampling_tables(), port.aniso_sampling_tables(fit.m_p22, er, ar)
+        assert got_t["n_qf1"] == want_t["n_qf1"] and got_t["n_qf2"] == want_t["n_qf2"], (er, ar, got_t["n_qf1"], want_t["n_qf1"])
+        for k in ("pdf1", "cdf1", "qf1", "pdf2", "cdf2", "qf2"):
+            assert np.array_equal(np.isnan(got_t[k]), np.isnan(want_t[k])), (er, ar, k)
+            fin = ~np.isnan(want_t[k])
+            if fin.any():
+                assert np.abs(got_t[k][fin] - want_t[k][fin]).max() <= 1e-5 * max(1.0, float(np.abs(want_t[k][fin]).max())), (er, ar, k)

@@ -191,3 +191,19 @@ def test_radial_scalar_queries_bit_identical(port, ref):
     fit = port.fit_tabular(src, 90)
     for what, x in args.items():
         assert bits_equal(port.radial_query(what, x, fit=fit), ref.radial_query(what, x, src=src, res=90)).all(), what
+
+
+@pytest.mark.timeout(300)
+def test_tabular_anisotropic_tiny_resolutions(port, ref):
+    """degenerate table sizes: NaN tables, inversion searches that run out without pushing (the vector sizes shrink), and the
+    single-threaded fit (whose ranges run inline on the calling thread)"""
+    ro = api.RefOracle(opened=True)
+    src = api.Source.microfacet(api.NDF_BECKMANN)
+    for er, ar in ((2, 2), (3, 2), (2, 5), (3, 3), (5, 3)):
+        rt = ro.aniso_sampling_tables(src, er, ar)
+        fit = port.fit_tabular_anisotropic(src, er, ar, nthreads=1)
+        assert bits_equal(fit["p22"], rt["p22"]).all() and bits_equal(fit["sigma"], rt["sigma"]).all(), (er, ar)
+        pt = port.aniso_sampling_tables(fit["p22"], er, ar)
+        assert rt["sizes"][2] == pt["n_qf1"] and rt["sizes"][5] == pt["n_qf2"], (er, ar, rt["sizes"], pt["n_qf1"], pt["n_qf2"])
+        for k in ("pdf1", "cdf1", "qf1", "pdf2", "cdf2", "qf2"):
+            assert bits_equal(pt[k], rt[k]).all(), (er, ar, k)
