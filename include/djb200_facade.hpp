@@ -510,7 +510,7 @@ public:
 		friend class beckmann;
 		float_t m_E1, m_E2, m_E3, m_E4, m_E5;
 	public:
-		lrep(float_t E1 = 0, float_t E2 = 0, float_t E3 = 0, float_t E4 = 0, float_t E5 = 0)
+		lrep(float_t E1 = 0, float_t E2 = 0, float_t E3 = 1, float_t E4 = 1, float_t E5 = 0) // defaults of dj_brdf.h:335-337
 		    : m_E1(E1), m_E2(E2), m_E3(E3), m_E4(E4), m_E5(E5) {}
 		lrep operator+(const lrep &r) const
 		{
