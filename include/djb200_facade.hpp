@@ -267,6 +267,19 @@ public:
 		{
 			detail::check(djb200_params_pdfparams(ax, ay, rho, tx_n, ty_n, &m));
 		}
+		void set_location(float_t tx_n, float_t ty_n) // dj_brdf.h:1437-1442 (the mean normal comes from the host factory)
+		{
+			djb200_params t;
+			detail::check(djb200_params_pdfparams(m.ax, m.ay, m.rho, tx_n, ty_n, &t));
+			m.tx_n = tx_n; m.ty_n = ty_n;
+			memcpy(m.n, t.n, sizeof m.n);
+		}
+		void set_location(const vec3 &n) // dj_brdf.h:1444-1449
+		{
+			m.n[0] = n.x; m.n[1] = n.y; m.n[2] = n.z;
+			m.tx_n = -n.x / n.z;
+			m.ty_n = -n.y / n.z;
+		}
 		void get_ellipse(float_t *a1, float_t *a2, float_t *phi_a = NULL) const
 		{
 			if (a1) *a1 = m.a1;

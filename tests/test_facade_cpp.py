@@ -44,6 +44,21 @@ def test_reference_example_compiles_unchanged(djb, tmp_path):
     compile_cpp(src, tmp_path / "ref_merl_params", [ROOT / "include/compat"], std="-std=gnu++11")
 
 
+def test_params_host_api_matches_reference(djb, tmp_path):
+    """params factories / setters / getters are host arithmetic on both sides: identical hex-float text, no GPU needed"""
+    if not (api.REF_ROOT / "dj_brdf.h").exists():
+        pytest.skip("/root/reference not present")
+    src = ROOT / "tests/cpp/params_host_check.cpp"
+    ours = compile_cpp(src, tmp_path / "params_b200", [ROOT / "include/compat"], std="-std=gnu++11")
+    r = subprocess.run(["g++", "-O3", "-ffp-contract=off", "-DNVERBOSE", "-DUSE_REFERENCE", f"-I{api.REF_ROOT}", str(src), "-o",
+                        str(tmp_path / "params_ref")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a = subprocess.run([str(ours)], capture_output=True, text=True)
+    b = subprocess.run([str(tmp_path / "params_ref")], capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    assert a.stdout == b.stdout and a.stdout.count("\n") == 242 + 61
+
+
 def test_facade_fails_loudly_without_gpu(djb, bins):
     if djb.device_count() > 0:
         pytest.skip("a CUDA device is present")
