@@ -269,6 +269,46 @@ class microfacet(brdf):
         return tuple(self._query(self._prefix + "evalp_is", u, o, 2, [3, 3, 1], user_param, per_pair))
 
 
+    # ---- the public component queries (dj_brdf.h:258-272), batched under one params block ---------------------------------
+    def _component(self, what, a, b=None, c=None, user_param=None):
+        bufs = [Buf(x, np.float32) for x in (a, b, c)]
+        mem = capi.same_space(*[x for x in bufs if x.mem is not None])
+        n = bufs[0].n // 3
+        out = capi.empty_like_space(bufs[0].keep, (n, 3) if what == 7 else (n,), np.float32)
+        bo = Buf(out, np.float32, True)
+        p = None if user_param is None else np.ascontiguousarray(user_param, np.float32).reshape(12)
+        d = self._desc()
+        check(capi.load().djb200_microfacet_component(C.byref(d), None if p is None else C.c_void_p(p.ctypes.data), C.c_int(what),
+                                                      bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, C.c_int64(n), bo.ptr, C.c_int(mem),
+                                                      capi.current_stream_ptr(mem)))
+        return out
+
+    def ndf(self, h, user_param=None):
+        return self._component(0, h, user_param=user_param)
+
+    def gaf(self, h, i, o, user_param=None):
+        return self._component(1, h, i, o, user_param)
+
+    def g1(self, h, k, user_param=None):
+        return self._component(2, h, k, user_param=user_param)
+
+    def sigma(self, k, user_param=None):
+        return self._component(3, k, user_param=user_param)
+
+    def p22(self, xy, user_param=None):
+        """xy: [n, 3] with the slopes in the first two columns."""
+        return self._component(4, xy, user_param=user_param)
+
+    def vp22(self, xy, k, user_param=None):
+        return self._component(5, xy, k, user_param=user_param)
+
+    def vndf(self, h, k, user_param=None):
+        return self._component(6, h, k, user_param=user_param)
+
+    def fresnel_term(self, cos_theta_d):
+        """microfacet::fresnel(cos_theta_d), dj_brdf.h:258; cos_theta_d: [n, 3] with the cosine in the first column -> rgb."""
+        return self._component(7, cos_theta_d)
+
     # ---- LEAN-filtered shading, fused (mitsuba/dj_beckmannconductor.cpp:283-319, 338-366, 379-410) ----------------
     @staticmethod
     def _lean_cfg(alpha, n, bias, dmap_scale, lean_filtering, like):

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "djb200_kernel_launch_count", "djb200_release_cache", "djb200_debug_force_generic", "djb200_debug_beckmann_compaction",
     "djb200_params_standard", "djb200_params_isotropic", "djb200_params_elliptic", "djb200_params_pdfparams",
     "djb200_microfacet_eval", "djb200_microfacet_evalp", "djb200_microfacet_pdf", "djb200_microfacet_sample",
-    "djb200_microfacet_evalp_is",
+    "djb200_microfacet_evalp_is", "djb200_microfacet_component",
     "djb200_io_to_hd", "djb200_hd_to_io",
     "djb200_merl_create", "djb200_merl_load", "djb200_merl_destroy", "djb200_merl_eval", "djb200_merl_index",
     "djb200_debug_merl_filter_stats",

@@ -738,6 +738,50 @@ djb200_status djb200_tabular_anisotropic_create(const djb200_tabular_anisotropic
 	return DJB200_OK;
 }
 
+djb200_status djb200_microfacet_component(const djb200_microfacet *mf, const djb200_params *params, int what, const float *a,
+                                          const float *b, const float *c, int64_t n, float *out, int mem, void *stream)
+{
+	if (!mf) return fail(DJB200_ERR_INVALID_ARGUMENT, "microfacet descriptor is NULL");
+	if (mf->ndf != DJB200_NDF_BECKMANN && mf->ndf != DJB200_NDF_GGX) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown ndf %d", mf->ndf);
+	if (mf->fresnel.kind < 0 || mf->fresnel.kind > DJB200_FRESNEL_SPLINE)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown fresnel kind %d", mf->fresnel.kind);
+	if (what < DJB200_COMP_NDF || what > DJB200_COMP_FRESNEL) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown component %d", what);
+	const bool need_b = what == DJB200_COMP_GAF || what == DJB200_COMP_G1 || what == DJB200_COMP_VP22 || what == DJB200_COMP_VNDF;
+	const bool need_c = what == DJB200_COMP_GAF;
+	if (n > 0 && ((need_b && !b) || (need_c && !c))) return fail(DJB200_ERR_INVALID_ARGUMENT, "direction array is NULL");
+	djb200_params P;
+	if (params) P = *params; else elliptic_h(1.0f, 1.0f, 0.0f, &P);
+	const djb200_microfacet M = *mf;
+	const bool spline = what == DJB200_COMP_FRESNEL && M.fresnel.kind == DJB200_FRESNEL_SPLINE;
+	if (spline && (!M.fresnel.points || M.fresnel.n_points < 1)) return fail(DJB200_ERR_INVALID_ARGUMENT, "spline fresnel needs points");
+	void *d_spline = nullptr;
+	if (spline && n > 0) {
+		djb200_status rs = require_device();
+		if (rs != DJB200_OK) return rs;
+		const size_t bytes = sizeof(float) * 3 * (size_t)M.fresnel.n_points;
+		CU(cudaMalloc(&d_spline, bytes));
+		cudaError_t e = cudaMemcpy(d_spline, M.fresnel.points, bytes, cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) { cudaFree(d_spline); return cuda_fail(e, "fresnel spline upload"); }
+	}
+	std::vector<BulkIn> ins = {{a, 12}};
+	int sb = -1, sc = -1;
+	if (need_b) { sb = (int)ins.size(); ins.push_back({b, 12}); }
+	if (need_c) { sc = (int)ins.size(); ins.push_back({c, 12}); }
+	const size_t out_item = what == DJB200_COMP_FRESNEL ? 12 : 4;
+	djb200_status rc = map_call(n, ins, {{out, out_item}}, mem, stream,
+		[&](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_microfacet_component(M.ndf, M.shadow, M.fresnel.kind, M.fresnel.v, (const float *)d_spline,
+			                                   M.fresnel.n_points, &P, what, (const float *)i[0],
+			                                   sb >= 0 ? (const float *)i[sb] : nullptr, sc >= 0 ? (const float *)i[sc] : nullptr, cn,
+			                                   (float *)o[0], st);
+		});
+	if (d_spline) {
+		if (mem == DJB200_MEM_DEVICE) cudaStreamSynchronize((cudaStream_t)stream);
+		cudaFree(d_spline);
+	}
+	return rc;
+}
+
 djb200_status djb200_radial_query(int what, int ndf, const djb200_tabular *t, const float *x, int64_t n, float *out, int mem,
                                   void *stream)
 {

@@ -107,6 +107,11 @@ cudaError_t launch_leanmap_to_params(const float *lean1, const float *lean2, int
 cudaError_t launch_analytic_eval(int kind, const double *coef, int n_coef, const float *wi, const float *wo, int64_t n,
                                  float *out, cudaStream_t st);
 
+// djb::microfacet's component queries (kernels_analytic.cu); params_host: one 48-byte block; spline_pts: device
+cudaError_t launch_microfacet_component(int ndf, int shadow, int fresnel_kind, const float fv[6], const float *spline_pts,
+                                        int spline_n, const void *params_host, int what, const float *a, const float *b,
+                                        const float *c, int64_t n, float *out, cudaStream_t st);
+
 // fits (kernels_fit.cu)
 struct FitSourceDev;
 size_t fit_tabular_smem_bytes(int res);

@@ -148,6 +148,19 @@ DJB200_API djb200_status djb200_microfacet_evalp_is(const djb200_microfacet *mf,
                                                     const float *wo, int64_t n, float *out_weight_rgb,
                                                     float *out_wi, float *out_pdf, int mem, void *stream);
 
+/* The public component queries of djb::microfacet (dj_brdf.h:258-272; implementations :1559-1665) under ONE params block
+ * (NULL = params::standard()).  a / b / c are n x 3 arrays whose meaning depends on `what` (unused ones may be NULL):
+ *   NDF (a = h) | GAF (a = h, b = i, c = o) | G1 (a = h, b = k) | SIGMA (a = k) | P22 (a = (x, y, -)) |
+ *   VP22 (a = (x, y, -), b = k) | VNDF (a = h, b = k) | FRESNEL (a = (cos_theta_d, -, -)).
+ * out: n floats; FRESNEL: n x 3 (rgb). */
+typedef enum djb200_component {
+	DJB200_COMP_NDF = 0, DJB200_COMP_GAF = 1, DJB200_COMP_G1 = 2, DJB200_COMP_SIGMA = 3, DJB200_COMP_P22 = 4,
+	DJB200_COMP_VP22 = 5, DJB200_COMP_VNDF = 6, DJB200_COMP_FRESNEL = 7
+} djb200_component;
+DJB200_API djb200_status djb200_microfacet_component(const djb200_microfacet *mf, const djb200_params *params, int what,
+                                                     const float *a, const float *b, const float *c, int64_t n, float *out,
+                                                     int mem, void *stream);
+
 /* ---- Rusinkiewicz frame (brdf::io_to_hd / hd_to_io, dj_brdf.h:771-793) ------------------ */
 DJB200_API djb200_status djb200_io_to_hd(const float *wi, const float *wo, int64_t n, float *h, float *d,
                                          int mem, void *stream);

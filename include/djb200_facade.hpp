@@ -427,6 +427,40 @@ public:
 		                                           out_i ? &out_i->x : NULL, out_pdf, where, stream));
 	}
 
+	// the public component queries, dj_brdf.h:258-272 (batches of one; component_batch takes n)
+	vec3 fresnel(float_t cos_theta_d) const
+	{
+		vec3 a(cos_theta_d, 0, 0), r;
+		component_batch(DJB200_COMP_FRESNEL, &a, NULL, NULL, 1, &r.x, NULL);
+		return r;
+	}
+	float_t ndf(const vec3 &h, const params &p = params::standard()) const { return component1(DJB200_COMP_NDF, &h, NULL, NULL, p); }
+	float_t gaf(const vec3 &h, const vec3 &i, const vec3 &o, const params &p = params::standard()) const
+	{
+		return component1(DJB200_COMP_GAF, &h, &i, &o, p);
+	}
+	float_t g1(const vec3 &h, const vec3 &k, const params &p = params::standard()) const { return component1(DJB200_COMP_G1, &h, &k, NULL, p); }
+	float_t sigma(const vec3 &k, const params &p = params::standard()) const { return component1(DJB200_COMP_SIGMA, &k, NULL, NULL, p); }
+	float_t p22(float_t x, float_t y, const params &p = params::standard()) const
+	{
+		vec3 a(x, y, 0);
+		return component1(DJB200_COMP_P22, &a, NULL, NULL, p);
+	}
+	float_t vp22(float_t x, float_t y, const vec3 &k, const params &p = params::standard()) const
+	{
+		vec3 a(x, y, 0);
+		return component1(DJB200_COMP_VP22, &a, &k, NULL, p);
+	}
+	float_t vndf(const vec3 &h, const vec3 &k, const params &p = params::standard()) const { return component1(DJB200_COMP_VNDF, &h, &k, NULL, p); }
+	void component_batch(djb200_component what, const vec3 *a, const vec3 *b, const vec3 *c, size_t n, float_t *out,
+	                     const params *p = NULL, memory_space where = host, void *stream = NULL) const
+	{
+		if (ndf_id() < 0) throw exc("djb_error: component queries are available on the analytic families (ggx, beckmann)");
+		djb200_microfacet d = describe();
+		detail::check(djb200_microfacet_component(&d, p ? p->raw() : NULL, what, &a->x, b ? &b->x : NULL, c ? &c->x : NULL, (int64_t)n,
+		                                          out, where, stream));
+	}
+
 	virtual bool supports_smith_vndf_sampling() const = 0;
 	void set_shadow(bool shadow) { m_shadow = shadow; ++m_fresnel_rev; }
 	void set_fresnel(const fresnel::impl &f)
@@ -476,6 +510,12 @@ protected:
 		detail::check(st);
 	}
 	static const djb200_params *raw(const void *p) { return reinterpret_cast<const djb200_params *>(p); }
+	float_t component1(djb200_component what, const vec3 *a, const vec3 *b, const vec3 *c, const params &p) const
+	{
+		float_t r;
+		component_batch(what, a, b, c, 1, &r, &p);
+		return r;
+	}
 	const fresnel::impl *m_fresnel;
 	bool m_shadow;
 	unsigned m_fresnel_rev;

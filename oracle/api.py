@@ -220,6 +220,23 @@ class PortOracle:
         self._mf("orc_microfacet_evalp_is", ndf, fresnel, shadow, params, u, wo, [w, i, pdf], nthreads)
         return w, i, pdf
 
+    COMPONENTS = {"ndf": 0, "gaf": 1, "g1": 2, "sigma": 3, "p22": 4, "vp22": 5, "vndf": 6, "fresnel": 7}
+
+    def component(self, what, ndf, params, a, b=None, c=None, fresnel=None, shadow=True):
+        """djb::microfacet's public component queries (dj_brdf.h:258-272) under one params block."""
+        code = self.COMPONENTS[what]
+        a = _f32(a)
+        b = None if b is None else _f32(b)
+        c = None if c is None else _f32(c)
+        n = len(a)
+        out = np.zeros((n, 3) if code == 7 else n, np.float32)
+        fr = fresnel or Fresnel.ideal()
+        fs = self._fres(fr)
+        p = None if params is None else _f32(params)
+        self.lib.orc_microfacet_component(C.c_int(ndf), C.byref(fs), C.c_int(int(shadow)), c_f32p(_ptr(p)), C.c_int(code),
+                                          c_f32p(a.ctypes.data), c_f32p(_ptr(b)), c_f32p(_ptr(c)), i64(n), c_f32p(out.ctypes.data))
+        return out
+
     def io_to_hd(self, wi, wo):
         wi, wo = _f32(wi), _f32(wo)
         h, d = np.empty_like(wi), np.empty_like(wi)
@@ -531,6 +548,23 @@ class RefOracle:
         self._with_mf(ndf, fresnel, shadow,
                       lambda h: self._q("ref_brdf_evalp_is", h, params, u, wo, [w, i, pdf], nthreads))
         return w, i, pdf
+
+    def component(self, what, ndf, params, a, b=None, c=None, fresnel=None, shadow=True):
+        code = PortOracle.COMPONENTS[what]
+        a = _f32(a)
+        b = None if b is None else _f32(b)
+        c = None if c is None else _f32(c)
+        n = len(a)
+        out = np.zeros((n, 3) if code == 7 else n, np.float32)
+        p = None if params is None else _f32(params)
+        h = self.microfacet(ndf, fresnel, shadow)
+        try:
+            rc = self.lib.ref_microfacet_component(h, c_f32p(_ptr(p)), C.c_int(code), c_f32p(a.ctypes.data), c_f32p(_ptr(b)),
+                                                   c_f32p(_ptr(c)), i64(n), c_f32p(out.ctypes.data))
+            assert rc == 0, rc
+        finally:
+            self.destroy(h)
+        return out
 
     def io_to_hd(self, wi, wo):
         wi, wo = _f32(wi), _f32(wo)

@@ -709,6 +709,33 @@ ORC_API void orc_microfacet_evalp_is(int ndf, const orc_fresnel *F, int shadow, 
                                      float *out_w3, float *out_i3, float *out_pdf, int nthreads)
 { mf_run(4, ndf, F, shadow, P, u2, wo, n, out_w3, out_i3, out_pdf, nthreads); }
 
+/* the public component queries of djb::microfacet (:258-272, 1559-1665): what = 0 ndf(h = a), 1 gaf(h = a, i = b, o = c),
+ * 2 g1(h = a, k = b), 3 sigma(k = a), 4 p22(x = a.x, y = a.y), 5 vp22(x, y = a.xy, k = b), 6 vndf(h = a, k = b),
+ * 7 fresnel(cos = a.x) -> rgb */
+ORC_API void orc_microfacet_component(int ndf, const orc_fresnel *Fr, int shadow, const orc_params *P, int what,
+                                      const float *a, const float *b, const float *c, int64_t n, float *out)
+{
+	orc_params std_p;
+	if (!P) { orc_params_elliptic(1.0f, 1.0f, 0.0f, &std_p); P = &std_p; }
+	for (int64_t k = 0; k < n; ++k) {
+		v3 va = v3_ld(a, k), vb = b ? v3_ld(b, k) : v3_make(0, 0, 1), vc = c ? v3_ld(c, k) : v3_make(0, 0, 1);
+		switch (what) {
+		case 0: out[k] = mf_ndf(ndf, P, va); break;
+		case 1: out[k] = mf_gaf(ndf, shadow, P, vb, vc); break;
+		case 2: out[k] = mf_g1(ndf, P, vb); break;
+		case 3: out[k] = mf_sigma(ndf, P, va); break;
+		case 4: out[k] = mf_p22(ndf, P, va.x, va.y); break;
+		case 5: { /* vp22, :1589-1598 */
+			v3 h = v3_normalize(v3_make(-va.x, -va.y, 1.0f));
+			float jacobian = h.z * h.z * h.z;
+			out[k] = jacobian * mf_vndf(ndf, P, h, vb);
+		} break;
+		case 6: out[k] = mf_vndf(ndf, P, va, vb); break;
+		default: v3_st(out, k, fresnel_eval(Fr, va.x)); break;
+		}
+	}
+}
+
 /* djb::tabular as an evaluable / samplable BRDF (the tables come from orc_fit_tabular): the microfacet queries of
  * dj_brdf.h:1529-1765 on the tabulated radial distribution.  op: 0 eval, 1 evalp, 2 pdf, 3 sample, 4 evalp_is */
 ORC_API void orc_tabular_query(int op, const float *p22, const float *sigma, const float *qf, int res,

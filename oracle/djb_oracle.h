@@ -59,6 +59,11 @@ void orc_microfacet_evalp_is(int ndf, const orc_fresnel *F, int shadow, const or
                              const float *u2, const float *wo, int64_t n,
                              float *out_w3, float *out_i3, float *out_pdf, int nthreads);
 
+/* djb::microfacet's public component queries (dj_brdf.h:258-272): what = 0 ndf, 1 gaf, 2 g1, 3 sigma, 4 p22, 5 vp22, 6 vndf,
+ * 7 fresnel (rgb); argument arrays as in include/djb200.h's djb200_microfacet_component */
+void orc_microfacet_component(int ndf, const orc_fresnel *F, int shadow, const orc_params *P, int what, const float *a,
+                              const float *b, const float *c, int64_t n, float *out);
+
 /* Rusinkiewicz transforms (dj_brdf.h:771-793) */
 void orc_io_to_hd(const float *wi, const float *wo, int64_t n, float *h3, float *d3);
 void orc_hd_to_io(const float *h3, const float *d3, int64_t n, float *wi, float *wo);

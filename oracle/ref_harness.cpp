@@ -198,6 +198,31 @@ REF_API void ref_microfacet_components(void *h, const float *params12, const flo
 	}
 }
 
+// all eight public component queries (dj_brdf.h:258-272): what = 0 ndf(h = a), 1 gaf(a, b, c), 2 g1(a, b), 3 sigma(a),
+// 4 p22(a.x, a.y), 5 vp22(a.x, a.y, b), 6 vndf(a, b), 7 fresnel(a.x) -> rgb
+REF_API int ref_microfacet_component(void *h, const float *params12, int what, const float *a, const float *b, const float *c,
+                                     int64_t n, float *out)
+{
+	const djb::microfacet *m = dynamic_cast<djb::microfacet *>(static_cast<djb::brdf *>(h));
+	if (!m) return -1;
+	djb::microfacet::params p = djb::microfacet::params::standard();
+	if (params12) memcpy(&p, params12, sizeof(p));
+	for (int64_t k = 0; k < n; ++k) {
+		djb::vec3 va = ld3(a, k), vb = b ? ld3(b, k) : djb::vec3(0, 0, 1), vc = c ? ld3(c, k) : djb::vec3(0, 0, 1);
+		switch (what) {
+		case 0: out[k] = m->ndf(va, p); break;
+		case 1: out[k] = m->gaf(va, vb, vc, p); break;
+		case 2: out[k] = m->g1(va, vb, p); break;
+		case 3: out[k] = m->sigma(va, p); break;
+		case 4: out[k] = m->p22(va.x, va.y, p); break;
+		case 5: out[k] = m->vp22(va.x, va.y, vb, p); break;
+		case 6: out[k] = m->vndf(va, vb, p); break;
+		default: st3(out, k, m->fresnel(va.x)); break;
+		}
+	}
+	return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // MERL cell index exactly as merl::eval forms it (dj_brdf.h:990-1002); uses the reference's own
 // static helpers, which are visible because this is the implementation TU.

@@ -76,6 +76,19 @@ def extra(ref):
     for tag, (h, w, sc) in (("a", (37, 53, 0.1)), ("b", (64, 96, 0.01)), ("c", (3, 5, 1.0))):
         d = rng.integers(0, 256, (h, w), dtype=np.uint8)
         e[f"dmap/{tag}/dmap"], e[f"dmap/{tag}/scale"], e[f"dmap/{tag}/nmap"] = d, np.float32(sc), ref.dmap2nmap(d, sc)
+    # the public component queries of djb::microfacet (dj_brdf.h:258-272)
+    cwi, cwo, cu = cases.pairs(512, stream=33)
+    ch = ((cwi + cwo) / np.linalg.norm(cwi + cwo, axis=1, keepdims=True)).astype(np.float32)
+    cxy = np.concatenate([(cu * 4 - 2).astype(np.float32), np.zeros((len(cu), 1), np.float32)], 1)
+    ccos = np.concatenate([cu[:, :1], np.zeros((len(cu), 2), np.float32)], 1).astype(np.float32)
+    e["components/wi"], e["components/wo"], e["components/h"], e["components/xy"], e["components/cos"] = cwi, cwo, ch, cxy, ccos
+    cP = cases.param_sets(ref)["offcentre"]
+    e["components/params"] = cP
+    cf = api.Fresnel.unpolarized([1.5, 1.8, 2.4])
+    cargs = dict(ndf=(ch,), gaf=(ch, cwi, cwo), g1=(ch, cwo), sigma=(cwo,), p22=(cxy,), vp22=(cxy, cwo), vndf=(ch, cwo), fresnel=(ccos,))
+    for ndf, nname in ((api.NDF_GGX, "ggx"), (api.NDF_BECKMANN, "beckmann")):
+        for what, a in cargs.items():
+            e[f"components/{nname}/{what}"] = ref.component(what, ndf, cP, *a, fresnel=cf)
     np.savez_compressed(OUT / "extra_golden.npz", **e)
     print("extra_golden.npz", (OUT / "extra_golden.npz").stat().st_size, "bytes")
 

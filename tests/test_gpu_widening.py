@@ -163,3 +163,29 @@ def test_radial_scalar_queries(djb, port):
     for what, x in args.items():
         got, want = getattr(t, what + "_radial")(x), port.radial_query(what, x, fit=fit)
         assert rel_err(got, want).max() <= REL_TOL and bits_equal(got, want).mean() >= 0.999, ("tabular", what)
+
+
+# ---- djb::microfacet's public component queries (dj_brdf.h:258-272) -------------------------------------------------------
+@pytest.mark.parametrize("nname", ["ggx", "beckmann"])
+def test_microfacet_components(djb, port, nname):
+    import torch
+    from tests.test_gpu_parity import mk_fresnel
+    x = np.load(GOLD / "extra_golden.npz")
+    ndf = api.NDF_GGX if nname == "ggx" else api.NDF_BECKMANN
+    f = api.Fresnel.unpolarized([1.5, 1.8, 2.4])
+    b = (djb.ggx if nname == "ggx" else djb.beckmann)(mk_fresnel(djb, f))
+    wi, wo, h, xy, cs = (x[f"components/{k}"] for k in ("wi", "wo", "h", "xy", "cos"))
+    P = x["components/params"]
+    calls = dict(ndf=lambda: b.ndf(h, P), gaf=lambda: b.gaf(h, wi, wo, P), g1=lambda: b.g1(h, wo, P), sigma=lambda: b.sigma(wo, P),
+                 p22=lambda: b.p22(xy, P), vp22=lambda: b.vp22(xy, wo, P), vndf=lambda: b.vndf(h, wo, P),
+                 fresnel=lambda: b.fresnel_term(cs))
+    for what, call in calls.items():
+        close(call(), x[f"components/{nname}/{what}"], f"{nname} {what} vs golden", 0.995)
+    # at scale against the port, device arrays
+    wi, wo, u = cases.pairs(cases.N_PARITY, stream=34)
+    h = ((wi + wo) / np.linalg.norm(wi + wo, axis=1, keepdims=True)).astype(np.float32)
+    th, two, twi = (torch.from_numpy(v).cuda() for v in (h, wo, wi))
+    Pa = cases.param_sets(port)["aniso"]
+    close(b.vndf(th, two, Pa).cpu().numpy(), port.component("vndf", ndf, Pa, h, wo, fresnel=f), f"{nname} vndf", 0.999)
+    close(b.gaf(th, twi, two, Pa).cpu().numpy(), port.component("gaf", ndf, Pa, h, wi, wo, fresnel=f), f"{nname} gaf", 0.999)
+    close(b.sigma(two).cpu().numpy(), port.component("sigma", ndf, None, wo), f"{nname} sigma NULL params", 0.999)

@@ -185,3 +185,12 @@ def test_lean_shading_params(port, x):
 def test_dmap2nmap(port, x):
     for tag in "abc":
         assert np.array_equal(port.dmap2nmap(x[f"dmap/{tag}/dmap"], float(x[f"dmap/{tag}/scale"])), x[f"dmap/{tag}/nmap"]), tag
+
+
+@pytest.mark.parametrize("nname", ["ggx", "beckmann"])
+def test_microfacet_components(port, x, nname):
+    wi, wo, h, xy, cs = (x[f"components/{k}"] for k in ("wi", "wo", "h", "xy", "cos"))
+    P, f = x["components/params"], api.Fresnel.unpolarized([1.5, 1.8, 2.4])
+    args = dict(ndf=(h,), gaf=(h, wi, wo), g1=(h, wo), sigma=(wo,), p22=(xy,), vp22=(xy, wo), vndf=(h, wo), fresnel=(cs,))
+    for what, a in args.items():
+        assert bits_equal(port.component(what, ndf_id(nname), P, *a, fresnel=f), x[f"components/{nname}/{what}"]).all(), what

@@ -207,3 +207,23 @@ def test_tabular_anisotropic_tiny_resolutions(port, ref):
         assert rt["sizes"][2] == pt["n_qf1"] and rt["sizes"][5] == pt["n_qf2"], (er, ar, rt["sizes"], pt["n_qf1"], pt["n_qf2"])
         for k in ("pdf1", "cdf1", "qf1", "pdf2", "cdf2", "qf2"):
             assert bits_equal(pt[k], rt[k]).all(), (er, ar, k)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_microfacet_components_bit_identical(port, ref, ndf):
+    """the eight public component queries of djb::microfacet (ndf, gaf, g1, sigma, p22, vp22, vndf, fresnel)"""
+    wi, wo, u = cases.pairs(20_000, stream=33)
+    h = (wi + wo) / np.linalg.norm(wi + wo, axis=1, keepdims=True)
+    h = h.astype(np.float32)
+    xy = np.concatenate([(u * 4 - 2).astype(np.float32), np.zeros((len(u), 1), np.float32)], 1)
+    cosd = np.concatenate([u[:, :1], np.zeros((len(u), 2), np.float32)], 1).astype(np.float32)
+    f = api.Fresnel.unpolarized([1.5, 1.8, 2.4])
+    for pname in ("aniso", "offcentre", "standard"):
+        P = cases.param_sets(ref)[pname]
+        for shadow in (True, False):
+            args = dict(ndf=(h,), gaf=(h, wi, wo), g1=(h, wo), sigma=(wo,), p22=(xy,), vp22=(xy, wo), vndf=(h, wo), fresnel=(cosd,))
+            for what, a in args.items():
+                g = port.component(what, ndf, P, *a, fresnel=f, shadow=shadow)
+                r = ref.component(what, ndf, P, *a, fresnel=f, shadow=shadow)
+                assert bits_equal(g, r).all(), (pname, shadow, what)
+    assert bits_equal(port.component("sigma", ndf, None, wo), ref.component("sigma", ndf, None, wo)).all()
