@@ -83,6 +83,7 @@ inline vec3 operator*(const vec3 &a, const vec3 &b) { return vec3(a.x * b.x, a.y
 inline vec3 operator*(float_t a, const vec3 &b) { return vec3(a * b.x, a * b.y, a * b.z); }
 inline vec3 operator*(const vec3 &a, float_t b) { return b * a; }
 inline vec3 operator/(const vec3 &a, float_t b) { return (float_t)(1.0 / (double)b) * a; }
+inline vec3 operator/(const vec3 &a, const vec3 &b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
 inline vec3 operator-(const vec3 &a) { return vec3(-a.x, -a.y, -a.z); }
 inline vec3 &operator+=(vec3 &a, const vec3 &b) { a = a + b; return a; }
 inline vec3 &operator-=(vec3 &a, const vec3 &b) { a = a - b; return a; }
@@ -171,17 +172,62 @@ protected:
 // ---------------------------------------------------------------------------------------------------
 // dj_brdf.h:149-207: Fresnel terms.  Here they are descriptors handed to the kernels.
 namespace fresnel {
-inline vec3 ior_to_f0(const vec3 &ior)
+// utilities, dj_brdf.h:151-154, 1255-1289 (host arithmetic; the reference's rounding points)
+inline void ior_to_f0(float_t ior, float_t *f0)
 {
-	vec3 t((float_t)(((double)ior.x - 1.0) / ((double)ior.x + 1.0)), (float_t)(((double)ior.y - 1.0) / ((double)ior.y + 1.0)),
-	       (float_t)(((double)ior.z - 1.0) / ((double)ior.z + 1.0)));
-	return t * t;
+	DJB_ASSERT(ior > 0.0 && "Invalid ior");
+	DJB_ASSERT(f0 && "Null output ptr");
+	float_t tmp = (float_t)(((double)ior - 1.0) / ((double)ior + 1.0));
+	*f0 = tmp * tmp;
+}
+inline void ior_to_f0(const vec3 &ior, vec3 *f0)
+{
+	DJB_ASSERT(f0 && "Null output ptr");
+	ior_to_f0(ior.x, &f0->x);
+	ior_to_f0(ior.y, &f0->y);
+	ior_to_f0(ior.z, &f0->z);
+}
+inline void f0_to_ior(float_t f0, float_t *ior)
+{
+	DJB_ASSERT(ior && "Null output ptr");
+	if ((double)f0 == 1.0) {
+		*ior = 1.0;
+	} else {
+		float_t sqrt_f0 = (float_t)std::sqrt((double)f0);
+		*ior = (float_t)((1.0 + (double)sqrt_f0) / (1.0 - (double)sqrt_f0));
+	}
+}
+inline void f0_to_ior(const vec3 &f0, vec3 *ior)
+{
+	DJB_ASSERT(ior && "Null output ptr");
+	f0_to_ior(f0.x, &ior->x);
+	f0_to_ior(f0.y, &ior->y);
+	f0_to_ior(f0.z, &ior->z);
+}
+inline vec3 ior_to_f0(const vec3 &ior) // convenience form (added)
+{
+	vec3 f0;
+	ior_to_f0(ior, &f0);
+	return f0;
 }
 class impl {
 public:
 	virtual ~impl() {}
 	virtual impl *copy() const = 0;
 	virtual void describe(djb200_fresnel *f) const = 0;
+	// F(cos theta_d), dj_brdf.h:160 (one device query; microfacet::component_batch evaluates many)
+	vec3 eval(float_t cos_theta_d) const
+	{
+		djb200_microfacet d;
+		memset(&d, 0, sizeof d);
+		d.ndf = DJB200_NDF_GGX;
+		d.shadow = 1;
+		describe(&d.fresnel);
+		const float a[3] = {cos_theta_d, 0, 0};
+		vec3 r;
+		detail::check(djb200_microfacet_component(&d, NULL, DJB200_COMP_FRESNEL, a, NULL, NULL, 1, &r.x, DJB200_MEM_HOST, NULL));
+		return r;
+	}
 };
 class ideal : public impl {
 public:

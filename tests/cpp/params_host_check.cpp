@@ -51,6 +51,16 @@ int main()
 			printf("lrep %a %a %a %a %a\n", m[0], m[1], m[2], m[3], m[4]);
 		}
 	}
+	// Fresnel utilities, dj_brdf.h:151-154
+	for (int k = 1; k < 30; ++k) {
+		float f0, ior;
+		djb::fresnel::ior_to_f0(1.0f + 0.11f * k, &f0);
+		djb::fresnel::f0_to_ior(0.033f * k, &ior);
+		djb::vec3 v0, v1;
+		djb::fresnel::ior_to_f0(djb::vec3(1.1f + 0.05f * k, 1.5f, 2.4f + 0.1f * k), &v0);
+		djb::fresnel::f0_to_ior(djb::vec3(0.02f * k, 1.0f, 0.5f), &v1);
+		printf("fresnel %a %a | %a %a %a | %a %a %a\n", f0, ior, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z);
+	}
 	djb::beckmann::lrep dflt;
 	const float *m = reinterpret_cast<const float *>(&dflt);
 	printf("lrep default %a %a %a %a %a\n", m[0], m[1], m[2], m[3], m[4]);

@@ -44,6 +44,18 @@ def test_reference_example_compiles_unchanged(djb, tmp_path):
     compile_cpp(src, tmp_path / "ref_merl_params", [ROOT / "include/compat"], std="-std=gnu++11")
 
 
+def test_api_surface_has_the_reference_signatures():
+    """tests/cpp/api_surface.cpp pins every public member the facade provides to the reference's exact signature; it must
+    compile against both headers"""
+    src = ROOT / "tests/cpp/api_surface.cpp"
+    r = subprocess.run(["g++", "-std=gnu++11", "-fsyntax-only", f"-I{ROOT / 'include/compat'}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if (api.REF_ROOT / "dj_brdf.h").exists():
+        r = subprocess.run(["g++", "-std=gnu++11", "-fsyntax-only", "-DUSE_REFERENCE", f"-I{api.REF_ROOT}", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_params_host_api_matches_reference(djb, tmp_path):
     """params factories / setters / getters are host arithmetic on both sides: identical hex-float text, no GPU needed"""
     if not (api.REF_ROOT / "dj_brdf.h").exists():
@@ -56,7 +68,7 @@ def test_params_host_api_matches_reference(djb, tmp_path):
     a = subprocess.run([str(ours)], capture_output=True, text=True)
     b = subprocess.run([str(tmp_path / "params_ref")], capture_output=True, text=True)
     assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
-    assert a.stdout == b.stdout and a.stdout.count("\n") == 242 + 61
+    assert a.stdout == b.stdout and a.stdout.count("\n") == 242 + 61 + 29
 
 
 def test_facade_fails_loudly_without_gpu(djb, bins):
