@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "djb_glibcf.h"
 
 namespace djb200 {
 
@@ -109,12 +110,23 @@ DJB_DEV float erf_as(float x, double e)
 }
 DJB_DEV float erf_as(float x) { return erf_as(x, exp((double)(-x * x))); }
 
-// single-precision libm calls of the reference (logf/expf/powf, :695, 1917, 1935): glibc returns
-// the correctly rounded float in all but a ~1e-3 fraction of cases, so they are mirrored by
-// evaluating in double and rounding once.
-DJB_DEV float logf_cr(float x) { return (float)log((double)x); }
-DJB_DEV float expf_cr(float x) { return (float)exp((double)x); }
-DJB_DEV float powf_cr(float x, float y) { return (float)pow((double)x, (double)y); }
+// single-precision libm calls of the reference (logf/expf/powf, :695, 1917, 1935): glibc's own algorithms, operation
+// for operation (djb_glibcf.h), so the results are glibc's results; arguments outside the restated main branches (zero,
+// subnormal, negative, NaN, overflowing) are evaluated in double and rounded once.
+static __device__ __noinline__ float logf_literal(float x) { return (float)log((double)x); }
+static __device__ __noinline__ float expf_literal(float x) { return (float)exp((double)x); }
+static __device__ __noinline__ float powf_literal(float x, float y) { return (float)pow((double)x, (double)y); }
+DJB_DEV float logf_cr(float x) { return glf_logf_ok(x) ? glf_logf(GlfTablePtr{g_glf_table}, x) : logf_literal(x); }
+DJB_DEV float expf_cr(float x) { return glf_expf_ok(x) ? glf_expf(GlfTablePtr{g_glf_table}, x) : expf_literal(x); }
+DJB_DEV float powf_cr(float x, float y)
+{
+	if (glf_powf_ok(x, y)) {
+		bool ok;
+		const float r = glf_powf(GlfTablePtr{g_glf_table}, x, y, ok);
+		if (ok) return r;
+	}
+	return powf_literal(x, y);
+}
 
 // djb::erfinv (Giles), :691-721
 DJB_DEV float erfinv_giles(float u)

@@ -253,196 +253,26 @@ DJB_DEV float beck_sigma_std_lean(const float2 *__restrict__ T, float c)
 
 struct FF { float h, l; }; // unevaluated sum h + l
 
-// ---- float-float logarithm (the sampling path's logf / powf, dj_brdf.h:695, 1917) -----------------------------
-// x = 2^e m with m in [0.707, 1.414); the table gives, per 2^16-ulp bin of m, a 12-bit reciprocal R of the bin
-// centre and -log(R) as float-float, so log m = -log R + log1p(r) with r = m R - 1 exact as float-float and
-// |r| < 2^-8 (the two bins that touch 1 use R = 1, which keeps the RELATIVE accuracy of log x near x = 1).
-// Absolute error < 2^-42 on (0, 2), relative < 2^-38: float(log) agrees with the correctly rounded logf except at
-// ties (0 differences in 5e6 prototype arguments).
-__device__ const float4 g_log_128[128] = {
-	{0x1.6920000000000p+0f, -0x1.604dc80000000p-2f, -0x1.47cfd40000000p-29f, 0.0f},
-	{0x1.6720000000000p+0f, -0x1.5a9dee0000000p-2f, 0x1.a50e6c0000000p-28f, 0.0f},
-	{0x1.6520000000000p+0f, -0x1.54e5f20000000p-2f, 0x1.8690880000000p-28f, 0.0f},
-	{0x1.6340000000000p+0f, -0x1.4f81fe0000000p-2f, -0x1.1d8f400000000p-28f, 0.0f},
-	{0x1.6140000000000p+0f, -0x1.49b9fe0000000p-2f, -0x1.6f82ee0000000p-27f, 0.0f},
-	{0x1.5f60000000000p+0f, -0x1.4446de0000000p-2f, 0x1.2344500000000p-29f, 0.0f},
-	{0x1.5d80000000000p+0f, -0x1.3ecc460000000p-2f, -0x1.debea00000000p-31f, 0.0f},
-	{0x1.5ba0000000000p+0f, -0x1.394a220000000p-2f, -0x1.858d160000000p-27f, 0.0f},
-	{0x1.59e0000000000p+0f, -0x1.341f200000000p-2f, -0x1.7ff9860000000p-27f, 0.0f},
-	{0x1.5800000000000p+0f, -0x1.2e8e2c0000000p-2f, 0x1.47b8b40000000p-28f, 0.0f},
-	{0x1.5640000000000p+0f, -0x1.2955300000000p-2f, 0x1.f802b80000000p-28f, 0.0f},
-	{0x1.5480000000000p+0f, -0x1.2415580000000p-2f, -0x1.7fa2800000000p-27f, 0.0f},
-	{0x1.52a0000000000p+0f, -0x1.1e6dd60000000p-2f, 0x1.55030a0000000p-27f, 0.0f},
-	{0x1.5100000000000p+0f, -0x1.1980d20000000p-2f, -0x1.ba846e0000000p-27f, 0.0f},
-	{0x1.4f40000000000p+0f, -0x1.142bfe0000000p-2f, -0x1.73408e0000000p-27f, 0.0f},
-	{0x1.4d80000000000p+0f, -0x1.0ed0060000000p-2f, 0x1.3504b80000000p-31f, 0.0f},
-	{0x1.4be0000000000p+0f, -0x1.09cf960000000p-2f, -0x1.01fd440000000p-27f, 0.0f},
-	{0x1.4a20000000000p+0f, -0x1.0465a00000000p-2f, -0x1.02aa000000000p-27f, 0.0f},
-	{0x1.4880000000000p+0f, -0x1.feb0240000000p-3f, 0x1.833f060000000p-28f, 0.0f},
-	{0x1.46e0000000000p+0f, -0x1.f488320000000p-3f, 0x1.c5c96e0000000p-28f, 0.0f},
-	{0x1.4540000000000p+0f, -0x1.ea534a0000000p-3f, 0x1.dc53f20000000p-31f, 0.0f},
-	{0x1.43a0000000000p+0f, -0x1.e0114c0000000p-3f, -0x1.4cc6600000000p-29f, 0.0f},
-	{0x1.4200000000000p+0f, -0x1.d5c2160000000p-3f, -0x1.69f7720000000p-28f, 0.0f},
-	{0x1.4080000000000p+0f, -0x1.cc320c0000000p-3f, -0x1.7650240000000p-35f, 0.0f},
-	{0x1.3ee0000000000p+0f, -0x1.c1c90a0000000p-3f, 0x1.d284300000000p-31f, 0.0f},
-	{0x1.3d60000000000p+0f, -0x1.b820f20000000p-3f, -0x1.f8fca20000000p-28f, 0.0f},
-	{0x1.3be0000000000p+0f, -0x1.ae6d260000000p-3f, 0x1.b179a80000000p-32f, 0.0f},
-	{0x1.3a60000000000p+0f, -0x1.a4ad860000000p-3f, -0x1.ceaa2e0000000p-30f, 0.0f},
-	{0x1.38e0000000000p+0f, -0x1.9ae1f60000000p-3f, -0x1.bdcb700000000p-28f, 0.0f},
-	{0x1.3760000000000p+0f, -0x1.910a5a0000000p-3f, -0x1.061c1e0000000p-28f, 0.0f},
-	{0x1.35e0000000000p+0f, -0x1.8726940000000p-3f, 0x1.4a6a740000000p-28f, 0.0f},
-	{0x1.3460000000000p+0f, -0x1.7d36840000000p-3f, 0x1.a8e1e40000000p-28f, 0.0f},
-	{0x1.3300000000000p+0f, -0x1.740f900000000p-3f, 0x1.57f90c0000000p-28f, 0.0f},
-	{0x1.3180000000000p+0f, -0x1.6a079e0000000p-3f, 0x1.e10aa60000000p-28f, 0.0f},
-	{0x1.3020000000000p+0f, -0x1.60ca900000000p-3f, 0x1.77a7500000000p-31f, 0.0f},
-	{0x1.2ec0000000000p+0f, -0x1.5782cc0000000p-3f, 0x1.9edd3a0000000p-28f, 0.0f},
-	{0x1.2d60000000000p+0f, -0x1.4e30360000000p-3f, 0x1.2b0ace0000000p-31f, 0.0f},
-	{0x1.2be0000000000p+0f, -0x1.43f8380000000p-3f, 0x1.d0c2ae0000000p-28f, 0.0f},
-	{0x1.2aa0000000000p+0f, -0x1.3b6a340000000p-3f, -0x1.1b702a0000000p-30f, 0.0f},
-	{0x1.2940000000000p+0f, -0x1.31f6940000000p-3f, 0x1.4e669a0000000p-31f, 0.0f},
-	{0x1.27e0000000000p+0f, -0x1.2877bc0000000p-3f, 0x1.fa4a2e0000000p-30f, 0.0f},
-	{0x1.2680000000000p+0f, -0x1.1eed900000000p-3f, -0x1.c5b8580000000p-28f, 0.0f},
-	{0x1.2540000000000p+0f, -0x1.1637800000000p-3f, 0x1.3b6f9c0000000p-29f, 0.0f},
-	{0x1.23e0000000000p+0f, -0x1.0c976c0000000p-3f, 0x1.7084ea0000000p-28f, 0.0f},
-	{0x1.22a0000000000p+0f, -0x1.03cd400000000p-3f, -0x1.4a35820000000p-28f, 0.0f},
-	{0x1.2160000000000p+0f, -0x1.f5f2c60000000p-4f, -0x1.e80efc0000000p-32f, 0.0f},
-	{0x1.2020000000000p+0f, -0x1.e4377a0000000p-4f, -0x1.b4936e0000000p-33f, 0.0f},
-	{0x1.1ec0000000000p+0f, -0x1.d09f720000000p-4f, -0x1.6989040000000p-29f, 0.0f},
-	{0x1.1d80000000000p+0f, -0x1.beba820000000p-4f, 0x1.fae6260000000p-30f, 0.0f},
-	{0x1.1c60000000000p+0f, -0x1.ae8e7a0000000p-4f, -0x1.04ebc80000000p-32f, 0.0f},
-	{0x1.1b20000000000p+0f, -0x1.9c83320000000p-4f, 0x1.cb5a320000000p-29f, 0.0f},
-	{0x1.19e0000000000p+0f, -0x1.8a63780000000p-4f, 0x1.5ba8f60000000p-30f, 0.0f},
-	{0x1.18a0000000000p+0f, -0x1.782f200000000p-4f, 0x1.8c8a1a0000000p-29f, 0.0f},
-	{0x1.1780000000000p+0f, -0x1.67bb080000000p-4f, 0x1.b227e00000000p-29f, 0.0f},
-	{0x1.1640000000000p+0f, -0x1.555efe0000000p-4f, -0x1.02d42e0000000p-30f, 0.0f},
-	{0x1.1520000000000p+0f, -0x1.44c6e00000000p-4f, 0x1.19227e0000000p-30f, 0.0f},
-	{0x1.1400000000000p+0f, -0x1.341d7a0000000p-4f, 0x1.3c85c60000000p-29f, 0.0f},
-	{0x1.12c0000000000p+0f, -0x1.2185b40000000p-4f, 0x1.22978c0000000p-30f, 0.0f},
-	{0x1.11a0000000000p+0f, -0x1.10b75a0000000p-4f, -0x1.facc180000000p-29f, 0.0f},
-	{0x1.1080000000000p+0f, -0x1.ffae920000000p-5f, 0x1.cc8da00000000p-30f, 0.0f},
-	{0x1.0f60000000000p+0f, -0x1.ddcaae0000000p-5f, 0x1.2e443a0000000p-31f, 0.0f},
-	{0x1.0e40000000000p+0f, -0x1.bbc2c00000000p-5f, 0x1.dd85f40000000p-32f, 0.0f},
-	{0x1.0d20000000000p+0f, -0x1.99967a0000000p-5f, -0x1.3cac720000000p-31f, 0.0f},
-	{0x1.0c00000000000p+0f, -0x1.7745900000000p-5f, 0x1.39a4600000000p-30f, 0.0f},
-	{0x1.0b00000000000p+0f, -0x1.58a5ba0000000p-5f, -0x1.f91c9a0000000p-30f, 0.0f},
-	{0x1.09e0000000000p+0f, -0x1.360ec00000000p-5f, 0x1.44f9140000000p-30f, 0.0f},
-	{0x1.08c0000000000p+0f, -0x1.1352380000000p-5f, 0x1.e9a3840000000p-31f, 0.0f},
-	{0x1.07c0000000000p+0f, -0x1.e8a3ee0000000p-6f, -0x1.866e560000000p-33f, 0.0f},
-	{0x1.06a0000000000p+0f, -0x1.a29b460000000p-6f, 0x1.8069220000000p-31f, 0.0f},
-	{0x1.05a0000000000p+0f, -0x1.641a180000000p-6f, 0x1.3b1e520000000p-31f, 0.0f},
-	{0x1.04a0000000000p+0f, -0x1.255ba20000000p-6f, -0x1.67de380000000p-32f, 0.0f},
-	{0x1.0380000000000p+0f, -0x1.bcf7120000000p-7f, -0x1.8e870a0000000p-32f, 0.0f},
-	{0x1.0280000000000p+0f, -0x1.3e72960000000p-7f, 0x1.6d2c140000000p-34f, 0.0f},
-	{0x1.0180000000000p+0f, -0x1.7ee11e0000000p-8f, -0x1.7b05d20000000p-33f, 0.0f},
-	{0x1.0000000000000p+0f, 0x0.0p+0f, 0x0.0p+0f, 0.0f},
-	{0x1.0000000000000p+0f, 0x0.0p+0f, 0x0.0p+0f, 0.0f},
-	{0x1.fa20000000000p-1f, 0x1.7a2c820000000p-7f, 0x1.c4258c0000000p-32f, 0.0f},
-	{0x1.f640000000000p-1f, 0x1.3b024c0000000p-6f, -0x1.0e75320000000p-31f, 0.0f},
-	{0x1.f260000000000p-1f, 0x1.b9e8020000000p-6f, 0x1.f864640000000p-32f, 0.0f},
-	{0x1.eea0000000000p-1f, 0x1.1ad3980000000p-5f, 0x1.8d9ab00000000p-30f, 0.0f},
-	{0x1.eae0000000000p-1f, 0x1.592bbc0000000p-5f, 0x1.5215c80000000p-33f, 0.0f},
-	{0x1.e740000000000p-1f, 0x1.95e4300000000p-5f, 0x1.f19c8c0000000p-30f, 0.0f},
-	{0x1.e3a0000000000p-1f, 0x1.d310ba0000000p-5f, 0x1.022ad00000000p-32f, 0.0f},
-	{0x1.e020000000000p-1f, 0x1.0748840000000p-4f, -0x1.3ad37e0000000p-29f, 0.0f},
-	{0x1.dca0000000000p-1f, 0x1.2540620000000p-4f, 0x1.e152820000000p-29f, 0.0f},
-	{0x1.d920000000000p-1f, 0x1.4370ce0000000p-4f, 0x1.5bef3e0000000p-35f, 0.0f},
-	{0x1.d5c0000000000p-1f, 0x1.60c38c0000000p-4f, -0x1.619ae80000000p-30f, 0.0f},
-	{0x1.d280000000000p-1f, 0x1.7d33680000000p-4f, 0x1.f0a4f20000000p-30f, 0.0f},
-	{0x1.cf20000000000p-1f, 0x1.9af1240000000p-4f, 0x1.ac98c40000000p-29f, 0.0f},
-	{0x1.cbe0000000000p-1f, 0x1.b7c9840000000p-4f, -0x1.a14ffc0000000p-29f, 0.0f},
-	{0x1.c8c0000000000p-1f, 0x1.d3b7400000000p-4f, -0x1.903c0c0000000p-29f, 0.0f},
-	{0x1.c580000000000p-1f, 0x1.f0f70c0000000p-4f, 0x1.bb325c0000000p-29f, 0.0f},
-	{0x1.c260000000000p-1f, 0x1.06a4d20000000p-3f, -0x1.6c9d0e0000000p-30f, 0.0f},
-	{0x1.bf60000000000p-1f, 0x1.1454d80000000p-3f, 0x1.2a6e840000000p-28f, 0.0f},
-	{0x1.bc40000000000p-1f, 0x1.22aff20000000p-3f, 0x1.bb7b2e0000000p-28f, 0.0f},
-	{0x1.b960000000000p-1f, 0x1.2ffbf20000000p-3f, 0x1.34cc8c0000000p-28f, 0.0f},
-	{0x1.b660000000000p-1f, 0x1.3df3ac0000000p-3f, -0x1.d95f420000000p-28f, 0.0f},
-	{0x1.b380000000000p-1f, 0x1.4b6d700000000p-3f, -0x1.01dd5c0000000p-31f, 0.0f},
-	{0x1.b0a0000000000p-1f, 0x1.58fe0e0000000p-3f, 0x1.318bac0000000p-29f, 0.0f},
-	{0x1.adc0000000000p-1f, 0x1.66a5d40000000p-3f, 0x1.51d69a0000000p-30f, 0.0f},
-	{0x1.ab00000000000p-1f, 0x1.73cb900000000p-3f, 0x1.d3f4540000000p-29f, 0.0f},
-	{0x1.a820000000000p-1f, 0x1.81a18c0000000p-3f, -0x1.7bbf5a0000000p-28f, 0.0f},
-	{0x1.a580000000000p-1f, 0x1.8e588e0000000p-3f, 0x1.7585b80000000p-28f, 0.0f},
-	{0x1.a2c0000000000p-1f, 0x1.9bc0620000000p-3f, 0x1.e4df880000000p-28f, 0.0f},
-	{0x1.a020000000000p-1f, 0x1.a8a1500000000p-3f, -0x1.1994280000000p-35f, 0.0f},
-	{0x1.9d80000000000p-1f, 0x1.b5971a0000000p-3f, 0x1.09d66e0000000p-30f, 0.0f},
-	{0x1.9ae0000000000p-1f, 0x1.c2a2060000000p-3f, -0x1.3df4d80000000p-28f, 0.0f},
-	{0x1.9860000000000p-1f, 0x1.cf21d60000000p-3f, -0x1.34559c0000000p-31f, 0.0f},
-	{0x1.95c0000000000p-1f, 0x1.dc56ca0000000p-3f, 0x1.c8a5ec0000000p-28f, 0.0f},
-	{0x1.9340000000000p-1f, 0x1.e8ff260000000p-3f, 0x1.15d5e40000000p-30f, 0.0f},
-	{0x1.90e0000000000p-1f, 0x1.f518260000000p-3f, 0x1.61c0420000000p-30f, 0.0f},
-	{0x1.8e60000000000p-1f, 0x1.00f4040000000p-2f, 0x1.c31cca0000000p-28f, 0.0f},
-	{0x1.8c00000000000p-1f, 0x1.0713860000000p-2f, 0x1.35618a0000000p-32f, 0.0f},
-	{0x1.89a0000000000p-1f, 0x1.0d3c760000000p-2f, -0x1.e4ca860000000p-28f, 0.0f},
-	{0x1.8740000000000p-1f, 0x1.136ef00000000p-2f, 0x1.7414860000000p-29f, 0.0f},
-	{0x1.8500000000000p-1f, 0x1.1956d40000000p-2f, -0x1.190f420000000p-28f, 0.0f},
-	{0x1.82a0000000000p-1f, 0x1.1f9c3a0000000p-2f, -0x1.1675520000000p-31f, 0.0f},
-	{0x1.8060000000000p-1f, 0x1.2596420000000p-2f, -0x1.e40d380000000p-27f, 0.0f},
-	{0x1.7e20000000000p-1f, 0x1.2b99440000000p-2f, -0x1.3e50a20000000p-28f, 0.0f},
-	{0x1.7be0000000000p-1f, 0x1.31a55e0000000p-2f, -0x1.f0af4e0000000p-27f, 0.0f},
-	{0x1.79c0000000000p-1f, 0x1.3763e60000000p-2f, 0x1.1915180000000p-28f, 0.0f},
-	{0x1.77a0000000000p-1f, 0x1.3d2abc0000000p-2f, -0x1.8989640000000p-27f, 0.0f},
-	{0x1.7560000000000p-1f, 0x1.4351b40000000p-2f, -0x1.9178280000000p-27f, 0.0f},
-	{0x1.7340000000000p-1f, 0x1.4929e80000000p-2f, 0x1.b69cdc0000000p-27f, 0.0f},
-	{0x1.7140000000000p-1f, 0x1.4eb1f40000000p-2f, -0x1.29f1d00000000p-27f, 0.0f},
-	{0x1.6f20000000000p-1f, 0x1.549aec0000000p-2f, 0x1.77be200000000p-28f, 0.0f},
-	{0x1.6d20000000000p-1f, 0x1.5a32ec0000000p-2f, -0x1.a362a60000000p-27f, 0.0f},
-	{0x1.6b20000000000p-1f, 0x1.5fd2c80000000p-2f, -0x1.ce1df60000000p-28f, 0.0f}
-};
-
-DJB_DEV FF log_ff(const float4 *__restrict__ LT, float x) // x > 0, normal
+// ---- the sampling path's logf / powf / expf (dj_brdf.h:695, 1917, 1935) ------------------------------------------
+// glibc's own algorithms in double (djb_glibcf.h): the results are glibc's results, bit for bit, at 7-12 double
+// operations each.  GT = the table block of djb_glibcf.h (staged in shared memory by the kernels).  Arguments outside
+// the restated main branch (zero, subnormal, negative, NaN, huge) take the literal double path of djb_device.cuh.
+DJB_DEV float logf_lean(GlfTableShared GT, float x)
 {
-	const float LN2H = 0x1.62e4p-1f, LN2L = 0x1.7f7d1cp-20f, LN2LL = 0x1.ef358p-45f;
-	int bits = __float_as_int(x);
-	int e = (bits >> 23) - 127;
-	int mb = (bits & 0x007FFFFF) | 0x3F800000;
-	if (mb >= 0x3FB50000) { mb -= 0x00800000; ++e; }
-	const float m = __int_as_float(mb);
-	const float4 t = LT[(mb - 0x3F350000) >> 16];
-	const float p = m * t.x, rl = __fmaf_rn(m, t.x, -p), rh = p - 1.0f; // r = rh + rl exactly
-	const float ef = (float)e;
-	const float eH = ef * LN2H; // exact: 15-bit constant
-	const float pl = ef * LN2L, ple = __fmaf_rn(ef, LN2L, -pl);
-	float bb, tt;
-	// running sum h + l
-	float h = eH + t.y;
-	bb = h - eH;
-	float l = (eH - (h - bb)) + (t.y - bb);
-	l += (t.z + ple) + ef * LN2LL;
-	float h2 = h + pl;
-	bb = h2 - h; tt = (h - (h2 - bb)) + (pl - bb); l += tt; h = h2;
-	h2 = h + rh;
-	bb = h2 - h; tt = (h - (h2 - bb)) + (rh - bb); l += tt; h = h2;
-	const float sh = rh * rh, sl = __fmaf_rn(rh, rh, -sh);
-	const float ms = -0.5f * sh;
-	h2 = h + ms;
-	bb = h2 - h; tt = (h - (h2 - bb)) + (ms - bb); l += tt; h = h2;
-	const float q = __fmaf_rn(rh, __fmaf_rn(rh, __fmaf_rn(rh, -1.0f / 6.0f, 0.2f), -0.25f), 1.0f / 3.0f);
-	const float w = (sh * rh) * q;
-	l += (((rl - 0.5f * sl) - rh * rl) + sh * rl) + w; // log1p'(rh) rl = rl (1 - rh + rh^2)
-	FF r;
-	r.h = h + l;
-	r.l = (h - r.h) + l;
-	return r;
+	if (!glf_logf_ok(x)) return logf_literal(x);
+	return glf_logf(GT, x);
 }
-
-// float(log(double(x))): the reference's logf
-DJB_DEV float logf_lean(const float4 *__restrict__ LT, float x)
+DJB_DEV float powf_lean(GlfTableShared GT, float x, float y)
 {
-	if (!(x > 1.2e-38f && x < 3e38f)) return logf_cr(x);
-	const FF L = log_ff(LT, x);
-	return L.h + L.l;
+	if (!glf_powf_ok(x, y)) return powf_literal(x, y);
+	bool ok;
+	const float r = glf_powf(GT, x, y, ok);
+	return ok ? r : powf_literal(x, y);
 }
-
-// float(pow(double(x), double(y))) for 0 < x <= 1, y > 0: exp(y log x) with the product carried in float-float
-DJB_DEV float powf_lean(const float2 *__restrict__ T, const float4 *__restrict__ LT, float x, float y)
+DJB_DEV float expf_lean(GlfTableShared GT, float x)
 {
-	if (!(x > 1.2e-38f && x <= 1.0f && y > 0.0f && y < 8.0f)) return powf_cr(x, y);
-	const FF L = log_ff(LT, x);
-	const float ph = y * L.h, pl = __fmaf_rn(y, L.h, -ph) + y * L.l;
-	if (!(ph > -86.0f)) return powf_cr(x, y);
-	const ExpFF e = exp_ff(T, ph);
-	return (e.ph + (e.pl + e.ph * pl)) * pow2i(e.m); // exp(ph + pl) = exp(ph) (1 + pl)
+	if (!glf_expf_ok(x)) return expf_literal(x);
+	return glf_expf(GT, x);
 }
 
 // ---- pieces of the visible-normal sampling path (dj_brdf.h:1669-1709, 1818-1846, 1897-1957, 2089-2146) --------
@@ -507,8 +337,26 @@ DJB_DEV float ggx_qf2_lean(float u, float ck, float sk)
 	return div_ff(nh, nl, dh, dl);
 }
 
+// What the sampling path derives from the pair's second uniform alone: computed once per pair, outside the material loop.
+//   Beckmann: a = qf3_radial(u2) = erfinv(2 u2 - 1)                                          (dj_brdf.h:1954-1957, 1891-1894)
+//   GGX:      a = the sign S, b = the rational approximation's quotient pn / qn              (dj_brdf.h:2121-2146)
+struct SampleU2 { float a, b; };
+
 // ggx::qf3_radial + qf3_rational_approx, dj_brdf.h:2121-2146 (the two double Horner forms stay in double)
-DJB_DEV float ggx_qf3_lean(float u, float qf2)
+DJB_DEV SampleU2 ggx_qf3_u2(float u)
+{
+	SampleU2 r;
+	if (u < 0.5f) { u = (0.5f - u) * 2.0f; r.a = -1.0f; } // float(2.0 * (0.5 - u)): one rounding either way
+	else { u = (u - 0.5f) * 2.0f; r.a = 1.0f; }
+	const double du = (double)u;
+	const float pn = (float)(du * (du * (du * (-0.365728915865723) + 0.790235037209296) - 0.424965825137544)
+	                         + 0.000152998850436920);
+	const float qn = (float)(du * (du * (du * (du * 0.169507819808272 - 0.397203533833404) - 0.232500544458471) + 1.0)
+	                         - 0.539825872510702);
+	r.b = div_lean(pn, qn);
+	return r;
+}
+DJB_DEV float ggx_qf3_lean(SampleU2 su, float qf2)
 {
 	// alpha = float(sqrt(1.0 + double(qf2 * qf2)))
 	const FF v = two_sum(1.0f, qf2 * qf2);
@@ -523,60 +371,13 @@ DJB_DEV float ggx_qf3_lean(float u, float qf2)
 	} else {
 		alpha = (float)sqrt(1.0 + (double)(qf2 * qf2));
 	}
-	float S;
-	if (u < 0.5f) { u = (0.5f - u) * 2.0f; S = -1.0f; } // float(2.0 * (0.5 - u)): one rounding either way
-	else { u = (u - 0.5f) * 2.0f; S = 1.0f; }
-	const double du = (double)u;
-	const float pn = (float)(du * (du * (du * (-0.365728915865723) + 0.790235037209296) - 0.424965825137544)
-	                         + 0.000152998850436920);
-	const float qn = (float)(du * (du * (du * (du * 0.169507819808272 - 0.397203533833404) - 0.232500544458471) + 1.0)
-	                         - 0.539825872510702);
-	return S * alpha * div_lean(pn, qn);
-}
-
-// djb::erf (A&S 7.1.26, dj_brdf.h:667-688) through the float-float exponential
-DJB_DEV float erf_lean(const float2 *__restrict__ T, float xin)
-{
-	const float x = fabsf(xin);
-	const float xx = -x * x;
-	// |x| >= 4: (poly t) exp(-x^2) <= 0.137 e^-16 = 1.5e-8 is below half an ulp of 1.0f (2^-25 = 3.0e-8), so the
-	// reference's float(1.0 - ...) is exactly 1 (also for x = inf: t = 0, exp = 0).  Checked exhaustively on the CPU for
-	// every float in [3.9, 10]: the result is 1.0f from x = 3.9195216 on.  Common: narrow lobes make cot(theta_k) large.
-	if (xx <= -16.0f) return xin < 0.0f ? -1.0f : 1.0f;
-	if (!(xx > -100.0f)) return erf_as(xin); // NaN: literal path
-	const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
-	const float px = 0.3275911f * x;
-	const float uh = 1.0f + px;
-	const float ul = px <= 1.0f ? px - (uh - 1.0f) : 1.0f - (uh - px);
-	const float y0 = rcp_lean(uh);
-	const float t = __fmaf_rn(y0, __fmaf_rn(-uh, y0, 1.0f) - ul * y0, y0);
-	const float poly = ((((a5 * t + a4) * t) + a3) * t + a2) * t + a1;
-	const float pt = poly * t;
-	const ExpFF e = exp_ff(T, xx);
-	float y = 1.0f;
-	if (e.m >= -120) {
-		const float sc = pow2i(e.m);
-		const float mh = pt * e.ph, ml = __fmaf_rn(pt, e.ph, -mh) + pt * e.pl;
-		const float Mh = mh * sc, Ml = ml * sc;
-		const float dh = 1.0f - Mh, dl = (1.0f - dh) - Mh;
-		y = dh + (dl - Ml);
-	}
-	return xin < 0.0f ? -y : y;
-}
-
-// float(exp(double(x))) for x <= 0: the reference's std::exp(float) (glibc expf rounds correctly except for
-// ~1e-3 of arguments, which is the existing mismatch budget of the sampling path)
-DJB_DEV float expf_lean(const float2 *__restrict__ T, float x)
-{
-	if (!(x <= 0.0f && x > -86.0f)) return expf_cr(x);
-	const ExpFF e = exp_ff(T, x);
-	return (e.ph + e.pl) * pow2i(e.m);
+	return su.a * alpha * su.b; // S * alpha * (pn / qn), left to right
 }
 
 // djb::erfinv (Giles), dj_brdf.h:691-721
-DJB_DEV float erfinv_lean(const float4 *__restrict__ LT, float u)
+DJB_DEV float erfinv_lean(GlfTableShared GT, float u)
 {
-	float w = -logf_lean(LT, (1.0f - u) * (1.0f + u)), p;
+	float w = -logf_lean(GT, (1.0f - u) * (1.0f + u)), p;
 	if (w < 5.0f) {
 		w = w - 2.5f;
 		p = 2.81022636e-08f;
@@ -611,54 +412,96 @@ DJB_DEV float erfinv_lean(const float4 *__restrict__ LT, float u)
 }
 
 // beckmann::qf2_radial, dj_brdf.h:1897-1952
-DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, const float4 *__restrict__ LT, float u, float ck, float sk)
+DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, GlfTableShared GT, float u, float ck, float sk)
 {
 	const float sqrt_pi_inv = (float)(1.0 / sqrt(DJB_PI));
-	const float cot = div_lean(ck, sk), tan_k = div_lean(sk, ck);
-	float a = -1.0f, c = erf_lean(T, cot);
-	u = fmax_ref(u, 1e-6f);
-	const float fit = 1.0f + ck * (-0.876f + ck * (0.4265f - 0.0594f * ck));
-	float b = c - (1.0f + c) * powf_lean(T, LT, 1.0f - u, fit);
+	const bool sk_ok = sk > 1e-18f; // sk == 0 (k along the normal): cot = inf, the guarded division gives it
+	const float cot = sk_ok ? div_lean(ck, sk) : __fdiv_rn(ck, sk), tan_k = div_lean(sk, ck);
+	// c = djb::erf(cot) (A&S 7.1.26, dj_brdf.h:667-688) and
 	// normalization = float(1.0 / (double(1 + c) + double(sqrt_pi_inv * tan_k) * exp(double(-cot * cot))))
-	const float A = 1.0f + c, B = sqrt_pi_inv * tan_k, xx = -cot * cot;
-	float normalization;
+	// contain the same exponential (erf's own argument is -|cot| |cot|, the same float): one float-float evaluation serves both.
+	const float xx = -cot * cot;
+	float c, normalization;
+	const float B = sqrt_pi_inv * tan_k;
 	if (xx > -40.0f) {
 		const ExpFF e = exp_ff(T, xx);
-		const float sc = pow2i(e.m);
+		const float sc = pow2i(e.m); // m >= -58
+		// |cot| >= 4: (poly t) exp(-cot^2) is below half an ulp of 1.0f, the reference's float(1.0 - ...) is exactly 1
+		// (checked exhaustively on the CPU for every float in [3.9, 10]: 1.0f from 3.9195216 on)
+		float y = 1.0f;
+		if (xx > -16.0f) {
+			const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
+			const float px = 0.3275911f * fabsf(cot);
+			const float uh = 1.0f + px;
+			const float ul = px <= 1.0f ? px - (uh - 1.0f) : 1.0f - (uh - px);
+			const float y0 = rcp_lean(uh);
+			const float t = __fmaf_rn(y0, __fmaf_rn(-uh, y0, 1.0f) - ul * y0, y0);
+			const float poly = ((((a5 * t + a4) * t) + a3) * t + a2) * t + a1;
+			const float pt = poly * t;
+			const float mh = pt * e.ph, ml = __fmaf_rn(pt, e.ph, -mh) + pt * e.pl;
+			const float Mh = mh * sc, Ml = ml * sc;
+			const float dh = 1.0f - Mh, dl = (1.0f - dh) - Mh;
+			y = dh + (dl - Ml);
+		}
+		c = cot < 0.0f ? -y : y;
+		const float A = 1.0f + c;
 		const float bh = B * e.ph, bl = __fmaf_rn(B, e.ph, -bh) + B * e.pl;
 		const FF d = two_sum(A, bh * sc);
 		normalization = div_ff(1.0f, 0.0f, d.h, d.l + bl * sc);
 	} else if (xx == xx) {
-		normalization = rcp_lean(A); // exp(-cot^2) < 2^-57: invisible next to 1 + c >= 1
+		c = cot < 0.0f ? -1.0f : 1.0f;
+		normalization = rcp_lean(1.0f + c); // exp(-cot^2) < 2^-57: invisible next to 1 + c
+		if (!(c > 0.0f)) normalization = (float)(1.0 / ((double)(1.0f + c) + (double)B * exp((double)xx)));
 	} else {
-		normalization = (float)(1.0 / ((double)A + (double)B * exp((double)xx)));
+		c = erf_as(cot);
+		normalization = (float)(1.0 / ((double)(1.0f + c) + (double)B * exp((double)xx)));
 	}
+	float a = -1.0f;
+	u = fmax_ref(u, 1e-6f);
+	const float fit = 1.0f + ck * (-0.876f + ck * (0.4265f - 0.0594f * ck));
+	float b = c - (1.0f + c) * powf_lean(GT, 1.0f - u, fit);
 	int it = 0;
+	float ie = 0.0f;
+	bool converged = false;
 	while (++it < 10) {
 		if (!(b >= a && b <= c)) b = 0.5f * (a + c);
-		const float ie = erfinv_lean(LT, b);
-		const float value = normalization * (1.0f + b + sqrt_pi_inv * tan_k * expf_lean(T, -ie * ie)) - u;
+		ie = erfinv_lean(GT, b);
+		const float value = normalization * (1.0f + b + sqrt_pi_inv * tan_k * expf_lean(GT, -ie * ie)) - u;
 		const float derivative = normalization * (1.0f - ie * tan_k);
-		if (fabsf(value) < 1e-5f) break;
+		if (fabsf(value) < 1e-5f) { converged = true; break; }
 		if (value > 0.0f) c = b; else a = b;
 		b -= __fdiv_rn(value, derivative);
 	}
-	return erfinv_lean(LT, fmax_ref(-0.9999f, b));
+	// erfinv(max(-0.9999, b)): after a converged search b is the argument `ie` was just computed from
+	const float bm = fmax_ref(-0.9999f, b);
+	if (converged && bm == b) return ie;
+	return erfinv_lean(GT, bm);
 }
+
+template <int NDF>
+DJB_DEV SampleU2 lean_sample_u2(GlfTableShared GT, float u2) // u2: already clamped as microfacet::sample does
+{
+	if (NDF == NDF_GGX) return ggx_qf3_u2(u2);
+	SampleU2 r;
+	r.a = erfinv_lean(GT, 2.0f * u2 - 1.0f); // float(2.0 * u2 - 1): the product is exact, one rounding
+	r.b = 0.0f;
+	return r;
+}
+DJB_DEV float sample_clamp_u(float u) { return sat_ref(u) * 0.99998f + 0.00001f; } // dj_brdf.h:1680-1681
 
 // radial::sample_vp22_std_smith, dj_brdf.h:1818-1846
 template <int NDF>
-DJB_DEV void lean_std_slopes(const float2 *T, const float4 *LT, float u1, float u2, V3 k, float &xs, float &ys)
+DJB_DEV void lean_std_slopes(const float2 *T, GlfTableShared GT, float u1, SampleU2 su2, V3 k, float &xs, float &ys)
 {
 	const float ck = k.z;
 	const float sk = k.z < 1.0f ? sqrt_1m_sq(k.z) : 0.0f;
 	float tx, ty;
 	if (NDF == NDF_GGX) {
 		tx = ggx_qf2_lean(u1, ck, sk);
-		ty = ggx_qf3_lean(u2, tx);
+		ty = ggx_qf3_lean(su2, tx);
 	} else {
-		tx = beckmann_qf2_lean(T, LT, u1, ck, sk);
-		ty = erfinv_lean(LT, 2.0f * u2 - 1.0f); // float(2.0 * u2 - 1): the product is exact, one rounding
+		tx = beckmann_qf2_lean(T, GT, u1, ck, sk);
+		ty = su2.a;
 	}
 	if (sk == 0.0f) {
 		xs = tx;
@@ -671,12 +514,10 @@ DJB_DEV void lean_std_slopes(const float2 *T, const float4 *LT, float u1, float 
 	}
 }
 
-// microfacet::sample, dj_brdf.h:1669-1709
+// microfacet::sample, dj_brdf.h:1669-1709; u1 clamped, su2 = lean_sample_u2(clamped u2)
 template <int NDF>
-DJB_DEV V3 lean_sample(const float2 *T, const float4 *LT, const Params &p, float u1, float u2, V3 o)
+DJB_DEV V3 lean_sample(const float2 *T, GlfTableShared GT, const Params &p, float u1, SampleU2 su2, V3 o)
 {
-	u1 = sat_ref(u1) * 0.99998f + 0.00001f;
-	u2 = sat_ref(u2) * 0.99998f + 0.00001f;
 	const float oyay = o.y * p.ay;
 	const float a = o.x * p.ax + oyay * p.rho;
 	const float b = oyay * p.srho;
@@ -684,7 +525,7 @@ DJB_DEV V3 lean_sample(const float2 *T, const float4 *LT, const Params &p, float
 	const V3 os = normalize(mk(a, b, c));
 	if (os.z > 0.0f) {
 		float txm, tym;
-		lean_std_slopes<NDF>(T, LT, u1, u2, os, txm, tym);
+		lean_std_slopes<NDF>(T, GT, u1, su2, os, txm, tym);
 		const float txh = p.ax * txm + p.tx;
 		const float chol = p.rho * txm + p.srho * tym;
 		const float tyh = p.ay * chol + p.ty;
@@ -881,11 +722,11 @@ DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const Pai
 
 // microfacet::evalp_is, dj_brdf.h:1734-1765: sample, weight F G / G1(o), pdf = vndf / (4 cos theta_d)
 template <int NDF, int FK>
-DJB_DEV V3 lean_evalp_is(const float2 *T, const float4 *LT, const ParamsX &m, const FresnelDev &f, bool shadow, float u1,
-                         float u2, V3 o, V3 &i_out, float &pdf_out)
+DJB_DEV V3 lean_evalp_is(const float2 *T, GlfTableShared GT, const ParamsX &m, const FresnelDev &f, bool shadow, float u1,
+                         SampleU2 su2, V3 o, V3 &i_out, float &pdf_out)
 {
 	const Params &p = m.p;
-	const V3 i = lean_sample<NDF>(T, LT, p, u1, u2, o);
+	const V3 i = lean_sample<NDF>(T, GT, p, u1, su2, o);
 	pdf_out = 0.0f;
 	i_out = mk(0.f, 0.f, 0.f);
 	// G1(o) and sigma(o) are shared by the shadowing term, the weight and the visible-normal density

@@ -191,11 +191,14 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 	constexpr bool PERPAIR = PSRC != PSRC_BROADCAST;
 	__shared__ ParamsX s_params[PERPAIR ? 1 : MF_MAX_SMEM_PARAMS];
 	__shared__ float2 s_exp2[64]; // 2^(j/64) as float-float, for the Beckmann exponentials
-	__shared__ float4 s_log[128]; // logarithm table of the Beckmann sampling path
+	__shared__ __align__(16) uint64_t s_glf_words[GLF_TABLE_WORDS]; // glibc's logf / powf / expf tables (Beckmann sampling path)
+	uint32_t glf_addr = (uint32_t)__cvta_generic_to_shared(s_glf_words);
+	asm volatile("" : "+r"(glf_addr)); // opaque: kept in a register instead of being re-derived (4 uniform instructions) at every lookup
+	const GlfTableShared s_glf = {glf_addr};
 	if (!PERPAIR)
 		for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
 	if (NDF == NDF_BECKMANN && threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
-	if (NDF == NDF_BECKMANN && uses_u && threadIdx.x < 128) s_log[threadIdx.x] = g_log_128[threadIdx.x];
+	if (NDF == NDF_BECKMANN && uses_u && threadIdx.x < GLF_TABLE_WORDS) s_glf_words[threadIdx.x] = g_glf_table[threadIdx.x];
 	__syncthreads();
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
@@ -211,15 +214,22 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 		const V3 o = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
 		PairX c;
 		if (!uses_u) c = make_pair<uses_u ? OP_EVAL : OP>(va, o);
+		// sampling: the clamped uniforms and everything that follows from u2 alone, once per pair
+		float u1c = 0.0f;
+		SampleU2 su2;
+		if (uses_u) {
+			u1c = sample_clamp_u(va.x);
+			su2 = lean_sample_u2<NDF>(s_glf, sample_clamp_u(va.y));
+		}
 		auto one = [&](const ParamsX &mx, long long slot) {
 			if (OP == OP_PDF) {
 				A.out0[slot] = lean_pdf<NDF>(s_exp2, mx, shadow, c);
 			} else if (OP == OP_SAMPLE) {
-				st3(A.out0, slot, lean_sample<NDF>(s_exp2, s_log, mx.p, va.x, va.y, o));
+				st3(A.out0, slot, lean_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o));
 			} else if (OP == OP_EVALP_IS) {
 				V3 iv;
 				float pdf;
-				const V3 w = lean_evalp_is<NDF, FK>(s_exp2, s_log, mx, fr, shadow, va.x, va.y, o, iv, pdf);
+				const V3 w = lean_evalp_is<NDF, FK>(s_exp2, s_glf, mx, fr, shadow, u1c, su2, o, iv, pdf);
 				if (A.out0) st3(A.out0, slot, w);
 				if (A.out1) st3(A.out1, slot, iv);
 				if (A.out2) A.out2[slot] = pdf;

@@ -18,7 +18,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <exception>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -162,10 +164,11 @@ protected:
 	{
 		float_t a = 2 * u1 - 1, b = 2 * u2 - 1, r, phi;
 		if (a == 0 && b == 0) { *x = *y = 0; return; }
-		if (a * a > b * b) { r = a; phi = (float_t)(M_PI / 4.0) * (b / a); }
-		else { r = b; phi = (float_t)(M_PI / 2.0) - (float_t)(M_PI / 4.0) * (a / b); }
-		*x = r * (float_t)std::cos((double)phi);
-		*y = r * (float_t)std::sin((double)phi);
+		// the reference's rounding points: phi and the two products are double expressions rounded once
+		if (a * a > b * b) { r = a; phi = (float_t)((M_PI / 4.0) * (double)(b / a)); }
+		else { r = b; phi = (float_t)((M_PI / 2.0) - (double)(a / b) * (M_PI / 4.0)); }
+		*x = (float_t)((double)r * std::cos((double)phi));
+		*y = (float_t)((double)r * std::sin((double)phi));
 	}
 };
 
@@ -387,8 +390,9 @@ public:
 		float_t u[2] = {u1, u2}, p = 0;
 		vec3 w, iv;
 		evalp_is_batch(u, &o, 1, &w, &iv, &p, user_param);
-		// the reference leaves *i untouched when the sample carries no energy (dj_brdf.h:1749-1764)
-		if (i && (p > 0 || w.x > 0 || w.y > 0 || w.z > 0)) *i = iv;
+		// the reference writes *i only inside `if (G > 0)` (dj_brdf.h:1749-1764); the kernel returns the zero vector as the
+		// direction exactly when G <= 0 (a sampled direction has unit length otherwise)
+		if (i && (iv.x != 0 || iv.y != 0 || iv.z != 0)) *i = iv;
 		if (pdf) *pdf = p;
 		return w;
 	}
@@ -784,6 +788,49 @@ inline djb200_source describe_source(const brdf &b)
 }
 } // namespace detail
 
+// The device-resident copy of a table-backed BRDF (djb::tabular, djb::tabular_anisotropic), created on first use and again
+// after set_fresnel / set_shadow.  The reference's query methods are const and data-race free, and its Mitsuba plugins call
+// pdf() / sample() on one shared object from every render thread (mitsuba/dj_abc.cpp:77, 89), so the const path here only READS a
+// published (handle, revision) pair; creation is serialised by a mutex, and a superseded handle is never destroyed while the
+// object lives (another thread may still be launching on it): it is retired and freed by the destructor.
+namespace detail {
+class device_tables {
+	struct node { djb200_tabular *h; unsigned rev; };
+	mutable std::atomic<node *> m_cur;
+	mutable std::mutex m_mutex;
+	mutable std::vector<node *> m_retired;
+	device_tables(const device_tables &);
+	device_tables &operator=(const device_tables &);
+public:
+	device_tables() : m_cur(NULL) {}
+	~device_tables()
+	{
+		if (node *n = m_cur.load()) m_retired.push_back(n);
+		for (size_t k = 0; k < m_retired.size(); ++k) {
+			djb200_tabular_destroy(m_retired[k]->h);
+			delete m_retired[k];
+		}
+	}
+	// the handle built for revision `rev`; `make` creates one (called at most once per revision, under the lock)
+	template <class Make>
+	const djb200_tabular *get(unsigned rev, const Make &make) const
+	{
+		node *n = m_cur.load(std::memory_order_acquire);
+		if (n && n->rev == rev) return n->h;
+		std::lock_guard<std::mutex> lock(m_mutex);
+		n = m_cur.load(std::memory_order_acquire);
+		if (n && n->rev == rev) return n->h;
+		node *fresh = new node;
+		fresh->h = NULL;
+		fresh->rev = rev;
+		try { fresh->h = make(); } catch (...) { delete fresh; throw; }
+		if (n) m_retired.push_back(n);
+		m_cur.store(fresh, std::memory_order_release);
+		return fresh->h;
+	}
+};
+} // namespace detail
+
 // ---------------------------------------------------------------------------------------------------
 // dj_brdf.h:394-425: the isotropic "power iteration" fit, and -- as in the reference -- a microfacet BRDF of its own: the
 // tables are built on the GPU, uploaded once as a device-resident handle, and eval / evalp / pdf / sample / evalp_is run on
@@ -792,18 +839,15 @@ class tabular : public radial {
 	std::vector<float_t> m_p22, m_sigma, m_cdf, m_qf, m_residuals;
 	std::vector<vec3> m_fresnel_pts;
 	float_t m_alpha_beckmann, m_alpha_ggx;
-	mutable djb200_tabular *m_handle;
-	mutable unsigned m_handle_rev;
-	tabular() : radial(), m_handle(NULL), m_handle_rev(0) {}
+	detail::device_tables m_device;
+	tabular() : radial() {}
 public:
-	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4)
-	    : radial(fresnel::ideal(), shadow), m_handle(NULL), m_handle_rev(0)
+	tabular(const brdf &source, int resolution, bool shadow = true, int iterations = 4) : radial(fresnel::ideal(), shadow)
 	{
 		const brdf *src = &source;
 		std::vector<tabular *> self(1, this);
 		run(&src, 1, resolution, shadow, iterations, self);
 	}
-	~tabular() { djb200_tabular_destroy(m_handle); }
 	// many materials in one device pass (one CTA per material)
 	static std::vector<tabular *> fit_batch(const std::vector<const brdf *> &sources, int resolution, bool shadow = true,
 	                                        int iterations = 4)
@@ -827,38 +871,40 @@ protected:
 	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
 	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
 	{
-		upload();
+		const djb200_tabular *h = upload();
 		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
 		switch (op) {
-		case 0: st = djb200_tabular_eval(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 1: st = djb200_tabular_evalp(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 2: st = djb200_tabular_pdf(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 3: st = djb200_tabular_sample(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 4: st = djb200_tabular_evalp_is(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
+		case 0: st = djb200_tabular_eval(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 1: st = djb200_tabular_evalp(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 2: st = djb200_tabular_pdf(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 3: st = djb200_tabular_sample(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 4: st = djb200_tabular_evalp_is(h, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
 		}
 		detail::check(st);
 	}
-	const djb200_tabular *radial_handle() const
-	{
-		upload();
-		return m_handle;
-	}
-	void upload() const
-	{
-		if (!m_handle || m_handle_rev != m_fresnel_rev) { // upload the tables once (again after set_fresnel)
-			djb200_tabular_destroy(m_handle);
-			m_handle = NULL;
+	const djb200_tabular *radial_handle() const { return upload(); }
+	struct make_handle {
+		const tabular *t;
+		djb200_tabular *operator()() const
+		{
 			std::vector<float> fr;
-			fresnel_points(m_p22.size(), &fr);
+			t->fresnel_points(t->m_p22.size(), &fr);
 			djb200_tabular_fit f;
 			memset(&f, 0, sizeof f);
-			f.res = (int32_t)m_p22.size();
-			f.p22 = const_cast<float *>(&m_p22[0]); f.sigma = const_cast<float *>(&m_sigma[0]);
-			f.cdf = const_cast<float *>(&m_cdf[0]); f.qf = const_cast<float *>(&m_qf[0]);
+			f.res = (int32_t)t->m_p22.size();
+			f.p22 = const_cast<float *>(&t->m_p22[0]); f.sigma = const_cast<float *>(&t->m_sigma[0]);
+			f.cdf = const_cast<float *>(&t->m_cdf[0]); f.qf = const_cast<float *>(&t->m_qf[0]);
 			f.fresnel = &fr[0];
-			detail::check(djb200_tabular_create(&f, m_shadow ? 1 : 0, &m_handle));
-			m_handle_rev = m_fresnel_rev;
+			djb200_tabular *h = NULL;
+			detail::check(djb200_tabular_create(&f, t->m_shadow ? 1 : 0, &h));
+			return h;
 		}
+	};
+	// the device handle for the current Fresnel term / shadowing switch (uploaded by the constructor; again after a setter)
+	const djb200_tabular *upload() const
+	{
+		make_handle mk = {this};
+		return m_device.get(m_fresnel_rev, mk);
 	}
 
 private:
@@ -884,6 +930,7 @@ private:
 			out[k]->m_alpha_beckmann = fit[k].alpha_beckmann;
 			out[k]->m_alpha_ggx = fit[k].alpha_ggx;
 			out[k]->set_fresnel(fresnel::spline(out[k]->m_fresnel_pts)); // get_fresnel() returns the fitted spline
+			out[k]->upload(); // eagerly: the const query path then only reads the handle
 		}
 	}
 };
@@ -896,12 +943,10 @@ class tabular_anisotropic : public microfacet {
 	std::vector<vec3> m_fresnel_pts;
 	float_t m_beckmann[5], m_ggx[5];
 	int m_elevation_res, m_azimuthal_res;
-	mutable djb200_tabular *m_handle;
-	mutable unsigned m_handle_rev;
+	detail::device_tables m_device;
 public:
 	tabular_anisotropic(const brdf &source, int elevation_res, int azimuthal_res, bool shadow = true, int iterations = 4)
-	    : microfacet(fresnel::ideal(), shadow), m_elevation_res(elevation_res), m_azimuthal_res(azimuthal_res), m_handle(NULL),
-	      m_handle_rev(0)
+	    : microfacet(fresnel::ideal(), shadow), m_elevation_res(elevation_res), m_azimuthal_res(azimuthal_res)
 	{
 		DJB_ASSERT(elevation_res > 1 && azimuthal_res > 1 && "Invalid Resolution");
 		djb200_source src = detail::describe_source(source);
@@ -917,8 +962,8 @@ public:
 		memcpy(m_beckmann, fit.beckmann, sizeof m_beckmann);
 		memcpy(m_ggx, fit.ggx, sizeof m_ggx);
 		set_fresnel(fresnel::spline(m_fresnel_pts)); // get_fresnel() returns the fitted spline (dj_brdf.h:2700)
+		upload(); // eagerly: the const query path then only reads the handle
 	}
-	~tabular_anisotropic() { djb200_tabular_destroy(m_handle); }
 	static microfacet::params fit_beckmann_parameters(const tabular_anisotropic &t)
 	{
 		return microfacet::params::pdfparams(t.m_beckmann[0], t.m_beckmann[1], t.m_beckmann[2], t.m_beckmann[3], t.m_beckmann[4]);
@@ -945,7 +990,7 @@ public:
 	void get_sampling_tables(std::vector<float_t> *pdf1, std::vector<float_t> *cdf1, std::vector<float_t> *qf1,
 	                         std::vector<float_t> *pdf2, std::vector<float_t> *cdf2, std::vector<float_t> *qf2) const
 	{
-		upload();
+		const djb200_tabular *handle = upload();
 		std::vector<float_t> *v[6] = {pdf1, cdf1, qf1, pdf2, cdf2, qf2};
 		float *p[6];
 		for (int k = 0; k < 6; ++k) {
@@ -953,39 +998,45 @@ public:
 			p[k] = v[k] ? &(*v[k])[0] : NULL;
 		}
 		int32_t counts[2];
-		detail::check(djb200_tabular_anisotropic_sampling_tables(m_handle, p[0], p[1], p[2], p[3], p[4], p[5], counts));
+		detail::check(djb200_tabular_anisotropic_sampling_tables(handle, p[0], p[1], p[2], p[3], p[4], p[5], counts));
 		if (qf1) qf1->resize(counts[0]);
 		if (qf2) qf2->resize(counts[1]);
 	}
 
 protected:
 	int ndf_id() const { return -1; }
-	void upload() const
+	struct make_handle {
+		const tabular_anisotropic *t;
+		djb200_tabular *operator()() const
+		{
+			std::vector<float> fr;
+			t->fresnel_points((size_t)t->m_elevation_res, &fr);
+			djb200_tabular_anisotropic_fit f;
+			memset(&f, 0, sizeof f);
+			f.elev_res = t->m_elevation_res; f.azim_res = t->m_azimuthal_res;
+			f.p22 = const_cast<float *>(&t->m_p22[0]); f.sigma = const_cast<float *>(&t->m_sigma[0]);
+			f.fresnel = &fr[0];
+			djb200_tabular *h = NULL;
+			detail::check(djb200_tabular_anisotropic_create(&f, t->m_shadow ? 1 : 0, &h));
+			return h;
+		}
+	};
+	const djb200_tabular *upload() const
 	{
-		if (m_handle && m_handle_rev == m_fresnel_rev) return;
-		djb200_tabular_destroy(m_handle);
-		m_handle = NULL;
-		std::vector<float> fr;
-		fresnel_points((size_t)m_elevation_res, &fr);
-		djb200_tabular_anisotropic_fit f;
-		memset(&f, 0, sizeof f);
-		f.elev_res = m_elevation_res; f.azim_res = m_azimuthal_res;
-		f.p22 = const_cast<float *>(&m_p22[0]); f.sigma = const_cast<float *>(&m_sigma[0]);
-		f.fresnel = &fr[0];
-		detail::check(djb200_tabular_anisotropic_create(&f, m_shadow ? 1 : 0, &m_handle));
-		m_handle_rev = m_fresnel_rev;
+		make_handle mk = {this};
+		return m_device.get(m_fresnel_rev, mk);
 	}
 	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
 	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const
 	{
-		upload();
+		const djb200_tabular *h = upload();
 		djb200_status st = DJB200_ERR_INVALID_ARGUMENT;
 		switch (op) {
-		case 0: st = djb200_tabular_eval(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 1: st = djb200_tabular_evalp(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 2: st = djb200_tabular_pdf(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 3: st = djb200_tabular_sample(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
-		case 4: st = djb200_tabular_evalp_is(m_handle, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
+		case 0: st = djb200_tabular_eval(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 1: st = djb200_tabular_evalp(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 2: st = djb200_tabular_pdf(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 3: st = djb200_tabular_sample(h, p, n_params, layout, a, b, (int64_t)n, o0, where, stream); break;
+		case 4: st = djb200_tabular_evalp_is(h, p, n_params, layout, a, b, (int64_t)n, o0, o1, o2, where, stream); break;
 		}
 		detail::check(st);
 	}

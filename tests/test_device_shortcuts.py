@@ -64,3 +64,16 @@ def test_generated_preset_table_is_in_sync_with_the_reference(tmp_path):
     (tmp_path / "extract.py").write_text(script)
     subprocess.run([sys.executable, str(tmp_path / "extract.py"), str(ref)], check=True, capture_output=True)
     assert (tmp_path / "presets.inc").read_text() == committed
+
+
+def test_restated_glibc_float_functions_are_bit_identical_to_libm(tmp_path):
+    """csrc/djb_glibcf.h restates glibc's logf / expf / powf (what the reference's erfinv / qf2_radial call) operation for
+    operation; the same header compiled for the host must reproduce the platform's libm bit for bit.  Strided here (about 6e6
+    arguments per function); stride 1 -- every float of the sampling path's domains, 2e9 per function -- was run when the
+    tables were written: 0 mismatches (profiles/r02_glibcf_exhaustive.txt)."""
+    exe = tmp_path / "glibcf_check"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-pthread", str(ROOT / "tests" / "cpp" / "glibcf_check.cpp"), "-o", str(exe)],
+                   check=True, capture_output=True)
+    r = subprocess.run([str(exe), "331"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.count(" 0 mismatches") == 3, r.stdout

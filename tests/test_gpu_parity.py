@@ -101,7 +101,7 @@ def test_broadcast_16_materials(djb, port, ndf):
         check_close(got[m], port.eval(ndf, mats[m], wi, wo), f"eval material {m}")
         check_close(gotp[m], port.pdf(ndf, mats[m], wi, wo), f"pdf material {m}")
         same = bits_equal(gots[m], port.sample(ndf, mats[m], u, wo))
-        assert same.mean() > (0.999 if ndf == api.NDF_GGX else 0.98), (m, same.mean())
+        assert same.mean() > (0.999 if ndf == api.NDF_GGX else 0.9995), (m, same.mean())
 
 
 @pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
@@ -128,8 +128,9 @@ def test_sample_parity(djb, port, ndf, pname):
     got, want = b.sample(u, wo, P), port.sample(ndf, P, u, wo)
     same = bits_equal(got, want).all(axis=1)
     # GGX has no single-precision libm call: it must match to the bit almost everywhere.
-    # Beckmann goes through logf/expf/powf, which glibc and the device round differently in ~1e-3 cases.
-    assert same.mean() >= (0.99999 if ndf == api.NDF_GGX else 0.97), same.mean()
+    # Beckmann goes through logf / expf / powf: the device runs glibc's own algorithms (csrc/djb_glibcf.h), so it matches too
+    # (round 1, which rounded double evaluations instead, matched 99.92-99.97 %).
+    assert same.mean() >= (0.99999 if ndf == api.NDF_GGX else 0.9999), same.mean()
     err = np.abs(got.astype(np.float64) - want.astype(np.float64)).max(axis=1)
     assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, 0.999)
 
@@ -143,7 +144,7 @@ def test_evalp_is_parity(djb, port, ndf):
     gw, gi, gp = b.evalp_is(u, wo, P)
     ww, wi_, wp = port.evalp_is(ndf, P, u, wo, f)
     ok = bits_equal(gi, wi_).all(axis=1)
-    assert ok.mean() >= (0.9999 if ndf == api.NDF_GGX else 0.97)
+    assert ok.mean() >= (0.9999 if ndf == api.NDF_GGX else 0.9995), ok.mean()
     # where the sampled direction agrees to the bit, weight and pdf must meet the eval/pdf bar
     check_close(gw[ok], ww[ok], "evalp_is weight")
     check_close(gp[ok], wp[ok], "evalp_is pdf")

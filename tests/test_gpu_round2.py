@@ -1,0 +1,192 @@
+"""GPU parity, round 2: the cases VERDICT r01 found unpinned.
+
+* the CUDA path against the UNMODIFIED reference itself (oracle/_ref/libdjbref.so travels to the GPU box), not only
+  against the port -- eval / pdf / sample / evalp_is / MERL lookups / the isotropic fit;
+* chi-square test of `sample` against `pdf` (GGX, Beckmann, tabular);
+* fresnel::sgd as a microfacet Fresnel term;
+* one MERL handle + one microfacet descriptor driven from four host threads at once (SURVEY 8b threading).
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import api
+from tests import cases
+from tests.conftest import bits_equal
+from tests.test_gpu_parity import check_close, mk_brdf
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- directly against the reference --------------------------------------------------------------------------------
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("pname", ["iso0.1", "aniso", "offcentre"])
+def test_queries_against_the_unmodified_reference(djb, ref, ndf, pname):
+    wi, wo, u = cases.pairs(100_000, stream=300)
+    P = cases.param_sets(ref)[pname]
+    f = api.Fresnel.schlick([0.95, 0.64, 0.54])
+    b = mk_brdf(djb, ndf, f)
+    check_close(b.eval(wi, wo, P), ref.eval(ndf, P, wi, wo, f), f"eval {pname}", min_bit_rate=0.9999)
+    check_close(b.pdf(wi, wo, P), ref.pdf(ndf, P, wi, wo, f), f"pdf {pname}", min_bit_rate=0.9999)
+    same = bits_equal(b.sample(u, wo, P), ref.sample(ndf, P, u, wo, f)).all(axis=1)
+    assert same.mean() >= (0.99999 if ndf == api.NDF_GGX else 0.9999), same.mean()
+    gw, gi, gp = b.evalp_is(u, wo, P)
+    ww, wi_, wp = ref.evalp_is(ndf, P, u, wo, f)
+    ok = bits_equal(gi, wi_).all(axis=1)
+    assert ok.mean() >= 0.9995, ok.mean()
+    check_close(gw[ok], ww[ok], "evalp_is weight")
+    check_close(gp[ok], wp[ok], "evalp_is pdf")
+
+
+def test_merl_lookup_against_the_unmodified_reference(djb, ref):
+    wi, wo, _ = cases.pairs(200_000, stream=310)
+    table = cases.synthetic_merl_table(0.15)
+    assert np.array_equal(djb.merl.index(wi, wo), ref.merl_index(wi, wo)), "MERL cell index differs from the reference"
+    got, want = djb.merl(table).eval(wi, wo), ref.merl_eval(table, wi, wo)
+    assert bits_equal(got, want).all(), "MERL eval differs from the reference"
+    assert (want == 0).all(axis=1).any() and (want > 0).all(axis=1).any()  # both the 'negative -> 0' rule and real cells
+
+
+def test_isotropic_fit_against_the_unmodified_reference(djb, ref):
+    from tests.test_gpu_fit import check_fit
+    tab = cases.synthetic_merl_table(0.2, kind="ggx")
+    want = ref.fit_tabular(api.Source.merl(tab), 90)
+    check_fit(djb.tabular(djb.merl(tab), 90), want, "synthetic GGX table vs reference")
+
+
+# ---- fresnel::sgd inside a microfacet BRDF (dj_brdf.h:1316-1328, djb_device.cuh FK_SGD) -----------------------------
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_sgd_fresnel_term_in_a_microfacet_brdf(djb, port, ndf):
+    wi, wo, u = cases.pairs(100_000, stream=320)
+    f0, f1 = [0.12, 0.31, 0.66], [0.02, 0.2, 0.9]
+    f = api.Fresnel(api.F_SGD, f0 + f1)
+    cls = djb.ggx if ndf == api.NDF_GGX else djb.beckmann
+    b = cls(djb.fresnel.sgd(f0, f1), True)
+    for pname in ("iso0.5", "aniso"):
+        P = cases.param_sets(port)[pname]
+        check_close(b.eval(wi, wo, P), port.eval(ndf, P, wi, wo, f), f"sgd-fresnel eval {pname}", min_bit_rate=0.999)
+        check_close(b.evalp(wi, wo, P), port.evalp(ndf, P, wi, wo, f), f"sgd-fresnel evalp {pname}", min_bit_rate=0.999)
+        gw, gi, gp = b.evalp_is(u, wo, P)
+        ww, wi_, wp = port.evalp_is(ndf, P, u, wo, f)
+        ok = bits_equal(gi, wi_).all(axis=1)
+        assert ok.mean() >= 0.9995
+        check_close(gw[ok], ww[ok], f"sgd-fresnel evalp_is weight {pname}")
+    cs = np.zeros((4097, 3), np.float32)
+    cs[:, 0] = np.linspace(0, 1, 4097, dtype=np.float32)
+    assert bits_equal(b.fresnel_term(cs), port.component("fresnel", ndf, None, cs, fresnel=f)).mean() >= 0.999
+
+
+# ---- chi-square: the sampler draws from the density `pdf` reports -----------------------------------------------------
+def _chi2_sample_vs_pdf(b, P, wo, n=1 << 20, nz=24, nphi=48, sub=12, seed=0):
+    """Histogram of n sampled directions over an (i.z, phi) grid of the upper hemisphere against n * integral of pdf over
+    each cell (midpoint rule with sub x sub points per cell: equal-area cells, so the integral is mean(pdf) * cell area).
+    Directions sampled below the horizon have pdf 0 in the reference (G1(i) = 0) and are not binned.  Returns the
+    statistic, the degrees of freedom and the p-value.  n = 2^20: the reference's sampler is itself approximate (GGX's
+    rational quantile, dj_brdf.h:2138-2146; the 1e-5 tolerance of Beckmann's Newton search, :1939) -- run on the CPU
+    oracle, 4e6 samples already expose that (p = 1e-2 .. 1e-11 for the reference itself) while 1e6 do not (p = 0.17 .. 0.79)."""
+    from scipy import stats
+    rng = np.random.default_rng(seed)
+    u = rng.random((n, 2), dtype=np.float32)
+    o = np.broadcast_to(np.asarray(wo, np.float32), (n, 3)).copy()
+    i = np.asarray(b.sample(u, o, P))
+    up = i[:, 2] > 0
+    zi = np.minimum((i[up, 2] * nz).astype(np.int64), nz - 1)
+    ph = np.arctan2(i[up, 1], i[up, 0]) % (2 * np.pi)
+    pi_ = np.minimum((ph / (2 * np.pi) * nphi).astype(np.int64), nphi - 1)
+    obs = np.bincount(zi * nphi + pi_, minlength=nz * nphi).astype(np.float64)
+    # expected counts
+    zs = (np.arange(nz * sub) + 0.5) / (nz * sub)
+    ps = (np.arange(nphi * sub) + 0.5) / (nphi * sub) * 2 * np.pi
+    Z, PH = np.meshgrid(zs, ps, indexing="ij")
+    r = np.sqrt(1 - Z * Z)
+    q = np.stack([r * np.cos(PH), r * np.sin(PH), Z], -1).reshape(-1, 3).astype(np.float32)
+    oo = np.broadcast_to(np.asarray(wo, np.float32), q.shape).copy()
+    pdf = np.asarray(b.pdf(q, oo, P)).astype(np.float64).reshape(nz, sub, nphi, sub)
+    cell = (1.0 / nz) * (2 * np.pi / nphi)  # d(z) d(phi) is the solid angle measure
+    exp = n * pdf.mean(axis=(1, 3)).reshape(-1) * cell
+    # The reference's pdf is gated by G > 0 (dj_brdf.h:1719), i.e. it is 0 for directions behind the mean normal of an
+    # off-centre lobe although the sampler does produce them: cells the gate touches are left out.
+    gated = ~(pdf > 0).all(axis=(1, 3)).reshape(-1)
+    keep = (exp >= 25) & ~gated
+    pool = ~keep & ~gated
+    # cells with small expectation are pooled into one
+    o_k, e_k = np.append(obs[keep], obs[pool].sum()), np.append(exp[keep], exp[pool].sum())
+    if e_k[-1] < 25:
+        o_k, e_k = o_k[:-1], e_k[:-1]
+    stat = float(((o_k - e_k) ** 2 / e_k).sum())
+    dof = len(e_k)  # n is not conditioned on: every cell is free (mass below the horizon is not binned)
+    return stat, dof, float(stats.chi2.sf(stat, dof)), float(obs[~gated].sum() / n), float(exp[~gated].sum() / n)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("case", ["iso", "aniso", "offcentre"])
+def test_sample_follows_pdf_chi_square(djb, ndf, case):
+    cls = djb.ggx if ndf == api.NDF_GGX else djb.beckmann
+    b = cls()
+    P = {"iso": djb.params.isotropic(0.35), "aniso": djb.params.elliptic(0.25, 0.6, 0.7),
+         "offcentre": djb.params.pdfparams(0.4, 0.3, 0.3, 0.1, -0.15)}[case]
+    wo = np.array([np.sin(0.7) * np.cos(0.4), np.sin(0.7) * np.sin(0.4), np.cos(0.7)], np.float32)
+    stat, dof, p, mass_obs, mass_exp = _chi2_sample_vs_pdf(b, P, wo)
+    # the binned mass and the integral of the pdf over the upper hemisphere agree, and the histogram is a plausible draw
+    assert abs(mass_obs - mass_exp) < 2e-3, (mass_obs, mass_exp)
+    assert p > 1e-4, f"chi2 = {stat:.1f} on {dof} cells, p = {p:.2e}"
+
+
+def test_sampler_chi_square_detects_a_wrong_density(djb):
+    """The test has teeth: the histogram of GGX samples is rejected against the Beckmann pdf of the same roughness."""
+    P = djb.params.isotropic(0.35)
+    wo = np.array([np.sin(0.7), 0.0, np.cos(0.7)], np.float32)
+
+    class mixed:
+        def sample(self, u, o, p): return djb.ggx().sample(u, o, p)
+        def pdf(self, i, o, p): return djb.beckmann().pdf(i, o, p)
+    stat, dof, p, _, _ = _chi2_sample_vs_pdf(mixed(), P, wo, n=1 << 20)
+    assert p < 1e-12
+
+
+def test_tabular_sample_follows_pdf_chi_square(djb):
+    tab = djb.tabular(djb.ggx(), 90)  # fitted from an analytic GGX (alpha = 1): sampling goes through the fitted qf table
+    P = djb.params.isotropic(0.4)
+    wo = np.array([np.sin(0.5), 0.0, np.cos(0.5)], np.float32)
+    stat, dof, p, mass_obs, mass_exp = _chi2_sample_vs_pdf(tab, P, wo, nz=16, nphi=32)
+    # djb::tabular samples the NDF (not the visible normals) through a 90-entry piecewise-linear quantile table whose
+    # inverse is not exactly the tabulated density (the reference's own plot_qf test shows it: SURVEY section 4), so the
+    # histogram is held to a relative bound per cell rather than to the chi-square distribution
+    assert abs(mass_obs - mass_exp) < 2e-2, (mass_obs, mass_exp)
+    assert stat / dof < 60.0, (stat, dof)
+
+
+# ---- threading: concurrent calls on the same handles ----------------------------------------------------
+def test_four_host_threads_share_one_merl_handle_and_one_descriptor(djb, port):
+    n = 50_000
+    table = cases.random_merl_table(5)
+    m = djb.merl(table)
+    f = api.Fresnel.schlick([0.9, 0.5, 0.2])
+    g = mk_brdf(djb, api.NDF_GGX, f)
+    bk = mk_brdf(djb, api.NDF_BECKMANN, f)
+    P = cases.param_sets(port)["aniso"]
+    jobs = []
+    for t in range(4):
+        wi, wo, u = cases.pairs(n, stream=400 + 8 * t)
+        jobs.append((wi, wo, u, port.merl_eval(table, wi, wo), port.eval(api.NDF_GGX, P, wi, wo, f),
+                     port.pdf(api.NDF_BECKMANN, P, wi, wo, f), port.sample(api.NDF_GGX, P, u, wo)))
+    errors = []
+    barrier = threading.Barrier(4)
+
+    def work(t):
+        try:
+            wi, wo, u, w_merl, w_eval, w_pdf, w_smp = jobs[t]
+            barrier.wait()
+            for rep in range(25):  # host buffers: every call stages, launches and copies back on the calling thread
+                assert bits_equal(m.eval(wi, wo), w_merl).all(), "merl"
+                check_close(g.eval(wi, wo, P), w_eval, "eval")
+                check_close(bk.pdf(wi, wo, P), w_pdf, "pdf")
+                assert bits_equal(g.sample(u, wo, P), w_smp).all(axis=1).mean() > 0.9999, "sample"
+        except Exception as e:  # noqa: BLE001 -- reported by the main thread
+            errors.append((t, repr(e)))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors
