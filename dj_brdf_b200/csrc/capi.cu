@@ -186,6 +186,13 @@ struct StagingArena {
 static thread_local StagingArena t_arena;
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+// device bytes per staging slot of the host-buffer pipeline (DJB200_CHUNK_MB, default 256); read per call so tests can shrink it
+static size_t staging_budget_bytes()
+{
+	const char *env_mb = getenv("DJB200_CHUNK_MB");
+	return (size_t)(env_mb && atoi(env_mb) > 0 ? atoi(env_mb) : 256) << 20;
+}
+constexpr int64_t MIN_CHUNK_PAIRS = 4096;
 
 // body(dev_in[], dev_out[], chunk_n, stream): enqueue the kernels for one chunk; outputs use
 // out_stride = chunk_n.  reps = number of material blocks each output holds per pair.
@@ -197,12 +204,11 @@ static djb200_status host_pipeline(int64_t n, const std::vector<BulkIn> &ins, co
 	size_t per_pair = 0;
 	for (auto &i : ins) per_pair += i.item;
 	for (auto &o : outs) per_pair += o.item * (size_t)reps;
-	const char *env_mb = getenv("DJB200_CHUNK_MB"); // device megabytes per staging slot (default 256); read per call so tests can shrink it
 	static const bool trace = getenv("DJB200_TRACE") != nullptr;
-	const size_t budget = (size_t)(env_mb && atoi(env_mb) > 0 ? atoi(env_mb) : 256) << 20; // device bytes per pipeline slot
+	const size_t budget = staging_budget_bytes();
 	auto t_begin = std::chrono::steady_clock::now();
 	int64_t chunk = (int64_t)(budget / (per_pair ? per_pair : 1));
-	chunk = chunk < 4096 ? 4096 : chunk;
+	chunk = chunk < MIN_CHUNK_PAIRS ? MIN_CHUNK_PAIRS : chunk; // callers tile over materials so that this floor stays inside the budget
 	chunk &= ~(int64_t)3;
 	if (chunk > n) chunk = n;
 	const int SLOTS = 3;
@@ -251,10 +257,15 @@ static djb200_status host_pipeline(int64_t n, const std::vector<BulkIn> &ins, co
 			if (reps == 1)
 				PCU(cudaMemcpyAsync((char *)outs[k].host + (size_t)off * outs[k].item, dout[k], outs[k].item * (size_t)cn,
 				                    cudaMemcpyDeviceToHost, st));
-			else
+			else if ((size_t)n * outs[k].item <= ((size_t)1 << 31) - 1)
 				PCU(cudaMemcpy2DAsync((char *)outs[k].host + (size_t)off * outs[k].item, (size_t)n * outs[k].item, dout[k],
 				                      (size_t)cn * outs[k].item, (size_t)cn * outs[k].item, (size_t)reps,
 				                      cudaMemcpyDeviceToHost, st));
+			else // host pitch beyond what a pitched copy accepts (cudaDeviceProp::memPitch): one 1-D copy per material row
+				for (int64_t r = 0; r < reps; ++r)
+					PCU(cudaMemcpyAsync((char *)outs[k].host + ((size_t)r * (size_t)n + (size_t)off) * outs[k].item,
+					                    (const char *)dout[k] + (size_t)r * (size_t)cn * outs[k].item, outs[k].item * (size_t)cn,
+					                    cudaMemcpyDeviceToHost, st));
 		}
 	}
 	auto t_enq = std::chrono::steady_clock::now();
@@ -364,28 +375,51 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 
 	if (mem == DJB200_MEM_DEVICE) {
 		cudaStream_t st = (cudaStream_t)stream;
-		void *d_params = nullptr, *d_spline = nullptr;
+		struct Scratch { // stream-ordered descriptor scratch, released on every exit path
+			void *p = nullptr;
+			cudaStream_t st;
+			explicit Scratch(cudaStream_t s) : st(s) {}
+			~Scratch() { if (p) cudaFreeAsync(p, st); }
+		} d_params(st), d_spline(st);
 		if (layout == DJB200_PARAMS_BROADCAST) {
-			CU(upload_small(params, sizeof(djb200_params) * (size_t)n_params, &d_params, st));
-			L.params = d_params;
+			CU(upload_small(params, sizeof(djb200_params) * (size_t)n_params, &d_params.p, st));
+			L.params = d_params.p;
 		} else {
 			L.params = params; // bulk device array
 		}
 		if (L.fresnel_kind == DJB200_FRESNEL_SPLINE) {
-			CU(upload_small(mf->fresnel.points, sizeof(float) * 3 * (size_t)mf->fresnel.n_points, &d_spline, st));
-			L.spline_pts = (const float *)d_spline;
+			CU(upload_small(mf->fresnel.points, sizeof(float) * 3 * (size_t)mf->fresnel.n_points, &d_spline.p, st));
+			L.spline_pts = (const float *)d_spline.p;
 			L.spline_n = mf->fresnel.n_points;
 		}
 		L.a = a; L.b = b; L.n = n; L.out_stride = n;
 		L.out0 = out0; L.out1 = out1; L.out2 = out2;
 		cudaError_t e = launch(L, st);
-		if (d_params) cudaFreeAsync(d_params, st);
-		if (d_spline) cudaFreeAsync(d_spline, st);
 		if (e != cudaSuccess) return cuda_fail(e, "microfacet kernel launch");
 		return DJB200_OK;
 	}
 
-	// host memory: stage through the device in chunks; descriptors go to the arena's aux area (no per-call malloc)
+	// host memory: stage through the device in chunks; descriptors go to the arena's aux area (no per-call malloc).
+	// A BROADCAST call with very many materials is tiled over blocks of materials, so that one staging slot (the pipeline's
+	// smallest chunk x every material's output) stays inside the DJB200_CHUNK_MB budget.
+	if (layout == DJB200_PARAMS_BROADCAST) {
+		const size_t in_bytes = a_item + 12;
+		const size_t out_bytes = (out0 ? out0_item : 0) + (out1 ? 12 : 0) + (out2 ? 4 : 0);
+		const size_t per_chunk = staging_budget_bytes() / (size_t)MIN_CHUNK_PAIRS;
+		int64_t max_mats = out_bytes && per_chunk > in_bytes ? (int64_t)((per_chunk - in_bytes) / out_bytes) : 1;
+		if (max_mats < 1) max_mats = 1;
+		if (n_params > max_mats) {
+			for (int64_t m0 = 0; m0 < n_params; m0 += max_mats) {
+				const int64_t mc = n_params - m0 < max_mats ? n_params - m0 : max_mats;
+				djb200_status rc = microfacet_call(op, mf, params + m0, mc, layout, a, b, n,
+				                                   out0 ? out0 + (size_t)m0 * (size_t)n * (out0_item / 4) : nullptr,
+				                                   out1 ? out1 + (size_t)m0 * (size_t)n * 3 : nullptr,
+				                                   out2 ? out2 + (size_t)m0 * (size_t)n : nullptr, mem, stream, tab);
+				if (rc != DJB200_OK) return rc;
+			}
+			return DJB200_OK;
+		}
+	}
 	void *d_params = nullptr;
 	{
 		StagingArena &A = t_arena;

@@ -116,8 +116,8 @@ DJB_DEV float erf_as(float x) { return erf_as(x, exp((double)(-x * x))); }
 static __device__ __noinline__ float logf_literal(float x) { return (float)log((double)x); }
 static __device__ __noinline__ float expf_literal(float x) { return (float)exp((double)x); }
 static __device__ __noinline__ float powf_literal(float x, float y) { return (float)pow((double)x, (double)y); }
-DJB_DEV float logf_cr(float x) { return glf_logf_ok(x) ? glf_logf(GlfTablePtr{g_glf_table}, x) : logf_literal(x); }
-DJB_DEV float expf_cr(float x) { return glf_expf_ok(x) ? glf_expf(GlfTablePtr{g_glf_table}, x) : expf_literal(x); }
+DJB_DEV float logf_cr(float x) { return glf_logf_ok(x) ? glf_logf(GlfTablePtr{g_glf_table}, glf_hot(), x) : logf_literal(x); }
+DJB_DEV float expf_cr(float x) { return glf_expf_ok(x) ? glf_expf(GlfTablePtr{g_glf_table}, glf_hot(), x) : expf_literal(x); }
 DJB_DEV float powf_cr(float x, float y)
 {
 	if (glf_powf_ok(x, y)) {

@@ -53,8 +53,9 @@ namespace djb200 {
 //   [0, 32)   __logf_data.tab:       (1/c, log c)   for the 16 sub-intervals of [0x1.66p-1, 0x1.66p0)
 //   [32, 64)  __powf_log2_data.tab:  (1/c, log2 c)  same sub-intervals
 //   [64, 96)  __exp2f_data.tab:      bits of 2^(i/32) minus (i << 47), i = 0..31
-constexpr int GLF_TABLE_WORDS = 96;
-constexpr int GLF_OFF_LOG = 0, GLF_OFF_LOG2 = 32, GLF_OFF_EXP2 = 64;
+//   [96, 99)  the three "hot" constants of GlfHot below (logf's A2, expf's Shift and C1), [99] padding
+constexpr int GLF_TABLE_WORDS = 100;
+constexpr int GLF_OFF_LOG = 0, GLF_OFF_LOG2 = 32, GLF_OFF_EXP2 = 64, GLF_OFF_HOT = 96;
 
 #define GLF_TABLE_INIT                                                                                                  \
 	{                                                                                                                   \
@@ -83,7 +84,9 @@ constexpr int GLF_OFF_LOG = 0, GLF_OFF_LOG2 = 32, GLF_OFF_EXP2 = 64;
 		0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,                     \
 		0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,                     \
 		0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,                     \
-		0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull                      \
+		0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,                     \
+		/* hot constants: -0x1.ffffef20a4123p-2, 0x1.8p+52, 0x1.ebfce50fac4f3p-13 */                                    \
+		0xbfdffffef20a4123ull, 0x4338000000000000ull, 0x3f2ebfce50fac4f3ull, 0ull                                       \
 	}
 
 #if defined(__CUDACC__)
@@ -96,16 +99,16 @@ static const uint64_t g_glf_table[GLF_TABLE_WORDS] = GLF_TABLE_INIT;
 // .shift_scaled / .poly, __powf_log2_data.poly).  On the device they live in the constant bank, where a double operand of an
 // FMA costs no instruction (as immediates each one is two moves per use).
 enum {
-	GLC_LN2, GLC_LOG_A0, GLC_LOG_A1, GLC_LOG_A2,
-	GLC_INVLN2N, GLC_SHIFT, GLC_EXP_C0, GLC_EXP_C1, GLC_EXP_C2,
+	GLC_LN2, GLC_LOG_A0, GLC_LOG_A1, GLC_INVLN2N, GLC_EXP_C0, GLC_EXP_C2, // single-constant FMA operands of logf / expf
+	GLC_LOG_A2, GLC_SHIFT, GLC_EXP_C1,                                      // the GlfHot three
 	GLC_POW_A0, GLC_POW_A1, GLC_POW_A2, GLC_POW_A3, GLC_POW_A4,
 	GLC_SHIFT47, GLC_EXP2_C0, GLC_EXP2_C1, GLC_EXP2_C2,
 	GLC_COUNT
 };
 #define GLF_CONST_INIT                                                                                                  \
 	{                                                                                                                   \
-		0x1.62e42fefa39efp-1, -0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2,                       \
-		0x1.71547652b82fep+5, 0x1.8p+52, 0x1.c6af84b912394p-20, 0x1.ebfce50fac4f3p-13, 0x1.62e42ff0c52d6p-6,            \
+		0x1.62e42fefa39efp-1, -0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, 0x1.71547652b82fep+5, 0x1.c6af84b912394p-20, \
+		0x1.62e42ff0c52d6p-6, -0x1.ffffef20a4123p-2, 0x1.8p+52, 0x1.ebfce50fac4f3p-13,                                  \
 		0x1.27616c9496e0bp-2, -0x1.71969a075c67ap-2, 0x1.ec70a6ca7baddp-2, -0x1.7154748bef6c8p-1, 0x1.71547652ab82bp0,  \
 		0x1.8p+47, 0x1.c6af84b912394p-5, 0x1.ebfce50fac4f3p-3, 0x1.62e42ff0c52d6p-1                                     \
 	}
@@ -128,21 +131,44 @@ struct GlfTableShared {
 	uint32_t s; // __cvta_generic_to_shared of the staged block (16-byte aligned)
 	GLF_MEM void pair(int w, double &a, double &b) const
 	{
-		asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(s + 8u * (uint32_t)w));
+		asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(s + 8u * (uint32_t)w));
 	}
 	GLF_MEM uint64_t word(int w) const
 	{
 		uint64_t v;
-		asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(s + 8u * (uint32_t)w));
+		asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(s + 8u * (uint32_t)w));
 		return v;
 	}
 };
 #endif
 
+// Three of the constants are the second constant operand of a fused multiply-add (A1 r + A2, InvLn2N x + Shift, C0 r + C1).
+// A device FMA takes one operand from the constant bank / a uniform register for free; the other has to sit in a register.
+// A kernel that calls these functions in a loop reads the three once from its staged table block (glf_hot): the assembler
+// re-materialises constant-bank loads at every use, but not loads from shared memory.
+struct GlfHot { double log_a2, exp_shift, exp_c1; };
+template <class TB>
+GLF_FN GlfHot glf_hot(TB T)
+{
+	GlfHot h;
+	h.log_a2 = GLF_AS_F64(T.word(GLF_OFF_HOT));
+	h.exp_shift = GLF_AS_F64(T.word(GLF_OFF_HOT + 1));
+	h.exp_c1 = GLF_AS_F64(T.word(GLF_OFF_HOT + 2));
+	return h;
+}
+GLF_FN GlfHot glf_hot() // from the constant bank: one-off calls
+{
+	GlfHot h;
+	h.log_a2 = GLC(GLC_LOG_A2);
+	h.exp_shift = GLC(GLC_SHIFT);
+	h.exp_c1 = GLC(GLC_EXP_C1);
+	return h;
+}
+
 // glibc logf, main branch: x positive, normal, finite (glibc e_logf.c; __logf_fma).  T = the table block above.
 GLF_FN bool glf_logf_ok(float x) { return GLF_AS_U32(x) - 0x00800000u < 0x7f800000u - 0x00800000u; }
 template <class TB>
-GLF_FN float glf_logf(TB T, float x)
+GLF_FN float glf_logf(TB T, const GlfHot &H, float x)
 {
 	const uint32_t ix = GLF_AS_U32(x);
 	// x = 2^k z with z in [0x1.66p-1, 0x1.66p0), c the centre of z's sub-interval: log x = k ln2 + log c + log1p(z / c - 1)
@@ -156,7 +182,7 @@ GLF_FN float glf_logf(TB T, float x)
 	const double r = GLF_FMA(z, invc, -1.0);
 	const double y0 = GLF_FMA((double)k, GLC(GLC_LN2), logc);
 	const double r2 = r * r;
-	double y = GLF_FMA(GLC(GLC_LOG_A1), r, GLC(GLC_LOG_A2));
+	double y = GLF_FMA(GLC(GLC_LOG_A1), r, H.log_a2);
 	y = GLF_FMA(GLC(GLC_LOG_A0), r2, y);
 	y = GLF_FMA(y, r2, y0 + r);
 	// glibc returns +0 for x == 1 before the evaluation; the evaluation gives the same (k = 0, i = 9: 1/c = 1, log c = 0, r = 0)
@@ -166,17 +192,17 @@ GLF_FN float glf_logf(TB T, float x)
 // glibc expf, main branch: |x| < 88 (glibc e_expf.c; __expf_fma)
 GLF_FN bool glf_expf_ok(float x) { return ((GLF_AS_U32(x) >> 20) & 0x7ffu) <= 0x42au; }
 template <class TB>
-GLF_FN float glf_expf(TB T, float x)
+GLF_FN float glf_expf(TB T, const GlfHot &H, float x)
 {
 	const double xd = (double)x;
 	// x = (k + r) ln2 / 32 with |r| <= 1/2: exp x = 2^(k / 32) 2^(r / 32); the shift constant leaves k in the low bits
-	const double zs = GLF_FMA(GLC(GLC_INVLN2N), xd, GLC(GLC_SHIFT));
+	const double zs = GLF_FMA(GLC(GLC_INVLN2N), xd, H.exp_shift);
 	const uint64_t ki = GLF_AS_U64(zs);
-	const double kd = zs - GLC(GLC_SHIFT);
+	const double kd = zs - H.exp_shift;
 	const double r = GLF_FMA(GLC(GLC_INVLN2N), xd, -kd);
 	const uint64_t t = T.word(GLF_OFF_EXP2 + (int)(ki & 31u)) + (ki << 47);
 	const double s = GLF_AS_F64(t);
-	const double z = GLF_FMA(GLC(GLC_EXP_C0), r, GLC(GLC_EXP_C1));
+	const double z = GLF_FMA(GLC(GLC_EXP_C0), r, H.exp_c1);
 	const double r2 = r * r;
 	double y = GLF_FMA(GLC(GLC_EXP_C2), r, 1.0);
 	y = GLF_FMA(z, r2, y);

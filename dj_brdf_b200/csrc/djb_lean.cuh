@@ -257,22 +257,23 @@ struct FF { float h, l; }; // unevaluated sum h + l
 // glibc's own algorithms in double (djb_glibcf.h): the results are glibc's results, bit for bit, at 7-12 double
 // operations each.  GT = the table block of djb_glibcf.h (staged in shared memory by the kernels).  Arguments outside
 // the restated main branch (zero, subnormal, negative, NaN, huge) take the literal double path of djb_device.cuh.
-DJB_DEV float logf_lean(GlfTableShared GT, float x)
+struct GlfCtx { GlfTableShared T; GlfHot H; }; // the staged tables + the register-held constants, set up once per kernel
+DJB_DEV float logf_lean(const GlfCtx &GT, float x)
 {
 	if (!glf_logf_ok(x)) return logf_literal(x);
-	return glf_logf(GT, x);
+	return glf_logf(GT.T, GT.H, x);
 }
-DJB_DEV float powf_lean(GlfTableShared GT, float x, float y)
+DJB_DEV float powf_lean(const GlfCtx &GT, float x, float y)
 {
 	if (!glf_powf_ok(x, y)) return powf_literal(x, y);
 	bool ok;
-	const float r = glf_powf(GT, x, y, ok);
+	const float r = glf_powf(GT.T, x, y, ok);
 	return ok ? r : powf_literal(x, y);
 }
-DJB_DEV float expf_lean(GlfTableShared GT, float x)
+DJB_DEV float expf_lean(const GlfCtx &GT, float x)
 {
 	if (!glf_expf_ok(x)) return expf_literal(x);
-	return glf_expf(GT, x);
+	return glf_expf(GT.T, GT.H, x);
 }
 
 // ---- pieces of the visible-normal sampling path (dj_brdf.h:1669-1709, 1818-1846, 1897-1957, 2089-2146) --------
@@ -374,10 +375,10 @@ DJB_DEV float ggx_qf3_lean(SampleU2 su, float qf2)
 	return su.a * alpha * su.b; // S * alpha * (pn / qn), left to right
 }
 
-// djb::erfinv (Giles), dj_brdf.h:691-721
-DJB_DEV float erfinv_lean(GlfTableShared GT, float u)
+// djb::erfinv (Giles), dj_brdf.h:691-721: the part after w = -logf((1 - u)(1 + u))
+DJB_DEV float erfinv_poly(float w, float u)
 {
-	float w = -logf_lean(GT, (1.0f - u) * (1.0f + u)), p;
+	float p;
 	if (w < 5.0f) {
 		w = w - 2.5f;
 		p = 2.81022636e-08f;
@@ -410,9 +411,29 @@ DJB_DEV float erfinv_lean(GlfTableShared GT, float u)
 	}
 	return p * u;
 }
+DJB_DEV float erfinv_lean(const GlfCtx &GT, float u) { return erfinv_poly(-logf_lean(GT, (1.0f - u) * (1.0f + u)), u); }
+// one trip of the quantile search needs erfinv(b) and expf(-erfinv(b)^2): the rare arguments outside the restated branches of
+// logf / expf (b = +-1, NaN) are tested once, after both fast evaluations, and redone literally
+static __device__ __noinline__ float2 erfinv_exp_literal(float u)
+{
+	const float ie = erfinv_giles(u);
+	return make_float2(ie, expf_cr(-ie * ie));
+}
+DJB_DEV void erfinv_exp_lean(const GlfCtx &GT, float u, float &ie, float &ex)
+{
+	const float x1 = (1.0f - u) * (1.0f + u);
+	ie = erfinv_poly(-glf_logf(GT.T, GT.H, x1), u);
+	const float x2 = -ie * ie;
+	ex = glf_expf(GT.T, GT.H, x2);
+	if (!(glf_logf_ok(x1) && glf_expf_ok(x2))) {
+		const float2 r = erfinv_exp_literal(u);
+		ie = r.x;
+		ex = r.y;
+	}
+}
 
 // beckmann::qf2_radial, dj_brdf.h:1897-1952
-DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, GlfTableShared GT, float u, float ck, float sk)
+DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, const GlfCtx &GT, float u, float ck, float sk)
 {
 	const float sqrt_pi_inv = (float)(1.0 / sqrt(DJB_PI));
 	const bool sk_ok = sk > 1e-18f; // sk == 0 (k along the normal): cot = inf, the guarded division gives it
@@ -465,8 +486,9 @@ DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, GlfTableShared GT,
 	bool converged = false;
 	while (++it < 10) {
 		if (!(b >= a && b <= c)) b = 0.5f * (a + c);
-		ie = erfinv_lean(GT, b);
-		const float value = normalization * (1.0f + b + sqrt_pi_inv * tan_k * expf_lean(GT, -ie * ie)) - u;
+		float ex;
+		erfinv_exp_lean(GT, b, ie, ex);
+		const float value = normalization * (1.0f + b + sqrt_pi_inv * tan_k * ex) - u;
 		const float derivative = normalization * (1.0f - ie * tan_k);
 		if (fabsf(value) < 1e-5f) { converged = true; break; }
 		if (value > 0.0f) c = b; else a = b;
@@ -479,7 +501,7 @@ DJB_DEV float beckmann_qf2_lean(const float2 *__restrict__ T, GlfTableShared GT,
 }
 
 template <int NDF>
-DJB_DEV SampleU2 lean_sample_u2(GlfTableShared GT, float u2) // u2: already clamped as microfacet::sample does
+DJB_DEV SampleU2 lean_sample_u2(const GlfCtx &GT, float u2) // u2: already clamped as microfacet::sample does
 {
 	if (NDF == NDF_GGX) return ggx_qf3_u2(u2);
 	SampleU2 r;
@@ -491,7 +513,7 @@ DJB_DEV float sample_clamp_u(float u) { return sat_ref(u) * 0.99998f + 0.00001f;
 
 // radial::sample_vp22_std_smith, dj_brdf.h:1818-1846
 template <int NDF>
-DJB_DEV void lean_std_slopes(const float2 *T, GlfTableShared GT, float u1, SampleU2 su2, V3 k, float &xs, float &ys)
+DJB_DEV void lean_std_slopes(const float2 *T, const GlfCtx &GT, float u1, SampleU2 su2, V3 k, float &xs, float &ys)
 {
 	const float ck = k.z;
 	const float sk = k.z < 1.0f ? sqrt_1m_sq(k.z) : 0.0f;
@@ -516,7 +538,7 @@ DJB_DEV void lean_std_slopes(const float2 *T, GlfTableShared GT, float u1, Sampl
 
 // microfacet::sample, dj_brdf.h:1669-1709; u1 clamped, su2 = lean_sample_u2(clamped u2)
 template <int NDF>
-DJB_DEV V3 lean_sample(const float2 *T, GlfTableShared GT, const Params &p, float u1, SampleU2 su2, V3 o)
+DJB_DEV V3 lean_sample(const float2 *T, const GlfCtx &GT, const Params &p, float u1, SampleU2 su2, V3 o)
 {
 	const float oyay = o.y * p.ay;
 	const float a = o.x * p.ax + oyay * p.rho;
@@ -722,7 +744,7 @@ DJB_DEV float lean_pdf(const float2 *T, const ParamsX &m, bool shadow, const Pai
 
 // microfacet::evalp_is, dj_brdf.h:1734-1765: sample, weight F G / G1(o), pdf = vndf / (4 cos theta_d)
 template <int NDF, int FK>
-DJB_DEV V3 lean_evalp_is(const float2 *T, GlfTableShared GT, const ParamsX &m, const FresnelDev &f, bool shadow, float u1,
+DJB_DEV V3 lean_evalp_is(const float2 *T, const GlfCtx &GT, const ParamsX &m, const FresnelDev &f, bool shadow, float u1,
                          SampleU2 su2, V3 o, V3 &i_out, float &pdf_out)
 {
 	const Params &p = m.p;

@@ -184,8 +184,15 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 
 // The lean FP32 path (djb_lean.cuh) for an ideal or Schlick Fresnel term, every query, both params layouts.
 // Same results as the mirrored kernels below (tests compare the two at full size), about half the instructions.
+// resident CTAs per SM the register allocation aims for: the Beckmann sampling kernel is a long dependent chain per thread
+// (stall_wait 39 % at 4 CTAs / 54 registers), so it is held to 51 registers = 5 CTAs
+#ifndef DJB200_BSAMPLE_MINB
+#define DJB200_BSAMPLE_MINB 5
+#endif
+constexpr int lean_min_blocks(int ndf, int op) { return (ndf == NDF_BECKMANN && op == OP_SAMPLE) ? DJB200_BSAMPLE_MINB : 1; }
+
 template <int NDF, int FK, int OP, int PSRC>
-__global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP)) mf_lean_kernel(MfKernelArgs A)
 {
 	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
 	constexpr bool PERPAIR = PSRC != PSRC_BROADCAST;
@@ -194,12 +201,14 @@ __global__ void __launch_bounds__(MF_THREADS) mf_lean_kernel(MfKernelArgs A)
 	__shared__ __align__(16) uint64_t s_glf_words[GLF_TABLE_WORDS]; // glibc's logf / powf / expf tables (Beckmann sampling path)
 	uint32_t glf_addr = (uint32_t)__cvta_generic_to_shared(s_glf_words);
 	asm volatile("" : "+r"(glf_addr)); // opaque: kept in a register instead of being re-derived (4 uniform instructions) at every lookup
-	const GlfTableShared s_glf = {glf_addr};
 	if (!PERPAIR)
 		for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
 	if (NDF == NDF_BECKMANN && threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
 	if (NDF == NDF_BECKMANN && uses_u && threadIdx.x < GLF_TABLE_WORDS) s_glf_words[threadIdx.x] = g_glf_table[threadIdx.x];
 	__syncthreads();
+	GlfCtx s_glf;
+	s_glf.T.s = glf_addr;
+	if (NDF == NDF_BECKMANN && uses_u) s_glf.H = glf_hot(s_glf.T); // three constants held in registers for the whole kernel
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
 	const long long stride = (long long)gridDim.x * blockDim.x;

@@ -217,11 +217,9 @@ template <int OP, bool PERPAIR>
 static cudaError_t launch_tq(const TabQueryArgs &A, cudaStream_t st)
 {
 	const size_t smem = sizeof(float) * 6 * (size_t)A.res;
-	static bool attr_set = false;
-	if (!attr_set && smem > 40 * 1024) {
+	if (smem > 40 * 1024) { // the attribute belongs to the current device's context: set whenever it is needed (cheap)
 		cudaError_t e = cudaFuncSetAttribute(tabular_query_kernel<OP, PERPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		if (e != cudaSuccess) return e;
-		attr_set = true;
 	}
 	long long want = (A.n + TQ_THREADS - 1) / TQ_THREADS, cap = (long long)sm_count() * 4;
 	tabular_query_kernel<OP, PERPAIR><<<(int)(want < cap ? want : cap), TQ_THREADS, smem, st>>>(A);

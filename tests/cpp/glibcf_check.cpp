@@ -49,6 +49,7 @@ int main(int argc, char **argv)
 {
 	const uint64_t stride = argc > 1 ? strtoull(argv[1], nullptr, 10) : 1021;
 	const GlfTablePtr T = {g_glf_table};
+	const GlfHot H = glf_hot();
 	int bad_total = 0;
 
 	{ // logf over the positive normal floats
@@ -56,7 +57,7 @@ int main(int argc, char **argv)
 		parallel(0x00800000u, 0x7f800000u, stride, [&](uint64_t b) {
 			const float x = glf_as_f32((uint32_t)b);
 			if (!glf_logf_ok(x)) { bad++; return; }
-			const float want = logf(x), got = glf_logf(T, x);
+			const float want = logf(x), got = glf_logf(T, H, x);
 			n.fetch_add(1, std::memory_order_relaxed);
 			if (glf_as_u32(want) != glf_as_u32(got)) {
 				if (bad++ < 5) printf("  logf(%a): libm %a, restated %a\n", x, want, got);
@@ -71,7 +72,7 @@ int main(int argc, char **argv)
 			parallel(0u, 0x42b00000u, stride, [&](uint64_t b) {
 				const float x = glf_as_f32((uint32_t)b | (sign << 31));
 				if (!glf_expf_ok(x)) { bad++; return; }
-				const float want = expf(x), got = glf_expf(T, x);
+				const float want = expf(x), got = glf_expf(T, H, x);
 				n.fetch_add(1, std::memory_order_relaxed);
 				if (glf_as_u32(want) != glf_as_u32(got)) {
 					if (bad++ < 5) printf("  expf(%a): libm %a, restated %a\n", x, want, got);

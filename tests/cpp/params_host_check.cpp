@@ -61,6 +61,18 @@ int main()
 		djb::fresnel::f0_to_ior(djb::vec3(0.02f * k, 1.0f, 0.5f), &v1);
 		printf("fresnel %a %a | %a %a %a | %a %a %a\n", f0, ior, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z);
 	}
+	// brdf::sample / brdf::pdf defaults (cosine-weighted concentric warp, dj_brdf.h:726-752, 828-843), through a BRDF class that
+	// keeps them (sgd; its constructor only looks the preset up)
+	{
+		djb::sgd sg("gold-metallic-paint");
+		const djb::vec3 up(0, 0, 1);
+		for (int k = 0; k <= 16; ++k)
+			for (int j = 0; j <= 16; ++j) {
+				const float u1 = (k == 16) ? 0.5f : (k + 0.37f) / 16.0f, u2 = (j == 16) ? 0.5f : (j + 0.81f) / 16.0f;
+				const djb::vec3 s = sg.sample(u1, u2, up);
+				printf("sample %a %a %a pdf %a\n", s.x, s.y, s.z, sg.pdf(s, up));
+			}
+	}
 	djb::beckmann::lrep dflt;
 	const float *m = reinterpret_cast<const float *>(&dflt);
 	printf("lrep default %a %a %a %a %a\n", m[0], m[1], m[2], m[3], m[4]);

@@ -68,7 +68,7 @@ def test_params_host_api_matches_reference(djb, tmp_path):
     a = subprocess.run([str(ours)], capture_output=True, text=True)
     b = subprocess.run([str(tmp_path / "params_ref")], capture_output=True, text=True)
     assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
-    assert a.stdout == b.stdout and a.stdout.count("\n") == 242 + 61 + 29
+    assert a.stdout == b.stdout and a.stdout.count("\n") == 242 + 61 + 29 + 17 * 17
 
 
 def test_facade_fails_loudly_without_gpu(djb, bins):
