@@ -11,10 +11,14 @@ every material: 6 x 16 x 1e8 = 9.6e9 BRDF queries per GPU per step.
 
 * `value`  : whole-job BRDF queries/s with inputs resident in HBM (device pointers through the C-ABI).
 * `e2e`    : the same step through the C-ABI with HOST (pinned) buffers: H2D of the directions and D2H of every
-             result inside the timed region.
+             result inside the timed region (distinct slabs of the 1e8 pairs, >= 3 steps); null with --no-e2e.
 * `roofline`: the dominant kernel of the step against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
 * `cpu_baseline`: oracle/_ref (the unmodified reference compiled in place) or the oracle port, timed on the
              host cores on a bounded sample of the same workload (rank 0, N = 1 only).
+* the other BASELINE.json configurations ride on the same line, each with its own roofline and (N = 1) CPU baseline:
+  `c1` (config 0: 1e6 pairs GGX iso 0.1, single-thread reference beside it), `merl` (config 3, section-8d table, random and
+  coherent lookups), `fit` (config 4: 128 distinct tables x 50 iterations sharded by material), `aniso_fit` (one 90 x 90
+  fit, rows sharded over the GPUs, exchange inside the library), `lean` (config 5, row bands).
 
 The oracle is executed here only as the CPU baseline / reference arm, never as the thing measured for `value`.
 """
@@ -34,10 +38,13 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+from dj_brdf_b200 import workloads  # noqa: E402  (host-side synthetic inputs, numpy only)
+
 METRIC = "brdf_evals_per_s"
 UNIT = "evals/s"
 OPS = ("eval", "pdf", "sample")
 NDFS = ("ggx", "beckmann")
+materials = workloads.materials
 # algorithmic bytes per (pair, material) query at M materials:
 #   eval:   24 B pair read once + 12 B result per material
 #   pdf:    24 B pair read once +  4 B result per material
@@ -50,15 +57,6 @@ def algo_bytes(op, pairs, mats):
     return pairs * per_pair_in + pairs * mats * per_out + 48 * mats
 
 
-def materials(m=16, seed=1):
-    """config 2: alpha1, alpha2 log-uniform in [0.02, 0.8], phi_a uniform in [0, pi)."""
-    rng = np.random.default_rng(seed)
-    a1 = np.exp(rng.uniform(np.log(0.02), np.log(0.8), m)).astype(np.float32)
-    a2 = np.exp(rng.uniform(np.log(0.02), np.log(0.8), m)).astype(np.float32)
-    ph = rng.uniform(0, np.pi, m).astype(np.float32)
-    return a1, a2, ph
-
-
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -67,6 +65,11 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def hbm_roofline(algorithmic_bytes, ms, peak, traffic=None):
+    gbs = algorithmic_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -118,13 +121,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own code (oracle/_ref) or the oracle port, all host threads
-def cpu_arm(pairs, mats, steps, warmup, threads):
+# CPU arm: the reference's own code (oracle/_ref) or the oracle port
+def cpu_oracle():
     from oracle import api
     if api.ref_available():
-        orc, kind = api.RefOracle(), "reference"
-    else:
-        orc, kind = api.PortOracle(), "port"
+        return api, api.RefOracle(), "reference"
+    return api, api.PortOracle(), "port"
+
+
+def cpu_arm(pairs, mats, steps, warmup, threads):
+    api, orc, kind = cpu_oracle()
     wi = api.directions(pairs, 0)
     wo = api.directions(pairs, 2)
     u = np.stack([api.uniforms(pairs, 4), api.uniforms(pairs, 5)], axis=1)
@@ -148,6 +154,85 @@ def cpu_arm(pairs, mats, steps, warmup, threads):
     return {"value": q / dt, "unit": UNIT, "cores": threads, "kind": kind,
             "sample": f"{pairs} pairs x {mats} materials x 6 queries per step, {steps} steps (same seeded generator)",
             "ms_per_step": 1e3 * dt / steps}
+
+
+def best_of(fn, reps=3):
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return best
+
+
+def cpu_leg_c1(threads):
+    """BASELINE.json configs[0]: GGX isotropic alpha = 0.1, brdf::eval over 1e6 random pairs, single thread (dj_brdf.h:1551-1555)."""
+    api, orc, kind = cpu_oracle()
+    n = 1_000_000
+    wi, wo = api.directions(n, 0), api.directions(n, 2)
+    P = orc.params_elliptic(0.1, 0.1, 0.0)
+    t1 = best_of(lambda: orc.eval(api.NDF_GGX, P, wi, wo, nthreads=1))
+    tT = best_of(lambda: orc.eval(api.NDF_GGX, P, wi, wo, nthreads=threads))
+    return {"value": n / tT, "unit": UNIT, "cores": threads, "kind": kind, "single_thread_value": n / t1,
+            "sample": "1e6 pairs, GGX isotropic alpha 0.1, eval, best of 3"}
+
+
+def cpu_leg_merl(table, threads):
+    api, orc, kind = cpu_oracle()
+    n1, nT = 500_000, 4_000_000
+    wi, wo = api.directions(nT, 0), api.directions(nT, 2)
+    if kind == "reference":
+        h = orc.merl_from_table(table)  # file -> object once, outside the timed calls (the reference's loader, dj_brdf.h:963-983)
+        t1 = best_of(lambda: orc.brdf_eval(h, None, wi[:n1], wo[:n1], 1), 2)
+        tT = best_of(lambda: orc.brdf_eval(h, None, wi, wo, threads), 2)
+        orc.destroy(h)
+    else:
+        t1 = best_of(lambda: orc.merl_eval(table, wi[:n1], wo[:n1], 1), 2)
+        tT = best_of(lambda: orc.merl_eval(table, wi, wo, threads), 2)
+    return {"value": nT / tT, "unit": "lookups/s", "cores": threads, "kind": kind, "single_thread_value": n1 / t1,
+            "sample": f"{nT} lookups on {threads} threads, {n1} on one (merl::eval, dj_brdf.h:987-1024), same table, best of 2"}
+
+
+def cpu_leg_lean():
+    api, orc, kind = cpu_oracle()
+    size = 2048
+    nm = workloads.synthetic_nmap(size, size)
+    t = best_of(lambda: orc.nmap2leanmap(nm, 1e-5, 0.0), 2)
+    return {"value": size * size / t, "unit": "pixels/s", "cores": 1, "kind": kind,
+            "sample": f"{size} x {size} map, nmap2leanmap (utils/nmap2leanmap.cpp:18-54) as the utility runs it: one thread, best of 2"}
+
+
+def cpu_leg_fit(specs, threads):
+    """tabular ctor + both fit_*_parameters per material (dj_brdf.h:2215-2236, 3133-3184), file I/O excluded: one material on one
+    thread, then `threads` materials on `threads` host threads (the reference has no threading of its own: disjoint objects)."""
+    api, orc, kind = cpu_oracle()
+    n = min(threads, len(specs))
+    tables = [workloads.fit_table(s) for s in specs[:n]]
+    if kind == "reference":
+        hs = [orc.merl_from_table(t) for t in tables]
+        alpha = np.zeros((n, 2), np.float32)
+
+        def one(k):
+            t = C.c_void_p(orc.lib.ref_tabular_create(hs[k], C.c_int(90), C.c_int(1)))
+            orc.lib.ref_tabular_get(t, None, None, None, None, None, C.c_void_p(alpha[k].ctypes.data))
+            orc.destroy(t)
+    else:
+        def one(k):
+            orc.fit_tabular(api.Source.merl(tables[k]), 90)
+
+    t0 = time.perf_counter()
+    one(0)
+    t1 = time.perf_counter() - t0
+    th = [threading.Thread(target=one, args=(k,)) for k in range(n)]
+    t0 = time.perf_counter()
+    [x.start() for x in th]
+    [x.join() for x in th]
+    tT = time.perf_counter() - t0
+    if kind == "reference":
+        [orc.destroy(h) for h in hs]
+    return {"value": n / tT, "unit": "fits/s", "cores": n, "kind": kind, "single_thread_value": 1.0 / t1,
+            "sample": f"{n} of the 128 tables, one material per host thread, 4 power iterations (the reference's fixed count)"}
 
 
 def run_reference(args, rank, world):
@@ -251,6 +336,13 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -274,49 +366,49 @@ def run_ours(args, rank, local_rank, world):
         for s in range(args.steps):
             print(f"[bench] rank {rank} step {s}: " + " ".join(f"{n}_{o}={ev[s][k][0].elapsed_time(ev[s][k][1]):.1f}ms"
                                                                  for k, (n, o) in enumerate(kernels)), file=sys.stderr)
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = max_over_ranks(ms_total) / args.steps
     q_step = 6.0 * pairs * M * world
     value = q_step / (ms_step * 1e-3)
 
-    # ---- end to end through the C-ABI with host buffers (pinned), in slabs of the same 1e8-pair workload ----
-    slab = min(pairs, args.e2e_slab)
-    n_slabs = (pairs + slab - 1) // slab
-    h_wi = torch.empty(slab, 3, dtype=torch.float32).pin_memory()
-    h_wo = torch.empty(slab, 3, dtype=torch.float32).pin_memory()
-    h_u = torch.empty(slab, 2, dtype=torch.float32).pin_memory()
-    h_out = torch.empty(M * slab * 3, dtype=torch.float32).pin_memory()
-    h_wi.copy_(wi[:slab]); h_wo.copy_(wo[:slab]); h_u.copy_(u[:slab])
-    torch.cuda.synchronize()
-    h_ins = {"eval": h_wi, "pdf": h_wi, "sample": h_u}
+    # ---- end to end through the C-ABI with host buffers (pinned): the whole 1e8-pair input lives in pinned host memory and is
+    # walked slab by slab (distinct data every call); each slab's results land in a pinned result buffer ----
+    e2e = None
+    if not args.no_e2e:
+        slab = min(pairs, args.e2e_slab)
+        n_slabs = (pairs + slab - 1) // slab
+        h_wi = torch.empty(pairs, 3, dtype=torch.float32).pin_memory()
+        h_wo = torch.empty(pairs, 3, dtype=torch.float32).pin_memory()
+        h_u = torch.empty(pairs, 2, dtype=torch.float32).pin_memory()
+        h_out = torch.empty(M * slab * 3, dtype=torch.float32).pin_memory()
+        h_wi.copy_(wi); h_wo.copy_(wo); h_u.copy_(u)
+        torch.cuda.synchronize()
+        h_ins = {"eval": h_wi, "pdf": h_wi, "sample": h_u}
+        width = {"eval": 3, "pdf": 3, "sample": 2}
 
-    def e2e_step():
-        for s in range(n_slabs):
-            n = min(slab, pairs - s * slab)
-            for ndf, op in kernels:
-                launch(ndf, op, h_ins[op].data_ptr(), h_wo.data_ptr(), n, h_out.data_ptr(), capi.MEM_HOST, None)
+        def e2e_step():
+            for s in range(n_slabs):
+                n = min(slab, pairs - s * slab)
+                for ndf, op in kernels:
+                    launch(ndf, op, h_ins[op].data_ptr() + 4 * width[op] * s * slab, h_wo.data_ptr() + 12 * s * slab, n,
+                           h_out.data_ptr(), capi.MEM_HOST, None)
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    if args.no_e2e:
-        e2e_steps, n_slabs = 1, 0
-    e2e_step() if args.warmup else None
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = max(time.perf_counter() - t0, 1e-9)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = q_step * e2e_steps / e2e_s
-    h2d = sum({"eval": 24, "pdf": 24, "sample": 20}[o] for _, o in kernels) * pairs
-    d2h = sum({"eval": 12, "pdf": 4, "sample": 12}[o] for _, o in kernels) * pairs * M
+        e2e_steps = max(1, args.e2e_steps)
+        e2e_step()  # warm-up: staging arenas, page faults of the pinned buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(max(time.perf_counter() - t0, 1e-9))
+        h2d = sum({"eval": 24, "pdf": 24, "sample": 20}[o] for _, o in kernels) * pairs
+        d2h = sum({"eval": 12, "pdf": 4, "sample": 12}[o] for _, o in kernels) * pairs * M
+        e2e = {"value": q_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "steps": e2e_steps, "slab_pairs": slab, "slabs_per_step": n_slabs,
+               "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / e2e_s / 1e9,
+               "note": "pinned host buffers through the C-ABI (DJB200_MEM_HOST): every slab of the 1e8 pairs is distinct host data; "
+                       "wall clock, max over ranks",
+               "cpus_bound_to_gpu_numa_node": numa}
+        del h_wi, h_wo, h_u, h_out
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -337,15 +429,23 @@ def run_ours(args, rank, local_rank, world):
                       "algo_gbs": algo_bytes(k.split("_")[1], pairs, M) / (v * 1e-3) / 1e9} for k, v in kern_ms.items()}
 
     extra = {}
-    if args.extras and rank == 0:
-        extra = run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak)
+    ctx = dict(args=args, djb=djb, capi=capi, lib=lib, torch=torch, dist=dist, dev=dev, wi=wi, wo=wo, out=out, stream=stream,
+               sptr=sptr, peak=peak, rank=rank, world=world, max_over_ranks=max_over_ranks, barrier=barrier)
     if args.extras:
-        extra.update(run_fit_extra(djb, torch, world, rank))
+        extra.update(run_config_legs(ctx))  # configs 0, 3, 4, 5 + the row-sharded anisotropic fit: every rank takes part
+        if rank == 0:
+            extra.update(run_widening_legs(ctx))  # section 8f kernels, one GPU
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(args.cpu_pairs, M, 1, 1, os.cpu_count() or 1)
+        threads = os.cpu_count() or 1
+        r = cpu_arm(args.cpu_pairs, M, 3, 1, threads)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if args.extras:
+            extra["c1"]["cpu_baseline"] = cpu_leg_c1(threads)
+            extra["merl"]["cpu_baseline"] = cpu_leg_merl(workloads.synthetic_merl_table(0.15), threads)
+            extra["lean"]["cpu_baseline"] = cpu_leg_lean()
+            extra["fit"]["cpu_baseline"] = cpu_leg_fit(workloads.fit_table_specs(), threads)
 
     if rank == 0:
         line = {
@@ -360,13 +460,11 @@ def run_ours(args, rank, local_rank, world):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab,
                          "note": "issue-bound, not HBM-bound: reproducing the reference's rounded floats costs ~190 (GGX eval) to "
-                                 "~1700 (Beckmann sample: 5 Newton steps of erfinv + exp per sample) warp instructions per "
-                                 "result; DRAM traffic equals the algorithmic bytes (profiles/dram_traffic.json)"},
+                                 "~860 (Beckmann sample: a Newton search of erfinv + exp per sample, glibc's own float algorithms in "
+                                 "double) warp instructions per result; DRAM traffic equals the algorithmic bytes "
+                                 "(profiles/dram_traffic.json)"},
             "kernels": per_kernel,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "steps": e2e_steps, "slab_pairs": slab,
-                    "note": "pinned host buffers through the C-ABI (DJB200_MEM_HOST), wall clock max over ranks",
-                    "cpus_bound_to_gpu_numa_node": numa},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "cpu_baseline": cpu,
@@ -377,14 +475,95 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak):
-    """Secondary lines of BASELINE.json (configs 3 and 5) on the same GPU: MERL lookups and the LEAN map."""
+def run_config_legs(c):
+    """The other BASELINE.json configurations, measured on EVERY rank (each GPU its own share; time = max over ranks)."""
+    args, djb, capi, lib, torch, dev = c["args"], c["djb"], c["capi"], c["lib"], c["torch"], c["dev"]
+    wi, wo, out, stream, sptr, peak, rank, world = c["wi"], c["wo"], c["out"], c["stream"], c["sptr"], c["peak"], c["rank"], c["world"]
+    max_over_ranks, barrier = c["max_over_ranks"], c["barrier"]
     res = {}
     n = wi.shape[0]
-    # config 3: synthetic 90x90x180 table, n Rusinkiewicz lookups
-    rng = np.random.default_rng(0)
-    table = rng.uniform(0.0, 3.0, 3 * 90 * 90 * 180)
-    m = djb.merl(table)
+    pv = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def timed(f, reps=3):
+        f()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            f()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return max_over_ranks(a.elapsed_time(b) / reps)
+
+    # config 0 (the reference's CPU-runnable case): GGX isotropic alpha 0.1, eval over 1e6 pairs, one material
+    n1 = min(n, 1_000_000)
+    d = djb.ggx()._desc()
+    P1 = djb.params.isotropic(0.1)
+    ms = timed(lambda: capi.check(lib.djb200_microfacet_eval(C.byref(d), C.c_void_p(P1.ctypes.data), C.c_int64(1),
+                                                             C.c_int(capi.PARAMS_BROADCAST), pv(wi), pv(wo), C.c_int64(n1), pv(out),
+                                                             C.c_int(capi.MEM_DEVICE), sptr)), 10)
+    res["c1"] = {"evals_per_s": n1 * world / (ms * 1e-3), "ms": ms, "pairs_per_gpu": n1,
+                 "note": "configs[0]: 36 MB of traffic: launch latency and L2 residency, not HBM, set this number",
+                 "roofline": hbm_roofline(36.0 * n1, ms, peak)}
+
+    # config 3: the section-8d table (analytic GGX 0.15 + diffuse, below-horizon cells -1), n Rusinkiewicz lookups per GPU
+    m = djb.merl(workloads.synthetic_merl_table(0.15))
+
+    def merl_call(a, b):
+        capi.check(lib.djb200_merl_eval(m._h, pv(a), pv(b), C.c_int64(n), pv(out), C.c_int(capi.MEM_DEVICE), sptr))
+
+    ms = timed(lambda: merl_call(wi, wo))
+    res["merl"] = {"lookups_per_s": n * world / (ms * 1e-3), "ms": ms, "lookups_per_gpu": n,
+                   "table": "section 8d: GGX(0.15) + diffuse at cell centres, below-horizon cells -1",
+                   "roofline": hbm_roofline(36.0 * n, ms, peak)}
+    # render-like lookups: one light, a smoothly varying view direction over a 10000-wide image (neighbouring lanes hit
+    # neighbouring cells), beside the uniformly random pairs above
+    k = torch.arange(n, device=dev, dtype=torch.float32)
+    x, y = (k % 10000.0) / 10000.0 - 0.5, torch.floor(k / 10000.0) / max(1.0, n / 10000.0) - 0.5
+    cwo = torch.stack([x, y, torch.full_like(x, 0.6)], 1)
+    cwo = (cwo / cwo.norm(dim=1, keepdim=True)).contiguous()
+    cwi = torch.tensor([0.3, 0.2, 0.9], device=dev) + 0.01 * torch.randn(n, 3, device=dev)
+    cwi = (cwi / cwi.norm(dim=1, keepdim=True)).contiguous()
+    del k, x, y
+    ms = timed(lambda: merl_call(cwi, cwo))
+    res["merl"]["coherent"] = {"lookups_per_s": n * world / (ms * 1e-3), "ms": ms, "roofline": hbm_roofline(36.0 * n, ms, peak)}
+    del cwi, cwo, m
+
+    # config 5: 8192^2 normal map -> two planar RGBA float maps.  Weak: every GPU converts a map of its own; strong: ONE map split
+    # in row bands over the GPUs (sharding.nmap2leanmap_row_band: per-texel map, no halo, no collective)
+    W = H = args.lean_size
+    nm = torch.randint(64, 192, (3, H, W), dtype=torch.uint8, device=dev)
+    nm[2] = torch.randint(128, 256, (H, W), dtype=torch.uint8, device=dev)
+    l1 = out[: 4 * H * W]
+    l2 = out[4 * H * W: 8 * H * W]
+
+    def lean_call(src, h):
+        capi.check(lib.djb200_nmap_to_leanmap(pv(src), C.c_int32(W), C.c_int32(h), C.c_float(1e-5), C.c_float(0.0), pv(l1), pv(l2),
+                                              C.c_int(capi.MEM_DEVICE), sptr))
+
+    ms = timed(lambda: lean_call(nm, H))
+    res["lean"] = {"pixels_per_s": W * H * world / (ms * 1e-3), "ms": ms, "size": [W, H],
+                   "roofline": hbm_roofline(35.0 * W * H, ms, peak)}
+    from dj_brdf_b200 import sharding
+    r0, r1 = sharding.shard_range(H, world, rank)
+    band = nm[:, r0:r1, :].contiguous()
+    ms_band = timed(lambda: lean_call(band, r1 - r0))
+    res["lean"]["one_map_row_bands"] = {"ms": ms_band, "pixels_per_s": W * H / (ms_band * 1e-3), "rows_per_gpu": r1 - r0,
+                                        "note": "one map split in row bands over the GPUs, no collective; time = slowest band"}
+    del nm, band
+
+    res.update(run_fit_leg(c))
+    res.update(run_aniso_fit_leg(c))
+    return res
+
+
+def run_widening_legs(c):
+    """SURVEY section 8f rows on one GPU, each with its own roofline."""
+    args, djb, capi, lib, torch, dev = c["args"], c["djb"], c["capi"], c["lib"], c["torch"], c["dev"]
+    wi, wo, out, stream, sptr, peak = c["wi"], c["wo"], c["out"], c["stream"], c["sptr"], c["peak"]
+    res = {}
+    n = wi.shape[0]
+    pv = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
     def timed(f, reps=3):
         f()
@@ -397,27 +576,8 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    ms = timed(lambda: capi.check(lib.djb200_merl_eval(m._h, C.c_void_p(wi.data_ptr()), C.c_void_p(wo.data_ptr()),
-                                                       C.c_int64(n), C.c_void_p(out.data_ptr()), C.c_int(capi.MEM_DEVICE), sptr)))
-    gbs = 36.0 * n / (ms * 1e-3) / 1e9
-    res["merl"] = {"lookups_per_s": n / (ms * 1e-3), "ms": ms, "lookups": n,
-                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                "traffic": None}}
-    # config 5: 8192^2 normal map -> two planar RGBA float maps
-    W = H = args.lean_size
-    nm = torch.randint(64, 192, (3, H, W), dtype=torch.uint8, device=dev)
-    nm[2] = torch.randint(128, 256, (H, W), dtype=torch.uint8, device=dev)
-    l1 = out[: 4 * H * W]
-    l2 = out[4 * H * W: 8 * H * W]
-    ms = timed(lambda: capi.check(lib.djb200_nmap_to_leanmap(C.c_void_p(nm.data_ptr()), C.c_int32(W), C.c_int32(H),
-                                                             C.c_float(1e-5), C.c_float(0.0), C.c_void_p(l1.data_ptr()),
-                                                             C.c_void_p(l2.data_ptr()), C.c_int(capi.MEM_DEVICE), sptr)))
-    gbs = 35.0 * W * H / (ms * 1e-3) / 1e9
-    res["lean"] = {"pixels_per_s": W * H / (ms * 1e-3), "ms": ms, "size": [W, H],
-                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                "traffic": None}}
-    # section 8f rows, measured the same way.  LEAN-filtered Beckmann shading (mitsuba/dj_beckmannconductor.cpp:283-319):
-    # fused params construction + evalp against the two-pass route (params blocks written to HBM, then a PER_PAIR query)
+    # LEAN-filtered Beckmann shading (mitsuba/dj_beckmannconductor.cpp:283-319): fused params construction + evalp against the
+    # two-pass route (params blocks written to HBM, then a PER_PAIR query)
     ns = min(n, 50_000_000)
     g = torch.Generator(device=dev).manual_seed(5)
     sl = torch.randn(ns, 2, device=dev, generator=g) * 0.25
@@ -435,7 +595,6 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
     d = bk._desc()
     P = out[: 12 * ns]
     res_rgb = out[12 * ns: 15 * ns]
-    pv = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     ms_f = timed(lambda: capi.check(lib.djb200_lean_shading_evalp(C.byref(d), C.byref(cfg), pv(al), pv(E), pv(wi), pv(wo),
                                                                   C.c_int64(ns), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
 
@@ -444,10 +603,9 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
         capi.check(lib.djb200_microfacet_evalp(C.byref(d), pv(P), C.c_int64(ns), C.c_int(capi.PARAMS_PER_PAIR), pv(wi), pv(wo),
                                                C.c_int64(ns), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr))
     ms_2 = timed(two_pass)
-    gbs = 68.0 * ns / (ms_f * 1e-3) / 1e9  # 24 B directions + 20 B moments + 12 B roughness in, 12 B out
+    # 24 B directions + 20 B moments + 12 B roughness in, 12 B out
     res["lean_shading"] = {"evals_per_s": ns / (ms_f * 1e-3), "ms": ms_f, "pairs": ns, "two_pass_ms": ms_2,
-                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                        "traffic": None}}
+                           "roofline": hbm_roofline(68.0 * ns, ms_f, peak)}
     del E, al
     # djb::sgd / djb::abc eval (36 B per pair; double exp / pow / acos per channel: issue bound)
     na = min(n, 20_000_000)
@@ -456,10 +614,7 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
         fn = getattr(lib, f"djb200_{kind}_eval")
         ms = timed(lambda: capi.check(fn(C.byref(mobj._data), pv(wi), pv(wo), C.c_int64(na), pv(res_rgb),
                                          C.c_int(capi.MEM_DEVICE), sptr)))
-        gbs = 36.0 * na / (ms * 1e-3) / 1e9
-        res[kind] = {"evals_per_s": na / (ms * 1e-3), "ms": ms, "pairs": na,
-                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                  "traffic": None}}
+        res[kind] = {"evals_per_s": na / (ms * 1e-3), "ms": ms, "pairs": na, "roofline": hbm_roofline(36.0 * na, ms, peak)}
     # djb::tabular / djb::tabular_anisotropic as BRDFs (fitted tables of an analytic GGX), djb::utia eval
     nt = min(n, 20_000_000)
     u_t = torch.rand(nt, 2, device=dev, generator=g).contiguous()
@@ -467,72 +622,89 @@ def run_extras(args, djb, capi, lib, torch, dev, wi, wo, out, stream, sptr, peak
     th, _keep = tab._first_arg()
     ms = timed(lambda: capi.check(lib.djb200_tabular_eval(th, None, C.c_int64(0), C.c_int(capi.PARAMS_BROADCAST), pv(wi), pv(wo),
                                                           C.c_int64(nt), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
-    res["tabular_eval"] = {"evals_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt,
-                           "roofline": {"bound": "hbm", "achieved": 36.0 * nt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                        "frac": 36.0 * nt / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+    res["tabular_eval"] = {"evals_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt, "roofline": hbm_roofline(36.0 * nt, ms, peak)}
     ta = djb.tabular_anisotropic(djb.ggx(), 90, 90)
     tah, _keep2 = ta._first_arg()
     ms = timed(lambda: capi.check(lib.djb200_tabular_sample(tah, None, C.c_int64(0), C.c_int(capi.PARAMS_BROADCAST), pv(u_t), pv(wo),
                                                             C.c_int64(nt), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
     res["tabular_anisotropic_sample"] = {"samples_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt,
-                                         "roofline": {"bound": "hbm", "achieved": 32.0 * nt / (ms * 1e-3) / 1e9, "peak": peak,
-                                                      "unit": "GB/s", "frac": 32.0 * nt / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+                                         "roofline": hbm_roofline(32.0 * nt, ms, peak)}
     ut = djb.utia(np.random.default_rng(3).uniform(0.0, 40.0, 3 * 6 * 48 * 6 * 48))
     ms = timed(lambda: capi.check(lib.djb200_utia_eval(ut._h, pv(wi), pv(wo), C.c_int64(nt), pv(res_rgb), C.c_int(capi.MEM_DEVICE), sptr)))
-    res["utia"] = {"evals_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt,
-                   "roofline": {"bound": "hbm", "achieved": 36.0 * nt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                "frac": 36.0 * nt / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+    res["utia"] = {"evals_per_s": nt / (ms * 1e-3), "ms": ms, "pairs": nt, "roofline": hbm_roofline(36.0 * nt, ms, peak)}
     return res
 
 
-def smooth_merl_table(seed):
-    """Synthetic MERL table (config 4): a radially decreasing lobe over the theta_h index plus a diffuse floor."""
-    rng = np.random.default_rng(seed)
-    width = float(rng.integers(4, 40))
-    k = np.arange(90, dtype=np.float64)
-    lobe = 1.0 / (1.0 + (k / width) ** 2) ** 2
-    td = 1.0 + (np.arange(90, dtype=np.float64) / 89.0) ** 4
-    base = lobe[:, None, None] * td[None, :, None] * np.ones((1, 1, 180))
-    return np.concatenate([(tint * base * (1.0 + 0.01 * rng.random(base.shape)) + 30.0 * (c + 1)).reshape(-1)
-                           for c, tint in enumerate((900.0, 700.0, 500.0))])
-
-
-def run_fit_extra(djb, torch, world, rank):
-    """BASELINE.json config 4: 128 synthetic MERL tables, 50 power iterations each, sharded by material across the ranks,
-    residual diagnostics gathered over NCCL.  Timed through the public API (fit_sharded.tabular_fit_batch_sharded)."""
-    import torch.distributed as dist
+def run_fit_leg(c):
+    """BASELINE.json config 4: 128 DISTINCT synthetic MERL tables (64 GGX + 64 Beckmann, alpha in [0.05, 0.6], known ground truth),
+    50 power iterations each, sharded by material across the ranks, residual diagnostics gathered over NCCL.  Timed through the
+    packed public API (fit_sharded.tabular_fit_batch_sharded(..., packed=True)); a 4-iteration pass (the reference's own count)
+    gives the recovered roughness."""
+    djb, torch, dist, world, rank = c["djb"], c["torch"], c["dist"], c["world"], c["rank"]
     from dj_brdf_b200 import fit_sharded as fs
     n_mat, iters = 128, 50
-    tables = {}
-
-    def make(k):  # 8 distinct tables uploaded per GPU, reused round-robin (a table is 23 MB on the device)
-        if k % 8 not in tables:
-            tables[k % 8] = djb.merl(smooth_merl_table(100 + k % 8))
-        return tables[k % 8]
-
-    for k in range(rank, n_mat, world):
-        make(k)
-    fs.tabular_fit_batch_sharded(make, n_mat, 90, True, iters)  # warm-up (workspaces, NCCL)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    specs = workloads.fit_table_specs(n_mat)
+    mine = fs.shard_items(n_mat, world, rank)
+    tables = [djb.merl(workloads.fit_table(specs[k])) for k in mine]  # this rank's materials, device resident (23 MB each)
+    srcs = djb.tabular.source_array(tables)
+    fs.tabular_fit_batch_sharded(None, n_mat, 90, True, iters, sources=srcs, packed=True)  # warm-up (workspaces, NCCL)
+    c["barrier"]()
     reps = 5
     t0 = time.perf_counter()
     for _ in range(reps):
-        fits, residuals = fs.tabular_fit_batch_sharded(make, n_mat, 90, True, iters)
-    torch.cuda.synchronize()
+        local, residuals = fs.tabular_fit_batch_sharded(None, n_mat, 90, True, iters, sources=srcs, packed=True)
+    c["barrier"]()
+    dt = c["max_over_ranks"]((time.perf_counter() - t0) / reps)
+    # ground truth: the 4-iteration fit (what the reference computes) of every table, gathered to rank 0
+    fit4, _ = fs.tabular_fit_batch_sharded(None, n_mat, 90, True, 4, sources=srcs, packed=True)
+    err = torch.zeros(n_mat, dtype=torch.float64, device="cuda")
+    for j, k in enumerate(mine):
+        kind, alpha_true, _f0 = specs[k]
+        err[k] = abs(float(fit4["alpha"][j, 1 if kind == "ggx" else 0]) - alpha_true)
     if world > 1:
-        dist.barrier()
-    dt = (time.perf_counter() - t0) / reps
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dist.all_reduce(err, op=dist.ReduceOp.SUM)
     if rank != 0:
         return {}
-    return {"fit": {"fits_per_s": n_mat / dt, "ms": dt * 1e3, "materials": n_mat, "iterations": iters, "res": 90,
-                    "alpha_ggx_0": float(fits[0].alpha_ggx), "max_final_residual": float(residuals[:, -1].max()),
-                    "note": "config 4: isotropic power-iteration fits sharded by material, residuals gathered; wall clock"}}
+    err = err.cpu().numpy()
+    is_ggx = np.array([s[0] == "ggx" for s in specs])
+    return {"fit": {"fits_per_s": n_mat / dt, "ms": dt * 1e3, "materials": n_mat, "distinct_tables": n_mat, "iterations": iters, "res": 90,
+                    "max_final_residual": float(residuals[:, -1].max()),
+                    "alpha_recovery_4_iterations": {
+                        "beckmann_tables_max_abs_err": float(err[~is_ggx].max()), "ggx_tables_max_abs_err": float(err[is_ggx].max()),
+                        "note": "|fitted alpha - alpha the table was generated with|: the reference's moment estimators "
+                                "(dj_brdf.h:3133-3184) are consistent for Beckmann lobes and biased for GGX's heavy tail; parity "
+                                "with the reference is what the tests check"},
+                    "note": "config 4: isotropic power-iteration fits sharded by material, residuals gathered over NCCL; wall "
+                            "clock of the packed public call, max over ranks"}}
+
+
+def run_aniso_fit_leg(c):
+    """One anisotropic 90 x 90 fit (dj_brdf.h:2238-2273) whose 8010 operator rows are split over the GPUs: the iteration loop and
+    the per-iteration NCCL all-gather of the iterate run inside libdjb200.so (djb200_aniso_fit_run)."""
+    djb, torch, world, rank = c["djb"], c["torch"], c["world"], c["rank"]
+    from dj_brdf_b200 import fit_sharded as fs
+    src = djb.utia(np.random.default_rng(12).uniform(-0.5, 60.0, 3 * 6 * 48 * 6 * 48))
+    fs.tabular_anisotropic_sharded(src, 90, 90, True, 4)  # warm-up (communicator, workspaces)
+    c["barrier"]()
+    best, tm_best = None, {}
+    for _ in range(3):
+        tm = {}
+        c["barrier"]()
+        t0 = time.perf_counter()
+        fit = fs.tabular_anisotropic_sharded(src, 90, 90, True, 4, timing=tm)
+        wall = time.perf_counter() - t0
+        if best is None or wall < best:
+            best, tm_best = wall, tm
+    wall = c["max_over_ranks"](best)
+    dev_ms = c["max_over_ranks"](tm_best.get("device_ms", 0.0))
+    ex_ms = c["max_over_ranks"](tm_best.get("exchange_ms", 0.0))
+    if rank != 0:
+        return {}
+    return {"aniso_fit": {"ms": wall * 1e3, "device_ms": dev_ms, "exchange_ms": ex_ms, "exchanges": 5 if world > 1 else 0,
+                          "grid": [90, 90], "rows": 8010, "iterations": 4, "n_gpus": world,
+                          "beckmann_alpha_x": float(fit.beckmann[0]),
+                          "note": "one material, operator rows sharded over the GPUs; per iteration an in-place ncclAllGather of the "
+                                  "iterate (64 KB) inside the library, one more for the projected-area rows; best of 3"}}
 
 
 def main():
@@ -545,11 +717,11 @@ def main():
     ap.add_argument("--materials", type=int, default=16)
     ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="pairs per step of the CPU arm / cpu_baseline")
     ap.add_argument("--e2e-slab", type=int, default=12_500_000, help="pairs per host-buffer call of the e2e leg")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--lean-size", type=int, default=8192)
     ap.add_argument("--no-extras", dest="extras", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only): e2e is null")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"bench.py: note: warmup {args.warmup} < 3 is below the timing rules", file=sys.stderr)

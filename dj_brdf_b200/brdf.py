@@ -660,30 +660,38 @@ class tabular(microfacet):
             pass
 
     @staticmethod
-    def _run(sources, res, shadow, iterations):
+    def source_array(sources):
+        """The C descriptor array of a list of source BRDFs; build it once when the same materials are fitted repeatedly."""
+        srcs = (capi.Source * len(sources))(*[_source_struct(s) for s in sources])
+        srcs._keep = list(sources)  # the handles must outlive the array
+        return srcs
+
+    @staticmethod
+    def fit_packed(sources, res=90, shadow=True, iterations=4):
+        """All fits of a batch in ONE packed result (djb200_fit_tabular_packed): no per-material objects, one device -> host
+        copy.  `sources`: a list of BRDFs or a `source_array`.  Returns a dict of arrays with a leading material axis:
+        p22, sigma, cdf, qf [n, res]; fresnel [n, res, 3]; alpha [n, 2] = (beckmann, ggx); residuals [n, iterations]."""
         if res <= 2:
             raise DjbError(1, "Invalid Resolution")  # DJB_ASSERT, dj_brdf.h:2218
-        n = len(sources)
-        srcs = (capi.Source * n)(*[_source_struct(s) for s in sources])
-        fits = (capi.TabularFit * n)()
-        arrays = []
-        for k in range(n):
-            a = dict(m_p22=np.zeros(res, np.float32), m_sigma=np.zeros(res, np.float32),
-                     m_cdf=np.zeros(res, np.float32), m_qf=np.zeros(res, np.float32),
-                     m_fresnel_points=np.zeros((res, 3), np.float32),
-                     residuals=np.zeros(max(1, iterations), np.float32))
-            arrays.append(a)
-            f = fits[k]
-            f.res = res
-            f.p22, f.sigma, f.cdf, f.qf = (a[x].ctypes.data for x in ("m_p22", "m_sigma", "m_cdf", "m_qf"))
-            f.fresnel = a["m_fresnel_points"].ctypes.data
-            f.residuals = a["residuals"].ctypes.data
-        check(capi.load().djb200_fit_tabular(srcs, C.c_int32(n), C.c_int32(res), C.c_int32(int(shadow)),
-                                             C.c_int32(iterations), fits, None))
-        for k in range(n):
-            arrays[k]["alpha_beckmann"] = float(fits[k].alpha_beckmann)
-            arrays[k]["alpha_ggx"] = float(fits[k].alpha_ggx)
-        return arrays
+        srcs = sources if isinstance(sources, C.Array) else tabular.source_array(list(sources))
+        n = len(srcs)
+        lib = capi.load()
+        out = np.empty(n * (7 * res + 2), np.float32)
+        resid = np.empty((n, max(1, iterations)), np.float32)
+        check(lib.djb200_fit_tabular_packed(srcs, C.c_int32(n), C.c_int32(res), C.c_int32(int(shadow)), C.c_int32(iterations),
+                                            C.c_void_p(out.ctypes.data), C.c_void_p(resid.ctypes.data), C.c_int(capi.MEM_HOST), None))
+        pk = n * res
+        return dict(p22=out[:pk].reshape(n, res), sigma=out[pk:2 * pk].reshape(n, res), cdf=out[2 * pk:3 * pk].reshape(n, res),
+                    qf=out[3 * pk:4 * pk].reshape(n, res), fresnel=out[4 * pk:7 * pk].reshape(n, res, 3),
+                    alpha=out[7 * pk:].reshape(n, 2), residuals=resid)
+
+    @staticmethod
+    def _run(sources, res, shadow, iterations):
+        r = tabular.fit_packed(sources, res, shadow, iterations)
+        return [dict(m_p22=r["p22"][k], m_sigma=r["sigma"][k], m_cdf=r["cdf"][k], m_qf=r["qf"][k],
+                     m_fresnel_points=r["fresnel"][k], residuals=r["residuals"][k],
+                     alpha_beckmann=float(r["alpha"][k, 0]), alpha_ggx=float(r["alpha"][k, 1]))
+                for k in range(len(r["alpha"]))]
 
     @staticmethod
     def fit_batch(sources, resolution=90, shadow=True, iterations=4):

@@ -1,6 +1,10 @@
 // capi_fit.cu -- C-ABI entry points of the power-iteration fits (include/djb200.h "fits"): argument
 // checks, source descriptors -> device, workspaces, result download.  Numerics: kernels_fit.cu.
+#include <dlfcn.h>
+#include <nccl.h> // types and prototypes only: the library is dlopen()ed at run time, libdjb200.so does not link NCCL
+
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "djb_fit.cuh"
@@ -115,22 +119,17 @@ djb200_status build_sources(const djb200_source *sources, int32_t n, std::vector
 
 extern "C" {
 
-djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources, int32_t res, int32_t shadow,
-                                 int32_t iterations, djb200_tabular_fit *results, void *stream)
+// Core of the batched isotropic fit: results stay packed on the device in `*out_dev` (per-thread scratch, valid until this thread's
+// next fit call): p22 | sigma | cdf | qf (n x res each) | fresnel (n x res x 3) | alpha (n x 2); residuals n x iterations.
+static djb200_status fit_tabular_device(const djb200_source *sources, int32_t n_sources, int32_t res, int32_t shadow,
+                                        int32_t iterations, cudaStream_t st, float **out_dev, float **resid_dev)
 {
 	if (n_sources < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative source count");
 	if (res <= 2) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid Resolution"); // DJB_ASSERT, dj_brdf.h:2218
 	if (fit_tabular_smem_bytes(res) > 227 * 1024)
 		return fail(DJB200_ERR_UNSUPPORTED, "resolution %d does not fit one CTA's shared memory (max ~1500)", res);
 	if (iterations < 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one power iteration");
-	if (n_sources == 0) return DJB200_OK;
-	if (!sources || !results) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
-	for (int32_t k = 0; k < n_sources; ++k) {
-		const djb200_tabular_fit &r = results[k];
-		if (r.res != res) return fail(DJB200_ERR_INVALID_ARGUMENT, "result %d: res field %d != %d", k, r.res, res);
-		if (!r.p22 || !r.sigma || !r.cdf || !r.qf || !r.fresnel)
-			return fail(DJB200_ERR_INVALID_ARGUMENT, "result %d: NULL output array", k);
-	}
+	if (!sources) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
 	djb200_status rs = require_device();
 	if (rs != DJB200_OK) return rs;
 
@@ -139,12 +138,10 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 	rs = build_sources(sources, n_sources, src, splines);
 	if (rs != DJB200_OK) return rs;
 
-	cudaStream_t st = (cudaStream_t)stream;
 	const size_t n = (size_t)n_sources, cnt = (size_t)res - 1;
 	Scratch &d_src = t_fit_src, &d_K = t_fit_K, &d_grid = t_fit_ws, &d_out = t_fit_out, &d_resid = t_fit_resid;
-	// outputs packed per kind: p22 | sigma | cdf | qf (n x res each) | fresnel (n x res x 3) | alpha (n x 2)
 	const size_t per_kind = n * (size_t)res;
-	const size_t out_floats = 4 * per_kind + 3 * per_kind + 2 * n;
+	const size_t out_floats = djb200_fit_tabular_packed_floats(n_sources, res);
 #define FCU(call)                                                \
 	do {                                                         \
 		cudaError_t e__ = (call);                                \
@@ -161,10 +158,53 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 	float *o_fres = o + 4 * per_kind, *o_alpha = o_fres + 3 * per_kind;
 	FCU(launch_fit_tabular(d_src.as<FitSourceDev>(), n_sources, res, shadow, iterations, d_K.as<double>(),
 	                       d_grid.as<float4>(), o_p22, o_sigma, o_cdf, o_qf, o_fres, o_alpha, d_resid.as<float>(), st));
-	std::vector<float> h(out_floats), hres(n * (size_t)iterations);
-	FCU(cudaMemcpyAsync(h.data(), o, sizeof(float) * out_floats, cudaMemcpyDeviceToHost, st));
-	FCU(cudaMemcpyAsync(hres.data(), d_resid.p, sizeof(float) * hres.size(), cudaMemcpyDeviceToHost, st));
-	FCU(cudaStreamSynchronize(st));
+	if (!splines.empty()) FCU(cudaStreamSynchronize(st)); // spline uploads are freed when this function returns
+	*out_dev = o;
+	*resid_dev = d_resid.as<float>();
+	return DJB200_OK;
+}
+
+int64_t djb200_fit_tabular_packed_floats(int32_t n_sources, int32_t res)
+{
+	return n_sources < 0 || res < 0 ? 0 : (int64_t)n_sources * ((int64_t)7 * res + 2);
+}
+
+djb200_status djb200_fit_tabular_packed(const djb200_source *sources, int32_t n_sources, int32_t res, int32_t shadow,
+                                        int32_t iterations, float *out, float *residuals, int mem, void *stream)
+{
+	if (n_sources == 0) return DJB200_OK;
+	if (!out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	cudaStream_t st = (cudaStream_t)stream;
+	float *o = nullptr, *r = nullptr;
+	djb200_status rs = fit_tabular_device(sources, n_sources, res, shadow, iterations, st, &o, &r);
+	if (rs != DJB200_OK) return rs;
+	const cudaMemcpyKind kind = mem == DJB200_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+	FCU(cudaMemcpyAsync(out, o, sizeof(float) * (size_t)djb200_fit_tabular_packed_floats(n_sources, res), kind, st));
+	if (residuals) FCU(cudaMemcpyAsync(residuals, r, sizeof(float) * (size_t)n_sources * (size_t)iterations, kind, st));
+	if (mem == DJB200_MEM_HOST) FCU(cudaStreamSynchronize(st)); // host results are ready on return; device results are stream ordered
+	return DJB200_OK;
+}
+
+djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources, int32_t res, int32_t shadow,
+                                 int32_t iterations, djb200_tabular_fit *results, void *stream)
+{
+	if (n_sources == 0) return DJB200_OK;
+	if (!sources || !results) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (n_sources < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative source count");
+	if (res <= 2) return fail(DJB200_ERR_INVALID_ARGUMENT, "Invalid Resolution"); // DJB_ASSERT, dj_brdf.h:2218
+	if (iterations < 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one power iteration");
+	for (int32_t k = 0; k < n_sources; ++k) {
+		const djb200_tabular_fit &r = results[k];
+		if (r.res != res) return fail(DJB200_ERR_INVALID_ARGUMENT, "result %d: res field %d != %d", k, r.res, res);
+		if (!r.p22 || !r.sigma || !r.cdf || !r.qf || !r.fresnel)
+			return fail(DJB200_ERR_INVALID_ARGUMENT, "result %d: NULL output array", k);
+	}
+	const size_t n = (size_t)n_sources, per_kind = n * (size_t)res;
+	std::vector<float> h((size_t)djb200_fit_tabular_packed_floats(n_sources, res)), hres(n * (size_t)iterations);
+	djb200_status rs = djb200_fit_tabular_packed(sources, n_sources, res, shadow, iterations, h.data(), hres.data(),
+	                                             DJB200_MEM_HOST, stream);
+	if (rs != DJB200_OK) return rs;
 #undef FCU
 	for (size_t k = 0; k < n; ++k) {
 		djb200_tabular_fit &r = results[k];
@@ -291,6 +331,168 @@ djb200_status djb200_aniso_fit_download(djb200_aniso_fit *f, djb200_tabular_anis
 	return DJB200_OK;
 }
 
+// ---- the exchange step of a fit whose rows span GPUs: NCCL all-gather over NVLink, inside the library ----------------
+// One process per GPU; the caller distributes a unique id (djb200_comm_unique_id on rank 0, broadcast by whatever the host
+// program uses -- torch.distributed in dj_brdf_b200/fit_sharded.py, MPI, a file) and every rank creates its communicator.
+} // extern "C"
+
+namespace {
+struct NcclApi {
+	void *handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+NcclApi &nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		// the soname: a process that already holds an NCCL (PyTorch's) gets that same library back
+		api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!api.handle) return;
+		api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+		api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+		api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+		api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+		api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+	});
+	return api;
+}
+djb200_status nccl_fail(ncclResult_t r, const char *what)
+{
+	return fail(DJB200_ERR_CUDA, "%s: NCCL error %d (%s)", what, (int)r, nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?");
+}
+} // namespace
+
+struct djb200_comm {
+	ncclComm_t comm;
+	int rank, world, device;
+};
+
+extern "C" {
+
+djb200_status djb200_comm_unique_id(void *out128)
+{
+	if (!out128) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	static_assert(sizeof(ncclUniqueId) == DJB200_COMM_ID_BYTES, "unique id size");
+	NcclApi &N = nccl_api();
+	if (!N.ok) return fail(DJB200_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+	ncclUniqueId id;
+	ncclResult_t r = N.GetUniqueId(&id);
+	if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+	memcpy(out128, &id, sizeof id);
+	return DJB200_OK;
+}
+
+djb200_status djb200_comm_create(const void *unique_id128, int32_t world, int32_t rank, djb200_comm **out)
+{
+	if (!unique_id128 || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (world < 1 || rank < 0 || rank >= world) return fail(DJB200_ERR_INVALID_ARGUMENT, "rank %d outside a world of %d", rank, world);
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	NcclApi &N = nccl_api();
+	if (!N.ok) return fail(DJB200_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+	ncclUniqueId id;
+	memcpy(&id, unique_id128, sizeof id);
+	djb200_comm *c = new djb200_comm;
+	c->rank = rank;
+	c->world = world;
+	cudaGetDevice(&c->device);
+	ncclResult_t r = N.CommInitRank(&c->comm, world, id, rank);
+	if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
+	*out = c;
+	return DJB200_OK;
+}
+
+djb200_status djb200_comm_destroy(djb200_comm *c)
+{
+	if (c) {
+		nccl_api().CommDestroy(c->comm);
+		delete c;
+	}
+	return DJB200_OK;
+}
+
+// matrix::eigenvector (dj_brdf.h:2467-2480) + the stages after it, with this rank computing rows [row0, row1) of every
+// matrix-vector product and of the projected-area table; the iterate (n doubles) and the table rows (n floats) are
+// all-gathered in place after each stage.  comm == NULL: one GPU, no exchange.  Every rank ends with the full result in `f`.
+djb200_status djb200_aniso_fit_run(djb200_aniso_fit *f, djb200_comm *comm, int32_t iterations, float *residuals_host,
+                                   float *timing_ms, void *stream)
+{
+	if (!f) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	if (iterations < 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one power iteration");
+	cudaStream_t st = (cudaStream_t)stream;
+	const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+	if (comm && comm->device != f->device) return fail(DJB200_ERR_INVALID_ARGUMENT, "communicator and fit live on different devices");
+	NcclApi &N = nccl_api();
+	const int64_t n = f->n, chunk = (n + world - 1) / world;
+	const int64_t row0 = rank * chunk < n ? rank * chunk : n, row1 = (rank + 1) * chunk < n ? (rank + 1) * chunk : n;
+	DevBuf va, vb, srows, resid;
+	cudaError_t e = va.alloc(sizeof(double) * world * chunk); // padded to whole chunks: the all-gather is in place
+	if (e == cudaSuccess) e = vb.alloc(sizeof(double) * world * chunk);
+	if (e == cudaSuccess) e = srows.alloc(sizeof(float) * world * chunk);
+	if (e == cudaSuccess) e = resid.alloc(sizeof(float) * iterations);
+	if (e != cudaSuccess) return cuda_fail(e, "aniso fit workspace");
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // total begin / end, one exchange begin / end
+	struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int k = 0; k < 4; ++k) if (e[k]) cudaEventDestroy(e[k]); } } guard{ev};
+	if (timing_ms) for (int k = 0; k < 4; ++k) ACU(cudaEventCreate(&ev[k]));
+	float exchange_ms = 0.0f;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xev; // one pair per exchange, read after the final synchronisation
+	auto exchange = [&](void *buf, size_t count, ncclDataType_t type, size_t elem) -> djb200_status {
+		if (world == 1) return DJB200_OK;
+		cudaEvent_t a = nullptr, b = nullptr;
+		if (timing_ms) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+		ncclResult_t r = N.AllGather((const char *)buf + (size_t)rank * count * elem, buf, count, type, comm->comm, st);
+		if (timing_ms) { cudaEventRecord(b, st); xev.push_back({a, b}); }
+		return r == ncclSuccess ? DJB200_OK : nccl_fail(r, "ncclAllGather");
+	};
+	if (timing_ms) ACU(cudaEventRecord(ev[0], st));
+	djb200_status rs = DJB200_OK;
+	const double *vin = nullptr;
+	double *bufs[2] = {va.as<double>(), vb.as<double>()};
+	for (int it = 0; it < iterations && rs == DJB200_OK; ++it) {
+		double *vout = bufs[it & 1];
+		rs = djb200_aniso_fit_matvec(f, vin, vout, row0, row1, stream);
+		if (rs == DJB200_OK) rs = exchange(vout, (size_t)chunk, ncclDouble, sizeof(double));
+		if (rs == DJB200_OK && residuals_host) {
+			e = aniso_launch_residual((int)n, vin ? vin : f->ones.as<double>(), vout, resid.as<float>() + it, st);
+			if (e != cudaSuccess) rs = cuda_fail(e, "residual kernel");
+		}
+		vin = vout;
+	}
+	if (rs == DJB200_OK) rs = djb200_aniso_fit_set_iterate(f, vin, stream);
+	if (rs == DJB200_OK) rs = djb200_aniso_fit_sigma(f, srows.as<float>(), row0, row1, stream);
+	if (rs == DJB200_OK) rs = exchange(srows.as<float>(), (size_t)chunk, ncclFloat, sizeof(float));
+	if (rs == DJB200_OK) rs = djb200_aniso_fit_finish(f, srows.as<float>(), stream);
+	if (rs == DJB200_OK && timing_ms) {
+		e = cudaEventRecord(ev[1], st);
+		if (e != cudaSuccess) rs = cuda_fail(e, "event record");
+	}
+	if (rs == DJB200_OK && residuals_host) {
+		e = cudaMemcpyAsync(residuals_host, resid.p, sizeof(float) * iterations, cudaMemcpyDeviceToHost, st);
+		if (e != cudaSuccess) rs = cuda_fail(e, "residual download");
+	}
+	e = cudaStreamSynchronize(st); // the workspaces above are freed on return
+	if (e != cudaSuccess && rs == DJB200_OK) rs = cuda_fail(e, "aniso fit");
+	for (auto &p : xev) {
+		float ms = 0.0f;
+		if (rs == DJB200_OK && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) exchange_ms += ms;
+		cudaEventDestroy(p.first);
+		cudaEventDestroy(p.second);
+	}
+	if (rs == DJB200_OK && timing_ms) {
+		timing_ms[0] = 0.0f;
+		cudaEventElapsedTime(&timing_ms[0], ev[0], ev[1]);
+		timing_ms[1] = exchange_ms;
+	}
+	return rs;
+}
+
 // the whole fit on one GPU: the stages above over the full row range, materials one after the other (each
 // stage is a grid-wide launch, so one material already fills the device)
 djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sources, int32_t n_sources, int32_t elev_res,
@@ -302,38 +504,12 @@ djb200_status djb200_fit_tabular_anisotropic(const djb200_source *sources, int32
 	if (iterations < 1) return fail(DJB200_ERR_INVALID_ARGUMENT, "need at least one power iteration");
 	if (n_sources == 0) return DJB200_OK;
 	if (!sources || !results) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
-	cudaStream_t st = (cudaStream_t)stream;
 	for (int32_t k = 0; k < n_sources; ++k) {
 		djb200_aniso_fit *f = nullptr;
 		djb200_status rs = djb200_aniso_fit_create(sources + k, elev_res, azim_res, shadow, stream, &f);
 		if (rs != DJB200_OK) return rs;
-		const int64_t n = f->n;
-		DevBuf va, vb, srows, resid;
-		cudaError_t e = va.alloc(sizeof(double) * n);
-		if (e == cudaSuccess) e = vb.alloc(sizeof(double) * n);
-		if (e == cudaSuccess) e = srows.alloc(sizeof(float) * n);
-		if (e == cudaSuccess) e = resid.alloc(sizeof(float) * iterations);
-		if (e != cudaSuccess) { delete f; return cuda_fail(e, "aniso fit workspace"); }
-		const double *vin = nullptr;
-		double *bufs[2] = {va.as<double>(), vb.as<double>()};
-		for (int it = 0; it < iterations && rs == DJB200_OK; ++it) {
-			double *vout = bufs[it & 1];
-			rs = djb200_aniso_fit_matvec(f, vin, vout, 0, n, stream);
-			if (rs == DJB200_OK && results[k].residuals) {
-				e = aniso_launch_residual((int)n, vin ? vin : f->ones.as<double>(), vout, resid.as<float>() + it, st);
-				if (e != cudaSuccess) rs = cuda_fail(e, "residual kernel");
-			}
-			vin = vout;
-		}
-		if (rs == DJB200_OK) rs = djb200_aniso_fit_set_iterate(f, vin, stream);
-		if (rs == DJB200_OK) rs = djb200_aniso_fit_sigma(f, srows.as<float>(), 0, n, stream);
-		if (rs == DJB200_OK) rs = djb200_aniso_fit_finish(f, srows.as<float>(), stream);
+		rs = djb200_aniso_fit_run(f, nullptr, iterations, results[k].residuals, nullptr, stream);
 		if (rs == DJB200_OK) rs = djb200_aniso_fit_download(f, results + k, stream);
-		if (rs == DJB200_OK && results[k].residuals) {
-			e = cudaMemcpy(results[k].residuals, resid.p, sizeof(float) * iterations, cudaMemcpyDeviceToHost);
-			if (e != cudaSuccess) rs = cuda_fail(e, "residual download");
-		}
-		cudaStreamSynchronize(st);
 		delete f;
 		if (rs != DJB200_OK) return rs;
 	}

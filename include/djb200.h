@@ -309,6 +309,16 @@ DJB200_API djb200_status djb200_fit_tabular(const djb200_source *sources, int32_
                                             int32_t shadow, int32_t iterations, djb200_tabular_fit *results,
                                             void *stream);
 
+/* The same batched fit with every result in ONE packed array (no per-material host objects, one device -> host copy; `mem` =
+ * DJB200_MEM_DEVICE leaves the results on the device, stream ordered): the form a pipeline that fits hundreds of materials per
+ * call wants (what examples/merl_params.cpp:55-60 does per file, batched).  Layout of `out`, n = n_sources:
+ *   p22[n][res] | sigma[n][res] | cdf[n][res] | qf[n][res] | fresnel[n][res][3] | alpha[n][2] = (beckmann, ggx)
+ * i.e. djb200_fit_tabular_packed_floats(n, res) = n (7 res + 2) floats; `residuals` (optional): [n][iterations]. */
+DJB200_API int64_t djb200_fit_tabular_packed_floats(int32_t n_sources, int32_t res);
+DJB200_API djb200_status djb200_fit_tabular_packed(const djb200_source *sources, int32_t n_sources, int32_t res,
+                                                   int32_t shadow, int32_t iterations, float *out, float *residuals,
+                                                   int mem, void *stream);
+
 /* ---- djb::tabular as a BRDF (dj_brdf.h:394-425) ---------------------------------------------- *
  * The fitted tables evaluated / sampled like any other microfacet BRDF: the queries of dj_brdf.h:1529-1765 with
  * tabular::p22_radial / sigma_std_radial / qf_radial (:2151-2176), the fitted Fresnel spline, and -- because
@@ -402,6 +412,24 @@ DJB200_API djb200_status djb200_aniso_fit_finish(djb200_aniso_fit *f, const floa
 /* copies the tables to host arrays of `result` (residuals are not touched) */
 DJB200_API djb200_status djb200_aniso_fit_download(djb200_aniso_fit *f, djb200_tabular_anisotropic_fit *result,
                                                    void *stream);
+
+/* ---- one fit spanning GPUs: the exchange step inside the library --------------------------- *
+ * One process per GPU.  Rank 0 calls djb200_comm_unique_id and hands the DJB200_COMM_ID_BYTES bytes to the other ranks by
+ * whatever the host program uses (torch.distributed, MPI, a file); every rank then creates its communicator on its current
+ * device.  NCCL (libnccl.so.2) is loaded at run time: a process without it gets DJB200_ERR_UNSUPPORTED here and nothing else
+ * in the library needs it. */
+#define DJB200_COMM_ID_BYTES 128
+typedef struct djb200_comm djb200_comm;
+DJB200_API djb200_status djb200_comm_unique_id(void *out_id /* DJB200_COMM_ID_BYTES */);
+DJB200_API djb200_status djb200_comm_create(const void *unique_id, int32_t world, int32_t rank, djb200_comm **out);
+DJB200_API djb200_status djb200_comm_destroy(djb200_comm *c);
+/* matrix::eigenvector(iterations) (dj_brdf.h:2467-2480) and every stage after it (:2238-2273) on a created fit, the n rows of the
+ * operator split in contiguous blocks over the ranks of `comm` (NULL: this GPU alone): per iteration each rank computes its rows
+ * and the iterate is all-gathered in place over NCCL (n doubles; 64 KB at 90 x 90), the projected-area rows likewise.  Every
+ * rank ends with the complete result (djb200_aniso_fit_download).  residuals (optional, host): `iterations` floats.
+ * timing_ms (optional, host): [0] = device time of the whole run, [1] = the part spent in the exchanges. */
+DJB200_API djb200_status djb200_aniso_fit_run(djb200_aniso_fit *f, djb200_comm *comm, int32_t iterations, float *residuals,
+                                              float *timing_ms, void *stream);
 
 #ifdef __cplusplus
 }

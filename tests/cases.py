@@ -74,42 +74,15 @@ def fresnels():
 
 def synthetic_merl_table(alpha=0.15, seed=7, kind="ggx"):
     """config 3: analytic microfacet lobe + diffuse sampled at MERL cell centres, stored unscaled (divided
-    by the MERL channel scales); below-horizon cells are -1 (exercises dj_brdf.h:1016-1021)."""
-    th = ((np.arange(90) + 0.5) / 90.0) ** 2 * (np.pi / 2)
-    td = (np.arange(90) + 0.5) / 90.0 * (np.pi / 2)
-    pd = (np.arange(180) + 0.5) / 180.0 * np.pi
-    TH, TD, PD = np.meshgrid(th, td, pd, indexing="ij")
-    # half / diff -> i, o (h in the xz-plane at elevation TH; d rotated by TH about y)
-    dx, dy, dz = np.sin(TD) * np.cos(PD), np.sin(TD) * np.sin(PD), np.cos(TD)
-    ix = dx * np.cos(TH) + dz * np.sin(TH)
-    iz = -dx * np.sin(TH) + dz * np.cos(TH)
-    hx, hz = np.sin(TH), np.cos(TH)
-    dot = ix * hx + iz * hz
-    ox, oz = 2 * dot * hx - ix, 2 * dot * hz - iz
-    below = (iz <= 0) | (oz <= 0)
-    t2 = np.tan(TH) ** 2
-    if kind == "ggx":
-        D = alpha ** 2 / (np.pi * np.cos(TH) ** 4 * (alpha ** 2 + t2) ** 2)
-    else:
-        D = np.exp(-t2 / alpha ** 2) / (np.pi * alpha ** 2 * np.cos(TH) ** 4)
-    F = 0.04 + 0.96 * (1 - np.clip(dot, 0, 1)) ** 5
-    spec = D * F / np.maximum(4 * np.abs(iz * oz), 1e-3)
-    rgb = []
-    scales = (1.00 / 1500.0, 1.15 / 1500.0, 1.66 / 1500.0)
-    for c, tint in enumerate((0.8, 0.6, 0.4)):
-        v = (tint * spec + 0.1 * (c + 1) / np.pi) / scales[c]
-        v = v.astype(np.float32).astype(np.float64)  # exactly representable in fp32 (SURVEY 8d)
-        v[below] = -1.0
-        rgb.append(v.reshape(-1))
-    return np.concatenate(rgb)
+    by the MERL channel scales); below-horizon cells are -1 (exercises dj_brdf.h:1016-1021).  The generator is the
+    benchmark's (dj_brdf_b200/workloads.py): tests and bench.py use the same tables."""
+    from dj_brdf_b200 import workloads
+    return workloads.synthetic_merl_table(alpha, kind)
 
 
 def synthetic_nmap(h, w, seed=12345):
-    rng = np.random.default_rng(seed)
-    r = rng.integers(64, 192, (h, w), dtype=np.uint8)
-    g = rng.integers(64, 192, (h, w), dtype=np.uint8)
-    b = rng.integers(128, 256, (h, w), dtype=np.uint8)
-    return np.stack([r, g, b])
+    from dj_brdf_b200 import workloads
+    return workloads.synthetic_nmap(h, w, seed)
 
 
 # ---- tables made only of platform-independent arithmetic (PCG64 doubles, + - * /), for the golden files ----

@@ -28,12 +28,20 @@ def main():
     ut = cases.random_utia_table(12)
     src = djb.utia(ut)
     er, ar = 90, 90
-    fs.tabular_anisotropic_sharded(src, 20, 20)  # warm-up (NCCL init)
+    fs.tabular_anisotropic_sharded(src, 20, 20)  # warm-up (the library's NCCL communicator)
+    fs.tabular_anisotropic_sharded(src, 20, 20, in_library=False)  # warm-up (torch's)
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
-    sharded = fs.tabular_anisotropic_sharded(src, er, ar, True, 4)
+    driven = fs.tabular_anisotropic_sharded(src, er, ar, True, 4, in_library=False)  # stage API driven from Python + torch collectives
+    torch.cuda.synchronize(); dist.barrier()
+    t_py = time.perf_counter() - t0
+    tm = {}
+    t0 = time.perf_counter()
+    sharded = fs.tabular_anisotropic_sharded(src, er, ar, True, 4, timing=tm)  # loop + ncclAllGather inside libdjb200.so
     torch.cuda.synchronize(); dist.barrier()
     t_sh = time.perf_counter() - t0
+    assert np.array_equal(driven.m_p22.view(np.uint32), sharded.m_p22.view(np.uint32))
+    assert np.array_equal(driven.m_sigma.view(np.uint32), sharded.m_sigma.view(np.uint32))
     t0 = time.perf_counter()
     single = djb.tabular_anisotropic(src, er, ar, True, 4)
     t_1 = time.perf_counter() - t0
@@ -43,7 +51,8 @@ def main():
     ok = torch.tensor([int(same)], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"aniso 90x90 row-sharded over {world} GPUs: {t_sh * 1e3:.1f} ms (single GPU {t_1 * 1e3:.1f} ms); "
+        print(f"aniso 90x90 row-sharded over {world} GPUs: in-library {t_sh * 1e3:.1f} ms (device {tm['device_ms']:.2f} ms, exchanges "
+              f"{tm['exchange_ms']:.3f} ms), Python-driven {t_py * 1e3:.1f} ms, single GPU {t_1 * 1e3:.1f} ms; "
               f"bit-identical on every rank: {bool(ok.item())}; beckmann {sharded.beckmann}", flush=True)
     assert ok.item() == 1
 

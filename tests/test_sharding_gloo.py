@@ -12,6 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from dj_brdf_b200 import fit_sharded as fs
+from dj_brdf_b200 import sharding
 
 
 def test_shard_rows_partition():
@@ -85,3 +86,50 @@ def test_row_sharded_power_iterations_gloo(n):
         assert np.array_equal(gv, v), f"rank {rank}: sharded iterate differs from the unsharded one"
         assert np.array_equal(srows, np.arange(n, dtype=np.float32))
         assert res.shape == (iters,) and np.isfinite(res).all() and res[-1] <= res[0] + 1e-6
+
+
+# ---- LEAN map row bands: the CUDA entry is replaced by the oracle port here ---------------------------
+def test_shard_range_partition():
+    for n in (1, 5, 64, 8192, 8191):
+        for world in (1, 2, 3, 8):
+            blocks = [sharding.shard_range(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _lean_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import api
+    from tests import cases
+    orc = api.PortOracle()
+    nm = cases.synthetic_nmap(37, 24)  # 37 rows: uneven bands
+    l1, l2 = sharding.nmap2leanmap_sharded(nm, 1e-5, 25.0, gather=True, kernel=orc.nmap2leanmap)
+    r0, r1, b1, b2 = sharding.nmap2leanmap_sharded(nm, 1e-5, 25.0, gather=False, kernel=orc.nmap2leanmap)
+    q.put((rank, l1.copy(), l2.copy(), r0, r1, np.asarray(b1).copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lean_map_row_bands_gloo():
+    from oracle import api
+    from tests import cases
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lean_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w1, w2 = api.PortOracle().nmap2leanmap(cases.synthetic_nmap(37, 24), 1e-5, 25.0)
+    for rank, l1, l2, r0, r1, b1 in got:
+        assert np.array_equal(l1.view(np.uint32), w1.view(np.uint32)) and np.array_equal(l2.view(np.uint32), w2.view(np.uint32))
+        assert (r0, r1) == sharding.shard_range(37, world, rank)
+        assert np.array_equal(b1.view(np.uint32), w1[:, r0:r1].view(np.uint32))
