@@ -37,6 +37,9 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed on stdout at NCCL_DEBUG=VERSION / INFO when the
+# first communicator is created) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 from dj_brdf_b200 import workloads  # noqa: E402  (host-side synthetic inputs, numpy only)
 

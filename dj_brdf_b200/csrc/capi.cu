@@ -381,7 +381,10 @@ static djb200_status microfacet_call(int op, const djb200_microfacet *mf, const 
 			explicit Scratch(cudaStream_t s) : st(s) {}
 			~Scratch() { if (p) cudaFreeAsync(p, st); }
 		} d_params(st), d_spline(st);
-		if (layout == DJB200_PARAMS_BROADCAST) {
+		if (layout == DJB200_PARAMS_BROADCAST && !tab && n_params <= MF_INLINE_PARAMS) {
+			L.params = nullptr; // inside the kernel arguments: no upload (a pageable H2D copy synchronises the stream first)
+			L.params_host = params;
+		} else if (layout == DJB200_PARAMS_BROADCAST) {
 			CU(upload_small(params, sizeof(djb200_params) * (size_t)n_params, &d_params.p, st));
 			L.params = d_params.p;
 		} else {

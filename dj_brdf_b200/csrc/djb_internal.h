@@ -38,6 +38,7 @@ djb200_status fail(djb200_status s, const char *fmt, ...);
 djb200_status cuda_fail(cudaError_t e, const char *what);
 djb200_status require_device();
 
+constexpr int MF_INLINE_PARAMS = 16; // params blocks (48 B each) a launch can carry in its kernel arguments
 constexpr int PARAMS_LEAN_SHADING = 2; // third params layout, only reachable through djb200_lean_shading_*
 enum MfOp { OP_EVAL = 0, OP_EVALP = 1, OP_PDF = 2, OP_SAMPLE = 3, OP_EVALP_IS = 4 };
 
@@ -48,6 +49,8 @@ struct MfLaunch {
 	const float *spline_pts; // device
 	int spline_n;
 	const void *params;      // device, djb200_params blocks
+	const void *params_host; // BROADCAST only: the same blocks in HOST memory; up to MF_INLINE_PARAMS of them travel inside the
+	                         // kernel arguments instead (no descriptor upload, no stream synchronisation): `params` may be NULL then
 	int64_t n_params;
 	int layout;              // djb200_params_layout, or PARAMS_LEAN_SHADING (internal)
 	// PARAMS_LEAN_SHADING: params are built per pair from the renderer's texture fetches (kernels_mf.cu)

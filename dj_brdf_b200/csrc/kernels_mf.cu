@@ -29,8 +29,9 @@ constexpr int MF_MAX_SMEM_SPLINE = 256; // points, 3 KB
 struct MfKernelArgs {
 	int shadow, fresnel_kind;
 	FresnelDev fr;
-	const Params *params;
+	const Params *params; // device blocks, or NULL: the blocks are in inline_params
 	int n_params;
+	Params inline_params[MF_INLINE_PARAMS];
 	const float *a, *b;
 	long long n, out_stride;
 	float *out0, *out1, *out2;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 
 	// stage the per-material parameters (48 B each) and the Fresnel spline once per CTA
 	{
-		const float *src = reinterpret_cast<const float *>(A.params);
+		const float *src = reinterpret_cast<const float *>(A.params ? A.params : A.inline_params);
 		float *dst = reinterpret_cast<float *>(s_params);
 		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
 	}
@@ -189,10 +190,13 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 #ifndef DJB200_BSAMPLE_MINB
 #define DJB200_BSAMPLE_MINB 5
 #endif
-constexpr int lean_min_blocks(int ndf, int op) { return (ndf == NDF_BECKMANN && op == OP_SAMPLE) ? DJB200_BSAMPLE_MINB : 1; }
+constexpr int lean_min_blocks(int ndf, int op, int psrc)
+{
+	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */) ? DJB200_BSAMPLE_MINB : 1;
+}
 
 template <int NDF, int FK, int OP, int PSRC>
-__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP)) mf_lean_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf_lean_kernel(MfKernelArgs A)
 {
 	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
 	constexpr bool PERPAIR = PSRC != PSRC_BROADCAST;
@@ -202,7 +206,8 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP)) mf_lean_
 	uint32_t glf_addr = (uint32_t)__cvta_generic_to_shared(s_glf_words);
 	asm volatile("" : "+r"(glf_addr)); // opaque: kept in a register instead of being re-derived (4 uniform instructions) at every lookup
 	if (!PERPAIR)
-		for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
+		for (int t = threadIdx.x; t < A.n_params; t += blockDim.x)
+			s_params[t] = extend_params(A.params ? A.params[t] : A.inline_params[t]);
 	if (NDF == NDF_BECKMANN && threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
 	if (NDF == NDF_BECKMANN && uses_u && threadIdx.x < GLF_TABLE_WORDS) s_glf_words[threadIdx.x] = g_glf_table[threadIdx.x];
 	__syncthreads();
@@ -276,7 +281,8 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 	__shared__ float2 s_exp2[64];
 	__shared__ PairS s_pair[MF_THREADS];
 	__shared__ uint2 s_q[WARPS][64], s_qs[WARPS][64];
-	for (int t = threadIdx.x; t < A.n_params; t += blockDim.x) s_params[t] = extend_params(A.params[t]);
+	for (int t = threadIdx.x; t < A.n_params; t += blockDim.x)
+		s_params[t] = extend_params(A.params ? A.params[t] : A.inline_params[t]);
 	if (threadIdx.x < 64) s_exp2[threadIdx.x] = g_exp2_64[threadIdx.x];
 	for (int t = threadIdx.x; t < WARPS * 64; t += blockDim.x) (&s_q[0][0])[t] = (&s_qs[0][0])[t] = make_uint2(0u, 0u);
 	__syncthreads();
@@ -497,7 +503,12 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 	const int per = (OP == OP_PDF) ? 1 : 3;
 	for (int64_t m0 = 0; m0 < L.n_params; m0 += MF_MAX_SMEM_PARAMS) {
 		int64_t mc = L.n_params - m0 < MF_MAX_SMEM_PARAMS ? L.n_params - m0 : MF_MAX_SMEM_PARAMS;
-		A.params = reinterpret_cast<const Params *>(L.params) + m0;
+		if (L.params) {
+			A.params = reinterpret_cast<const Params *>(L.params) + m0;
+		} else { // a small set, carried by value in the kernel arguments
+			A.params = nullptr;
+			memcpy(A.inline_params, L.params_host, sizeof(Params) * (size_t)mc);
+		}
 		A.n_params = (int)mc;
 		int64_t off = m0 * L.out_stride;
 		A.out0 = L.out0 ? L.out0 + off * per : nullptr;
