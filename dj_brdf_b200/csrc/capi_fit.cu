@@ -224,7 +224,7 @@ djb200_status djb200_fit_tabular(const djb200_source *sources, int32_t n_sources
 struct djb200_aniso_fit {
 	int er, ar, shadow, n, device;
 	FitSourceDev src;
-	DevBuf spline, rowpre, colpre, ones, p22, sigma, fresnel, terms, scale, pre_f, pre_d, params;
+	DevBuf spline, rowpre, colpre, colrcp, ones, p22, sigma, fresnel, terms, scale, pre_f, pre_d, params;
 };
 
 #define ACU(call)                                                \
@@ -253,6 +253,7 @@ djb200_status djb200_aniso_fit_create(const djb200_source *source, int32_t elev_
 	const size_t n = (size_t)f->n, tab = (size_t)elev_res * azim_res;
 	cudaError_t e = f->rowpre.alloc(sizeof(float4) * n);
 	if (e == cudaSuccess) e = f->colpre.alloc(sizeof(float4) * n);
+	if (e == cudaSuccess) e = f->colrcp.alloc(sizeof(float) * n);
 	if (e == cudaSuccess) e = f->ones.alloc(sizeof(double) * n);
 	if (e == cudaSuccess) e = f->p22.alloc(sizeof(float) * tab);
 	if (e == cudaSuccess) e = f->sigma.alloc(sizeof(float) * tab);
@@ -263,8 +264,8 @@ djb200_status djb200_aniso_fit_create(const djb200_source *source, int32_t elev_
 	if (e == cudaSuccess) e = f->pre_d.alloc(sizeof(double) * aniso_sigma_pre_doubles(azim_res));
 	if (e == cudaSuccess) e = f->params.alloc(sizeof(float) * 10);
 	if (e == cudaSuccess)
-		e = aniso_launch_pre(f->src, elev_res, azim_res, f->rowpre.as<float4>(), f->colpre.as<float4>(), f->ones.as<double>(),
-		                     (cudaStream_t)stream);
+		e = aniso_launch_pre(f->src, elev_res, azim_res, f->rowpre.as<float4>(), f->colpre.as<float4>(), f->colrcp.as<float>(),
+		                     f->ones.as<double>(), (cudaStream_t)stream);
 	if (e != cudaSuccess) { delete f; return cuda_fail(e, "aniso fit setup"); }
 	*out = f;
 	return DJB200_OK;
@@ -283,7 +284,8 @@ djb200_status djb200_aniso_fit_matvec(djb200_aniso_fit *f, const double *v_in, d
 {
 	if (!f || !v_out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
 	if (row0 < 0 || row1 > f->n || row0 > row1) return fail(DJB200_ERR_INVALID_ARGUMENT, "row range [%lld, %lld) outside [0, %d)", (long long)row0, (long long)row1, f->n);
-	ACU(aniso_launch_matvec(f->er, f->ar, f->rowpre.as<float4>(), f->colpre.as<float4>(), v_in ? v_in : f->ones.as<double>(),
+	ACU(aniso_launch_matvec(f->er, f->ar, f->rowpre.as<float4>(), f->colpre.as<float4>(), f->colrcp.as<float>(),
+	                        v_in ? v_in : f->ones.as<double>(),
 	                        v_out, (int)row0, (int)row1, (cudaStream_t)stream));
 	return DJB200_OK;
 }
@@ -351,7 +353,9 @@ NcclApi &nccl_api()
 	static NcclApi api;
 	static std::once_flag once;
 	std::call_once(once, [] {
-		// the soname: a process that already holds an NCCL (PyTorch's) gets that same library back
+		// the soname: a process that already holds an NCCL (PyTorch's) gets that same library back.  (The reverse order -- this
+		// load first, a PyTorch built against a newer NCCL imported afterwards -- would hand PyTorch the wrong library, so nothing
+		// in libdjb200.so loads NCCL until a communicator is asked for.)
 		api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
 		if (!api.handle) return;
 		api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
@@ -429,7 +433,6 @@ djb200_status djb200_aniso_fit_run(djb200_aniso_fit *f, djb200_comm *comm, int32
 	cudaStream_t st = (cudaStream_t)stream;
 	const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
 	if (comm && comm->device != f->device) return fail(DJB200_ERR_INVALID_ARGUMENT, "communicator and fit live on different devices");
-	NcclApi &N = nccl_api();
 	const int64_t n = f->n, chunk = (n + world - 1) / world;
 	const int64_t row0 = rank * chunk < n ? rank * chunk : n, row1 = (rank + 1) * chunk < n ? (rank + 1) * chunk : n;
 	DevBuf va, vb, srows, resid;
@@ -447,7 +450,8 @@ djb200_status djb200_aniso_fit_run(djb200_aniso_fit *f, djb200_comm *comm, int32
 		if (world == 1) return DJB200_OK;
 		cudaEvent_t a = nullptr, b = nullptr;
 		if (timing_ms) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
-		ncclResult_t r = N.AllGather((const char *)buf + (size_t)rank * count * elem, buf, count, type, comm->comm, st);
+		// NCCL is only touched when there is a communicator (it was loaded to create one): a single-GPU fit never loads it
+		ncclResult_t r = nccl_api().AllGather((const char *)buf + (size_t)rank * count * elem, buf, count, type, comm->comm, st);
 		if (timing_ms) { cudaEventRecord(b, st); xev.push_back({a, b}); }
 		return r == ncclSuccess ? DJB200_OK : nccl_fail(r, "ncclAllGather");
 	};

@@ -123,9 +123,9 @@ cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st);
 
 // anisotropic fit stages; [row0, row1) = this GPU's shard of the n = (er - 1) * ar rows
-cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *rowpre, float4 *colpre, double *v_ones,
+cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *rowpre, float4 *colpre, float *colrcp, double *v_ones,
                              cudaStream_t st);
-cudaError_t aniso_launch_matvec(int er, int ar, const float4 *rowpre, const float4 *colpre, const double *v_in,
+cudaError_t aniso_launch_matvec(int er, int ar, const float4 *rowpre, const float4 *colpre, const float *colrcp, const double *v_in,
                                 double *v_out, int row0, int row1, cudaStream_t st);
 cudaError_t aniso_launch_residual(int n, const double *v0, const double *v1, float *out, cudaStream_t st);
 cudaError_t aniso_launch_p22(int er, int ar, const double *v, float *p22, float *terms, float *scale_tmp, cudaStream_t st);

@@ -393,7 +393,8 @@ struct AnisoGeom {
 
 // row factors {zo, xo, yo, kji_tmp1} and column factors {tan_theta, slope1, slope2, cos_theta^2}: both live on
 // the same (theta_i1, phi_i2) grid, dj_brdf.h:2536-2561
-__global__ void __launch_bounds__(FIT_THREADS) aniso_pre_kernel(FitSourceDev src, AnisoGeom g, float4 *rowpre, float4 *colpre)
+__global__ void __launch_bounds__(FIT_THREADS) aniso_pre_kernel(FitSourceDev src, AnisoGeom g, float4 *rowpre, float4 *colpre,
+                                                                float *colrcp)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= g.n) return;
@@ -415,25 +416,66 @@ __global__ void __launch_bounds__(FIT_THREADS) aniso_pre_kernel(FitSourceDev src
 	float cos_theta = zo, tan_theta = (float)tan((double)theta);
 	float s1 = (float)((double)(-tan_theta) * cp), s2 = (float)((double)(-tan_theta) * sp);
 	colpre[r] = make_float4(tan_theta, s1, s2, cos_theta * cos_theta);
+	colrcp[r] = __frcp_rn(cos_theta * cos_theta); // correctly rounded 1 / den: the matvec divides by den with two FMAs
 }
 
-// out[r] = sum_k K(r, k) v[k] for r in [row0, row1), k ascending (matrix::transform, dj_brdf.h:2456-2465)
-__global__ void __launch_bounds__(64) aniso_matvec_kernel(AnisoGeom g, const float4 *__restrict__ rowpre,
-                                                          const float4 *__restrict__ colpre, const double *__restrict__ v,
-                                                          double *__restrict__ out, int row0, int row1)
+// out[r] = sum_k K(r, k) v[k] for r in [row0, row1), k ascending (matrix::transform, dj_brdf.h:2456-2465).
+// The double sum of a row is a chain of n dependent additions: it cannot be split without changing the result, so a row's
+// chain (8010 x the latency of a double add at 90 x 90) is the floor of this kernel whatever the number of rows -- which is also
+// why sharding the rows over GPUs cannot shorten it.  Everything else is made parallel around that chain.  A CTA owns 32 rows
+// (lane = row).  Seven PRODUCER warps form the products K(r, k) v[k] of a block of MV_CHUNK columns -- independent work: entry,
+// conversion, multiplication -- into shared memory; the ADDER warp walks the previous block and does nothing but the ordered
+// additions (one shared-memory load and one add per term).  Blocks are double-buffered, one barrier per block.  The division by
+// den = cos^2(theta_k) uses the column's correctly rounded reciprocal (quotient + one FMA correction = the IEEE quotient).
+constexpr int MV_WARPS = 8, MV_THREADS = 32 * MV_WARPS, MV_PER_WARP = 8, MV_CHUNK = (MV_WARPS - 1) * MV_PER_WARP;
+DJB_DEV float aniso_entry(const float4 rp, const float4 c, const float y)
 {
-	int r = row0 + blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= row1) return;
-	const float4 rp = rowpre[r];
+	const float m_dot_o = rp.x - rp.y * c.y - rp.z * c.z;
+	const float p = c.x * fmax_ref(0.0f, m_dot_o);
+	// p / c.w given y = RN(1 / c.w): quotient estimate + one FMA correction is the IEEE quotient when the residual is exact,
+	// i.e. for normal p; a tiny numerator is lifted by 2^64 first (exact) and the quotient lowered again -- branch-free
+	const bool tiny = p < 1e-30f;
+	const float ps = tiny ? p * 0x1p64f : p;
+	float q = ps * y;
+	q = __fmaf_rn(__fmaf_rn(-c.w, q, ps), y, q);
+	q = tiny ? q * 0x1p-64f : q;
+	return rp.w * q;
+}
+__global__ void __launch_bounds__(MV_THREADS) aniso_matvec_kernel(AnisoGeom g, const float4 *__restrict__ rowpre,
+                                                                  const float4 *__restrict__ colpre,
+                                                                  const float *__restrict__ colrcp, const double *__restrict__ v,
+                                                                  double *__restrict__ out, int row0, int row1)
+{
+	__shared__ double s_prod[2][MV_CHUNK][32]; // [buffer][column of the block][row of the CTA]: 28 KB
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int r = row0 + blockIdx.x * 32 + lane;
+	const bool live = r < row1;
+	const float4 rp = live ? rowpre[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+	const int nblocks = (g.n + MV_CHUNK - 1) / MV_CHUNK;
 	double acc = 0.0;
-#pragma unroll 4
-	for (int k = 0; k < g.n; ++k) {
-		const float4 c = __ldg(colpre + k);
-		float m_dot_o = rp.x - rp.y * c.y - rp.z * c.z;
-		float kji2 = c.x * fmax_ref(0.0f, m_dot_o) / c.w;
-		acc += (double)(rp.w * kji2) * __ldg(v + k);
+	for (int b = 0; b <= nblocks; ++b) {
+		if (warp > 0 && b < nblocks) { // producers: block b
+			const int k0 = b * MV_CHUNK + (warp - 1) * MV_PER_WARP;
+#pragma unroll
+			for (int j = 0; j < MV_PER_WARP; ++j) {
+				const int k = k0 + j;
+				double t = 0.0;
+				if (k < g.n) t = (double)aniso_entry(rp, __ldg(colpre + k), __ldg(colrcp + k)) * __ldg(v + k);
+				s_prod[b & 1][(warp - 1) * MV_PER_WARP + j][lane] = t;
+			}
+		} else if (warp == 0 && b > 0) { // adder: block b - 1, in column order
+			const int cnt = g.n - (b - 1) * MV_CHUNK < MV_CHUNK ? g.n - (b - 1) * MV_CHUNK : MV_CHUNK;
+			const double(*p)[32] = s_prod[(b - 1) & 1];
+			if (cnt == MV_CHUNK) {
+#pragma unroll
+				for (int j = 0; j < MV_CHUNK; ++j) acc += p[j][lane];
+			} else {
+				for (int j = 0; j < cnt; ++j) acc += p[j][lane];
+			}
+		}
+		__syncthreads();
 	}
-	out[r] = acc;
+	if (warp == 0 && live) out[r] = acc;
 }
 
 __global__ void fill_ones_kernel(double *v, int n)
@@ -493,13 +535,58 @@ __global__ void aniso_norm_terms_kernel(AnisoGeom g, const float *p22, float *te
 	terms[e] = weight * pdf;
 }
 
-// one thread adds the terms in the reference's order and derives the normalisation constant
+// The sum of p[0 .. n) in index order (a float sum is not associative: the reference's order is the result), computed by a whole
+// warp: the lanes fetch the next 1024 terms with coalesced 16-byte loads while the current 1024, staged in shared memory, are
+// added in order (every lane redundantly: one broadcast 16-byte load per four additions) -- the chain of dependent additions is
+// the only serial part left (one thread walking global memory paid a cache latency per term).  n must be a multiple of 4 and
+// p 16-byte aligned; `stage`: 1024 floats of shared memory owned by this warp.
+constexpr int OS_CHUNK = 1024;
+DJB_DEV float ordered_sum_warp(const float *__restrict__ p, int n, float *stage)
+{
+	const int lane = threadIdx.x & 31;
+	const float4 *p4 = reinterpret_cast<const float4 *>(p);
+	float4 *s4 = reinterpret_cast<float4 *>(stage);
+	const int n4 = n >> 2;
+	float4 nxt[OS_CHUNK / 128];
+	auto fetch = [&](int base4) {
+#pragma unroll
+		for (int q = 0; q < OS_CHUNK / 128; ++q) {
+			const int i = base4 + q * 32 + lane;
+			nxt[q] = i < n4 ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+	};
+	float acc = 0.0f;
+	fetch(0);
+	for (int base4 = 0; base4 < n4; base4 += OS_CHUNK / 4) {
+		__syncwarp();
+#pragma unroll
+		for (int q = 0; q < OS_CHUNK / 128; ++q) s4[q * 32 + lane] = nxt[q];
+		__syncwarp();
+		fetch(base4 + OS_CHUNK / 4); // in flight while this chunk is added
+		const int c4 = n4 - base4 < OS_CHUNK / 4 ? n4 - base4 : OS_CHUNK / 4;
+		if (c4 == OS_CHUNK / 4) {
+#pragma unroll 16
+			for (int j = 0; j < OS_CHUNK / 4; ++j) {
+				const float4 x = s4[j];
+				acc += x.x; acc += x.y; acc += x.z; acc += x.w;
+			}
+		} else {
+			for (int j = 0; j < c4; ++j) {
+				const float4 x = s4[j];
+				acc += x.x; acc += x.y; acc += x.z; acc += x.w;
+			}
+		}
+	}
+	return acc;
+}
+
+// one warp adds the terms in the reference's order and derives the normalisation constant
 __global__ void aniso_norm_sum_kernel(const float *terms, float *scale_out)
 {
-	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	__shared__ __align__(16) float s_stage[OS_CHUNK];
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
-	float k = 0.0f;
-	for (int e = 0; e < AN_NPHI * AN_NTHETA; ++e) k += terms[e];
+	float k = ordered_sum_warp(terms, AN_NPHI * AN_NTHETA, s_stage);
+	if (threadIdx.x != 0) return;
 	float dtheta = (float)(sqrt(0.5 * DJB_PI) / (double)(float)AN_NTHETA);
 	float dphi = (float)(2.0 * DJB_PI / (double)(float)AN_NPHI);
 	(void)sqrt_half_pi;
@@ -589,16 +676,55 @@ __global__ void aniso_sigma_table_kernel(AnisoGeom g, const float *sigma_rows, f
 	sigma[e] = sigma_rows[j * g.w + (i < g.w ? i : g.w - 1)];
 }
 
-// compute_fresnel, dj_brdf.h:2643-2701
-__global__ void __launch_bounds__(FIT_THREADS) aniso_fresnel_kernel(FitSourceDev src, AnisoGeom g, int shadow, const float *p22,
-                                                                    const float *sigma, float *fresnel)
+// compute_fresnel, dj_brdf.h:2643-2701.  The reference walks theta_h for every theta_d bin i; the (i, j) evaluations are independent,
+// only the running sums are ordered.  ws[i * (cnt + 2) + j] = (ratio rgb, 1) when trip j of bin i runs and passes the 1e-4 gate,
+// zeros otherwise.  Trip j runs iff theta_h of trip j - 1 is below the bin's bound (theta_h grows with j: the trips are a prefix).
+__global__ void __launch_bounds__(128) aniso_fresnel_ratio_kernel(FitSourceDev src, AnisoGeom g, int shadow, const float *p22,
+                                                                  const float *sigma, float4 *ws)
 {
 	TabAniso t; t.p22 = p22; t.sigma = sigma; t.w = g.er; t.h = g.ar;
-	const int cnt = g.er - 1;
+	const int cnt = g.er - 1, stride = cnt + 2;
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= cnt * stride) return;
+	const int i = e / stride, j = e - i * stride;
+	const Params sp = standard_params();
+	const float phi_d = (float)(DJB_PI * 0.5), phi_h = 0.0f;
+	const float theta_d = (float)((double)((float)i / (float)cnt) * DJB_PI * 0.5);
+	const double bound = DJB_PI * 0.5 - (double)theta_d;
+	float prev = 0.0f;
+	if (j > 0) {
+		const float t0 = (float)(j - 1) / (float)cnt;
+		prev = (float)((double)(t0 * t0) * DJB_PI * 0.5);
+	}
+	float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float t1 = (float)j / (float)cnt;
+	const float theta_h = (float)((double)(t1 * t1) * DJB_PI * 0.5);
+	if ((double)prev < bound && !((double)theta_h > DJB_PI * 0.5)) {
+		V3 dir_i, dir_o;
+		hd_to_io(spherical(theta_h, phi_h), spherical(theta_d, phi_d), dir_i, dir_o);
+		dir_i = mk(0.f, 0.f, 1.f); // "hack to reproduce my EGSR fits", dj_brdf.h:2669
+		const V3 fr1 = source_eval(src, dir_i, dir_o);
+		const float fr2 = tab_eval_ideal(t, sp, shadow != 0, dir_i, dir_o); // ideal Fresnel: r == g == b
+		if ((double)fr2 > 1e-4) r = make_float4(fr1.x / fr2, fr1.y / fr2, fr1.z / fr2, 1.0f);
+	}
+	ws[e] = r;
+}
+__global__ void __launch_bounds__(FIT_THREADS) aniso_fresnel_sum_kernel(AnisoGeom g, const float4 *ws, float *fresnel)
+{
+	const int cnt = g.er - 1, stride = cnt + 2;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-		V3 f = fresnel_bin(t, src, shadow != 0, i, cnt);
-		fresnel[3 * i] = f.x; fresnel[3 * i + 1] = f.y; fresnel[3 * i + 2] = f.z;
-		if (i == cnt - 1) { fresnel[3 * cnt] = f.x; fresnel[3 * cnt + 1] = f.y; fresnel[3 * cnt + 2] = f.z; }
+		V3 f = mk(0.f, 0.f, 0.f);
+		int c = 0;
+		for (int j = 0; j < stride; ++j) {
+			const float4 r = ws[i * stride + j];
+			if (r.w != 0.0f) { f.x += r.x; f.y += r.y; f.z += r.z; ++c; }
+		}
+		V3 o;
+		o.x = c == 0 ? 1.0f : fmin_ref(1.0f, f.x / (float)c);
+		o.y = c == 0 ? 1.0f : fmin_ref(1.0f, f.y / (float)c);
+		o.z = c == 0 ? 1.0f : fmin_ref(1.0f, f.z / (float)c);
+		fresnel[3 * i] = o.x; fresnel[3 * i + 1] = o.y; fresnel[3 * i + 2] = o.z;
+		if (i == cnt - 1) { fresnel[3 * cnt] = o.x; fresnel[3 * cnt + 1] = o.y; fresnel[3 * cnt + 2] = o.z; }
 	}
 }
 
@@ -633,19 +759,19 @@ __global__ void aniso_param_terms_kernel(AnisoGeom g, const float *p22, float *t
 	terms[6 * N + e] = tmp2 * fabsf(e2);
 }
 
-// seven lanes add their sequence in order; lane 0 then forms both parameter sets
-__global__ void aniso_param_sums_kernel(const float *terms, float *beckmann5, float *ggx5)
+// seven warps add one sequence each, in order; thread 0 then forms both parameter sets
+__global__ void __launch_bounds__(7 * 32) aniso_param_sums_kernel(const float *terms, float *beckmann5, float *ggx5)
 {
 	__shared__ float s[7];
+	__shared__ __align__(16) float s_stage[7][OS_CHUNK];
 	const int N = AP_NPHI * AP_NTHETA;
-	if (threadIdx.x < 7) {
-		const float *p = terms + (size_t)threadIdx.x * N;
-		float acc = 0.0f;
-		for (int e = 0; e < N; ++e) acc += p[e];
+	{
+		const int seq = threadIdx.x >> 5;
+		const float acc = ordered_sum_warp(terms + (size_t)seq * N, N, s_stage[seq]);
 		const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
 		float dtheta = (float)(sqrt_half_pi / (double)(float)AP_NTHETA);
 		float dphi = (float)(2.0 * DJB_PI / (double)(float)AP_NPHI);
-		s[threadIdx.x] = (float)((double)acc * (2.0 * (double)dtheta * (double)dphi));
+		if ((threadIdx.x & 31) == 0) s[seq] = (float)((double)acc * (2.0 * (double)dtheta * (double)dphi));
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -664,10 +790,11 @@ __global__ void aniso_param_sums_kernel(const float *terms, float *beckmann5, fl
 static inline void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
-cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *rowpre, float4 *colpre, double *v_ones, cudaStream_t st)
+cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *rowpre, float4 *colpre, float *colrcp, double *v_ones,
+                             cudaStream_t st)
 {
 	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
-	aniso_pre_kernel<<<blocks_for(g.n, FIT_THREADS), FIT_THREADS, 0, st>>>(src, g, rowpre, colpre);
+	aniso_pre_kernel<<<blocks_for(g.n, FIT_THREADS), FIT_THREADS, 0, st>>>(src, g, rowpre, colpre, colrcp);
 	count_launch();
 	if (v_ones) {
 		fill_ones_kernel<<<blocks_for(g.n, 256), 256, 0, st>>>(v_ones, g.n);
@@ -676,12 +803,12 @@ cudaError_t aniso_launch_pre(const FitSourceDev &src, int er, int ar, float4 *ro
 	return cudaGetLastError();
 }
 
-cudaError_t aniso_launch_matvec(int er, int ar, const float4 *rowpre, const float4 *colpre, const double *v_in, double *v_out,
-                                int row0, int row1, cudaStream_t st)
+cudaError_t aniso_launch_matvec(int er, int ar, const float4 *rowpre, const float4 *colpre, const float *colrcp, const double *v_in,
+                                double *v_out, int row0, int row1, cudaStream_t st)
 {
 	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
 	if (row1 <= row0) return cudaSuccess;
-	aniso_matvec_kernel<<<blocks_for(row1 - row0, 64), 64, 0, st>>>(g, rowpre, colpre, v_in, v_out, row0, row1);
+	aniso_matvec_kernel<<<blocks_for(row1 - row0, 32), MV_THREADS, 0, st>>>(g, rowpre, colpre, colrcp, v_in, v_out, row0, row1);
 	count_launch();
 	return cudaGetLastError();
 }
@@ -730,10 +857,14 @@ cudaError_t aniso_launch_finish(const FitSourceDev &src, int er, int ar, int sha
 {
 	AnisoGeom g = {er, ar, er - 1, ar, (er - 1) * ar};
 	aniso_sigma_table_kernel<<<blocks_for(er * ar, 256), 256, 0, st>>>(g, sigma_rows, sigma);
-	aniso_fresnel_kernel<<<blocks_for(er - 1, 32), 32, 0, st>>>(src, g, shadow, p22, sigma, fresnel);
+	// the Fresnel ratios borrow the head of `terms` (er x (er + 1) float4 <= 7 x 512 x 128 floats for er <= 330); the stream orders
+	// their use before aniso_param_terms_kernel overwrites it
+	float4 *fres_ws = reinterpret_cast<float4 *>(terms);
+	aniso_fresnel_ratio_kernel<<<blocks_for((er - 1) * (er + 1), 128), 128, 0, st>>>(src, g, shadow, p22, sigma, fres_ws);
+	aniso_fresnel_sum_kernel<<<blocks_for(er - 1, FIT_THREADS), FIT_THREADS, 0, st>>>(g, fres_ws, fresnel);
 	aniso_param_terms_kernel<<<blocks_for(AP_NPHI * AP_NTHETA, 256), 256, 0, st>>>(g, p22, terms);
-	aniso_param_sums_kernel<<<1, 32, 0, st>>>(terms, beckmann5, ggx5);
-	for (int k = 0; k < 4; ++k) count_launch();
+	aniso_param_sums_kernel<<<1, 7 * 32, 0, st>>>(terms, beckmann5, ggx5);
+	for (int k = 0; k < 5; ++k) count_launch();
 	return cudaGetLastError();
 }
 
