@@ -7,9 +7,9 @@ conversion.  The product is ``libdjb200.so`` (hand-written CUDA behind the C-ABI
 There is no CPU fallback.
 """
 from .capi import DjbError, device_count, kernel_launch_count, load  # noqa: F401
-from .brdf import (abc, beckmann, brdf, dmap2nmap, fresnel, ggx, leanmap_to_params, merl, merl_filter_stats, microfacet, nmap2leanmap,  # noqa: F401
+from .brdf import (abc, beckmann, brdf, dmap2nmap, fresnel, ggx, leanmap_half_mips, leanmap_to_params, merl, merl_filter_stats, microfacet, nmap2leanmap,  # noqa: F401
                    params, sgd, tabular, tabular_anisotropic, utia)
 
 __all__ = ["DjbError", "device_count", "kernel_launch_count", "load", "abc", "sgd", "dmap2nmap", "beckmann", "brdf", "fresnel", "ggx",
-           "leanmap_to_params", "merl", "merl_filter_stats", "microfacet", "nmap2leanmap", "params", "tabular", "tabular_anisotropic",
+           "leanmap_half_mips", "leanmap_to_params", "merl", "merl_filter_stats", "microfacet", "nmap2leanmap", "params", "tabular", "tabular_anisotropic",
            "utia"]

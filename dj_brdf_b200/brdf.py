@@ -573,6 +573,34 @@ def nmap2leanmap(nmap, base_roughness=1e-5, bias=0.0):
     return l1, l2
 
 
+def leanmap_half_mips(leanmap, levels=0):
+    """A LEAN map as the renderer consumes it: half-float RGBA with a mip pyramid (djb200_leanmap_to_half_mips).  Level 0 = what
+    the reference's save_exr writes (utils/CImg.h:44940-44947); level L = 2 x 2 box filter of level L - 1.
+    leanmap: planar float32 [4, h, w] -> list of float16 arrays [h_L, w_L, 4], one per level (levels <= 0: down to 1 x 1)."""
+    b = Buf(leanmap, np.float32)
+    shape = tuple(b.keep.shape)
+    if len(shape) != 3 or shape[0] != 4:
+        raise ValueError("leanmap must be planar [4, h, w]")
+    _, h, w = shape
+    lib = capi.load()
+    n_levels = int(lib.djb200_leanmap_mip_levels(C.c_int32(w), C.c_int32(h), C.c_int32(levels)))
+    texels = int(lib.djb200_leanmap_mip_texels(C.c_int32(w), C.c_int32(h), C.c_int32(levels)))
+    if capi._is_torch(b.keep):
+        import torch
+        out = torch.empty(texels * 4, dtype=torch.float16, device=b.keep.device)
+    else:
+        out = np.empty(texels * 4, np.float16)
+    optr = C.c_void_p(out.data_ptr() if capi._is_torch(out) else out.ctypes.data)
+    check(lib.djb200_leanmap_to_half_mips(b.ptr, C.c_int32(w), C.c_int32(h), C.c_int32(levels), optr, C.c_int(b.mem),
+                                          capi.current_stream_ptr(b.mem)))
+    res, off, lw, lh = [], 0, w, h
+    for _ in range(n_levels):
+        res.append(out[off * 4:(off + lw * lh) * 4].reshape(lh, lw, 4))
+        off += lw * lh
+        lw, lh = max(1, lw // 2), max(1, lh // 2)
+    return res
+
+
 def dmap2nmap(dmap, scale=0.01):
     """utils/dmap2nmap.cpp:13-44: uint8 displacement map [h, w] -> planar uint8 normal map [3, h, w]."""
     b = Buf(dmap, np.uint8)

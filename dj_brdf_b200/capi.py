@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "djb200_utia_create", "djb200_utia_load", "djb200_utia_destroy", "djb200_utia_eval",
     "djb200_sgd_preset", "djb200_abc_preset", "djb200_preset_count", "djb200_sgd_preset_name", "djb200_abc_preset_name",
     "djb200_sgd_eval", "djb200_abc_eval",
-    "djb200_nmap_to_leanmap", "djb200_dmap_to_nmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
+    "djb200_nmap_to_leanmap", "djb200_leanmap_to_half_mips", "djb200_leanmap_mip_levels", "djb200_leanmap_mip_texels", "djb200_dmap_to_nmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
     "djb200_lean_shading_params", "djb200_lean_shading_evalp", "djb200_lean_shading_pdf", "djb200_lean_shading_evalp_is",
     "djb200_fit_tabular", "djb200_fit_tabular_packed", "djb200_fit_tabular_packed_floats", "djb200_fit_tabular_anisotropic",
     "djb200_radial_query", "djb200_tabular_create", "djb200_tabular_anisotropic_create", "djb200_tabular_anisotropic_sampling_tables", "djb200_tabular_destroy", "djb200_tabular_eval", "djb200_tabular_evalp", "djb200_tabular_pdf",
@@ -110,6 +110,7 @@ def load():
     lib.djb200_kernel_launch_count.restype = C.c_uint64
     lib.djb200_aniso_fit_size.restype = C.c_int64
     lib.djb200_fit_tabular_packed_floats.restype = C.c_int64
+    lib.djb200_leanmap_mip_texels.restype = C.c_int64
     lib.djb200_sgd_preset_name.restype = C.c_char_p
     lib.djb200_abc_preset_name.restype = C.c_char_p
     _lib = lib

@@ -1040,6 +1040,55 @@ djb200_status djb200_utia_eval(const djb200_utia *u, const float *wi, const floa
 }
 
 // ---- LEAN ------------------------------------------------------------------------------------------
+int32_t djb200_leanmap_mip_levels(int32_t w, int32_t h, int32_t levels) { return w < 1 || h < 1 ? 0 : lean_mip_levels(w, h, levels); }
+
+int64_t djb200_leanmap_mip_texels(int32_t w, int32_t h, int32_t levels)
+{
+	if (w < 1 || h < 1) return 0;
+	int64_t total = 0;
+	int a = w, b = h;
+	for (int L = 0; L < lean_mip_levels(w, h, levels); ++L) {
+		total += (int64_t)a * b;
+		a = a > 1 ? a / 2 : 1;
+		b = b > 1 ? b / 2 : 1;
+	}
+	return total;
+}
+
+djb200_status djb200_leanmap_to_half_mips(const float *leanmap, int32_t w, int32_t h, int32_t levels, uint16_t *out_rgba16f, int mem,
+                                          void *stream)
+{
+	if (w < 0 || h < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative image size");
+	if (mem != DJB200_MEM_HOST && mem != DJB200_MEM_DEVICE) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown memory space %d", mem);
+	const int64_t npix = (int64_t)w * h;
+	if (npix == 0) return DJB200_OK;
+	if (!leanmap || !out_rgba16f) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL image pointer");
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int64_t texels = djb200_leanmap_mip_texels(w, h, levels);
+	const size_t qa = (size_t)(w > 1 ? w / 2 : 1) * (h > 1 ? h / 2 : 1), qb = (size_t)(w > 3 ? w / 4 : 1) * (h > 3 ? h / 4 : 1);
+	float4 *scratch = nullptr;
+	float *d_in = nullptr;
+	uint16_t *d_out = nullptr;
+	cudaError_t e = cudaMallocAsync((void **)&scratch, sizeof(float4) * (qa + qb), st);
+	if (e == cudaSuccess && mem == DJB200_MEM_HOST) {
+		e = cudaMallocAsync((void **)&d_in, sizeof(float) * 4 * (size_t)npix, st);
+		if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, sizeof(uint16_t) * 4 * (size_t)texels, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, leanmap, sizeof(float) * 4 * (size_t)npix, cudaMemcpyHostToDevice, st);
+	}
+	if (e == cudaSuccess)
+		e = launch_leanmap_half_mips(d_in ? d_in : leanmap, w, h, levels, d_out ? d_out : out_rgba16f, scratch, scratch + qa, st);
+	if (e == cudaSuccess && mem == DJB200_MEM_HOST)
+		e = cudaMemcpyAsync(out_rgba16f, d_out, sizeof(uint16_t) * 4 * (size_t)texels, cudaMemcpyDeviceToHost, st);
+	if (scratch) cudaFreeAsync(scratch, st);
+	if (d_in) cudaFreeAsync(d_in, st);
+	if (d_out) cudaFreeAsync(d_out, st);
+	if (e == cudaSuccess && mem == DJB200_MEM_HOST) e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) return cuda_fail(e, "leanmap half / mip conversion");
+	return DJB200_OK;
+}
+
 djb200_status djb200_nmap_to_leanmap(const uint8_t *nmap, int32_t w, int32_t h, float base_roughness, float bias,
                                      float *lean1, float *lean2, int mem, void *stream)
 {

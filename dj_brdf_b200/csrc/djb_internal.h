@@ -100,6 +100,9 @@ cudaError_t launch_utia_eval(const float *table, const float *wi, const float *w
                              cudaStream_t st);
 cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base_roughness, float bias,
                                    float *lean1, float *lean2, cudaStream_t st);
+int lean_mip_levels(int w, int h, int levels); // levels <= 0: the full chain down to 1 x 1
+cudaError_t launch_leanmap_half_mips(const float *planar, int w, int h, int levels, uint16_t *out, float4 *scratch_a, float4 *scratch_b,
+                                     cudaStream_t st);
 cudaError_t launch_dmap2nmap(const uint8_t *dmap, int w, int h, float scale, uint8_t *nmap, cudaStream_t st);
 cudaError_t launch_lrep_to_params(const float *E, int64_t n, void *out_params, cudaStream_t st);
 cudaError_t launch_params_to_lrep(const void *params, int64_t n, float *E, cudaStream_t st);

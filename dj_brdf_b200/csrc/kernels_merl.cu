@@ -23,6 +23,7 @@
 // result is the reference's, cell for cell.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "djb_device.cuh"
 #include "djb_internal.h"
@@ -38,12 +39,6 @@ constexpr float ETA_CROSS = 3.0e-6f;   // same, for the (d.x, d.y) direction (bo
 constexpr float POLE_GUARD = 0.99998f; // fast path only below this |z| (the reference's pole guard is 0.99999)
 
 DJB_DEV V3 ldv(const float *p, long long k) { return mk(p[3 * k], p[3 * k + 1], p[3 * k + 2]); }
-DJB_DEV void stv(float *p, long long k, V3 v)
-{
-	p[3 * k] = v.x;
-	p[3 * k + 1] = v.y;
-	p[3 * k + 2] = v.z;
-}
 
 // bare MUFU ops (no denormal fix-up code): only used where the result is a proposal or inside the error bounds
 DJB_DEV float rsq(float x)
@@ -182,6 +177,7 @@ __global__ void __launch_bounds__(TBM, MINB) merl_eval_quad_kernel(const float4 
 		const bool live = q < nquads;
 		int c[4] = {0, 0, 0, 0};
 		if (live) {
+			// (tried: ld.global.L1::no_allocate for these streams, and the largest L1 carve-out -- both slower, profiles/r02_merl_ceiling.md)
 			const float4 a0 = __ldcs(wi4 + 3 * q), a1 = __ldcs(wi4 + 3 * q + 1), a2 = __ldcs(wi4 + 3 * q + 2);
 			const float4 b0 = __ldcs(wo4 + 3 * q), b1 = __ldcs(wo4 + 3 * q + 1), b2 = __ldcs(wo4 + 3 * q + 2);
 			V3 d;
@@ -314,9 +310,31 @@ cudaError_t launch_merl_convert(const double *samples_dev, float4 *cells_dev, cu
 	return cudaGetLastError();
 }
 
+// Experiment switch (DJB200_MERL_PERSIST=1): pin the 23 MB table in L2 with an access-policy window on the launch stream, the
+// streams already being marked evict-first.  Measured (profiles/r02_merl_ceiling.md): 104 -> 73 G lookups/s -- the table already
+// hits in L2; what saturates is the SM -> L2 request interface, not L2 capacity, and the window only adds set-aside pressure.
+static void merl_persist_window(const float4 *cells, cudaStream_t st, bool on)
+{
+	static bool limit_set = false;
+	if (on && !limit_set) {
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)32 << 20);
+		limit_set = true;
+	}
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof attr);
+	attr.accessPolicyWindow.base_ptr = const_cast<float4 *>(cells);
+	attr.accessPolicyWindow.num_bytes = on ? sizeof(float4) * (size_t)MERL_CELLS_N : 0;
+	attr.accessPolicyWindow.hitRatio = 1.0f;
+	attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+
 cudaError_t launch_merl_eval(const float4 *cells, const float *wi, const float *wo, int64_t n, float *out, cudaStream_t st)
 {
 	if (n <= 0) return cudaSuccess;
+	static const bool persist = getenv("DJB200_MERL_PERSIST") != nullptr;
+	if (persist) merl_persist_window(cells, st, true);
 	// quads need 16-byte aligned arrays; the tail (n % 4) and unaligned callers take the one-lookup-per-thread kernel
 	const bool aligned = ((uintptr_t)wi % 16 == 0) && ((uintptr_t)wo % 16 == 0) && ((uintptr_t)out % 16 == 0);
 	const int64_t nq = aligned ? n / 4 : 0, done = nq * 4;

@@ -185,6 +185,84 @@ cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base
 	return cudaGetLastError();
 }
 
+// ---- LEAN maps -> half-float RGBA texture with a mip pyramid ---------------------------------------
+// What happens to the two maps after nmap2leanmap in the reference's asset chain: save_exr converts the four float planes to
+// interleaved half RGBA (utils/CImg.h:44940-44947, called at utils/nmap2leanmap.cpp:128-131: (half)(float), round to nearest
+// even), and the renderer's texture unit filters the moments LINEARLY over a mip pyramid -- which is the whole point of the LEAN
+// representation (mitsuba/dj_beckmannconductor.cpp:295-314 fetches the filtered texels).  Level 0 is that conversion; level L is
+// the 2 x 2 box filter of level L - 1 carried in float32 (((a + b) + (c + d)) * 0.25, edge texels repeated for odd sizes), each
+// level rounded to half once.  One kernel per level: HBM bound, 16 B in + 8 B out per level-0 texel.
+#include <cuda_fp16.h>
+__global__ void __launch_bounds__(TB) lean_half_level0_kernel(const float *__restrict__ planar, int64_t npix, uint2 *__restrict__ out)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += stride) {
+		const __half2 rg = __floats2half2_rn(planar[k], planar[npix + k]);
+		const __half2 ba = __floats2half2_rn(planar[2 * npix + k], planar[3 * npix + k]);
+		out[k] = make_uint2(*reinterpret_cast<const unsigned *>(&rg), *reinterpret_cast<const unsigned *>(&ba));
+	}
+}
+// src: float4 RGBA texels of the previous level (level 1 reads the planar level-0 image instead: src_planar != NULL)
+__global__ void __launch_bounds__(TB) lean_mip_level_kernel(const float4 *__restrict__ src, const float *__restrict__ src_planar, int sw,
+                                                            int sh, int dw, int dh, float4 *__restrict__ dst, uint2 *__restrict__ out)
+{
+	const int64_t n = (int64_t)dw * dh, splane = (int64_t)sw * sh;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		const int y = (int)(k / dw), x = (int)(k - (int64_t)y * dw);
+		const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+		const int64_t i00 = (int64_t)y0 * sw + x0, i10 = (int64_t)y0 * sw + x1, i01 = (int64_t)y1 * sw + x0, i11 = (int64_t)y1 * sw + x1;
+		float4 a, b, c, d;
+		if (src_planar) {
+			auto ld = [&](int64_t i) { return make_float4(src_planar[i], src_planar[splane + i], src_planar[2 * splane + i], src_planar[3 * splane + i]); };
+			a = ld(i00); b = ld(i10); c = ld(i01); d = ld(i11);
+		} else {
+			a = src[i00]; b = src[i10]; c = src[i01]; d = src[i11];
+		}
+		float4 r;
+		r.x = ((a.x + b.x) + (c.x + d.x)) * 0.25f;
+		r.y = ((a.y + b.y) + (c.y + d.y)) * 0.25f;
+		r.z = ((a.z + b.z) + (c.z + d.z)) * 0.25f;
+		r.w = ((a.w + b.w) + (c.w + d.w)) * 0.25f;
+		dst[k] = r;
+		const __half2 rg = __floats2half2_rn(r.x, r.y), ba = __floats2half2_rn(r.z, r.w);
+		out[k] = make_uint2(*reinterpret_cast<const unsigned *>(&rg), *reinterpret_cast<const unsigned *>(&ba));
+	}
+}
+
+int lean_mip_levels(int w, int h, int levels)
+{
+	int full = 1;
+	for (int a = w, b = h; a > 1 || b > 1; a = a > 1 ? a / 2 : 1, b = b > 1 ? b / 2 : 1) ++full;
+	return levels <= 0 || levels > full ? full : levels;
+}
+
+// out: all levels back to back, level L = [h_L][w_L] RGBA half texels; scratch: 2 float4 buffers of (w/2)(h/2) and (w/4)(h/4) texels
+cudaError_t launch_leanmap_half_mips(const float *planar, int w, int h, int levels, uint16_t *out, float4 *scratch_a, float4 *scratch_b,
+                                     cudaStream_t st)
+{
+	const int64_t npix = (int64_t)w * h;
+	if (npix <= 0) return cudaSuccess;
+	uint2 *o = reinterpret_cast<uint2 *>(out);
+	lean_half_level0_kernel<<<grid_for(npix), TB, 0, st>>>(planar, npix, o);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	o += npix;
+	int sw = w, sh = h;
+	const float4 *src = nullptr;
+	float4 *bufs[2] = {scratch_a, scratch_b};
+	for (int L = 1; L < lean_mip_levels(w, h, levels); ++L) {
+		const int dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
+		float4 *dst = bufs[(L - 1) & 1];
+		lean_mip_level_kernel<<<grid_for((int64_t)dw * dh), TB, 0, st>>>(src, L == 1 ? planar : nullptr, sw, sh, dw, dh, dst, o);
+		g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+		o += (int64_t)dw * dh;
+		src = dst;
+		sw = dw;
+		sh = dh;
+	}
+	return cudaGetLastError();
+}
+
 // ---- dmap2nmap, utils/dmap2nmap.cpp:13-44 --------------------------------------------------------------------------
 // Central differences of an 8-bit displacement map (CImg atXY(): clamped at the borders) -> unit normal packed as planar
 // 8-bit RGB.  1 B in (+ 4 neighbours, which the row / L2 locality makes free) and 3 B out per texel: HBM bound.

@@ -224,6 +224,17 @@ DJB200_API djb200_status djb200_abc_eval(const djb200_abc_data *material, const 
  * (bias = 25).  nmap: planar uint8 [3][h][w]; lean1/lean2: planar float [4][h][w] (CImg layout). */
 DJB200_API djb200_status djb200_nmap_to_leanmap(const uint8_t *nmap, int32_t w, int32_t h, float base_roughness,
                                                 float bias, float *lean1, float *lean2, int mem, void *stream);
+
+/* The two LEAN maps as the renderer consumes them: interleaved half-float RGBA with a mip pyramid.  Level 0 is what save_exr does
+ * with the planar float image (utils/CImg.h:44940-44947, called at utils/nmap2leanmap.cpp:128-131: (half)(float), round to nearest
+ * even); level L is the 2 x 2 box filter of level L - 1 -- linear filtering of the moments, which is what the renderer's texture
+ * unit does before mitsuba/dj_beckmannconductor.cpp:295-314 reads them -- carried in float32 (((a + b) + (c + d)) * 0.25, edge
+ * texels repeated at odd sizes) and rounded to half once per level.  leanmap: planar float32 [4][h][w]; out: all levels back to
+ * back, level L = [h_L][w_L][4] halves with (w_L, h_L) = max(1, floor(w / 2^L)), ...; levels <= 0: the whole chain to 1 x 1. */
+DJB200_API int32_t djb200_leanmap_mip_levels(int32_t w, int32_t h, int32_t levels);
+DJB200_API int64_t djb200_leanmap_mip_texels(int32_t w, int32_t h, int32_t levels);
+DJB200_API djb200_status djb200_leanmap_to_half_mips(const float *leanmap, int32_t w, int32_t h, int32_t levels,
+                                                     uint16_t *out_rgba16f, int mem, void *stream);
 /* dmap2nmap, utils/dmap2nmap.cpp:13-44: 8-bit displacement map [h][w] -> planar 8-bit normal map [3][h][w] (central
  * differences clamped at the borders, slopes scaled by (size / 2) * scale; the tool's default scale is 0.01, :69) */
 DJB200_API djb200_status djb200_dmap_to_nmap(const uint8_t *dmap, int32_t w, int32_t h, float scale, uint8_t *nmap,

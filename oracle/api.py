@@ -307,6 +307,28 @@ class PortOracle:
                                   c_f32p(l1.ctypes.data), c_f32p(l2.ctypes.data))
         return l1, l2
 
+    def leanmap_half_mips(self, leanmap, levels=0):
+        """The LEAN map as a half-float RGBA mip pyramid: level 0 = save_exr's (half)(float) of the four planes
+        (utils/CImg.h:44940-44947), level L = 2 x 2 box filter of level L - 1 in float32, ((a + b) + (c + d)) * 0.25 with edge
+        texels repeated, rounded to half (nearest even) once per level.  numpy restatement (IEEE float32 adds, no FMA)."""
+        lm = np.asarray(leanmap, np.float32)
+        cur = np.ascontiguousarray(np.moveaxis(lm, 0, -1))
+        full = 1
+        hh, ww = cur.shape[:2]
+        while hh > 1 or ww > 1:
+            hh, ww, full = max(1, hh // 2), max(1, ww // 2), full + 1
+        n = full if levels <= 0 or levels > full else levels
+        out = [cur.astype(np.float16)]
+        while len(out) < n:
+            sh, sw = cur.shape[:2]
+            dh, dw = max(1, sh // 2), max(1, sw // 2)
+            y0, y1 = np.minimum(2 * np.arange(dh), sh - 1), np.minimum(2 * np.arange(dh) + 1, sh - 1)
+            x0, x1 = np.minimum(2 * np.arange(dw), sw - 1), np.minimum(2 * np.arange(dw) + 1, sw - 1)
+            a, b, c, d = cur[y0][:, x0], cur[y0][:, x1], cur[y1][:, x0], cur[y1][:, x1]
+            cur = ((a + b) + (c + d)) * np.float32(0.25)
+            out.append(cur.astype(np.float16))
+        return out
+
     def erf(self, x):
         x = _f32(x)
         out = np.zeros(len(x), np.float32)

@@ -7,6 +7,7 @@
 * one MERL handle + one microfacet descriptor driven from four host threads at once (SURVEY 8b threading).
 """
 import threading
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -190,3 +191,63 @@ def test_four_host_threads_share_one_merl_handle_and_one_descriptor(djb, port):
     [x.start() for x in th]
     [x.join() for x in th]
     assert not errors, errors
+
+
+# ---- the fits at the sizes the reference uses, against outputs of the reference itself (tests/golden/fixture_golden.npz) ------------
+FIXTURE_GOLD = Path(__file__).resolve().parent / "golden" / "fixture_golden.npz"
+FIXTURES = Path(__file__).resolve().parent / "_fixtures"  # unpacked by tests/golden/make_fixture_golden.py; not committed (licensed data)
+
+
+def test_anisotropic_fit_90x90_against_the_reference(djb):
+    """djb::tabular_anisotropic(utia, 90, 90) -- the size mitsuba/dj_brdf.cpp:238 uses and bench.py times -- on the seeded synthetic
+    UTIA table: 8010 unknowns, 4 power iterations, the 8100-entry tables and both 5-parameter fits against the reference's own output."""
+    from tests.test_gpu_fit import check_aniso
+    g = np.load(FIXTURE_GOLD)
+    want = {k: g[f"utia12_90x90/{k}"] for k in ("p22", "sigma", "fresnel", "beckmann", "ggx")}
+    t = djb.tabular_anisotropic(djb.utia(cases.random_utia_table(12)), 90, 90)
+    check_aniso(t, want, "utia12 90x90 vs reference")
+
+
+def test_shipped_fixtures_on_the_device(djb):
+    """The two measured materials the reference ships (mitsuba/dj_matpreview.zip), loaded from their files by the device loaders
+    and fitted at the reference's sizes: examples/merl_params.cpp on blue-metallic-paint.binary, mitsuba/dj_brdf.cpp:238 on
+    m064_fabric099.bin.  Golden = the reference's outputs; the alphas are the ones SURVEY.md section 8c records."""
+    from tests.test_gpu_fit import check_aniso, check_fit
+    merl_path, utia_path = FIXTURES / "blue-metallic-paint.binary", FIXTURES / "m064_fabric099.bin"
+    if not (merl_path.exists() and utia_path.exists()):
+        pytest.skip("tests/_fixtures not unpacked (python tests/golden/make_fixture_golden.py where /root/reference exists)")
+    g = np.load(FIXTURE_GOLD)
+    t = djb.tabular(djb.merl(str(merl_path)), 90)
+    check_fit(t, {k: g[f"merl_fixture/{k}"] for k in ("p22", "sigma", "cdf", "qf", "fresnel", "alpha")}, "MERL fixture vs reference")
+    assert abs(t.alpha_beckmann - 0.417621881) <= 1e-4 and abs(t.alpha_ggx - 0.172961175) <= 1e-4
+    a = djb.tabular_anisotropic(djb.utia(str(utia_path)), 90, 90)
+    check_aniso(a, {k: g[f"utia_fixture/{k}"] for k in ("p22", "sigma", "fresnel", "beckmann", "ggx")}, "UTIA fixture vs reference")
+    assert np.abs(np.asarray(a.beckmann) - np.array([1.75892246, 1.35479379, -0.00675898697, 0.0259098969, 0.0165748745])).max() <= 1e-4
+    assert np.abs(np.asarray(a.ggx)[:2] - np.array([0.727996469, 0.568536818])).max() <= 1e-4
+
+
+# ---- SURVEY 8f N4: LEAN maps as the renderer consumes them (half RGBA + mip pyramid) -------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 96), (37, 53), (1, 7), (128, 128)])
+def test_leanmap_half_rgba_mip_pyramid_bit_exact(djb, port, shape):
+    import torch
+    h, w = shape
+    nm = cases.synthetic_nmap(h, w, seed=9)
+    for bias in (0.0, 25.0):
+        l1, l2 = port.nmap2leanmap(nm, 1e-5, bias)
+        for lm in (l1, l2):
+            want = port.leanmap_half_mips(lm)
+            got_h = djb.leanmap_half_mips(lm)
+            got_d = djb.leanmap_half_mips(torch.from_numpy(lm).cuda())
+            assert len(got_h) == len(want) == len(got_d)
+            assert want[-1].shape == (1, 1, 4)
+            for L, (a, b, c) in enumerate(zip(got_h, got_d, want)):
+                assert a.shape == c.shape, (L, a.shape, c.shape)
+                assert np.array_equal(a.view(np.uint16), c.view(np.uint16)), ("host", shape, bias, L)
+                assert np.array_equal(b.cpu().numpy().view(np.uint16), c.view(np.uint16)), ("device", shape, bias, L)
+    # a bounded chain, and the whole asset chain on the device: dmap -> nmap -> LEAN maps -> half mips
+    assert len(djb.leanmap_half_mips(l1, levels=3)) == min(3, len(want))
+    d = torch.from_numpy(np.random.default_rng(1).integers(96, 160, (64, 64), dtype=np.uint8)).cuda()
+    g1, g2 = djb.nmap2leanmap(djb.dmap2nmap(d, 0.01), 1e-5, 25.0)
+    w1, _ = port.nmap2leanmap(port.dmap2nmap(d.cpu().numpy(), 0.01), 1e-5, 25.0)
+    for a, c in zip(djb.leanmap_half_mips(g1), port.leanmap_half_mips(w1)):
+        assert np.array_equal(a.cpu().numpy().view(np.uint16), c.view(np.uint16))

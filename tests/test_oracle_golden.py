@@ -194,3 +194,12 @@ def test_microfacet_components(port, x, nname):
     args = dict(ndf=(h,), gaf=(h, wi, wo), g1=(h, wo), sigma=(wo,), p22=(xy,), vp22=(xy, wo), vndf=(h, wo), fresnel=(cs,))
     for what, a in args.items():
         assert bits_equal(port.component(what, ndf_id(nname), P, *a, fresnel=f), x[f"components/{nname}/{what}"]).all(), what
+
+
+def test_port_anisotropic_fit_at_90x90_matches_the_reference(port):
+    """The port at the size the reference's plugin uses (90 x 90, 8010 unknowns) against the reference's output
+    (tests/golden/fixture_golden.npz, generated by tests/golden/make_fixture_golden.py): bit for bit."""
+    g = np.load(GOLD / "fixture_golden.npz")
+    p = port.fit_tabular_anisotropic(api.Source.utia(cases.random_utia_table(12)), 90, 90, nthreads=8)
+    for k in ("p22", "sigma", "fresnel", "beckmann", "ggx"):
+        assert bits_equal(p[k], g[f"utia12_90x90/{k}"]).all(), k
