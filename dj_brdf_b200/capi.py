@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "NO_DEVICE", 3: "CUDA", 4: "O
 # every symbol include/djb200.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
     "djb200_last_error", "djb200_version", "djb200_device_count", "djb200_set_device",
-    "djb200_kernel_launch_count", "djb200_release_cache", "djb200_debug_force_generic", "djb200_debug_beckmann_compaction",
+    "djb200_kernel_launch_count", "djb200_release_cache", "djb200_set_precision", "djb200_get_precision", "djb200_debug_force_generic", "djb200_debug_beckmann_compaction",
     "djb200_params_standard", "djb200_params_isotropic", "djb200_params_elliptic", "djb200_params_pdfparams",
     "djb200_microfacet_eval", "djb200_microfacet_evalp", "djb200_microfacet_pdf", "djb200_microfacet_sample",
     "djb200_microfacet_evalp_is", "djb200_microfacet_component",
@@ -130,6 +130,20 @@ def device_count():
 
 def kernel_launch_count():
     return int(load().djb200_kernel_launch_count())
+
+
+PRECISION_REFERENCE_BITS, PRECISION_1E5 = 0, 1
+
+
+def set_precision(mode):
+    """Precision of microfacet eval / evalp / pdf (djb200_set_precision): "1e-5" (default: within 1e-5 relative of the reference's
+    floats, identical zero pattern, ~2x faster) or "bits" (the reference's rounded floats)."""
+    code = {"bits": PRECISION_REFERENCE_BITS, "1e-5": PRECISION_1E5, 0: 0, 1: 1}[mode]
+    check(load().djb200_set_precision(C.c_int(code)))
+
+
+def get_precision():
+    return "1e-5" if int(load().djb200_get_precision()) == PRECISION_1E5 else "bits"
 
 
 # ---- buffer plumbing: numpy arrays are host memory, torch CUDA tensors are device memory --------------

@@ -633,6 +633,16 @@ djb200_status djb200_debug_force_generic(int on)
 	return DJB200_OK;
 }
 
+djb200_status djb200_set_precision(int mode)
+{
+	if (mode != DJB200_PRECISION_REFERENCE_BITS && mode != DJB200_PRECISION_1E5)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown precision mode %d", mode);
+	g_fast_tier.store(mode == DJB200_PRECISION_1E5 ? 1 : 0);
+	return DJB200_OK;
+}
+
+int djb200_get_precision(void) { return g_fast_tier.load() ? DJB200_PRECISION_1E5 : DJB200_PRECISION_REFERENCE_BITS; }
+
 djb200_status djb200_debug_beckmann_compaction(int on)
 {
 	g_beck_compact.store(on ? 1 : 0);

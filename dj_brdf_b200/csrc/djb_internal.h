@@ -68,6 +68,7 @@ struct MfLaunch {
 
 extern std::atomic<uint64_t> g_kernel_launches;
 extern std::atomic<int> g_force_generic; // kernels_mf.cu: 1 = never take the lean FP32 kernels
+extern std::atomic<int> g_fast_tier;     // kernels_mf.cu: 1 = eval / evalp / pdf run the 1e-5 tier (default), 0 = the reference's bits
 extern std::atomic<int> g_beck_compact;  // kernels_mf.cu: 0 = Beckmann BROADCAST queries stay on the uncompacted lean kernel
 int sm_count();
 

@@ -585,6 +585,7 @@ struct PairX {
 	float den, rcp_den; // 4 o.z (eval / evalp) or 4 (i . h) (pdf)
 	float inv_iz;       // RN(1 / i.z) (eval)
 	float cd;           // sat(o . h)
+	float kh;           // o . h (pdf: the visible-normal density's numerator)
 	bool facing;        // h.z > 1e-4: the NDF is non-zero (dj_brdf.h:1561)
 	bool den_ok;        // den, c4 and their reciprocals are normal numbers: the lean divisions are exact
 };
@@ -605,7 +606,8 @@ DJB_DEV PairX make_pair(V3 i, V3 o)
 	c.den = 4.0f * (OP == OP_PDF ? dot(i, c.h) : o.z);
 	c.rcp_den = __frcp_rn(c.den);
 	c.inv_iz = OP == OP_EVAL ? __frcp_rn(i.z) : 0.0f;
-	c.cd = sat_ref(dot(o, c.h));
+	c.kh = dot(o, c.h);
+	c.cd = sat_ref(c.kh);
 	const float lo = 1e-28f, hi = 1e30f;
 	c.den_ok = fabsf(c.den) > lo && fabsf(c.den) < hi && c.c4 > lo;
 	return c;
@@ -785,6 +787,148 @@ DJB_DEV V3 lean_evalp_is(const float2 *T, const GlfCtx &GT, const ParamsX &m, co
 		return scale(div_by(G, g1o, rcp_lean(g1o)), fresnel_eval<FK>(f, cd));
 	}
 	return mk(0.f, 0.f, 0.f);
+}
+
+// =====================================================================================================================
+// The 1e-5 tier of eval / evalp / pdf (BASELINE.json north_star: "match the reference header's eval / pdf to <= 1e-5 relative").
+// The functions above reproduce the reference's rounded floats bit for bit; these spend the tolerance instead: MUFU reciprocal /
+// reciprocal square root / exp2 without correction steps, FMA contraction, no float-float arithmetic -- about 40 % of the
+// instructions.  What is NOT approximated, because the reference's own arithmetic is ill-conditioned there and only mirroring
+// it stays within 1e-5 (finding 3):
+//   * every gate that decides the zero pattern: h.z > 1e-4, dot(k, n) > 0, G > 0, D == 0 -- formed from the same floats by the
+//     same operations as in the exact tier (h, its slopes and the per-pair denominators are the exact tier's: they are computed
+//     once per pair, not per material);
+//   * the squared standard-space slope radius r2 that enters exp(-r2): a relative error e in r2 is an error r2 e in the
+//     exponential (r2 goes up to 100), so r2 is lean_ndf_r2, bit-identical to the reference's;
+//   * Beckmann results in the gradual-underflow tail (r2 > 78): handed to the exact tier;
+//   * s = sqrt(1 - float(c c)) of beckmann::sigma_std_radial keeps the reference's rounded product.
+// Measured against the exact tier on the device and against the reference on the CPU: tests/test_gpu_parity.py::test_fast_tier_*.
+DJB_DEV float mufu_ex2(float x)
+{
+	float y;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+// exp(x) for -87 < x <= 0: x log2(e) as head + tail (the rounding of the product alone would cost 3e-6 at x = -80), 2^head by
+// MUFU.EX2 (2 ulp), the tail applied linearly: relative error < 4e-7
+DJB_DEV float exp_neg_fast(float x)
+{
+	const float L2E_H = 0x1.715476p+0f, L2E_L = 0x1.4ae0c0p-26f, LN2 = 0x1.62e430p-1f;
+	const float th = x * L2E_H;
+	float tl = __fmaf_rn(x, L2E_H, -th);
+	tl = __fmaf_rn(x, L2E_L, tl);
+	const float r = mufu_ex2(th);
+	return __fmaf_rn(r, tl * LN2, r);
+}
+// beckmann::sigma_std_radial (dj_brdf.h:1871-1879) with djb::erf (A&S 7.1.26 as the reference evaluates it, :667-688)
+DJB_DEV float fast_beck_sigma_std(float c)
+{
+	const float cc = c * c;       // the reference's rounded product: 1 - cc below is exact for cc >= 1/2
+	const float v = 1.0f - cc;
+	if (!(v > 0.0f)) return 1.0f; // c == 1 (the reference's early-out); c a rounding above 1 cannot happen there
+	const float rs = mufu_rsq(v), s = v * rs, nu = c * rs;
+	const float x = -nu * nu;
+	if (x < -16.5f && c > 0.0f) return c; // same exact shortcut as the exact tier
+	const float e = exp_neg_fast(fmaxf(x, -87.0f));
+	const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
+	const float d = __fmaf_rn(0.3275911f, fabsf(nu), 1.0f);
+	float t = mufu_rcp(d);
+	t = __fmaf_rn(t, __fmaf_rn(-d, t, 1.0f), t);
+	float poly = __fmaf_rn(a5, t, a4);
+	poly = __fmaf_rn(poly, t, a3);
+	poly = __fmaf_rn(poly, t, a2);
+	poly = __fmaf_rn(poly, t, a1);
+	const float y = __fmaf_rn(-(poly * t), e, 1.0f);
+	const float erfv = nu < 0.0f ? -y : y;
+	return 0.5f * __fmaf_rn(c, 1.0f + erfv, s * (e * 0x1.20dd74p-1f));
+}
+// microfacet::sigma (dj_brdf.h:1619-1631) and, for the caller's G1, its reciprocal
+template <int NDF>
+DJB_DEV float fast_sigma(const Params &p, V3 k)
+{
+	const float kyay = k.y * p.ay;
+	const float a = __fmaf_rn(k.x, p.ax, kyay * p.rho);
+	const float b = kyay * p.srho;
+	const float c = __fmaf_rn(-k.y, p.ty, __fmaf_rn(-k.x, p.tx, k.z));
+	const float n2 = __fmaf_rn(a, a, __fmaf_rn(b, b, c * c));
+	const float rn = mufu_rsq(n2), nrm = n2 * rn;
+	if (NDF == NDF_GGX) return 0.5f * (nrm + c); // nrm (1 + c / nrm) / 2
+	return nrm * fast_beck_sigma_std(fminf(c * rn, 1.0f));
+}
+// microfacet::gaf (dj_brdf.h:1644-1665); rsg_o_out: 1 / sigma(o) for the pdf.
+// `ill` is set when the reference's own expression G1i G1o / (G1i + G1o - G1i G1o) is ill-conditioned: with an off-centre lobe
+// (tx_n, ty_n != 0) a G1 can exceed 1 and the denominator cancels, so only the reference's exact floats reproduce its result;
+// the caller then takes the exact tier for that query.  For centred lobes G1 <= 1 and the denominator is >= max(G1i, G1o): never.
+template <int NDF>
+DJB_DEV float fast_gaf(const Params &p, bool shadow, V3 i, V3 o, float &rsg_o_out, bool &ill)
+{
+	const V3 n = mk(p.nx, p.ny, p.nz);
+	const float rsg_o = mufu_rcp(fast_sigma<NDF>(p, o));
+	const float g1o = dot(o, n) > 0.0f ? o.z * rsg_o : 0.0f; // the gate: the reference's own dot product
+	rsg_o_out = rsg_o;
+	ill = false;
+	if (!shadow) return g1o;
+	const float g1i = dot(i, n) > 0.0f ? i.z * mufu_rcp(fast_sigma<NDF>(p, i)) : 0.0f;
+	const float t = g1i * g1o, d = g1i + g1o - t;
+	ill = d < 0.9f * fmaxf(g1i, g1o); // cancellation (needs a G1 > 1); for G1 <= 1 the denominator is >= both terms
+	return t > 0.0f ? t * mufu_rcp(d) : 0.0f;
+}
+// microfacet::ndf (dj_brdf.h:1559-1587) from the exact r2; Beckmann: r2 <= 78 (the caller sends the tail to the exact tier)
+template <int NDF>
+DJB_DEV float fast_ndf_from_r2(const ParamsX &m, const PairX &c, float r2)
+{
+	if (NDF == NDF_GGX) {
+		const float t = 1.0f + r2;
+		return mufu_rcp(((0x1.921fb6p+1f * t) * t) * (m.nrm * c.c4));
+	}
+	return ((exp_neg_fast(-r2) * 0x1.45f306p-2f) * m.rcp_nrm) * c.rcp_c4;
+}
+constexpr float FAST_BECK_R2_MAX = 78.0f;
+// the part of a query after the cheap D == 0 / tail tests (what the Beckmann kernel compacts across a warp)
+template <int NDF, int FK, int OP>
+DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c, float r2)
+{
+	float rsg_o;
+	bool ill;
+	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
+	if (ill) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	if (G > 0.0f) {
+		const float num = fast_ndf_from_r2<NDF>(m, c, r2) * G;
+		const float k = c.den_ok ? num * c.rcp_den : __fdiv_rn(num, c.den);
+		const V3 e = scale(k, fresnel_eval<FK>(f, c.cd));
+		return OP == OP_EVAL ? scale(c.inv_iz, e) : e;
+	}
+	return lean_zero<OP>(c);
+}
+template <int NDF>
+DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, const PairX &c, float r2)
+{
+	float rsg_o;
+	bool ill;
+	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
+	if (ill) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	if (G > 0.0f) {
+		const float v = c.kh > 0.0f ? (c.kh * fast_ndf_from_r2<NDF>(m, c, r2)) * rsg_o : 0.0f;
+		return c.den_ok ? v * c.rcp_den : __fdiv_rn(v, c.den);
+	}
+	return 0.0f;
+}
+// one (pair, material) query of the 1e-5 tier; Beckmann's underflow tail takes the exact functions
+template <int NDF, int FK, int OP>
+DJB_DEV V3 fast_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)
+{
+	if (!c.facing) return c.den > 0.0f ? lean_zero<OP>(c) : lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
+	const float r2 = lean_ndf_r2(m, c);
+	if (NDF == NDF_BECKMANN && !(r2 <= FAST_BECK_R2_MAX)) return lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
+	return fast_evalp_tail<NDF, FK, OP>(T, m, f, shadow, c, r2);
+}
+template <int NDF>
+DJB_DEV float fast_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c)
+{
+	if (!c.facing) return c.den > 0.0f ? 0.0f : lean_pdf<NDF>(T, m, shadow, c);
+	const float r2 = lean_ndf_r2(m, c);
+	if (NDF == NDF_BECKMANN && !(r2 <= FAST_BECK_R2_MAX)) return lean_pdf<NDF>(T, m, shadow, c);
+	return fast_pdf_tail<NDF>(T, m, shadow, c, r2);
 }
 
 } // namespace djb200

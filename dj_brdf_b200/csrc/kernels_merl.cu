@@ -39,6 +39,12 @@ constexpr float ETA_CROSS = 3.0e-6f;   // same, for the (d.x, d.y) direction (bo
 constexpr float POLE_GUARD = 0.99998f; // fast path only below this |z| (the reference's pole guard is 0.99999)
 
 DJB_DEV V3 ldv(const float *p, long long k) { return mk(p[3 * k], p[3 * k + 1], p[3 * k + 2]); }
+DJB_DEV void stv(float *p, long long k, V3 v)
+{
+	p[3 * k] = v.x;
+	p[3 * k + 1] = v.y;
+	p[3 * k + 2] = v.z;
+}
 
 // bare MUFU ops (no denormal fix-up code): only used where the result is a proposal or inside the error bounds
 DJB_DEV float rsq(float x)

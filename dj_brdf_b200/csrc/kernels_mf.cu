@@ -21,6 +21,14 @@ namespace djb200 {
 std::atomic<int> g_force_generic{getenv("DJB200_MF_GENERIC") != nullptr ? 1 : 0};
 // 0 (or DJB200_MF_NOCOMPACT=1): Beckmann BROADCAST eval / evalp / pdf stay on mf_lean_kernel (A/B tests)
 std::atomic<int> g_beck_compact{getenv("DJB200_MF_NOCOMPACT") != nullptr ? 0 : 1};
+// 1 (default): eval / evalp / pdf of the lean kernels run the 1e-5 tier (djb_lean.cuh, "The 1e-5 tier"); 0 (djb200_set_precision(
+// DJB200_PRECISION_REFERENCE_BITS), or DJB200_PRECISION=bits in the environment): every query reproduces the reference's floats
+static int initial_fast_tier()
+{
+	const char *e = getenv("DJB200_PRECISION");
+	return e && (!strcmp(e, "bits") || !strcmp(e, "0")) ? 0 : 1;
+}
+std::atomic<int> g_fast_tier{initial_fast_tier()};
 
 constexpr int MF_THREADS = 256;
 constexpr int MF_MAX_SMEM_PARAMS = 256; // 12 KB of shared memory
@@ -195,7 +203,7 @@ constexpr int lean_min_blocks(int ndf, int op, int psrc)
 	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */) ? DJB200_BSAMPLE_MINB : 1;
 }
 
-template <int NDF, int FK, int OP, int PSRC>
+template <int NDF, int FK, int OP, int PSRC, bool FAST>
 __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf_lean_kernel(MfKernelArgs A)
 {
 	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf
 		}
 		auto one = [&](const ParamsX &mx, long long slot) {
 			if (OP == OP_PDF) {
-				A.out0[slot] = lean_pdf<NDF>(s_exp2, mx, shadow, c);
+				A.out0[slot] = FAST ? fast_pdf<NDF>(s_exp2, mx, shadow, c) : lean_pdf<NDF>(s_exp2, mx, shadow, c);
 			} else if (OP == OP_SAMPLE) {
 				st3(A.out0, slot, lean_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o));
 			} else if (OP == OP_EVALP_IS) {
@@ -248,7 +256,8 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf
 				if (A.out1) st3(A.out1, slot, iv);
 				if (A.out2) A.out2[slot] = pdf;
 			} else {
-				st3(A.out0, slot, lean_evalp<NDF, FK, (OP == OP_EVALP ? OP_EVALP : OP_EVAL)>(s_exp2, mx, fr, shadow, c));
+				constexpr int EOP = OP == OP_EVALP ? OP_EVALP : OP_EVAL;
+				st3(A.out0, slot, FAST ? fast_evalp<NDF, FK, EOP>(s_exp2, mx, fr, shadow, c) : lean_evalp<NDF, FK, EOP>(s_exp2, mx, fr, shadow, c));
 			}
 		};
 		if (PERPAIR) {
@@ -267,12 +276,12 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf
 // r2; r2 > 103.5 <=> D == 0), lanes that pass push a work item (source lane, material, r2) into a per-warp queue in shared
 // memory, and whenever 32 items are waiting the whole warp evaluates them, one item per lane, reading the source lane's
 // pair from shared memory.  Results are the same floats: the same functions run on the same operands, on another lane.
-struct PairS { float4 a, b, c, d; }; // i.xyz o.x | o.yz h.xy | h.z den rcp_den inv_iz | cd den_ok c4 rcp_c4
+struct PairS { float4 a, b, c, d; }; // i.xyz o.x | o.yz h.xy | h.z den rcp_den inv_iz | o.h den_ok c4 rcp_c4
 
 #ifndef DJB200_COMPACT_MINB
 #define DJB200_COMPACT_MINB 1
 #endif
-template <int FK, int OP>
+template <int FK, int OP, bool FAST>
 __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compact_kernel(MfKernelArgs A)
 {
 	constexpr int NDF = NDF_BECKMANN;
@@ -302,11 +311,17 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 		c.o = mk(s.a.w, s.b.x, s.b.y);
 		c.h = mk(s.b.z, s.b.w, s.c.x);
 		c.den = s.c.y; c.rcp_den = s.c.z; c.inv_iz = s.c.w;
-		c.cd = s.d.x; c.den_ok = s.d.y != 0.0f; c.c4 = s.d.z; c.rcp_c4 = s.d.w;
+		c.kh = s.d.x; c.cd = sat_ref(c.kh); c.den_ok = s.d.y != 0.0f; c.c4 = s.d.z; c.rcp_c4 = s.d.w;
 		const ParamsX &mx = s_params[m];
-		// item.y: r2, or the NaN-free marker "not facing" (D == 0 with a non-positive denominator: the rare literal case)
-		const float Dn = (item.x & 0x80u) ? 0.0f : lean_ndf_from_r2<NDF>(s_exp2, mx, c, __uint_as_float(item.y));
 		const long long slot = (long long)m * A.out_stride + kb + src;
+		const float r2 = __uint_as_float(item.y);
+		if (FAST && !(item.x & 0x80u) && r2 <= FAST_BECK_R2_MAX) { // the 1e-5 tier; the underflow tail (the slow queue) stays exact
+			if (OP == OP_PDF) A.out0[slot] = fast_pdf_tail<NDF>(s_exp2, mx, shadow, c, r2);
+			else st3(A.out0, slot, fast_evalp_tail<NDF, FK, OP>(s_exp2, mx, fr, shadow, c, r2));
+			return;
+		}
+		// item.y: r2, or the NaN-free marker "not facing" (D == 0 with a non-positive denominator: the rare literal case)
+		const float Dn = (item.x & 0x80u) ? 0.0f : lean_ndf_from_r2<NDF>(s_exp2, mx, c, r2);
 		if (OP == OP_PDF) A.out0[slot] = lean_skip(Dn, c) ? 0.0f : lean_pdf_tail<NDF>(s_exp2, mx.p, shadow, c, Dn);
 		else st3(A.out0, slot, lean_skip(Dn, c) ? lean_zero<OP>(c) : lean_evalp_tail<NDF, FK, OP>(s_exp2, mx.p, fr, shadow, c, Dn));
 	};
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 		s.a = make_float4(c.i.x, c.i.y, c.i.z, c.o.x);
 		s.b = make_float4(c.o.y, c.o.z, c.h.x, c.h.y);
 		s.c = make_float4(c.h.z, c.den, c.rcp_den, c.inv_iz);
-		s.d = make_float4(c.cd, c.den_ok ? 1.0f : 0.0f, c.c4, c.rcp_c4);
+		s.d = make_float4(c.kh, c.den_ok ? 1.0f : 0.0f, c.c4, c.rcp_c4);
 		__syncwarp(); // the previous round's items have all been finished: the pair slots may be overwritten
 		pairs[lane] = s;
 		__syncwarp();
@@ -377,16 +392,16 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 	}
 }
 
-template <int FK, int OP>
+template <int FK, int OP, bool FAST>
 static void launch_beck_compact(const MfKernelArgs &A, long long want, cudaStream_t st)
 {
 	static int resident = 0;
 	if (!resident) {
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_beck_compact_kernel<FK, OP>, MF_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_beck_compact_kernel<FK, OP, FAST>, MF_THREADS, 0);
 		if (resident < 1) resident = 1;
 	}
 	const long long cap = (long long)sm_count() * resident;
-	mf_beck_compact_kernel<FK, OP><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
+	mf_beck_compact_kernel<FK, OP, FAST><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
 }
 
 // PER_PAIR layout: pair k under params block k (roughness from textures at every shading point).
@@ -422,22 +437,35 @@ __global__ void __launch_bounds__(MF_THREADS) lean_shading_params_kernel(MfKerne
 	}
 }
 
-template <int NDF, int FK, int OP, int PSRC>
+template <int NDF, int FK, int OP, int PSRC, bool FAST>
 static int lean_grid_cap()
 {
 	static int resident = 0;
 	if (!resident) {
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_lean_kernel<NDF, FK, OP, PSRC>, MF_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, mf_lean_kernel<NDF, FK, OP, PSRC, FAST>, MF_THREADS, 0);
 		if (resident < 1) resident = 1;
 	}
 	return sm_count() * resident;
 }
 
+template <int NDF, int FK, int OP, int PSRC, bool FAST>
+static void launch_lean_tier(const MfKernelArgs &A, long long want, cudaStream_t st)
+{
+	const long long cap = lean_grid_cap<NDF, FK, OP, PSRC, FAST>();
+	mf_lean_kernel<NDF, FK, OP, PSRC, FAST><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
+}
+// eval / evalp / pdf have the two tiers; sampling only the exact one
 template <int NDF, int FK, int OP, int PSRC>
 static void launch_lean(const MfKernelArgs &A, long long want, cudaStream_t st)
 {
-	const long long cap = lean_grid_cap<NDF, FK, OP, PSRC>();
-	mf_lean_kernel<NDF, FK, OP, PSRC><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
+	constexpr bool has_fast = OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF;
+	if constexpr (has_fast) {
+		if (g_fast_tier.load(std::memory_order_relaxed) != 0) {
+			launch_lean_tier<NDF, FK, OP, PSRC, true>(A, want, st);
+			return;
+		}
+	}
+	launch_lean_tier<NDF, FK, OP, PSRC, false>(A, want, st);
 }
 
 template <int NDF, int OP>
@@ -519,8 +547,11 @@ static cudaError_t launch_T(const MfLaunch &L, cudaStream_t st)
 		bool compacted = false;
 		if constexpr (can_compact) {
 			if (lean && A.n_params >= 2 && g_beck_compact.load(std::memory_order_relaxed) != 0) {
-				if (schlick) launch_beck_compact<FK_SCHLICK, OP>(A, want, st);
-				else launch_beck_compact<FK_IDEAL, OP>(A, want, st);
+				const bool fast = g_fast_tier.load(std::memory_order_relaxed) != 0;
+				if (schlick && fast) launch_beck_compact<FK_SCHLICK, OP, true>(A, want, st);
+				else if (schlick) launch_beck_compact<FK_SCHLICK, OP, false>(A, want, st);
+				else if (fast) launch_beck_compact<FK_IDEAL, OP, true>(A, want, st);
+				else launch_beck_compact<FK_IDEAL, OP, false>(A, want, st);
 				compacted = true;
 			}
 		}

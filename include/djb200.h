@@ -104,6 +104,18 @@ DJB200_API uint64_t djb200_kernel_launch_count(void);
  * calling thread's buffers (they are also freed when the thread exits) */
 DJB200_API djb200_status djb200_release_cache(void);
 
+/* Precision of microfacet eval / evalp / pdf (ideal and Schlick Fresnel terms; process-wide, read at every launch).
+ *   DJB200_PRECISION_1E5 (default): within 1e-5 relative of the reference header's float results, identical zero / NaN pattern
+ *     (the tolerance BASELINE.json's north_star states): MUFU reciprocals / exp2 and fused multiply-adds instead of correctly
+ *     rounded divisions, square roots and a float-float exponential -- about 2x the throughput.  Measured worst relative
+ *     difference against the reference's floats over 3.2e8 results per query: DESIGN.md section 3.
+ *   DJB200_PRECISION_REFERENCE_BITS: every query reproduces the reference's rounded floats (bit-identical on >= 99.99 % of
+ *     results; the remainder are double-rounding ties of a device libm call).  Also selected by DJB200_PRECISION=bits in the
+ *     environment.  sample / evalp_is, the table BRDFs, the fits and the maps always run at this level. */
+enum { DJB200_PRECISION_REFERENCE_BITS = 0, DJB200_PRECISION_1E5 = 1 };
+DJB200_API djb200_status djb200_set_precision(int mode);
+DJB200_API int djb200_get_precision(void);
+
 /* Debug switch for A/B tests: 1 = microfacet eval / evalp / pdf always run the mirrored-rounding kernel
  * (double sub-expressions literally as in the reference), 0 (default) = the lean FP32 kernels where they apply.
  * Both give the reference's rounded results; tests/test_gpu_parity.py compares them at full size. */

@@ -7,6 +7,10 @@ import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+# The parity tests hold eval / evalp / pdf to the reference's BITS: they run the exact tier (also inherited by the C++ test
+# programs and plugin binaries the tests start).  The default 1e-5 tier has its own tests (test_gpu_parity.py::test_fast_tier_*,
+# test_facade_cpp.py), which switch modes explicitly.
+os.environ.setdefault("DJB200_PRECISION", "bits")
 
 
 def pytest_configure(config):

@@ -83,13 +83,16 @@ def test_facade_fails_loudly_without_gpu(djb, bins):
 
 
 @pytest.mark.gpu
-def test_facade_matches_oracle(bins, port):
+@pytest.mark.parametrize("precision", ["bits", "1e-5"])
+def test_facade_matches_oracle(bins, port, precision):
+    """The reference's C++ interface on the GPU, in both precision modes of eval / pdf (DJB200_PRECISION; "1e-5" is the default)."""
     n = 20_000
     wi, wo, u = cases.pairs(n, stream=300)
     inp, outp = bins["dir"] / "in.bin", bins["dir"] / "out.bin"
     with open(inp, "wb") as f:
         f.write(np.int32(n).tobytes() + wi.tobytes() + wo.tobytes() + u.tobytes())
-    r = subprocess.run([str(bins["check"]), str(inp), str(outp)], capture_output=True, text=True)
+    r = subprocess.run([str(bins["check"]), str(inp), str(outp)], capture_output=True, text=True,
+                       env=dict(os.environ, DJB200_PRECISION=precision))
     assert r.returncode == 0, r.stderr
     raw = np.fromfile(outp, dtype=np.float32)
     pos = 0

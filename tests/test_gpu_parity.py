@@ -429,3 +429,108 @@ def test_beckmann_compaction_is_bit_identical(djb, port, fname):
             check_close(got_p[m], port.pdf(api.NDF_BECKMANN, mats[m], wi, wo, f), f"compact pdf m{m}", min_bit_rate=0.9999)
     finally:
         lib.djb200_debug_beckmann_compaction(C.c_int(1))
+
+
+# ---- the 1e-5 tier (the library's default; the tests above run the exact tier, see conftest.py) ---------------------------------
+@pytest.fixture
+def tier_1e5(djb):
+    djb.set_precision("1e-5")
+    yield djb
+    djb.set_precision("bits")
+
+
+def check_1e5(got, want, what):
+    """north_star: eval / pdf <= 1e-5 relative FP32, identical zero / NaN pattern.  Returns (worst relative error, bit-identical rate)."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert np.array_equal(got == 0, want == 0), f"{what}: zero pattern differs"
+    assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: NaN pattern differs"
+    assert np.array_equal(np.signbit(got[got == 0]), np.signbit(want[want == 0])), f"{what}: sign of zero differs"
+    e = rel_err(got, want)
+    worst = float(e.max()) if e.size else 0.0
+    assert worst <= REL_TOL, f"{what}: max rel err {worst:.3e} > {REL_TOL}"
+    return worst, float(bits_equal(got, want).mean())
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("pname", ["iso0.1", "iso0.5", "aniso", "aniso2", "offcentre", "standard"])
+def test_fast_tier_against_oracle(tier_1e5, port, ndf, pname):
+    """The default tier against the CPU oracle: 200 k pairs + the edge pairs, ideal and Schlick Fresnel, shadowing on / off,
+    single material (plain lean kernel) -- <= 1e-5 relative, zero / NaN / signed-zero pattern identical."""
+    djb = tier_1e5
+    assert djb.get_precision() == "1e-5"
+    wi, wo, _ = cases.pairs(cases.N_PARITY)
+    ewi, ewo, _ = cases.edge_pairs()
+    wi, wo = np.concatenate([wi, ewi]), np.concatenate([wo, ewo])
+    P = cases.param_sets(port)[pname]
+    for f in (api.Fresnel.ideal(), api.Fresnel.schlick([0.9, 0.5, 0.2])):
+        for shadow in (True, False):
+            b = mk_brdf(djb, ndf, f, shadow)
+            tag = f"{pname} fresnel {f.kind} shadow {shadow}"
+            check_1e5(b.eval(wi, wo, P), port.eval(ndf, P, wi, wo, f, shadow), "eval " + tag)
+            check_1e5(b.evalp(wi, wo, P), port.evalp(ndf, P, wi, wo, f, shadow), "evalp " + tag)
+            check_1e5(b.pdf(wi, wo, P), port.pdf(ndf, P, wi, wo, f, shadow), "pdf " + tag)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_fast_tier_broadcast_16_materials_against_oracle(tier_1e5, port, ndf):
+    """configs[1] layout (16 materials, the warp-compacting Beckmann kernel) in the default tier against the oracle."""
+    djb = tier_1e5
+    wi, wo, _ = cases.pairs(100_000, stream=16)
+    mats = cases.c2_materials(port)
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    got, gotp = b.eval(wi, wo, mats), b.pdf(wi, wo, mats)
+    worst = 0.0
+    for m in range(16):
+        worst = max(worst, check_1e5(got[m], port.eval(ndf, mats[m], wi, wo), f"eval material {m}")[0])
+        worst = max(worst, check_1e5(gotp[m], port.pdf(ndf, mats[m], wi, wo), f"pdf material {m}")[0])
+    print(f"1e-5 tier, 16 materials, ndf {ndf}: worst relative error {worst:.2e}")
+
+
+@pytest.mark.parametrize("ndf", ["ggx", "beckmann"])
+def test_fast_tier_vs_exact_tier_at_scale(djb, ndf):
+    """The 1e-5 tier against the exact tier on the device: 2e7 pairs x 16 materials = 3.2e8 results per query (eval, evalp, pdf;
+    Schlick Fresnel; BROADCAST and PER_PAIR layouts): worst relative difference <= 1e-5, zero / NaN pattern identical."""
+    import torch
+    n = 20_000_000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    def dirs():
+        z = 1.0 - 0.999 * torch.rand(n, device="cuda", generator=g)
+        ph = 6.283185307179586 * torch.rand(n, device="cuda", generator=g)
+        r = torch.sqrt(torch.clamp(1 - z * z, min=0))
+        return torch.stack([r * torch.cos(ph), r * torch.sin(ph), z], 1).contiguous()
+    wi, wo = dirs(), dirs()
+    rng = np.random.default_rng(1)
+    mats = np.stack([djb.params.elliptic(float(np.exp(rng.uniform(np.log(0.02), np.log(0.8)))),
+                                         float(np.exp(rng.uniform(np.log(0.02), np.log(0.8)))), float(rng.uniform(0, np.pi)))
+                     for _ in range(15)] + [djb.params.pdfparams(0.3, 0.2, 0.4, 0.1, -0.2)])
+    b = (djb.ggx if ndf == "ggx" else djb.beckmann)(djb.fresnel.schlick([0.9, 0.5, 0.2]))
+    report = {}
+    try:
+        for q in ("eval", "evalp", "pdf"):
+            djb.set_precision("1e-5")
+            fast = getattr(b, q)(wi, wo, mats)
+            djb.set_precision("bits")
+            ref = getattr(b, q)(wi, wo, mats)
+            assert torch.equal(fast == 0, ref == 0), f"{ndf} {q}: zero pattern differs"
+            assert torch.equal(torch.isnan(fast), torch.isnan(ref)), f"{ndf} {q}: NaN pattern differs"
+            rel = ((fast - ref).abs() / ref.abs().clamp_min(1e-30))
+            rel = torch.where(torch.isnan(rel), torch.zeros_like(rel), rel)
+            worst = rel.max().item()
+            report[q] = worst
+            assert worst <= 1e-5, f"{ndf} {q}: worst relative difference {worst:.3e}"
+            del fast, ref, rel
+        k = 2_000_000
+        pp = torch.from_numpy(np.ascontiguousarray(mats[np.arange(k) % 16])).cuda()
+        for q in ("eval", "pdf"):
+            djb.set_precision("1e-5")
+            fast = getattr(b, q)(wi[:k], wo[:k], pp, per_pair=True)
+            djb.set_precision("bits")
+            ref = getattr(b, q)(wi[:k], wo[:k], pp, per_pair=True)
+            assert torch.equal(fast == 0, ref == 0)
+            rel = ((fast - ref).abs() / ref.abs().clamp_min(1e-30))
+            rel = torch.where(torch.isnan(rel), torch.zeros_like(rel), rel)
+            report["per-pair " + q] = rel.max().item()
+            assert report["per-pair " + q] <= 1e-5, (ndf, q, report)
+    finally:
+        djb.set_precision("bits")
+    print(f"1e-5 tier vs exact tier, {ndf}: worst relative difference per query {report}")
