@@ -405,9 +405,29 @@ def run_ours(args, rank, local_rank, world):
         e2e_s = max_over_ranks(max(time.perf_counter() - t0, 1e-9))
         h2d = sum({"eval": 24, "pdf": 24, "sample": 20}[o] for _, o in kernels) * pairs
         d2h = sum({"eval": 12, "pdf": 4, "sample": 12}[o] for _, o in kernels) * pairs * M
+        # the host's ceiling for this leg, measured here: every rank copies device -> pinned host memory at the same time and does
+        # nothing else (87 % of the leg's bytes go that way); profiles/scripts/e2e_host_probe.py is the long form of this probe
+        probe_bytes = h_out.numel() * 4
+        d_probe = out[: h_out.numel()]
+
+        def d2h_probe():
+            h_out.copy_(d_probe, non_blocking=True)
+
+        d2h_probe()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            d2h_probe()
+        torch.cuda.synchronize()
+        ceiling = probe_bytes * 3 / max_over_ranks(time.perf_counter() - t0) / 1e9
+        d2h_gbs = d2h * e2e_steps / e2e_s / 1e9
         e2e = {"value": q_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "steps": e2e_steps, "slab_pairs": slab, "slabs_per_step": n_slabs,
                "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / e2e_s / 1e9,
+               "d2h_gbs_per_gpu": d2h_gbs, "d2h_ceiling_gbs_per_gpu": ceiling, "frac_of_host_d2h_ceiling": d2h_gbs / ceiling,
+               "ceiling_note": "ceiling = all ranks copying device -> pinned host concurrently, nothing else, measured in this run "
+                               "(this pool: 54 GB/s on one GPU = PCIe Gen5 x16; 92 GB/s aggregate on eight: the host side of the "
+                               "virtualised PCIe, profiles/r02_e2e_host_probe_n8.json); the leg also carries the H2D and the kernels",
                "note": "pinned host buffers through the C-ABI (DJB200_MEM_HOST): every slab of the 1e8 pairs is distinct host data; "
                        "wall clock, max over ranks",
                "cpus_bound_to_gpu_numa_node": numa}
