@@ -392,12 +392,55 @@ class microfacet(brdf):
     def qf_radial(self, u):
         return self._radial(3, u)
 
+    # microfacet::qf2 / qf3 and radial::qf2_radial / qf3_radial throw in the reference unless the family overrides them
+    # (dj_brdf.h:1783-1791, 1848-1860); ggx / beckmann override the radial pair below
+    def qf2(self, u, k):
+        raise DjbError(1, "djb_error: Not Implemented")
 
-class ggx(microfacet):
+    def qf3(self, u, k, qf2):
+        raise DjbError(1, "djb_error: Not Implemented")
+
+    def qf2_radial(self, u, cos_theta_k, sin_theta_k):
+        raise DjbError(1, "djb_error: Not Implemented")
+
+    def qf3_radial(self, u, qf2):
+        raise DjbError(1, "djb_error: Not Implemented")
+
+
+def _member_call(fn_name, first, what, args, widths, out_width):
+    """One of the scalar-member entry points (include/djb200.h: djb200_quantile_query, djb200_tabular_anisotropic_query,
+    djb200_sgd_member, djb200_abc_member): `args` are up to three argument arrays (None = unused) of `widths` floats per item."""
+    bufs = [Buf(a, np.float32) if a is not None else None for a in args]
+    lead = next(b for b in bufs if b is not None)
+    mem = capi.same_space(*[b for b in bufs if b is not None])
+    n = lead.n // widths[0]
+    out = capi.empty_like_space(lead.keep, (n, out_width) if out_width > 1 else (n,), np.float32)
+    bo = Buf(out, np.float32, True)
+    ptrs = [b.ptr if b is not None else None for b in bufs]
+    check(getattr(capi.load(), fn_name)(first, C.c_int32(what), *ptrs, C.c_int64(n), bo.ptr, C.c_int(mem),
+                                        capi.current_stream_ptr(mem)))
+    return out
+
+
+class _quantile_members:
+    """beckmann / ggx ::qf1, qf2_radial, qf3_radial (dj_brdf.h:366-369, 384-389), batched."""
+
+    def qf1(self, u):
+        return _member_call("djb200_quantile_query", C.c_int32(self._ndf), capi.MEMBER_QF1, [u, None, None], [1], 1)
+
+    def qf2_radial(self, u, cos_theta_k, sin_theta_k):
+        return _member_call("djb200_quantile_query", C.c_int32(self._ndf), capi.MEMBER_QF2_RADIAL, [u, cos_theta_k, sin_theta_k],
+                            [1, 1, 1], 1)
+
+    def qf3_radial(self, u, qf2):
+        return _member_call("djb200_quantile_query", C.c_int32(self._ndf), capi.MEMBER_QF3_RADIAL, [u, qf2, None], [1, 1], 1)
+
+
+class ggx(_quantile_members, microfacet):
     _ndf = capi.NDF_GGX
 
 
-class beckmann(microfacet):
+class beckmann(_quantile_members, microfacet):
     _ndf = capi.NDF_BECKMANN
 
     # LEAN algebra (dj_brdf.h:355-356)
@@ -541,6 +584,19 @@ class sgd(_analytic_brdf):
         c = self.coefficients()
         return fresnel.sgd(c[:, 4].astype(np.float32), c[:, 5].astype(np.float32))
 
+    # the per-channel terms eval is made of (dj_brdf.h:506-509, 3471-3499): vec3 per argument
+    def ndf(self, h):
+        return _member_call("djb200_sgd_member", C.byref(self._data), capi.MEMBER_NDF, [h, None, None], [3], 3)
+
+    def gaf(self, h, i, o):
+        return _member_call("djb200_sgd_member", C.byref(self._data), capi.MEMBER_GAF, [h, i, o], [3, 3, 3], 3)
+
+    def g1(self, k):
+        return _member_call("djb200_sgd_member", C.byref(self._data), capi.MEMBER_G1, [k, None, None], [3], 3)
+
+    def fresnel_term(self, cos_theta_d):
+        return _member_call("djb200_sgd_member", C.byref(self._data), capi.MEMBER_FRESNEL, [cos_theta_d, None, None], [1], 3)
+
 
 class abc(_analytic_brdf):
     """djb::abc (dj_brdf.h:514-535): ABC-distribution BRDF of a MERL material, by name."""
@@ -553,6 +609,16 @@ class abc(_analytic_brdf):
 
     def get_fresnel(self):
         return fresnel.unpolarized([np.float32(self._data.ior)] * 3)
+
+    # dj_brdf.h:531-533, 3649-3668: ndf -> vec3, gaf -> scalar, fresnel -> vec3
+    def ndf(self, h):
+        return _member_call("djb200_abc_member", C.byref(self._data), capi.MEMBER_NDF, [h, None, None], [3], 3)
+
+    def gaf(self, h, i, o):
+        return _member_call("djb200_abc_member", C.byref(self._data), capi.MEMBER_GAF, [h, i, o], [3, 3, 3], 1)
+
+    def fresnel_term(self, cos_theta_d):
+        return _member_call("djb200_abc_member", C.byref(self._data), capi.MEMBER_FRESNEL, [cos_theta_d, None, None], [1], 3)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -830,6 +896,36 @@ class tabular_anisotropic(microfacet):
             h, *[C.c_void_p(a.ctypes.data) for a in (one[0], one[1], one[2], two[0], two[1], two[2])], counts))
         return dict(pdf1=one[0], cdf1=one[1], qf1=one[2], pdf2=two[0], cdf2=two[1], qf2=two[2], n_qf1=counts[0],
                     n_qf2=counts[1])
+
+    # the public table queries (dj_brdf.h:450-455, 2766-2824), batched
+    def _table_member(self, what, a, b=None):
+        h, _ = self._first_arg()
+        bufs = [Buf(a, np.float32), Buf(b, np.float32) if b is not None else None]
+        mem = capi.same_space(*[x for x in bufs if x is not None])
+        out = capi.empty_like_space(bufs[0].keep, (bufs[0].n,), np.float32)
+        bo = Buf(out, np.float32, True)
+        check(capi.load().djb200_tabular_anisotropic_query(h, C.c_int32(what), bufs[0].ptr, bufs[1].ptr if bufs[1] else None,
+                                                           C.c_int64(bufs[0].n), bo.ptr, C.c_int(mem),
+                                                           capi.current_stream_ptr(mem)))
+        return out
+
+    def pdf1(self, phi):
+        return self._table_member(capi.MEMBER_PDF1, phi)
+
+    def cdf1(self, phi):
+        return self._table_member(capi.MEMBER_CDF1, phi)
+
+    def qf1(self, u1):
+        return self._table_member(capi.MEMBER_TQF1, u1)
+
+    def pdf2(self, theta, phi):
+        return self._table_member(capi.MEMBER_PDF2, theta, phi)
+
+    def cdf2(self, theta, phi):
+        return self._table_member(capi.MEMBER_CDF2, theta, phi)
+
+    def qf2(self, u, phi):
+        return self._table_member(capi.MEMBER_TQF2, u, phi)
 
     @staticmethod
     def fit_beckmann_parameters(tab):

@@ -847,6 +847,72 @@ djb200_status djb200_radial_query(int what, int ndf, const djb200_tabular *t, co
 		});
 }
 
+// the remaining public scalar members: one kernel, the argument plumbing of map_call
+static djb200_status member_call(int family, int what, const djb200_tabular *t, const double *coef, int n_coef, const float *a,
+                                 size_t a_item, const float *b, size_t b_item, const float *c, size_t c_item, size_t out_item, int64_t n,
+                                 float *out, int mem, void *stream)
+{
+	if (n < 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "negative count");
+	if (n == 0) return DJB200_OK;
+	if ((a_item && !a) || (b_item && !b) || (c_item && !c) || !out) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument array");
+	std::vector<BulkIn> ins;
+	int sa = -1, sb = -1, sc = -1;
+	if (a_item) { sa = (int)ins.size(); ins.push_back({a, a_item}); }
+	if (b_item) { sb = (int)ins.size(); ins.push_back({b, b_item}); }
+	if (c_item) { sc = (int)ins.size(); ins.push_back({c, c_item}); }
+	const float *tables = t ? t->tables : nullptr;
+	const int er = t ? t->res : 0, ar = t ? t->azim_res : 0, nq = t ? t->n_qf1 : 0;
+	return map_call(n, ins, {{out, out_item}}, mem, stream,
+		[=](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
+			return launch_member_query(family, what, tables, er, ar, nq, coef, n_coef, sa >= 0 ? (const float *)i[sa] : nullptr,
+			                           sb >= 0 ? (const float *)i[sb] : nullptr, sc >= 0 ? (const float *)i[sc] : nullptr, cn,
+			                           (float *)o[0], st);
+		});
+}
+
+djb200_status djb200_quantile_query(int32_t ndf, int32_t what, const float *a, const float *b, const float *c, int64_t n, float *out,
+                                    int mem, void *stream)
+{
+	if (ndf != DJB200_NDF_BECKMANN && ndf != DJB200_NDF_GGX) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown ndf %d", ndf);
+	if (what < DJB200_MEMBER_QF1 || what > DJB200_MEMBER_QF3_RADIAL) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown quantile member %d", what);
+	const bool two = what != DJB200_MEMBER_QF1, three = what == DJB200_MEMBER_QF2_RADIAL;
+	return member_call(ndf, what, nullptr, nullptr, 0, a, 4, b, two ? 4 : 0, c, three ? 4 : 0, 4, n, out, mem, stream);
+}
+
+djb200_status djb200_tabular_anisotropic_query(const djb200_tabular *t, int32_t what, const float *a, const float *b, int64_t n,
+                                               float *out, int mem, void *stream)
+{
+	if (!t) return fail(DJB200_ERR_INVALID_ARGUMENT, "tabular handle is NULL");
+	if (t->azim_res <= 0) return fail(DJB200_ERR_INVALID_ARGUMENT, "not a tabular_anisotropic handle");
+	if (what < DJB200_MEMBER_PDF1 || what > DJB200_MEMBER_TQF2) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown table member %d", what);
+	const bool two = what == DJB200_MEMBER_PDF2 || what == DJB200_MEMBER_CDF2 || what == DJB200_MEMBER_TQF2;
+	return member_call(2, what, t, nullptr, 0, a, 4, b, two ? 4 : 0, nullptr, 0, 4, n, out, mem, stream);
+}
+
+djb200_status djb200_sgd_member(const djb200_sgd_data *m, int32_t what, const float *a, const float *b, const float *c, int64_t n,
+                                float *out, int mem, void *stream)
+{
+	if (!m) return fail(DJB200_ERR_INVALID_ARGUMENT, "sgd coefficients are NULL");
+	if (what < DJB200_MEMBER_NDF || what > DJB200_MEMBER_FRESNEL) return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown sgd member %d", what);
+	const bool gaf = what == DJB200_MEMBER_GAF;
+	const size_t a_item = what == DJB200_MEMBER_FRESNEL ? 4 : 12;
+	return member_call(3, what, nullptr, &m->ch[0][0], 33, a, a_item, b, gaf ? 12 : 0, c, gaf ? 12 : 0, 12, n, out, mem, stream);
+}
+
+djb200_status djb200_abc_member(const djb200_abc_data *m, int32_t what, const float *a, const float *b, const float *c, int64_t n,
+                                float *out, int mem, void *stream)
+{
+	if (!m) return fail(DJB200_ERR_INVALID_ARGUMENT, "abc coefficients are NULL");
+	if (what != DJB200_MEMBER_NDF && what != DJB200_MEMBER_GAF && what != DJB200_MEMBER_FRESNEL)
+		return fail(DJB200_ERR_INVALID_ARGUMENT, "unknown abc member %d", what);
+	double coef[9];
+	for (int k = 0; k < 3; ++k) { coef[k] = m->kD[k]; coef[3 + k] = m->A[k]; }
+	coef[6] = m->B; coef[7] = m->C; coef[8] = m->ior;
+	const bool gaf = what == DJB200_MEMBER_GAF;
+	const size_t a_item = what == DJB200_MEMBER_FRESNEL ? 4 : 12;
+	return member_call(4, what, nullptr, coef, 9, a, a_item, b, gaf ? 12 : 0, c, gaf ? 12 : 0, gaf ? 4 : 12, n, out, mem, stream);
+}
+
 djb200_status djb200_tabular_anisotropic_sampling_tables(const djb200_tabular *t, float *pdf1, float *cdf1, float *qf1,
                                                          float *pdf2, float *cdf2, float *qf2, int32_t counts[2])
 {

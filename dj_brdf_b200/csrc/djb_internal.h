@@ -83,6 +83,9 @@ cudaError_t launch_tabular_aniso_query(const float *tables, int elev_res, int az
 // djb::radial's scalar queries; family: djb200_ndf or 2 = tabular (radial tables: p22 | sigma | qf | fresnel[3] | cdf)
 cudaError_t launch_radial_query(int family, int what, const float *tables, int res, const float *x, int64_t n, float *out,
                                 cudaStream_t st);
+// the remaining public scalar members (kernels_tabular.cu); family: 0 beckmann, 1 ggx, 2 tabular_anisotropic, 3 sgd, 4 abc
+cudaError_t launch_member_query(int family, int what, const float *tables, int er, int ar, int n_qf1, const double *coef, int n_coef,
+                                const float *a, const float *b, const float *c, int64_t n, float *out, cudaStream_t st);
 // builds qf1 | qf2 | pdf1 | cdf1 | pdf2 | cdf2 inside `tables` from its p22 block (dj_brdf.h:2848-3103); counts_host[2]
 // receives the fill counts of qf1 / qf2 (the call synchronises the stream)
 cudaError_t build_aniso_sampling_tables(float *tables, int elev_res, int azim_res, int counts_host[2], cudaStream_t st);

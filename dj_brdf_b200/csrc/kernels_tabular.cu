@@ -626,4 +626,115 @@ cudaError_t launch_tabular_query(const float *tables, int res, const MfLaunch &L
 	return e;
 }
 
+// ---- the remaining public scalar members of the reference's classes (dj_brdf.h:366-369, 384-389, 450-455, 506-509, 531-533) ------
+// beckmann / ggx ::qf1, qf2_radial, qf3_radial; tabular_anisotropic ::pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2; sgd ::ndf / gaf / g1 /
+// fresnel; abc ::ndf / gaf / fresnel.  One query per thread, mirrored-rounding tier (these are the very functions sample / eval
+// are built from).  Rare calls: correctness and the reference's interface, not throughput.
+struct MemberArgs {
+	int family, what;         // family: 0 beckmann, 1 ggx, 2 tabular_anisotropic, 3 sgd, 4 abc
+	const float *tables;      // tabular_anisotropic handle tables
+	int er, ar, n_qf1;
+	double coef[33];          // sgd / abc coefficients
+	const float *a, *b, *c;
+	long long n;
+	float *out;
+};
+DJB_DEV float ggx_qf1_ref(float u) // ggx::qf1, dj_brdf.h:2078-2087
+{
+	if ((double)u < 0.5) {
+		u = (float)((0.5 - (double)u) * 2.0);
+		return -u * inv_sqrt((float)(1.0 - (double)(u * u)));
+	}
+	u = (float)(((double)u - 0.5) * 2.0);
+	return u * inv_sqrt((float)(1.0 - (double)(u * u)));
+}
+__global__ void __launch_bounds__(TQ_THREADS) member_query_kernel(MemberArgs A)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
+		if (A.family <= 1) { // a = u, b = cos_theta_k or qf2, c = sin_theta_k
+			const float u = A.a[k];
+			float r;
+			if (A.what == DJB200_MEMBER_QF1) r = A.family == NDF_GGX ? ggx_qf1_ref(u) : erfinv_giles((float)(2.0 * (double)u - 1.0));
+			else if (A.what == DJB200_MEMBER_QF2_RADIAL) r = A.family == NDF_GGX ? ggx_qf2(u, A.b[k], A.c[k]) : beckmann_qf2(u, A.b[k], A.c[k]);
+			else r = A.family == NDF_GGX ? ggx_qf3(u, A.b[k]) : erfinv_giles((float)(2.0 * (double)u - 1.0)); // beckmann::qf3_radial = qf1(u)
+			A.out[k] = r;
+		} else if (A.family == 2) { // dj_brdf.h:2766-2824
+			const int er = A.er, ar = A.ar;
+			const float x = A.a[k], y = A.b ? A.b[k] : 0.0f;
+			float r;
+			switch (A.what) {
+			case DJB200_MEMBER_PDF1: r = ab_lookup1(A.tables + aniso_off_pdf1(er, ar), ar, x); break;
+			case DJB200_MEMBER_CDF1: r = ab_lookup1(A.tables + aniso_off_cdf1(er, ar), ar, x); break;
+			case DJB200_MEMBER_TQF1: r = (float)((double)spline_f(A.tables + aniso_off_qf1(er, ar), A.n_qf1, x) * 2.0 * DJB_PI); break;
+			case DJB200_MEMBER_PDF2: r = ab_lookup2(A.tables + aniso_off_pdf2(er, ar), er, ar, x, y, 0.0f); break;
+			case DJB200_MEMBER_CDF2: r = ab_lookup2(A.tables + aniso_off_cdf2(er, ar), er, ar, x, y, 1.0f); break;
+			default: r = (float)((double)spline2d_f(A.tables + aniso_off_qf2(er, ar), er, ar, x, (float)((double)y / (2.0 * DJB_PI))) * 0.5 * DJB_PI);
+			}
+			A.out[k] = r;
+		} else if (A.family == 3) { // sgd, dj_brdf.h:3471-3499: a = h (ndf) / unused (gaf) / k (g1) / cos (fresnel); b = i, c = o
+			V3 r;
+			if (A.what == DJB200_MEMBER_NDF) {
+				const double ch = (double)A.a[3 * k + 2], c2 = ch * ch, t2 = (1.0 - c2) / c2, inv_pi = 1.0 / DJB_PI;
+				float v[3];
+				for (int c = 0; c < 3; ++c) {
+					const double *mc = A.coef + 11 * c;
+					const double ax = mc[2] + t2 / mc[2];
+					v[c] = (float)((mc[6] * exp(-ax) * inv_pi) / (pow(ax, mc[3]) * c2 * c2));
+				}
+				r = mk(v[0], v[1], v[2]);
+			} else if (A.what == DJB200_MEMBER_G1 || A.what == DJB200_MEMBER_GAF) {
+				float g[3] = {1.f, 1.f, 1.f};
+				const int terms = A.what == DJB200_MEMBER_GAF ? 2 : 1;
+				for (int t = 0; t < terms; ++t) { // gaf(h, i, o) = g1(i) * g1(o), vec3 products in float
+					const float *dir = A.what == DJB200_MEMBER_GAF ? (t == 0 ? A.b : A.c) : A.a;
+					const double ak = acos((double)dir[3 * k + 2]);
+					for (int c = 0; c < 3; ++c) {
+						const float g1 = (float)sgd_g1_ch(ak, A.coef + 11 * c);
+						g[c] = t == 0 ? g1 : g[c] * g1;
+					}
+				}
+				r = mk(g[0], g[1], g[2]);
+			} else {
+				FresnelDev fr;
+				fr.pts = nullptr; fr.npts = 0;
+				for (int c = 0; c < 3; ++c) { fr.v[c] = (float)A.coef[11 * c + 4]; fr.v[3 + c] = (float)A.coef[11 * c + 5]; }
+				r = fresnel_eval<FK_SGD>(fr, A.a[k]);
+			}
+			A.out[3 * k] = r.x; A.out[3 * k + 1] = r.y; A.out[3 * k + 2] = r.z;
+		} else { // abc, dj_brdf.h:3649-3668: coef = kD[3] A[3] B C ior
+			if (A.what == DJB200_MEMBER_GAF) {
+				const V3 h = mk(A.a[3 * k], A.a[3 * k + 1], A.a[3 * k + 2]), i = mk(A.b[3 * k], A.b[3 * k + 1], A.b[3 * k + 2]);
+				const V3 o = mk(A.c[3 * k], A.c[3 * k + 1], A.c[3 * k + 2]);
+				const float g1_i = fmin_ref(1.0f, 2.0f * (h.z * i.z / dot(h, i))), g1_o = fmin_ref(1.0f, 2.0f * (h.z * o.z / dot(h, o)));
+				A.out[k] = fmin_ref(g1_i, g1_o);
+				continue;
+			}
+			V3 r;
+			if (A.what == DJB200_MEMBER_NDF) {
+				const double den = pow(1.0 + A.coef[6] * (1.0 - (double)A.a[3 * k + 2]), A.coef[7]);
+				r = mk((float)(A.coef[3] / den), (float)(A.coef[4] / den), (float)(A.coef[5] / den));
+			} else {
+				const float f = unpolarized_channel(A.a[k], (float)A.coef[8]);
+				r = mk(f, f, f);
+			}
+			A.out[3 * k] = r.x; A.out[3 * k + 1] = r.y; A.out[3 * k + 2] = r.z;
+		}
+	}
+}
+
+cudaError_t launch_member_query(int family, int what, const float *tables, int er, int ar, int n_qf1, const double *coef, int n_coef,
+                                const float *a, const float *b, const float *c, int64_t n, float *out, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	MemberArgs A;
+	A.family = family; A.what = what; A.tables = tables; A.er = er; A.ar = ar; A.n_qf1 = n_qf1;
+	for (int k = 0; k < 33; ++k) A.coef[k] = coef && k < n_coef ? coef[k] : 0.0;
+	A.a = a; A.b = b; A.c = c; A.n = n; A.out = out;
+	long long want = (n + TQ_THREADS - 1) / TQ_THREADS, cap = (long long)sm_count() * 8;
+	member_query_kernel<<<(int)(want < cap ? want : cap), TQ_THREADS, 0, st>>>(A);
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
 } // namespace djb200

@@ -409,6 +409,33 @@ DJB200_API djb200_status djb200_tabular_anisotropic_sampling_tables(const djb200
                                                                     float *qf1, float *pdf2, float *cdf2, float *qf2,
                                                                     int32_t counts[2]);
 
+/* ---- the remaining public scalar members of the reference's classes ------------------------------------------------------ *
+ * One call evaluates one member for n arguments; unused argument arrays are NULL.  Scalars in, one float out per argument,
+ * except the sgd / abc members that return a vec3 (out: n x 3).
+ *   djb200_quantile_query(ndf, what, ...)   beckmann / ggx (dj_brdf.h:366-369, 384-389):
+ *       DJB200_MEMBER_QF1 (a = u) | DJB200_MEMBER_QF2_RADIAL (a = u, b = cos_theta_k, c = sin_theta_k) | DJB200_MEMBER_QF3_RADIAL (a = u, b = qf2)
+ *   djb200_tabular_anisotropic_query(t, what, ...)   tabular_anisotropic (dj_brdf.h:450-455, 2766-2824):
+ *       DJB200_MEMBER_PDF1 / CDF1 (a = phi) | DJB200_MEMBER_TQF1 (a = u1) | DJB200_MEMBER_PDF2 / CDF2 (a = theta, b = phi) | DJB200_MEMBER_TQF2 (a = u, b = phi)
+ *   djb200_sgd_member / djb200_abc_member (dj_brdf.h:506-509, 531-533, 3471-3499, 3649-3668), vec3 arguments as n x 3:
+ *       DJB200_MEMBER_NDF (a = h) | DJB200_MEMBER_GAF (a = h, b = i, c = o; abc returns a scalar: out n x 1) | DJB200_MEMBER_G1 (sgd: a = k)
+ *       | DJB200_MEMBER_FRESNEL (a = cos_theta_d, n x 1)
+ * (microfacet::qf2 / qf3 and radial's own qf2_radial / qf3_radial throw "Not Implemented" in the reference, dj_brdf.h:1783-1791,
+ * 1848-1860: the facade does the same, no device entry.) */
+enum {
+	DJB200_MEMBER_QF1 = 0, DJB200_MEMBER_QF2_RADIAL = 1, DJB200_MEMBER_QF3_RADIAL = 2,
+	DJB200_MEMBER_PDF1 = 10, DJB200_MEMBER_CDF1 = 11, DJB200_MEMBER_TQF1 = 12, DJB200_MEMBER_PDF2 = 13, DJB200_MEMBER_CDF2 = 14,
+	DJB200_MEMBER_TQF2 = 15,
+	DJB200_MEMBER_NDF = 20, DJB200_MEMBER_GAF = 21, DJB200_MEMBER_G1 = 22, DJB200_MEMBER_FRESNEL = 23
+};
+DJB200_API djb200_status djb200_quantile_query(int32_t ndf, int32_t what, const float *a, const float *b, const float *c, int64_t n,
+                                               float *out, int mem, void *stream);
+DJB200_API djb200_status djb200_tabular_anisotropic_query(const djb200_tabular *t, int32_t what, const float *a, const float *b,
+                                                          int64_t n, float *out, int mem, void *stream);
+DJB200_API djb200_status djb200_sgd_member(const djb200_sgd_data *m, int32_t what, const float *a, const float *b, const float *c,
+                                           int64_t n, float *out, int mem, void *stream);
+DJB200_API djb200_status djb200_abc_member(const djb200_abc_data *m, int32_t what, const float *a, const float *b, const float *c,
+                                           int64_t n, float *out, int mem, void *stream);
+
 /* ---- anisotropic fit, stage by stage ------------------------------------------------------- *
  * The same fit as djb200_fit_tabular_anisotropic(), split at the two places where a fit whose
  * n = (elev_res - 1) * azim_res matrix rows are sharded over several GPUs has to exchange data: the

@@ -512,6 +512,9 @@ public:
 	}
 
 	virtual bool supports_smith_vndf_sampling() const = 0;
+	// dj_brdf.h:275-276, 1783-1791: the base versions throw, and no class of the reference overrides them
+	virtual float_t qf2(float_t, const vec3 &) const { throw exc("djb_error: Not Implemented"); }
+	virtual float_t qf3(float_t, const vec3 &, float_t) const { throw exc("djb_error: Not Implemented"); }
 	void set_shadow(bool shadow) { m_shadow = shadow; ++m_fresnel_rev; }
 	void set_fresnel(const fresnel::impl &f)
 	{
@@ -578,6 +581,9 @@ public:
 	float_t sigma_std_radial(float_t cos_theta_k) const { return radial_query(DJB200_RADIAL_SIGMA_STD, cos_theta_k); }
 	float_t cdf_radial(float_t r) const { return radial_query(DJB200_RADIAL_CDF, r); }
 	float_t qf_radial(float_t u) const { return radial_query(DJB200_RADIAL_QF, u); }
+	// dj_brdf.h:311-314, 1848-1860: "Not Implemented" unless the family overrides them (ggx and beckmann do)
+	virtual float_t qf2_radial(float_t, float_t, float_t) const { throw exc("djb_error: Not Implemented"); }
+	virtual float_t qf3_radial(float_t, float_t) const { throw exc("djb_error: Not Implemented"); }
 	// batched (added): n arguments per call
 	void radial_query_batch(djb200_radial_what what, const float_t *x, size_t n, float_t *out, memory_space where = host,
 	                        void *stream = NULL) const
@@ -587,6 +593,13 @@ public:
 protected:
 	radial(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : microfacet(f, shadow) {}
 	virtual const djb200_tabular *radial_handle() const { return NULL; } // tabular: its device tables
+	// ggx / beckmann ::qf1, qf2_radial, qf3_radial (dj_brdf.h:366-369, 384-389): the pieces `sample` is made of
+	float_t quantile_query(int what, float_t a, float_t b = 0, float_t c = 0) const
+	{
+		float_t r;
+		detail::check(djb200_quantile_query(ndf_id(), what, &a, &b, &c, 1, &r, DJB200_MEM_HOST, NULL));
+		return r;
+	}
 private:
 	float_t radial_query(djb200_radial_what what, float_t x) const
 	{
@@ -601,6 +614,18 @@ class ggx : public radial {
 public:
 	ggx(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : radial(f, shadow) {}
 	bool supports_smith_vndf_sampling() const { return true; }
+	float_t qf1(float_t u) const { return quantile_query(DJB200_MEMBER_QF1, u); }
+	float_t qf2_radial(float_t u, float_t cos_theta_k, float_t sin_theta_k) const
+	{
+		return quantile_query(DJB200_MEMBER_QF2_RADIAL, u, cos_theta_k, sin_theta_k);
+	}
+	float_t qf3_radial(float_t u, float_t qf2) const { return quantile_query(DJB200_MEMBER_QF3_RADIAL, u, qf2); }
+	// batched (added): unused argument arrays may be NULL
+	void quantile_query_batch(int what, const float_t *a, const float_t *b, const float_t *c, size_t n, float_t *out,
+	                          memory_space where = host, void *stream = NULL) const
+	{
+		detail::check(djb200_quantile_query(ndf_id(), what, a, b, c, (int64_t)n, out, where, stream));
+	}
 protected:
 	int ndf_id() const { return DJB200_NDF_GGX; }
 };
@@ -648,6 +673,18 @@ public:
 	};
 	beckmann(const fresnel::impl &f = fresnel::ideal(), bool shadow = true) : radial(f, shadow) {}
 	bool supports_smith_vndf_sampling() const { return true; }
+	float_t qf1(float_t u) const { return quantile_query(DJB200_MEMBER_QF1, u); }
+	float_t qf2_radial(float_t u, float_t cos_theta_k, float_t sin_theta_k) const
+	{
+		return quantile_query(DJB200_MEMBER_QF2_RADIAL, u, cos_theta_k, sin_theta_k);
+	}
+	float_t qf3_radial(float_t u, float_t qf2) const { return quantile_query(DJB200_MEMBER_QF3_RADIAL, u, qf2); }
+	// batched (added): unused argument arrays may be NULL
+	void quantile_query_batch(int what, const float_t *a, const float_t *b, const float_t *c, size_t n, float_t *out,
+	                          memory_space where = host, void *stream = NULL) const
+	{
+		detail::check(djb200_quantile_query(ndf_id(), what, a, b, c, (int64_t)n, out, where, stream));
+	}
 	static void params_to_lrep(const microfacet::params &p, lrep *l)
 	{
 		DJB_ASSERT(l && "Null output ptr");
@@ -740,8 +777,25 @@ public:
 	{
 		detail::check(djb200_sgd_eval(&m_data, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
 	}
+	// the per-channel terms eval is made of (dj_brdf.h:506-509, 3471-3499)
+	vec3 ndf(const vec3 &h) const { return member(DJB200_MEMBER_NDF, &h.x, NULL, NULL); }
+	vec3 gaf(const vec3 &h, const vec3 &i, const vec3 &o) const { return member(DJB200_MEMBER_GAF, &h.x, &i.x, &o.x); }
+	vec3 g1(const vec3 &k) const { return member(DJB200_MEMBER_G1, &k.x, NULL, NULL); }
+	vec3 fresnel(float_t cos_theta_d) const { return member(DJB200_MEMBER_FRESNEL, &cos_theta_d, NULL, NULL); }
+	void member_batch(int what, const float_t *a, const float_t *b, const float_t *c, size_t n, vec3 *out,
+	                  memory_space where = host, void *stream = NULL) const
+	{
+		detail::check(djb200_sgd_member(&m_data, what, a, b, c, (int64_t)n, &out->x, where, stream));
+	}
 	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
 	const djb200_sgd_data *data() const { return &m_data; }
+private:
+	vec3 member(int what, const float_t *a, const float_t *b, const float_t *c) const
+	{
+		vec3 r;
+		member_batch(what, a, b, c, 1, &r);
+		return r;
+	}
 };
 
 // dj_brdf.h:514-535: ABC distribution BRDF of a MERL material
@@ -766,8 +820,30 @@ public:
 	{
 		detail::check(djb200_abc_eval(&m_data, &i->x, &o->x, (int64_t)n, &out->x, where, stream));
 	}
+	// dj_brdf.h:531-533, 3649-3668
+	vec3 ndf(const vec3 &h) const { return member3(DJB200_MEMBER_NDF, &h.x); }
+	float_t gaf(const vec3 &h, const vec3 &i, const vec3 &o) const
+	{
+		float_t r;
+		detail::check(djb200_abc_member(&m_data, DJB200_MEMBER_GAF, &h.x, &i.x, &o.x, 1, &r, DJB200_MEM_HOST, NULL));
+		return r;
+	}
+	vec3 fresnel(float_t cos_theta_d) const { return member3(DJB200_MEMBER_FRESNEL, &cos_theta_d); }
+	// batched (added): out is n x 3 floats, n x 1 for DJB200_MEMBER_GAF
+	void member_batch(int what, const float_t *a, const float_t *b, const float_t *c, size_t n, float_t *out,
+	                  memory_space where = host, void *stream = NULL) const
+	{
+		detail::check(djb200_abc_member(&m_data, what, a, b, c, (int64_t)n, out, where, stream));
+	}
 	const fresnel::impl &get_fresnel() const { return *m_fresnel; }
 	const djb200_abc_data *data() const { return &m_data; }
+private:
+	vec3 member3(int what, const float_t *a) const
+	{
+		vec3 r;
+		member_batch(what, a, NULL, NULL, 1, &r.x);
+		return r;
+	}
 };
 
 namespace detail {
@@ -986,6 +1062,35 @@ public:
 	}
 	const std::vector<float_t> &get_residuals() const { return m_residuals; }
 	bool supports_smith_vndf_sampling() const { return false; }
+	// the public table queries, dj_brdf.h:450-455, 2766-2824
+	float_t pdf1(float_t phi) const { return table_query(DJB200_MEMBER_PDF1, phi, 0); }
+	float_t pdf2(float_t theta, float_t phi) const
+	{
+		DJB_ASSERT(theta >= 0.0 && "Invalid Angle");
+		return table_query(DJB200_MEMBER_PDF2, theta, phi);
+	}
+	float_t cdf1(float_t phi) const { return table_query(DJB200_MEMBER_CDF1, phi, 0); }
+	float_t cdf2(float_t theta, float_t phi) const
+	{
+		DJB_ASSERT(theta >= 0.0 && "Invalid Angle");
+		return table_query(DJB200_MEMBER_CDF2, theta, phi);
+	}
+	float_t qf1(float_t u1) const
+	{
+		DJB_ASSERT(u1 >= 0.0 && u1 <= 1.0 && "Invalid Variate");
+		return table_query(DJB200_MEMBER_TQF1, u1, 0);
+	}
+	float_t qf2(float_t u, float_t phi) const
+	{
+		DJB_ASSERT(u >= 0.0 && u <= 1.0 && "Invalid Variate");
+		return table_query(DJB200_MEMBER_TQF2, u, phi);
+	}
+	// batched (added): b may be NULL for the one-argument members
+	void table_query_batch(int what, const float_t *a, const float_t *b, size_t n, float_t *out, memory_space where = host,
+	                       void *stream = NULL) const
+	{
+		detail::check(djb200_tabular_anisotropic_query(upload(), what, a, b, (int64_t)n, out, where, stream));
+	}
 	// the six sampling tables behind pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 (dj_brdf.h:2766-2824); any pointer may be NULL
 	void get_sampling_tables(std::vector<float_t> *pdf1, std::vector<float_t> *cdf1, std::vector<float_t> *qf1,
 	                         std::vector<float_t> *pdf2, std::vector<float_t> *cdf2, std::vector<float_t> *qf2) const
@@ -1025,6 +1130,12 @@ protected:
 	{
 		make_handle mk = {this};
 		return m_device.get(m_fresnel_rev, mk);
+	}
+	float_t table_query(int what, float_t a, float_t b) const
+	{
+		float_t r;
+		table_query_batch(what, &a, &b, 1, &r);
+		return r;
 	}
 	void dispatch(int op, const djb200_params *p, int64_t n_params, djb200_params_layout layout, const float *a, const float *b,
 	              size_t n, float *o0, float *o1, float *o2, memory_space where, void *stream) const

@@ -805,6 +805,50 @@ class RefOracle:
             self.destroy(t)
             self.destroy(h)
 
+    # ---- the remaining public scalar members (dj_brdf.h:366-369, 384-389, 450-455, 506-509, 531-533) -----------------
+    MEMBER_CODES = {"qf1": 0, "qf2_radial": 1, "qf3_radial": 2, "ndf": 20, "gaf": 21, "g1": 22, "fresnel": 23}
+
+    def member_query(self, what, a, b=None, c=None, ndf=None, sgd=None, abc=None):
+        """beckmann / ggx ::qf1 / qf2_radial / qf3_radial (ndf=...), sgd ::ndf / gaf / g1 / fresnel (sgd=name), abc ::ndf / gaf /
+        fresnel (abc=name) on the reference's own objects; vec3 arguments as [n, 3]."""
+        code = self.MEMBER_CODES[what]
+        h = self.microfacet(ndf) if ndf is not None else self.analytic("sgd" if sgd else "abc", sgd or abc)
+        a = _f32(a)
+        b, c = (None if x is None else _f32(x) for x in (b, c))
+        vec_in = ndf is None and what != "fresnel"
+        n = len(a) if not vec_in else a.reshape(-1, 3).shape[0]
+        out = np.zeros((n, 3), np.float32)
+        try:
+            rc = self.lib.ref_member_query(h, C.c_int(code), c_f32p(a.ctypes.data), c_f32p(_ptr(b)), c_f32p(_ptr(c)), C.c_int(n),
+                                           c_f32p(out.ctypes.data))
+            assert rc in (1, 3), rc
+        finally:
+            self.destroy(h)
+        return out.reshape(-1)[:n].copy() if rc == 1 else out
+
+    def tabular_aniso_lookup(self, src, er, ar, what, a, b=None, shadow=True):
+        """tabular_anisotropic::pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 of the reference's object fitted to `src` (needs opened=True:
+        the wrapper lives in oracle/ref_open.cpp)."""
+        assert self.opened, "ref_tabular_anisotropic_lookup is built into libdjbref_open.so"
+        code = {"pdf1": 0, "cdf1": 1, "qf1": 2, "pdf2": 3, "cdf2": 4, "qf2": 5}[what]
+        h = self._source_handle(src)
+        t = C.c_void_p(self.lib.ref_tabular_anisotropic_create(h, C.c_int(er), C.c_int(ar), C.c_int(int(shadow))))
+        try:
+            return self.tabular_aniso_lookup_on(t, what, a, b)
+        finally:
+            self.destroy(t)
+            self.destroy(h)
+
+    def tabular_aniso_lookup_on(self, t, what, a, b=None):
+        code = {"pdf1": 0, "cdf1": 1, "qf1": 2, "pdf2": 3, "cdf2": 4, "qf2": 5}[what]
+        a = _f32(a)
+        b = _f32(b) if b is not None else np.zeros_like(a)
+        out = np.zeros(len(a), np.float32)
+        rc = self.lib.ref_tabular_anisotropic_lookup(t, C.c_int(code), c_f32p(a.ctypes.data), c_f32p(b.ctypes.data),
+                                                     C.c_int(len(a)), c_f32p(out.ctypes.data))
+        assert rc == 0, rc
+        return out
+
     def fit_tabular_anisotropic(self, src, elev_res=90, azim_res=90, shadow=True, iterations=4, nthreads=1):
         assert iterations == 4
         h = self._source_handle(src)

@@ -406,3 +406,48 @@ REF_API int ref_radial_qf_cdf(void *h, const float *x, int n, float *qf_out, flo
 	}
 	return 0;
 }
+
+// the remaining public scalar members (dj_brdf.h:366-369, 384-389, 506-509, 531-533).  what: 0 qf1(a), 1 qf2_radial(a, b, c),
+// 2 qf3_radial(a, b) on a ggx / beckmann handle; 20 ndf(a3), 21 gaf(a3, b3, c3), 22 g1(a3), 23 fresnel(a) on an sgd / abc
+// handle (vec3 arguments as n x 3; vec3 results n x 3; abc::gaf returns a scalar, n x 1).  Returns floats written per item.
+REF_API int ref_member_query(void *h, int what, const float *a, const float *b, const float *c, int n, float *out)
+{
+	djb::brdf *base = static_cast<djb::brdf *>(h);
+	if (what <= 2) {
+		const djb::beckmann *bk = dynamic_cast<djb::beckmann *>(base);
+		const djb::ggx *gg = dynamic_cast<djb::ggx *>(base);
+		if (!bk && !gg) return -1;
+		for (int k = 0; k < n; ++k) {
+			if (what == 0) out[k] = bk ? bk->qf1(a[k]) : gg->qf1(a[k]);
+			else if (what == 1) out[k] = bk ? bk->qf2_radial(a[k], b[k], c[k]) : gg->qf2_radial(a[k], b[k], c[k]);
+			else out[k] = bk ? bk->qf3_radial(a[k], b[k]) : gg->qf3_radial(a[k], b[k]);
+		}
+		return 1;
+	}
+	if (const djb::sgd *s = dynamic_cast<djb::sgd *>(base)) {
+		for (int k = 0; k < n; ++k) {
+			djb::vec3 r;
+			switch (what) {
+			case 20: r = s->ndf(ld3(a, k)); break;
+			case 21: r = s->gaf(ld3(a, k), ld3(b, k), ld3(c, k)); break;
+			case 22: r = s->g1(ld3(a, k)); break;
+			case 23: r = s->fresnel(a[k]); break;
+			default: return -2;
+			}
+			st3(out, k, r);
+		}
+		return 3;
+	}
+	if (const djb::abc *s = dynamic_cast<djb::abc *>(base)) {
+		for (int k = 0; k < n; ++k) {
+			if (what == 21) { out[k] = s->gaf(ld3(a, k), ld3(b, k), ld3(c, k)); continue; }
+			djb::vec3 r;
+			if (what == 20) r = s->ndf(ld3(a, k));
+			else if (what == 23) r = s->fresnel(a[k]);
+			else return -2;
+			st3(out, k, r);
+		}
+		return what == 21 ? 1 : 3;
+	}
+	return -1;
+}

@@ -72,6 +72,8 @@ int main()
 	MEMBER(&microfacet::vp22, float_t (microfacet::*)(float_t, float_t, const vec3 &, const P &) const)
 	MEMBER(&microfacet::vndf, float_t (microfacet::*)(const vec3 &, const vec3 &, const P &) const)
 	MEMBER(&microfacet::supports_smith_vndf_sampling, bool (microfacet::*)() const)
+	MEMBER(&microfacet::qf2, float_t (microfacet::*)(float_t, const vec3 &) const)
+	MEMBER(&microfacet::qf3, float_t (microfacet::*)(float_t, const vec3 &, float_t) const)
 	MEMBER(&microfacet::set_shadow, void (microfacet::*)(bool))
 	MEMBER(&microfacet::set_fresnel, void (microfacet::*)(const fresnel::impl &))
 	MEMBER(&microfacet::get_shadow, int (microfacet::*)() const)
@@ -81,6 +83,14 @@ int main()
 	MEMBER(&radial::sigma_std_radial, float_t (radial::*)(float_t) const)
 	MEMBER(&radial::cdf_radial, float_t (radial::*)(float_t) const)
 	MEMBER(&radial::qf_radial, float_t (radial::*)(float_t) const)
+	MEMBER(&radial::qf2_radial, float_t (radial::*)(float_t, float_t, float_t) const)
+	MEMBER(&radial::qf3_radial, float_t (radial::*)(float_t, float_t) const)
+	MEMBER(&beckmann::qf1, float_t (beckmann::*)(float_t) const)
+	MEMBER(&beckmann::qf2_radial, float_t (beckmann::*)(float_t, float_t, float_t) const)
+	MEMBER(&beckmann::qf3_radial, float_t (beckmann::*)(float_t, float_t) const)
+	MEMBER(&ggx::qf1, float_t (ggx::*)(float_t) const)
+	MEMBER(&ggx::qf2_radial, float_t (ggx::*)(float_t, float_t, float_t) const)
+	MEMBER(&ggx::qf3_radial, float_t (ggx::*)(float_t, float_t) const)
 	MEMBER(&beckmann::params_to_lrep, void (*)(const P &, beckmann::lrep *))
 	MEMBER(&beckmann::lrep_to_params, void (*)(const beckmann::lrep &, P *))
 	MEMBER(&beckmann::lrep::operator+, beckmann::lrep (beckmann::lrep::*)(const beckmann::lrep &) const)
@@ -100,11 +110,24 @@ int main()
 	MEMBER(&tabular_anisotropic::fit_ggx_parameters, P (*)(const tabular_anisotropic &))
 	MEMBER(&tabular_anisotropic::get_p22v, const std::vector<float_t> &(tabular_anisotropic::*)(int *, int *) const)
 	MEMBER(&tabular_anisotropic::get_sigmav, const std::vector<float_t> &(tabular_anisotropic::*)(int *, int *) const)
+	MEMBER(&tabular_anisotropic::pdf1, float_t (tabular_anisotropic::*)(float_t) const)
+	MEMBER(&tabular_anisotropic::pdf2, float_t (tabular_anisotropic::*)(float_t, float_t) const)
+	MEMBER(&tabular_anisotropic::cdf1, float_t (tabular_anisotropic::*)(float_t) const)
+	MEMBER(&tabular_anisotropic::cdf2, float_t (tabular_anisotropic::*)(float_t, float_t) const)
+	MEMBER(&tabular_anisotropic::qf1, float_t (tabular_anisotropic::*)(float_t) const)
+	MEMBER(&tabular_anisotropic::qf2, float_t (tabular_anisotropic::*)(float_t, float_t) const)
 	// data-driven BRDFs (dj_brdf.h:126-146, 481-535): construction is by file / material name
 	MEMBER(&merl::eval, vec3 (merl::*)(const vec3 &, const vec3 &, const void *) const)
 	MEMBER(&utia::eval, vec3 (utia::*)(const vec3 &, const vec3 &, const void *) const)
 	MEMBER(&sgd::eval, vec3 (sgd::*)(const vec3 &, const vec3 &, const void *) const)
 	MEMBER(&abc::eval, vec3 (abc::*)(const vec3 &, const vec3 &, const void *) const)
+	MEMBER(&sgd::ndf, vec3 (sgd::*)(const vec3 &) const)
+	MEMBER(&sgd::gaf, vec3 (sgd::*)(const vec3 &, const vec3 &, const vec3 &) const)
+	MEMBER(&sgd::g1, vec3 (sgd::*)(const vec3 &) const)
+	MEMBER(&sgd::fresnel, vec3 (sgd::*)(float_t) const)
+	MEMBER(&abc::ndf, vec3 (abc::*)(const vec3 &) const)
+	MEMBER(&abc::gaf, float_t (abc::*)(const vec3 &, const vec3 &, const vec3 &) const)
+	MEMBER(&abc::fresnel, vec3 (abc::*)(float_t) const)
 	MEMBER(&sgd::get_fresnel, const fresnel::impl &(sgd::*)() const)
 	MEMBER(&abc::get_fresnel, const fresnel::impl &(abc::*)() const)
 	// vec3 (dj_brdf.h:62-71, 597-637)

@@ -7,6 +7,7 @@
 //          eval[n][3], sample[n][3], eval_scalar[3], alpha (beckmann, ggx)
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <vector>
 
 #include "dj_brdf.h" // include/compat: the reference's header name
@@ -71,6 +72,32 @@ int main(int argc, char **argv)
 		djb::tabular::fit_beckmann_parameters(tab).get_ellipse(&ab[0], &dummy, NULL);
 		djb::tabular::fit_ggx_parameters(tab).get_ellipse(&ab[1], &dummy, NULL);
 		put(fo, ab, sizeof ab);
+		// the scalar members behind sample / eval (dj_brdf.h:366-369, 384-389, 450-455, 506-509, 531-533), one call per item
+		const int nm = n < 64 ? n : 64;
+		djb::sgd sgd("gold-metallic-paint");
+		djb::abc abc("gold-metallic-paint");
+		djb::beckmann bplain;
+		djb::tabular_anisotropic ta(bplain, 8, 10);
+		for (int k = 0; k < nm; ++k) {
+			const float c = wo[k].z, sn = sqrtf(1.0f - c * c), u1 = u[2 * k], u2 = u[2 * k + 1];
+			float q[8];
+			q[0] = ggx.qf1(u1); q[1] = ggx.qf2_radial(u1, c, sn); q[2] = ggx.qf3_radial(u2, q[1]);
+			q[3] = beckmann.qf1(u1); q[4] = beckmann.qf2_radial(u1, c, sn); q[5] = beckmann.qf3_radial(u2, q[4]);
+			q[6] = abc.gaf(wi[k], wi[k], wo[k]);
+			q[7] = 0;
+			put(fo, q, sizeof q);
+			djb::vec3 v[7] = {sgd.ndf(wi[k]), sgd.gaf(wi[k], wi[k], wo[k]), sgd.g1(wo[k]), sgd.fresnel(c), abc.ndf(wi[k]), abc.fresnel(c),
+			                  djb::vec3(0)};
+			put(fo, v, sizeof v);
+			const float phi = 6.2f * u2, theta = 1.5f * u1;
+			float t[6] = {ta.pdf1(phi), ta.cdf1(phi), ta.qf1(u1), ta.pdf2(theta, phi), ta.cdf2(theta, phi), ta.qf2(u1, phi)};
+			put(fo, t, sizeof t);
+		}
+		int threw = 0;
+		try { ((const djb::microfacet &)ggx).qf2(0.5f, wo[0]); } catch (const djb::exc &) { ++threw; }
+		try { ((const djb::radial &)tab).qf2_radial(0.5f, 0.5f, 0.5f); } catch (const djb::exc &) { ++threw; }
+		float thr = (float)threw;
+		put(fo, &thr, 4);
 	} catch (const std::exception &e) {
 		fprintf(stderr, "%s\n", e.what());
 		return 1;

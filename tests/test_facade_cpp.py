@@ -133,6 +133,31 @@ def test_facade_matches_oracle(bins, port, precision):
     assert bits_equal(tsm, port.tabular_query("sample", fit, u, wo, None, nthreads=8)).all(axis=1).mean() >= 0.9995
     assert bits_equal(te0, tev[0]).all()
     assert np.allclose(tal, fit["alpha"], rtol=1e-6)
+    # the scalar members, one facade call per item, against the batched Python mirror of the same entry points (which
+    # tests/test_gpu_round2.py pins to the reference): same kernels, so the same bits
+    import dj_brdf_b200 as djb
+    nm = 64
+    rows = take(nm, 8 + 21 + 6)
+    q, v, t = rows[:, :8], rows[:, 8:29].reshape(nm, 7, 3), rows[:, 29:]
+    c = wo[:nm, 2].copy()
+    sn = np.sqrt(np.float32(1.0) - c * c).astype(np.float32)
+    u1, u2 = u[:nm, 0].copy(), u[:nm, 1].copy()
+    g, b = djb.ggx(), djb.beckmann()
+    sg, ab = djb.sgd("gold-metallic-paint"), djb.abc("gold-metallic-paint")
+    a, o = np.ascontiguousarray(wi[:nm]), np.ascontiguousarray(wo[:nm])
+    want_q = [g.qf1(u1), g.qf2_radial(u1, c, sn), g.qf3_radial(u2, q[:, 1].copy()), b.qf1(u1), b.qf2_radial(u1, c, sn),
+              b.qf3_radial(u2, q[:, 4].copy()), ab.gaf(a, a, o)]
+    for k, w in enumerate(want_q):
+        assert bits_equal(q[:, k], w).all(), ("scalar member", k)
+    want_v = [sg.ndf(a), sg.gaf(a, a, o), sg.g1(o), sg.fresnel_term(c), ab.ndf(a), ab.fresnel_term(c)]
+    for k, w in enumerate(want_v):
+        assert bits_equal(v[:, k], w).all(), ("vec3 member", k)
+    ta = djb.tabular_anisotropic(djb.beckmann(), 8, 10)
+    phi, theta = (np.float32(6.2) * u2).astype(np.float32), (np.float32(1.5) * u1).astype(np.float32)
+    want_t = [ta.pdf1(phi), ta.cdf1(phi), ta.qf1(u1), ta.pdf2(theta, phi), ta.cdf2(theta, phi), ta.qf2(u1, phi)]
+    for k, w in enumerate(want_t):
+        assert bits_equal(t[:, k], w).all(), ("table member", k)
+    assert take(1)[0] == 2.0, "microfacet::qf2 and radial::qf2_radial must throw djb::exc as in the reference"
     assert pos == raw.size
 
 

@@ -14,7 +14,7 @@ import pytest
 
 from oracle import api
 from tests import cases
-from tests.conftest import bits_equal
+from tests.conftest import bits_equal, rel_err
 from tests.test_gpu_parity import check_close, mk_brdf
 
 pytestmark = pytest.mark.gpu
@@ -251,3 +251,82 @@ def test_leanmap_half_rgba_mip_pyramid_bit_exact(djb, port, shape):
     w1, _ = port.nmap2leanmap(port.dmap2nmap(d.cpu().numpy(), 0.01), 1e-5, 25.0)
     for a, c in zip(djb.leanmap_half_mips(g1), port.leanmap_half_mips(w1)):
         assert np.array_equal(a.cpu().numpy().view(np.uint16), c.view(np.uint16))
+
+
+# ---- the remaining public scalar members (VERDICT r01 missing #5) against reference-generated golden vectors ---------------
+MEMBER_GOLDEN = Path(__file__).parent / "golden" / "member_golden.npz"
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_quantile_members_against_the_reference(djb, ndf):
+    """beckmann / ggx ::qf1, qf2_radial, qf3_radial (dj_brdf.h:366-369, 384-389) -- the pieces `sample` is made of."""
+    g = np.load(MEMBER_GOLDEN)
+    name = "ggx" if ndf == api.NDF_GGX else "beckmann"
+    b = (djb.ggx if ndf == api.NDF_GGX else djb.beckmann)()
+    floor = 1.0 if ndf == api.NDF_GGX else 0.999  # Beckmann's search: glibc powf / expf / logf re-run on the device
+    for what, got in (("qf1", b.qf1(g["q/u"])), ("qf2_radial", b.qf2_radial(g["q/u"], g["q/cos"], g["q/sin"])),
+                      ("qf3_radial", b.qf3_radial(g["q/u3"], g[f"q/{name}/qf2_radial"]))):
+        want = g[f"q/{name}/{what}"]
+        same = bits_equal(got, want)
+        assert same.mean() >= floor, (name, what, same.mean())
+        assert rel_err(got, want).max() <= 1e-3, (name, what)
+    with pytest.raises(djb.DjbError):  # microfacet::qf2 / qf3 throw in the reference (dj_brdf.h:1783-1791)
+        b.qf2(g["q/u"], g["a/i"])
+
+
+@pytest.mark.parametrize("name", ["gold-metallic-paint", "alum-bronze", "blue-fabric"])
+def test_sgd_abc_members_against_the_reference(djb, name):
+    """sgd ::ndf / gaf / g1 / fresnel and abc ::ndf / gaf / fresnel (dj_brdf.h:506-509, 531-533)."""
+    g = np.load(MEMBER_GOLDEN)
+    h, i, o, cs = g["a/h"], g["a/i"], g["a/o"], g["a/cos"]
+    s, a = djb.sgd(name), djb.abc(name)
+    for kind, m, whats in (("sgd", s, ("ndf", "gaf", "g1", "fresnel")), ("abc", a, ("ndf", "gaf", "fresnel"))):
+        for what in whats:
+            got = {"ndf": lambda: m.ndf(h), "gaf": lambda: m.gaf(h, i, o), "g1": lambda: m.g1(i),
+                   "fresnel": lambda: m.fresnel_term(cs)}[what]()
+            want = g[f"a/{kind}/{name}/{what}"]
+            assert got.shape == want.shape, (kind, what, got.shape, want.shape)
+            same = bits_equal(got, want)
+            assert same.mean() >= 0.99, (kind, what, same.mean())   # device double pow / exp / acos vs glibc: last-bit cases
+            assert rel_err(got, want).max() <= 1e-5, (kind, what)
+
+
+def test_tabular_anisotropic_table_members_against_the_reference(djb):
+    """tabular_anisotropic::pdf1 / cdf1 / qf1 / pdf2 / cdf2 / qf2 (dj_brdf.h:450-455, 2766-2824) on a handle built from the
+    reference's own p22 / sigma tables; arguments run past one period and past the horizon."""
+    g = np.load(MEMBER_GOLDEN)
+    er, ar = 14, 18
+    r = dict(m_p22=g["t/utia12/14x18/p22"], m_sigma=g["t/utia12/14x18/sigma"],
+             m_fresnel_points=np.ascontiguousarray(g["t/utia12/14x18/fresnel"]), residuals=np.zeros(4, np.float32),
+             beckmann=g["t/utia12/14x18/beckmann"], ggx=g["t/utia12/14x18/ggx"])
+    t = djb.tabular_anisotropic(None, er, ar, _result=r)
+    phi, theta, u = g["t/phi"], g["t/theta"], g["t/u"]
+    for what, got in (("pdf1", t.pdf1(phi)), ("cdf1", t.cdf1(phi)), ("qf1", t.qf1(u)), ("pdf2", t.pdf2(theta, phi)),
+                      ("cdf2", t.cdf2(theta, phi)), ("qf2", t.qf2(u, phi))):
+        want = g[f"t/utia12/14x18/{what}"]
+        same = bits_equal(got, want)
+        assert same.mean() >= 0.999, (what, same.mean(), np.abs(got - want).max())
+        assert np.abs(got - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max())), what
+
+
+def test_members_directly_against_the_unmodified_reference(djb, ref):
+    """The same members on fresh inputs, reference run on the spot (oracle/_ref travels to the GPU box)."""
+    n = 20_000
+    u = (api.uniforms(n, 530) * np.float32(0.99998) + np.float32(0.00001)).astype(np.float32)
+    c = (np.float32(1e-3) + np.float32(0.999) * api.uniforms(n, 531)).astype(np.float32)
+    s = np.sqrt(np.maximum(0.0, 1.0 - c.astype(np.float64) ** 2)).astype(np.float32)
+    for ndf, b, floor in ((api.NDF_GGX, djb.ggx(), 1.0), (api.NDF_BECKMANN, djb.beckmann(), 0.999)):
+        assert bits_equal(b.qf1(u), ref.member_query("qf1", u, ndf=ndf)).mean() >= floor
+        want = ref.member_query("qf2_radial", u, c, s, ndf=ndf)
+        assert bits_equal(b.qf2_radial(u, c, s), want).mean() >= floor
+        assert bits_equal(b.qf3_radial(u[::-1].copy(), want), ref.member_query("qf3_radial", u[::-1].copy(), want, ndf=ndf)).mean() >= floor
+    h, i, o = api.directions(n, 540), api.directions(n, 542), api.directions(n, 544)
+    name = "violet-acrylic"
+    m = djb.sgd(name)
+    for what, got, args in (("ndf", m.ndf(h), (h,)), ("gaf", m.gaf(h, i, o), (h, i, o)), ("g1", m.g1(o), (o,))):
+        want = ref.member_query(what, *args, sgd=name)
+        assert rel_err(got, want).max() <= 1e-5 and bits_equal(got, want).mean() >= 0.99, what
+    m = djb.abc(name)
+    for what, got, args in (("ndf", m.ndf(h), (h,)), ("gaf", m.gaf(h, i, o), (h, i, o))):
+        want = ref.member_query(what, *args, abc=name)
+        assert rel_err(got, want).max() <= 1e-5 and bits_equal(got, want).mean() >= 0.99, what

@@ -227,3 +227,17 @@ def test_microfacet_components_bit_identical(port, ref, ndf):
                 r = ref.component(what, ndf, P, *a, fresnel=f, shadow=shadow)
                 assert bits_equal(g, r).all(), (pname, shadow, what)
     assert bits_equal(port.component("sigma", ndf, None, wo), ref.component("sigma", ndf, None, wo)).all()
+
+
+def test_member_golden_matches_the_reference_run_now(ref):
+    """tests/golden/member_golden.npz (what the GPU box checks the scalar members against) is what the reference gives here."""
+    g = np.load(Path(__file__).parent / "golden" / "member_golden.npz")
+    for ndf, name in ((api.NDF_GGX, "ggx"), (api.NDF_BECKMANN, "beckmann")):
+        assert bits_equal(ref.member_query("qf1", g["q/u"], ndf=ndf), g[f"q/{name}/qf1"]).all()
+        assert bits_equal(ref.member_query("qf2_radial", g["q/u"], g["q/cos"], g["q/sin"], ndf=ndf), g[f"q/{name}/qf2_radial"]).all()
+    for name in ("gold-metallic-paint", "blue-fabric"):
+        assert bits_equal(ref.member_query("gaf", g["a/h"], g["a/i"], g["a/o"], sgd=name), g[f"a/sgd/{name}/gaf"]).all()
+        assert bits_equal(ref.member_query("ndf", g["a/h"], abc=name), g[f"a/abc/{name}/ndf"]).all()
+    ro = api.RefOracle(opened=True)
+    src = api.Source.utia(cases.random_utia_table(12))
+    assert bits_equal(ro.tabular_aniso_lookup(src, 14, 18, "qf2", g["t/u"], g["t/phi"]), g["t/utia12/14x18/qf2"]).all()
