@@ -140,8 +140,10 @@ MEMBER_NDF, MEMBER_GAF, MEMBER_G1, MEMBER_FRESNEL = 20, 21, 22, 23
 
 
 def set_precision(mode):
-    """Precision of microfacet eval / evalp / pdf (djb200_set_precision): "1e-5" (default: within 1e-5 relative of the reference's
-    floats, identical zero pattern, ~2x faster) or "bits" (the reference's rounded floats)."""
+    """Precision of microfacet eval / evalp / pdf / sample (djb200_set_precision): "1e-5" (default: eval / pdf within 1e-5 relative of
+    the reference's floats with the identical zero pattern; sampled directions within 1e-5 except where Beckmann's quantile search
+    stops one trip apart from the reference's -- include/djb200.h has the measured figures; ~2x faster) or "bits" (the reference's
+    rounded floats)."""
     code = {"bits": PRECISION_REFERENCE_BITS, "1e-5": PRECISION_1E5, 0: 0, 1: 1}[mode]
     check(load().djb200_set_precision(C.c_int(code)))
 

@@ -870,7 +870,9 @@ DJB_DEV float fast_gaf(const Params &p, bool shadow, V3 i, V3 o, float &rsg_o_ou
 	if (!shadow) return g1o;
 	const float g1i = dot(i, n) > 0.0f ? i.z * mufu_rcp(fast_sigma<NDF>(p, i)) : 0.0f;
 	const float t = g1i * g1o, d = g1i + g1o - t;
-	ill = d < 0.9f * fmaxf(g1i, g1o); // cancellation (needs a G1 > 1); for G1 <= 1 the denominator is >= both terms
+	// cancellation (needs a G1 > 1): the quotient amplifies the G1s' relative errors (a few 1e-7 here) by (g1i + g1o + t) / d;
+	// up to 8x stays well inside 1e-5.  For G1 <= 1 the denominator is >= both terms, so (g1i + g1o + t) / d <= 3: never ill
+	ill = d < 0.125f * (g1i + g1o + t);
 	return t > 0.0f ? t * mufu_rcp(d) : 0.0f;
 }
 // microfacet::ndf (dj_brdf.h:1559-1587) from the exact r2; Beckmann: r2 <= 78 (the caller sends the tail to the exact tier)
@@ -891,7 +893,7 @@ DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &
 	float rsg_o;
 	bool ill;
 	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
-	if (ill) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	if (__any_sync(__activemask(), ill)) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	if (G > 0.0f) {
 		const float num = fast_ndf_from_r2<NDF>(m, c, r2) * G;
 		const float k = c.den_ok ? num * c.rcp_den : __fdiv_rn(num, c.den);
@@ -906,20 +908,30 @@ DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, cons
 	float rsg_o;
 	bool ill;
 	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
-	if (ill) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	if (__any_sync(__activemask(), ill)) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	if (G > 0.0f) {
 		const float v = c.kh > 0.0f ? (c.kh * fast_ndf_from_r2<NDF>(m, c, r2)) * rsg_o : 0.0f;
 		return c.den_ok ? v * c.rcp_den : __fdiv_rn(v, c.den);
 	}
 	return 0.0f;
 }
-// one (pair, material) query of the 1e-5 tier; Beckmann's underflow tail takes the exact functions
+// Beckmann's underflow tail (78 < r2 <= 103.5) takes the exact functions.  In the kernels that do not compact their work
+// (PER_PAIR / LEAN-texel params: one query per lane) a warp with ONE tail lane would run the fast path for 31 lanes and then
+// the exact path for one: when any converged lane is in the tail, the whole warp takes the exact path instead (both tiers
+// are within 1e-5 of the reference, so which one a lane runs is immaterial); r2 > 103.5 (D == 0) is the exact tier's
+// cheap early-out either way.
+DJB_DEV bool fast_beck_exact_vote(float r2)
+{
+	const bool beyond = !(r2 <= FAST_BECK_R2_MAX);
+	return __any_sync(__activemask(), beyond && r2 <= 103.5f) || beyond;
+}
+// one (pair, material) query of the 1e-5 tier
 template <int NDF, int FK, int OP>
 DJB_DEV V3 fast_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)
 {
 	if (!c.facing) return c.den > 0.0f ? lean_zero<OP>(c) : lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
 	const float r2 = lean_ndf_r2(m, c);
-	if (NDF == NDF_BECKMANN && !(r2 <= FAST_BECK_R2_MAX)) return lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
+	if (NDF == NDF_BECKMANN && fast_beck_exact_vote(r2)) return lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
 	return fast_evalp_tail<NDF, FK, OP>(T, m, f, shadow, c, r2);
 }
 template <int NDF>
@@ -927,8 +939,164 @@ DJB_DEV float fast_pdf(const float2 *T, const ParamsX &m, bool shadow, const Pai
 {
 	if (!c.facing) return c.den > 0.0f ? 0.0f : lean_pdf<NDF>(T, m, shadow, c);
 	const float r2 = lean_ndf_r2(m, c);
-	if (NDF == NDF_BECKMANN && !(r2 <= FAST_BECK_R2_MAX)) return lean_pdf<NDF>(T, m, shadow, c);
+	if (NDF == NDF_BECKMANN && fast_beck_exact_vote(r2)) return lean_pdf<NDF>(T, m, shadow, c);
 	return fast_pdf_tail<NDF>(T, m, shadow, c, r2);
+}
+
+// =====================================================================================================================
+// The 1e-5 tier of sample (the same switch as eval / evalp / pdf above).  The exact tier re-runs glibc's logf / powf / expf
+// in double inside the quantile search of beckmann::qf2_radial so that every trip reproduces the reference's floats; this
+// tier evaluates the same search, trip for trip, with MUFU.LG2 / EX2 / RCP and FMAs (errors of a few 1e-7 per step).
+// What stays exact, because the reference's own arithmetic is ill-conditioned there:
+//   * the warped view vector o_std = normalize(a, b, c) and with it the gate o_std.z > 0 (the (0, 0, 1) pattern is
+//     identical), cos_theta_k and sin_theta_k = float(sqrt(1 - cos^2)) (a 1-ulp change of cos_theta_k near normal incidence
+//     moves sin_theta_k by per cent);
+//   * GGX: sin_theta = float(u (1 + cos_theta_k) - 1) and 1 - sin_theta^2 (cancellation for u -> 0, 1);
+//   * everything that depends on u2 alone (computed once per pair by lean_sample_u2).
+// The search stops at the reference's own criterion |CDF(b) - u| < 1e-5; where the two tiers' values straddle it, this tier
+// makes one trip more or less than the reference and the sample differs by the reference's own convergence tolerance.
+// A result that is not finite (a division by an exact zero, a search that met b = +-1) is recomputed by the exact tier.
+// Measured against the reference / the exact tier: tests/test_gpu_parity.py::test_fast_tier_sample_*.
+DJB_DEV float mufu_lg2(float x)
+{
+	float y;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+// 1 / sqrt(x), MUFU.RSQ + one Newton step (relative error ~1e-7)
+DJB_DEV float rsq_fast(float x)
+{
+	const float r = mufu_rsq(x);
+	return __fmaf_rn(0.5f * r, __fmaf_rn(-(x * r), r, 1.0f), r);
+}
+// djb::erfinv (Giles), dj_brdf.h:691-721, with w = -ln((1 - u)(1 + u)) from MUFU.LG2
+DJB_DEV float erfinv_fast(float u)
+{
+	float w = mufu_lg2((1.0f - u) * (1.0f + u)) * -0x1.62e430p-1f;
+	float p;
+	if (w < 5.0f) {
+		w -= 2.5f;
+		p = 2.81022636e-08f;
+		p = __fmaf_rn(p, w, 3.43273939e-07f);
+		p = __fmaf_rn(p, w, -3.5233877e-06f);
+		p = __fmaf_rn(p, w, -4.39150654e-06f);
+		p = __fmaf_rn(p, w, 0.00021858087f);
+		p = __fmaf_rn(p, w, -0.00125372503f);
+		p = __fmaf_rn(p, w, -0.00417768164f);
+		p = __fmaf_rn(p, w, 0.246640727f);
+		p = __fmaf_rn(p, w, 1.50140941f);
+	} else {
+		w = w * mufu_rsq(w) - 3.0f;
+		p = -0.000200214257f;
+		p = __fmaf_rn(p, w, 0.000100950558f);
+		p = __fmaf_rn(p, w, 0.00134934322f);
+		p = __fmaf_rn(p, w, -0.00367342844f);
+		p = __fmaf_rn(p, w, 0.00573950773f);
+		p = __fmaf_rn(p, w, -0.0076224613f);
+		p = __fmaf_rn(p, w, 0.00943887047f);
+		p = __fmaf_rn(p, w, 1.00167406f);
+		p = __fmaf_rn(p, w, 2.83297682f);
+	}
+	return p * u;
+}
+// beckmann::qf2_radial, dj_brdf.h:1897-1952; ck > 0, sk >= 0
+DJB_DEV float beckmann_qf2_fast(float u, float ck, float sk)
+{
+	const float SPI = 0x1.20dd76p-1f; // float(1 / sqrt(pi))
+	const float cot = ck * mufu_rcp(sk), tan_k = sk * mufu_rcp(ck); // sk == 0: cot = +inf, handled by the clamps below
+	const float xx = -cot * cot;
+	const float e = exp_neg_fast(fmaxf(xx, -87.0f));
+	float c = 1.0f; // djb::erf(cot): exactly 1 from cot = 3.92 on (exact tier, beckmann_qf2_lean)
+	if (xx > -16.0f) {
+		const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
+		const float d = __fmaf_rn(0.3275911f, cot, 1.0f);
+		float t = mufu_rcp(d);
+		t = __fmaf_rn(t, __fmaf_rn(-d, t, 1.0f), t);
+		float poly = __fmaf_rn(a5, t, a4);
+		poly = __fmaf_rn(poly, t, a3);
+		poly = __fmaf_rn(poly, t, a2);
+		poly = __fmaf_rn(poly, t, a1);
+		c = __fmaf_rn(-(poly * t), e, 1.0f);
+	}
+	const float B = SPI * tan_k;
+	const float normalization = mufu_rcp(__fmaf_rn(B, e, 1.0f + c));
+	float a = -1.0f;
+	u = fmaxf(u, 1e-6f);
+	const float fit = __fmaf_rn(ck, __fmaf_rn(ck, __fmaf_rn(-0.0594f, ck, 0.4265f), -0.876f), 1.0f);
+	float b = __fmaf_rn(-(1.0f + c), mufu_ex2(fit * mufu_lg2(1.0f - u)), c);
+	float ie = 0.0f;
+	bool converged = false;
+	int it = 0;
+	while (++it < 10) {
+		if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+		ie = erfinv_fast(b);
+		const float ex = exp_neg_fast(-ie * ie);
+		const float value = __fmaf_rn(normalization, __fmaf_rn(B, ex, 1.0f + b), -u);
+		const float derivative = normalization * __fmaf_rn(-ie, tan_k, 1.0f);
+		if (fabsf(value) < 1e-5f) { converged = true; break; }
+		if (value > 0.0f) c = b; else a = b;
+		b = __fmaf_rn(-value, mufu_rcp(derivative), b);
+	}
+	const float bm = fmaxf(-0.9999f, b);
+	if (converged && bm == b) return ie;
+	return erfinv_fast(bm);
+}
+// ggx::qf2_radial, dj_brdf.h:2089-2119: the reference's four tangent / cotangent forms are one function,
+// -(sin cos_k + cos sin_k) / (cos cos_k - sin sin_k)
+DJB_DEV float ggx_qf2_fast(float u, float ck, float sk)
+{
+	const float wh = 1.0f + ck, wl = ck - (wh - 1.0f);
+	const float pr = u * wh, pe = __fmaf_rn(u, wh, -pr) + u * wl;
+	const FF d = two_sum(pr, -1.0f);
+	const float st = d.h + (d.l + pe); // float(u (1.0 + ck) - 1.0), as the exact tier forms it
+	const float cc = st * st;
+	const float vh = 1.0f - cc, vl = (1.0f - vh) - cc; // 1 - st^2 exactly (|st| < 1: u is clamped to [1e-5, 0.99999])
+	const float y = mufu_rsq(vh);
+	const float ct = __fmaf_rn(vl, 0.5f * y, vh * y);
+	const float num = __fmaf_rn(st, ck, ct * sk), den = __fmaf_rn(ct, ck, -(st * sk));
+	return -num * mufu_rcp(den);
+}
+template <int NDF>
+static __device__ __noinline__ V3 lean_sample_redo(const float2 *T, GlfCtx GT, Params p, float u1, SampleU2 su2, V3 o)
+{
+	return lean_sample<NDF>(T, GT, p, u1, su2, o);
+}
+// microfacet::sample, dj_brdf.h:1669-1709; u1 clamped, su2 = lean_sample_u2(clamped u2)
+template <int NDF>
+DJB_DEV V3 fast_sample(const float2 *T, const GlfCtx &GT, const Params &p, float u1, SampleU2 su2, V3 o)
+{
+	const float oyay = o.y * p.ay;
+	const float a = o.x * p.ax + oyay * p.rho;
+	const float b = oyay * p.srho;
+	const float c = o.z - o.x * p.tx - o.y * p.ty;
+	const V3 os = normalize(mk(a, b, c)); // exact: the gate and (cos, sin) of the view angle
+	if (!(os.z > 0.0f)) return mk(0.f, 0.f, 1.f);
+	const float ck = os.z;
+	const float sk = ck < 1.0f ? sqrt_1m_sq(ck) : 0.0f;
+	float tx, ty;
+	if (NDF == NDF_GGX) {
+		tx = ggx_qf2_fast(u1, ck, sk);
+		const float v = __fmaf_rn(tx, tx, 1.0f);
+		ty = su2.a * (v * mufu_rsq(v)) * su2.b; // S sqrt(1 + tx^2) (pn / qn)
+	} else {
+		tx = beckmann_qf2_fast(u1, ck, sk);
+		ty = su2.a;
+	}
+	float xs = tx, ys = ty;
+	if (sk != 0.0f) {
+		const float nrm = mufu_rsq(__fmaf_rn(os.x, os.x, os.y * os.y));
+		const float cp = os.x * nrm, sp = os.y * nrm;
+		xs = __fmaf_rn(cp, tx, -(sp * ty));
+		ys = __fmaf_rn(sp, tx, cp * ty);
+	}
+	const float txh = __fmaf_rn(p.ax, xs, p.tx);
+	const float tyh = __fmaf_rn(p.ay, __fmaf_rn(p.rho, xs, p.srho * ys), p.ty);
+	const float r = rsq_fast(__fmaf_rn(txh, txh, __fmaf_rn(tyh, tyh, 1.0f)));
+	const V3 h = mk(-txh * r, -tyh * r, r);
+	const float k = 2.0f * __fmaf_rn(o.x, h.x, __fmaf_rn(o.y, h.y, o.z * h.z));
+	const V3 i = mk(__fmaf_rn(k, h.x, -o.x), __fmaf_rn(k, h.y, -o.y), __fmaf_rn(k, h.z, -o.z));
+	if (!(fabsf(i.x) + fabsf(i.y) + fabsf(i.z) < 1e30f)) return lean_sample_redo<NDF>(T, GT, p, u1, su2, o);
+	return i;
 }
 
 } // namespace djb200

@@ -198,13 +198,13 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A
 #ifndef DJB200_BSAMPLE_MINB
 #define DJB200_BSAMPLE_MINB 5
 #endif
-constexpr int lean_min_blocks(int ndf, int op, int psrc)
+constexpr int lean_min_blocks(int ndf, int op, int psrc, bool fast)
 {
-	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */) ? DJB200_BSAMPLE_MINB : 1;
+	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */ && !fast) ? DJB200_BSAMPLE_MINB : 1;
 }
 
 template <int NDF, int FK, int OP, int PSRC, bool FAST>
-__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf_lean_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC, FAST)) mf_lean_kernel(MfKernelArgs A)
 {
 	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
 	constexpr bool PERPAIR = PSRC != PSRC_BROADCAST;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC)) mf
 			if (OP == OP_PDF) {
 				A.out0[slot] = FAST ? fast_pdf<NDF>(s_exp2, mx, shadow, c) : lean_pdf<NDF>(s_exp2, mx, shadow, c);
 			} else if (OP == OP_SAMPLE) {
-				st3(A.out0, slot, lean_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o));
+				st3(A.out0, slot, FAST ? fast_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o) : lean_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o));
 			} else if (OP == OP_EVALP_IS) {
 				V3 iv;
 				float pdf;
@@ -454,11 +454,15 @@ static void launch_lean_tier(const MfKernelArgs &A, long long want, cudaStream_t
 	const long long cap = lean_grid_cap<NDF, FK, OP, PSRC, FAST>();
 	mf_lean_kernel<NDF, FK, OP, PSRC, FAST><<<(int)(want < cap ? want : cap), MF_THREADS, 0, st>>>(A);
 }
-// eval / evalp / pdf have the two tiers; sampling only the exact one
+// eval / evalp / pdf / sample have the two tiers; evalp_is only the exact one
 template <int NDF, int FK, int OP, int PSRC>
 static void launch_lean(const MfKernelArgs &A, long long want, cudaStream_t st)
 {
-	constexpr bool has_fast = OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF;
+	// Beckmann eval / evalp / pdf on LEAN-texel params stay on the exact tier: those lobes are off-centre by construction, where
+	// the reference's G is ill-conditioned often enough (grazing directions opposite to the tilt: G1 > 1) that most warps
+	// would run the fast G first and the exact one after it (measured on bench.py's lean_shading leg: 2.48 ms against 2.01)
+	constexpr bool exact_only = NDF == NDF_BECKMANN && PSRC == PSRC_LEAN && OP != OP_SAMPLE;
+	constexpr bool has_fast = (OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF || OP == OP_SAMPLE) && !exact_only;
 	if constexpr (has_fast) {
 		if (g_fast_tier.load(std::memory_order_relaxed) != 0) {
 			launch_lean_tier<NDF, FK, OP, PSRC, true>(A, want, st);

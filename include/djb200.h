@@ -104,14 +104,21 @@ DJB200_API uint64_t djb200_kernel_launch_count(void);
  * calling thread's buffers (they are also freed when the thread exits) */
 DJB200_API djb200_status djb200_release_cache(void);
 
-/* Precision of microfacet eval / evalp / pdf (ideal and Schlick Fresnel terms; process-wide, read at every launch).
- *   DJB200_PRECISION_1E5 (default): within 1e-5 relative of the reference header's float results, identical zero / NaN pattern
- *     (the tolerance BASELINE.json's north_star states): MUFU reciprocals / exp2 and fused multiply-adds instead of correctly
+/* Precision of microfacet eval / evalp / pdf / sample (ideal and Schlick Fresnel terms; process-wide, read at every launch).
+ *   DJB200_PRECISION_1E5 (default):
+ *     eval / evalp / pdf within 1e-5 relative of the reference header's float results, identical zero / NaN pattern (the
+ *     tolerance BASELINE.json's north_star states): MUFU reciprocals / exp2 and fused multiply-adds instead of correctly
  *     rounded divisions, square roots and a float-float exponential -- about 2x the throughput.  Measured worst relative
- *     difference against the reference's floats over 3.2e8 results per query: DESIGN.md section 3.
+ *     difference against the reference's floats over 3.2e8 results per query: 2.0e-6.
+ *     sample: the same algorithm, trip for trip, with MUFU log2 / exp2 / reciprocals; the (0, 0, 1) pattern is identical.
+ *     GGX directions are within 1e-5 per component of the reference's (measured maximum 5.3e-6 over 3.2e8 samples).  Beckmann:
+ *     median difference 6e-8; the quantile search of dj_brdf.h:1897-1952 stops at |CDF(b) - u| < 1e-5, and where the two
+ *     evaluations straddle that threshold the search makes one trip more or less than the reference's, so a sample can move by
+ *     the reference's own convergence tolerance: 2.2e-4 of the samples differ by more than 1e-5, 4.4e-6 by more than 1e-4.
  *   DJB200_PRECISION_REFERENCE_BITS: every query reproduces the reference's rounded floats (bit-identical on >= 99.99 % of
  *     results; the remainder are double-rounding ties of a device libm call).  Also selected by DJB200_PRECISION=bits in the
- *     environment.  sample / evalp_is, the table BRDFs, the fits and the maps always run at this level. */
+ *     environment.  evalp_is, Beckmann queries on LEAN-texel params, the table BRDFs, the fits and the maps always run at this
+ *     level. */
 enum { DJB200_PRECISION_REFERENCE_BITS = 0, DJB200_PRECISION_1E5 = 1 };
 DJB200_API djb200_status djb200_set_precision(int mode);
 DJB200_API int djb200_get_precision(void);

@@ -112,8 +112,13 @@ def test_facade_matches_oracle(bins, port, precision):
         want = port.eval(ndf, P, wi, wo, fr)
         assert rel_err(ev, want).max() <= 1e-5 and np.array_equal(ev == 0, want == 0)
         assert rel_err(pdf, port.pdf(ndf, P, wi, wo, fr)).max() <= 1e-5
-        same = bits_equal(smp, port.sample(ndf, P, u, wo)).all(axis=1).mean()
-        assert same >= (0.9999 if ndf == api.NDF_GGX else 0.97)
+        wsm = port.sample(ndf, P, u, wo)
+        if precision == "bits":
+            same = bits_equal(smp, wsm).all(axis=1).mean()
+            assert same >= (0.9999 if ndf == api.NDF_GGX else 0.999)
+        else:  # the 1e-5 tier of sample: tests/test_gpu_parity.py::test_fast_tier_sample_*
+            err = np.abs(smp.astype(np.float64) - wsm).max(axis=1)
+            assert (err <= 1e-5).mean() >= (1.0 if ndf == api.NDF_GGX else 0.999) and err.max() <= 2e-2
         assert bits_equal(sc, ev[:16]).all(), "scalar virtual calls must equal the batch"
         for m in range(2):
             assert rel_err(ev2[m], port.eval(ndf, two[m], wi, wo, fr)).max() <= 1e-5

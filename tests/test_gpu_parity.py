@@ -534,3 +534,69 @@ def test_fast_tier_vs_exact_tier_at_scale(djb, ndf):
     finally:
         djb.set_precision("bits")
     print(f"1e-5 tier vs exact tier, {ndf}: worst relative difference per query {report}")
+
+
+# ---- the 1e-5 tier of sample ---------------------------------------------------------------------------------------------
+# The sampled direction is compared component-wise (absolute: unit vectors).  GGX: every sample within 1e-5.  Beckmann: the
+# quantile search stops at the reference's own test |CDF(b) - u| < 1e-5; where the two tiers' values straddle that threshold the
+# fast tier makes one trip more or less and the sample moves by the reference's convergence tolerance -- measured 2.2e-4 of the
+# samples beyond 1e-5, 4.4e-6 beyond 1e-4 (3.2e8 samples, profiles/r02_g_fast_sample.md).  The (0, 0, 1) fallback pattern
+# (o_std.z <= 0) is identical: the gate is formed by the exact tier's operations.
+def sample_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    up = np.array([0.0, 0.0, 1.0])
+    assert np.array_equal((got == up).all(axis=-1), (want == up).all(axis=-1)), "the (0, 0, 1) pattern differs"
+    assert not np.isnan(got).any()
+    return np.abs(got - want).max(axis=-1)
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+@pytest.mark.parametrize("pname", ["iso0.1", "iso0.5", "aniso", "aniso2", "offcentre", "standard"])
+def test_fast_tier_sample_against_oracle(tier_1e5, port, ndf, pname):
+    djb = tier_1e5
+    _, wo, u = cases.pairs(cases.N_PARITY)
+    _, ewo, eu = cases.edge_pairs()
+    wo, u = np.concatenate([wo, ewo]), np.concatenate([u, eu])
+    P = cases.param_sets(port)[pname]
+    b = mk_brdf(djb, ndf, api.Fresnel.ideal())
+    err = sample_err(b.sample(u, wo, P), port.sample(ndf, P, u, wo))
+    if ndf == api.NDF_GGX:
+        assert err.max() <= 1e-5, (pname, err.max())
+    else:
+        assert (err <= 1e-5).mean() >= 0.999 and (err <= 1e-4).mean() >= 0.9999 and err.max() <= 2e-2, \
+            (pname, (err <= 1e-5).mean(), (err <= 1e-4).mean(), err.max())
+    assert np.median(err) <= 2.5e-7
+
+
+@pytest.mark.parametrize("ndf", ["ggx", "beckmann"])
+def test_fast_tier_sample_vs_exact_tier_at_scale(djb, port, ndf):
+    """2e7 pairs x 16 materials (one of them off-centre) = 3.2e8 samples per distribution, the 1e-5 tier against the exact tier."""
+    import torch
+    n = 20_000_000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    z = 1.0 - 0.999 * torch.rand(n, device="cuda", generator=g)
+    ph = 6.283185307179586 * torch.rand(n, device="cuda", generator=g)
+    r = torch.sqrt(torch.clamp(1 - z * z, min=0))
+    wo = torch.stack([r * torch.cos(ph), r * torch.sin(ph), z], 1).contiguous()
+    u = torch.rand(n, 2, device="cuda", generator=g)
+    mats = cases.c2_materials(port)
+    mats[15] = djb.params.pdfparams(0.3, 0.2, 0.4, 0.1, -0.2)
+    b = (djb.ggx if ndf == "ggx" else djb.beckmann)()
+    try:
+        djb.set_precision("1e-5")
+        fast = b.sample(u, wo, mats)
+        djb.set_precision("bits")
+        exact = b.sample(u, wo, mats)
+    finally:
+        djb.set_precision("bits")
+    assert not torch.isnan(fast).any()
+    up = torch.tensor([0.0, 0.0, 1.0], device="cuda")
+    assert torch.equal((fast == up).all(-1), (exact == up).all(-1)), "the (0, 0, 1) pattern differs"
+    d = (fast - exact).abs().amax(dim=-1).reshape(-1)
+    f5, f4, worst = (d <= 1e-5).double().mean().item(), (d <= 1e-4).double().mean().item(), d.max().item()
+    print(f"1e-5 tier sample vs exact tier, {ndf}: within 1e-5 {f5:.7f}, within 1e-4 {f4:.7f}, max {worst:.3e}, mean {d.double().mean().item():.2e}")
+    if ndf == "ggx":
+        assert worst <= 1e-5
+    else:
+        assert f5 >= 0.9995 and f4 >= 0.99998 and worst <= 5e-2
+    assert d.double().mean().item() <= 3e-7

@@ -120,15 +120,20 @@ def _chi2_sample_vs_pdf(b, P, wo, n=1 << 20, nz=24, nphi=48, sub=12, seed=0):
     return stat, dof, float(stats.chi2.sf(stat, dof)), float(obs[~gated].sum() / n), float(exp[~gated].sum() / n)
 
 
+@pytest.mark.parametrize("tier", ["bits", "1e-5"])
 @pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
 @pytest.mark.parametrize("case", ["iso", "aniso", "offcentre"])
-def test_sample_follows_pdf_chi_square(djb, ndf, case):
+def test_sample_follows_pdf_chi_square(djb, ndf, case, tier):
     cls = djb.ggx if ndf == api.NDF_GGX else djb.beckmann
     b = cls()
     P = {"iso": djb.params.isotropic(0.35), "aniso": djb.params.elliptic(0.25, 0.6, 0.7),
          "offcentre": djb.params.pdfparams(0.4, 0.3, 0.3, 0.1, -0.15)}[case]
     wo = np.array([np.sin(0.7) * np.cos(0.4), np.sin(0.7) * np.sin(0.4), np.cos(0.7)], np.float32)
-    stat, dof, p, mass_obs, mass_exp = _chi2_sample_vs_pdf(b, P, wo)
+    try:
+        djb.set_precision(tier)  # both tiers of sample and pdf
+        stat, dof, p, mass_obs, mass_exp = _chi2_sample_vs_pdf(b, P, wo)
+    finally:
+        djb.set_precision("bits")
     # the binned mass and the integral of the pdf over the upper hemisphere agree, and the histogram is a plausible draw
     assert abs(mass_obs - mass_exp) < 2e-3, (mass_obs, mass_exp)
     assert p > 1e-4, f"chi2 = {stat:.1f} on {dof} cells, p = {p:.2e}"
