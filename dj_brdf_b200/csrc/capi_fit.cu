@@ -164,6 +164,17 @@ static djb200_status fit_tabular_device(const djb200_source *sources, int32_t n_
 	return DJB200_OK;
 }
 
+djb200_status djb200_debug_fit_phase_clocks(int64_t out_clocks[10])
+{
+	if (!out_clocks) return fail(DJB200_ERR_INVALID_ARGUMENT, "NULL argument");
+	long long c[10];
+	cudaError_t e = cudaDeviceSynchronize();
+	if (e == cudaSuccess) e = fit_phase_clocks(c);
+	if (e != cudaSuccess) return cuda_fail(e, "fit_phase_clocks");
+	for (int k = 0; k < 10; ++k) out_clocks[k] = (int64_t)c[k];
+	return DJB200_OK;
+}
+
 int64_t djb200_fit_tabular_packed_floats(int32_t n_sources, int32_t res)
 {
 	return n_sources < 0 || res < 0 ? 0 : (int64_t)n_sources * ((int64_t)7 * res + 2);

@@ -125,6 +125,7 @@ cudaError_t launch_microfacet_component(int ndf, int shadow, int fresnel_kind, c
 // fits (kernels_fit.cu)
 struct FitSourceDev;
 size_t fit_tabular_smem_bytes(int res);
+cudaError_t fit_phase_clocks(long long out[10]); // SM clock at the phase boundaries of material 0 of the last isotropic fit
 cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
                                double *K_ws, float4 *fres_ws, float *p22, float *sigma, float *cdf, float *qf,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st);

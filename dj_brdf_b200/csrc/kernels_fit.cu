@@ -43,37 +43,63 @@ struct IsoFitArgs {
 //   float scan[8 * cnt]
 //   float grid[SIG_NPHI * SIG_NTHETA]      the NDF over the sigma quadrature nodes
 //   int   fr_count[cnt], fr_offset[cnt + 1]  trip counts of the Fresnel loops
-static size_t iso_smem_bytes(int res)
+// then: double gsp_d[SIG_NPHI], gcp_d[SIG_NPHI] (sincos of the azimuths: the vec3(theta, phi) of the NDF grid), double ck_d[cnt],
+// float sk_f[cnt] (per-view-angle constants of compute_sigma), and, when it fits (iso_smem_plan), double Ks[cnt * cnt], the
+// kernel matrix (63 KB at res 90).  The kernel lays the doubles out first, then the floats / ints: every pointer is plain
+// arithmetic on the shared base.
+static size_t iso_smem_base(int res)
 {
 	size_t cnt = res - 1;
-	return sizeof(double) * (2 * cnt + SIG_NPHI + SIG_NTHETA) +
+	return sizeof(double) * (2 * cnt + SIG_NPHI + SIG_NTHETA + 2 * SIG_NPHI + cnt) +
 	       sizeof(float) * (3 * (size_t)res + 4 * cnt + MAX_PHI_STEPS + 2 * NORM_NTHETA + 2 * SIG_NTHETA + 8 * cnt + 8 +
-	                        SIG_NPHI * SIG_NTHETA) +
+	                        SIG_NPHI * SIG_NTHETA + cnt) +
 	       sizeof(int) * (2 * cnt + 2);
 }
+struct IsoSmemPlan { size_t bytes; int k_in_smem; };
+static IsoSmemPlan iso_smem_plan(int res)
+{
+	const size_t cnt = res - 1, limit = 227 * 1024, kmat = sizeof(double) * cnt * cnt;
+	IsoSmemPlan p;
+	p.bytes = iso_smem_base(res) + 16;
+	p.k_in_smem = p.bytes + kmat <= limit;
+	if (p.k_in_smem) p.bytes += kmat;
+	return p;
+}
+static size_t iso_smem_bytes(int res) { return iso_smem_plan(res).bytes; }
 
+// SM clock at the phase boundaries of material 0's CTA (djb200_debug_fit_phase_clocks): rows | matrix | iterations | normalise |
+// NDF grid | sigma | Fresnel ratios | Fresnel sums + cdf | qf + parameters
+__device__ long long g_fit_phase_clock[10];
+#define FIT_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_fit_phase_clock[k] = clock64(); } while (0)
+
+template <bool K_SMEM>
 __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 {
 	extern __shared__ double smem_d[];
 	const int res = A.res, cnt = res - 1, tid = threadIdx.x, nt = blockDim.x, mat = blockIdx.x;
 	double *v0 = smem_d, *v1 = v0 + cnt, *cphi_d = v1 + cnt, *cth_d = cphi_d + SIG_NPHI;
-	float *s_p22 = reinterpret_cast<float *>(cth_d + SIG_NTHETA);
+	double *gsp_d = cth_d + SIG_NTHETA, *gcp_d = gsp_d + SIG_NPHI, *ck_d = gcp_d + SIG_NPHI;
+	double *Ks = ck_d + cnt; // cnt * cnt doubles when K_SMEM
+	float *s_p22 = reinterpret_cast<float *>(Ks + (K_SMEM ? cnt * cnt : 0));
 	float *s_sigma = s_p22 + res, *s_cdf = s_sigma + res;
 	float *row_theta = s_cdf + res, *row_tan = row_theta + cnt, *row_cos = row_tan + cnt, *row_kji = row_cos + cnt;
 	float *cosphi = row_kji + cnt, *terms = cosphi + MAX_PHI_STEPS, *sth = terms + 2 * NORM_NTHETA, *ui = sth + SIG_NTHETA;
 	float *scan = ui + SIG_NTHETA;
 	float *grid = scan + 8 * cnt;
 	int *fr_count = reinterpret_cast<int *>(grid + SIG_NPHI * SIG_NTHETA), *fr_offset = fr_count + cnt;
+	float *sk_f = reinterpret_cast<float *>(fr_offset + cnt + 1);
 	__shared__ int s_nphi;
 	__shared__ double s_red[3][FIT_THREADS / 32];
 	__shared__ float s_scale;
 
 	const FitSourceDev src = A.sources[mat];
 	const bool shadow = A.shadow != 0;
-	double *K = A.K + (size_t)mat * cnt * cnt;
+	double *K = Ks;
+	if (!K_SMEM) K = A.K + (size_t)mat * cnt * cnt;
 	float4 *fres_ws = A.fres_ws + (size_t)mat * cnt * (cnt + 2);
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
 	const Params sp = standard_params();
+	FIT_PHASE(0);
 
 	// ---- compute_p22_smith, dj_brdf.h:2482-2522 ------------------------------------------------
 	const float dphi_h = (float)(DJB_PI / 180.0);
@@ -101,6 +127,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		}
 	}
 	__syncthreads();
+	FIT_PHASE(1);
 	for (int e = tid; e < cnt * cnt; e += nt) {
 		int j = e / cnt, i = e - j * cnt; // consecutive threads walk i: coalesced writes of K[j * cnt + i]
 		float tan_product = row_tan[j] * row_tan[i];
@@ -117,6 +144,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	}
 	for (int a = tid; a < cnt; a += nt) v0[a] = 1.0;
 	__syncthreads();
+	FIT_PHASE(2);
 	// matrix::eigenvector, dj_brdf.h:2467-2480: un-normalised power iterations, sums in index order
 	double *vin = v0, *vout = v1;
 	for (int it = 0; it < A.iterations; ++it) {
@@ -149,6 +177,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	for (int a = tid; a < cnt; a += nt) s_p22[a] = (float)(1e-2 * vin[a]);
 	if (tid == 0) s_p22[cnt] = 0.0f;
 	__syncthreads();
+	FIT_PHASE(3);
 	TabIso tab;
 	tab.p22 = s_p22; tab.sigma = s_sigma; tab.n = res;
 
@@ -170,11 +199,17 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	__syncthreads();
 	for (int a = tid; a < res; a += nt) s_p22[a] *= s_scale;
 	__syncthreads();
+	FIT_PHASE(4);
 
 	// ---- compute_sigma, dj_brdf.h:2348-2386 -------------------------------------------------------
+	// vec3(theta_h, phi_h) of the NDF grid (dj_brdf.h:589-595) is built from sincos of each angle: tabulated per angle (90 + 180
+	// calls instead of 2 x 16 200); gst_f / gct_f borrow `terms`, which is idle between normalize_p22 and the parameter fits
+	float *gst_f = terms, *gct_f = terms + SIG_NTHETA;
 	for (int j = tid; j < SIG_NPHI; j += nt) {
 		float u_j = (float)j / (float)SIG_NPHI;
-		cphi_d[j] = cos((double)(float)((double)u_j * 2.0 * DJB_PI));
+		const double phi_h = (double)(float)((double)u_j * 2.0 * DJB_PI);
+		cphi_d[j] = cos(phi_h);
+		sincos(phi_h, &gsp_d[j], &gcp_d[j]);
 	}
 	for (int j = tid; j < SIG_NTHETA; j += nt) {
 		float u_i = (float)j / (float)SIG_NTHETA;
@@ -182,43 +217,59 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		cth_d[j] = cos((double)theta_h);
 		sth[j] = (float)sin((double)theta_h);
 		ui[j] = u_i;
+		double st_, ct_;
+		sincos((double)theta_h, &st_, &ct_);
+		gst_f[j] = (float)st_;
+		gct_f[j] = (float)ct_;
 	}
-	for (int e = tid; e < SIG_NPHI * SIG_NTHETA; e += nt) { // ndf(vec3(theta_h, phi_h)) does not depend on the view angle
-		int j2 = e / SIG_NTHETA, j1 = e - j2 * SIG_NTHETA;
-		float u_j = (float)j2 / (float)SIG_NPHI, u_i = (float)j1 / (float)SIG_NTHETA;
-		float phi_h = (float)((double)u_j * 2.0 * DJB_PI);
-		float theta_h = (float)((double)(u_i * u_i) * DJB_PI * 0.5);
-		grid[e] = tab_ndf(tab, sp, spherical(theta_h, phi_h));
+	for (int i = tid; i < cnt; i += nt) { // the view angles
+		float t = (float)i / (float)cnt;
+		float theta_k = (float)((double)t * 0.5 * DJB_PI);
+		ck_d[i] = (double)(float)cos((double)theta_k);
+		sk_f[i] = (float)sin((double)theta_k);
 	}
 	__syncthreads();
+	for (int e = tid; e < SIG_NPHI * SIG_NTHETA; e += nt) { // ndf(vec3(theta_h, phi_h)) does not depend on the view angle
+		int j2 = e / SIG_NTHETA, j1 = e - j2 * SIG_NTHETA;
+		const double sd = (double)gst_f[j1];
+		grid[e] = tab_ndf(tab, sp, mk((float)(sd * gcp_d[j2]), (float)(sd * gsp_d[j2]), gct_f[j1]));
+	}
+	__syncthreads();
+	FIT_PHASE(5);
 	{
-		// 89 ordered sums of 16 200 terms each, one thread per view angle; every operand of the inner loop is in
-		// shared memory and is the same address for all lanes (broadcast)
+		// 89 ordered sums of 16 200 terms each, one thread per view angle; every operand of the inner loop is a shared-memory
+		// broadcast.  Per term: two float <-> double conversions and three FP64 operations; a warp-wide FP64 / conversion
+		// instruction occupies its scheduler's pipe for ~8 cycles whatever the number of active lanes, which is what bounds the
+		// stage (36 cycles per term on each of the three schedulers in use).  Tried and dropped (profiles/r02_h_fit_phases.md):
+		// (a) the whole CTA computing the 89 x 90 terms of one azimuth slab into shared memory, lane i adding its 90 terms in
+		// order -- the same FP64 work plus the staging: 810 k cycles against 588 k; (b) tabulating the two azimuth-independent
+		// operands (128 KB): 530 k, but the matrix then no longer fits in shared memory and the 50 iterations lose more.
 		const float dtheta = (float)(DJB_PI / (double)(float)SIG_NTHETA);
 		const float dphi = (float)(2.0 * DJB_PI / (double)(float)SIG_NPHI);
-		for (int i = tid; i < cnt; i += nt) {
-			float t = (float)i / (float)cnt;
-			float theta_k = (float)((double)t * 0.5 * DJB_PI);
-			float ck = (float)cos((double)theta_k), sk = (float)sin((double)theta_k);
-			const double ckd = (double)ck;
-			float nint = 0.0f;
-			for (int j2 = 0; j2 < SIG_NPHI; ++j2) {
-				const double cp = cphi_d[j2];
-				const float *g = grid + j2 * SIG_NTHETA;
+		{
+			for (int i = tid; i < cnt; i += nt) { // every operand of the inner loop is a shared-memory broadcast
+				const float sk = sk_f[i];
+				const double ckd = ck_d[i];
+				float nint = 0.0f;
+				for (int j2 = 0; j2 < SIG_NPHI; ++j2) {
+					const double cp = cphi_d[j2];
+					const float *g = grid + j2 * SIG_NTHETA;
 #pragma unroll 10
-				for (int j1 = 0; j1 < SIG_NTHETA; ++j1) {
-					float s_h = sth[j1];
-					float kh = (float)((double)(sk * s_h) * cp + ckd * cth_d[j1]);
-					nint += fmax_ref(0.0f, kh) * g[j1] * ui[j1] * s_h;
+					for (int j1 = 0; j1 < SIG_NTHETA; ++j1) {
+						float s_h = sth[j1];
+						float kh = (float)((double)(sk * s_h) * cp + ckd * cth_d[j1]);
+						nint += fmax_ref(0.0f, kh) * g[j1] * ui[j1] * s_h;
+					}
 				}
+				nint *= dtheta * dphi;
+				s_sigma[i] = fmax_ref((float)ckd, nint);
 			}
-			nint *= dtheta * dphi;
-			s_sigma[i] = fmax_ref(ck, nint);
 		}
 	}
 	__syncthreads();
 	if (tid == 0) s_sigma[cnt] = s_sigma[cnt - 1];
 	__syncthreads();
+	FIT_PHASE(6);
 
 	// ---- compute_fresnel, dj_brdf.h:2583-2641 -------------------------------------------------------
 	// The reference walks theta_h for every theta_d bin i; the (i, j) evaluations are independent, only the running
@@ -270,6 +321,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		}
 	}
 	__syncthreads();
+	FIT_PHASE(7);
 	float *o_fres = A.fresnel + (size_t)mat * res * 3;
 	for (int i = tid; i < cnt; i += nt) {
 		V3 f = mk(0.f, 0.f, 0.f);
@@ -305,6 +357,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		s_cdf[cnt] = 1.0f;
 	}
 	__syncthreads();
+	FIT_PHASE(8);
 
 	// ---- compute_qf, dj_brdf.h:2731-2762: cdf_radial on the 8x finer grid in parallel, then the scan ---
 	const int qres = cnt * 8;
@@ -355,6 +408,12 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		A.sigma[(size_t)mat * res + a] = s_sigma[a];
 		A.cdf[(size_t)mat * res + a] = s_cdf[a];
 	}
+	FIT_PHASE(9);
+}
+
+cudaError_t fit_phase_clocks(long long out[10])
+{
+	return cudaMemcpyFromSymbol(out, g_fit_phase_clock, sizeof(long long) * 10);
 }
 
 cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
@@ -367,10 +426,15 @@ cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials,
 	A.res = res; A.shadow = shadow; A.iterations = iterations;
 	A.K = K_ws; A.fres_ws = fres_ws;
 	A.p22 = p22; A.sigma = sigma; A.cdf = cdf; A.qf = qf; A.fresnel = fresnel; A.alpha = alpha; A.residuals = residuals;
-	size_t smem = iso_smem_bytes(res);
-	cudaError_t e = cudaFuncSetAttribute(fit_tabular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	const IsoSmemPlan plan = iso_smem_plan(res);
+	size_t smem = plan.bytes;
+	auto go = [&](auto kernel) {
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e == cudaSuccess) kernel<<<n_materials, FIT_THREADS, smem, st>>>(A);
+		return e;
+	};
+	cudaError_t e = plan.k_in_smem ? go(fit_tabular_kernel<true>) : go(fit_tabular_kernel<false>);
 	if (e != cudaSuccess) return e;
-	fit_tabular_kernel<<<n_materials, FIT_THREADS, smem, st>>>(A);
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	return cudaGetLastError();
 }

@@ -131,6 +131,9 @@ DJB200_API djb200_status djb200_debug_force_generic(int on);
  * kernel instead of the warp-compacting one (csrc/kernels_mf.cu, mf_beck_compact_kernel); 1 (default) = compaction on.
  * The two produce the same floats (same functions on the same operands, scheduled on other lanes). */
 DJB200_API djb200_status djb200_debug_beckmann_compaction(int on);
+/* Profiling aid: SM clock values at the ten phase boundaries of material 0's CTA in the last isotropic fit launched by this
+ * process (start | rows | matrix | iterations | normalise | NDF grid | sigma | Fresnel ratios | Fresnel sums + cdf | end). */
+DJB200_API djb200_status djb200_debug_fit_phase_clocks(int64_t out_clocks[10]);
 
 /* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
 DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */
