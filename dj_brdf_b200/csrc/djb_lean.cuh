@@ -725,7 +725,7 @@ DJB_DEV float lean_pdf_tail(const float2 *T, const Params &p, bool shadow, const
 		G = t > 0.0f ? div_lean(t, g1i + g1o - t) : 0.0f;
 	}
 	if (G > 0.0f) {
-		const float kh = dot(c.o, c.h);
+		const float kh = c.kh; // dot(o, h), as make_pair formed it
 		float v = 0.0f;
 		if (kh > 0.0f) {
 			const float num = kh * Dn;
@@ -893,7 +893,7 @@ DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &
 	float rsg_o;
 	bool ill;
 	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
-	if (__any_sync(__activemask(), ill)) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	if (ill) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	if (G > 0.0f) {
 		const float num = fast_ndf_from_r2<NDF>(m, c, r2) * G;
 		const float k = c.den_ok ? num * c.rcp_den : __fdiv_rn(num, c.den);
@@ -908,23 +908,16 @@ DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, cons
 	float rsg_o;
 	bool ill;
 	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
-	if (__any_sync(__activemask(), ill)) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	if (ill) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	if (G > 0.0f) {
 		const float v = c.kh > 0.0f ? (c.kh * fast_ndf_from_r2<NDF>(m, c, r2)) * rsg_o : 0.0f;
 		return c.den_ok ? v * c.rcp_den : __fdiv_rn(v, c.den);
 	}
 	return 0.0f;
 }
-// Beckmann's underflow tail (78 < r2 <= 103.5) takes the exact functions.  In the kernels that do not compact their work
-// (PER_PAIR / LEAN-texel params: one query per lane) a warp with ONE tail lane would run the fast path for 31 lanes and then
-// the exact path for one: when any converged lane is in the tail, the whole warp takes the exact path instead (both tiers
-// are within 1e-5 of the reference, so which one a lane runs is immaterial); r2 > 103.5 (D == 0) is the exact tier's
-// cheap early-out either way.
-DJB_DEV bool fast_beck_exact_vote(float r2)
-{
-	const bool beyond = !(r2 <= FAST_BECK_R2_MAX);
-	return __any_sync(__activemask(), beyond && r2 <= 103.5f) || beyond;
-}
+// Beckmann's underflow tail (r2 > 78) takes the exact functions; r2 > 103.5 (D == 0) is their cheap early-out.  The choice is
+// made per query from its own operands only, so a result never depends on which other queries share the warp or the batch.
+DJB_DEV bool fast_beck_exact_vote(float r2) { return !(r2 <= FAST_BECK_R2_MAX); }
 // one (pair, material) query of the 1e-5 tier
 template <int NDF, int FK, int OP>
 DJB_DEV V3 fast_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)

@@ -163,7 +163,7 @@ DJB_DEV void load_pair(const MfKernelArgs &A, long long k, V3 &va, V3 &o, V3 &h,
 
 // BROADCAST layout: every pair under every params block; output (m, k) at m * out_stride + k.
 template <int NDF, int OP>
-__global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(const __grid_constant__ MfKernelArgs A)
 {
 	__shared__ Params s_params[MF_MAX_SMEM_PARAMS];
 	__shared__ float s_spline[3 * MF_MAX_SMEM_SPLINE];
@@ -204,7 +204,7 @@ constexpr int lean_min_blocks(int ndf, int op, int psrc, bool fast)
 }
 
 template <int NDF, int FK, int OP, int PSRC, bool FAST>
-__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC, FAST)) mf_lean_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC, FAST)) mf_lean_kernel(const __grid_constant__ MfKernelArgs A)
 {
 	constexpr bool uses_u = (OP == OP_SAMPLE || OP == OP_EVALP_IS);
 	constexpr bool PERPAIR = PSRC != PSRC_BROADCAST;
@@ -276,13 +276,17 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC, FAS
 // r2; r2 > 103.5 <=> D == 0), lanes that pass push a work item (source lane, material, r2) into a per-warp queue in shared
 // memory, and whenever 32 items are waiting the whole warp evaluates them, one item per lane, reading the source lane's
 // pair from shared memory.  Results are the same floats: the same functions run on the same operands, on another lane.
+// Tried and dropped (round 2): screening all 16 materials into two per-lane bit masks first (no ballots inside the material
+// loop), one warp scan to scatter 16-bit items, r2 recomputed by the finishing lane -- bit-identical, but slower (1e-5 tier:
+// eval 17.0 -> 18.7 ms, pdf 17.3 -> 17.7 ms; exact tier 24.9 -> 29.2 ms): interleaving the finishing batches with the
+// screening of the next materials hides their latencies, separated phases do not.
 struct PairS { float4 a, b, c, d; }; // i.xyz o.x | o.yz h.xy | h.z den rcp_den inv_iz | o.h den_ok c4 rcp_c4
 
 #ifndef DJB200_COMPACT_MINB
 #define DJB200_COMPACT_MINB 1
 #endif
 template <int FK, int OP, bool FAST>
-__global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compact_kernel(MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compact_kernel(const __grid_constant__ MfKernelArgs A)
 {
 	constexpr int NDF = NDF_BECKMANN;
 	constexpr int WARPS = MF_THREADS / 32;
