@@ -37,9 +37,17 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed on stdout at NCCL_DEBUG=VERSION / INFO when the
-# first communicator is created) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries print there too (NCCL's banner "NCCL version ..." at NCCL_DEBUG=VERSION / INFO
+# whenever a communicator is created -- torch's and the one inside libdjb200.so), so file descriptor 1 is pointed at stderr for the
+# whole run and the result line is written to the saved descriptor of the real stdout.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 from dj_brdf_b200 import workloads  # noqa: E402  (host-side synthetic inputs, numpy only)
 
@@ -256,7 +264,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bind_to_gpu_numa_node(index):
@@ -477,15 +485,16 @@ def run_ours(args, rank, local_rank, world):
             "dtype": "f32 (f64 at the reference's double sub-expressions)", "data": "synthetic",
             "config": {"workload": "configs[1]: GGX+Beckmann eval/pdf/sample, 1e8 pairs x 16 anisotropic materials per GPU",
                        "pairs_per_gpu": pairs, "materials": M, "queries_per_step_per_gpu": 6 * pairs * M,
+                       "precision": djb.get_precision() + " (include/djb200.h: djb200_set_precision)",
                        "l2": "inputs (2.4 GB) and outputs (19.2 GB) larger than L2; no flush needed",
                        "sharding": "pairs sharded across ranks, params replicated, no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab,
-                         "note": "issue-bound, not HBM-bound: reproducing the reference's rounded floats costs ~190 (GGX eval) to "
-                                 "~860 (Beckmann sample: a Newton search of erfinv + exp per sample, glibc's own float algorithms in "
-                                 "double) warp instructions per result; DRAM traffic equals the algorithmic bytes "
-                                 "(profiles/dram_traffic.json)"},
+                         "note": "issue-bound, not HBM-bound: in the default 1e-5 tier a result costs ~120 (GGX eval / pdf) to ~315 "
+                                 "(Beckmann sample: the reference's Newton search of erfinv + exp, trip for trip) thread instructions, "
+                                 "in the exact tier (DJB200_PRECISION=bits) ~190 to ~680; DRAM traffic equals the algorithmic bytes "
+                                 "(profiles/dram_traffic.json, profiles/r02_h_microfacet.md)"},
             "kernels": per_kernel,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -493,7 +502,7 @@ def run_ours(args, rank, local_rank, world):
             "cpu_baseline": cpu,
         }
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
