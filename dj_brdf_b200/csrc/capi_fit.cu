@@ -43,7 +43,7 @@ struct Scratch {
 	}
 	template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
-thread_local Scratch t_fit_src, t_fit_K, t_fit_ws, t_fit_out, t_fit_resid;
+thread_local Scratch t_fit_src, t_fit_K, t_fit_ws, t_fit_out, t_fit_resid, t_fit_ndfgrid;
 
 // host source descriptors -> device array (spline Fresnel points are uploaded into `spline_store`)
 djb200_status build_sources(const djb200_source *sources, int32_t n, std::vector<FitSourceDev> &out,
@@ -139,7 +139,7 @@ static djb200_status fit_tabular_device(const djb200_source *sources, int32_t n_
 	if (rs != DJB200_OK) return rs;
 
 	const size_t n = (size_t)n_sources, cnt = (size_t)res - 1;
-	Scratch &d_src = t_fit_src, &d_K = t_fit_K, &d_grid = t_fit_ws, &d_out = t_fit_out, &d_resid = t_fit_resid;
+	Scratch &d_src = t_fit_src, &d_K = t_fit_K, &d_grid = t_fit_ws, &d_out = t_fit_out, &d_resid = t_fit_resid, &d_ndfgrid = t_fit_ndfgrid;
 	const size_t per_kind = n * (size_t)res;
 	const size_t out_floats = djb200_fit_tabular_packed_floats(n_sources, res);
 #define FCU(call)                                                \
@@ -156,11 +156,23 @@ static djb200_status fit_tabular_device(const djb200_source *sources, int32_t n_
 	float *o = d_out.as<float>();
 	float *o_p22 = o, *o_sigma = o + per_kind, *o_cdf = o + 2 * per_kind, *o_qf = o + 3 * per_kind;
 	float *o_fres = o + 4 * per_kind, *o_alpha = o_fres + 3 * per_kind;
+	float *grid_ws = nullptr;
+	if (fit_tabular_parts(n_sources, res) > 1) { // small batch: the split mode passes the NDF grid through global memory
+		FCU(d_ndfgrid.reserve(sizeof(float) * n * 180 * 90));
+		grid_ws = d_ndfgrid.as<float>();
+	}
 	FCU(launch_fit_tabular(d_src.as<FitSourceDev>(), n_sources, res, shadow, iterations, d_K.as<double>(),
-	                       d_grid.as<float4>(), o_p22, o_sigma, o_cdf, o_qf, o_fres, o_alpha, d_resid.as<float>(), st));
+	                       d_grid.as<float4>(), grid_ws, o_p22, o_sigma, o_cdf, o_qf, o_fres, o_alpha, d_resid.as<float>(), st));
 	if (!splines.empty()) FCU(cudaStreamSynchronize(st)); // spline uploads are freed when this function returns
 	*out_dev = o;
 	*resid_dev = d_resid.as<float>();
+	return DJB200_OK;
+}
+
+djb200_status djb200_debug_fit_parts(int parts)
+{
+	if (parts != 0 && parts != 1 && (parts < 3 || parts > 8)) return fail(DJB200_ERR_INVALID_ARGUMENT, "parts must be 0, 1 or 3..8");
+	g_fit_parts.store(parts);
 	return DJB200_OK;
 }
 

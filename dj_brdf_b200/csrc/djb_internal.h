@@ -126,8 +126,12 @@ cudaError_t launch_microfacet_component(int ndf, int shadow, int fresnel_kind, c
 struct FitSourceDev;
 size_t fit_tabular_smem_bytes(int res);
 cudaError_t fit_phase_clocks(long long out[10]); // SM clock at the phase boundaries of material 0 of the last isotropic fit
+// grid_ws: n_materials x 16 200 floats, needed when fit_tabular_parts(n_materials, res) > 1 (small batches run one launch per
+// phase with several CTAs per material); NULL forces the single launch
+int fit_tabular_parts(int n_materials, int res);
+extern std::atomic<int> g_fit_parts; // 0: automatic; 1: always the single launch; 3..8: that many CTAs per material where possible
 cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
-                               double *K_ws, float4 *fres_ws, float *p22, float *sigma, float *cdf, float *qf,
+                               double *K_ws, float4 *fres_ws, float *grid_ws, float *p22, float *sigma, float *cdf, float *qf,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st);
 
 // anisotropic fit stages; [row0, row1) = this GPU's shard of the n = (er - 1) * ar rows

@@ -30,6 +30,8 @@ struct IsoFitArgs {
 	int res, shadow, iterations;
 	double *K;        // workspace: n_materials x cnt x cnt, K[b * cnt + a] = km(b, a)   (column of row a contiguous in a)
 	float4 *fres_ws;  // workspace: n_materials x cnt x (cnt + 2) Fresnel ratios (rx, ry, rz, valid)
+	float *grid_ws;   // workspace of the split mode: n_materials x SIG_NPHI x SIG_NTHETA NDF grid values
+	int phase;        // 0: the whole fit in one launch, one CTA per material.  1..6: ONE phase of the split mode (below)
 	// outputs, n_materials x ...
 	float *p22, *sigma, *cdf, *qf, *fresnel, *alpha, *residuals;
 };
@@ -72,11 +74,29 @@ static size_t iso_smem_bytes(int res) { return iso_smem_plan(res).bytes; }
 __device__ long long g_fit_phase_clock[10];
 #define FIT_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_fit_phase_clock[k] = clock64(); } while (0)
 
+// SPLIT MODE (small batches: fewer materials than SMs / 3).  One CTA per material leaves most of the device idle when a call
+// fits a handful of materials -- the reference's own example fits one at a time -- and the fit is 0.7 ms of dependent work inside that
+// CTA.  The same kernel then runs once per phase with gridDim.y CTAs per material (blockIdx.y = part), passing the state
+// through L2-resident global arrays (the outputs themselves + K / grid_ws / fres_ws):
+//   1 MATRIX   rows in every CTA, the kernel-matrix entries split over the parts                -> K
+//   2 ITER     one CTA: K -> shared memory, power iterations, normalize_p22                     -> p22
+//   3 GRID     the 16 200 NDF grid values split over the parts                                   -> grid_ws
+//   4 SIGMA    the 89 ordered sums split over the parts; inside a CTA seven producer warps compute the terms of the next
+//              azimuth slab while lanes of warp 0 add the current slab's terms in the reference's order        -> sigma
+//   5 FRESNEL  the 5 456 ratio evaluations split over the parts                                  -> fres_ws
+//   6 FINISH   one CTA: Fresnel sums, cdf, qf, roughness parameters                              -> fresnel, cdf, qf, alpha
+// Same operations on the same operands in the same order as the single launch: bit-identical (tests/test_gpu_fit.py).
+enum { PH_ALL = 0, PH_MATRIX = 1, PH_ITER = 2, PH_GRID = 3, PH_SIGMA = 4, PH_FRESNEL = 5, PH_FINISH = 6 };
+constexpr int SLAB_PITCH = 92; // floats per chain and slab: rows 16-byte aligned
+
 template <bool K_SMEM>
 __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 {
 	extern __shared__ double smem_d[];
 	const int res = A.res, cnt = res - 1, tid = threadIdx.x, nt = blockDim.x, mat = blockIdx.x;
+	const int ph = A.phase, part = blockIdx.y, nparts = gridDim.y;
+	const bool split = ph != PH_ALL;
+	auto on = [&](int p) { return ph == PH_ALL || ph == p; };
 	double *v0 = smem_d, *v1 = v0 + cnt, *cphi_d = v1 + cnt, *cth_d = cphi_d + SIG_NPHI;
 	double *gsp_d = cth_d + SIG_NTHETA, *gcp_d = gsp_d + SIG_NPHI, *ck_d = gcp_d + SIG_NPHI;
 	double *Ks = ck_d + cnt; // cnt * cnt doubles when K_SMEM
@@ -94,15 +114,22 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 
 	const FitSourceDev src = A.sources[mat];
 	const bool shadow = A.shadow != 0;
+	double *Kg = A.K + (size_t)mat * cnt * cnt;
 	double *K = Ks;
-	if (!K_SMEM) K = A.K + (size_t)mat * cnt * cnt;
+	if (!K_SMEM) K = Kg;
+	double *Kw = split ? Kg : K; // the matrix phase of the split mode writes to global memory, whatever K_SMEM is
+	float *grid_g = A.grid_ws + (size_t)mat * SIG_NPHI * SIG_NTHETA;
+	float *o_p22 = A.p22 + (size_t)mat * res, *o_sigma = A.sigma + (size_t)mat * res;
 	float4 *fres_ws = A.fres_ws + (size_t)mat * cnt * (cnt + 2);
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
 	const Params sp = standard_params();
 	FIT_PHASE(0);
+	TabIso tab;
+	tab.p22 = s_p22; tab.sigma = s_sigma; tab.n = res;
 
 	// ---- compute_p22_smith, dj_brdf.h:2482-2522 ------------------------------------------------
 	const float dphi_h = (float)(DJB_PI / 180.0);
+	if (on(PH_MATRIX)) {
 	if (tid == 0) { // for (phi = 0; phi < 2 pi; phi += dphi) with a float counter: 361 steps
 		int n = 0;
 		for (float phi = 0.0f; (double)phi < 2.0 * DJB_PI && n < MAX_PHI_STEPS; phi += dphi_h) cosphi[n++] = phi;
@@ -128,7 +155,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	}
 	__syncthreads();
 	FIT_PHASE(1);
-	for (int e = tid; e < cnt * cnt; e += nt) {
+	for (int e = part * nt + tid; e < cnt * cnt; e += nt * nparts) {
 		int j = e / cnt, i = e - j * cnt; // consecutive threads walk i: coalesced writes of K[j * cnt + i]
 		float tan_product = row_tan[j] * row_tan[i];
 		float nint;
@@ -140,8 +167,11 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		}
 		nint *= dphi_h;
 		float entry = row_theta[j] * row_kji[i] * nint * row_tan[j] / (row_cos[j] * row_cos[j]);
-		K[(size_t)j * cnt + i] = (double)entry; // out[i] = sum_j K(i, j) v[j]; stored transposed for coalesced reads
+		Kw[(size_t)j * cnt + i] = (double)entry; // out[i] = sum_j K(i, j) v[j]; stored transposed for coalesced reads
 	}
+	} // PH_MATRIX
+	if (on(PH_ITER)) {
+	if (split && K_SMEM) for (int e = tid; e < cnt * cnt; e += nt) Ks[e] = Kg[e];
 	for (int a = tid; a < cnt; a += nt) v0[a] = 1.0;
 	__syncthreads();
 	FIT_PHASE(2);
@@ -178,8 +208,6 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	if (tid == 0) s_p22[cnt] = 0.0f;
 	__syncthreads();
 	FIT_PHASE(3);
-	TabIso tab;
-	tab.p22 = s_p22; tab.sigma = s_sigma; tab.n = res;
 
 	// ---- normalize_p22, dj_brdf.h:2277-2304 ------------------------------------------------------
 	for (int i = tid; i < NORM_NTHETA; i += nt) {
@@ -199,12 +227,19 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	__syncthreads();
 	for (int a = tid; a < res; a += nt) s_p22[a] *= s_scale;
 	__syncthreads();
+	if (split) for (int a = tid; a < res; a += nt) o_p22[a] = s_p22[a];
 	FIT_PHASE(4);
+	} // PH_ITER
+	if (split && ph >= PH_GRID) { // the later phases of the split mode start from the tables the earlier ones left in global memory
+		for (int a = tid; a < res; a += nt) { s_p22[a] = o_p22[a]; s_sigma[a] = ph >= PH_FRESNEL ? o_sigma[a] : 0.0f; }
+		__syncthreads();
+	}
 
 	// ---- compute_sigma, dj_brdf.h:2348-2386 -------------------------------------------------------
 	// vec3(theta_h, phi_h) of the NDF grid (dj_brdf.h:589-595) is built from sincos of each angle: tabulated per angle (90 + 180
 	// calls instead of 2 x 16 200); gst_f / gct_f borrow `terms`, which is idle between normalize_p22 and the parameter fits
 	float *gst_f = terms, *gct_f = terms + SIG_NTHETA;
+	if (on(PH_GRID) || on(PH_SIGMA)) {
 	for (int j = tid; j < SIG_NPHI; j += nt) {
 		float u_j = (float)j / (float)SIG_NPHI;
 		const double phi_h = (double)(float)((double)u_j * 2.0 * DJB_PI);
@@ -229,13 +264,22 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		sk_f[i] = (float)sin((double)theta_k);
 	}
 	__syncthreads();
-	for (int e = tid; e < SIG_NPHI * SIG_NTHETA; e += nt) { // ndf(vec3(theta_h, phi_h)) does not depend on the view angle
+	}
+	if (on(PH_GRID)) {
+	float *gw = split ? grid_g : grid;
+	for (int e = part * nt + tid; e < SIG_NPHI * SIG_NTHETA; e += nt * nparts) { // ndf(vec3(theta_h, phi_h)) does not depend on the view angle
 		int j2 = e / SIG_NTHETA, j1 = e - j2 * SIG_NTHETA;
 		const double sd = (double)gst_f[j1];
-		grid[e] = tab_ndf(tab, sp, mk((float)(sd * gcp_d[j2]), (float)(sd * gsp_d[j2]), gct_f[j1]));
+		gw[e] = tab_ndf(tab, sp, mk((float)(sd * gcp_d[j2]), (float)(sd * gsp_d[j2]), gct_f[j1]));
 	}
 	__syncthreads();
 	FIT_PHASE(5);
+	} // PH_GRID
+	if (on(PH_SIGMA)) {
+	if (split) {
+		for (int e = tid; e < SIG_NPHI * SIG_NTHETA; e += nt) grid[e] = grid_g[e];
+		__syncthreads();
+	}
 	{
 		// 89 ordered sums of 16 200 terms each, one thread per view angle; every operand of the inner loop is a shared-memory
 		// broadcast.  Per term: two float <-> double conversions and three FP64 operations; a warp-wide FP64 / conversion
@@ -246,7 +290,49 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		// operands (128 KB): 530 k, but the matrix then no longer fits in shared memory and the 50 iterations lose more.
 		const float dtheta = (float)(DJB_PI / (double)(float)SIG_NTHETA);
 		const float dphi = (float)(2.0 * DJB_PI / (double)(float)SIG_NPHI);
-		{
+		if (split && K_SMEM) {
+			// this part's chains c0 .. c1 - 1 (at most 32); two slab buffers in the idle matrix block
+			const int cpp = (cnt + nparts - 1) / nparts, c0 = part * cpp, nc = (c0 + cpp < cnt ? c0 + cpp : cnt) - c0;
+			float *slab = reinterpret_cast<float *>(Ks) + (((3 * cnt + 2 * SIG_NPHI + SIG_NPHI + SIG_NTHETA) & 1) ? 2 : 0); // 16-byte aligned
+			const int nterm = nc * SIG_NTHETA, lane = tid & 31, warp = tid >> 5, nprod = nt - 32;
+			auto produce = [&](int j2, float *buf) { // independent terms of azimuth slab j2, warps 1..7
+				const double cp = cphi_d[j2];
+				const float *g = grid + j2 * SIG_NTHETA;
+				for (int e = tid - 32; e < nterm; e += nprod) {
+					const int il = e / SIG_NTHETA, j1 = e - il * SIG_NTHETA;
+					const float s_h = sth[j1];
+					const float kh = (float)((double)(sk_f[c0 + il] * s_h) * cp + ck_d[c0 + il] * cth_d[j1]);
+					buf[il * SLAB_PITCH + j1] = fmax_ref(0.0f, kh) * g[j1] * ui[j1] * s_h;
+				}
+			};
+			if (warp != 0) produce(0, slab);
+			__syncthreads();
+			float nint = 0.0f;
+			for (int j2 = 0; j2 < SIG_NPHI; ++j2) {
+				float *cur = slab + (j2 & 1) * 32 * SLAB_PITCH, *nxt = slab + ((j2 + 1) & 1) * 32 * SLAB_PITCH;
+				if (warp == 0) {
+					if (lane < nc) {
+						const float4 *row = reinterpret_cast<const float4 *>(cur + lane * SLAB_PITCH);
+#pragma unroll
+						for (int q = 0; q < SIG_NTHETA / 4; ++q) { // 22 x 4 terms, in index order
+							const float4 t = row[q];
+							nint += t.x; nint += t.y; nint += t.z; nint += t.w;
+						}
+						nint += cur[lane * SLAB_PITCH + 88];
+						nint += cur[lane * SLAB_PITCH + 89];
+					}
+				} else if (j2 + 1 < SIG_NPHI) {
+					produce(j2 + 1, nxt);
+				}
+				__syncthreads();
+			}
+			if (warp == 0 && lane < nc) {
+				nint *= dtheta * dphi;
+				const float sg = fmax_ref((float)ck_d[c0 + lane], nint);
+				o_sigma[c0 + lane] = sg;
+				if (c0 + lane == cnt - 1) o_sigma[cnt] = sg;
+			}
+		} else {
 			for (int i = tid; i < cnt; i += nt) { // every operand of the inner loop is a shared-memory broadcast
 				const float sk = sk_f[i];
 				const double ckd = ck_d[i];
@@ -267,13 +353,17 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		}
 	}
 	__syncthreads();
-	if (tid == 0) s_sigma[cnt] = s_sigma[cnt - 1];
-	__syncthreads();
+	if (!split) {
+		if (tid == 0) s_sigma[cnt] = s_sigma[cnt - 1];
+		__syncthreads();
+	}
 	FIT_PHASE(6);
+	} // PH_SIGMA
 
 	// ---- compute_fresnel, dj_brdf.h:2583-2641 -------------------------------------------------------
 	// The reference walks theta_h for every theta_d bin i; the (i, j) evaluations are independent, only the running
 	// sums are ordered.  So: trip counts per bin, all ratios in parallel over the flattened (i, j) list, ordered sums.
+	if (on(PH_FRESNEL) || on(PH_FINISH)) {
 	for (int i = tid; i < cnt; i += nt) {
 		float tt = (float)i / (float)cnt;
 		float theta_d = (float)((double)tt * DJB_PI * 0.5);
@@ -294,10 +384,11 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 		fr_offset[cnt] = acc;
 	}
 	__syncthreads();
-	{
+	}
+	if (on(PH_FRESNEL)) {
 		const int total = fr_offset[cnt];
 		const float phi_d = (float)(DJB_PI * 0.5), phi_h = 0.0f;
-		for (int e = tid; e < total; e += nt) {
+		for (int e = part * nt + tid; e < total; e += nt * nparts) {
 			int lo = 0, hi = cnt - 1; // bin i with fr_offset[i] <= e < fr_offset[i + 1]
 			while (lo < hi) {
 				int mid = (lo + hi + 1) >> 1;
@@ -322,6 +413,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	}
 	__syncthreads();
 	FIT_PHASE(7);
+	if (!on(PH_FINISH)) return;
 	float *o_fres = A.fresnel + (size_t)mat * res * 3;
 	for (int i = tid; i < cnt; i += nt) {
 		V3 f = mk(0.f, 0.f, 0.f);
@@ -416,27 +508,53 @@ cudaError_t fit_phase_clocks(long long out[10])
 	return cudaMemcpyFromSymbol(out, g_fit_phase_clock, sizeof(long long) * 10);
 }
 
+std::atomic<int> g_fit_parts{0};
+// CTAs per material: 1 = the whole fit in one launch; 3..8 = the split mode (six launches), chosen when the batch would leave
+// most SMs idle.  The split mode needs the matrix block in shared memory (the slab buffers of its sigma phase live there) and
+// at most 32 chains per part.
+int fit_tabular_parts(int n_materials, int res)
+{
+	const int forced = g_fit_parts.load(std::memory_order_relaxed); // djb200_debug_fit_parts: A/B tests
+	const int cnt = res - 1;
+	const size_t slab_bytes = 2 * 32 * SLAB_PITCH * sizeof(float) + 8;
+	if (!iso_smem_plan(res).k_in_smem || sizeof(double) * cnt * cnt < slab_bytes) return 1;
+	int parts = forced > 0 ? forced : sm_count() / (n_materials > 0 ? n_materials : 1);
+	if (parts > 8) parts = 8;
+	if (parts < 3 || (cnt + parts - 1) / parts > 32) return 1;
+	return parts;
+}
+
+
 cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials, int res, int shadow, int iterations,
-                               double *K_ws, float4 *fres_ws, float *p22, float *sigma, float *cdf, float *qf,
+                               double *K_ws, float4 *fres_ws, float *grid_ws, float *p22, float *sigma, float *cdf, float *qf,
                                float *fresnel, float *alpha, float *residuals, cudaStream_t st)
 {
 	if (n_materials <= 0) return cudaSuccess;
 	IsoFitArgs A;
 	A.sources = sources_dev;
 	A.res = res; A.shadow = shadow; A.iterations = iterations;
-	A.K = K_ws; A.fres_ws = fres_ws;
+	A.K = K_ws; A.fres_ws = fres_ws; A.grid_ws = grid_ws; A.phase = PH_ALL;
 	A.p22 = p22; A.sigma = sigma; A.cdf = cdf; A.qf = qf; A.fresnel = fresnel; A.alpha = alpha; A.residuals = residuals;
 	const IsoSmemPlan plan = iso_smem_plan(res);
 	size_t smem = plan.bytes;
+	const int parts = grid_ws ? fit_tabular_parts(n_materials, res) : 1;
 	auto go = [&](auto kernel) {
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e == cudaSuccess) kernel<<<n_materials, FIT_THREADS, smem, st>>>(A);
-		return e;
+		if (e != cudaSuccess) return e;
+		if (parts == 1) {
+			kernel<<<n_materials, FIT_THREADS, smem, st>>>(A);
+			g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+			return cudaGetLastError();
+		}
+		for (int ph = PH_MATRIX; ph <= PH_FINISH; ++ph) {
+			A.phase = ph;
+			const bool one = ph == PH_ITER || ph == PH_FINISH;
+			kernel<<<dim3(n_materials, one ? 1 : parts), FIT_THREADS, smem, st>>>(A);
+			g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+		}
+		return cudaGetLastError();
 	};
-	cudaError_t e = plan.k_in_smem ? go(fit_tabular_kernel<true>) : go(fit_tabular_kernel<false>);
-	if (e != cudaSuccess) return e;
-	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-	return cudaGetLastError();
+	return plan.k_in_smem ? go(fit_tabular_kernel<true>) : go(fit_tabular_kernel<false>);
 }
 
 size_t fit_tabular_smem_bytes(int res) { return iso_smem_bytes(res); }

@@ -134,6 +134,10 @@ DJB200_API djb200_status djb200_debug_beckmann_compaction(int on);
 /* Profiling aid: SM clock values at the ten phase boundaries of material 0's CTA in the last isotropic fit launched by this
  * process (start | rows | matrix | iterations | normalise | NDF grid | sigma | Fresnel ratios | Fresnel sums + cdf | end). */
 DJB200_API djb200_status djb200_debug_fit_phase_clocks(int64_t out_clocks[10]);
+/* A/B switch of the isotropic fit's launch shape: 0 (default) = automatic -- batches that would leave most SMs idle run one
+ * launch per phase with up to 8 CTAs per material, larger ones the whole fit in one launch with one CTA per material;
+ * 1 = always the single launch; 3..8 = that many CTAs per material wherever the resolution allows.  Same results either way. */
+DJB200_API djb200_status djb200_debug_fit_parts(int parts);
 
 /* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
 DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */

@@ -250,3 +250,29 @@ def test_tabular_anisotropic_tiny_resolutions_on_device(djb, port):
             fin = ~np.isnan(want_t[k])
             if fin.any():
                 assert np.abs(got_t[k][fin] - want_t[k][fin]).max() <= 1e-5 * max(1.0, float(np.abs(want_t[k][fin]).max())), (er, ar, k)
+
+
+def test_split_launch_of_small_batches_is_bit_identical(djb):
+    """Small batches run the isotropic fit as six launches with several CTAs per material (split mode, kernels_fit.cu); the tables
+    must be the single launch's, bit for bit -- for every part count, an analytic and a MERL source, 4 and 50 iterations."""
+    import ctypes as C
+    from dj_brdf_b200 import capi
+    lib = capi.load()
+    srcs = [djb.merl(cases.smooth_merl_table(21)), djb.ggx(), djb.merl(cases.synthetic_merl_table(0.3, kind="beckmann"))]
+    try:
+        for iters in (4, 50):
+            capi.check(lib.djb200_debug_fit_parts(C.c_int(1)))
+            want = djb.tabular.fit_packed(srcs, 90, True, iters)
+            for parts in (3, 5, 8, 0):
+                capi.check(lib.djb200_debug_fit_parts(C.c_int(parts)))
+                got = djb.tabular.fit_packed(srcs, 90, True, iters)
+                for k in ("p22", "sigma", "cdf", "qf", "fresnel", "alpha", "residuals"):
+                    assert bits_equal(got[k], want[k]).all(), (iters, parts, k)
+        # resolutions whose matrix block cannot hold the slab buffers fall back to the single launch
+        capi.check(lib.djb200_debug_fit_parts(C.c_int(8)))
+        a = djb.tabular.fit_packed(srcs[:1], 32, True, 4)
+        capi.check(lib.djb200_debug_fit_parts(C.c_int(1)))
+        b = djb.tabular.fit_packed(srcs[:1], 32, True, 4)
+        assert all(bits_equal(a[k], b[k]).all() for k in ("p22", "sigma", "cdf", "qf", "fresnel", "alpha"))
+    finally:
+        capi.check(lib.djb200_debug_fit_parts(C.c_int(0)))
