@@ -31,6 +31,7 @@ struct IsoFitArgs {
 	double *K;        // workspace: n_materials x cnt x cnt, K[b * cnt + a] = km(b, a)   (column of row a contiguous in a)
 	float4 *fres_ws;  // workspace: n_materials x cnt x (cnt + 2) Fresnel ratios (rx, ry, rz, valid)
 	float *grid_ws;   // workspace of the split mode: n_materials x SIG_NPHI x SIG_NTHETA NDF grid values
+	int hist;         // the iterates of the power iteration are kept in shared memory (iso_smem_plan)
 	int phase;        // 0: the whole fit in one launch, one CTA per material.  1..6: ONE phase of the split mode (below)
 	// outputs, n_materials x ...
 	float *p22, *sigma, *cdf, *qf, *fresnel, *alpha, *residuals;
@@ -57,17 +58,21 @@ static size_t iso_smem_base(int res)
 	                        SIG_NPHI * SIG_NTHETA + cnt) +
 	       sizeof(int) * (2 * cnt + 2);
 }
-struct IsoSmemPlan { size_t bytes; int k_in_smem; };
-static IsoSmemPlan iso_smem_plan(int res)
+struct IsoSmemPlan { size_t bytes; int k_in_smem, hist; };
+static IsoSmemPlan iso_smem_plan(int res, int iterations)
 {
 	const size_t cnt = res - 1, limit = 227 * 1024, kmat = sizeof(double) * cnt * cnt;
 	IsoSmemPlan p;
 	p.bytes = iso_smem_base(res) + 16;
 	p.k_in_smem = p.bytes + kmat <= limit;
 	if (p.k_in_smem) p.bytes += kmat;
+	// every iterate of the power iteration (the residual diagnostics are then computed after the loop, in parallel), at the end
+	const size_t hist = sizeof(double) * cnt * ((size_t)(iterations > 0 ? iterations : 0) + 1);
+	p.hist = p.k_in_smem && iterations > 0 && p.bytes + hist <= limit;
+	if (p.hist) p.bytes += hist;
 	return p;
 }
-static size_t iso_smem_bytes(int res) { return iso_smem_plan(res).bytes; }
+static size_t iso_smem_bytes(int res) { return iso_smem_plan(res, 0).bytes; }
 
 // SM clock at the phase boundaries of material 0's CTA (djb200_debug_fit_phase_clocks): rows | matrix | iterations | normalise |
 // NDF grid | sigma | Fresnel ratios | Fresnel sums + cdf | qf + parameters
@@ -108,6 +113,9 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	float *grid = scan + 8 * cnt;
 	int *fr_count = reinterpret_cast<int *>(grid + SIG_NPHI * SIG_NTHETA), *fr_offset = fr_count + cnt;
 	float *sk_f = reinterpret_cast<float *>(fr_offset + cnt + 1);
+	// (iterations + 1) x cnt doubles when A.hist: starts at the next 8-byte boundary after sk_f
+	double *hist = reinterpret_cast<double *>(sk_f + cnt + ((3 * res + 8 * cnt + 4 * cnt + MAX_PHI_STEPS + 2 * NORM_NTHETA + 2 * SIG_NTHETA +
+	                                                       SIG_NPHI * SIG_NTHETA + 2 * cnt + 1 + cnt) & 1));
 	__shared__ int s_nphi;
 	__shared__ double s_red[3][FIT_THREADS / 32];
 	__shared__ float s_scale;
@@ -177,6 +185,41 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	FIT_PHASE(2);
 	// matrix::eigenvector, dj_brdf.h:2467-2480: un-normalised power iterations, sums in index order
 	double *vin = v0, *vout = v1;
+	if (A.hist) {
+		// every iterate stays in shared memory: the loop is the 89 dependent sums and one barrier per iteration; the diagnostics
+		// (not in the reference, never fed back: ||v1/|v1| - v0/|v0||| = sqrt(2 - 2 cos)) follow, one warp per iteration
+		for (int a = tid; a < cnt; a += nt) hist[a] = 1.0;
+		__syncthreads();
+		for (int it = 0; it < A.iterations; ++it) {
+			const double *hin = hist + (size_t)it * cnt;
+			double *hout = hist + (size_t)(it + 1) * cnt;
+			for (int a = tid; a < cnt; a += nt) {
+				double acc = 0.0;
+#pragma unroll 8
+				for (int b = 0; b < cnt; ++b) acc += K[(size_t)b * cnt + a] * hin[b]; // loads and products ahead of the ordered adds
+				hout[a] = acc;
+			}
+			__syncthreads();
+		}
+		if (A.residuals) {
+			const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+			for (int it = warp; it < A.iterations; it += nw) {
+				const double *hin = hist + (size_t)it * cnt, *hout = hin + cnt;
+				double n0 = 0.0, n1 = 0.0, d01 = 0.0;
+				for (int a = lane; a < cnt; a += 32) { n0 += hin[a] * hin[a]; n1 += hout[a] * hout[a]; d01 += hin[a] * hout[a]; }
+				for (int o = 16; o > 0; o >>= 1) {
+					n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+					n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+					d01 += __shfl_xor_sync(0xffffffffu, d01, o);
+				}
+				if (lane == 0) {
+					const double d = 2.0 - 2.0 * d01 / (sqrt(n0) * sqrt(n1));
+					A.residuals[(size_t)mat * A.iterations + it] = (float)sqrt(d > 0.0 ? d : 0.0);
+				}
+			}
+		}
+		vin = hist + (size_t)A.iterations * cnt;
+	} else
 	for (int it = 0; it < A.iterations; ++it) {
 		for (int a = tid; a < cnt; a += nt) {
 			double acc = 0.0;
@@ -517,7 +560,7 @@ int fit_tabular_parts(int n_materials, int res)
 	const int forced = g_fit_parts.load(std::memory_order_relaxed); // djb200_debug_fit_parts: A/B tests
 	const int cnt = res - 1;
 	const size_t slab_bytes = 2 * 32 * SLAB_PITCH * sizeof(float) + 8;
-	if (!iso_smem_plan(res).k_in_smem || sizeof(double) * cnt * cnt < slab_bytes) return 1;
+	if (!iso_smem_plan(res, 0).k_in_smem || sizeof(double) * cnt * cnt < slab_bytes) return 1;
 	int parts = forced > 0 ? forced : sm_count() / (n_materials > 0 ? n_materials : 1);
 	if (parts > 8) parts = 8;
 	if (parts < 3 || (cnt + parts - 1) / parts > 32) return 1;
@@ -535,7 +578,8 @@ cudaError_t launch_fit_tabular(const FitSourceDev *sources_dev, int n_materials,
 	A.res = res; A.shadow = shadow; A.iterations = iterations;
 	A.K = K_ws; A.fres_ws = fres_ws; A.grid_ws = grid_ws; A.phase = PH_ALL;
 	A.p22 = p22; A.sigma = sigma; A.cdf = cdf; A.qf = qf; A.fresnel = fresnel; A.alpha = alpha; A.residuals = residuals;
-	const IsoSmemPlan plan = iso_smem_plan(res);
+	const IsoSmemPlan plan = iso_smem_plan(res, iterations);
+	A.hist = plan.hist;
 	size_t smem = plan.bytes;
 	const int parts = grid_ws ? fit_tabular_parts(n_materials, res) : 1;
 	auto go = [&](auto kernel) {
