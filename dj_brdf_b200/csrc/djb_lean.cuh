@@ -887,13 +887,13 @@ DJB_DEV float fast_ndf_from_r2(const ParamsX &m, const PairX &c, float r2)
 }
 constexpr float FAST_BECK_R2_MAX = 78.0f;
 // the part of a query after the cheap D == 0 / tail tests (what the Beckmann kernel compacts across a warp)
+// `ill` (fast_gaf): the result is not written by the fast path; the caller evaluates the query with the exact functions -- in
+// place (the plain kernels) or, in the compacting Beckmann kernel, by moving the item to the queue of exact work.
 template <int NDF, int FK, int OP>
-DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c, float r2)
+DJB_DEV V3 fast_evalp_try(const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c, float r2, bool &ill)
 {
 	float rsg_o;
-	bool ill;
 	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
-	if (ill) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	if (G > 0.0f) {
 		const float num = fast_ndf_from_r2<NDF>(m, c, r2) * G;
 		const float k = c.den_ok ? num * c.rcp_den : __fdiv_rn(num, c.den);
@@ -903,17 +903,31 @@ DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &
 	return lean_zero<OP>(c);
 }
 template <int NDF>
-DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, const PairX &c, float r2)
+DJB_DEV float fast_pdf_try(const ParamsX &m, bool shadow, const PairX &c, float r2, bool &ill)
 {
 	float rsg_o;
-	bool ill;
 	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
-	if (ill) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	if (G > 0.0f) {
 		const float v = c.kh > 0.0f ? (c.kh * fast_ndf_from_r2<NDF>(m, c, r2)) * rsg_o : 0.0f;
 		return c.den_ok ? v * c.rcp_den : __fdiv_rn(v, c.den);
 	}
 	return 0.0f;
+}
+template <int NDF, int FK, int OP>
+DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c, float r2)
+{
+	bool ill;
+	const V3 r = fast_evalp_try<NDF, FK, OP>(m, f, shadow, c, r2, ill);
+	if (ill) return lean_evalp_tail<NDF, FK, OP>(T, m.p, f, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	return r;
+}
+template <int NDF>
+DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, const PairX &c, float r2)
+{
+	bool ill;
+	const float r = fast_pdf_try<NDF>(m, shadow, c, r2, ill);
+	if (ill) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
+	return r;
 }
 // Beckmann's underflow tail (r2 > 78) takes the exact functions; r2 > 103.5 (D == 0) is their cheap early-out.  The choice is
 // made per query from its own operands only, so a result never depends on which other queries share the warp or the batch.

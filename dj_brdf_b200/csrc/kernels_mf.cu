@@ -286,7 +286,7 @@ struct PairS { float4 a, b, c, d; }; // i.xyz o.x | o.yz h.xy | h.z den rcp_den 
 #define DJB200_COMPACT_MINB 1
 #endif
 template <int FK, int OP, bool FAST>
-__global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compact_kernel(const __grid_constant__ MfKernelArgs A)
+__global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compact_kernel(MfKernelArgs A)
 {
 	constexpr int NDF = NDF_BECKMANN;
 	constexpr int WARPS = MF_THREADS / 32;
@@ -306,8 +306,10 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 	uint2 *q = s_q[warp], *qs = s_qs[warp];
 	PairS *pairs = s_pair + warp * 32;
 
-	// one queued item, run by whichever lane picked it up: D from r2, then (unless D == 0) shadowing, Fresnel, quotient
-	auto finish = [&](uint2 item, long long kb) {
+	// one queued item, run by whichever lane picked it up: D from r2, then (unless D == 0) shadowing, Fresnel, quotient.
+	// Returns true when the 1e-5 tier declines the item (the reference's G is ill-conditioned for it): nothing was written, the
+	// caller moves the item to the slow queue, where every item takes the exact functions
+	auto finish = [&](uint2 item, long long kb) -> bool {
 		const int src = item.x & 31, m = item.x >> 8;
 		const PairS s = pairs[src];
 		PairX c;
@@ -319,15 +321,22 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 		const ParamsX &mx = s_params[m];
 		const long long slot = (long long)m * A.out_stride + kb + src;
 		const float r2 = __uint_as_float(item.y);
-		if (FAST && !(item.x & 0x80u) && r2 <= FAST_BECK_R2_MAX) { // the 1e-5 tier; the underflow tail (the slow queue) stays exact
-			if (OP == OP_PDF) A.out0[slot] = fast_pdf_tail<NDF>(s_exp2, mx, shadow, c, r2);
-			else st3(A.out0, slot, fast_evalp_tail<NDF, FK, OP>(s_exp2, mx, fr, shadow, c, r2));
-			return;
+		if (FAST && !(item.x & 0xC0u) && r2 <= FAST_BECK_R2_MAX) { // the 1e-5 tier; the underflow tail (the slow queue) stays exact
+			bool ill;
+			if (OP == OP_PDF) {
+				const float v = fast_pdf_try<NDF>(mx, shadow, c, r2, ill);
+				if (!ill) A.out0[slot] = v;
+			} else {
+				const V3 v = fast_evalp_try<NDF, FK, OP>(mx, fr, shadow, c, r2, ill);
+				if (!ill) st3(A.out0, slot, v);
+			}
+			return ill;
 		}
 		// item.y: r2, or the NaN-free marker "not facing" (D == 0 with a non-positive denominator: the rare literal case)
 		const float Dn = (item.x & 0x80u) ? 0.0f : lean_ndf_from_r2<NDF>(s_exp2, mx, c, r2);
 		if (OP == OP_PDF) A.out0[slot] = lean_skip(Dn, c) ? 0.0f : lean_pdf_tail<NDF>(s_exp2, mx.p, shadow, c, Dn);
 		else st3(A.out0, slot, lean_skip(Dn, c) ? lean_zero<OP>(c) : lean_evalp_tail<NDF, FK, OP>(s_exp2, mx.p, fr, shadow, c, Dn));
+		return false;
 	};
 
 	const long long stride = (long long)gridDim.x * blockDim.x;
@@ -377,7 +386,8 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 			for (;;) { // full batches; on the last trip whatever is left (the pair slots are reused afterwards)
 				uint2 *Q;
 				int cnt;
-				const bool fast = qn >= 32 || (last && qn > 0);
+				// a full slow batch goes first: a regular batch may hand up to 32 declined items over to the slow queue (64 slots)
+				const bool fast = qsn < 32 && (qn >= 32 || (last && qn > 0));
 				if (fast) { Q = q; cnt = qn; }
 				else if (qsn >= 32 || (last && qsn > 0)) { Q = qs; cnt = qsn; }
 				else break;
@@ -385,11 +395,17 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 				const int nb = cnt < 32 ? cnt : 32;
 				const uint2 item = Q[lane];
 				const uint2 rest = Q[32 + lane]; // only the first cnt - 32 are meaningful
-				if (lane < nb) finish(item, kb);
+				bool redo = false;
+				if (lane < nb) redo = finish(item, kb);
 				__syncwarp();
 				cnt -= nb;
 				if (lane < cnt) Q[lane] = rest;
 				if (fast) qn = cnt; else qsn = cnt;
+				if (FAST && fast) { // declined items: to the slow queue, marked "exact tier" (0x40)
+					const unsigned mask_r = __ballot_sync(FULL, redo);
+					if (redo) qs[qsn + __popc(mask_r & lt)] = make_uint2(item.x | 0x40u, item.y);
+					qsn += __popc(mask_r);
+				}
 				__syncwarp();
 			}
 		}
