@@ -478,10 +478,12 @@ static void launch_lean_tier(const MfKernelArgs &A, long long want, cudaStream_t
 template <int NDF, int FK, int OP, int PSRC>
 static void launch_lean(const MfKernelArgs &A, long long want, cudaStream_t st)
 {
-	// Beckmann eval / evalp / pdf on LEAN-texel params stay on the exact tier: those lobes are off-centre by construction, where
-	// the reference's G is ill-conditioned often enough (grazing directions opposite to the tilt: G1 > 1) that most warps
-	// would run the fast G first and the exact one after it (measured on bench.py's lean_shading leg: 2.48 ms against 2.01)
-	constexpr bool exact_only = NDF == NDF_BECKMANN && PSRC == PSRC_LEAN && OP != OP_SAMPLE;
+	// Beckmann eval / evalp / pdf with one params block per pair (PER_PAIR, LEAN texels) stay on the exact tier.  These kernels do
+	// not compact their work, so a lane the fast tier declines (underflow tail, ill-conditioned G of an off-centre lobe) runs the
+	// exact functions after its warp has run the fast ones.  LEAN-texel lobes are off-centre by construction -- measured on
+	// bench.py's lean_shading leg: 2.48 ms against 2.01 fused, 3.2 against 2.4 through PER_PAIR blocks -- and for centred lobes
+	// the two tiers take the same time there (0.72 vs 0.74 ms per 2e7 pairs: the params traffic dominates)
+	constexpr bool exact_only = NDF == NDF_BECKMANN && PSRC != PSRC_BROADCAST && OP != OP_SAMPLE;
 	constexpr bool has_fast = (OP == OP_EVAL || OP == OP_EVALP || OP == OP_PDF || OP == OP_SAMPLE) && !exact_only;
 	if constexpr (has_fast) {
 		if (g_fast_tier.load(std::memory_order_relaxed) != 0) {

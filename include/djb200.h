@@ -117,7 +117,7 @@ DJB200_API djb200_status djb200_release_cache(void);
  *     the reference's own convergence tolerance: 2.2e-4 of the samples differ by more than 1e-5, 4.4e-6 by more than 1e-4.
  *   DJB200_PRECISION_REFERENCE_BITS: every query reproduces the reference's rounded floats (bit-identical on >= 99.99 % of
  *     results; the remainder are double-rounding ties of a device libm call).  Also selected by DJB200_PRECISION=bits in the
- *     environment.  evalp_is, Beckmann queries on LEAN-texel params, the table BRDFs, the fits and the maps always run at this
+ *     environment.  evalp_is, Beckmann eval / pdf with per-pair params (PER_PAIR, LEAN texels), the table BRDFs, the fits and the maps always run at this
  *     level. */
 enum { DJB200_PRECISION_REFERENCE_BITS = 0, DJB200_PRECISION_1E5 = 1 };
 DJB200_API djb200_status djb200_set_precision(int mode);
