@@ -932,12 +932,23 @@ DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, cons
 // Beckmann's underflow tail (r2 > 78) takes the exact functions; r2 > 103.5 (D == 0) is their cheap early-out.  The choice is
 // made per query from its own operands only, so a result never depends on which other queries share the warp or the batch.
 DJB_DEV bool fast_beck_exact_vote(float r2) { return !(r2 <= FAST_BECK_R2_MAX); }
+// r2 for GGX in the 1e-5 tier: D = 1 / (pi (1 + r2)^2 ...) turns a relative error e of r2 into at most 2 e, so the contracted
+// form (reciprocals instead of correctly rounded quotients) is enough; Beckmann's exp(-r2) needs the exact one (r2 e, r2 <= 100)
+template <int NDF>
+DJB_DEV float fast_ndf_r2(const ParamsX &m, const PairX &c)
+{
+	if (NDF != NDF_GGX) return lean_ndf_r2(m, c);
+	const float x = c.sx - m.p.tx, y = c.sy - m.p.ty;
+	const float xs = x * m.rcp_ax;
+	const float ys = __fmaf_rn(m.p.ax, y, -(m.rho_ay * x)) * m.rcp_nrm;
+	return __fmaf_rn(xs, xs, ys * ys);
+}
 // one (pair, material) query of the 1e-5 tier
 template <int NDF, int FK, int OP>
 DJB_DEV V3 fast_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bool shadow, const PairX &c)
 {
 	if (!c.facing) return c.den > 0.0f ? lean_zero<OP>(c) : lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
-	const float r2 = lean_ndf_r2(m, c);
+	const float r2 = fast_ndf_r2<NDF>(m, c);
 	if (NDF == NDF_BECKMANN && fast_beck_exact_vote(r2)) return lean_evalp<NDF, FK, OP>(T, m, f, shadow, c);
 	return fast_evalp_tail<NDF, FK, OP>(T, m, f, shadow, c, r2);
 }
@@ -945,7 +956,7 @@ template <int NDF>
 DJB_DEV float fast_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c)
 {
 	if (!c.facing) return c.den > 0.0f ? 0.0f : lean_pdf<NDF>(T, m, shadow, c);
-	const float r2 = lean_ndf_r2(m, c);
+	const float r2 = fast_ndf_r2<NDF>(m, c);
 	if (NDF == NDF_BECKMANN && fast_beck_exact_vote(r2)) return lean_pdf<NDF>(T, m, shadow, c);
 	return fast_pdf_tail<NDF>(T, m, shadow, c, r2);
 }

@@ -198,9 +198,12 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(const __grid_c
 #ifndef DJB200_BSAMPLE_MINB
 #define DJB200_BSAMPLE_MINB 5
 #endif
+#ifndef DJB200_FSAMPLE_MINB
+#define DJB200_FSAMPLE_MINB 1
+#endif
 constexpr int lean_min_blocks(int ndf, int op, int psrc, bool fast)
 {
-	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */ && !fast) ? DJB200_BSAMPLE_MINB : 1;
+	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */) ? (fast ? DJB200_FSAMPLE_MINB : DJB200_BSAMPLE_MINB) : 1;
 }
 
 template <int NDF, int FK, int OP, int PSRC, bool FAST>
