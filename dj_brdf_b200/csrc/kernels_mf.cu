@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(const __grid_c
 #define DJB200_BSAMPLE_MINB 5
 #endif
 #ifndef DJB200_FSAMPLE_MINB
-#define DJB200_FSAMPLE_MINB 1
+#define DJB200_FSAMPLE_MINB 4
 #endif
 constexpr int lean_min_blocks(int ndf, int op, int psrc, bool fast)
 {
