@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "djb_glibcf.h"
+#include "djb_dmath.cuh"
 
 namespace djb200 {
 
@@ -697,13 +698,13 @@ DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
 // m: djb200_sgd_data.ch, i.e. [3][11] = rhoD rhoS alpha p f0 f1 kap lambda c k theta0 per channel
 // x^y for x > 0 as exp(y log x): within ~1e-12 relative of pow() for the exponents the presets hold (|y log x| < 3e4), i.e. the
 // same float after the final rounding in all but ~1e-5 of cases, at less than half of pow()'s double operations
-DJB_DEV double pow_pos(double x, double y) { return exp(y * log(x)); }
+DJB_DEV double pow_pos(double x, double y) { return exp_d(y * log_d(x)); } // djb_dmath.cuh: constant-bank polynomials
 DJB_DEV double sgd_g1_ch(double acos_kz, const double *m) // sgd__g1, :3415-3422
 {
 	const double t1 = acos_kz - m[10];
 	// theta <= theta0: pow(0, k) = 0, exp(c 0) = 1, 1 + lambda 0 = 1 exactly (k > 0, c and lambda finite in every preset)
 	if (!(t1 > 0.0) && m[9] > 0.0) return t1 == t1 ? 1.0 : t1;
-	double t3 = 1.0 + m[7] * (1.0 - exp(m[8] * pow_pos(t1, m[9])));
+	double t3 = 1.0 + m[7] * (1.0 - exp_d(m[8] * pow_pos(t1, m[9])));
 	t3 = 0.0 > t3 ? 0.0 : t3;
 	return 1.0 < t3 ? 1.0 : t3;
 }
@@ -731,7 +732,7 @@ DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o) // sgd::eval, :34
 		const float g1i = (float)sgd_g1_ch(ai, mc), g1o = (float)sgd_g1_ch(ao, mc);
 		const double ax = mc[2] + t2 / mc[2];
 		// sgd__ndf, :3424-3432: (kap exp(-ax) / pi) / (ax^p c2 c2), the two exponentials merged into one
-		const float nd = ax > 0.0 ? (float)((mc[6] * exp(-ax - mc[3] * log(ax)) * inv_pi) / (c2 * c2))
+		const float nd = ax > 0.0 ? (float)((mc[6] * exp_d(-ax - mc[3] * log_d(ax)) * inv_pi) / (c2 * c2))
 		                          : (float)((mc[6] * exp(-ax) * inv_pi) / (pow(ax, mc[3]) * c2 * c2));
 		fdg[c] = (f3[c] * nd) * (g1i * g1o);
 		kd[c] = (float)mc[0];
@@ -749,7 +750,8 @@ DJB_DEV V3 abc_eval1(const double *__restrict__ m, V3 i, V3 o) // abc::eval, :36
 	const float g1_i = fmin_ref(1.0f, 2.0f * (h.z * i.z / dot(h, i))); // abc::gaf, :3649-3655
 	const float g1_o = fmin_ref(1.0f, 2.0f * (h.z * o.z / dot(h, o)));
 	const float G = fmin_ref(g1_i, g1_o);
-	const double den = pow(1.0 + m[6] * (1.0 - (double)h.z), m[7]); // abc__ndf, :3608-3613
+	const double base = 1.0 + m[6] * (1.0 - (double)h.z);
+	const double den = base > 0.0 ? pow_pos(base, m[7]) : pow(base, m[7]); // abc__ndf, :3608-3613
 	const float r1 = rcp_via_double((float)DJB_PI), r2 = rcp_via_double((float)(DJB_PI * (double)i.z * (double)o.z));
 	float out[3];
 #pragma unroll

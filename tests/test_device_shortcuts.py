@@ -77,3 +77,17 @@ def test_restated_glibc_float_functions_are_bit_identical_to_libm(tmp_path):
     r = subprocess.run([str(exe), "331"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert r.stdout.count(" 0 mismatches") == 3, r.stdout
+
+
+def test_lean_double_exp_log_match_libm(tmp_path):
+    """dj_brdf_b200/csrc/djb_dmath.cuh (constant-bank exp / log of the analytic BRDF kernels) compiled for the host against libm:
+    <= 4 ulp of double over 2e7 arguments per function (measured 1.0), identical special cases."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "dmath_check"
+    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", f"-I{root / 'dj_brdf_b200/csrc'}", str(root / "tests/cpp/dmath_check.cpp"),
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
