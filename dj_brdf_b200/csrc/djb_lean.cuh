@@ -987,7 +987,8 @@ DJB_DEV float rsq_fast(float x)
 	const float r = mufu_rsq(x);
 	return __fmaf_rn(0.5f * r, __fmaf_rn(-(x * r), r, 1.0f), r);
 }
-// djb::erfinv (Giles), dj_brdf.h:691-721, with w = -ln((1 - u)(1 + u)) from MUFU.LG2
+// djb::erfinv (Giles), dj_brdf.h:691-721, with w = -ln((1 - u)(1 + u)) from MUFU.LG2.  (One Horner chain on selected
+// coefficients instead of the two branches was measured: 22.7 -> 24.4 ms for Beckmann sampling; the branch stays.)
 DJB_DEV float erfinv_fast(float u)
 {
 	float w = mufu_lg2((1.0f - u) * (1.0f + u)) * -0x1.62e430p-1f;
