@@ -600,3 +600,29 @@ def test_fast_tier_sample_vs_exact_tier_at_scale(djb, port, ndf):
     else:
         assert f5 >= 0.9995 and f4 >= 0.99998 and worst <= 5e-2
     assert d.double().mean().item() <= 3e-7
+
+
+@pytest.mark.parametrize("ndf", ["ggx", "beckmann"])
+def test_fast_tier_many_materials_and_host_arrays(djb, port, ndf):
+    """The default tier through the other plumbing: 300 params blocks (more than one shared-memory stage of 256, not in the kernel
+    arguments), host (numpy) arrays through the staged pipeline, an odd pair count -- against the exact tier on the same inputs."""
+    n = 10_007
+    wi, wo, u = cases.pairs(n, stream=700)
+    rng = np.random.default_rng(9)
+    mats = np.stack([djb.params.elliptic(float(np.exp(rng.uniform(np.log(0.02), np.log(0.8)))),
+                                         float(np.exp(rng.uniform(np.log(0.02), np.log(0.8)))), float(rng.uniform(0, np.pi)))
+                     for _ in range(299)] + [djb.params.pdfparams(0.3, 0.2, 0.4, 0.3, -0.4)])
+    b = (djb.ggx if ndf == "ggx" else djb.beckmann)(djb.fresnel.schlick([0.9, 0.5, 0.2]))
+    try:
+        djb.set_precision("bits")
+        want = {q: getattr(b, q)(wi, wo, mats) for q in ("eval", "pdf")}
+        want_s = b.sample(u, wo, mats)
+        djb.set_precision("1e-5")
+        for q in ("eval", "pdf"):
+            got = getattr(b, q)(wi, wo, mats)
+            assert got.shape == want[q].shape and got.shape[0] == 300
+            check_1e5(got, want[q], f"{ndf} {q}, 300 materials, host arrays")
+        err = sample_err(b.sample(u, wo, mats), want_s)
+        assert (err <= 1e-5).mean() >= (1.0 if ndf == "ggx" else 0.999), (err <= 1e-5).mean()
+    finally:
+        djb.set_precision("bits")
