@@ -636,6 +636,9 @@ DJB_DEV int merl_cell(V3 i, V3 o)
 constexpr int UT_NTI = 6, UT_NPI = 48, UT_NTV = 6, UT_NPV = 48;
 constexpr int UT_CELLS = 3 * UT_NTI * UT_NPI * UT_NTV * UT_NPV;
 
+// x^y for x > 0 as exp(y log x): within ~1e-12 relative of pow() for the exponents the presets hold (|y log x| < 3e4), i.e. the
+// same float after the final rounding in all but ~1e-5 of cases, at less than half of pow()'s double operations
+DJB_DEV double pow_pos(double x, double y) { return exp_d(y * log_d(x)); } // djb_dmath.cuh: constant-bank polynomials
 DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
 {
 	const float r2d = (float)(180.0 / DJB_PI);
@@ -683,7 +686,7 @@ DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
 			acc += w * __ldg(tab + idx);
 		}
 		if ((double)acc > 0.0375)
-			acc = (float)pow((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f);
+			acc = (float)pow_pos((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f); // base > 0.0875: pow as exp(y log x)
 		else
 			acc /= 12.92f;
 		rgb[isp] = acc * 100.0f;
@@ -696,9 +699,6 @@ DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
 // Coefficients stay doubles (they are doubles in the reference's tables); the per-channel helpers run in double and
 // their results are narrowed where the reference's vec3::from_raw narrows them.
 // m: djb200_sgd_data.ch, i.e. [3][11] = rhoD rhoS alpha p f0 f1 kap lambda c k theta0 per channel
-// x^y for x > 0 as exp(y log x): within ~1e-12 relative of pow() for the exponents the presets hold (|y log x| < 3e4), i.e. the
-// same float after the final rounding in all but ~1e-5 of cases, at less than half of pow()'s double operations
-DJB_DEV double pow_pos(double x, double y) { return exp_d(y * log_d(x)); } // djb_dmath.cuh: constant-bank polynomials
 DJB_DEV double sgd_g1_ch(double acos_kz, const double *m) // sgd__g1, :3415-3422
 {
 	const double t1 = acos_kz - m[10];
