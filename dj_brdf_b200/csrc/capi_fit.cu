@@ -39,7 +39,10 @@ struct BlockCache {
 	}
 	void give(void *p, size_t bytes, int device)
 	{
-		if (total + bytes > (256u << 20) || free_.size() >= 256) { cudaFree(p); return; }
+		int cur = -1;
+		cudaGetDevice(&cur);
+		// a block of another device than the current one is simply freed (the synchronisation below covers the current device only)
+		if (cur != device || total + bytes > (256u << 20) || free_.size() >= 256) { cudaFree(p); return; }
 		cudaDeviceSynchronize(); // nothing in flight may still use the block when it is handed out again
 		free_.push_back({p, bytes, device});
 		total += bytes;
