@@ -21,7 +21,8 @@ BUILD = PKG / "build"
 LIB = PKG / "libdjb200.so"
 SOURCES = ["capi.cu", "capi_fit.cu", "kernels_mf.cu", "kernels_tables.cu", "kernels_merl.cu", "kernels_fit.cu", "kernels_tabular.cu",
            "kernels_analytic.cu", "presets.cu"]
-HEADERS = ["djb_presets.inc", "djb_device.cuh", "djb_lean.cuh", "djb_fit.cuh", "djb_internal.h", "../../include/djb200.h"]
+HEADERS = ["djb_presets.inc", "djb_device.cuh", "djb_lean.cuh", "djb_fit.cuh", "djb_internal.h", "djb_dmath.cuh", "djb_dmath_tables.inc",
+           "djb_glibcf.h", "../../include/djb200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

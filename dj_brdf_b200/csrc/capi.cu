@@ -1068,9 +1068,9 @@ djb200_status djb200_utia_create(const double *raw_samples, djb200_utia **out)
 	djb200_status rs = require_device();
 	if (rs != DJB200_OK) return rs;
 	double *tmp = nullptr;
-	float *table = nullptr;
+	float4 *table = nullptr;
 	CU(cudaMalloc(&tmp, sizeof(double) * UTIA_N));
-	cudaError_t e = cudaMalloc(&table, sizeof(float) * UTIA_N);
+	cudaError_t e = cudaMalloc(&table, sizeof(float4) * (UTIA_N / 3));
 	if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "cudaMalloc(utia table)"); }
 	e = cudaMemcpy(tmp, raw_samples, sizeof(double) * UTIA_N, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = launch_utia_convert(tmp, table, 0);
@@ -1108,7 +1108,7 @@ djb200_status djb200_utia_eval(const djb200_utia *u, const float *wi, const floa
                                int mem, void *stream)
 {
 	if (!u) return fail(DJB200_ERR_INVALID_ARGUMENT, "utia handle is NULL");
-	const float *table = u->table;
+	const float4 *table = u->table;
 	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_rgb, 12}}, mem, stream,
 		[table](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
 			return launch_utia_eval(table, (const float *)i[0], (const float *)i[1], cn, (float *)o[0], st);

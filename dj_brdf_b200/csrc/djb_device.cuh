@@ -239,11 +239,11 @@ DJB_DEV V3 fresnel_eval(const FresnelDev &f, float c)
 	} else if (FK == FK_UNPOLARIZED) {
 		return mk(unpolarized_channel(c, f.v[0]), unpolarized_channel(c, f.v[1]), unpolarized_channel(c, f.v[2]));
 	} else if (FK == FK_SGD) {
-		float pw = (float)pow(1.0 - (double)c, 5.0);
+		float pw = pow5_one_minus(c); // (float)pow(1.0 - (double)c, 5.0) for every float c (tests/cpp/dmath_check.cpp)
 		return mk((f.v[0] - c * f.v[3]) + pw * (1.0f - f.v[0]), (f.v[1] - c * f.v[4]) + pw * (1.0f - f.v[1]),
 		          (f.v[2] - c * f.v[5]) + pw * (1.0f - f.v[2]));
 	} else if (FK == FK_SPLINE) {
-		float u = (float)(2.0 * acos((double)c) / DJB_PI);
+		float u = acos_coord_pi(c); // (float)(2.0 * acos((double)c) / M_PI) for every float c (tests/cpp/dmath_check.cpp)
 		return spline_rgb(f.pts, f.npts, u);
 	}
 	return mk(1.0f, 1.0f, 1.0f);
@@ -639,24 +639,50 @@ constexpr int UT_CELLS = 3 * UT_NTI * UT_NPI * UT_NTV * UT_NPV;
 // x^y for x > 0 as exp(y log x): within ~1e-12 relative of pow() for the exponents the presets hold (|y log x| < 3e4), i.e. the
 // same float after the final rounding in all but ~1e-5 of cases, at less than half of pow()'s double operations
 DJB_DEV double pow_pos(double x, double y) { return exp_d(y * log_d(x)); } // djb_dmath.cuh: constant-bank polynomials
-DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
+
+// floor(x / d) for a float x >= 0 and d = 15 or 7.5 (utia's cell index, dj_brdf.h:1090-1100, is (int)floor((double)x / d)): the
+// float product with 1 / d may land on the wrong side of a multiple of d, the remainder x - q d -- exact in float, x and q d
+// share x's grid -- puts it back
+DJB_DEV int floor_div(float x, float d, float inv_d)
+{
+	int q = (int)floorf(x * inv_d);
+	const float r = __fmaf_rn(-d, (float)q, x);
+	if (r < 0.0f) --q;
+	else if (r >= d) ++q;
+	return q;
+}
+
+// utia::eval, dj_brdf.h:1063-1157.  `tab`: one float4 (r, g, b, 0) per (theta_i, phi_i, theta_v, phi_v) cell, so that a tap is one
+// 16-byte load instead of three 4-byte ones a plane apart; `T`: the djb_dmath.cuh table (shared memory in the query kernel)
+DJB_DEV V3 utia_eval1(const float4 *__restrict__ tab, V3 i, V3 o, const double *T)
 {
 	const float r2d = (float)(180.0 / DJB_PI);
-	float ti = (float)((double)r2d * acos((double)i.z)), to = (float)((double)r2d * acos((double)o.z));
-	float pi = (float)((double)r2d * atan2((double)i.y, (double)i.x));
-	float po = (float)((double)r2d * atan2((double)o.y, (double)o.x));
+	float ti = (float)((double)r2d * acos_d((double)i.z)), to = (float)((double)r2d * acos_d((double)o.z));
+	float pi = (float)((double)r2d * atan2_t((double)i.y, (double)i.x, T));
+	float po = (float)((double)r2d * atan2_t((double)o.y, (double)o.x, T));
 	if (ti >= 90.0f || to >= 90.0f) return mk(0.f, 0.f, 0.f);
 	while (pi < 0.0f) pi = (float)((double)pi + 360.0);
 	while (po < 0.0f) po = (float)((double)po + 360.0);
 	while (pi >= 360.0f) pi = (float)((double)pi - 360.0);
 	while (po >= 360.0f) po = (float)((double)po - 360.0);
 	int iti[2], itv[2], ipi[2], ipv[2];
-	iti[0] = (int)floor((double)ti / 15.0); iti[1] = iti[0] + 1;
+	if (ti >= 0.0f && to >= 0.0f) { // always, for finite directions
+		iti[0] = floor_div(ti, 15.0f, 1.0f / 15.0f);
+		itv[0] = floor_div(to, 15.0f, 1.0f / 15.0f);
+		ipi[0] = floor_div(pi, 7.5f, 1.0f / 7.5f);
+		ipv[0] = floor_div(po, 7.5f, 1.0f / 7.5f);
+	} else {
+		iti[0] = (int)floor((double)ti / 15.0);
+		itv[0] = (int)floor((double)to / 15.0);
+		ipi[0] = (int)floor((double)pi / 7.5);
+		ipv[0] = (int)floor((double)po / 7.5);
+	}
+	iti[1] = iti[0] + 1;
 	if (iti[0] > UT_NTI - 2) { iti[0] = UT_NTI - 2; iti[1] = UT_NTI - 1; }
-	itv[0] = (int)floor((double)to / 15.0); itv[1] = itv[0] + 1;
+	itv[1] = itv[0] + 1;
 	if (itv[0] > UT_NTV - 2) { itv[0] = UT_NTV - 2; itv[1] = UT_NTV - 1; }
-	ipi[0] = (int)floor((double)pi / 7.5); ipi[1] = ipi[0] + 1;
-	ipv[0] = (int)floor((double)po / 7.5); ipv[1] = ipv[0] + 1;
+	ipi[1] = ipi[0] + 1;
+	ipv[1] = ipv[0] + 1;
 	float sum, wti[2], wtv[2], wpi[2], wpv[2];
 	wti[1] = ti - (float)(15.0 * iti[0]); wti[0] = (float)(15.0 * iti[1]) - ti;
 	sum = wti[0] + wti[1]; wti[0] /= sum; wti[1] /= sum;
@@ -668,25 +694,27 @@ DJB_DEV V3 utia_eval1(const float *__restrict__ tab, V3 i, V3 o)
 	sum = wpv[0] + wpv[1]; wpv[0] /= sum; wpv[1] /= sum;
 	if (ipi[1] == UT_NPI) ipi[1] = 0;
 	if (ipv[1] == UT_NPV) ipv[1] = 0;
-	const int nc = UT_NPV * UT_NTV, nr = UT_NPI * UT_NTI;
-	float rgb[3];
+	const int nc = UT_NPV * UT_NTV;
+	float rgb[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+	for (int a = 0; a < 2; ++a)
+#pragma unroll
+	for (int b = 0; b < 2; ++b)
+#pragma unroll
+	for (int c = 0; c < 2; ++c)
+#pragma unroll
+	for (int d = 0; d < 2; ++d) { // the reference's order of the 16 taps, per channel
+		const float w = wti[a] * wtv[b] * wpi[c] * wpv[d];
+		const float4 v = __ldg(tab + (nc * (UT_NPI * iti[a] + ipi[c]) + UT_NPV * itv[b] + ipv[d]));
+		rgb[0] += w * v.x;
+		rgb[1] += w * v.y;
+		rgb[2] += w * v.z;
+	}
 #pragma unroll
 	for (int isp = 0; isp < 3; ++isp) {
-		float acc = 0.0f;
-#pragma unroll
-		for (int a = 0; a < 2; ++a)
-#pragma unroll
-		for (int b = 0; b < 2; ++b)
-#pragma unroll
-		for (int c = 0; c < 2; ++c)
-#pragma unroll
-		for (int d = 0; d < 2; ++d) {
-			float w = wti[a] * wtv[b] * wpi[c] * wpv[d];
-			int idx = isp * nr * nc + nc * (UT_NPI * iti[a] + ipi[c]) + UT_NPV * itv[b] + ipv[d];
-			acc += w * __ldg(tab + idx);
-		}
+		float acc = rgb[isp];
 		if ((double)acc > 0.0375)
-			acc = (float)pow_pos((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f); // base > 0.0875: pow as exp(y log x)
+			acc = (float)pow_pos_t((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f, T); // base > 0.0875: exp(y log x)
 		else
 			acc /= 12.92f;
 		rgb[isp] = acc * 100.0f;
@@ -708,7 +736,62 @@ DJB_DEV double sgd_g1_ch(double acos_kz, const double *m) // sgd__g1, :3415-3422
 	t3 = 0.0 > t3 ? 0.0 : t3;
 	return 1.0 < t3 ? 1.0 : t3;
 }
-DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o) // sgd::eval, :3454-3469
+// the general path: every special case of the reference (zero / negative / non-finite intermediate values) through the library
+static __device__ __noinline__ V3 sgd_eval1_general(const double *__restrict__ m, float iz, float oz, float hz, V3 Fr)
+{
+	const float f3[3] = {Fr.x, Fr.y, Fr.z};
+	float out[3];
+	const double ai = acos((double)iz), ao = acos((double)oz);
+	const double ch = (double)hz, c2 = ch * ch, t2 = (1.0 - c2) / c2;
+	const double inv_pi = 1.0 / DJB_PI;
+	const float r1 = rcp_via_double(iz * oz), r2 = rcp_via_double((float)DJB_PI);
+	for (int c = 0; c < 3; ++c) {
+		const double *mc = m + 11 * c;
+		const float g1i = (float)sgd_g1_ch(ai, mc), g1o = (float)sgd_g1_ch(ao, mc);
+		const double ax = mc[2] + t2 / mc[2];
+		// sgd__ndf, :3424-3432: (kap exp(-ax) / pi) / (ax^p c2 c2), the two exponentials merged into one
+		const float nd = ax > 0.0 ? (float)((mc[6] * exp_d(-ax - mc[3] * log_d(ax)) * inv_pi) / (c2 * c2))
+		                          : (float)((mc[6] * exp(-ax) * inv_pi) / (pow(ax, mc[3]) * c2 * c2));
+		const float fdg = (f3[c] * nd) * (g1i * g1o);
+		out[c] = r2 * ((float)mc[0] + r1 * ((float)mc[1] * fdg));
+	}
+	return mk(out[0], out[1], out[2]);
+}
+// sgd__g1 of one direction for the three channels at once (straight-line code: the three chains of double operations interleave).
+// Returns false when a value leaves the range of the table-driven exp / log (the caller then takes the general path).
+DJB_DEV bool sgd_g1_x3(double acos_kz, const double *__restrict__ m, const double *T, float *g1)
+{
+	double t1[3], w[3];
+	bool pos[3], ok = true, any = false;
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		t1[c] = acos_kz - m[11 * c + 10];
+		pos[c] = t1[c] > 0.0;
+		any = any || pos[c];
+		ok = ok && t1[c] == t1[c] && (pos[c] || m[11 * c + 9] > 0.0); // theta <= theta0 with k > 0: exactly 1 (see sgd_g1_ch)
+	}
+	g1[0] = g1[1] = g1[2] = 1.0f;
+	if (!any) return ok;
+	// pow(t1, k) = exp(k log t1); below -700 it is < 1e-304: c times it is 0 to the exponential that follows (|c| < 1e200 checked),
+	// so the clamp changes nothing.  An exponential of less than -700 is < 1e-304: 1 - it is 1 either way.
+#pragma unroll
+	for (int c = 0; c < 3; ++c) w[c] = m[11 * c + 9] * log_t_core(pos[c] ? t1[c] : 1.0, T);
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		ok = ok && (!pos[c] || (w[c] <= 700.0 && fabs(m[11 * c + 8]) < 1e200));
+		w[c] = m[11 * c + 8] * exp_t_core(fmin(fmax(w[c], -700.0), 700.0), T);
+	}
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		ok = ok && (!pos[c] || w[c] <= 700.0);
+		double t3 = 1.0 + m[11 * c + 7] * (1.0 - exp_t_core(fmin(fmax(w[c], -700.0), 700.0), T));
+		t3 = 0.0 > t3 ? 0.0 : t3;
+		t3 = 1.0 < t3 ? 1.0 : t3;
+		if (pos[c]) g1[c] = (float)t3;
+	}
+	return ok;
+}
+DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o, const double *T) // sgd::eval, :3454-3469
 {
 	if (!(i.z > 0.0f && o.z > 0.0f)) return mk(0.f, 0.f, 0.f);
 	const V3 h = normalize(i + o);
@@ -721,28 +804,51 @@ DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o) // sgd::eval, :34
 		fr.v[3 + c] = (float)m[11 * c + 5];
 	}
 	const V3 Fr = fresnel_eval<FK_SGD>(fr, sat_ref(dot(i, h)));
-	const double ai = acos((double)i.z), ao = acos((double)o.z);
-	const double ch = (double)h.z, c2 = ch * ch, t2 = (1.0 - c2) / c2;
-	const double inv_pi = 1.0 / DJB_PI;
-	float fdg[3], ks[3], kd[3];
 	const float f3[3] = {Fr.x, Fr.y, Fr.z};
+	float out[3];
+	// the plain case: every logarithm of a positive normal number, every exponential within (-inf, 700], alpha and cos^4 in float
+	// range -- 9 logarithms and 15 exponentials through the table-driven forms, the divisions through one Newton step
+	const double ch = (double)h.z, c2 = ch * ch, c4 = c2 * c2;
+	bool ok = c4 >= 1e-30; // c2 <= 1
+	float g1i[3], g1o[3], nd[3];
+	if (ok) {
+		const double ai = acos_d((double)i.z), ao = acos_d((double)o.z);
+		ok = sgd_g1_x3(ai, m, T, g1i);
+		ok = sgd_g1_x3(ao, m, T, g1o) && ok;
+		const double t2 = div_core(1.0 - c2, c2);
+		double y = (double)dm_rcp_seed((float)c4); // 1 / c4 to full precision: two Newton steps
+		y = dm_fma(dm_fma(-c4, y, 1.0), y, y);
+		y = dm_fma(dm_fma(-c4, y, 1.0), y, y);
+		const double s = y * (1.0 / DJB_PI);
+		double ax[3], e[3];
+#pragma unroll
+		for (int c = 0; c < 3; ++c) {
+			const double al = m[11 * c + 2];
+			ok = ok && fabs(al) >= 1e-30 && fabs(al) <= 1e30;
+			ax[c] = al + div_core(t2, al);
+			ok = ok && log_d_ok(ax[c]);
+		}
+#pragma unroll
+		for (int c = 0; c < 3; ++c) e[c] = -ax[c] - m[11 * c + 3] * log_t_core(log_d_ok(ax[c]) ? ax[c] : 1.0, T);
+#pragma unroll
+		for (int c = 0; c < 3; ++c) {
+			ok = ok && e[c] <= 700.0;
+			// below -700 the exponential is < 1e-304 and kap / (pi cos^4) < 1e130 (checked): 0 as a float either way
+			ok = ok && fabs(m[11 * c + 6]) < 1e100;
+			nd[c] = (float)(m[11 * c + 6] * exp_t_core(fmin(fmax(e[c], -700.0), 700.0), T) * s);
+		}
+	}
+	if (!ok) return sgd_eval1_general(m, i.z, o.z, h.z, Fr);
+	const float r1 = rcp_via_double(i.z * o.z), r2 = rcp_via_double((float)DJB_PI);
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
-		const double *mc = m + 11 * c;
-		const float g1i = (float)sgd_g1_ch(ai, mc), g1o = (float)sgd_g1_ch(ao, mc);
-		const double ax = mc[2] + t2 / mc[2];
-		// sgd__ndf, :3424-3432: (kap exp(-ax) / pi) / (ax^p c2 c2), the two exponentials merged into one
-		const float nd = ax > 0.0 ? (float)((mc[6] * exp_d(-ax - mc[3] * log_d(ax)) * inv_pi) / (c2 * c2))
-		                          : (float)((mc[6] * exp(-ax) * inv_pi) / (pow(ax, mc[3]) * c2 * c2));
-		fdg[c] = (f3[c] * nd) * (g1i * g1o);
-		kd[c] = (float)mc[0];
-		ks[c] = (float)mc[1];
+		const float fdg = (f3[c] * nd[c]) * (g1i[c] * g1o[c]);
+		out[c] = r2 * ((float)m[11 * c] + r1 * ((float)m[11 * c + 1] * fdg));
 	}
-	const float r1 = rcp_via_double(i.z * o.z), r2 = rcp_via_double((float)DJB_PI);
-	return mk(r2 * (kd[0] + r1 * (ks[0] * fdg[0])), r2 * (kd[1] + r1 * (ks[1] * fdg[1])), r2 * (kd[2] + r1 * (ks[2] * fdg[2])));
+	return mk(out[0], out[1], out[2]);
 }
 // m: kD[3] A[3] B C ior (djb200_abc_data)
-DJB_DEV V3 abc_eval1(const double *__restrict__ m, V3 i, V3 o) // abc::eval, :3633-3647
+DJB_DEV V3 abc_eval1(const double *__restrict__ m, V3 i, V3 o, const double *T) // abc::eval, :3633-3647
 {
 	if (!(i.z > 0.0f && o.z > 0.0f)) return mk(0.f, 0.f, 0.f);
 	const V3 h = normalize(i + o);
@@ -751,7 +857,7 @@ DJB_DEV V3 abc_eval1(const double *__restrict__ m, V3 i, V3 o) // abc::eval, :36
 	const float g1_o = fmin_ref(1.0f, 2.0f * (h.z * o.z / dot(h, o)));
 	const float G = fmin_ref(g1_i, g1_o);
 	const double base = 1.0 + m[6] * (1.0 - (double)h.z);
-	const double den = base > 0.0 ? pow_pos(base, m[7]) : pow(base, m[7]); // abc__ndf, :3608-3613
+	const double den = base > 0.0 ? pow_pos_t(base, m[7], T) : pow(base, m[7]); // abc__ndf, :3608-3613
 	const float r1 = rcp_via_double((float)DJB_PI), r2 = rcp_via_double((float)(DJB_PI * (double)i.z * (double)o.z));
 	float out[3];
 #pragma unroll

@@ -11,7 +11,7 @@ namespace djb200 {
 struct FitSourceDev {
 	int kind;             // djb200_source_kind
 	const float4 *merl;   // scaled cells
-	const float *utia;    // normalised float table
+	const float4 *utia;   // normalised float table, one (r, g, b, 0) per cell
 	int ndf, shadow, fresnel_kind;
 	FresnelDev fr;        // fr.pts: device pointer
 	double coef[33];      // SGD: djb200_sgd_data.ch flattened; ABC: djb200_abc_data (9 values)
@@ -46,9 +46,9 @@ DJB_DEV V3 mf_eval_rt(const Params &p, int fk, const FresnelDev &f, bool shadow,
 DJB_DEV V3 source_eval(const FitSourceDev &s, V3 i, V3 o)
 {
 	if (s.kind == DJB200_SOURCE_MERL) return merl_eval1(s.merl, i, o);
-	if (s.kind == DJB200_SOURCE_UTIA) return utia_eval1(s.utia, i, o);
-	if (s.kind == DJB200_SOURCE_SGD) return sgd_eval1(s.coef, i, o);
-	if (s.kind == DJB200_SOURCE_ABC) return abc_eval1(s.coef, i, o);
+	if (s.kind == DJB200_SOURCE_UTIA) return utia_eval1(s.utia, i, o, g_dm_table_dev);
+	if (s.kind == DJB200_SOURCE_SGD) return sgd_eval1(s.coef, i, o, g_dm_table_dev);
+	if (s.kind == DJB200_SOURCE_ABC) return abc_eval1(s.coef, i, o, g_dm_table_dev);
 	const Params p = standard_params();
 	if (s.ndf == NDF_GGX) return mf_eval_rt<NDF_GGX>(p, s.fresnel_kind, s.fr, s.shadow != 0, i, o);
 	return mf_eval_rt<NDF_BECKMANN>(p, s.fresnel_kind, s.fr, s.shadow != 0, i, o);
@@ -86,20 +86,22 @@ DJB_DEV float spline2d_f(const float *pts, int w, int h, float u1, float u2)
 }
 
 // djb::tabular (radial tables), dj_brdf.h:2151-2163
+// The table coordinates are functions of one float: djb_dmath.cuh's versions give the reference's (libm's) float for every argument
+// (acos_coord: all but one of 2.1e9; tests/cpp/dmath_check.cpp).  `T`: the djb_dmath.cuh table -- shared memory in the query kernels,
+// g_dm_table_dev (global memory) in the fit kernels.
 struct TabIso {
 	const float *p22, *sigma;
 	int n;
+	const double *T;
 	DJB_DEV float p22_radial(float r2) const
 	{
-		float r = (float)sqrt((double)r2);
-		float u = (float)sqrt(2.0 * atan((double)r) / (double)(float)DJB_PI);
-		return spline_f(p22, n, u);
+		float r = __fsqrt_rn(r2); // == (float)sqrt((double)r2)
+		return spline_f(p22, n, atan_coord(r, T));
 	}
 	DJB_DEV float p22_std(float x, float y) const { return p22_radial(x * x + y * y); }
 	DJB_DEV float sigma_std(V3 k) const
 	{
-		float u = (float)(2.0 * acos((double)k.z) / (double)(float)DJB_PI);
-		return spline_f(sigma, n, u);
+		return spline_f(sigma, n, acos_coord(k.z));
 	}
 };
 
@@ -107,6 +109,7 @@ struct TabIso {
 struct TabAniso {
 	const float *p22, *sigma;
 	int w, h; // elevation_res, azimuthal_res
+	const double *T;
 	DJB_DEV float p22_theta_phi(float theta, float phi) const
 	{
 		if ((double)phi < 0.0) phi = (float)((double)phi + 2.0 * DJB_PI);
@@ -116,14 +119,14 @@ struct TabAniso {
 	}
 	DJB_DEV float p22_std(float x, float y) const
 	{
-		float theta = (float)atan(sqrt((double)(x * x + y * y)));
-		float phi = (float)atan2((double)(-y), (double)(-x));
+		float theta = (float)atan_t(sqrt_d((double)(x * x + y * y)), T);
+		float phi = (float)atan2_t((double)(-y), (double)(-x), T);
 		return p22_theta_phi(theta, phi);
 	}
 	DJB_DEV float sigma_std(V3 k) const
 	{
-		float theta = (float)acos((double)k.z);
-		float phi = (float)atan2((double)k.y, (double)k.x);
+		float theta = (float)acos_d((double)k.z);
+		float phi = (float)atan2_t((double)k.y, (double)k.x, T);
 		if ((double)phi < 0.0) phi = (float)((double)phi + 2.0 * DJB_PI);
 		float u1 = (float)((double)theta * 2.0 / DJB_PI);
 		float u2 = (float)((double)phi * 0.5 / DJB_PI);
@@ -138,7 +141,7 @@ DJB_DEV float tab_sigma(const T &t, const Params &p, V3 k)
 	float a = k.x * p.ax + k.y * p.ay * p.rho;
 	float b = k.y * p.ay * p.srho;
 	float c = k.z - k.x * p.tx - k.y * p.ty;
-	float nrm = (float)sqrt((double)(a * a + b * b + c * c));
+	float nrm = __fsqrt_rn(a * a + b * b + c * c); // == (float)sqrt((double)(...))
 	V3 ks = scale(rcp_via_double(nrm), mk(a, b, c));
 	return nrm * t.sigma_std(ks);
 }
@@ -181,7 +184,7 @@ DJB_DEV float tab_eval_ideal(const T &t, const Params &p, bool shadow, V3 i, V3 
 	float e = 0.0f;
 	if (G > 0.0f) {
 		float Dn = tab_ndf(t, p, h);
-		e = 1.0f * (float)((double)(Dn * G) / (4.0 * (double)o.z));
+		e = 1.0f * __fdiv_rn(Dn * G, 4.0f * o.z); // == (float)((double)(Dn * G) / (4.0 * (double)o.z))
 	}
 	return rcp_via_double(i.z) * e;
 }

@@ -24,15 +24,17 @@ inline int grid_for(int64_t n)
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(TB) analytic_eval_kernel(const AnalyticCoef m, const float *__restrict__ wi,
+__global__ void __launch_bounds__(TB) analytic_eval_kernel(const __grid_constant__ AnalyticCoef m, const float *__restrict__ wi,
                                                            const float *__restrict__ wo, long long n,
                                                            float *__restrict__ out)
 {
+	__shared__ __align__(16) double s_dm[DMT_COUNT]; // djb_dmath.cuh: tables of the double exp / log
+	dm_load_tables(s_dm);
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
 		const V3 i = mk(wi[3 * k], wi[3 * k + 1], wi[3 * k + 2]);
 		const V3 o = mk(wo[3 * k], wo[3 * k + 1], wo[3 * k + 2]);
-		const V3 r = KIND == DJB200_SOURCE_SGD ? sgd_eval1(m.v, i, o) : abc_eval1(m.v, i, o);
+		const V3 r = KIND == DJB200_SOURCE_SGD ? sgd_eval1(m.v, i, o, s_dm) : abc_eval1(m.v, i, o, s_dm);
 		out[3 * k] = r.x;
 		out[3 * k + 1] = r.y;
 		out[3 * k + 2] = r.z;

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_tabular_kernel(IsoFitArgs A)
 	const Params sp = standard_params();
 	FIT_PHASE(0);
 	TabIso tab;
-	tab.p22 = s_p22; tab.sigma = s_sigma; tab.n = res;
+	tab.p22 = s_p22; tab.sigma = s_sigma; tab.n = res; tab.T = g_dm_table_dev;
 
 	// ---- compute_p22_smith, dj_brdf.h:2482-2522 ------------------------------------------------
 	const float dphi_h = (float)(DJB_PI / 180.0);
@@ -749,7 +749,7 @@ __global__ void aniso_norm_terms_kernel(AnisoGeom g, const float *p22, float *te
 	if (e >= AN_NPHI * AN_NTHETA) return;
 	int j = e / AN_NTHETA, i = e - j * AN_NTHETA;
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
-	TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar;
+	TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar; t.T = g_dm_table_dev;
 	float u = (float)j / (float)AN_NPHI;
 	float phi = (float)((double)u * 2.0 * DJB_PI);
 	float ui = (float)i / (float)AN_NTHETA;
@@ -835,7 +835,7 @@ __global__ void aniso_sigma_pre_kernel(AnisoGeom g, const float *p22, float *nd,
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
 	if (e < AS_NPHI * AS_NTHETA) {
 		int j2 = e / AS_NTHETA, j1 = e - j2 * AS_NTHETA;
-		TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar;
+		TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar; t.T = g_dm_table_dev;
 		float phi = (float)((double)((float)j2 / (float)AS_NPHI) * 2.0 * DJB_PI);
 		float theta = (float)((double)((float)j1 / (float)AS_NTHETA) * sqrt_half_pi);
 		nd[e] = tab_ndf(t, standard_params(), spherical(theta * theta, phi));
@@ -908,7 +908,7 @@ __global__ void aniso_sigma_table_kernel(AnisoGeom g, const float *sigma_rows, f
 __global__ void __launch_bounds__(128) aniso_fresnel_ratio_kernel(FitSourceDev src, AnisoGeom g, int shadow, const float *p22,
                                                                   const float *sigma, float4 *ws)
 {
-	TabAniso t; t.p22 = p22; t.sigma = sigma; t.w = g.er; t.h = g.ar;
+	TabAniso t; t.p22 = p22; t.sigma = sigma; t.w = g.er; t.h = g.ar; t.T = g_dm_table_dev;
 	const int cnt = g.er - 1, stride = cnt + 2;
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= cnt * stride) return;
@@ -963,7 +963,7 @@ __global__ void aniso_param_terms_kernel(AnisoGeom g, const float *p22, float *t
 	if (e >= N) return;
 	int j = e / AP_NTHETA, i = e - j * AP_NTHETA;
 	const double sqrt_half_pi = sqrt(DJB_PI * 0.5);
-	TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar;
+	TabAniso t; t.p22 = p22; t.sigma = nullptr; t.w = g.er; t.h = g.ar; t.T = g_dm_table_dev;
 	float phi = (float)((double)((float)j / (float)AP_NPHI) * 2.0 * DJB_PI);
 	float cos_phi = (float)cos((double)phi), sin_phi = (float)sin((double)phi);
 	float cos_phi_sqr = cos_phi * cos_phi, sin_phi_sqr = sin_phi * sin_phi;

@@ -56,7 +56,7 @@ DJB_DEV V3 tabq_evalp(const TB &B, const Params &p, V3 i, V3 o)
 		float cd = sat_ref(dot(o, h));
 		V3 Fr = fresnel_eval<FK_SPLINE>(B.fr, cd);
 		float Dn = tab_ndf(B.t, p, h);
-		return scale((float)((double)(Dn * G) / (4.0 * (double)o.z)), Fr);
+		return scale(__fdiv_rn(Dn * G, 4.0f * o.z), Fr); // == (float)((double)(Dn * G) / (4.0 * (double)o.z)): one IEEE op
 	}
 	return mk(0.f, 0.f, 0.f);
 }
@@ -67,7 +67,7 @@ DJB_DEV float tabq_pdf(const TB &B, const Params &p, V3 i, V3 o)
 {
 	V3 h = normalize(i + o);
 	float G = tabq_gaf(B, p, i, o);
-	if (G > 0.0f) return (float)((double)(h.z * tab_ndf(B.t, p, h)) / (4.0 * (double)dot(i, h)));
+	if (G > 0.0f) return __fdiv_rn(h.z * tab_ndf(B.t, p, h), 4.0f * dot(i, h)); // == the quotient in double, rounded once more
 	return 0.0f;
 }
 
@@ -143,7 +143,7 @@ DJB_DEV V3 tabq_evalp_is(const TB &B, const Params &p, float u1, float u2, V3 o,
 	if (G > 0.0f) {
 		float cd = sat_ref(dot(o, h));
 		i_out = i;
-		float pdf = (float)((double)(h.z * tab_ndf(B.t, p, h)) / (4.0 * (double)cd));
+		float pdf = __fdiv_rn(h.z * tab_ndf(B.t, p, h), 4.0f * cd);
 		pdf_out = pdf;
 		return scale(rcp_via_double(pdf), tabq_evalp(B, p, i, o));
 	}
@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(TQ_THREADS) tabular_query_kernel(TabQueryArgs 
 {
 	extern __shared__ float s_tab[]; // 6 * res floats
 	__shared__ Params s_params[PERPAIR ? 1 : TQ_MAX_SMEM_PARAMS];
+	__shared__ __align__(16) double s_dm[DMT_COUNT]; // djb_dmath.cuh: table of the double atan
+	for (int t = threadIdx.x; t < DMT_COUNT; t += blockDim.x) s_dm[t] = g_dm_table_dev[t];
 	for (int t = threadIdx.x; t < 6 * A.res; t += blockDim.x) s_tab[t] = A.tables[t];
 	if (!PERPAIR) {
 		const float *src = reinterpret_cast<const float *>(A.params);
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(TQ_THREADS) tabular_query_kernel(TabQueryArgs 
 	}
 	__syncthreads();
 	TabBrdf B;
-	B.t.p22 = s_tab; B.t.sigma = s_tab + A.res; B.t.n = A.res;
+	B.t.p22 = s_tab; B.t.sigma = s_tab + A.res; B.t.n = A.res; B.t.T = s_dm;
 	B.qf = s_tab + 2 * A.res;
 	B.fr.pts = s_tab + 3 * A.res; B.fr.npts = A.res;
 	B.shadow = A.shadow != 0;
@@ -233,15 +235,16 @@ template <int OP, bool PERPAIR>
 __global__ void __launch_bounds__(TQ_THREADS) tabular_aniso_query_kernel(TabQueryArgs A, int azim_res, int n_qf1)
 {
 	__shared__ Params s_params[PERPAIR ? 1 : TQ_MAX_SMEM_PARAMS];
+	__shared__ __align__(16) double s_dm[DMT_COUNT]; // djb_dmath.cuh: table of the double atan / atan2
 	if (!PERPAIR) {
 		const float *src = reinterpret_cast<const float *>(A.params);
 		float *dst = reinterpret_cast<float *>(s_params);
 		for (int t = threadIdx.x; t < A.n_params * 12; t += blockDim.x) dst[t] = src[t];
-		__syncthreads();
 	}
+	dm_load_tables(s_dm);
 	TabBrdfT<TabAniso> B;
 	const int tab = A.res * azim_res;
-	B.t.p22 = A.tables; B.t.sigma = A.tables + tab; B.t.w = A.res; B.t.h = azim_res;
+	B.t.p22 = A.tables; B.t.sigma = A.tables + tab; B.t.w = A.res; B.t.h = azim_res; B.t.T = s_dm;
 	B.qf = nullptr;
 	B.fr.pts = A.tables + 2 * tab; B.fr.npts = A.res;
 	B.qf1 = A.tables + aniso_off_qf1(A.res, azim_res); B.n_qf1 = n_qf1;
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(TQ_THREADS) radial_query_kernel(int family, in
 		const float v = x[k];
 		float r = 0.0f;
 		if (family == 2) {
-			TabIso t; t.p22 = tables; t.sigma = tables + res; t.n = res;
+			TabIso t; t.p22 = tables; t.sigma = tables + res; t.n = res; t.T = g_dm_table_dev;
 			if (what == 0) r = t.p22_radial(v);
 			else if (what == 1) r = spline_f(t.sigma, res, (float)(2.0 * acos((double)v) / (double)(float)DJB_PI)); // :2158-2162
 			else if (what == 2) { // tabular::cdf_radial, :2164-2169
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(1024) aniso_sampling_tables_kernel(AnisoBuild 
 	float *qf1 = A.tab + aniso_off_qf1(er, ar), *qf2 = A.tab + aniso_off_qf2(er, ar);
 	float *pdf1 = A.tab + aniso_off_pdf1(er, ar), *cdf1 = A.tab + aniso_off_cdf1(er, ar);
 	float *pdf2 = A.tab + aniso_off_pdf2(er, ar), *cdf2 = A.tab + aniso_off_cdf2(er, ar);
-	TabAniso tp; tp.p22 = p22; tp.sigma = nullptr; tp.w = er; tp.h = ar;
+	TabAniso tp; tp.p22 = p22; tp.sigma = nullptr; tp.w = er; tp.h = ar; tp.T = g_dm_table_dev;
 	const double TWO_PI = 2.0 * DJB_PI, HALF_PI = 0.5 * DJB_PI;
 	__shared__ float s_k;
 	__shared__ int s_total;

@@ -86,7 +86,7 @@ def test_lean_double_exp_log_match_libm(tmp_path):
     from pathlib import Path
     root = Path(__file__).resolve().parents[1]
     exe = tmp_path / "dmath_check"
-    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", f"-I{root / 'dj_brdf_b200/csrc'}", str(root / "tests/cpp/dmath_check.cpp"),
+    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-pthread", f"-I{root / 'dj_brdf_b200/csrc'}", str(root / "tests/cpp/dmath_check.cpp"),
                         "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
