@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "djb200_sgd_eval", "djb200_abc_eval",
     "djb200_nmap_to_leanmap", "djb200_leanmap_to_half_mips", "djb200_leanmap_mip_levels", "djb200_leanmap_mip_texels", "djb200_dmap_to_nmap", "djb200_lrep_to_params", "djb200_params_to_lrep", "djb200_leanmap_to_params",
     "djb200_lean_shading_params", "djb200_lean_shading_evalp", "djb200_lean_shading_pdf", "djb200_lean_shading_evalp_is",
-    "djb200_debug_fit_phase_clocks", "djb200_debug_fit_parts", "djb200_fit_tabular", "djb200_fit_tabular_packed", "djb200_fit_tabular_packed_floats", "djb200_fit_tabular_anisotropic",
+    "djb200_debug_fit_phase_clocks", "djb200_debug_fit_parts", "djb200_debug_dmath", "djb200_fit_tabular", "djb200_fit_tabular_packed", "djb200_fit_tabular_packed_floats", "djb200_fit_tabular_anisotropic",
     "djb200_radial_query", "djb200_quantile_query", "djb200_tabular_anisotropic_query", "djb200_sgd_member", "djb200_abc_member", "djb200_tabular_create", "djb200_tabular_anisotropic_create", "djb200_tabular_anisotropic_sampling_tables", "djb200_tabular_destroy", "djb200_tabular_eval", "djb200_tabular_evalp", "djb200_tabular_pdf",
     "djb200_tabular_sample", "djb200_tabular_evalp_is",
     "djb200_aniso_fit_create", "djb200_aniso_fit_destroy", "djb200_aniso_fit_size", "djb200_aniso_fit_matvec",

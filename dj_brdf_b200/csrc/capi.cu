@@ -1059,6 +1059,17 @@ djb200_status djb200_debug_merl_filter_stats(const float *wi_dev, const float *w
 	return DJB200_OK;
 }
 
+djb200_status djb200_debug_dmath(int fn, const double *x_dev, const double *y_dev, int64_t n, double *out_dev, void *stream)
+{
+	if (!x_dev || !out_dev || n < 0 || fn < 0 || fn > 9) return fail(DJB200_ERR_INVALID_ARGUMENT, "bad argument");
+	if ((fn == 5 || fn == 8 || fn == 9) && !y_dev) return fail(DJB200_ERR_INVALID_ARGUMENT, "function %d takes two arguments", fn);
+	djb200_status rs = require_device();
+	if (rs != DJB200_OK) return rs;
+	cudaError_t e = launch_debug_dmath(fn, x_dev, y_dev, n, out_dev, (cudaStream_t)stream);
+	if (e != cudaSuccess) return cuda_fail(e, "debug dmath");
+	return DJB200_OK;
+}
+
 // ---- UTIA ------------------------------------------------------------------------------------------
 static const int64_t UTIA_N = 3 * 6 * 48 * 6 * 48;
 
@@ -1068,9 +1079,9 @@ djb200_status djb200_utia_create(const double *raw_samples, djb200_utia **out)
 	djb200_status rs = require_device();
 	if (rs != DJB200_OK) return rs;
 	double *tmp = nullptr;
-	float4 *table = nullptr;
+	djb200::UtiaEntry *table = nullptr;
 	CU(cudaMalloc(&tmp, sizeof(double) * UTIA_N));
-	cudaError_t e = cudaMalloc(&table, sizeof(float4) * (UTIA_N / 3));
+	cudaError_t e = cudaMalloc(&table, sizeof(djb200::UtiaEntry) * (UTIA_N / 3));
 	if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "cudaMalloc(utia table)"); }
 	e = cudaMemcpy(tmp, raw_samples, sizeof(double) * UTIA_N, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = launch_utia_convert(tmp, table, 0);
@@ -1108,7 +1119,7 @@ djb200_status djb200_utia_eval(const djb200_utia *u, const float *wi, const floa
                                int mem, void *stream)
 {
 	if (!u) return fail(DJB200_ERR_INVALID_ARGUMENT, "utia handle is NULL");
-	const float4 *table = u->table;
+	const djb200::UtiaEntry *table = u->table;
 	return map_call(n, {{wi, 12}, {wo, 12}}, {{out_rgb, 12}}, mem, stream,
 		[table](const std::vector<void *> &i, const std::vector<void *> &o, int64_t cn, cudaStream_t st) {
 			return launch_utia_eval(table, (const float *)i[0], (const float *)i[1], cn, (float *)o[0], st);

@@ -73,9 +73,9 @@ DJB_DEV float sat_ref(float x) { return fmin_ref(1.0f, fmax_ref(0.0f, x)); }
 // vec3(theta, phi), :589-595
 DJB_DEV V3 spherical(float theta, float phi)
 {
-	double st, ct, sp, cp;
-	sincos((double)theta, &st, &ct);
-	sincos((double)phi, &sp, &cp);
+	double st, ct, sp, cp; // djb_dmath.cuh: (float)sin / (float)cos equal libm's for every float up to 1e5 but one
+	sincos_d((double)theta, &st, &ct);
+	sincos_d((double)phi, &sp, &cp);
 	float s = (float)st;
 	return mk((float)((double)s * cp), (float)((double)s * sp), (float)ct);
 }
@@ -91,8 +91,8 @@ DJB_DEV void to_theta_phi(V3 p, float &theta, float &phi)
 		theta = (float)DJB_PI;
 		phi = 0.0f;
 	} else {
-		theta = (float)acos(z);
-		phi = (float)atan2((double)p.y, (double)p.x);
+		theta = (float)acos_d(z);
+		phi = (float)atan2_t((double)p.y, (double)p.x, g_dm_table_dev);
 	}
 }
 
@@ -163,7 +163,7 @@ DJB_DEV float erfinv_giles(float u)
 DJB_DEV V3 rotate_about(V3 x, V3 axis, float angle)
 {
 	double sd, cd;
-	sincos((double)angle, &sd, &cd);
+	sincos_d((double)angle, &sd, &cd);
 	float c = (float)cd, s = (float)sd;
 	V3 out = scale(c, x);
 	float t1 = dot(axis, x);
@@ -195,7 +195,7 @@ DJB_DEV void hd_to_io(V3 h, V3 d, V3 &i, V3 &o)
 // ---- Fresnel, :1292-1344 -----------------------------------------------------------------------
 DJB_DEV float unpolarized_channel(float c, float n)
 {
-	float g = (float)sqrt((double)(n * n + c * c) - 1.0);
+	float g = (float)sqrt_d((double)(n * n + c * c) - 1.0);
 	float t1 = (float)((double)(c * (g + c)) - 1.0);
 	float t2 = (float)((double)(c * (g - c)) + 1.0);
 	float t3 = (t1 * t1) / (t2 * t2);
@@ -274,7 +274,7 @@ DJB_DEV float sigma_std_radial(float c)
 	if (NDF == NDF_GGX) return (1.0f + c) * 0.5f; // :2062-2065, float((1.0 + c) / 2.0): one rounding either way
 	// beckmann, :1871-1879
 	if (c == 1.0f) return 1.0f;
-	float s = (float)sqrt(1.0 - (double)(c * c));
+	float s = (float)sqrt_d(1.0 - (double)(c * c));
 	float nu = c / s;
 	double e = exp((double)(-nu * nu)); // also the exp() inside djb::erf: (-|nu|)*|nu| == (-nu)*nu
 	float tmp = (float)(e * (double)inv_sqrt((float)DJB_PI));
@@ -379,7 +379,7 @@ DJB_DEV float mf_pdf(const Params &p, bool shadow, V3 i, V3 o, V3 h)
 DJB_DEV float ggx_qf2(float u, float ck, float sk)
 {
 	float st = (float)((double)u * (1.0 + (double)ck) - 1.0);
-	float ct = (float)sqrt(1.0 - (double)(st * st));
+	float ct = (float)sqrt_d(1.0 - (double)(st * st));
 	if ((double)ct > 0.707107) {
 		float tt = st / ct;
 		if ((double)sk < 0.707107) {
@@ -404,7 +404,7 @@ DJB_DEV float ggx_qf2(float u, float ck, float sk)
 // ggx::qf3_radial + qf3_rational_approx, :2121-2146
 DJB_DEV float ggx_qf3(float u, float qf2)
 {
-	float alpha = (float)sqrt(1.0 + (double)(qf2 * qf2));
+	float alpha = (float)sqrt_d(1.0 + (double)(qf2 * qf2));
 	float S;
 	if ((double)u < 0.5) {
 		u = (float)(2.0 * (0.5 - (double)u));
@@ -450,7 +450,7 @@ template <int NDF>
 DJB_DEV void sample_std_slopes(float u1, float u2, V3 k, float &xs, float &ys)
 {
 	float ck = k.z;
-	float sk = k.z < 1.0f ? (float)sqrt(1.0 - (double)(k.z * k.z)) : 0.0f;
+	float sk = k.z < 1.0f ? (float)sqrt_d(1.0 - (double)(k.z * k.z)) : 0.0f;
 	float tx, ty;
 	if (NDF == NDF_GGX) {
 		tx = ggx_qf2(u1, ck, sk);
@@ -515,19 +515,22 @@ DJB_DEV V3 mf_evalp_is(const Params &p, const FresnelDev &f, bool shadow, float 
 }
 
 // ---- params construction on the device (E10 / L2), dj_brdf.h:1378-1393, 1437-1474 ---------------
+// (float)sqrt(0.5 * (double)x) for a float x: 0.5 x is a float unless x is subnormal-small, and the double rounding of a square
+// root is innocuous (djb_device.cuh header)
+DJB_DEV float sqrt_half(float x) { return fabsf(x) >= 1e-30f ? __fsqrt_rn(0.5f * x) : (float)sqrt(0.5 * (double)x); }
 DJB_DEV void params_from_pdf(float ax, float ay, float rho, float tx, float ty, Params &p)
 {
 	p.ax = ax;
 	p.ay = ay;
 	p.rho = rho;
-	p.srho = (float)sqrt(1.0 - (double)(rho * rho));
+	p.srho = (float)sqrt_d(1.0 - (double)(rho * rho));
 	float qx = ax * ax, qy = ay * ay;
 	float cov = (float)((double)(rho * ax * ay) * 2.0);
 	float t1 = qx + qy, t2 = qx - qy;
-	float t3 = (float)sqrt((double)(t2 * t2 + cov * cov));
-	p.a1 = (float)sqrt(0.5 * (double)(t1 + t3));
-	p.a2 = (float)sqrt(0.5 * (double)(t1 - t3));
-	p.phi_a = (cov != 0.0f) ? (float)atan((double)((qx - qy - t3) / cov)) : 0.0f;
+	float t3 = __fsqrt_rn(t2 * t2 + cov * cov); // == (float)sqrt((double)(...)): the argument is a float
+	p.a1 = sqrt_half(t1 + t3);
+	p.a2 = sqrt_half(t1 - t3);
+	p.phi_a = (cov != 0.0f) ? (float)atan_t((double)((qx - qy - t3) / cov), g_dm_table_dev) : 0.0f;
 	p.tx = tx;
 	p.ty = ty;
 	V3 n = normalize(mk(-tx, -ty, 1.0f));
@@ -540,17 +543,17 @@ DJB_DEV void params_from_pdf(float ax, float ay, float rho, float tx, float ty, 
 DJB_DEV void params_elliptic_dev(float a1, float a2, float phi, Params &p)
 {
 	double sd, cd;
-	sincos((double)phi, &sd, &cd);
+	sincos_d((double)phi, &sd, &cd);
 	const float c = (float)cd, s = (float)sd;
 	const float c2 = (float)(2.0 * (double)c * (double)c - 1.0);
 	const float q1 = a1 * a1, q2 = a2 * a2, t1 = q1 + q2, t2 = q1 - q2;
 	p.a1 = a1;
 	p.a2 = a2;
 	p.phi_a = phi;
-	p.ax = (float)sqrt(0.5 * (double)(t1 + t2 * c2));
-	p.ay = (float)sqrt(0.5 * (double)(t1 - t2 * c2));
+	p.ax = sqrt_half(t1 + t2 * c2);
+	p.ay = sqrt_half(t1 - t2 * c2);
 	p.rho = (q2 - q1) * c * s / (p.ax * p.ay);
-	p.srho = (float)sqrt(1.0 - (double)(p.rho * p.rho));
+	p.srho = (float)sqrt_d(1.0 - (double)(p.rho * p.rho));
 	p.tx = 0.0f;
 	p.ty = 0.0f;
 	const V3 n = normalize(mk(-0.0f, -0.0f, 1.0f));
@@ -564,7 +567,7 @@ DJB_DEV void lrep_to_params(float E1, float E2, float E3, float E4, float E5, Pa
 {
 	float t1 = fmax_ref(0.0f, E3 - E1 * E1);
 	float t2 = fmax_ref(0.0f, E4 - E2 * E2);
-	double sx = sqrt(2.0 * (double)t1), sy = sqrt(2.0 * (double)t2);
+	double sx = sqrt_d(2.0 * (double)t1), sy = sqrt_d(2.0 * (double)t2); // t >= 0; 0 and the tiny / huge ones take the library
 	float ax = (float)(1e-5 > sx ? 1e-5 : sx);
 	float ay = (float)(1e-5 > sy ? 1e-5 : sy);
 	float rho = 2.0f * (E5 - E1 * E2) / (ax * ay);
@@ -608,7 +611,7 @@ DJB_DEV int merl_theta_half_index(float th)
 	if (th <= 0.0f) return 0;
 	float deg = (float)(((double)th / (DJB_PI / 2.0)) * 90.0);
 	float t = deg * 90.0f;
-	t = (float)sqrt((double)t);
+	t = __fsqrt_rn(t); // == (float)sqrt((double)t)
 	int r = (int)t;
 	return r < 0 ? 0 : (r >= 90 ? 89 : r);
 }
@@ -652,9 +655,22 @@ DJB_DEV int floor_div(float x, float d, float inv_d)
 	return q;
 }
 
-// utia::eval, dj_brdf.h:1063-1157.  `tab`: one float4 (r, g, b, 0) per (theta_i, phi_i, theta_v, phi_v) cell, so that a tap is one
-// 16-byte load instead of three 4-byte ones a plane apart; `T`: the djb_dmath.cuh table (shared memory in the query kernel)
-DJB_DEV V3 utia_eval1(const float4 *__restrict__ tab, V3 i, V3 o, const double *T)
+// Device layout of the UTIA table: per (theta_i, phi_i, theta_v, phi_v) cell the three channels of the cell (lo) and of its phi_v
+// neighbour, wrapped (hi): 32 bytes, fetched by one 256-bit load (sm_100's LDG.256)
+#ifndef DJB200_UTIA_ENTRY_DEFINED
+#define DJB200_UTIA_ENTRY_DEFINED
+struct __align__(32) UtiaEntry { float4 lo, hi; };
+#endif
+DJB_DEV UtiaEntry utia_load(const UtiaEntry *p)
+{
+	UtiaEntry v;
+	asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+	    : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.lo.z), "=f"(v.lo.w), "=f"(v.hi.x), "=f"(v.hi.y), "=f"(v.hi.z), "=f"(v.hi.w)
+	    : "l"(p));
+	return v;
+}
+// utia::eval, dj_brdf.h:1063-1157.  `T`: the djb_dmath.cuh table (shared memory in the query kernel)
+DJB_DEV V3 utia_eval1(const UtiaEntry *__restrict__ tab, V3 i, V3 o, const double *T)
 {
 	const float r2d = (float)(180.0 / DJB_PI);
 	float ti = (float)((double)r2d * acos_d((double)i.z)), to = (float)((double)r2d * acos_d((double)o.z));
@@ -665,7 +681,7 @@ DJB_DEV V3 utia_eval1(const float4 *__restrict__ tab, V3 i, V3 o, const double *
 	while (po < 0.0f) po = (float)((double)po + 360.0);
 	while (pi >= 360.0f) pi = (float)((double)pi - 360.0);
 	while (po >= 360.0f) po = (float)((double)po - 360.0);
-	int iti[2], itv[2], ipi[2], ipv[2];
+	int iti[2], itv[2], ipi[2], ipv[1];
 	if (ti >= 0.0f && to >= 0.0f) { // always, for finite directions
 		iti[0] = floor_div(ti, 15.0f, 1.0f / 15.0f);
 		itv[0] = floor_div(to, 15.0f, 1.0f / 15.0f);
@@ -682,33 +698,30 @@ DJB_DEV V3 utia_eval1(const float4 *__restrict__ tab, V3 i, V3 o, const double *
 	itv[1] = itv[0] + 1;
 	if (itv[0] > UT_NTV - 2) { itv[0] = UT_NTV - 2; itv[1] = UT_NTV - 1; }
 	ipi[1] = ipi[0] + 1;
-	ipv[1] = ipv[0] + 1;
+	if (ipi[1] == UT_NPI) ipi[1] = 0;
 	float sum, wti[2], wtv[2], wpi[2], wpv[2];
 	wti[1] = ti - (float)(15.0 * iti[0]); wti[0] = (float)(15.0 * iti[1]) - ti;
 	sum = wti[0] + wti[1]; wti[0] /= sum; wti[1] /= sum;
 	wtv[1] = to - (float)(15.0 * itv[0]); wtv[0] = (float)(15.0 * itv[1]) - to;
 	sum = wtv[0] + wtv[1]; wtv[0] /= sum; wtv[1] /= sum;
-	wpi[1] = pi - (float)(7.5 * ipi[0]); wpi[0] = (float)(7.5 * ipi[1]) - pi;
+	// the phi weights use the unwrapped upper index (dj_brdf.h:1110-1117 computes them before the wrap)
+	const int ipi1 = ipi[0] + 1, ipv1 = ipv[0] + 1;
+	wpi[1] = pi - (float)(7.5 * ipi[0]); wpi[0] = (float)(7.5 * ipi1) - pi;
 	sum = wpi[0] + wpi[1]; wpi[0] /= sum; wpi[1] /= sum;
-	wpv[1] = po - (float)(7.5 * ipv[0]); wpv[0] = (float)(7.5 * ipv[1]) - po;
+	wpv[1] = po - (float)(7.5 * ipv[0]); wpv[0] = (float)(7.5 * ipv1) - po;
 	sum = wpv[0] + wpv[1]; wpv[0] /= sum; wpv[1] /= sum;
-	if (ipi[1] == UT_NPI) ipi[1] = 0;
-	if (ipv[1] == UT_NPV) ipv[1] = 0;
+	// An entry holds its own cell and its phi_v neighbour (wrapped): the two innermost taps of the reference's loop nest are one
+	// 256-bit load, 8 loads per query.  The table (2.65 MB) lives in L2; a warp's 32 taps fall in 32 different lines, so the number of
+	// load wavefronts, not bytes, is what the query pays for.
 	const int nc = UT_NPV * UT_NTV;
 	float rgb[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
-	for (int a = 0; a < 2; ++a)
-#pragma unroll
-	for (int b = 0; b < 2; ++b)
-#pragma unroll
-	for (int c = 0; c < 2; ++c)
-#pragma unroll
-	for (int d = 0; d < 2; ++d) { // the reference's order of the 16 taps, per channel
-		const float w = wti[a] * wtv[b] * wpi[c] * wpv[d];
-		const float4 v = __ldg(tab + (nc * (UT_NPI * iti[a] + ipi[c]) + UT_NPV * itv[b] + ipv[d]));
-		rgb[0] += w * v.x;
-		rgb[1] += w * v.y;
-		rgb[2] += w * v.z;
+	for (int t = 0; t < 8; ++t) { // the reference's order of the 16 taps (theta_i, theta_v, phi_i, phi_v nested), per channel
+		const int a = t >> 2, b = (t >> 1) & 1, c = t & 1;
+		const UtiaEntry v = utia_load(tab + (nc * (UT_NPI * iti[a] + ipi[c]) + UT_NPV * itv[b] + ipv[0]));
+		const float w3 = wti[a] * wtv[b] * wpi[c], w0 = w3 * wpv[0], w1 = w3 * wpv[1];
+		rgb[0] += w0 * v.lo.x; rgb[1] += w0 * v.lo.y; rgb[2] += w0 * v.lo.z;
+		rgb[0] += w1 * v.hi.x; rgb[1] += w1 * v.hi.y; rgb[2] += w1 * v.hi.z;
 	}
 #pragma unroll
 	for (int isp = 0; isp < 3; ++isp) {
@@ -757,41 +770,49 @@ static __device__ __noinline__ V3 sgd_eval1_general(const double *__restrict__ m
 	}
 	return mk(out[0], out[1], out[2]);
 }
+// what the plain path of sgd_eval1 asks of a material (the same for every pair of a launch: the kernel evaluates it once)
+DJB_DEV bool sgd_material_plain(const double *__restrict__ m)
+{
+	bool ok = true;
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		const double al = fabs(m[11 * c + 2]);
+		ok = ok && al >= 1e-30 && al <= 1e30 && fabs(m[11 * c + 6]) < 1e100 && fabs(m[11 * c + 8]) < 1e200 && m[11 * c + 9] > 0.0;
+	}
+	return ok;
+}
 // sgd__g1 of one direction for the three channels at once (straight-line code: the three chains of double operations interleave).
-// Returns false when a value leaves the range of the table-driven exp / log (the caller then takes the general path).
-DJB_DEV bool sgd_g1_x3(double acos_kz, const double *__restrict__ m, const double *T, float *g1)
+// `ok` is cleared when a value leaves the range of the table-driven exp / log (the caller then takes the general path).
+// Requires sgd_material_plain: k > 0, so theta <= theta0 gives exactly 1 (see sgd_g1_ch), and |c| < 1e200.
+DJB_DEV void sgd_g1_x3(double acos_kz, const double *__restrict__ m, const double *T, float *g1, bool &ok)
 {
 	double t1[3], w[3];
-	bool pos[3], ok = true, any = false;
+	bool pos[3], any = false;
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
 		t1[c] = acos_kz - m[11 * c + 10];
 		pos[c] = t1[c] > 0.0;
 		any = any || pos[c];
-		ok = ok && t1[c] == t1[c] && (pos[c] || m[11 * c + 9] > 0.0); // theta <= theta0 with k > 0: exactly 1 (see sgd_g1_ch)
 	}
 	g1[0] = g1[1] = g1[2] = 1.0f;
-	if (!any) return ok;
-	// pow(t1, k) = exp(k log t1); below -700 it is < 1e-304: c times it is 0 to the exponential that follows (|c| < 1e200 checked),
-	// so the clamp changes nothing.  An exponential of less than -700 is < 1e-304: 1 - it is 1 either way.
+	if (!any) return;
+	// pow(t1, k) = exp(k log t1); where that is < 1e-300, c times it is 0 to the exponential that follows (|c| < 1e200): exp_t_sat's
+	// "some number < 1e-300" changes nothing.  An exponential of less than 1e-300: 1 - it is 1 either way.
+	bool okl = true;
 #pragma unroll
-	for (int c = 0; c < 3; ++c) w[c] = m[11 * c + 9] * log_t_core(pos[c] ? t1[c] : 1.0, T);
+	for (int c = 0; c < 3; ++c) w[c] = m[11 * c + 9] * log_t_core(pos[c] ? t1[c] : 1.0, T); // t1 > 0 is a normal number here
 #pragma unroll
-	for (int c = 0; c < 3; ++c) {
-		ok = ok && (!pos[c] || (w[c] <= 700.0 && fabs(m[11 * c + 8]) < 1e200));
-		w[c] = m[11 * c + 8] * exp_t_core(fmin(fmax(w[c], -700.0), 700.0), T);
-	}
+	for (int c = 0; c < 3; ++c) w[c] = m[11 * c + 8] * exp_t_sat(pos[c] ? w[c] : 0.0, T, okl);
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
-		ok = ok && (!pos[c] || w[c] <= 700.0);
-		double t3 = 1.0 + m[11 * c + 7] * (1.0 - exp_t_core(fmin(fmax(w[c], -700.0), 700.0), T));
+		double t3 = 1.0 + m[11 * c + 7] * (1.0 - exp_t_sat(pos[c] ? w[c] : 0.0, T, okl));
 		t3 = 0.0 > t3 ? 0.0 : t3;
 		t3 = 1.0 < t3 ? 1.0 : t3;
 		if (pos[c]) g1[c] = (float)t3;
 	}
-	return ok;
+	ok = ok && okl;
 }
-DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o, const double *T) // sgd::eval, :3454-3469
+DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o, const double *T, bool plain) // sgd::eval, :3454-3469
 {
 	if (!(i.z > 0.0f && o.z > 0.0f)) return mk(0.f, 0.f, 0.f);
 	const V3 h = normalize(i + o);
@@ -806,37 +827,34 @@ DJB_DEV V3 sgd_eval1(const double *__restrict__ m, V3 i, V3 o, const double *T) 
 	const V3 Fr = fresnel_eval<FK_SGD>(fr, sat_ref(dot(i, h)));
 	const float f3[3] = {Fr.x, Fr.y, Fr.z};
 	float out[3];
-	// the plain case: every logarithm of a positive normal number, every exponential within (-inf, 700], alpha and cos^4 in float
-	// range -- 9 logarithms and 15 exponentials through the table-driven forms, the divisions through one Newton step
+	// the plain case: every logarithm of a positive normal number, every exponential within (-1e6, 700), alpha and cos^4 in float
+	// range, both cosines at most 1 -- 9 logarithms and 15 exponentials through the table-driven forms, the divisions through
+	// one Newton step
 	const double ch = (double)h.z, c2 = ch * ch, c4 = c2 * c2;
-	bool ok = c4 >= 1e-30; // c2 <= 1
+	bool ok = plain && c4 >= 1e-30 && i.z <= 1.0f && o.z <= 1.0f; // c2 <= 1
 	float g1i[3], g1o[3], nd[3];
 	if (ok) {
 		const double ai = acos_d((double)i.z), ao = acos_d((double)o.z);
-		ok = sgd_g1_x3(ai, m, T, g1i);
-		ok = sgd_g1_x3(ao, m, T, g1o) && ok;
+		sgd_g1_x3(ai, m, T, g1i, ok);
+		sgd_g1_x3(ao, m, T, g1o, ok);
 		const double t2 = div_core(1.0 - c2, c2);
-		double y = (double)dm_rcp_seed((float)c4); // 1 / c4 to full precision: two Newton steps
+		double y = dm_rcp_seed(c4); // 1 / c4 to full precision: two Newton steps
 		y = dm_fma(dm_fma(-c4, y, 1.0), y, y);
 		y = dm_fma(dm_fma(-c4, y, 1.0), y, y);
 		const double s = y * (1.0 / DJB_PI);
 		double ax[3], e[3];
+		bool lok[3];
 #pragma unroll
 		for (int c = 0; c < 3; ++c) {
-			const double al = m[11 * c + 2];
-			ok = ok && fabs(al) >= 1e-30 && fabs(al) <= 1e30;
-			ax[c] = al + div_core(t2, al);
-			ok = ok && log_d_ok(ax[c]);
+			ax[c] = m[11 * c + 2] + div_core(t2, m[11 * c + 2]);
+			lok[c] = log_t_ok(ax[c]);
+			ok = ok && lok[c];
 		}
 #pragma unroll
-		for (int c = 0; c < 3; ++c) e[c] = -ax[c] - m[11 * c + 3] * log_t_core(log_d_ok(ax[c]) ? ax[c] : 1.0, T);
+		for (int c = 0; c < 3; ++c) e[c] = -ax[c] - m[11 * c + 3] * log_t_core(lok[c] ? ax[c] : 1.0, T);
 #pragma unroll
-		for (int c = 0; c < 3; ++c) {
-			ok = ok && e[c] <= 700.0;
-			// below -700 the exponential is < 1e-304 and kap / (pi cos^4) < 1e130 (checked): 0 as a float either way
-			ok = ok && fabs(m[11 * c + 6]) < 1e100;
-			nd[c] = (float)(m[11 * c + 6] * exp_t_core(fmin(fmax(e[c], -700.0), 700.0), T) * s);
-		}
+		for (int c = 0; c < 3; ++c) // an exponential < 1e-300 times kap / (pi cos^4) < 1e130 (checked) is 0 as a float either way
+			nd[c] = (float)(m[11 * c + 6] * exp_t_sat(e[c], T, ok) * s);
 	}
 	if (!ok) return sgd_eval1_general(m, i.z, o.z, h.z, Fr);
 	const float r1 = rcp_via_double(i.z * o.z), r2 = rcp_via_double((float)DJB_PI);

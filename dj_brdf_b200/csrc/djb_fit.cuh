@@ -11,7 +11,7 @@ namespace djb200 {
 struct FitSourceDev {
 	int kind;             // djb200_source_kind
 	const float4 *merl;   // scaled cells
-	const float4 *utia;   // normalised float table, one (r, g, b, 0) per cell
+	const UtiaEntry *utia; // normalised float table (djb_device.cuh: UtiaEntry)
 	int ndf, shadow, fresnel_kind;
 	FresnelDev fr;        // fr.pts: device pointer
 	double coef[33];      // SGD: djb200_sgd_data.ch flattened; ABC: djb200_abc_data (9 values)
@@ -47,7 +47,7 @@ DJB_DEV V3 source_eval(const FitSourceDev &s, V3 i, V3 o)
 {
 	if (s.kind == DJB200_SOURCE_MERL) return merl_eval1(s.merl, i, o);
 	if (s.kind == DJB200_SOURCE_UTIA) return utia_eval1(s.utia, i, o, g_dm_table_dev);
-	if (s.kind == DJB200_SOURCE_SGD) return sgd_eval1(s.coef, i, o, g_dm_table_dev);
+	if (s.kind == DJB200_SOURCE_SGD) return sgd_eval1(s.coef, i, o, g_dm_table_dev, sgd_material_plain(s.coef));
 	if (s.kind == DJB200_SOURCE_ABC) return abc_eval1(s.coef, i, o, g_dm_table_dev);
 	const Params p = standard_params();
 	if (s.ndf == NDF_GGX) return mf_eval_rt<NDF_GGX>(p, s.fresnel_kind, s.fr, s.shadow != 0, i, o);

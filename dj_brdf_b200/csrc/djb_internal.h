@@ -16,8 +16,15 @@ struct djb200_tabular {
 	int azim_res; // 0: radial tables (djb::tabular); > 0: djb::tabular_anisotropic with res = elevation resolution
 	int n_qf1, n_qf2; // anisotropic: entries the quantile-table searches produced (dj_brdf.h:2904-2935, 3004-3037)
 };
+namespace djb200 {
+// per (theta_i, phi_i, theta_v, phi_v) cell: the three channels of the cell (lo) and of its phi_v neighbour, wrapped (hi)
+#ifndef DJB200_UTIA_ENTRY_DEFINED
+#define DJB200_UTIA_ENTRY_DEFINED
+struct __align__(32) UtiaEntry { float4 lo, hi; };
+#endif
+} // namespace djb200
 struct djb200_utia {
-	float4 *table; // utia::normalize()d samples cast to float, one (r, g, b, 0) per (theta_i, phi_i, theta_v, phi_v) cell
+	djb200::UtiaEntry *table; // utia::normalize()d samples cast to float, one entry per (theta_i, phi_i, theta_v, phi_v) cell
 	int device;
 };
 
@@ -99,8 +106,9 @@ cudaError_t launch_merl_eval(const float4 *cells, const float *wi, const float *
 cudaError_t launch_merl_index(const float *wi, const float *wo, int64_t n, int32_t *out, cudaStream_t st);
 cudaError_t launch_merl_filter_stats(const float *wi, const float *wo, int64_t n, unsigned long long *stats_dev,
                                      cudaStream_t st);
-cudaError_t launch_utia_convert(const double *raw_dev, float4 *table_dev, cudaStream_t st);
-cudaError_t launch_utia_eval(const float4 *table, const float *wi, const float *wo, int64_t n, float *out,
+cudaError_t launch_debug_dmath(int fn, const double *x, const double *y, int64_t n, double *out, cudaStream_t st);
+cudaError_t launch_utia_convert(const double *raw_dev, UtiaEntry *table_dev, cudaStream_t st);
+cudaError_t launch_utia_eval(const UtiaEntry *table, const float *wi, const float *wo, int64_t n, float *out,
                              cudaStream_t st);
 cudaError_t launch_nmap_to_leanmap(const uint8_t *nmap, int64_t npix, float base_roughness, float bias,
                                    float *lean1, float *lean2, cudaStream_t st);

@@ -30,14 +30,40 @@ __global__ void __launch_bounds__(TB) analytic_eval_kernel(const __grid_constant
 {
 	__shared__ __align__(16) double s_dm[DMT_COUNT]; // djb_dmath.cuh: tables of the double exp / log
 	dm_load_tables(s_dm);
+	const bool plain = KIND == DJB200_SOURCE_SGD && sgd_material_plain(m.v);
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
 		const V3 i = mk(wi[3 * k], wi[3 * k + 1], wi[3 * k + 2]);
 		const V3 o = mk(wo[3 * k], wo[3 * k + 1], wo[3 * k + 2]);
-		const V3 r = KIND == DJB200_SOURCE_SGD ? sgd_eval1(m.v, i, o, s_dm) : abc_eval1(m.v, i, o, s_dm);
+		const V3 r = KIND == DJB200_SOURCE_SGD ? sgd_eval1(m.v, i, o, s_dm, plain) : abc_eval1(m.v, i, o, s_dm);
 		out[3 * k] = r.x;
 		out[3 * k + 1] = r.y;
 		out[3 * k + 2] = r.z;
+	}
+}
+// djb200_debug_dmath: the double functions of djb_dmath.cuh as the kernels above compile them
+__global__ void __launch_bounds__(TB) dmath_kernel(int fn, const double *__restrict__ x, const double *__restrict__ y, long long n,
+                                                   double *__restrict__ out)
+{
+	__shared__ __align__(16) double s_dm[DMT_COUNT];
+	dm_load_tables(s_dm);
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		const double a = x[k], b = y ? y[k] : 0.0;
+		double r = 0.0, sn, cs;
+		switch (fn) {
+		case 0: r = exp_t(a, s_dm); break;
+		case 1: r = log_t(a, s_dm); break;
+		case 2: r = sqrt_d(a); break;
+		case 3: r = acos_d(a); break;
+		case 4: r = atan_t(a, s_dm); break;
+		case 5: r = atan2_t(a, b, s_dm); break;
+		case 6: sincos_d(a, &sn, &cs); r = sn; break;
+		case 7: sincos_d(a, &sn, &cs); r = cs; break;
+		case 8: r = (fabs(b) >= 1e-30 && fabs(b) <= 1e30) ? div_core(a, b) : a / b; break;
+		default: r = pow_pos_t(a, b, s_dm); break;
+		}
+		out[k] = r;
 	}
 }
 // the public component queries of djb::microfacet (dj_brdf.h:258-272, 1559-1665): ndf(h), gaf(h, i, o), g1(h, k), sigma(k),
@@ -100,6 +126,14 @@ cudaError_t launch_microfacet_component(int ndf, int shadow, int fresnel_kind, c
 	if (ndf == NDF_GGX) component_kernel<NDF_GGX><<<grid_for(n), TB, 0, st>>>(A);
 	else if (ndf == NDF_BECKMANN) component_kernel<NDF_BECKMANN><<<grid_for(n), TB, 0, st>>>(A);
 	else return cudaErrorInvalidValue;
+	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_debug_dmath(int fn, const double *x, const double *y, int64_t n, double *out, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	dmath_kernel<<<grid_for(n), TB, 0, st>>>(fn, x, y, n, out);
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	return cudaGetLastError();
 }

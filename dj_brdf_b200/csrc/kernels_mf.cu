@@ -201,8 +201,14 @@ __global__ void __launch_bounds__(MF_THREADS) mf_broadcast_kernel(const __grid_c
 #ifndef DJB200_FSAMPLE_MINB
 #define DJB200_FSAMPLE_MINB 4
 #endif
+#ifndef DJB200_LEANSRC_MINB
+#define DJB200_LEANSRC_MINB 4
+#endif
 constexpr int lean_min_blocks(int ndf, int op, int psrc, bool fast)
 {
+	// PSRC_LEAN: the params construction in front of the query (double sincos / atan / square roots, djb_dmath.cuh) would otherwise
+	// take 70 - 76 registers
+	if (psrc == 2 /* PSRC_LEAN */) return DJB200_LEANSRC_MINB;
 	return (ndf == NDF_BECKMANN && op == OP_SAMPLE && psrc == 0 /* PSRC_BROADCAST */) ? (fast ? DJB200_FSAMPLE_MINB : DJB200_BSAMPLE_MINB) : 1;
 }
 

@@ -71,24 +71,31 @@ cudaError_t launch_hd_to_io(const float *h, const float *d, int64_t n, float *wi
 // ---- UTIA, dj_brdf.h:1039-1177 ---------------------------------------------------------------------
 // utia::normalize (clamp at 0, scale by the float constant 1/140 in double) followed by the
 // (float_t) cast utia::eval applies to every fetched sample (:1144, 1162-1177)
-// Device layout: the file's three channel planes interleaved, one float4 (r, g, b, 0) per cell -- the 16 taps of a query are 16
-// 16-byte loads (1.3 MB table, L2 resident) instead of 48 scattered 4-byte ones
-__global__ void __launch_bounds__(TB) utia_convert_kernel(const double *raw, float4 *table)
+// Device layout (djb_device.cuh: UtiaEntry): the file's three channel planes interleaved, each cell together with its phi_v
+// neighbour -- the 16 taps of a query are 8 256-bit loads (2.65 MB table, L2 resident) instead of 48 scattered 4-byte ones
+__global__ void __launch_bounds__(TB) utia_convert_kernel(const double *raw, UtiaEntry *table)
 {
 	constexpr int PLANE = UT_CELLS / 3;
 	int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= PLANE) return;
 	const float k = 1.f / 140.f;
-	float ch[3];
-	for (int s = 0; s < 3; ++s) {
-		double v = raw[s * PLANE + c];
+	const int c1 = (c % UT_NPV) == UT_NPV - 1 ? c - (UT_NPV - 1) : c + 1; // phi_v + 1, wrapped (dj_brdf.h:1118-1121)
+	float ch[6];
+	for (int s = 0; s < 6; ++s) {
+		double v = raw[(s % 3) * PLANE + (s < 3 ? c : c1)];
 		v = 0.0 > v ? 0.0 : v;
 		ch[s] = (float)(v * (double)k);
 	}
-	table[c] = make_float4(ch[0], ch[1], ch[2], 0.0f);
+	UtiaEntry e;
+	e.lo = make_float4(ch[0], ch[1], ch[2], 0.0f);
+	e.hi = make_float4(ch[3], ch[4], ch[5], 0.0f);
+	table[c] = e;
 }
 
-__global__ void __launch_bounds__(TB) utia_eval_kernel(const float4 *__restrict__ tab, const float *__restrict__ wi,
+#ifndef DJB200_UTIA_MINB
+#define DJB200_UTIA_MINB 6
+#endif
+__global__ void __launch_bounds__(TB, DJB200_UTIA_MINB) utia_eval_kernel(const UtiaEntry *__restrict__ tab, const float *__restrict__ wi,
                                                        const float *__restrict__ wo, long long n, float *__restrict__ out)
 {
 	__shared__ __align__(16) double s_dm[DMT_COUNT];
@@ -98,14 +105,14 @@ __global__ void __launch_bounds__(TB) utia_eval_kernel(const float4 *__restrict_
 		st3t(out, k, utia_eval1(tab, ld3(wi, k), ld3(wo, k), s_dm));
 }
 
-cudaError_t launch_utia_convert(const double *raw_dev, float4 *table_dev, cudaStream_t st)
+cudaError_t launch_utia_convert(const double *raw_dev, UtiaEntry *table_dev, cudaStream_t st)
 {
 	utia_convert_kernel<<<(UT_CELLS / 3 + TB - 1) / TB, TB, 0, st>>>(raw_dev, table_dev);
 	g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 	return cudaGetLastError();
 }
 
-cudaError_t launch_utia_eval(const float4 *table, const float *wi, const float *wo, int64_t n, float *out,
+cudaError_t launch_utia_eval(const UtiaEntry *table, const float *wi, const float *wo, int64_t n, float *out,
                              cudaStream_t st)
 {
 	if (n <= 0) return cudaSuccess;

@@ -83,15 +83,24 @@ DJB_DEV float spline_repeat_f(const float *pts, int n, float u)
 	return p1 + frac * (p2 - p1);
 }
 
+// (float)tan((double)x) as sin / cos of djb_dmath.cuh (<= 3 ulp of double before the rounding to float)
+DJB_DEV float tan_f(float x)
+{
+	double sn, cs;
+	sincos_d((double)x, &sn, &cs);
+	const double a = fabs(cs);
+	if (!(a >= 1e-30 && fabs((double)x) <= 1e5)) return (float)tan((double)x);
+	return (float)div_core(sn, cs);
+}
 // standard slopes of a normal drawn from the tabulated distribution
 DJB_DEV void tabq_std_slopes(const TabBrdfT<TabIso> &B, float u1, float u2, float &txm, float &tym)
 {
 	// radial::sample_vp22_std_nmap, dj_brdf.h:1806-1816
 	float phi_h = (float)((double)u1 * DJB_PI * 2.0);
 	float q = spline_f(B.qf, B.t.n, u2);                        // tabular::qf_radial, :2172-2176
-	float r_h = (float)tan((double)(q * (float)DJB_PI / 2.0f));
+	float r_h = tan_f(q * (float)DJB_PI / 2.0f);
 	double sp, cp;
-	sincos((double)phi_h, &sp, &cp);
+	sincos_d((double)phi_h, &sp, &cp);
 	txm = (float)((double)r_h * cp);
 	tym = (float)((double)r_h * sp);
 }
@@ -101,9 +110,9 @@ DJB_DEV void tabq_std_slopes(const TabBrdfT<TabAniso> &B, float u1, float u2, fl
 	const float phi = (float)((double)spline_f(B.qf1, B.n_qf1, u1) * 2.0 * DJB_PI);
 	const float uphi = (float)((double)phi / (2.0 * DJB_PI));
 	const float theta = (float)((double)spline2d_f(B.qf2, B.t.w, B.t.h, u2, uphi) * 0.5 * DJB_PI);
-	const float tan_theta = (float)tan((double)theta);
+	const float tan_theta = tan_f(theta);
 	double sp, cp;
-	sincos((double)phi, &sp, &cp);
+	sincos_d((double)phi, &sp, &cp);
 	txm = (float)((double)(-tan_theta) * cp);
 	tym = (float)((double)(-tan_theta) * sp);
 }

@@ -138,6 +138,11 @@ DJB200_API djb200_status djb200_debug_fit_phase_clocks(int64_t out_clocks[10]);
  * launch per phase with up to 8 CTAs per material, larger ones the whole fit in one launch with one CTA per material;
  * 1 = always the single launch; 3..8 = that many CTAs per material wherever the resolution allows.  Same results either way. */
 DJB200_API djb200_status djb200_debug_fit_parts(int parts);
+/* Test aid: the double functions of csrc/djb_dmath.cuh evaluated ON THE DEVICE over DEVICE arrays of doubles (the host build of the
+ * same source is checked against libm by tests/cpp/dmath_check.cpp; this entry shows that the device build -- MUFU seeds, fused
+ * operations -- gives the same accuracy).  fn: 0 exp_t, 1 log_t, 2 sqrt_d, 3 acos_d, 4 atan_t, 5 atan2_t(x, y), 6 sin, 7 cos (sincos_d),
+ * 8 x / y (div_core), 9 pow_pos_t(x, y).  y_dev may be NULL for the one-argument functions. */
+DJB200_API djb200_status djb200_debug_dmath(int fn, const double *x_dev, const double *y_dev, int64_t n, double *out_dev, void *stream);
 
 /* ---- params factories (host side, dj_brdf.h:1355-1474) ---------------------------------- */
 DJB200_API djb200_status djb200_params_standard(djb200_params *out);                           /* :1412 */

@@ -55,7 +55,7 @@ int main(int argc, char **argv)
 
 	// ---- table-driven set ----
 	const double *T = dm_table_host();
-	double w_et = 0, w_lt = 0, w_pw = 0, w_sq = 0, w_ac = 0, w_at = 0, w_a2 = 0;
+	double w_et = 0, w_lt = 0, w_pw = 0, w_sq = 0, w_ac = 0, w_at = 0, w_a2 = 0, w_sc = 0;
 	for (int k = 0; k < N; ++k) {
 		const double u = rnd(), v = rnd();
 		const double x = (k & 1) ? (u * 2.0 - 1.0) * 700.0 : (u * 2.0 - 1.0) * 2.0;
@@ -75,6 +75,10 @@ int main(int argc, char **argv)
 		w_at = fmax(w_at, ulps(atan_t(ta, T), atan(ta)));
 		const double ay = (u * 2.0 - 1.0) * ((k & 4) ? 1.0 : 1e-3), bx = (v * 2.0 - 1.0) * ((k & 8) ? 1.0 : 1e-3);
 		w_a2 = fmax(w_a2, ulps(atan2_t(ay, bx, T), atan2(ay, bx)));
+		const double sa = (k & 1) ? (u * 2.0 - 1.0) * 1e5 : (u * 2.0 - 1.0) * 7.0;
+		double ss, cc;
+		sincos_d(sa, &ss, &cc);
+		w_sc = fmax(w_sc, fmax(ulps(ss, sin(sa)), ulps(cc, cos(sa))));
 	}
 	const double e2[][2] = {{0.0, 1.0}, {-0.0, 1.0}, {0.0, -1.0}, {-0.0, -1.0}, {1.0, 0.0}, {-1.0, 0.0}, {1.0, -0.0}, {-1.0, -0.0},
 	                        {0.0, 0.0}, {1.0, 1.0}, {-1.0, -1.0}, {INFINITY, 1.0}, {1.0, INFINITY}, {NAN, 1.0}, {1e-40, 1e-39}, {3.0, -4.0}};
@@ -89,9 +93,9 @@ int main(int argc, char **argv)
 		if (!((a == b) || (std::isnan(a) && std::isnan(b)) || ulps(a, b) <= 2)) ++bad2;
 		if (!((c == d && std::signbit(c) == std::signbit(d)) || (std::isnan(c) && std::isnan(d)) || ulps(c, d) <= 2)) ++bad2;
 	}
-	printf("exp_t max_ulp %.3f  log_t max_abs %.3f  pow_pos_t %.3f  sqrt_d %.3f  acos_d %.3f  atan_t %.3f  atan2_t %.3f  edge_mismatches %d\n",
-	       w_et, w_lt, w_pw, w_sq, w_ac, w_at, w_a2, bad2);
-	if (!(w_et <= 2.0 && w_lt <= 2.0 && w_pw <= 8.0 && w_sq <= 1.0 && w_ac <= 2.0 && w_at <= 2.0 && w_a2 <= 2.0 && bad2 == 0)) rc = 1;
+	printf("exp_t max_ulp %.3f  log_t max_abs %.3f  pow_pos_t %.3f  sqrt_d %.3f  acos_d %.3f  atan_t %.3f  atan2_t %.3f  sincos_d %.3f  edge_mismatches %d\n",
+	       w_et, w_lt, w_pw, w_sq, w_ac, w_at, w_a2, w_sc, bad2);
+	if (!(w_et <= 2.0 && w_lt <= 2.0 && w_pw <= 8.0 && w_sq <= 1.0 && w_ac <= 2.0 && w_at <= 2.0 && w_a2 <= 2.0 && w_sc <= 2.0 && bad2 == 0)) rc = 1;
 
 	// ---- the two coordinate maps, every float ----
 	// name, first and last bit pattern (non-negative floats), also the negated arguments?
@@ -108,6 +112,10 @@ int main(int argc, char **argv)
 		 [](float q) { return (float)atan_t(sqrt_d((double)q), dm_table_host()); }},
 		{"utia theta (degrees)", 0u, 0x3f800000u, true, [](float c) { return (float)((double)r2d * acos((double)c)); },
 		 [](float c) { return (float)((double)r2d * acos_d((double)c)); }},
+		{"(float)sin", 0u, 0x47c35000u, true, [](float x) { return (float)sin((double)x); },
+		 [](float x) { double s, c; sincos_d((double)x, &s, &c); return (float)s; }},
+		{"(float)cos", 0u, 0x47c35000u, true, [](float x) { return (float)cos((double)x); },
+		 [](float x) { double s, c; sincos_d((double)x, &s, &c); return (float)c; }},
 		{"pow5_one_minus", 0u, 0x3f800000u, false, [](float c) { return (float)pow(1.0 - (double)c, 5.0); }, [](float c) { return pow5_one_minus(c); }},
 	};
 	unsigned nt = std::thread::hardware_concurrency();

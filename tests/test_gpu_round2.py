@@ -335,3 +335,68 @@ def test_members_directly_against_the_unmodified_reference(djb, ref):
     for what, got, args in (("ndf", m.ndf(h), (h,)), ("gaf", m.gaf(h, i, o), (h, i, o))):
         want = ref.member_query(what, *args, abc=name)
         assert rel_err(got, want).max() <= 1e-5 and bits_equal(got, want).mean() >= 0.99, what
+
+
+# ---- the double functions of csrc/djb_dmath.cuh as the device compiles them ----------------------------------------------------------
+def _ulps(got, want):
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.abs(got - want) / np.spacing(np.abs(want))
+
+
+def test_device_dmath_against_libm(djb):
+    """exp_t / log_t / sqrt_d / acos_d / atan_t / atan2_t / sincos_d / div_core / pow_pos_t evaluated on the device
+    (djb200_debug_dmath: MUFU seeds, fused operations, shared-memory tables) against numpy's libm over 2e6 arguments each -- the
+    device build has the accuracy tests/cpp/dmath_check.cpp establishes for the host build of the same source."""
+    import ctypes as C
+    import torch
+    from dj_brdf_b200 import capi
+    lib = capi.load()
+    rng = np.random.default_rng(77)
+    n = 2_000_000
+    u, v = rng.random(n), rng.random(n)
+
+    def run(fn, x, y=None):
+        xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        yd = torch.from_numpy(np.ascontiguousarray(y)).cuda() if y is not None else None
+        out = torch.empty(len(x), dtype=torch.float64, device="cuda")
+        capi.check(lib.djb200_debug_dmath(C.c_int(fn), C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr() if yd is not None else None),
+                                          C.c_int64(len(x)), C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    half = np.arange(n) % 2 == 0
+    x = np.where(half, (2 * u - 1) * 700.0, (2 * u - 1) * 2.0)
+    assert _ulps(run(0, x), np.exp(x)).max() <= 2.0
+    x = np.where(half, 10.0 ** ((2 * u - 1) * 300.0), 0.5 + u)
+    lx = np.log(x)
+    assert (np.abs(run(1, x) - lx) / (2.0 ** -52 * np.maximum(1.0, np.abs(lx)))).max() <= 2.0  # absolute criterion (djb_dmath.cuh)
+    x = np.where(half, 10.0 ** ((2 * u - 1) * 29.0), u)
+    assert _ulps(run(2, x), np.sqrt(x)).max() <= 1.0
+    x = np.where(half, 2 * u - 1, 1.0 - u ** 4)
+    assert _ulps(run(3, x), np.arccos(x)).max() <= 2.0
+    x = np.where(half, 10.0 ** ((2 * u - 1) * 25.0) * np.sign(v - 0.5), (2 * u - 1) * 4.0)
+    assert _ulps(run(4, x), np.arctan(x)).max() <= 2.0
+    y, x = (2 * u - 1), (2 * v - 1) * np.where(half, 1.0, 1e-3)
+    assert _ulps(run(5, y, x), np.arctan2(y, x)).max() <= 2.0
+    x = np.where(half, (2 * u - 1) * 1e5, (2 * u - 1) * 7.0)
+    assert _ulps(run(6, x), np.sin(x)).max() <= 2.0
+    assert _ulps(run(7, x), np.cos(x)).max() <= 2.0
+    a, b = (2 * u - 1) * 10.0, np.where(half, 10.0 ** ((2 * v - 1) * 29.0), 0.1 + v)
+    assert _ulps(run(8, a, b), a / b).max() <= 1.0
+    pb, pe = 1e-3 + 4.0 * u, (2 * v - 1) * np.where(half, 500.0, 3.0)
+    with np.errstate(over="ignore", under="ignore"):
+        want = np.power(pb, pe)
+    ok = (want > 1e-300) & (want < 1e300)
+    got = run(9, pb, pe)
+    err = np.abs(got[ok] - want[ok]) / (want[ok] * 2.0 ** -52 * (1.0 + np.abs(pe * np.log(pb))[ok]))
+    k = int(np.nanargmax(err)) if np.isfinite(err).any() else 0
+    assert np.isfinite(err).all() and err.max() <= 8.0, (err[k], pb[ok][k], pe[ok][k], got[ok][k], want[ok][k], int((~np.isfinite(err)).sum()))
+    # special arguments take the library's path
+    x = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-320, 800.0, -800.0, 1.5, 1e31])
+    with np.errstate(all="ignore"):
+        for fn, f in ((0, np.exp), (1, np.log), (2, np.sqrt), (3, np.arccos), (4, np.arctan), (6, np.sin), (7, np.cos)):
+            got, want = run(fn, x), f(x)
+            same = (got == want) | (np.isnan(got) & np.isnan(want)) | (_ulps(got, want) <= 2.0)
+            if fn == 1:  # log_t's criterion is absolute: log_t(1.0) is 1.7e-18, not 0
+                same |= np.abs(got - want) <= 2.0 ** -52 * np.maximum(1.0, np.abs(want))
+            assert same.all(), (fn, got, want)
