@@ -639,7 +639,7 @@ def run_widening_legs(c):
     res["lean_shading"] = {"evals_per_s": ns / (ms_f * 1e-3), "ms": ms_f, "pairs": ns, "two_pass_ms": ms_2,
                            "roofline": hbm_roofline(68.0 * ns, ms_f, peak)}
     del E, al
-    # djb::sgd / djb::abc eval (36 B per pair; double exp / pow / acos per channel: issue bound)
+    # djb::sgd / djb::abc eval (36 B per pair; table-driven double exp / log, polynomial acos per channel -- djb_dmath.cuh: FP64-pipe bound)
     na = min(n, 20_000_000)
     for kind, name in (("sgd", "gold-metallic-paint"), ("abc", "blue-metallic-paint")):
         mobj = getattr(djb, kind)(name)

@@ -543,7 +543,7 @@ DJB_DEV void params_from_pdf(float ax, float ay, float rho, float tx, float ty, 
 DJB_DEV void params_elliptic_dev(float a1, float a2, float phi, Params &p)
 {
 	double sd, cd;
-	sincos_d((double)phi, &sd, &cd);
+	sincos((double)phi, &sd, &cd); // the library's: sincos_d here costs the fused LEAN shading kernel 8 registers and 6 % (measured)
 	const float c = (float)cd, s = (float)sd;
 	const float c2 = (float)(2.0 * (double)c * (double)c - 1.0);
 	const float q1 = a1 * a1, q2 = a2 * a2, t1 = q1 + q2, t2 = q1 - q2;
@@ -677,10 +677,11 @@ DJB_DEV V3 utia_eval1(const UtiaEntry *__restrict__ tab, V3 i, V3 o, const doubl
 	float pi = (float)((double)r2d * atan2_t((double)i.y, (double)i.x, T));
 	float po = (float)((double)r2d * atan2_t((double)o.y, (double)o.x, T));
 	if (ti >= 90.0f || to >= 90.0f) return mk(0.f, 0.f, 0.f);
-	while (pi < 0.0f) pi = (float)((double)pi + 360.0);
-	while (po < 0.0f) po = (float)((double)po + 360.0);
-	while (pi >= 360.0f) pi = (float)((double)pi - 360.0);
-	while (po >= 360.0f) po = (float)((double)po - 360.0);
+	// (float)((double)x +- 360.0) is the float sum: a double holds the sum of two floats to more than 2 x 24 + 2 bits
+	while (pi < 0.0f) pi = pi + 360.0f;
+	while (po < 0.0f) po = po + 360.0f;
+	while (pi >= 360.0f) pi = pi - 360.0f;
+	while (po >= 360.0f) po = po - 360.0f;
 	int iti[2], itv[2], ipi[2], ipv[1];
 	if (ti >= 0.0f && to >= 0.0f) { // always, for finite directions
 		iti[0] = floor_div(ti, 15.0f, 1.0f / 15.0f);
@@ -700,15 +701,16 @@ DJB_DEV V3 utia_eval1(const UtiaEntry *__restrict__ tab, V3 i, V3 o, const doubl
 	ipi[1] = ipi[0] + 1;
 	if (ipi[1] == UT_NPI) ipi[1] = 0;
 	float sum, wti[2], wtv[2], wpi[2], wpv[2];
-	wti[1] = ti - (float)(15.0 * iti[0]); wti[0] = (float)(15.0 * iti[1]) - ti;
+	// (float)(15.0 * k), (float)(7.5 * k): multiples of 7.5 up to 367.5 are floats, so the float product is the same number
+	wti[1] = ti - 15.0f * (float)iti[0]; wti[0] = 15.0f * (float)iti[1] - ti;
 	sum = wti[0] + wti[1]; wti[0] /= sum; wti[1] /= sum;
-	wtv[1] = to - (float)(15.0 * itv[0]); wtv[0] = (float)(15.0 * itv[1]) - to;
+	wtv[1] = to - 15.0f * (float)itv[0]; wtv[0] = 15.0f * (float)itv[1] - to;
 	sum = wtv[0] + wtv[1]; wtv[0] /= sum; wtv[1] /= sum;
 	// the phi weights use the unwrapped upper index (dj_brdf.h:1110-1117 computes them before the wrap)
 	const int ipi1 = ipi[0] + 1, ipv1 = ipv[0] + 1;
-	wpi[1] = pi - (float)(7.5 * ipi[0]); wpi[0] = (float)(7.5 * ipi1) - pi;
+	wpi[1] = pi - 7.5f * (float)ipi[0]; wpi[0] = 7.5f * (float)ipi1 - pi;
 	sum = wpi[0] + wpi[1]; wpi[0] /= sum; wpi[1] /= sum;
-	wpv[1] = po - (float)(7.5 * ipv[0]); wpv[0] = (float)(7.5 * ipv1) - po;
+	wpv[1] = po - 7.5f * (float)ipv[0]; wpv[0] = 7.5f * (float)ipv1 - po;
 	sum = wpv[0] + wpv[1]; wpv[0] /= sum; wpv[1] /= sum;
 	// An entry holds its own cell and its phi_v neighbour (wrapped): the two innermost taps of the reference's loop nest are one
 	// 256-bit load, 8 loads per query.  The table (2.65 MB) lives in L2; a warp's 32 taps fall in 32 different lines, so the number of
@@ -726,8 +728,8 @@ DJB_DEV V3 utia_eval1(const UtiaEntry *__restrict__ tab, V3 i, V3 o, const doubl
 #pragma unroll
 	for (int isp = 0; isp < 3; ++isp) {
 		float acc = rgb[isp];
-		if ((double)acc > 0.0375)
-			acc = (float)pow_pos_t((double)(float)((double)acc + 0.055) / 1.055, (double)2.4f, T); // base > 0.0875: exp(y log x)
+		if (acc >= 0.0375f) // (double)acc > 0.0375: the float 0.0375f lies above the double 0.0375 and no float lies between
+			acc = (float)pow_pos_t(div_core((double)(float)((double)acc + 0.055), 1.055), (double)2.4f, T); // base > 0.0875
 		else
 			acc /= 12.92f;
 		rgb[isp] = acc * 100.0f;

@@ -28,6 +28,6 @@ for _ in range(2):
 torch.cuda.synchronize()
 PY
 ncu --set full --clock-control none --import-source on -k regex:"analytic_eval_kernel|utia_eval_kernel|tabular_query_kernel" -s 3 -c 3 -f \
-    -o gpurun_out/prof_r02_n2_widened env PYTHONPATH=$PWD python /tmp/wk.py > gpurun_out/ncu_r02_n2.log 2>&1
-tail -2 gpurun_out/ncu_r02_n2.log
-ls -la gpurun_out/prof_r02_n2_widened.ncu-rep
+    -o gpurun_out/prof_r02_n3_widened env PYTHONPATH=$PWD python /tmp/wk.py > gpurun_out/ncu_r02_n3.log 2>&1
+tail -2 gpurun_out/ncu_r02_n3.log
+ls -la gpurun_out/prof_r02_n3_widened.ncu-rep
