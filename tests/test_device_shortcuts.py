@@ -80,8 +80,10 @@ def test_restated_glibc_float_functions_are_bit_identical_to_libm(tmp_path):
 
 
 def test_lean_double_exp_log_match_libm(tmp_path):
-    """dj_brdf_b200/csrc/djb_dmath.cuh (constant-bank exp / log of the analytic BRDF kernels) compiled for the host against libm:
-    <= 4 ulp of double over 2e7 arguments per function (measured 1.0), identical special cases."""
+    """dj_brdf_b200/csrc/djb_dmath.cuh (the double exp / log / pow / sqrt / acos / atan / atan2 / sincos of the analytic and table BRDF
+    kernels) compiled for the host against libm: ulp bounds over 2e7 arguments per function, identical special cases, and the nine
+    one-float coordinate maps against the reference's expressions over every 16th float of their domains (`dmath_check full` checks
+    every float: profiles/r02_n_dmath_exhaustive.txt)."""
     import subprocess
     from pathlib import Path
     root = Path(__file__).resolve().parents[1]
@@ -91,3 +93,17 @@ def test_lean_double_exp_log_match_libm(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_dmath_tables_match_their_generator():
+    """dj_brdf_b200/csrc/djb_dmath_tables.inc is exactly what tools/gen_dmath_tables.py prints (mpmath at 60 digits, each value rounded
+    once to double and written as a hex float): the tables of the double exp / log / atan and the asin coefficients are reproducible."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    pytest = __import__("pytest")
+    pytest.importorskip("mpmath")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "tools/gen_dmath_tables.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == (root / "dj_brdf_b200/csrc/djb_dmath_tables.inc").read_text()
