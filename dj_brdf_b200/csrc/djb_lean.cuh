@@ -588,7 +588,15 @@ struct PairX {
 	float kh;           // o . h (pdf: the visible-normal density's numerator)
 	bool facing;        // h.z > 1e-4: the NDF is non-zero (dj_brdf.h:1561)
 	bool den_ok;        // den, c4 and their reciprocals are normal numbers: the lean divisions are exact
+	bool both_up;       // pdf, 1e-5 tier: i.z > 0, o.z > 0, i.z o.z > 1e-30, |i|, |o| <= 2 (see fast_pdf_try)
 };
+// A centred lobe of bounded roughness (params::isotropic / elliptic: n = (0, 0, 1), no slope offset): both G1 lie in (0, 1], so
+// the shadowing term is positive exactly when both are (fast_pdf_try)
+DJB_DEV bool params_centred(const Params &p)
+{
+	return p.tx == 0.0f && p.ty == 0.0f && p.nx == 0.0f && p.ny == 0.0f && p.nz == 1.0f && p.ax > 0.0f && p.ax <= 1e3f && p.ay > 0.0f &&
+	       p.ay <= 1e3f && fabsf(p.rho) < 1.0f;
+}
 
 template <int OP>
 DJB_DEV PairX make_pair(V3 i, V3 o)
@@ -610,6 +618,7 @@ DJB_DEV PairX make_pair(V3 i, V3 o)
 	c.cd = sat_ref(c.kh);
 	const float lo = 1e-28f, hi = 1e30f;
 	c.den_ok = fabsf(c.den) > lo && fabsf(c.den) < hi && c.c4 > lo;
+	c.both_up = OP == OP_PDF && i.z > 0.0f && o.z > 0.0f && i.z * o.z > 1e-30f && dot(i, i) <= 4.0f && dot(o, o) <= 4.0f;
 	return c;
 }
 
@@ -902,11 +911,21 @@ DJB_DEV V3 fast_evalp_try(const ParamsX &m, const FresnelDev &f, bool shadow, co
 	}
 	return lean_zero<OP>(c);
 }
+// The pdf uses the shadowing term only as a gate (dj_brdf.h:1713-1730: `if (gaf(h, i, o) > 0)`).  `centred` (params_centred, every
+// material of the launch) with c.both_up decides it without sigma(i): G1(k) = k.z / sigma(k) with 0 < sigma(k) <= 4e3 for |k| <= 2,
+// so both G1 are positive, their product is >= i.z o.z / 1.6e7 > 6e-38 (no underflow), and with G1 <= 1 the denominator
+// G1i + G1o - G1i G1o is >= the larger of the two: the reference's G is positive, and never ill-conditioned.
 template <int NDF>
-DJB_DEV float fast_pdf_try(const ParamsX &m, bool shadow, const PairX &c, float r2, bool &ill)
+DJB_DEV float fast_pdf_try(const ParamsX &m, bool shadow, const PairX &c, float r2, bool &ill, bool centred = false)
 {
 	float rsg_o;
-	const float G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
+	float G = 1.0f;
+	if (centred && c.both_up) {
+		ill = false;
+		rsg_o = mufu_rcp(fast_sigma<NDF>(m.p, c.o));
+	} else {
+		G = fast_gaf<NDF>(m.p, shadow, c.i, c.o, rsg_o, ill);
+	}
 	if (G > 0.0f) {
 		const float v = c.kh > 0.0f ? (c.kh * fast_ndf_from_r2<NDF>(m, c, r2)) * rsg_o : 0.0f;
 		return c.den_ok ? v * c.rcp_den : __fdiv_rn(v, c.den);
@@ -922,10 +941,10 @@ DJB_DEV V3 fast_evalp_tail(const float2 *T, const ParamsX &m, const FresnelDev &
 	return r;
 }
 template <int NDF>
-DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, const PairX &c, float r2)
+DJB_DEV float fast_pdf_tail(const float2 *T, const ParamsX &m, bool shadow, const PairX &c, float r2, bool centred = false)
 {
 	bool ill;
-	const float r = fast_pdf_try<NDF>(m, shadow, c, r2, ill);
+	const float r = fast_pdf_try<NDF>(m, shadow, c, r2, ill, centred);
 	if (ill) return lean_pdf_tail<NDF>(T, m.p, shadow, c, lean_ndf_from_r2<NDF>(T, m, c, r2));
 	return r;
 }
@@ -953,12 +972,12 @@ DJB_DEV V3 fast_evalp(const float2 *T, const ParamsX &m, const FresnelDev &f, bo
 	return fast_evalp_tail<NDF, FK, OP>(T, m, f, shadow, c, r2);
 }
 template <int NDF>
-DJB_DEV float fast_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c)
+DJB_DEV float fast_pdf(const float2 *T, const ParamsX &m, bool shadow, const PairX &c, bool centred = false)
 {
 	if (!c.facing) return c.den > 0.0f ? 0.0f : lean_pdf<NDF>(T, m, shadow, c);
 	const float r2 = fast_ndf_r2<NDF>(m, c);
 	if (NDF == NDF_BECKMANN && fast_beck_exact_vote(r2)) return lean_pdf<NDF>(T, m, shadow, c);
-	return fast_pdf_tail<NDF>(T, m, shadow, c, r2);
+	return fast_pdf_tail<NDF>(T, m, shadow, c, r2, centred);
 }
 
 // =====================================================================================================================

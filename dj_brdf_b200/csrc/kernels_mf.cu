@@ -233,6 +233,10 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC, FAS
 	if (NDF == NDF_BECKMANN && uses_u) s_glf.H = glf_hot(s_glf.T); // three constants held in registers for the whole kernel
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
+	// 1e-5 tier of pdf: every material a centred lobe => the shadowing gate needs no sigma(i) (fast_pdf_try)
+	bool centred = FAST && OP == OP_PDF && !PERPAIR && shadow;
+	if (FAST && OP == OP_PDF && !PERPAIR)
+		for (int t = 0; t < A.n_params; ++t) centred = centred && params_centred(s_params[t].p);
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += stride) {
 		V3 va;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(MF_THREADS, lean_min_blocks(NDF, OP, PSRC, FAS
 		}
 		auto one = [&](const ParamsX &mx, long long slot) {
 			if (OP == OP_PDF) {
-				A.out0[slot] = FAST ? fast_pdf<NDF>(s_exp2, mx, shadow, c) : lean_pdf<NDF>(s_exp2, mx, shadow, c);
+				A.out0[slot] = FAST ? fast_pdf<NDF>(s_exp2, mx, shadow, c, centred) : lean_pdf<NDF>(s_exp2, mx, shadow, c);
 			} else if (OP == OP_SAMPLE) {
 				st3(A.out0, slot, FAST ? fast_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o) : lean_sample<NDF>(s_exp2, s_glf, mx.p, u1c, su2, o));
 			} else if (OP == OP_EVALP_IS) {
@@ -310,6 +314,9 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 	__syncthreads();
 	const FresnelDev fr = A.fr;
 	const bool shadow = A.shadow != 0;
+	bool centred = FAST && OP == OP_PDF && shadow; // 1e-5 tier of pdf over centred lobes: no sigma(i) for the gate (fast_pdf_try)
+	if (FAST && OP == OP_PDF)
+		for (int t = 0; t < A.n_params; ++t) centred = centred && params_centred(s_params[t].p);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
 	uint2 *q = s_q[warp], *qs = s_qs[warp];
@@ -326,14 +333,14 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 		c.o = mk(s.a.w, s.b.x, s.b.y);
 		c.h = mk(s.b.z, s.b.w, s.c.x);
 		c.den = s.c.y; c.rcp_den = s.c.z; c.inv_iz = s.c.w;
-		c.kh = s.d.x; c.cd = sat_ref(c.kh); c.den_ok = s.d.y != 0.0f; c.c4 = s.d.z; c.rcp_c4 = s.d.w;
+		c.kh = s.d.x; c.cd = sat_ref(c.kh); c.den_ok = s.d.y == 1.0f || s.d.y == 3.0f; c.both_up = s.d.y >= 2.0f; c.c4 = s.d.z; c.rcp_c4 = s.d.w;
 		const ParamsX &mx = s_params[m];
 		const long long slot = (long long)m * A.out_stride + kb + src;
 		const float r2 = __uint_as_float(item.y);
 		if (FAST && !(item.x & 0xC0u) && r2 <= FAST_BECK_R2_MAX) { // the 1e-5 tier; the underflow tail (the slow queue) stays exact
 			bool ill;
 			if (OP == OP_PDF) {
-				const float v = fast_pdf_try<NDF>(mx, shadow, c, r2, ill);
+				const float v = fast_pdf_try<NDF>(mx, shadow, c, r2, ill, centred);
 				if (!ill) A.out0[slot] = v;
 			} else {
 				const V3 v = fast_evalp_try<NDF, FK, OP>(mx, fr, shadow, c, r2, ill);
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(MF_THREADS, DJB200_COMPACT_MINB) mf_beck_compa
 		s.a = make_float4(c.i.x, c.i.y, c.i.z, c.o.x);
 		s.b = make_float4(c.o.y, c.o.z, c.h.x, c.h.y);
 		s.c = make_float4(c.h.z, c.den, c.rcp_den, c.inv_iz);
-		s.d = make_float4(c.kh, c.den_ok ? 1.0f : 0.0f, c.c4, c.rcp_c4);
+		s.d = make_float4(c.kh, (c.den_ok ? 1.0f : 0.0f) + (c.both_up ? 2.0f : 0.0f), c.c4, c.rcp_c4); // two flags in one slot
 		__syncwarp(); // the previous round's items have all been finished: the pair slots may be overwritten
 		pairs[lane] = s;
 		__syncwarp();

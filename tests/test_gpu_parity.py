@@ -519,6 +519,18 @@ def test_fast_tier_vs_exact_tier_at_scale(djb, ndf):
             report[q] = worst
             assert worst <= 1e-5, f"{ndf} {q}: worst relative difference {worst:.3e}"
             del fast, ref, rel
+        # pdf over centred lobes only: the launch decides the shadowing gate without sigma(i) (djb_lean.cuh, fast_pdf_try)
+        djb.set_precision("1e-5")
+        fast = b.pdf(wi, wo, mats[:15])
+        djb.set_precision("bits")
+        ref = b.pdf(wi, wo, mats[:15])
+        assert torch.equal(fast == 0, ref == 0), f"{ndf} pdf, centred lobes: zero pattern differs"
+        assert torch.equal(torch.isnan(fast), torch.isnan(ref))
+        rel = ((fast - ref).abs() / ref.abs().clamp_min(1e-30))
+        rel = torch.where(torch.isnan(rel), torch.zeros_like(rel), rel)
+        report["pdf, centred lobes"] = rel.max().item()
+        assert report["pdf, centred lobes"] <= 1e-5, (ndf, report)
+        del fast, ref, rel
         k = 2_000_000
         pp = torch.from_numpy(np.ascontiguousarray(mats[np.arange(k) % 16])).cuda()
         for q in ("eval", "pdf"):
