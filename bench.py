@@ -491,7 +491,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab,
-                         "note": "issue-bound, not HBM-bound: in the default 1e-5 tier a result costs ~120 (GGX eval / pdf) to ~315 "
+                         "note": "issue-bound, not HBM-bound: in the default 1e-5 tier a result costs ~75 (GGX pdf) to ~315 "
                                  "(Beckmann sample: the reference's Newton search of erfinv + exp, trip for trip) thread instructions, "
                                  "in the exact tier (DJB200_PRECISION=bits) ~190 to ~680; DRAM traffic equals the algorithmic bytes "
                                  "(profiles/dram_traffic.json, profiles/r02_h_microfacet.md)"},

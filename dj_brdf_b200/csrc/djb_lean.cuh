@@ -806,7 +806,8 @@ DJB_DEV V3 lean_evalp_is(const float2 *T, const GlfCtx &GT, const ParamsX &m, co
 // it stays within 1e-5 (finding 3):
 //   * every gate that decides the zero pattern: h.z > 1e-4, dot(k, n) > 0, G > 0, D == 0 -- formed from the same floats by the
 //     same operations as in the exact tier (h, its slopes and the per-pair denominators are the exact tier's: they are computed
-//     once per pair, not per material);
+//     once per pair, not per material).  One exception, decided by argument instead of evaluation: the `G > 0` gate of pdf over
+//     centred lobes (fast_pdf_try);
 //   * the squared standard-space slope radius r2 that enters exp(-r2): a relative error e in r2 is an error r2 e in the
 //     exponential (r2 goes up to 100), so r2 is lean_ndf_r2, bit-identical to the reference's;
 //   * Beckmann results in the gradual-underflow tail (r2 > 78): handed to the exact tier;
