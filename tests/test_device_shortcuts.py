@@ -107,3 +107,49 @@ def test_dmath_tables_match_their_generator():
     r = subprocess.run([sys.executable, str(root / "tools/gen_dmath_tables.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert r.stdout == (root / "dj_brdf_b200/csrc/djb_dmath_tables.inc").read_text()
+
+
+# ---- float forms of "double operation rounded to float" in the table / analytic kernels (csrc/djb_device.cuh, round 2) ------------
+def test_utia_cell_index_as_float_product_plus_remainder():
+    """floor_div (djb_device.cuh): (int)floor((double)x / d) for the floats x of utia::eval's ranges -- theta in [0, 90) over
+    d = 15, phi in [0, 360) over d = 7.5 (dj_brdf.h:1090-1100) -- equals the float product with 1 / d, floored, corrected by the
+    float remainder x - q d (one fused operation)."""
+    for d, hi in ((15.0, 90.0), (7.5, 360.0)):
+        # every 37th float of the range, and every float within 4096 ulps of a multiple of d (where a quotient can land on the
+        # wrong side); the full range was run once with stride 1: no difference
+        x = floats_between(0.0, hi)[::37]
+        near = []
+        for m in np.arange(d, hi + d / 2, d, dtype=np.float64):
+            c = np.array([m], np.float32).view(np.uint32)[0]
+            near.append(np.arange(c - 4096, c + 4097, dtype=np.uint32).view(np.float32))
+        x = np.concatenate([x] + near)
+        x = x[x < np.float32(hi)]
+        want = np.floor(x.astype(np.float64) / d).astype(np.int32)
+        inv = np.float32(1.0) / np.float32(d)
+        q = np.floor(x * inv).astype(np.int32)                       # floorf(x * inv_d), float product
+        r = (x.astype(np.float64) - d * q.astype(np.float64)).astype(np.float32)  # fmaf(-d, q, x): exact product, one rounding
+        q = np.where(r < 0, q - 1, np.where(r >= np.float32(d), q + 1, q))
+        assert np.array_equal(q, want), (d, int((q != want).sum()))
+        # the correction is needed: the plain float product alone is wrong somewhere in the range
+        assert (np.floor(x * inv).astype(np.int32) != want).any()
+
+
+def test_utia_float_forms_of_double_expressions():
+    """utia_eval1: (float)(15.0 * k) == 15.0f * (float)k for the cell indices; (double)acc > 0.0375 <=> acc >= 0.0375f for every
+    float; (float)((double)x +- 360.0) == x +- 360.0f."""
+    k = np.arange(0, 50)
+    for d in (15.0, 7.5):
+        assert np.array_equal((d * k).astype(np.float32), np.float32(d) * k.astype(np.float32))
+    a = floats_between(0.03, 0.045)
+    assert np.array_equal(a.astype(np.float64) > 0.0375, a >= np.float32(0.0375))
+    x = np.concatenate([floats_between(1e-3, 400.0)[::7], -floats_between(1e-3, 400.0)[::7]])
+    for s in (360.0, -360.0):
+        assert np.array_equal((x.astype(np.float64) + s).astype(np.float32), x + np.float32(s))
+
+
+def test_sqrt_half_and_float_square_roots():
+    """sqrt_half (params construction): (float)sqrt(0.5 * (double)x) == sqrtf(0.5f * x) for floats of magnitude >= 1e-30;
+    (float)sqrt((double)x) == sqrtf(x) (the double rounding of a square root is innocuous) -- strided over all positive floats."""
+    x = floats_between(1e-30, 3e38)[::257]
+    assert np.array_equal(np.sqrt(0.5 * x.astype(np.float64)).astype(np.float32), np.sqrt(np.float32(0.5) * x))
+    assert np.array_equal(np.sqrt(x.astype(np.float64)).astype(np.float32), np.sqrt(x))
