@@ -153,3 +153,44 @@ def test_sqrt_half_and_float_square_roots():
     x = floats_between(1e-30, 3e38)[::257]
     assert np.array_equal(np.sqrt(0.5 * x.astype(np.float64)).astype(np.float32), np.sqrt(np.float32(0.5) * x))
     assert np.array_equal(np.sqrt(x.astype(np.float64)).astype(np.float32), np.sqrt(x))
+
+
+@pytest.mark.parametrize("ndf", [api.NDF_GGX, api.NDF_BECKMANN], ids=["ggx", "beckmann"])
+def test_shadowing_gate_of_centred_lobes_is_open_whenever_both_directions_are_up(port, ndf):
+    """fast_pdf_try (djb_lean.cuh): for centred lobes (params::elliptic, alpha <= 1e3) and pairs with i.z > 0, o.z > 0,
+    i.z o.z > 1e-30, |i|, |o| <= 2 the pdf kernels take `gaf(h, i, o) > 0` for granted instead of evaluating sigma(i).  Here the
+    reference's own gaf (the port, bit-identical to it) over directions from normal to extreme grazing incidence (z down to 1e-14),
+    unit and non-unit lengths, roughness from 1e-4 to 1e3, isotropic to 1 : 1e4 anisotropy: positive, finite, every time."""
+    rng = np.random.default_rng(2024)
+    n = 200_000
+
+    def dirs():
+        z = np.where(rng.random(n) < 0.5, rng.random(n), 10.0 ** rng.uniform(-14.0, 0.0, n))
+        phi = rng.uniform(0, 2 * np.pi, n)
+        r = np.sqrt(np.maximum(1.0 - z * z, 0.0))
+        d = np.stack([r * np.cos(phi), r * np.sin(phi), z], 1)
+        return (d * rng.uniform(0.5, 1.99, (n, 1))).astype(np.float32)  # |d| <= 2, not necessarily 1
+
+    def params_centred(P):  # djb_lean.cuh; P = n.xyz a1 a2 phi_a ax ay rho srho tx ty
+        return (P[10] == 0 and P[11] == 0 and P[0] == 0 and P[1] == 0 and P[2] == 1 and 0 < P[6] <= 1e3 and 0 < P[7] <= 1e3
+                and abs(P[8]) < 1)
+
+    worst, excluded = np.inf, 0
+    for a1, a2, ph in [(0.1, 0.1, 0.0), (1e-4, 1e-4, 0.0), (1e-4, 1.0, 0.7), (1e3, 1e3, 0.0), (1e3, 0.1, 2.0), (0.02, 0.8, 1.1),
+                       (5.0, 5e-4, 3.0), (900.0, 0.3, 0.4), (0.5, 0.05, 2.5)]:
+        P = port.params_elliptic(a1, a2, ph)
+        wi, wo = dirs(), dirs()
+        up = (wi[:, 2] > 0) & (wo[:, 2] > 0) & (wi[:, 2] * wo[:, 2] > np.float32(1e-30))
+        assert up.mean() > 0.99
+        h = wi + wo
+        h /= np.linalg.norm(h, axis=1, keepdims=True)
+        G = port.component("gaf", ndf, P, h.astype(np.float32), wi, wo, shadow=True)
+        if not params_centred(P):
+            # e.g. (1e3, 0.1, 2.0): params::elliptic rounds rho to 1.0000001, sqrt(1 - rho^2) is NaN and the reference's G is 0 for every
+            # pair -- such a material switches the shortcut off for its launch, and the kernels evaluate G as the reference does
+            excluded += 1
+            continue
+        assert np.isfinite(G[up]).all() and (G[up] > 0).all(), (a1, a2, ph, int((~(G[up] > 0)).sum()))
+        worst = min(worst, float(G[up].min()))
+    assert excluded == 3  # rho rounds to 1 for (1e-4, 1, 0.7) and (5, 5e-4, 3), above 1 for (1e3, 0.1, 2): six materials were checked
+    assert worst > 1e-36  # far from the underflow threshold
